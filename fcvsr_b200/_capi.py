@@ -1,0 +1,79 @@
+"""ctypes binding of the C ABI declared in include/fcvsr_b200.h (libfcvsr_b200.so).
+
+There is deliberately no fallback: if the library is missing or a call returns a non-zero status a
+RuntimeError is raised.  Pointers are passed as integers (``tensor.data_ptr()``), the stream as
+``torch.cuda.current_stream().cuda_stream``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libfcvsr_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_PRELU = 0, 1, 2, 3
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
+
+_T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_longlong, "s": ctypes.c_void_p}
+
+# name -> argument codes, in the order of include/fcvsr_b200.h
+SIGNATURES = {
+    "fcvsr_conv2d_direct": "pii pp pi pi pi iiiiiii if p i s",
+    "fcvsr_conv2d_tc": "pi pp pi pi pi iiiiii if p i s",
+    "fcvsr_fft_r2c_w": "pi p p iiii s",
+    "fcvsr_fft_c2c_h": "p p p p iiii i f s",
+    "fcvsr_fft_c2r_w": "p pi p iiii f s",
+    "fcvsr_corr_gather": "piii pi iiii s",
+    "fcvsr_offset_blocks": "ppppp pi pppp iiii s",
+    "fcvsr_iac_step": "pi pi pi pi pi pi pi ii pi iii s",
+    "fcvsr_chansum64": "pi p ii s",
+    "fcvsr_reduce_finalize": "p ii f i pp p i s",
+    "fcvsr_divenh_step": "ppppp i ii pppp ppp ii s",
+    "fcvsr_mffr_final": "pp pi pi ii s",
+    "fcvsr_context_block": "pi ppp pp ii s",
+    "fcvsr_rcb_finish": "ppp p ii s",
+    "fcvsr_level_mix": "pi pi p f pp iii s",
+    "fcvsr_pixel_shuffle": "pi pi iiii s",
+    "fcvsr_bilinear_up4": "p l p iii s",
+    "fcvsr_fill_channels": "p iii f l s",
+    "fcvsr_modulated_deform_conv_forward": "ppppp p iiii i ii ii ii ii ii s",
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"fcvsr_b200: {LIB_PATH} is missing -- build it with `python -m fcvsr_b200.build` "
+                "(there is no CPU / PyTorch fallback)")
+        import torch  # noqa: F401  (loads libcudart before our library resolves it)
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, sig in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [_T[c] for c in sig.replace(" ", "")]
+        _lib.fcvsr_version.restype = ctypes.c_char_p
+        _lib.fcvsr_version.argtypes = []
+    return _lib
+
+
+_ERR = {ERR_ARG: "invalid argument", ERR_CUDA: "CUDA error", ERR_UNSUPPORTED: "unsupported shape"}
+
+
+def call(name: str, *args) -> None:
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed: {_ERR.get(rc, rc)}")
+
+
+def try_call(name: str, *args) -> int:
+    """Returns the status; used where ERR_UNSUPPORTED selects another kernel."""
+    return getattr(lib(), name)(*args)
+
+
+def version() -> str:
+    return lib().fcvsr_version().decode()

@@ -1,0 +1,61 @@
+"""Host-side constants of the frequency kernels: band masks and FFT twiddles.
+
+Band masks restate Split_freq.generate_freq_mask / forward (CVSR_train/arch/CVSR_freq.py:2016-2051,
+:2078): Q gaussian difference masks on a 1024x1024 grid, resized to (H, W) with torchvision's bicubic
+``Resize`` (the reference calls it with torchvision defaults, so the antialias behaviour is whatever
+the installed torchvision does -- the same call is made here on purpose).  The device kernels apply
+them to the half spectrum, which needs the Hermitian-symmetrised mask
+    Msym(k) = (M(k) + M(-k)) / 2,   M = ifftshift(resized mask)
+because Re ifft2(F * M) == irfft2(rfft2(x) * Msym) for real x.
+Computed once per (Q, H, W) and cached on the device.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+_MASK1024: Dict[int, torch.Tensor] = {}
+_MASKS: Dict[Tuple[int, int, int, str], torch.Tensor] = {}
+_TW: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def _gaussian_masks_1024(q: int) -> torch.Tensor:
+    if q not in _MASK1024:
+        n = 1024
+        step = math.sqrt(2.0 * (n / 2) ** 2) / q
+        ax = (np.arange(n) - n // 2).astype(np.float64) ** 2
+        r2 = ax[:, None] + ax[None, :]
+        out, acc = [], None
+        for i in range(q):
+            g = torch.from_numpy(np.exp(-np.power(np.sqrt(r2), 2) / (2.0 * (step * (i + 1)) ** 2))).float()
+            for prev in out:
+                g = g - prev
+            out.append(g)
+        _MASK1024[q] = torch.stack(out, 0)
+    return _MASK1024[q]
+
+
+def symmetric_half_masks(q: int, h: int, w: int, device) -> torch.Tensor:
+    """[Q, H, W/2+1] float32 on `device`."""
+    key = (q, h, w, str(device))
+    if key not in _MASKS:
+        from torchvision.transforms import Resize, functional as TF
+        m = Resize([h, w], interpolation=TF.InterpolationMode.BICUBIC)(_gaussian_masks_1024(q))
+        m = torch.fft.ifftshift(m, dim=(1, 2))
+        neg = torch.roll(torch.flip(m, dims=(1, 2)), shifts=(1, 1), dims=(1, 2))   # M(-k)
+        msym = 0.5 * (m + neg)
+        _MASKS[key] = msym[:, :, : w // 2 + 1].contiguous().to(device)
+    return _MASKS[key]
+
+
+def twiddles(n: int, device) -> torch.Tensor:
+    """float2[n] = exp(-2 pi i k / n), computed in float64."""
+    key = (n, str(device))
+    if key not in _TW:
+        k = np.arange(n, dtype=np.float64)
+        tw = np.stack([np.cos(2 * np.pi * k / n), -np.sin(2 * np.pi * k / n)], axis=1).astype(np.float32)
+        _TW[key] = torch.from_numpy(tw).contiguous().to(device)
+    return _TW[key]

@@ -1,0 +1,41 @@
+// Shared helpers for the fcvsr_b200 sm_100a kernels.
+// Layout convention of the whole library: activations are NHWC fp32 ("pixel-major"): element
+// (b, y, x, c) of a tensor with pixel stride `ld` (in elements, ld >= C) lives at
+// base[((b*H + y)*W + x)*ld + c].  A channel slice of a wider tensor is just base+offset with the
+// same ld, so torch.cat / channel splits of the reference never move data.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FCVSR_OK 0
+#define FCVSR_ERR_ARG (-1)
+#define FCVSR_ERR_CUDA (-2)
+#define FCVSR_ERR_UNSUPPORTED (-3)
+
+// activation codes shared by the conv epilogues (host mirror: fcvsr_b200/_capi.py)
+#define FCVSR_ACT_NONE 0
+#define FCVSR_ACT_RELU 1
+#define FCVSR_ACT_LEAKY 2   // negative slope passed by value
+#define FCVSR_ACT_PRELU 3   // negative slope read from a device scalar (nn.PReLU weight)
+
+static inline int fcvsr_launch_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? FCVSR_OK : FCVSR_ERR_CUDA;
+}
+
+__device__ __forceinline__ float fcvsr_act(float v, int act, float slope) {
+    if (act == FCVSR_ACT_NONE) return v;
+    if (act == FCVSR_ACT_RELU) return fmaxf(v, 0.f);
+    return v >= 0.f ? v : v * slope;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}

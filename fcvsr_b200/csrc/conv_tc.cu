@@ -1,0 +1,428 @@
+// tcgen05 / TMEM implicit-GEMM convolution fed by TMA  (sm_100a only).
+//
+// Computes, for NHWC fp32 tensors, y = act(conv_kxk(x, w) + bias) + res - res2 (k in {1,3}, stride 1,
+// zero padding k/2) as a GEMM  D[pixels, Cout] = sum_{tap, cin} A_tap[pixels, cin] * W[Cout, tap, cin]
+// on the 5th-generation tensor cores with TF32 operands and fp32 accumulation in tensor memory.
+// It replaces every 3x3 / 1x1 nn.Conv2d of the reference hot path whose shape fits
+// (CVSR_freq.py:1371-1430 MGAAbk, :705-822 SCNetbk, :2739-2749 tail); the library-call equivalent in
+// the reference is cuDNN (conv2d) -- there is no such kernel in the reference to port.
+//
+// Design (one persistent CTA per SM, 7 warps, warp-specialised):
+//   * M tile = 8 x 16 output pixels (128 = UMMA M), N tile = Cout (<= 128 per pass), K walked as
+//     (32-channel chunk) x (filter tap); one tcgen05.mma covers K = 8 (32 bytes of TF32).
+//   * A operand, halo re-use: for each 32-channel chunk the producer warp TMA-loads THREE copies of the
+//     (8+2) x 16-pixel input window, shifted by -1/0/+1 pixel in x (TMA zero-fills out-of-image
+//     pixels = the conv padding).  Each copy is a [160 rows][128 B] SWIZZLE_128B K-major tile, so the
+//     operand of filter tap (ky,kx) is simply copy[kx] viewed from row ky*16 on: a 2048-byte (1024-
+//     aligned) shift of the matrix descriptor.  Nine taps read 3 loads instead of 9: L2->SMEM traffic
+//     per pixel drops from 9x to 3.75x the input bytes, which is what lets a Cout=64 conv stay
+//     tensor-bound instead of L2-bound.
+//   * B operand (weights, [Cout][tap*Cin] K-major in HBM/L2) streams through its own 4-stage ring,
+//     one (tap, chunk) slice of [Cout][32] per stage.
+//   * Accumulators: 2 x N columns of TMEM, double-buffered so the epilogue of tile t overlaps the MMAs
+//     of tile t+1.  Epilogue warps read TMEM with tcgen05.ld (lane == pixel), apply bias / activation /
+//     residuals in registers and store 64-byte runs per thread (optionally through pixel_shuffle(2)).
+//
+// Roofline: tensor (TF32: K=8 per instruction, half the bf16 rate).  Algorithmic FLOPs per output pixel
+// = 2 * Cin * Cout * k * k; algorithmic HBM bytes per pixel = 4 * (Cin + Cout) (+4*Cout per residual).
+#include "common.cuh"
+#include <cuda.h>
+
+#define TC_TH 8
+#define TC_TW 16
+#define TC_KCH 32                      // channels per K chunk (128 bytes of fp32)
+#define TC_NA 2                        // A ring stages
+#define TC_NB 4                        // B ring stages
+#define TC_ROW_BYTES 128
+#define TC_A_COPY_BYTES ((TC_TH + 2) * TC_TW * TC_ROW_BYTES)      // 20480
+#define TC_A_STAGE_BYTES (3 * TC_A_COPY_BYTES)                    // 61440
+#define TC_B_STAGE_BYTES (128 * TC_ROW_BYTES)                     // 16384 (N <= 128)
+#define TC_THREADS 224
+#define TC_SPIN_LIMIT (1u << 26)
+
+struct ConvTcParams {
+    const float* bias; const float* res; int ldres; const float* res2; int ldres2;
+    float* y; int ldy;
+    int B, H, W, Cin, Cout, ks;          // Cout = padded (multiple of 16) GEMM N
+    int cout_valid;                      // channels actually stored (== Cout, or < 16 for thin heads)
+    int n_tile, n_tiles;               // N per pass, number of passes
+    int tiles_x, tiles_y, total_tiles;
+    int act; float slope; const float* slope_ptr; int ps;
+    int* err;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > TC_SPIN_LIMIT) {
+            if (err) atomicExch(err, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct TileCoord { int nt, tx, ty, b; };
+__device__ __forceinline__ TileCoord decode_tile(int t, const ConvTcParams& p) {
+    TileCoord c;
+    c.nt = t % p.n_tiles; t /= p.n_tiles;
+    c.tx = t % p.tiles_x; t /= p.tiles_x;
+    c.ty = t % p.tiles_y; c.b = t / p.tiles_y;
+    return c;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* a_buf = smem;                                        // TC_NA x 61440
+    uint8_t* b_buf = smem + TC_NA * TC_A_STAGE_BYTES;             // TC_NB x 16384
+    uint64_t* bars = (uint64_t*)(b_buf + TC_NB * TC_B_STAGE_BYTES);
+    uint64_t* full_a = bars;            // [TC_NA]
+    uint64_t* empty_a = bars + TC_NA;   // [TC_NA]
+    uint64_t* full_b = bars + 2 * TC_NA;            // [TC_NB]
+    uint64_t* empty_b = bars + 2 * TC_NA + TC_NB;   // [TC_NB]
+    uint64_t* tm_full = bars + 2 * TC_NA + 2 * TC_NB;   // [2]
+    uint64_t* tm_empty = tm_full + 2;                    // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tm_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int taps = p.ks * p.ks;
+    const int ncopies = p.ks == 3 ? 3 : 1;
+    const int nrows = p.ks == 3 ? TC_TH + 2 : TC_TH;
+    const int kchunks = p.Cin / TC_KCH;
+    const uint32_t a_copy_bytes = (uint32_t)nrows * TC_TW * TC_ROW_BYTES;
+    const uint32_t b_bytes = (uint32_t)p.n_tile * TC_ROW_BYTES;
+    const uint32_t tmem_cols = p.n_tile <= 16 ? 32 : (p.n_tile <= 32 ? 64 : (p.n_tile <= 64 ? 128 : 256));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < TC_NB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== A producer: haloed input windows, 3 x-shifted copies per 32-channel chunk =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, p);
+                const int y0 = tc.ty * TC_TH - (p.ks == 3 ? 1 : 0), x0 = tc.tx * TC_TW - (p.ks == 3 ? 1 : 0);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&empty_a[stage], phase ^ 1, p.err, 1);
+                    mbar_expect_tx(&full_a[stage], a_copy_bytes * ncopies);
+                    uint8_t* dst = a_buf + stage * TC_A_STAGE_BYTES;
+                    for (int cpy = 0; cpy < ncopies; ++cpy)
+                        tma_load_4d(dst + cpy * TC_A_COPY_BYTES, &map_x, &full_a[stage], kc * TC_KCH, x0 + cpy, y0, tc.b);
+                    if (++stage == TC_NA) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== B producer: one [n_tile][32] weight slice per (chunk, tap) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, p);
+                for (int kc = 0; kc < kchunks; ++kc)
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&empty_b[stage], phase ^ 1, p.err, 2);
+                        mbar_expect_tx(&full_b[stage], b_bytes);
+                        tma_load_2d(b_buf + stage * TC_B_STAGE_BYTES, &map_w, &full_b[stage], tap * p.Cin + kc * TC_KCH,
+                                    tc.nt * p.n_tile);
+                        if (++stage == TC_NB) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int acc = 0; uint32_t pacc = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                mbar_wait(&tm_empty[acc], pacc ^ 1, p.err, 3);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+                uint32_t first = 1;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&full_a[sa], pa, p.err, 4);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(a_buf + sa * TC_A_STAGE_BYTES);
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&full_b[sb], pb, p.err, 5);
+                        tc_fence_after();
+                        const int ky = tap / p.ks, kx = tap - ky * p.ks;
+                        const uint32_t a_addr = a_base + (uint32_t)kx * TC_A_COPY_BYTES + (uint32_t)ky * (TC_TW * TC_ROW_BYTES);
+                        const uint32_t b_addr = smem_u32(b_buf + sb * TC_B_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_tf32(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                        umma_commit(&empty_b[sb]);
+                        if (++sb == TC_NB) { sb = 0; pb ^= 1; }
+                    }
+                    umma_commit(&empty_a[sa]);
+                    if (++sa == TC_NA) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&tm_full[acc]);
+                if (++acc == 2) { acc = 0; pacc ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 3..6: TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;                   // pixel within the tile == TMEM lane
+        const int ly = m / TC_TW, lx = m - ly * TC_TW;
+        const float slope = p.act == FCVSR_ACT_PRELU ? p.slope_ptr[0] : p.slope;
+        const int c4 = p.Cout >> 2;
+        int acc = 0; uint32_t pacc = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(t, p);
+            const int y = tc.ty * TC_TH + ly, x = tc.tx * TC_TW + lx;
+            const bool valid = y < p.H && x < p.W;
+            const size_t pix = ((size_t)tc.b * p.H + y) * p.W + x;
+            mbar_wait(&tm_full[acc], pacc, p.err, 6);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile);
+            for (int cb = 0; cb < p.n_tile; cb += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + cb, r);
+                tmem_ld_wait();
+                if (valid && p.cout_valid < p.Cout) {
+                    // thin head (Cout in {1,4}): scalar stores of the first cout_valid columns
+                    const int n0 = tc.nt * p.n_tile + cb;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + j;
+                        if (n < p.cout_valid) {
+                            float f = __uint_as_float(r[j]);
+                            if (p.bias) f += __ldg(p.bias + n);
+                            f = fcvsr_act(f, p.act, slope);
+                            if (p.res) f += p.res[pix * p.ldres + n];
+                            if (p.res2) f -= p.res2[pix * p.ldres2 + n];
+                            p.y[pix * p.ldy + n] = f;
+                        }
+                    }
+                } else if (valid) {
+                    const int n0 = tc.nt * p.n_tile + cb;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float f = __uint_as_float(r[j]);
+                        if (p.bias) f += __ldg(p.bias + n0 + j);
+                        v[j] = fcvsr_act(f, p.act, slope);
+                    }
+                    if (p.res) {
+                        const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.ldres + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 rv = rp[j];
+                            v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+                        }
+                    }
+                    if (p.res2) {
+                        const float4* rp = reinterpret_cast<const float4*>(p.res2 + pix * p.ldres2 + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 rv = rp[j];
+                            v[4 * j] -= rv.x; v[4 * j + 1] -= rv.y; v[4 * j + 2] -= rv.z; v[4 * j + 3] -= rv.w;
+                        }
+                    }
+                    float* dst;
+                    if (p.ps) {
+                        const int ij = n0 / c4, c = n0 - ij * c4;
+                        const size_t opix = ((size_t)tc.b * 2 * p.H + 2 * y + (ij >> 1)) * (2 * (size_t)p.W) + 2 * x + (ij & 1);
+                        dst = p.y + opix * p.ldy + c;
+                    } else {
+                        dst = p.y + pix * p.ldy + n0;
+                    }
+                    float4* dp = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tm_empty[acc]);
+            if (++acc == 2) { acc = 0; pacc ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+static int* tc_err_flag() {
+    static int* flag = nullptr;
+    if (!flag) {
+        if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(flag, 0, sizeof(int));
+    }
+    return flag;
+}
+
+extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
+                               const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
+                               int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
+                               cudaStream_t st) {
+    if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
+    if ((ksize != 1 && ksize != 3) || Cin % TC_KCH || Cin <= 0 || Cout <= 0) return FCVSR_ERR_UNSUPPORTED;
+    const int cout_valid = Cout;
+    const bool thin = Cout < 16;            // thin heads: w is zero-padded to 16 rows by the packer
+    if (thin) Cout = 16;
+    if (Cout % 16) return FCVSR_ERR_UNSUPPORTED;
+    if (ldx & 3) return FCVSR_ERR_UNSUPPORTED;
+    if (!thin && ((ldy & 3) || (res && (ldres & 3)) || (res2 && (ldres2 & 3)))) return FCVSR_ERR_UNSUPPORTED;
+    if (((uintptr_t)x | (uintptr_t)w) & 15) return FCVSR_ERR_UNSUPPORTED;
+    if (!thin && (((uintptr_t)y | (uintptr_t)res | (uintptr_t)res2) & 15)) return FCVSR_ERR_UNSUPPORTED;
+    if (thin && pixel_shuffle) return FCVSR_ERR_UNSUPPORTED;
+    if (act == FCVSR_ACT_PRELU && !slope_ptr) return FCVSR_ERR_ARG;
+    int n_tile = Cout, n_tiles = 1;
+    if (Cout > 128) {       // largest N tile <= 128 that is a multiple of 16 and divides Cout
+        n_tile = 0;
+        for (int cand = 128; cand >= 16; cand -= 16)
+            if (Cout % cand == 0) { n_tile = cand; break; }
+        if (!n_tile) return FCVSR_ERR_UNSUPPORTED;
+        n_tiles = Cout / n_tile;
+    }
+    if (pixel_shuffle && ((Cout & 3) || ((Cout >> 2) % 16))) return FCVSR_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return FCVSR_ERR_CUDA;
+
+    CUtensorMap map_x, map_w;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
+        cuuint32_t box[4] = {TC_KCH, TC_TW, (cuuint32_t)(ksize == 3 ? TC_TH + 2 : TC_TH), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FCVSR_ERR_CUDA;
+    }
+    {
+        const int ktot = ksize * ksize * Cin;
+        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)Cout};
+        cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
+        cuuint32_t box[2] = {TC_KCH, (cuuint32_t)n_tile};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FCVSR_ERR_CUDA;
+    }
+    ConvTcParams p;
+    p.bias = bias; p.res = res; p.ldres = ldres; p.res2 = res2; p.ldres2 = ldres2; p.y = y; p.ldy = ldy;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ksize; p.cout_valid = cout_valid;
+    p.n_tile = n_tile; p.n_tiles = n_tiles;
+    p.tiles_x = (W + TC_TW - 1) / TC_TW; p.tiles_y = (H + TC_TH - 1) / TC_TH;
+    p.total_tiles = p.tiles_x * p.tiles_y * B * n_tiles;
+    p.act = act; p.slope = slope; p.slope_ptr = slope_ptr; p.ps = pixel_shuffle;
+    p.err = tc_err_flag();
+
+    static int num_sms = 0;
+    static bool attr_set = false;
+    const size_t smem = 1024 + TC_NA * TC_A_STAGE_BYTES + TC_NB * TC_B_STAGE_BYTES + 256;
+    if (!attr_set) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return FCVSR_ERR_CUDA;
+        attr_set = true;
+    }
+    const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+    return fcvsr_launch_status();
+}

@@ -1,0 +1,283 @@
+// Batched mixed-radix FFT kernels for NHWC tensors (shared-memory Stockham autosort).
+//
+// Replaces the torch.fft calls of the reference hot path:
+//   torch.fft.rfft2(x, norm='backward')        CVSR_freq.py:1452-1454   (MGAAbk)
+//   torch.fft.irfft2(z, s=(H,W))               CVSR_freq.py:1499,1504   (offset maps)
+//   fft.fftn / fftshift / *mask / ifftn(.real) CVSR_freq.py:2082-2088   (Split_freq)
+//
+// A 2-D transform is two passes of 1-D "line" kernels.  Because channels are the contiguous
+// dimension (NHWC), a block transforms CB channels of one line at once: every global access is a
+// CB*8-byte contiguous segment and every shared-memory access is conflict-free, for the W pass
+// and the H pass alike.  Real transforms pack two real channels into one complex FFT
+// (z = a + i b), which halves the work and makes the real tensor's (c, c+1) float2 the complex
+// sample directly.
+//
+// Sizes: any N = 2^a 3^b 5^c 7^d 11^e 13^f 17^g (covers 64, 180, 320, 272 = 16*17, 480, 540, 960).
+// HBM-bound by design: each pass reads and writes its tensor exactly once.
+#include "common.cuh"
+
+#define FFT_MAX_PASSES 16
+#define FFT_THREADS 256
+
+struct FftPlan {
+    int n;
+    int npass;
+    int radix[FFT_MAX_PASSES];
+};
+
+static bool make_plan(int n, FftPlan* p) {
+    static const int cand[] = {4, 2, 3, 5, 7, 11, 13, 17};
+    p->n = n;
+    p->npass = 0;
+    int rem = n;
+    for (int r : cand) {
+        while (rem % r == 0) {
+            if (p->npass >= FFT_MAX_PASSES) return false;
+            p->radix[p->npass++] = r;
+            rem /= r;
+        }
+    }
+    return rem == 1 && n >= 2;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// One Stockham pass of radix R over a line of length n held as [n][cb] float2 in shared memory.
+//   a_k = in[q + s*(p + m*k)],  out[q + s*(R*p + j)] = w_n'^(p*j) * sum_k a_k w_R^(jk)
+// with n' = n/s the current sub-transform length, m = n'/R, twiddles taken from the length-n table
+// (tw[t] = exp(-+2 pi i t / n), already conjugated for the inverse).
+template <int R>
+__device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* __restrict__ out, int n, int cb_log2,
+                                         int s, const float2* __restrict__ tw, bool inverse) {
+    const int nb = n / R;
+    const int m = nb / s;
+    const int cb = 1 << cb_log2;
+    float2 wr[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) wr[t] = tw[t * nb];
+    for (int idx = threadIdx.x; idx < (nb << cb_log2); idx += blockDim.x) {
+        const int bf = idx >> cb_log2, ch = idx & (cb - 1);
+        const int p = bf / s, q = bf - p * s;
+        float2 v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = in[((q + s * (p + m * k)) << cb_log2) + ch];
+        float2 o[R];
+        if (R == 2) {
+            o[0] = cadd(v[0], v[1]);
+            o[1] = csub(v[0], v[1]);
+        } else if (R == 4) {
+            float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+            float2 t2 = cadd(v[1], v[3]), t3 = csub(v[1], v[3]);
+            // multiply t3 by -i (forward) or +i (inverse)
+            float2 t3r = inverse ? make_float2(-t3.y, t3.x) : make_float2(t3.y, -t3.x);
+            o[0] = cadd(t0, t2);
+            o[2] = csub(t0, t2);
+            o[1] = cadd(t1, t3r);
+            o[3] = csub(t1, t3r);
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                float2 acc = v[0];
+#pragma unroll
+                for (int k = 1; k < R; ++k) acc = cadd(acc, cmul(v[k], wr[(j * k) % R]));
+                o[j] = acc;
+            }
+        }
+        const int obase = q + s * R * p;
+        out[(obase << cb_log2) + ch] = o[0];
+#pragma unroll
+        for (int j = 1; j < R; ++j) out[((obase + s * j) << cb_log2) + ch] = cmul(o[j], tw[p * j * s]);
+    }
+}
+
+// Runs all passes; returns the buffer that holds the result.
+__device__ float2* fft_line(float2* a, float2* b, const FftPlan& plan, int cb_log2, const float2* tw, bool inverse) {
+    int s = 1;
+    for (int i = 0; i < plan.npass; ++i) {
+        const int r = plan.radix[i];
+        switch (r) {
+            case 2: fft_pass<2>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+            case 3: fft_pass<3>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+            case 4: fft_pass<4>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+            case 5: fft_pass<5>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+            case 7: fft_pass<7>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+            case 11: fft_pass<11>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+            case 13: fft_pass<13>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+            default: fft_pass<17>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+        }
+        __syncthreads();
+        float2* t = a;
+        a = b;
+        b = t;
+        s *= r;
+    }
+    return a;
+}
+
+__device__ __forceinline__ void load_twiddles(float2* tws, const float2* __restrict__ tw, int n, bool inverse) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float2 t = tw[i];
+        tws[i] = inverse ? make_float2(t.x, -t.y) : t;
+    }
+}
+
+// ---- real -> complex along W --------------------------------------------------------------------
+// x real [B,H,W,ldx] (C real channels from x), out complex [B,H,Wf,C].  grid (B*H, C/2/CB).
+__global__ void __launch_bounds__(FFT_THREADS) fft_r2c_w_kernel(const float* __restrict__ x, int ldx,
+                                                                float2* __restrict__ out, const float2* __restrict__ tw,
+                                                                int W, int C, int cb_log2, FftPlan plan) {
+    extern __shared__ float2 sm[];
+    const int cb = 1 << cb_log2, n = W, wf = W / 2 + 1;
+    float2* a = sm;
+    float2* b = sm + (size_t)n * cb;
+    float2* tws = sm + 2 * (size_t)n * cb;
+    const size_t line = blockIdx.x;
+    const int c0 = blockIdx.y * cb;          // first complex lane == real channel pair index
+    load_twiddles(tws, tw, n, false);
+    const float* src = x + line * (size_t)W * ldx + 2 * c0;
+    for (int idx = threadIdx.x; idx < (n << cb_log2); idx += blockDim.x) {
+        const int i = idx >> cb_log2, ch = idx & (cb - 1);
+        a[idx] = *reinterpret_cast<const float2*>(src + (size_t)i * ldx + 2 * ch);
+    }
+    __syncthreads();
+    const float2* r = fft_line(a, b, plan, cb_log2, tws, false);
+    float2* dst = out + line * (size_t)wf * C + 2 * c0;
+    for (int idx = threadIdx.x; idx < (wf << cb_log2); idx += blockDim.x) {
+        const int k = idx >> cb_log2, ch = idx & (cb - 1);
+        const float2 zk = r[idx];
+        const int kn = k == 0 ? 0 : n - k;
+        float2 zn = r[(kn << cb_log2) + ch];
+        zn.y = -zn.y;
+        const float2 fa = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y));
+        const float2 d = csub(zk, zn);
+        const float2 fb = make_float2(0.5f * d.y, -0.5f * d.x);
+        *reinterpret_cast<float4*>(dst + (size_t)k * C + 2 * ch) = make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+}
+
+// ---- complex -> complex along H ------------------------------------------------------------------
+// in/out complex [B,H,Wf,C]; optional real mask [H*Wf] multiplied at load; grid (B*Wf, C/CB).
+__global__ void __launch_bounds__(FFT_THREADS) fft_c2c_h_kernel(const float2* in, float2* out,
+                                                                const float2* __restrict__ tw,
+                                                                const float* __restrict__ mask, int H, int Wf, int C,
+                                                                int cb_log2, int inverse, float scale, FftPlan plan) {
+    extern __shared__ float2 sm[];
+    const int cb = 1 << cb_log2, n = H;
+    float2* a = sm;
+    float2* b = sm + (size_t)n * cb;
+    float2* tws = sm + 2 * (size_t)n * cb;
+    const int bidx = blockIdx.x / Wf, wf = blockIdx.x - bidx * Wf;
+    const int c0 = blockIdx.y * cb;
+    load_twiddles(tws, tw, n, inverse != 0);
+    const size_t base = ((size_t)bidx * H * Wf + wf) * C + c0;
+    for (int idx = threadIdx.x; idx < (n << cb_log2); idx += blockDim.x) {
+        const int i = idx >> cb_log2, ch = idx & (cb - 1);
+        float2 v = in[base + (size_t)i * Wf * C + ch];
+        if (mask) {
+            const float mk = mask[i * Wf + wf];
+            v.x *= mk;
+            v.y *= mk;
+        }
+        a[idx] = v;
+    }
+    __syncthreads();
+    const float2* r = fft_line(a, b, plan, cb_log2, tws, inverse != 0);
+    for (int idx = threadIdx.x; idx < (n << cb_log2); idx += blockDim.x) {
+        const int i = idx >> cb_log2, ch = idx & (cb - 1);
+        float2 v = r[idx];
+        out[base + (size_t)i * Wf * C + ch] = make_float2(v.x * scale, v.y * scale);
+    }
+}
+
+// ---- complex -> real along W (torch c2r semantics: Im of the DC and Nyquist bins is ignored) -----
+// in complex [B,H,Wf,C], y real [B,H,W,ldy] (C real channels); grid (B*H, C/2/CB).
+__global__ void __launch_bounds__(FFT_THREADS) fft_c2r_w_kernel(const float2* __restrict__ in, float* __restrict__ y,
+                                                                int ldy, const float2* __restrict__ tw, int W, int C,
+                                                                int cb_log2, float scale, FftPlan plan) {
+    extern __shared__ float2 sm[];
+    const int cb = 1 << cb_log2, n = W, wf = W / 2 + 1;
+    float2* a = sm;
+    float2* b = sm + (size_t)n * cb;
+    float2* tws = sm + 2 * (size_t)n * cb;
+    const size_t line = blockIdx.x;
+    const int c0 = blockIdx.y * cb;
+    load_twiddles(tws, tw, n, true);
+    const float2* src = in + line * (size_t)wf * C + 2 * c0;
+    for (int idx = threadIdx.x; idx < (wf << cb_log2); idx += blockDim.x) {
+        const int k = idx >> cb_log2, ch = idx & (cb - 1);
+        float4 ab = *reinterpret_cast<const float4*>(src + (size_t)k * C + 2 * ch);   // A = (x,y), B = (z,w)
+        if (k == 0 || 2 * k == n) {
+            ab.y = 0.f;
+            ab.w = 0.f;
+        }
+        a[idx] = make_float2(ab.x - ab.w, ab.y + ab.z);                 // A + iB
+        if (k != 0 && 2 * k != n) a[((n - k) << cb_log2) + ch] = make_float2(ab.x + ab.w, ab.z - ab.y);  // conj(A) + i conj(B)
+    }
+    __syncthreads();
+    const float2* r = fft_line(a, b, plan, cb_log2, tws, true);
+    float* dst = y + line * (size_t)W * ldy + 2 * c0;
+    for (int idx = threadIdx.x; idx < (n << cb_log2); idx += blockDim.x) {
+        const int i = idx >> cb_log2, ch = idx & (cb - 1);
+        const float2 v = r[idx];
+        *reinterpret_cast<float2*>(dst + (size_t)i * ldy + 2 * ch) = make_float2(v.x * scale, v.y * scale);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int pick_cb_log2(int n, int lanes) {
+    // largest power of two CB <= 16 that divides `lanes` and keeps 2*n*CB*8 + n*8 <= ~200 KB
+    int cbl = 4;
+    while (cbl > 0 && ((lanes % (1 << cbl)) != 0 || (size_t)(2 * (size_t)n * (1 << cbl) + n) * 8 > 200 * 1024)) --cbl;
+    return cbl;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+            return FCVSR_ERR_CUDA;
+    }
+    return FCVSR_OK;
+}
+
+extern "C" int fcvsr_fft_r2c_w(const float* x, int ldx, float* out, const float* tw, int B, int H, int W, int C,
+                               cudaStream_t st) {
+    FftPlan plan;
+    if (!x || !out || !tw || (C & 1) || (W & 1) || (ldx & 1) || !make_plan(W, &plan)) return FCVSR_ERR_ARG;
+    const int lanes = C / 2, cbl = pick_cb_log2(W, lanes);
+    const size_t smem = (2 * (size_t)W * (1 << cbl) + W) * sizeof(float2);
+    if (set_smem(fft_r2c_w_kernel, smem)) return FCVSR_ERR_CUDA;
+    dim3 grid(B * H, lanes >> cbl);
+    fft_r2c_w_kernel<<<grid, FFT_THREADS, smem, st>>>(x, ldx, (float2*)out, (const float2*)tw, W, C, cbl, plan);
+    return fcvsr_launch_status();
+}
+
+extern "C" int fcvsr_fft_c2c_h(const float* in, float* out, const float* tw, const float* mask, int B, int H, int Wf,
+                               int C, int inverse, float scale, cudaStream_t st) {
+    FftPlan plan;
+    if (!in || !out || !tw || !make_plan(H, &plan)) return FCVSR_ERR_ARG;
+    const int cbl = pick_cb_log2(H, C);
+    const size_t smem = (2 * (size_t)H * (1 << cbl) + H) * sizeof(float2);
+    if (set_smem(fft_c2c_h_kernel, smem)) return FCVSR_ERR_CUDA;
+    dim3 grid(B * Wf, C >> cbl);
+    fft_c2c_h_kernel<<<grid, FFT_THREADS, smem, st>>>((const float2*)in, (float2*)out, (const float2*)tw, mask, H, Wf,
+                                                      C, cbl, inverse, scale, plan);
+    return fcvsr_launch_status();
+}
+
+extern "C" int fcvsr_fft_c2r_w(const float* in, float* y, int ldy, const float* tw, int B, int H, int W, int C,
+                               float scale, cudaStream_t st) {
+    FftPlan plan;
+    if (!in || !y || !tw || (C & 1) || (W & 1) || (ldy & 1) || !make_plan(W, &plan)) return FCVSR_ERR_ARG;
+    const int lanes = C / 2, cbl = pick_cb_log2(W, lanes);
+    const size_t smem = (2 * (size_t)W * (1 << cbl) + W) * sizeof(float2);
+    if (set_smem(fft_c2r_w_kernel, smem)) return FCVSR_ERR_CUDA;
+    dim3 grid(B * H, lanes >> cbl);
+    fft_c2r_w_kernel<<<grid, FFT_THREADS, smem, st>>>((const float2*)in, y, ldy, (const float2*)tw, W, C, cbl, scale,
+                                                      plan);
+    return fcvsr_launch_status();
+}

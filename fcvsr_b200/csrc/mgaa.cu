@@ -1,0 +1,311 @@
+// Kernels specific to the motion-guided adaptive alignment (MGAAbk, CVSR_freq.py:1365-1547).
+//
+//   corr_gather      CorrBlock lookup (:1279-1337) -- a pure gather, see oracle.corr_lookup
+//   offset_blk_*     ConvBlk(dim=4, index=i) on the 4-channel frequency maps (:344-357, :1494-1496)
+//                    for all ACNum iterations and both directions in one launch per stage
+//   iac_step         one IAC iteration (:1230-1250): flow_warp (:1188-1227) + SAC (:1253-1276)
+//                    + residual + LeakyReLU(0.1), fused in one pass with the warped tile and the
+//                    vertical-pass tile held in shared memory
+//
+// Spectra layout used by this library: complex-interleaved NHWC, [B, H, Wf, G*128] floats where
+// group g (x1, x2, x3) occupies floats [g*128, g*128+128) and channel c of the group sits at
+// (2c: real, 2c+1: imag).  The reference's xk_f = cat([imag, real]) channel j therefore maps to
+// float index  j < 64 ? 2j+1 : 2(j-64)  -- the host applies that permutation to the 1x1 weights.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// CorrBlock gather.  S: [B, P, ldS] floats (P = H*Wf), groups a_off / b_off (float offsets) hold the
+// two spectra.  out: [B, P, ldo], 81 channels.  prod (reference layout [C2][P]) flat index F = p*C2
+// + row*2 + col  ->  ref channel F / P, position F % P.
+__global__ void corr_gather_kernel(const float* __restrict__ S, int ldS, int a_off, int b_off, float* __restrict__ out,
+                                   int ldo, int H, int Wf, int C2, float inv_sqrt_c, int total) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int P = H * Wf;
+    const int o = idx % 81;
+    const int bp = idx / 81;
+    const int p = bp % P, b = bp / P;
+    const int i = o / 9, j = o - i * 9;
+    const int y0 = p / Wf, x0 = p - y0 * Wf;
+    const int col = x0 + i - 4, row = y0 + j - 4;
+    float v = 0.f;
+    if (col >= 0 && col < 2 && row >= 0 && row < C2 / 2) {
+        const long long F = (long long)p * C2 + row * 2 + col;
+        const int ch = (int)(F / P), p2 = (int)(F - (long long)ch * P);
+        const int half = C2 / 2;
+        const int mi = ch < half ? 2 * ch + 1 : 2 * (ch - half);
+        const float* s = S + ((size_t)b * P + p2) * ldS;
+        v = s[a_off + mi] * s[b_off + mi] * inv_sqrt_c;
+    }
+    out[((size_t)b * P + p) * ldo + o] = v;
+}
+
+extern "C" int fcvsr_corr_gather(const float* S, int ldS, int a_off, int b_off, float* out, int ldo, int B, int H,
+                                 int Wf, int C2, cudaStream_t st) {
+    if (!S || !out || C2 <= 0) return FCVSR_ERR_ARG;
+    const long long total = (long long)B * H * Wf * 81;
+    if (total > 0x7fffffffLL) return FCVSR_ERR_ARG;
+    corr_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, ldS, a_off, b_off, out, ldo, H, Wf, C2,
+                                                                      rsqrtf((float)C2), (int)total);
+    return fcvsr_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// ConvBlk on 4-channel maps.  `off` is [2][B][H*Wf][4] (direction-major: forward, backward).
+// Weights of iteration i (kernel size k = 2i+1) live at w + 16 * sum_{t<i} (2t+1)^2, packed
+// [tap][ci][co].  blockIdx = (pos chunk, i, b*2+dir).
+#define OB_THREADS 128
+__device__ __forceinline__ int ob_woff(int i) {   // 16 * sum_{t<i} (2t+1)^2 = 16 * i(2i-1)(2i+1)/3
+    return 16 * (i * (2 * i - 1) * (2 * i + 1) / 3);
+}
+
+template <bool SECOND>
+__global__ void __launch_bounds__(OB_THREADS) offset_blk_conv_kernel(const float* __restrict__ in, size_t in_iter_stride,
+                                                                    const float* __restrict__ w,
+                                                                    const float* __restrict__ prelu,   // [A] (stage 1)
+                                                                    float* __restrict__ out, size_t out_iter_stride,
+                                                                    float* __restrict__ partial,       // stage 2
+                                                                    int H, int Wf) {
+    __shared__ float ws[121 * 16];
+    __shared__ float red[OB_THREADS / 32][4];
+    const int it = blockIdx.y, k = 2 * it + 1, pad = it;
+    const int b = blockIdx.z >> 1, dir = blockIdx.z & 1;
+    const float* wi = w + ob_woff(it);
+    for (int t = threadIdx.x; t < k * k * 16; t += blockDim.x) ws[t] = wi[t];
+    __syncthreads();
+    const int P = H * Wf;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < P) {
+        const int y = p / Wf, x = p - y * Wf;
+        const int B = gridDim.z >> 1;
+        const float* src = in + (SECOND ? (size_t)it * in_iter_stride : 0) + ((size_t)dir * B + b) * P * 4;
+        for (int ky = 0; ky < k; ++ky) {
+            const int yy = y + ky - pad;
+            if (yy < 0 || yy >= H) continue;
+            for (int kx = 0; kx < k; ++kx) {
+                const int xx = x + kx - pad;
+                if (xx < 0 || xx >= Wf) continue;
+                const float4 v = *reinterpret_cast<const float4*>(src + ((size_t)yy * Wf + xx) * 4);
+                const float* wt = ws + (ky * k + kx) * 16;
+#pragma unroll
+                for (int co = 0; co < 4; ++co)
+                    acc[co] += v.x * wt[co] + v.y * wt[4 + co] + v.z * wt[8 + co] + v.w * wt[12 + co];
+            }
+        }
+        if (!SECOND) {
+            const float sl = prelu[it];
+#pragma unroll
+            for (int co = 0; co < 4; ++co) acc[co] = acc[co] >= 0.f ? acc[co] : acc[co] * sl;
+        }
+        float* dst = out + (size_t)it * out_iter_stride + (((size_t)dir * B + b) * P + p) * 4;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+    if (SECOND) {
+        // deterministic per-block partial sums for the CALayer mean
+#pragma unroll
+        for (int co = 0; co < 4; ++co) {
+            float s = warp_sum(acc[co]);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][co] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            float s = 0.f;
+            for (int wv = 0; wv < OB_THREADS / 32; ++wv) s += red[wv][threadIdx.x];
+            // partial[it][b*2+dir][blk][4]
+            partial[(((size_t)it * gridDim.z + blockIdx.z) * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = s;
+        }
+    }
+}
+
+// Stage 3: CALayer(4, r=1) gate from the partial sums, (gate+1) * t2 * sim, packed as the complex
+// input of irfft2: complex channel (it*2+dir)*2 + m = (v[m], v[2+m])  (:1497-1498).
+__global__ void __launch_bounds__(OB_THREADS) offset_blk_finish_kernel(const float* __restrict__ t2, size_t iter_stride,
+                                                                      const float* __restrict__ partial, int nblk,
+                                                                      const float* __restrict__ ca_w,   // [A][2][4][4]
+                                                                      const float* __restrict__ sim, int ldsim,
+                                                                      float* __restrict__ z, int A, int H, int Wf) {
+    __shared__ float gate[4];
+    const int it = blockIdx.y;
+    const int b = blockIdx.z >> 1, dir = blockIdx.z & 1;
+    const int P = H * Wf;
+    if (threadIdx.x < 32) {
+        float m[4];
+        const float* pp = partial + ((size_t)it * gridDim.z + blockIdx.z) * nblk * 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float s = 0.f;
+            for (int t = threadIdx.x; t < nblk; t += 32) s += pp[t * 4 + c];
+            m[c] = warp_sum(s) / (float)P;
+        }
+        if (threadIdx.x < 4) {
+            const float* w1 = ca_w + it * 32;
+            const float* w2 = w1 + 16;
+            float hdn[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s += w1[o * 4 + c] * m[c];
+                hdn[o] = fmaxf(s, 0.f);
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s += w2[threadIdx.x * 4 + c] * hdn[c];
+            gate[threadIdx.x] = 1.f + 1.f / (1.f + __expf(-s));
+        }
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int B = gridDim.z >> 1;
+    const float4 v = *reinterpret_cast<const float4*>(t2 + (size_t)it * iter_stride + (((size_t)dir * B + b) * P + p) * 4);
+    const float4 s = *reinterpret_cast<const float4*>(sim + ((size_t)b * P + p) * ldsim);
+    const float o0 = v.x * gate[0] * s.x, o1 = v.y * gate[1] * s.y, o2 = v.z * gate[2] * s.z, o3 = v.w * gate[3] * s.w;
+    float* dst = z + (((size_t)b * P + p) * (4 * A) + (it * 2 + dir) * 2) * 2;
+    *reinterpret_cast<float4*>(dst) = make_float4(o0, o2, o1, o3);
+}
+
+extern "C" int fcvsr_offset_blocks(const float* off, const float* w1, const float* w2, const float* prelu,
+                                   const float* ca_w, const float* sim, int ldsim, float* t1, float* t2,
+                                   float* partial, float* z, int B, int H, int Wf, int A, cudaStream_t st) {
+    if (!off || !w1 || !w2 || !prelu || !ca_w || !sim || !t1 || !t2 || !partial || !z || A < 1 || A > 6 || (ldsim & 3))
+        return FCVSR_ERR_ARG;
+    const int P = H * Wf;
+    const int nblk = (P + OB_THREADS - 1) / OB_THREADS;
+    dim3 grid(nblk, A, B * 2);
+    const size_t iter_stride = (size_t)B * P * 8;
+    offset_blk_conv_kernel<false><<<grid, OB_THREADS, 0, st>>>(off, 0, w1, prelu, t1, iter_stride, nullptr, H, Wf);
+    offset_blk_conv_kernel<true><<<grid, OB_THREADS, 0, st>>>(t1, iter_stride, w2, nullptr, t2, iter_stride, partial, H, Wf);
+    offset_blk_finish_kernel<<<grid, OB_THREADS, 0, st>>>(t2, iter_stride, partial, nblk, ca_w, sim, ldsim, z, A, H, Wf);
+    return fcvsr_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// One IAC iteration for both directions.  Tile = 8 x 16 output pixels x 64 channels; a warp owns a
+// pixel at a time and a lane owns channels (2*lane, 2*lane+1).
+//   samp(y',x')  = bilinear(prev, x'+dx(y',x'), y'+dy(y',x'))        zeros outside, align_corners
+//   v(y,x')      = sum_t K[t](y,x') * samp(clamp(y+t-1), x')         (vertical pass, replicate pad)
+//   out(y,x)     = lrelu_0.1( sum_t K[t](y,x) * v(y, clamp(x+t-1)) + xin(y,x) )
+// K[t] of this iteration = taps[..., t*64 + c] (host packs F.1's live rows as [iter][t][c]).
+#define IAC_TH 8
+#define IAC_TW 16
+#define IAC_C 64
+struct IacArgs {
+    const float* prev[2]; int ldprev[2];
+    const float* xin[2];  int ldxin[2];
+    float* next[2];       int ldnext[2];
+    const float* offs; int ldoffs; int offs_ch[2];   // channel of dx for each direction
+    const float* taps; int ldtaps;                   // already offset to this iteration's 192 channels
+    int B, H, W;
+};
+
+__global__ void __launch_bounds__(256) iac_step_kernel(IacArgs a) {
+    extern __shared__ float smem[];
+    float* samp = smem;                                             // [(TH+2)*(TW+2)][64]
+    float* vbuf = smem + (IAC_TH + 2) * (IAC_TW + 2) * IAC_C;       // [TH*(TW+2)][64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_x = (a.W + IAC_TW - 1) / IAC_TW;
+    const int ty0 = (blockIdx.x / tiles_x) * IAC_TH, tx0 = (blockIdx.x % tiles_x) * IAC_TW;
+    const int b = blockIdx.y, dir = blockIdx.z;
+    const float* prev = a.prev[dir];
+    const int ldp = a.ldprev[dir];
+    const int H = a.H, W = a.W;
+    const size_t img = (size_t)b * H * W;
+
+    // phase 1: warped samples on the haloed tile (coordinates clamped == replicate padding)
+    for (int hp = warp; hp < (IAC_TH + 2) * (IAC_TW + 2); hp += 8) {
+        const int hy = hp / (IAC_TW + 2), hx = hp - hy * (IAC_TW + 2);
+        const int yy = min(max(ty0 - 1 + hy, 0), H - 1), xx = min(max(tx0 - 1 + hx, 0), W - 1);
+        const float2 d = *reinterpret_cast<const float2*>(a.offs + (img + (size_t)yy * W + xx) * a.ldoffs + a.offs_ch[dir]);
+        const float sx = (float)xx + d.x, sy = (float)yy + d.y;
+        const float fx0 = floorf(sx), fy0 = floorf(sy);
+        const float lx = sx - fx0, ly = sy - fy0;
+        float2 acc = make_float2(0.f, 0.f);
+        // guard against inf/nan/huge offsets: anything outside contributes zero
+        if (sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H) {
+            const int x0 = (int)fx0, y0 = (int)fy0;
+#pragma unroll
+            for (int cy = 0; cy < 2; ++cy) {
+                const int y = y0 + cy;
+                if (y < 0 || y >= H) continue;
+                const float wy = cy ? ly : 1.f - ly;
+#pragma unroll
+                for (int cx = 0; cx < 2; ++cx) {
+                    const int x = x0 + cx;
+                    if (x < 0 || x >= W) continue;
+                    const float wgt = wy * (cx ? lx : 1.f - lx);
+                    const float2 v = *reinterpret_cast<const float2*>(prev + (img + (size_t)y * W + x) * ldp + 2 * lane);
+                    acc.x = fmaf(wgt, v.x, acc.x);
+                    acc.y = fmaf(wgt, v.y, acc.y);
+                }
+            }
+        }
+        *reinterpret_cast<float2*>(samp + hp * IAC_C + 2 * lane) = acc;
+    }
+    __syncthreads();
+    // phase 2: vertical pass for TH rows x (TW+2) columns
+    for (int vp = warp; vp < IAC_TH * (IAC_TW + 2); vp += 8) {
+        const int ly = vp / (IAC_TW + 2), hx = vp - ly * (IAC_TW + 2);
+        const int y = ty0 + ly;
+        const int xx = min(max(tx0 - 1 + hx, 0), W - 1);
+        float2 acc = make_float2(0.f, 0.f);
+        if (y < H) {
+            const float* kp = a.taps + (img + (size_t)y * W + xx) * a.ldtaps + 2 * lane;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const float2 k = *reinterpret_cast<const float2*>(kp + t * IAC_C);
+                const float2 s = *reinterpret_cast<const float2*>(samp + ((ly + t) * (IAC_TW + 2) + hx) * IAC_C + 2 * lane);
+                acc.x = fmaf(k.x, s.x, acc.x);
+                acc.y = fmaf(k.y, s.y, acc.y);
+            }
+        }
+        *reinterpret_cast<float2*>(vbuf + vp * IAC_C + 2 * lane) = acc;
+    }
+    __syncthreads();
+    // phase 3: horizontal pass + residual + LeakyReLU(0.1)
+    const float* xin = a.xin[dir];
+    float* next = a.next[dir];
+    for (int op = warp; op < IAC_TH * IAC_TW; op += 8) {
+        const int ly = op / IAC_TW, lxp = op - ly * IAC_TW;
+        const int y = ty0 + ly, x = tx0 + lxp;
+        if (y >= H || x >= W) continue;
+        const float* kp = a.taps + (img + (size_t)y * W + x) * a.ldtaps + 2 * lane;
+        float2 acc = *reinterpret_cast<const float2*>(xin + (img + (size_t)y * W + x) * a.ldxin[dir] + 2 * lane);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const float2 k = *reinterpret_cast<const float2*>(kp + t * IAC_C);
+            const float2 v = *reinterpret_cast<const float2*>(vbuf + (ly * (IAC_TW + 2) + lxp + t) * IAC_C + 2 * lane);
+            acc.x = fmaf(k.x, v.x, acc.x);
+            acc.y = fmaf(k.y, v.y, acc.y);
+        }
+        acc.x = acc.x >= 0.f ? acc.x : 0.1f * acc.x;
+        acc.y = acc.y >= 0.f ? acc.y : 0.1f * acc.y;
+        *reinterpret_cast<float2*>(next + (img + (size_t)y * W + x) * a.ldnext[dir] + 2 * lane) = acc;
+    }
+}
+
+extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int ldprev_b, const float* xin_f,
+                              int ldxin_f, const float* xin_b, int ldxin_b, float* next_f, int ldnext_f, float* next_b,
+                              int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps,
+                              int ldtaps, int B, int H, int W, cudaStream_t st) {
+    if (!prev_f || !prev_b || !xin_f || !xin_b || !next_f || !next_b || !offs || !taps) return FCVSR_ERR_ARG;
+    if ((ldprev_f | ldprev_b | ldxin_f | ldxin_b | ldnext_f | ldnext_b | ldoffs | ldtaps | ch_f | ch_b) & 1)
+        return FCVSR_ERR_ARG;
+    IacArgs a;
+    a.prev[0] = prev_f; a.prev[1] = prev_b; a.ldprev[0] = ldprev_f; a.ldprev[1] = ldprev_b;
+    a.xin[0] = xin_f; a.xin[1] = xin_b; a.ldxin[0] = ldxin_f; a.ldxin[1] = ldxin_b;
+    a.next[0] = next_f; a.next[1] = next_b; a.ldnext[0] = ldnext_f; a.ldnext[1] = ldnext_b;
+    a.offs = offs; a.ldoffs = ldoffs; a.offs_ch[0] = ch_f; a.offs_ch[1] = ch_b;
+    a.taps = taps; a.ldtaps = ldtaps; a.B = B; a.H = H; a.W = W;
+    const size_t smem = ((IAC_TH + 2) * (IAC_TW + 2) + IAC_TH * (IAC_TW + 2)) * IAC_C * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(iac_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return FCVSR_ERR_CUDA;
+        attr_set = true;
+    }
+    dim3 grid(((H + IAC_TH - 1) / IAC_TH) * ((W + IAC_TW - 1) / IAC_TW), B, 2);
+    iac_step_kernel<<<grid, 256, smem, st>>>(a);
+    return fcvsr_launch_status();
+}

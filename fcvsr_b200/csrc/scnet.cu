@@ -1,0 +1,170 @@
+// Non-GEMM kernels of the SCNetbk trunk (CVSR_freq.py:657-822).
+//
+//   ctx_partial / ctx_finalize   ContextBlock (:657-701): softmax-over-HW attention pooling done as an
+//                                online-softmax reduction (running max / sum / weighted channel sums
+//                                per block, merged in fixed order) followed by the 64->64->64 MLP.
+//   rcb_finish                   RCB tail (:720-724):  r = lrelu_0.2(res + add_term) + r0
+//   level_mix                    BlockRCB cross-level sum (:766-777):
+//                                x += coef*r + avgpool2(td) + bilinear_x2(tu)
+//                                (Interpolate(0.5) of an even-sized map == 2x2 mean; Interpolate(2.0) is
+//                                bilinear, align_corners=False; td/tu are the 1x1 down/up conv outputs)
+#include "common.cuh"
+
+#define CTX_PIX_PER_BLOCK 512
+#define CTX_STRIDE 66          // m, z, acc[64]
+
+__global__ void __launch_bounds__(256) ctx_partial_kernel(const float* __restrict__ x, int ldx,
+                                                          const float* __restrict__ wmask, float* __restrict__ partial,
+                                                          int P) {
+    __shared__ float sm_m[8], sm_z[8];
+    __shared__ float sm_acc[8][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, c = 2 * lane;
+    const float2 w = *reinterpret_cast<const float2*>(wmask + c);
+    float m = -INFINITY, z = 0.f;
+    float2 acc = make_float2(0.f, 0.f);
+    const int p_end = min(P, (int)(blockIdx.x + 1) * CTX_PIX_PER_BLOCK);
+    for (int p = blockIdx.x * CTX_PIX_PER_BLOCK + warp; p < p_end; p += 8) {
+        const float2 v = *reinterpret_cast<const float2*>(x + ((size_t)b * P + p) * ldx + c);
+        const float logit = warp_sum(v.x * w.x + v.y * w.y);
+        const float mn = fmaxf(m, logit);
+        const float sc = __expf(m - mn), e = __expf(logit - mn);
+        z = z * sc + e;
+        acc.x = acc.x * sc + e * v.x;
+        acc.y = acc.y * sc + e * v.y;
+        m = mn;
+    }
+    if (lane == 0) { sm_m[warp] = m; sm_z[warp] = z; }
+    sm_acc[warp][c] = acc.x; sm_acc[warp][c + 1] = acc.y;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) M = fmaxf(M, sm_m[k]);
+        float Z = 0.f, A = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float s = sm_m[k] == -INFINITY ? 0.f : __expf(sm_m[k] - M);
+            Z += sm_z[k] * s;
+            A += sm_acc[k][threadIdx.x] * s;
+        }
+        float* dst = partial + ((size_t)b * gridDim.x + blockIdx.x) * CTX_STRIDE;
+        if (threadIdx.x == 0) { dst[0] = M; dst[1] = Z; }
+        dst[2 + threadIdx.x] = A;
+    }
+}
+
+// grid B, 64 threads: merge partials -> context[64] -> add = W2 lrelu_0.2(W1 ctx)
+__global__ void __launch_bounds__(64) ctx_finalize_kernel(const float* __restrict__ partial, int nblk,
+                                                          const float* __restrict__ w1, const float* __restrict__ w2,
+                                                          float* __restrict__ add) {
+    __shared__ float ctx[64], hid[64];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float* pp = partial + (size_t)b * nblk * CTX_STRIDE;
+    float M = -INFINITY;
+    for (int k = 0; k < nblk; ++k) M = fmaxf(M, pp[k * CTX_STRIDE]);
+    float Z = 0.f, A = 0.f;
+    for (int k = 0; k < nblk; ++k) {
+        const float s = __expf(pp[k * CTX_STRIDE] - M);
+        Z += pp[k * CTX_STRIDE + 1] * s;
+        A += pp[k * CTX_STRIDE + 2 + t] * s;
+    }
+    ctx[t] = A / Z;
+    __syncthreads();
+    float h = 0.f;
+    for (int c = 0; c < 64; ++c) h += w1[t * 64 + c] * ctx[c];
+    hid[t] = h >= 0.f ? h : 0.2f * h;
+    __syncthreads();
+    float o = 0.f;
+    for (int c = 0; c < 64; ++c) o += w2[t * 64 + c] * hid[c];
+    add[(size_t)b * 64 + t] = o;
+}
+
+extern "C" int fcvsr_context_block(const float* x, int ldx, const float* wmask, const float* w1, const float* w2,
+                                   float* partial, float* add, int B, int P, cudaStream_t st) {
+    if (!x || !wmask || !w1 || !w2 || !partial || !add || (ldx & 1)) return FCVSR_ERR_ARG;
+    const int nblk = (P + CTX_PIX_PER_BLOCK - 1) / CTX_PIX_PER_BLOCK;
+    ctx_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, ldx, wmask, partial, P);
+    ctx_finalize_kernel<<<B, 64, 0, st>>>(partial, nblk, w1, w2, add);
+    return fcvsr_launch_status();
+}
+
+// r = lrelu_0.2(res + add[b]) + r0     (all 64 channels, float4 per thread)
+__global__ void rcb_finish_kernel(const float* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
+                                  float* __restrict__ r, int P, size_t total4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int c = (int)(i & 15) * 4;
+    const size_t pix = i >> 4;
+    const int b = (int)(pix / P);
+    const float4 v = *reinterpret_cast<const float4*>(res + pix * 64 + c);
+    const float4 a = *reinterpret_cast<const float4*>(add + (size_t)b * 64 + c);
+    const float4 q = *reinterpret_cast<const float4*>(r0 + pix * 64 + c);
+    float4 o;
+    o.x = v.x + a.x; o.y = v.y + a.y; o.z = v.z + a.z; o.w = v.w + a.w;
+    o.x = (o.x >= 0.f ? o.x : 0.2f * o.x) + q.x;
+    o.y = (o.y >= 0.f ? o.y : 0.2f * o.y) + q.y;
+    o.z = (o.z >= 0.f ? o.z : 0.2f * o.z) + q.z;
+    o.w = (o.w >= 0.f ? o.w : 0.2f * o.w) + q.w;
+    *reinterpret_cast<float4*>(r + pix * 64 + c) = o;
+}
+
+extern "C" int fcvsr_rcb_finish(const float* res, const float* add, const float* r0, float* r, int B, int P,
+                                cudaStream_t st) {
+    if (!res || !add || !r0 || !r) return FCVSR_ERR_ARG;
+    const size_t total4 = (size_t)B * P * 16;
+    rcb_finish_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(res, add, r0, r, P, total4);
+    return fcvsr_launch_status();
+}
+
+// x[b,y,x,:] += coef * r + mean2x2(td) + bilinear_x2(tu)      (64 channels, ld 64 everywhere except x/y)
+__global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* __restrict__ xout, int ldo,
+                                 const float* __restrict__ r, float coef, const float* __restrict__ td,
+                                 const float* __restrict__ tu, int H, int W, size_t total4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int c = (int)(i & 15) * 4;
+    const size_t pix = i >> 4;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int b = (int)(pix / ((size_t)W * H));
+    float4 o = *reinterpret_cast<const float4*>(xin + pix * ldx + c);
+    const float4 rv = *reinterpret_cast<const float4*>(r + pix * 64 + c);
+    o.x = fmaf(coef, rv.x, o.x); o.y = fmaf(coef, rv.y, o.y); o.z = fmaf(coef, rv.z, o.z); o.w = fmaf(coef, rv.w, o.w);
+    if (td) {   // td is [B,2H,2W,64]
+        const size_t base = (((size_t)b * 2 * H + 2 * y) * (2 * W) + 2 * x) * 64 + c;
+        const float4 a0 = *reinterpret_cast<const float4*>(td + base);
+        const float4 a1 = *reinterpret_cast<const float4*>(td + base + 64);
+        const float4 a2 = *reinterpret_cast<const float4*>(td + base + (size_t)2 * W * 64);
+        const float4 a3 = *reinterpret_cast<const float4*>(td + base + (size_t)2 * W * 64 + 64);
+        o.x += 0.25f * (a0.x + a1.x + a2.x + a3.x);
+        o.y += 0.25f * (a0.y + a1.y + a2.y + a3.y);
+        o.z += 0.25f * (a0.z + a1.z + a2.z + a3.z);
+        o.w += 0.25f * (a0.w + a1.w + a2.w + a3.w);
+    }
+    if (tu) {   // tu is [B,H/2,W/2,64]; bilinear, align_corners=False, scale 2
+        const int hs = H >> 1, ws = W >> 1;
+        const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
+        const float ly = sy - y0, lx = sx - x0;
+        const float* tb = tu + (size_t)b * hs * ws * 64 + c;
+        const float4 a00 = *reinterpret_cast<const float4*>(tb + ((size_t)y0 * ws + x0) * 64);
+        const float4 a01 = *reinterpret_cast<const float4*>(tb + ((size_t)y0 * ws + x1) * 64);
+        const float4 a10 = *reinterpret_cast<const float4*>(tb + ((size_t)y1 * ws + x0) * 64);
+        const float4 a11 = *reinterpret_cast<const float4*>(tb + ((size_t)y1 * ws + x1) * 64);
+        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        o.x += w00 * a00.x + w01 * a01.x + w10 * a10.x + w11 * a11.x;
+        o.y += w00 * a00.y + w01 * a01.y + w10 * a10.y + w11 * a11.y;
+        o.z += w00 * a00.z + w01 * a01.z + w10 * a10.z + w11 * a11.z;
+        o.w += w00 * a00.w + w01 * a01.w + w10 * a10.w + w11 * a11.w;
+    }
+    *reinterpret_cast<float4*>(xout + pix * ldo + c) = o;
+}
+
+extern "C" int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float* r, float coef,
+                               const float* td, const float* tu, int B, int H, int W, cudaStream_t st) {
+    if (!xin || !xout || !r || (ldx & 3) || (ldo & 3) || (tu && ((H | W) & 1))) return FCVSR_ERR_ARG;
+    const size_t total4 = (size_t)B * H * W * 16;
+    level_mix_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(xin, ldx, xout, ldo, r, coef, td, tu, H, W, total4);
+    return fcvsr_launch_status();
+}

@@ -1,0 +1,458 @@
+"""Host-side orchestration of the FCVSR forward on the sm_100a kernel library.
+
+``Engine`` owns (1) the packed weights (reference OIHW fp32 -> the layouts the kernels read, with
+the channel permutations that let concatenations / pixel shuffles / the [imag|real] spectrum
+packing of the reference disappear), (2) a per-shape workspace of NHWC device buffers, and (3) the
+launch sequence that restates ``GShiftNet.forward`` (CVSR_train/arch/CVSR_freq.py:2688-2756) kernel
+by kernel.  Every arithmetic step is a call into ``libfcvsr_b200.so`` through the C ABI
+(include/fcvsr_b200.h); no ATen op touches the data path.  The whole launch sequence can be captured
+into a CUDA graph (``use_graph``), which removes the Python launch overhead of the ~10^3 launches.
+
+Line numbers in comments refer to CVSR_train/arch/CVSR_freq.py.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _capi as C
+from . import bands
+
+F32 = torch.float32
+
+
+def _spec_perm(n: int = 64) -> torch.Tensor:
+    """reference xk_f channel j (cat[imag, real], :1456-1465) -> float index in our complex-interleaved
+    spectrum (2c real, 2c+1 imag)."""
+    j = torch.arange(2 * n)
+    return torch.where(j < n, 2 * j + 1, 2 * (j - n))
+
+
+class _ConvPack:
+    """One convolution's weights in both kernel layouts."""
+
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, ps: bool = False,
+                 cin_pad: Optional[int] = None, in_perm: Optional[torch.Tensor] = None,
+                 out_perm: Optional[torch.Tensor] = None):
+        w = w.detach().to(F32)
+        if in_perm is not None:       # new input position in_perm[j] <- reference input channel j
+            w2 = torch.zeros_like(w)
+            w2[:, in_perm] = w
+            w = w2
+        if out_perm is not None:      # new output position out_perm[j] <- reference output channel j
+            w2 = torch.zeros_like(w)
+            w2[out_perm] = w
+            w = w2
+            if b is not None:
+                b2 = torch.zeros_like(b)
+                b2[out_perm] = b.detach()
+                b = b2
+        cout, cin, k, _ = w.shape
+        if ps:                        # GEMM column ij*C4 + c <- reference channel c*4 + ij (pixel_shuffle)
+            c4 = cout // 4
+            idx = (torch.arange(c4).view(1, c4) * 4 + torch.arange(4).view(4, 1)).reshape(-1).to(w.device)
+            w = w[idx]
+            if b is not None:
+                b = b.detach()[idx]
+        if cin_pad is not None and cin_pad > cin:
+            w = torch.cat([w, w.new_zeros(cout, cin_pad - cin, k, k)], 1)
+            cin = cin_pad
+        self.cin, self.cout, self.k, self.stride, self.ps = cin, cout, k, stride, ps
+        self.bias = b.detach().to(F32).contiguous() if b is not None else None
+        self.w_direct = w.permute(2, 3, 1, 0).contiguous()                 # [k*k][Cin][Cout]
+        wt = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin)              # [Cout][k*k*Cin]
+        if cout < 16:
+            wt = torch.cat([wt, wt.new_zeros(16 - cout, wt.shape[1])], 0)
+        self.w_tc = wt.contiguous()
+        self.tc_ok = stride == 1 and k in (1, 3) and cin % 32 == 0 and (cout < 16 or cout % 16 == 0)
+
+
+class Engine:
+    def __init__(self, model, use_tc: bool = True):
+        self.model = model
+        self.use_tc = use_tc
+        self.packs: Optional[Dict[str, object]] = None
+        self._pack_key = None
+        self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self.launches = 0            # kernel launches issued by the last forward (for bench.py)
+        self.tc_launches = 0
+        C.lib()                      # fail loudly now if the library is missing
+
+    # -------------------------------------------------------------------------------------------
+    # weights
+    # -------------------------------------------------------------------------------------------
+    def _key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def _ensure_packs(self, device):
+        key = (str(device),) + self._key()
+        if self.packs is not None and key == self._pack_key:
+            return
+        m = self.model
+        sd = {k: v.detach().to(device=device, dtype=F32) for k, v in m.state_dict().items()}
+        P: Dict[str, object] = {}
+        A = m.ACNum
+        n = m.n_feats
+        pi = _spec_perm(n).to(device)
+
+        def cp(name, **kw):
+            return _ConvPack(sd[name + ".weight"], sd.get(name + ".bias"), **kw)
+
+        P["feat"] = cp("feat_extract.0")
+        # --- MGAA per-bin MLPs (:1371-1396) on the interleaved spectrum ---
+        ar = torch.arange(2 * n, device=device)
+        perm_f = torch.cat([pi, 2 * n + pi])                     # cat[x1_f, x2_f] -> [grp0 | grp1]
+        perm_b = torch.cat([2 * n + pi, pi])                     # cat[x3_f, x2_f] -> [grp1 | grp2] slice
+        P["fuse0_f"] = cp("MGAA.convfuse.0", in_perm=perm_f)
+        P["fuse0_b"] = cp("MGAA.convfuse.0", in_perm=perm_b)
+        P["fuse2"] = cp("MGAA.convfuse.2")
+        P["fuse4"] = cp("MGAA.convfuse.4", out_perm=pi)
+        P["crt0"] = cp("MGAA.convcrt.0", in_perm=pi)
+        P["crt2"] = cp("MGAA.convcrt.2")
+        wcc = sd["MGAA.convcorr.0.weight"][:, : 2 * n + 81]       # the 2 flow channels are zeros (:1484-1485)
+        perm_cc = torch.cat([pi, 2 * n + torch.arange(81, device=device)])
+        P["corr0"] = _ConvPack(wcc, None, in_perm=perm_cc, cin_pad=224)
+        P["corr2"] = cp("MGAA.convcorr.2")
+        P["corr4"] = cp("MGAA.convcorr.4")
+        # ConvBlk stack (:344-357): weights [tap][ci][co] per iteration, back to back
+        w1 = [sd[f"MGAA.MConvB.{i}.conv1.weight"].permute(2, 3, 1, 0).reshape(-1) for i in range(A)]
+        w2 = [sd[f"MGAA.MConvB.{i}.conv2.weight"].permute(2, 3, 1, 0).reshape(-1) for i in range(A)]
+        P["ob_w1"] = torch.cat(w1).contiguous()
+        P["ob_w2"] = torch.cat(w2).contiguous()
+        P["ob_prelu"] = torch.cat([sd[f"MGAA.MConvB.{i}.relu.weight"].reshape(1) for i in range(A)]).contiguous()
+        P["ob_ca"] = torch.cat([torch.cat([sd[f"MGAA.MConvB.{i}.CA.conv_du.0.weight"].reshape(-1),
+                                           sd[f"MGAA.MConvB.{i}.CA.conv_du.2.weight"].reshape(-1)])
+                                for i in range(A)]).contiguous()
+        P["kp"] = cp("MGAA.conv_KP")
+        P["F0"] = cp("MGAA.F.0")
+        # F.1: keep only the live rows i*384 + c*3 + t (:1231-1235, SAC uses kernel1 twice :1272-1273),
+        # re-ordered to [i][t][c] so the IAC kernel reads 64 contiguous channels per tap
+        ii, tt, cc = torch.meshgrid(torch.arange(A), torch.arange(3), torch.arange(n), indexing="ij")
+        rows = (ii * 6 * n + cc * 3 + tt).reshape(-1).to(device)
+        P["F1"] = _ConvPack(sd["MGAA.F.1.weight"][rows], sd["MGAA.F.1.bias"][rows])
+        P["conv3"] = cp("MGAA.conv3")
+        # --- MFFR (:2104-2133) ---
+        for i in range(m.Freq_Inv):
+            P[f"de{i}.a"] = sd[f"MFFRblock.DivEnh_block.{i}.a"].reshape(-1).contiguous()
+            P[f"de{i}.b"] = sd[f"MFFRblock.DivEnh_block.{i}.b"].reshape(-1).contiguous()
+            P[f"de{i}.w1"] = sd[f"MFFRblock.DivEnh_block.{i}.ca.conv_du.0.weight"].reshape(4, n).contiguous()
+            P[f"de{i}.w2"] = sd[f"MFFRblock.DivEnh_block.{i}.ca.conv_du.2.weight"].reshape(n, 4).contiguous()
+        P["mffr.w1"] = sd["MFFRblock.ca.conv_du.0.weight"].reshape(4, n).contiguous()
+        P["mffr.w2"] = sd["MFFRblock.ca.conv_du.2.weight"].reshape(n, 4).contiguous()
+        P["rc1"] = cp("rconcat1", stride=2)
+        P["rc2"] = cp("rconcat2", stride=2)
+        # --- SCNetbk (:705-822) ---
+        for g in range(m.SCGroupN):
+            P[f"g{g}.conv"] = cp(f"recorb1.body.{g}.conv")
+            for k in range(3):
+                pre = f"recorb1.body.{g}.body.{k}"
+                q = f"g{g}.b{k}."
+                P[q + "c0"] = cp(pre + ".body.0")
+                P[q + "c2"] = cp(pre + ".body.2")
+                P[q + "r0"] = cp(pre + ".RCB.body.0")
+                P[q + "r2"] = cp(pre + ".RCB.body.2")
+                P[q + "mask"] = sd[pre + ".RCB.gcnet.conv_mask.weight"].reshape(-1).contiguous()
+                P[q + "a0"] = sd[pre + ".RCB.gcnet.channel_add_conv.0.weight"].reshape(n, n).contiguous()
+                P[q + "a2"] = sd[pre + ".RCB.gcnet.channel_add_conv.2.weight"].reshape(n, n).contiguous()
+                P[q + "down"] = cp(pre + ".down.0")
+                P[q + "up"] = cp(pre + ".up.0")
+        # --- tail (:2739-2749) ---
+        c4 = n // 4
+        ps_pos = torch.empty(n, dtype=torch.long, device=device)   # position of reference channel c*4+ij
+        ps_pos[(torch.arange(c4).view(1, c4) * 4 + torch.arange(4).view(4, 1)).reshape(-1)] = torch.arange(n)
+        P["up_l3"] = cp("upconv1_L3", ps=True)
+        # u2 is kept in pixel-shuffle order (position ij*16+c) so that `u2 + conv(cat)` lines up with the
+        # shuffled GEMM columns of upconv1_L2_2 (:2743)
+        P["up_l2"] = cp("upconv1_L2", out_perm=ps_pos)
+        perm_l22 = torch.cat([ps_pos, n + torch.arange(c4, device=device)])
+        P["up_l2_2"] = cp("upconv1_L2_2", in_perm=perm_l22, cin_pad=96, ps=True)
+        P["fuse"] = cp("upconv_fuse", cin_pad=96)
+        P["rec0"] = cp("recorb0")
+        P["up1"] = cp("upconv1", ps=True)
+        P["up2"] = cp("upconv2", ps=True)
+        P["last"] = cp("conv_last0")
+        P["prelu"] = sd["lrelu.weight"].reshape(1).contiguous()
+        self.packs = P
+        self._pack_key = key
+
+    # -------------------------------------------------------------------------------------------
+    # workspace
+    # -------------------------------------------------------------------------------------------
+    def _workspace(self, B, H, W, device):
+        key = (B, H, W, str(device))
+        if key in self._ws:
+            return self._ws[key]
+        m = self.model
+        A, Q = m.ACNum, m.Freq_Inv
+        Wf = W // 2 + 1
+        P, Pf = H * W, H * Wf
+        ws: Dict[str, torch.Tensor] = {}
+
+        def buf(name, *shape, zero=False):
+            ws[name] = (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=F32)
+
+        buf("feat", B, P, 448)
+        buf("spec", B, Pf, 384)
+        buf("h1", 2 * B, Pf, 128)
+        buf("h2", 2 * B, Pf, 128)
+        buf("cc", 2 * B, Pf, 224, zero=True)
+        buf("c1", 2 * B, Pf, 64)
+        buf("c2", 2 * B, Pf, 64)
+        buf("off", 2 * B, Pf, 4)
+        buf("simh", B, Pf, 64)
+        buf("sim", B, Pf, 4)
+        buf("t1", A, 2 * B, Pf, 4)
+        buf("t2", A, 2 * B, Pf, 4)
+        buf("ob_partial", A * 2 * B * ((Pf + 127) // 128) * 4)
+        buf("z", B, Pf, 8 * A)
+        buf("offs", B, P, 4 * A)
+        buf("kp1", B, P, 64)
+        buf("kp2", B, P, 64)
+        buf("pk", B, P, A * 192)
+        buf("ping", 2, 2, B, P, 64)
+        buf("cat128", B, P, 128)
+        buf("m2", B, P, 64)
+        buf("specx", B, Pf, 128)
+        buf("tmpc", B, Pf, 128)
+        buf("bands", Q, B, P, 64)
+        buf("sb", B, P, 64)
+        buf("so", B, P, 64)
+        buf("mf_partial", B * ((P + 255) // 256) * 128)
+        buf("mean0", B, 128)
+        buf("gates", Q + 1, B, 128)
+        dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
+        for l, (h, w) in enumerate(dims):
+            p = h * w
+            for nm in ("xs", "cur", "t", "r0", "c1", "res", "rr"):
+                buf(f"{nm}{l}", B, p, 64)
+            buf(f"a128_{l}", B, p, 128)
+            buf(f"td{l}", B, p, 64)
+            buf(f"tu{l}", B, p, 64)
+            buf(f"ctxp{l}", B * ((p + 511) // 512) * 66)
+            buf(f"add{l}", B, 64)
+        buf("o2", B, dims[1][0] * dims[1][1], 64)
+        buf("o3", B, dims[2][0] * dims[2][1], 64)
+        buf("cat2", B, dims[1][0] * dims[1][1], 96, zero=True)
+        buf("fuse", B, P, 96, zero=True)
+        buf("f1", B, P, 64)
+        buf("f2", B, P, 64)
+        buf("up1", B, 4 * P, 64)
+        buf("up2", B, 16 * P, 64)
+        buf("base", B, 16 * P)
+        ws["masks"] = bands.symmetric_half_masks(Q, H, W, device)
+        ws["tw_w"] = bands.twiddles(W, device)
+        ws["tw_h"] = bands.twiddles(H, device)
+        self._ws[key] = ws
+        return ws
+
+    # -------------------------------------------------------------------------------------------
+    # launch helpers
+    # -------------------------------------------------------------------------------------------
+    def _conv(self, pk: _ConvPack, x, ldx, y, ldy, B, H, W, act=C.ACT_NONE, slope=0.0, slope_ptr=0, res=0, ldres=0,
+              res2=0, ldres2=0, nchw=False, cin=None):
+        """x, y, res*: integer device addresses.  `cin`: logical Cin for the direct kernel when the pack
+        was padded for the tensor-core path."""
+        st = self.st
+        self.launches += 1
+        if self.use_tc and pk.tc_ok and not nchw:
+            rc = C.try_call("fcvsr_conv2d_tc", x, ldx, pk.w_tc.data_ptr(), pk.bias.data_ptr() if pk.bias is not None else 0,
+                            res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin, pk.cout, pk.k, act, slope, slope_ptr,
+                            int(pk.ps), st)
+            if rc == 0:
+                self.tc_launches += 1
+                return
+            if rc != C.ERR_UNSUPPORTED:
+                raise RuntimeError(f"fcvsr_conv2d_tc failed with status {rc}")
+        C.call("fcvsr_conv2d_direct", x, ldx, int(nchw), pk.w_direct.data_ptr(),
+               pk.bias.data_ptr() if pk.bias is not None else 0, res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin,
+               pk.cout, pk.k, pk.stride, act, slope, slope_ptr, int(pk.ps), st)
+
+    def _k(self, name, *args):
+        self.launches += 1
+        C.call(name, *args, self.st)
+
+    # -------------------------------------------------------------------------------------------
+    # forward
+    # -------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, T, Cc, H, W = x.shape
+        if T != 7 or Cc != 1:
+            raise ValueError("GShiftNet expects [B, 7, 1, H, W] (Y-channel clips of 7 frames)")
+        if H % 4 or W % 4:
+            raise ValueError("H and W must be multiples of 4 (two stride-2 levels, reference :2671-2672)")
+        if x.dtype != F32:
+            raise TypeError("fcvsr_b200 expects float32 input")
+        x = x.contiguous()
+        dev = x.device
+        with torch.cuda.device(dev):
+            self._ensure_packs(dev)
+            ws = self._workspace(B, H, W, dev)
+            out = torch.empty(B, 1, 4 * H, 4 * W, device=dev, dtype=F32)
+            self.st = torch.cuda.current_stream().cuda_stream
+            self.launches = 0
+            self.tc_launches = 0
+            self._run(x, out, ws, B, H, W)
+        return out
+
+    def _run(self, x, out, ws, B, H, W):
+        m, P = self.model, self.packs
+        A = m.ACNum
+        p = {k: v.data_ptr() for k, v in ws.items()}
+        npix = H * W
+        f = p["feat"]
+        # feat_extract (:2663): NCHW clip -> NHWC 448 channels
+        self._conv(P["feat"], x.data_ptr(), 0, f, 448, B, H, W, nchw=True)
+        # MGAA(f1) -> feat[128:192], MGAA(f3) -> feat[256:320]: cat[o1, f2, o3] (:2720) is then the
+        # contiguous channel slice feat[128:320] and no concatenation is materialised.
+        self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)
+        self._mgaa(ws, p, f + 256 * 4, 448, f + 256 * 4, 448, B, H, W)
+        self._mgaa(ws, p, f + 128 * 4, 448, p["m2"], 64, B, H, W)
+        self._mffr(ws, p, B, H, W)                                   # m2 -> xs0
+        self._conv(P["rc1"], p["xs0"], 64, p["xs1"], 64, B, H, W)                      # :2735
+        self._conv(P["rc2"], p["xs1"], 64, p["xs2"], 64, B, H // 2, W // 2)            # :2736
+        self._scnet(ws, p, B, H, W)
+        self._tail(x, out, ws, p, B, H, W)
+
+    # MGAAbk.forward (:1442-1547) on the 192-channel slice at `src`; result (64 ch) to `dst`
+    def _mgaa(self, ws, p, src, lds, dst, ldd, B, H, W):
+        P, A = self.packs, self.model.ACNum
+        Wf = W // 2 + 1
+        Pf = H * Wf
+        st = self.st
+        spec = p["spec"]
+        RELU = C.ACT_RELU
+        # rfft2 of x1|x2|x3 (:1452-1454)
+        self._k("fcvsr_fft_r2c_w", src, lds, spec, p["tw_w"], B, H, W, 192)
+        self._k("fcvsr_fft_c2c_h", spec, spec, p["tw_h"], 0, B, H, Wf, 192, 0, 1.0)
+        h1, h2, cc = p["h1"], p["h2"], p["cc"]
+        half = B * Pf
+        # convfuse (:1472-1473); the diff skip rides in the last layer's epilogue (res - res2)
+        self._conv(P["fuse0_f"], spec, 384, h1, 128, B, H, Wf, act=RELU)
+        self._conv(P["fuse0_b"], spec + 128 * 4, 384, h1 + half * 128 * 4, 128, B, H, Wf, act=RELU)
+        self._conv(P["fuse2"], h1, 128, h2, 128, 2 * B, H, Wf, act=RELU)
+        self._conv(P["fuse4"], h2, 128, cc, 224, B, H, Wf, res=spec, ldres=384, res2=spec + 128 * 4, ldres2=384)
+        self._conv(P["fuse4"], h2 + half * 128 * 4, 128, cc + half * 224 * 4, 224, B, H, Wf,
+                   res=spec + 256 * 4, ldres=384, res2=spec + 128 * 4, ldres2=384)
+        # convcrt (:1474)
+        self._conv(P["crt0"], spec + 128 * 4, 384, p["simh"], 64, B, H, Wf, act=RELU)
+        self._conv(P["crt2"], p["simh"], 64, p["sim"], 4, B, H, Wf)
+        # CorrBlock lookup (:1475-1483); corr_f feeds both branches (:1487-1488)
+        self._k("fcvsr_corr_gather", spec, 384, 0, 128, cc + 128 * 4, 224, B, H, Wf, 128)
+        self._k("fcvsr_corr_gather", spec, 384, 0, 128, cc + (half * 224 + 128) * 4, 224, B, H, Wf, 128)
+        # convcorr (:1487-1488), both branches as a batch of 2B
+        self._conv(P["corr0"], cc, 224, p["c1"], 64, 2 * B, H, Wf, act=RELU)
+        self._conv(P["corr2"], p["c1"], 64, p["c2"], 64, 2 * B, H, Wf, act=RELU)
+        self._conv(P["corr4"], p["c2"], 64, p["off"], 4, 2 * B, H, Wf)
+        # ConvBlk_i * x2_f_sim for all i (:1494-1498), then irfft2 (:1499-1505)
+        self.launches += 2
+        self._k("fcvsr_offset_blocks", p["off"], P["ob_w1"].data_ptr(), P["ob_w2"].data_ptr(), P["ob_prelu"].data_ptr(),
+                P["ob_ca"].data_ptr(), p["sim"], 4, p["t1"], p["t2"], p["ob_partial"], p["z"], B, H, Wf, A)
+        self._k("fcvsr_fft_c2c_h", p["z"], p["z"], p["tw_h"], 0, B, H, Wf, 4 * A, 1, 1.0)
+        self._k("fcvsr_fft_c2r_w", p["z"], p["offs"], 4 * A, p["tw_w"], B, H, W, 4 * A, 1.0 / (H * W))
+        # kernel predictor (:1522-1523)
+        self._conv(P["kp"], src + 64 * 4, lds, p["kp1"], 64, B, H, W)
+        self._conv(P["F0"], p["kp1"], 64, p["kp2"], 64, B, H, W)
+        self._conv(P["F1"], p["kp2"], 64, p["pk"], A * 192, B, H, W)
+        # IAC (:1526-1527)
+        ping = p["ping"]
+        sz = B * H * W * 64 * 4
+        prev_f, ldpf, prev_b, ldpb = src, lds, src + 128 * 4, lds
+        for i in range(A):
+            if i == A - 1:
+                nf, nb, ldn = p["cat128"], p["cat128"] + 64 * 4, 128
+            else:
+                nf, nb, ldn = ping + (i % 2) * 2 * sz, ping + ((i % 2) * 2 + 1) * sz, 64
+            self._k("fcvsr_iac_step", prev_f, ldpf, prev_b, ldpb, src, lds, src + 128 * 4, lds, nf, ldn, nb, ldn,
+                    p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["pk"] + i * 192 * 4, A * 192, B, H, W)
+            prev_f, ldpf, prev_b, ldpb = nf, ldn, nb, ldn
+        # conv3(cat) + x2 (:1529)
+        self._conv(P["conv3"], p["cat128"], 128, dst, ldd, B, H, W, res=src + 64 * 4, ldres=lds)
+
+    # MultiFreq_Refinment.forward (:2201-2254): m2 -> xs0
+    def _mffr(self, ws, p, B, H, W):
+        P, Q = self.packs, self.model.Freq_Inv
+        Wf = W // 2 + 1
+        npix = H * W
+        nblk = (npix + 255) // 256
+        x = p["m2"]
+        self._k("fcvsr_fft_r2c_w", x, 64, p["specx"], p["tw_w"], B, H, W, 64)
+        self._k("fcvsr_fft_c2c_h", p["specx"], p["specx"], p["tw_h"], 0, B, H, Wf, 64, 0, 1.0)
+        bsz = B * npix * 64 * 4
+        for q in range(Q):      # Split_freq (:2075-2101): band_q = irfft2(spectrum * Msym_q)
+            self._k("fcvsr_fft_c2c_h", p["specx"], p["tmpc"], p["tw_h"], p["masks"] + q * H * Wf * 4, B, H, Wf, 64, 1, 1.0)
+            self._k("fcvsr_fft_c2r_w", p["tmpc"], p["bands"] + q * bsz, 64, p["tw_w"], B, H, W, 64, 1.0 / npix)
+        band = lambda i: p["bands"] + (Q - 1 - i) * bsz            # freq[::-1] (:2204-2205)
+        gate = lambda i: p["gates"] + i * B * 128 * 4
+        inv = 1.0 / npix
+        self._k("fcvsr_chansum64", band(0), 64, p["mf_partial"], B, npix)
+        self._k("fcvsr_reduce_finalize", p["mf_partial"], nblk, 1, inv, 0, 0, 0, p["mean0"], B)
+        de = lambda i, s: P[f"de{i}.{s}"].data_ptr()
+        self._k("fcvsr_divenh_step", 0, 0, 0, 0, 0, 0, 1, 1, band(0), de(0, "a"), de(0, "b"), p["mean0"], p["sb"], p["so"],
+                p["mf_partial"], B, npix)
+        self._k("fcvsr_reduce_finalize", p["mf_partial"], nblk, 1, inv, 1, de(0, "w1"), de(0, "w2"), gate(0), B)
+        for i in range(1, Q):
+            self._k("fcvsr_divenh_step", band(i - 1), de(i - 1, "a"), de(i - 1, "b"), p["mean0"], gate(i - 1),
+                    int(i - 1 == 0), 1, 0, band(i), de(i, "a"), de(i, "b"), 0, p["sb"], p["so"], p["mf_partial"], B, npix)
+            self._k("fcvsr_reduce_finalize", p["mf_partial"], nblk, 2, inv, 1, de(i, "w1"), de(i, "w2"), gate(i), B)
+        self._k("fcvsr_divenh_step", band(Q - 1), de(Q - 1, "a"), de(Q - 1, "b"), p["mean0"], gate(Q - 1), int(Q == 1), 2,
+                0, 0, 0, 0, 0, p["sb"], p["so"], p["mf_partial"], B, npix)
+        self._k("fcvsr_reduce_finalize", p["mf_partial"], nblk, 1, inv, 1, P["mffr.w1"].data_ptr(),
+                P["mffr.w2"].data_ptr(), gate(Q), B)
+        self._k("fcvsr_mffr_final", p["so"], gate(Q), x, 64, p["xs0"], 64, B, npix)
+
+    # SCNetbk (:807-822)
+    def _scnet(self, ws, p, B, H, W):
+        P, G = self.packs, self.model.SCGroupN
+        dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
+        LK = C.ACT_LEAKY
+        for g in range(G):
+            inp = [p[f"xs{l}"] if g == 0 else p[f"cur{l}"] for l in range(3)]
+            for k in range(3):
+                q = f"g{g}.b{k}."
+                src = inp if k == 0 else [p[f"t{l}"] for l in range(3)]
+                for l, (h, w) in enumerate(dims):      # BlockRCB body (:729-751) + RCB (:705-725)
+                    self._conv(P[q + "c0"], src[l], 64, p[f"a128_{l}"], 128, B, h, w, act=LK, slope=0.1)
+                    self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w)
+                    self._conv(P[q + "r0"], p[f"r0{l}"], 64, p[f"c1{l}"], 64, B, h, w, act=LK, slope=0.2)
+                    self._conv(P[q + "r2"], p[f"c1{l}"], 64, p[f"res{l}"], 64, B, h, w)
+                    self.launches += 1
+                    self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
+                            P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w)
+                    self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w)
+                for l in (0, 1):                        # down: 1x1 conv, pooled in level_mix (:753-757)
+                    self._conv(P[q + "down"], p[f"rr{l}"], 64, p[f"td{l}"], 64, B, dims[l][0], dims[l][1])
+                for l in (1, 2):                        # up: 1x1 conv, interpolated in level_mix (:759-763)
+                    self._conv(P[q + "up"], p[f"rr{l}"], 64, p[f"tu{l}"], 64, B, dims[l][0], dims[l][1])
+                # x + r + d + u (:771-776): level 0 has d = r, level 2 has u = r
+                self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0])
+                self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1])
+                self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2])
+            for l, (h, w) in enumerate(dims):           # SCGroupbk tail: x + conv(res) (:797-803)
+                self._conv(P[f"g{g}.conv"], p[f"t{l}"], 64, p[f"cur{l}"], 64, B, h, w, res=inp[l], ldres=64)
+        # SCNetbk skip (:816-822): level 0 lands in the 84(96)-channel fuse buffer
+        self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], 96, p["cur0"], 1.0, 0, 0, B, *dims[0])
+        self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1])
+        self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2])
+
+    # pyramid fuse + up-sampler (:2739-2751)
+    def _tail(self, x, out, ws, p, B, H, W):
+        P = self.packs
+        h2, w2, h3, w3 = H // 2, W // 2, H // 4, W // 4
+        PR = C.ACT_PRELU
+        sl = P["prelu"].data_ptr()
+        cat2, fuse = p["cat2"], p["fuse"]
+        # out_L3 -> PS -> cat2[64:80] (L2 res) -> PS -> fuse[80:84]
+        self._conv(P["up_l3"], p["o3"], 64, cat2 + 64 * 4, 96, B, h3, w3, act=PR, slope_ptr=sl)
+        self._k("fcvsr_pixel_shuffle", cat2 + 64 * 4, 96, fuse + 80 * 4, 96, B, h2, w2, 4)
+        # out_L2 (kept in shuffle order) -> cat2[0:64]
+        self._conv(P["up_l2"], p["o2"], 64, cat2, 96, B, h2, w2, act=PR, slope_ptr=sl)
+        # PS(out_L2 + upconv1_L2_2(cat)) -> fuse[64:80]
+        self._conv(P["up_l2_2"], cat2, 96, fuse + 64 * 4, 96, B, h2, w2, res=cat2, ldres=96)
+        self._conv(P["fuse"], fuse, 96, p["f1"], 64, B, H, W)
+        self._conv(P["rec0"], p["f1"], 64, p["f2"], 64, B, H, W)
+        self._conv(P["up1"], p["f2"], 64, p["up1"], 64, B, H, W, act=PR, slope_ptr=sl)
+        self._conv(P["up2"], p["up1"], 64, p["up2"], 64, B, 2 * H, 2 * W, act=PR, slope_ptr=sl)
+        # bilinear x4 of the centre LR frame (:2750) rides in conv_last0's epilogue as the residual
+        self._k("fcvsr_bilinear_up4", x.data_ptr() + 3 * H * W * 4, 7 * H * W, p["base"], B, H, W)
+        self._conv(P["last"], p["up2"], 64, out.data_ptr(), 1, B, 4 * H, 4 * W, res=p["base"], ldres=1)

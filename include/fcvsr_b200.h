@@ -1,0 +1,144 @@
+/* fcvsr_b200 -- C ABI of the B200-native FCVSR forward kernels (libfcvsr_b200.so).
+ *
+ * Plain pointers and sizes only: every pointer is a DEVICE pointer to fp32 data unless stated,
+ * the caller owns all buffers (nothing here allocates), every call enqueues work on `stream` and
+ * returns immediately with FCVSR_OK (0) or a negative error code.  This is the boundary the Python
+ * host layer (fcvsr_b200/_capi.py, ctypes) binds, and the one a maintainer of the reference would
+ * bind in place of the ATen / deform_conv_cuda calls cited per entry.
+ *
+ * Tensor layout: NHWC ("pixel-major") fp32.  Element (b,y,x,c) of a tensor with pixel stride `ld`
+ * lives at base[((b*H + y)*W + x)*ld + c]; a channel slice is base+offset with the same ld.
+ * Spectra are complex-interleaved NHWC: [B,H,Wf,C] float2, Wf = W/2+1.
+ *
+ * Reference files are relative to /root/reference (QZ1-boy/FCVSR).
+ */
+#ifndef FCVSR_B200_H
+#define FCVSR_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCVSR_OK 0
+#define FCVSR_ERR_ARG (-1)          /* invalid argument / unsupported shape */
+#define FCVSR_ERR_CUDA (-2)         /* a CUDA runtime call or launch failed */
+#define FCVSR_ERR_UNSUPPORTED (-3)  /* shape outside the kernel's envelope (caller must use another entry) */
+
+#define FCVSR_ACT_NONE 0
+#define FCVSR_ACT_RELU 1
+#define FCVSR_ACT_LEAKY 2 /* slope by value */
+#define FCVSR_ACT_PRELU 3 /* slope read from device scalar slope_ptr (nn.PReLU weight) */
+
+/* ---- convolutions --------------------------------------------------------------------------- */
+
+/* Generic NHWC convolution on the CUDA cores: y = act(conv(x,w)+bias) + res - res2, optionally stored
+ * through pixel_shuffle(2) (columns then ordered (i,j,c), y is [B,2Ho,2Wo,ldy]).  Padding k/2.
+ * w packed [k*k][Cin][Cout].  x may be NCHW (x_nchw=1, ldx ignored).
+ * Replaces F.conv2d at CVSR_train/arch/CVSR_freq.py:2663 (feat_extract), :2671-2672 (stride 2),
+ * :2684 (conv_last0), :1380-1395 (per-bin MLP heads) and is the fp32 cross-check of the tensor-core
+ * kernel. */
+int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const float* w, const float* bias,
+                        const float* res, int ldres, const float* res2, int ldres2, float* y, int ldy,
+                        int B, int H, int W, int Cin, int Cout, int ksize, int stride, int act, float slope,
+                        const float* slope_ptr, int pixel_shuffle, cudaStream_t stream);
+
+/* tcgen05/TMEM implicit-GEMM convolution fed by TMA (stride 1, k in {1,3}, Cin % 32 == 0, Cout % 16 == 0,
+ * Cout <= 256), TF32 operands / fp32 accumulate, same fused epilogue as above.
+ * w packed [Cout][k*k][Cin] (K-major).  x, y, w, res must be 16-byte aligned, ld multiples of 4.
+ * Replaces every 3x3 / 1x1 nn.Conv2d of MGAAbk (CVSR_freq.py:1371-1430), SCNetbk (:705-822) and the
+ * up-sampling tail (:2739-2749).  Returns FCVSR_ERR_UNSUPPORTED for shapes outside the envelope. */
+int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
+                    const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
+                    int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
+                    cudaStream_t stream);
+
+/* ---- FFT (torch.fft.rfft2 / irfft2 / fftn / ifftn of CVSR_freq.py:1452-1454, :1499-1504, :2082-2088) */
+
+/* tw: float2[N] = exp(-2 pi i k / N) for the transform length N (W for *_w, H for *_h). */
+int fcvsr_fft_r2c_w(const float* x, int ldx, float* out_c, const float* tw, int B, int H, int W, int C,
+                    cudaStream_t stream);
+/* in/out complex [B,H,Wf,C] (C complex channels); optional real mask [H*Wf] multiplied at load;
+ * in == out allowed.  inverse: 0 forward, 1 inverse (unnormalised); result * scale. */
+int fcvsr_fft_c2c_h(const float* in_c, float* out_c, const float* tw, const float* mask, int B, int H, int Wf,
+                    int C, int inverse, float scale, cudaStream_t stream);
+/* complex [B,H,Wf,C] -> real [B,H,W,ldy] (C real channels), torch c2r semantics, result * scale. */
+int fcvsr_fft_c2r_w(const float* in_c, float* y, int ldy, const float* tw, int B, int H, int W, int C,
+                    float scale, cudaStream_t stream);
+
+/* ---- MGAAbk (CVSR_freq.py:1365-1547) ----------------------------------------------------------- */
+
+/* CorrBlock lookup (:1279-1337): S [B,H*Wf,ldS] floats with the two packed spectra at float offsets
+ * a_off / b_off (C2 floats each, complex-interleaved); out [B,H*Wf,ldo], 81 channels. */
+int fcvsr_corr_gather(const float* S, int ldS, int a_off, int b_off, float* out, int ldo, int B, int H, int Wf,
+                      int C2, cudaStream_t stream);
+
+/* ConvBlk(4, index=i) for i < A and both directions (:344-357, :1494-1498):
+ * off [2][B][H*Wf][4] (dir-major), w1/w2 packed per iteration [k*k][ci][co] back to back, prelu [A],
+ * ca_w [A][2][4][4], sim [B,H*Wf,ldsim] (4 ch).  Scratch t1,t2 [A][2][B][H*Wf][4], partial
+ * [A][2B][ceil(H*Wf/128)][4].  z: complex [B,H*Wf,4A], channel (i*2+dir)*2+m = (v[m], v[2+m]). */
+int fcvsr_offset_blocks(const float* off, const float* w1, const float* w2, const float* prelu,
+                        const float* ca_w, const float* sim, int ldsim, float* t1, float* t2, float* partial,
+                        float* z, int B, int H, int Wf, int A, cudaStream_t stream);
+
+/* One IAC iteration (:1230-1250 = flow_warp :1188-1227 + SAC :1253-1276 + residual + LeakyReLU 0.1) for
+ * the forward (f) and backward (b) neighbour, 64 channels.  offs [B,H,W,ldoffs]: (dx,dy) at channel
+ * ch_f / ch_b.  taps [B,H,W,ldtaps]: 192 channels [t][c] of this iteration. */
+int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int ldprev_b, const float* xin_f,
+                   int ldxin_f, const float* xin_b, int ldxin_b, float* next_f, int ldnext_f, float* next_b,
+                   int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps, int ldtaps,
+                   int B, int H, int W, cudaStream_t stream);
+
+/* ---- MultiFreq_Refinment (CVSR_freq.py:2104-2133, :2183-2254) ---------------------------------- */
+
+int fcvsr_chansum64(const float* x, int ldx, float* partial, int B, int P, cudaStream_t stream);
+/* partial [B][nblk][128] -> out [B][128]: mode 0 mean, mode 1 CALayer gate sigmoid(W2 relu(W1 mean)) */
+int fcvsr_reduce_finalize(const float* partial, int nblk, int nvec, float inv_count, int mode, const float* w1,
+                          const float* w2, float* out, int B, cudaStream_t stream);
+/* apply DivEnh step i-1 (x_prev != NULL) and reduce step i (mode 1) or sum So (mode 2); see mffr.cu */
+int fcvsr_divenh_step(const float* x_prev, const float* a_prev, const float* b_prev, const float* mean_prev,
+                      const float* gate_prev, int prev_is_first, int mode, int cur_is_first, const float* x_cur,
+                      const float* a_cur, const float* b_cur, const float* mean_cur, float* sb, float* so,
+                      float* partial, int B, int P, cudaStream_t stream);
+int fcvsr_mffr_final(const float* so, const float* gate, const float* x, int ldx, float* y, int ldy, int B, int P,
+                     cudaStream_t stream);
+
+/* ---- SCNetbk helpers (CVSR_freq.py:657-777) ----------------------------------------------------- */
+
+/* ContextBlock (:657-701): add[b][64] = W2 lrelu_0.2(W1 softmax-pool(x)); partial [B][ceil(P/512)][66] */
+int fcvsr_context_block(const float* x, int ldx, const float* wmask, const float* w1, const float* w2,
+                        float* partial, float* add, int B, int P, cudaStream_t stream);
+/* RCB tail (:720-724): r = lrelu_0.2(res + add[b]) + r0 (64 ch, ld 64) */
+int fcvsr_rcb_finish(const float* res, const float* add, const float* r0, float* r, int B, int P,
+                     cudaStream_t stream);
+/* BlockRCB cross-level sum (:766-777): xout = xin + coef*r + mean2x2(td[B,2H,2W,64]) + bilinear_x2(tu[B,H/2,W/2,64]) */
+int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float* r, float coef, const float* td,
+                    const float* tu, int B, int H, int W, cudaStream_t stream);
+
+/* ---- tail (CVSR_freq.py:2739-2751) -------------------------------------------------------------- */
+int fcvsr_pixel_shuffle(const float* in, int ldi, float* out, int ldo, int B, int H, int W, int Co,
+                        cudaStream_t stream);
+int fcvsr_bilinear_up4(const float* in, long long bstride, float* out, int B, int H, int W, cudaStream_t stream);
+int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npix, cudaStream_t stream);
+
+/* ---- deformable convolution operator (CVSR_train/ops/dcn) --------------------------------------- */
+
+/* Fused bilinear-gather + GEMM modulated deformable convolution forward, NCHW fp32 exactly as the
+ * reference extension: replaces modulated_deform_conv_cuda_forward (ops/dcn/src/deform_conv_cuda.cpp:486-564;
+ * call site ops/dcn/deform_conv.py:144-148) and, with mask == NULL, deform_conv_forward_cuda (:151-258;
+ * call site deform_conv.py:52-57).  No column buffer: `columns`/`ones` scratch of the reference ABI are
+ * not needed.  offset [B, dg*2*kh*kw, Ho, Wo] (dh, dw interleaved per tap), mask [B, dg*kh*kw, Ho, Wo]. */
+int fcvsr_modulated_deform_conv_forward(const float* input, const float* weight, const float* bias,
+                                        const float* offset, const float* mask, float* output, int B, int Cin,
+                                        int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w,
+                                        int pad_h, int pad_w, int dil_h, int dil_w, int groups,
+                                        int deformable_groups, cudaStream_t stream);
+
+/* library / build info: returns a static string "fcvsr_b200 <version> sm_100a" */
+const char* fcvsr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCVSR_B200_H */

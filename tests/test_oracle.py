@@ -1,0 +1,100 @@
+"""CPU tests: the oracle restatement is pinned to the reference's own outputs (tests/golden, produced by
+oracle/make_golden.py from the unmodified reference) and to the reference's known-answer tests."""
+import json
+import os
+
+import pytest
+import torch
+
+from fcvsr_b200.arch import GShiftNet, GShiftNet_S, seeded_state_dict
+from oracle import fcvsr_oracle as O
+from oracle import ref_loader
+from tests.util import GOLD, load_golden, make_clip
+
+
+@pytest.mark.parametrize("name", ["fcvsr_s_64", "fcvsr_s_36x40"])
+def test_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    c = g["case"]
+    sd = seeded_state_dict(c["variant"], c["seed"])
+    x = make_clip(c["clip_seed"], c["b"], c["h"], c["w"])
+    with torch.no_grad():
+        y, taps = O.forward(sd, x, return_taps=True)
+    assert (y - g["out"]).abs().max().item() <= 2e-5
+    for k in ("mgaa1", "mgaa2", "mffr", "sc_l1", "fuse"):
+        assert (taps[k][..., ::4, ::4] - g[k]).abs().max().item() <= 5e-5, k
+    assert (taps["sc_l3"] - g["sc_l3"]).abs().max().item() <= 5e-5
+
+
+def test_oracle_matches_reference_golden_full():
+    g = load_golden("fcvsr_full_64")
+    c = g["case"]
+    sd = seeded_state_dict(c["variant"], c["seed"])
+    x = make_clip(c["clip_seed"], c["b"], c["h"], c["w"])
+    with torch.no_grad():
+        y = O.forward(sd, x)
+    assert (y - g["out"]).abs().max().item() <= 2e-5
+
+
+def test_state_dict_matches_reference_keys_and_shapes():
+    """Drop-in contract: same keys, order and shapes as the reference state_dict, including
+    the aliased RCB / body.3 entries."""
+    with open(os.path.join(GOLD, "state_dict_shapes.json")) as f:
+        ref = json.load(f)
+    for variant, cls in (("S", GShiftNet_S), ("full", GShiftNet)):
+        sd = cls().state_dict()
+        mine = [[k, list(v.shape)] for k, v in sd.items()]
+        assert mine == ref[variant]
+        k0 = "recorb1.body.0.body.0"
+        assert sd[k0 + ".RCB.body.0.weight"].data_ptr() == sd[k0 + ".body.3.body.0.weight"].data_ptr()
+    assert sum(p.numel() for p in GShiftNet().parameters()) == 8811336
+    assert sum(p.numel() for p in GShiftNet_S().parameters()) == 3704709
+
+
+def test_dcn_oracle_known_answer():
+    """ops/dcn/simple_check.py:8-22 (the reference's only KAT on this path)."""
+    with open(os.path.join(GOLD, "dcn_simple_check.json")) as f:
+        kat = json.load(f)
+    x = torch.tensor(kat["input"])
+    off = torch.tensor(kat["offset18"], dtype=torch.float32).view(1, 18, 1, 1).repeat(1, 2, 3, 3)
+    w = torch.ones(1, 2, 3, 3)
+    y = O.modulated_deform_conv(x, off, None, w, padding=1, deformable_groups=2)
+    assert torch.equal(y.flatten(), torch.tensor(kat["expected"], dtype=torch.float32))
+
+
+def test_dcn_oracle_matches_torchvision():
+    """torchvision.ops.deform_conv2d shares the reference's offset/mask layout."""
+    tv = pytest.importorskip("torchvision.ops")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 8, 9, 11, generator=g)
+    w = torch.randn(6, 4, 3, 3, generator=g)
+    b = torch.randn(6, generator=g)
+    off = 2.5 * torch.randn(2, 4 * 18, 9, 11, generator=g)
+    msk = torch.rand(2, 4 * 9, 9, 11, generator=g)
+    y = O.modulated_deform_conv(x, off, msk, w, b, padding=1, groups=2, deformable_groups=4)
+    ref = tv.deform_conv2d(x, off, w, b, padding=1, mask=msk)
+    assert (y - ref).abs().max().item() < 1e-4
+
+
+def test_flow_warp_integer_shift():
+    """mmedit_train/tests/test_models/test_common/test_flow_warp.py:31-52: flow = -1 is an exact
+    one-pixel shift with zero fill."""
+    x = torch.arange(16.0).view(1, 1, 4, 4)
+    flow = -torch.ones(1, 2, 4, 4)
+    y = O.warp_bilinear(x, flow)
+    ref = torch.zeros_like(x)
+    ref[..., 1:, 1:] = x[..., :-1, :-1]
+    assert torch.allclose(y, ref, atol=1e-6)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_oracle_blocks_against_live_reference():
+    ref = ref_loader.load()
+    g = torch.Generator().manual_seed(11)
+    feat = torch.randn(1, 64, 12, 16, generator=g)
+    taps = torch.randn(1, 192, 12, 16, generator=g)
+    assert torch.allclose(O.sac(feat, taps), ref.SAC(feat, taps, torch.zeros_like(taps), 3), atol=1e-6)
+    a = torch.randn(1, 128, 10, 9, generator=g)
+    b = torch.randn(1, 128, 10, 9, generator=g)
+    coords = ref.coords_grid(1, 10, 9, "cpu")
+    assert torch.allclose(O.corr_lookup(a, b), ref.CorrBlock(a, b)(coords), atol=1e-5)
