@@ -19,7 +19,7 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.
 
 # name -> argument codes, in the order of include/fcvsr_b200.h
 SIGNATURES = {
-    "fcvsr_conv2d_direct": "pii pp pi pi pi iiiiiii if p i s",
+    "fcvsr_conv2d_direct": "pii pp pi pi pi iiiiiii if p ii s",
     "fcvsr_conv2d_tc": "pi pp pi pi pi iiiiii if p i s",
     "fcvsr_fft_r2c_w": "pi p p iiii s",
     "fcvsr_fft_c2c_h": "p p p p iiii i f s",
@@ -37,7 +37,7 @@ SIGNATURES = {
     "fcvsr_pixel_shuffle": "pi pi iiii s",
     "fcvsr_bilinear_up4": "p l p iii s",
     "fcvsr_fill_channels": "p iii f l s",
-    "fcvsr_modulated_deform_conv_forward": "ppppp p iiii i ii ii ii ii ii s",
+    "fcvsr_modulated_deform_conv_forward": "ppppp p iiii i ii ii ii ii ii ll i s",
 }
 
 _lib = None

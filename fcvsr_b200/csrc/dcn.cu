@@ -17,6 +17,8 @@
 struct DcnArgs {
     const float* x; const float* w; const float* bias; const float* offset; const float* mask; float* y;
     int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, groups, dg, Ho, Wo;
+    long long off_bs, mask_bs;   // batch strides (elements) of offset / mask
+    int mask_sigmoid;
 };
 
 __device__ __forceinline__ float dcn_sample(const float* __restrict__ img, int H, int W, float h, float w) {
@@ -64,12 +66,16 @@ __global__ void __launch_bounds__(256) dcn_forward_kernel(DcnArgs a) {
                 const int c = grp * cin_g + k / kk2, tap = k % kk2;
                 const int i = tap / a.kw, j = tap - i * a.kw;
                 const int g = c / ch_per_dg;
-                const size_t obase = (((size_t)b * a.dg + g) * 2 * kk2 + 2 * tap) * P + p;
+                const size_t obase = (size_t)b * a.off_bs + ((size_t)g * 2 * kk2 + 2 * tap) * P + p;
                 const float oh = a.offset[obase], ow = a.offset[obase + P];
                 const float hs = (float)(ho * a.sh - a.ph + i * a.dh) + oh;
                 const float ws_ = (float)(wo * a.sw - a.pw + j * a.dw) + ow;
                 v = dcn_sample(a.x + ((size_t)b * a.Cin + c) * a.H * a.W, a.H, a.W, hs, ws_);
-                if (a.mask) v *= a.mask[(((size_t)b * a.dg + g) * kk2 + tap) * P + p];
+                if (a.mask) {
+                    float mk = a.mask[(size_t)b * a.mask_bs + ((size_t)g * kk2 + tap) * P + p];
+                    if (a.mask_sigmoid) mk = 1.f / (1.f + __expf(-mk));
+                    v *= mk;
+                }
             }
             As[lk + u][lp] = v;
         }
@@ -114,7 +120,8 @@ extern "C" int fcvsr_modulated_deform_conv_forward(const float* input, const flo
                                                    const float* offset, const float* mask, float* output, int B,
                                                    int Cin, int H, int W, int Cout, int kh, int kw, int stride_h,
                                                    int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups,
-                                                   int deformable_groups, cudaStream_t st) {
+                                                   int deformable_groups, long long offset_batch_stride,
+                                                   long long mask_batch_stride, int mask_sigmoid, cudaStream_t st) {
     if (!input || !weight || !offset || !output) return FCVSR_ERR_ARG;
     if (B <= 0 || groups <= 0 || deformable_groups <= 0 || Cin % groups || Cout % groups || Cin % deformable_groups)
         return FCVSR_ERR_ARG;
@@ -125,6 +132,9 @@ extern "C" int fcvsr_modulated_deform_conv_forward(const float* input, const flo
     a.Ho = (H + 2 * pad_h - (dil_h * (kh - 1) + 1)) / stride_h + 1;
     a.Wo = (W + 2 * pad_w - (dil_w * (kw - 1) + 1)) / stride_w + 1;
     if (a.Ho <= 0 || a.Wo <= 0) return FCVSR_ERR_ARG;
+    a.off_bs = offset_batch_stride > 0 ? offset_batch_stride : (long long)deformable_groups * 2 * kh * kw * a.Ho * a.Wo;
+    a.mask_bs = mask_batch_stride > 0 ? mask_batch_stride : (long long)deformable_groups * kh * kw * a.Ho * a.Wo;
+    a.mask_sigmoid = mask_sigmoid;
     const int cout_g = Cout / groups;
     dim3 grid((a.Ho * a.Wo + DC_TP - 1) / DC_TP, groups * ((cout_g + DC_TN - 1) / DC_TN), B);
     dcn_forward_kernel<<<grid, 256, 0, st>>>(a);

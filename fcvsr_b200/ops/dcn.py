@@ -1,0 +1,208 @@
+"""Deformable-convolution operator with the signature of the reference's CVSR_train/ops/dcn/deform_conv.py.
+
+    deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
+                im2col_step=64)                                                     (deform_conv.py:17-26,186)
+    modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1,
+                          groups=1, deformable_groups=1)                            (deform_conv.py:117-127,187)
+    DeformConv / DeformConvPack / ModulatedDeformConv / ModulatedDeformConvPack     (deform_conv.py:190-337)
+
+Same tensor contract (NCHW contiguous fp32 CUDA tensors; offset [B, dg*2*kh*kw, Ho, Wo] with (dh, dw)
+interleaved per tap; mask [B, dg*kh*kw, Ho, Wo]; NotImplementedError on CPU, :46-47,:136-137).  The native
+entry it binds is ``fcvsr_modulated_deform_conv_forward`` (include/fcvsr_b200.h), a fused gather + GEMM
+kernel that replaces deform_conv_forward_cuda / modulated_deform_conv_cuda_forward
+(ops/dcn/src/deform_conv_cuda.cpp:151,486) without the HBM column buffer.  ``im2col_step`` is accepted for
+API compatibility (v1 still validates that it divides the batch, :49-51) but there is no column buffer
+to chunk.  Forward only in this round: tensors that require grad raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+from torch.nn.modules.utils import _pair
+
+from .. import _capi as C
+
+
+def _check(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise NotImplementedError("deformable convolution is CUDA-only (as the reference, deform_conv.py:46-47)")
+        if t.dtype != torch.float32:
+            raise TypeError("fcvsr_b200 DCN kernels are fp32")
+        if torch.is_grad_enabled() and t.requires_grad:
+            raise NotImplementedError("fcvsr_b200: DCN backward kernels are not implemented in this round; "
+                                      "call under torch.no_grad()")
+
+
+def _out_hw(h, w, kh, kw, stride, padding, dilation):
+    ho = (h + 2 * padding[0] - (dilation[0] * (kh - 1) + 1)) // stride[0] + 1
+    wo = (w + 2 * padding[1] - (dilation[1] * (kw - 1) + 1)) // stride[1] + 1
+    if ho <= 0 or wo <= 0:
+        raise ValueError("convolution input is too small")
+    return ho, wo
+
+
+def _launch(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, off_bs=0, mask_bs=0, sigmoid=0):
+    b, cin, h, w = x.shape
+    cout, cin_g, kh, kw = weight.shape
+    if cin_g * groups != cin:
+        raise ValueError("weight shape does not match input channels / groups")
+    ho, wo = _out_hw(h, w, kh, kw, stride, padding, dilation)
+    y = x.new_empty(b, cout, ho, wo)
+    st = torch.cuda.current_stream().cuda_stream
+    with torch.cuda.device(x.device):
+        C.call("fcvsr_modulated_deform_conv_forward", x.data_ptr(), weight.data_ptr(),
+               bias.data_ptr() if bias is not None else 0, offset.data_ptr(), mask.data_ptr() if mask is not None else 0,
+               y.data_ptr(), b, cin, h, w, cout, kh, kw, stride[0], stride[1], padding[0], padding[1], dilation[0],
+               dilation[1], groups, dg, off_bs, mask_bs, sigmoid, st)
+    return y
+
+
+def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64):
+    if input is not None and input.dim() != 4:
+        raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
+    _check(input, offset, weight)
+    cur = min(im2col_step, input.shape[0])
+    assert input.shape[0] % cur == 0, "im2col step must divide batchsize"
+    stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)
+    kh, kw = weight.shape[2:]
+    ho, wo = _out_hw(input.shape[2], input.shape[3], kh, kw, stride, padding, dilation)
+    if tuple(offset.shape) != (input.shape[0], deformable_groups * 2 * kh * kw, ho, wo):
+        raise ValueError(f"invalid offset shape {tuple(offset.shape)}")
+    return _launch(input.contiguous(), offset.contiguous(), None, weight.contiguous(), None, stride, padding, dilation,
+                   groups, deformable_groups)
+
+
+def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                          deformable_groups=1):
+    _check(input, offset, mask, weight, bias)
+    stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)   # scalars in the reference (:179-182)
+    kh, kw = weight.shape[2:]
+    ho, wo = _out_hw(input.shape[2], input.shape[3], kh, kw, stride, padding, dilation)
+    if tuple(offset.shape) != (input.shape[0], deformable_groups * 2 * kh * kw, ho, wo):
+        raise ValueError(f"invalid offset shape {tuple(offset.shape)}")
+    if tuple(mask.shape) != (input.shape[0], deformable_groups * kh * kw, ho, wo):
+        raise ValueError(f"invalid mask shape {tuple(mask.shape)}")
+    return _launch(input.contiguous(), offset.contiguous(), mask.contiguous(), weight.contiguous(),
+                   bias.contiguous() if bias is not None else None, stride, padding, dilation, groups, deformable_groups)
+
+
+def _offset_conv(x, conv: nn.Conv2d):
+    """conv_offset / conv_offset_mask of the *Pack modules (deform_conv.py:243-250,:315-323) on our own
+    convolution kernel (NCHW in, NCHW out)."""
+    _check(x, conv.weight, conv.bias)
+    w = conv.weight.detach()
+    cout, cin, kh, kw = w.shape
+    if kh != kw or conv.stride[0] != conv.stride[1] or conv.padding[0] != kh // 2 or conv.padding[1] != kw // 2:
+        raise NotImplementedError("conv_offset: only square kernels with 'same' padding k//2 are supported")
+    b, _, h, wd = x.shape
+    s = conv.stride[0]
+    ho, wo = (h + 2 * (kh // 2) - kh) // s + 1, (wd + 2 * (kw // 2) - kw) // s + 1
+    y = x.new_empty(b, cout, ho, wo)
+    wp = w.permute(2, 3, 1, 0).contiguous()
+    with torch.cuda.device(x.device):
+        C.call("fcvsr_conv2d_direct", x.data_ptr(), 0, 1, wp.data_ptr(), conv.bias.data_ptr() if conv.bias is not None else 0,
+               0, 0, 0, 0, y.data_ptr(), 0, b, h, wd, cin, cout, kh, s, C.ACT_NONE, 0.0, 0, 0, 1,
+               torch.cuda.current_stream().cuda_stream)
+    return y
+
+
+class DeformConv(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=False):
+        super().__init__()
+        assert not bias
+        assert in_channels % groups == 0, "in_channels {} cannot be divisible by groups {}".format(in_channels, groups)
+        assert out_channels % groups == 0, "out_channels {} cannot be divisible by groups {}".format(out_channels, groups)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride, self.padding, self.dilation = _pair(stride), _pair(padding), _pair(dilation)
+        self.groups, self.deformable_groups = groups, deformable_groups
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, *self.kernel_size))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels * self.kernel_size[0] * self.kernel_size[1]
+        stdv = 1.0 / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def forward(self, x, offset):
+        return deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                           self.deformable_groups)
+
+
+class DeformConvPack(DeformConv):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.conv_offset = nn.Conv2d(self.in_channels, self.deformable_groups * 2 * self.kernel_size[0] * self.kernel_size[1],
+                                     kernel_size=self.kernel_size, stride=_pair(self.stride), padding=_pair(self.padding),
+                                     bias=True)
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+
+    def forward(self, x):
+        offset = _offset_conv(x, self.conv_offset)
+        return deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                           self.deformable_groups)
+
+
+class ModulatedDeformConv(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.groups, self.deformable_groups = groups, deformable_groups
+        self.with_bias = bias
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, *self.kernel_size))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels * self.kernel_size[0] * self.kernel_size[1]
+        stdv = 1.0 / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.zero_()
+
+    def forward(self, x, offset, mask):
+        return modulated_deform_conv(x, offset, mask, self.weight, self.bias, self.stride, self.padding, self.dilation,
+                                     self.groups, self.deformable_groups)
+
+
+class ModulatedDeformConvPack(ModulatedDeformConv):
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.conv_offset_mask = nn.Conv2d(self.in_channels,
+                                          self.deformable_groups * 3 * self.kernel_size[0] * self.kernel_size[1],
+                                          kernel_size=self.kernel_size, stride=_pair(self.stride),
+                                          padding=_pair(self.padding), bias=True)
+        self.conv_offset_mask.weight.data.zero_()
+        self.conv_offset_mask.bias.data.zero_()
+
+    def forward(self, x):
+        """chunk -> cat(o1, o2) -> sigmoid(mask) (:331-334) are fused away: offset is the first 2/3 of the
+        conv_offset_mask output, the mask the last third (sigmoid applied inside the DCN kernel)."""
+        _check(x, self.weight, self.bias)
+        out = _offset_conv(x, self.conv_offset_mask)
+        b, c3, ho, wo = out.shape
+        kk = self.kernel_size[0] * self.kernel_size[1]
+        n_off = self.deformable_groups * 2 * kk
+        mask = out.view(b, -1)[:, n_off * ho * wo:]
+        stride, padding, dilation = _pair(self.stride), _pair(self.padding), _pair(self.dilation)
+        y = x.new_empty(b, self.out_channels, ho, wo)
+        with torch.cuda.device(x.device):
+            C.call("fcvsr_modulated_deform_conv_forward", x.contiguous().data_ptr(), self.weight.data_ptr(),
+                   self.bias.data_ptr() if self.bias is not None else 0, out.data_ptr(), mask.data_ptr(), y.data_ptr(), b,
+                   self.in_channels, x.shape[2], x.shape[3], self.out_channels, self.kernel_size[0], self.kernel_size[1],
+                   stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], self.groups,
+                   self.deformable_groups, c3 * ho * wo, c3 * ho * wo, 1, torch.cuda.current_stream().cuda_stream)
+        return y

@@ -35,14 +35,14 @@ extern "C" {
 
 /* Generic NHWC convolution on the CUDA cores: y = act(conv(x,w)+bias) + res - res2, optionally stored
  * through pixel_shuffle(2) (columns then ordered (i,j,c), y is [B,2Ho,2Wo,ldy]).  Padding k/2.
- * w packed [k*k][Cin][Cout].  x may be NCHW (x_nchw=1, ldx ignored).
+ * w packed [k*k][Cin][Cout].  x may be NCHW (x_nchw=1, ldx ignored), y may be NCHW (y_nchw=1, ldy ignored).
  * Replaces F.conv2d at CVSR_train/arch/CVSR_freq.py:2663 (feat_extract), :2671-2672 (stride 2),
  * :2684 (conv_last0), :1380-1395 (per-bin MLP heads) and is the fp32 cross-check of the tensor-core
  * kernel. */
 int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const float* w, const float* bias,
                         const float* res, int ldres, const float* res2, int ldres2, float* y, int ldy,
                         int B, int H, int W, int Cin, int Cout, int ksize, int stride, int act, float slope,
-                        const float* slope_ptr, int pixel_shuffle, cudaStream_t stream);
+                        const float* slope_ptr, int pixel_shuffle, int y_nchw, cudaStream_t stream);
 
 /* tcgen05/TMEM implicit-GEMM convolution fed by TMA (stride 1, k in {1,3}, Cin % 32 == 0, Cout % 16 == 0,
  * Cout <= 256), TF32 operands / fp32 accumulate, same fused epilogue as above.
@@ -128,12 +128,16 @@ int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npi
  * reference extension: replaces modulated_deform_conv_cuda_forward (ops/dcn/src/deform_conv_cuda.cpp:486-564;
  * call site ops/dcn/deform_conv.py:144-148) and, with mask == NULL, deform_conv_forward_cuda (:151-258;
  * call site deform_conv.py:52-57).  No column buffer: `columns`/`ones` scratch of the reference ABI are
- * not needed.  offset [B, dg*2*kh*kw, Ho, Wo] (dh, dw interleaved per tap), mask [B, dg*kh*kw, Ho, Wo]. */
+ * not needed.  offset [B, dg*2*kh*kw, Ho, Wo] (dh, dw interleaved per tap), mask [B, dg*kh*kw, Ho, Wo].
+ * offset_batch_stride / mask_batch_stride (elements, 0 = dense) let offset and mask be channel slices of
+ * one conv_offset_mask output (ModulatedDeformConvPack, deform_conv.py:330-337); mask_sigmoid=1 applies
+ * the sigmoid of :334 on the fly. */
 int fcvsr_modulated_deform_conv_forward(const float* input, const float* weight, const float* bias,
                                         const float* offset, const float* mask, float* output, int B, int Cin,
                                         int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w,
                                         int pad_h, int pad_w, int dil_h, int dil_w, int groups,
-                                        int deformable_groups, cudaStream_t stream);
+                                        int deformable_groups, long long offset_batch_stride,
+                                        long long mask_batch_stride, int mask_sigmoid, cudaStream_t stream);
 
 /* library / build info: returns a static string "fcvsr_b200 <version> sm_100a" */
 const char* fcvsr_version(void);

@@ -1,0 +1,277 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C ABI of libfcvsr_b200.so and is
+compared with the CPU oracle (oracle/fcvsr_oracle.py) and with the committed golden vectors produced
+by the unmodified reference (tests/golden).
+
+Tolerances (BASELINE.json north_star / SURVEY 8d):
+  * fp32 CUDA-core path (``use_tc=False``): max-abs <= 2e-5 on the unclamped output.
+  * TF32 tensor-core path (default; fp32 storage, TF32 operands, fp32 accumulate) -- the "fp32" mode of
+    the contract: max-abs <= 1e-3 and |PSNR(ours,T) - PSNR(ref,T)| <= 0.01 dB.
+"""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from fcvsr_b200 import _capi as C, arch, bands
+from fcvsr_b200.engine import Engine, _ConvPack
+from oracle import fcvsr_oracle as O
+from tests.util import GOLD, load_golden, make_clip, nchw, nhwc, psnr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _model(variant, sd, dev, use_tc=True):
+    m = (arch.GShiftNet_S if variant == "S" else arch.GShiftNet)().to(dev).eval()
+    m.load_state_dict(sd)
+    m._engine = Engine(m, use_tc=use_tc)
+    return m
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,W,Cc", [(64, 64, 64), (36, 40, 24), (180, 320, 16), (272, 480, 12), (4, 4, 2)])
+def test_fft_kernels_match_torch_fft(dev, H, W, Cc):
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(2, Cc, H, W, generator=g)
+    Wf = W // 2 + 1
+    xd = nhwc(x).to(dev)
+    spec = torch.empty(2, H, Wf, Cc, 2, device=dev)
+    tw_w, tw_h = bands.twiddles(W, dev), bands.twiddles(H, dev)
+    C.call("fcvsr_fft_r2c_w", xd.data_ptr(), Cc, spec.data_ptr(), tw_w.data_ptr(), 2, H, W, Cc, _st())
+    C.call("fcvsr_fft_c2c_h", spec.data_ptr(), spec.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 0, 1.0, _st())
+    ref = torch.fft.rfft2(x)
+    got = torch.view_as_complex(spec.cpu()).permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
+    # irfft2 on a learned (non-Hermitian) spectrum: Im of DC / Nyquist columns must be ignored
+    z = torch.randn(2, Cc, H, Wf, dtype=torch.complex64, generator=g)
+    zd = torch.view_as_real(z.permute(0, 2, 3, 1).contiguous()).contiguous().to(dev)
+    y = torch.empty(2, H, W, Cc, device=dev)
+    C.call("fcvsr_fft_c2c_h", zd.data_ptr(), zd.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 1, 1.0, _st())
+    C.call("fcvsr_fft_c2r_w", zd.data_ptr(), y.data_ptr(), Cc, tw_w.data_ptr(), 2, H, W, Cc, 1.0 / (H * W), _st())
+    ref2 = torch.fft.irfft2(z, s=(H, W))
+    assert float((nchw(y.cpu()) - ref2).abs().max()) <= 2e-6 * float(ref2.abs().max())
+
+
+def test_fft_rejects_unsupported_length(dev):
+    x = torch.zeros(1, 4, 38, 2, device=dev)          # 38 = 2 * 19: radix 19 is not built
+    out = torch.zeros(1, 4, 20, 2, 2, device=dev)
+    tw = bands.twiddles(38, dev)
+    rc = C.try_call("fcvsr_fft_r2c_w", x.data_ptr(), 2, out.data_ptr(), tw.data_ptr(), 1, 4, 38, 2, _st())
+    assert rc == C.ERR_ARG
+
+
+def _run_conv(dev, x, w, b, tc, act=0, slope=0.0, res=None, ps=False, stride=1):
+    B, Cin, H, W = x.shape
+    pk = _ConvPack(w.to(dev), b.to(dev) if b is not None else None, stride=stride, ps=ps)
+    xd = nhwc(x).to(dev)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    cout = w.shape[0]
+    y = torch.empty((B, 2 * Ho, 2 * Wo, cout // 4) if ps else (B, Ho, Wo, cout), device=dev)
+    rd = nhwc(res).to(dev) if res is not None else None
+    bias = pk.bias.data_ptr() if b is not None else 0
+    rptr = rd.data_ptr() if rd is not None else 0
+    if tc:
+        C.call("fcvsr_conv2d_tc", xd.data_ptr(), Cin, pk.w_tc.data_ptr(), bias, rptr, cout, 0, 0, y.data_ptr(),
+               y.shape[-1], B, H, W, Cin, cout, w.shape[-1], act, slope, 0, int(ps), _st())
+    else:
+        C.call("fcvsr_conv2d_direct", xd.data_ptr(), Cin, 0, pk.w_direct.data_ptr(), bias, rptr, cout, 0, 0,
+               y.data_ptr(), y.shape[-1], B, H, W, Cin, cout, w.shape[-1], stride, act, slope, 0, int(ps), 0, _st())
+    torch.cuda.synchronize()
+    return nchw(y.cpu())
+
+
+CONV_CASES = [(1, 64, 64, 16, 16, 3), (2, 64, 128, 20, 36, 3), (1, 128, 64, 45, 80, 3), (1, 64, 256, 12, 20, 3),
+              (1, 96, 64, 9, 17, 3), (2, 256, 128, 10, 33, 1), (1, 64, 4, 11, 19, 1), (1, 64, 1, 24, 40, 3),
+              (1, 64, 576, 8, 16, 1), (1, 64, 1152, 5, 7, 1)]
+
+
+@pytest.mark.parametrize("case", CONV_CASES + [(1, 7, 448, 12, 12, 3), (1, 209, 64, 6, 9, 1)])
+def test_conv_direct_matches_fp32_reference(dev, case):
+    B, ci, co, H, W, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+    b = torch.randn(co, generator=g)
+    res = torch.randn(B, co, H, W, generator=g)
+    y = _run_conv(dev, x, w, b, False, act=2, slope=0.1, res=res)
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=k // 2), 0.1) + res
+    assert float((y - ref).abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tcgen05_matches_fp32_reference(dev, case):
+    """TF32 operands: tolerance 2e-3 relative to the output scale (K up to 1152 products of ~N(0,1))."""
+    B, ci, co, H, W, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+    b = torch.randn(co, generator=g)
+    res = torch.randn(B, co, H, W, generator=g)
+    y = _run_conv(dev, x, w, b, True, act=2, slope=0.1, res=res)
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=k // 2), 0.1) + res
+    assert float((y - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+    if co % 64 == 0:
+        y = _run_conv(dev, x, w, b, True, ps=True)
+        ref = F.pixel_shuffle(F.conv2d(x, w, b, padding=k // 2), 2)
+        assert float((y - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+def test_conv_direct_stride2(dev):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 64, 16, 20, generator=g)
+    w = torch.randn(64, 64, 3, 3, generator=g) / 24
+    b = torch.randn(64, generator=g)
+    y = _run_conv(dev, x, w, b, False, stride=2)
+    assert float((y - F.conv2d(x, w, b, stride=2, padding=1)).abs().max()) <= 2e-5
+
+
+def test_conv_tc_reports_unsupported_shapes(dev):
+    x = torch.zeros(1, 8, 8, 48, device=dev)
+    w = torch.zeros(64, 48, device=dev)
+    y = torch.zeros(1, 8, 8, 64, device=dev)
+    rc = C.try_call("fcvsr_conv2d_tc", x.data_ptr(), 48, w.data_ptr(), 0, 0, 0, 0, 0, y.data_ptr(), 64, 1, 8, 8, 48, 64, 1,
+                    0, 0.0, 0, 0, _st())
+    assert rc == C.ERR_UNSUPPORTED          # Cin % 32 != 0 -> caller must use fcvsr_conv2d_direct
+
+
+# ------------------------------------------------------------------------------------------------
+# model-level parity
+# ------------------------------------------------------------------------------------------------
+def _stage_taps(model, B, H, W, dev):
+    ws = model._engine._ws[(B, H, W, str(dev))]
+
+    def tap(t, c0, c1, h, w):
+        return nchw(t.view(B, h, w, -1)[..., c0:c1].cpu())
+
+    return {"mgaa1": tap(ws["feat"], 128, 192, H, W), "mgaa2": tap(ws["m2"], 0, 64, H, W),
+            "mffr": tap(ws["xs0"], 0, 64, H, W), "sc_l1": tap(ws["fuse"], 0, 64, H, W),
+            "sc_l3": tap(ws["o3"], 0, 64, H // 4, W // 4), "fuse": tap(ws["f2"], 0, 64, H, W)}
+
+
+@pytest.mark.parametrize("name", ["fcvsr_s_64", "fcvsr_s_36x40", "fcvsr_full_64"])
+def test_fp32_path_matches_reference_golden(dev, name):
+    """CUDA-core fp32 path against the golden outputs of the unmodified reference, stage by stage."""
+    g = load_golden(name)
+    c = g["case"]
+    sd = arch.seeded_state_dict(c["variant"], c["seed"])
+    x = make_clip(c["clip_seed"], c["b"], c["h"], c["w"])
+    m = _model(c["variant"], sd, dev, use_tc=False)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    taps = _stage_taps(m, c["b"], c["h"], c["w"], dev)
+    for k in ("mgaa1", "mgaa2", "mffr", "sc_l1", "fuse"):
+        assert float((taps[k][..., ::4, ::4] - g[k]).abs().max()) <= 1e-4, k
+    assert float((taps["sc_l3"] - g["sc_l3"]).abs().max()) <= 1e-4
+    assert float((y - g["out"]).abs().max()) <= 2e-5
+    assert m._engine.tc_launches == 0 and m._engine.launches > 100
+
+
+@pytest.mark.parametrize("name", ["fcvsr_s_64", "fcvsr_s_36x40", "fcvsr_full_64"])
+def test_tf32_path_matches_reference_golden(dev, name):
+    """Default (tcgen05, TF32 operands) path: the contract's fp32 tolerance, max-abs <= 1e-3 and
+    PSNR delta <= 0.01 dB against a fixed random target."""
+    g = load_golden(name)
+    c = g["case"]
+    sd = arch.seeded_state_dict(c["variant"], c["seed"])
+    x = make_clip(c["clip_seed"], c["b"], c["h"], c["w"])
+    m = _model(c["variant"], sd, dev, use_tc=True)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    ref = g["out"]
+    assert m._engine.tc_launches > 100            # the tensor-core kernel is the one that ran
+    assert float((y - ref).abs().max()) <= 1e-3
+    tgt = torch.rand(ref.shape, generator=torch.Generator().manual_seed(99))
+    assert abs(psnr(y, tgt) - psnr(ref, tgt)) <= 0.01
+
+
+def test_forward_against_oracle_unseen_shape(dev):
+    """A shape with no golden file (ragged tiles: 44 x 52, batch 2) against the live oracle."""
+    sd = arch.seeded_state_dict("S", 5)
+    x = make_clip(321, 2, 44, 52)
+    with torch.no_grad():
+        ref = O.forward(sd, x)
+    for use_tc, tol in ((False, 2e-5), (True, 1e-3)):
+        m = _model("S", sd, dev, use_tc=use_tc)
+        with torch.no_grad():
+            y = m(x.to(dev)).cpu()
+        assert float((y - ref).abs().max()) <= tol
+
+
+def test_drop_in_api_errors(dev):
+    m = arch.GShiftNet_S().to(dev).eval()
+    with torch.no_grad():
+        with pytest.raises(ValueError):
+            m(torch.zeros(1, 7, 64, 64, device=dev))                 # not 5-D
+        with pytest.raises(ValueError):
+            m(torch.zeros(1, 7, 1, 30, 32, device=dev))              # H % 4 != 0
+        with pytest.raises(RuntimeError):
+            m(torch.zeros(1, 7, 1, 32, 32))                          # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 7, 1, 32, 32, device=dev))                  # autograd not supported this round
+
+
+def test_weights_repack_after_load(dev):
+    """load_state_dict after a forward must invalidate the packed weights."""
+    sd_a, sd_b = arch.seeded_state_dict("S", 0), arch.seeded_state_dict("S", 7)
+    x = make_clip(5, 1, 32, 32).to(dev)
+    m = _model("S", sd_a, dev)
+    with torch.no_grad():
+        ya = m(x).clone()
+        m.load_state_dict(sd_b)
+        yb = m(x).clone()
+        m.load_state_dict(sd_a)
+        ya2 = m(x)
+    assert float((ya - yb).abs().max()) > 1e-3
+    assert torch.equal(ya, ya2)               # deterministic: same weights, same bits
+
+
+# ------------------------------------------------------------------------------------------------
+# DCN operator
+# ------------------------------------------------------------------------------------------------
+def test_dcn_known_answer(dev):
+    """ops/dcn/simple_check.py:8-22 through the C ABI."""
+    from fcvsr_b200.ops.dcn import DeformConv
+    with open(os.path.join(GOLD, "dcn_simple_check.json")) as f:
+        kat = json.load(f)
+    conv = DeformConv(2, 1, kernel_size=3, padding=1, deformable_groups=2).to(dev)
+    torch.nn.init.constant_(conv.weight, 1)
+    off = torch.tensor(kat["offset18"], dtype=torch.float32, device=dev).view(1, 18, 1, 1).repeat(1, 2, 3, 3)
+    x = torch.tensor(kat["input"], device=dev)
+    with torch.no_grad():
+        y = conv(x, off)
+    assert torch.equal(y.cpu().flatten(), torch.tensor(kat["expected"], dtype=torch.float32))
+
+
+@pytest.mark.parametrize("cfg", [dict(B=2, cin=16, cout=16, H=9, W=11, k=3, g=1, dg=16, pad=1, stride=1, dil=1),
+                                 dict(B=1, cin=64, cout=64, H=20, W=24, k=3, g=1, dg=16, pad=1, stride=1, dil=1),
+                                 dict(B=2, cin=8, cout=6, H=9, W=11, k=3, g=2, dg=4, pad=1, stride=2, dil=1),
+                                 dict(B=1, cin=4, cout=4, H=12, W=10, k=5, g=1, dg=4, pad=4, stride=1, dil=2)])
+def test_modulated_dcn_matches_oracle(dev, cfg):
+    from fcvsr_b200.ops.dcn import modulated_deform_conv
+    g = torch.Generator().manual_seed(cfg["H"] * cfg["W"])
+    k, dg = cfg["k"], cfg["dg"]
+    x = torch.randn(cfg["B"], cfg["cin"], cfg["H"], cfg["W"], generator=g)
+    w = torch.randn(cfg["cout"], cfg["cin"] // cfg["g"], k, k, generator=g) / 6
+    b = torch.randn(cfg["cout"], generator=g)
+    ho = (cfg["H"] + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    wo = (cfg["W"] + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    off = 3.0 * torch.randn(cfg["B"], dg * 2 * k * k, ho, wo, generator=g)
+    msk = torch.rand(cfg["B"], dg * k * k, ho, wo, generator=g)
+    ref = O.modulated_deform_conv(x, off, msk, w, b, cfg["stride"], cfg["pad"], cfg["dil"], cfg["g"], dg)
+    with torch.no_grad():
+        y = modulated_deform_conv(x.to(dev), off.to(dev), msk.to(dev), w.to(dev), b.to(dev), cfg["stride"], cfg["pad"],
+                                  cfg["dil"], cfg["g"], dg)
+    assert float((y.cpu() - ref).abs().max()) <= 1e-4
