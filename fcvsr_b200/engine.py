@@ -194,6 +194,7 @@ class Engine:
         ws: Dict[str, torch.Tensor] = {}
 
         def buf(name, *shape, zero=False):
+            assert name not in ws, f"workspace name collision: {name}"
             ws[name] = (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=F32)
 
         buf("feat", B, P, 448)
@@ -206,8 +207,8 @@ class Engine:
         buf("off", 2 * B, Pf, 4)
         buf("simh", B, Pf, 64)
         buf("sim", B, Pf, 4)
-        buf("t1", A, 2 * B, Pf, 4)
-        buf("t2", A, 2 * B, Pf, 4)
+        buf("ob_t1", A, 2 * B, Pf, 4)
+        buf("ob_t2", A, 2 * B, Pf, 4)
         buf("ob_partial", A * 2 * B * ((Pf + 127) // 128) * 4)
         buf("z", B, Pf, 8 * A)
         buf("offs", B, P, 4 * A)
@@ -391,7 +392,7 @@ class Engine:
         # ConvBlk_i * x2_f_sim for all i (:1494-1498), then irfft2 (:1499-1505)
         self.launches += 2
         self._k("fcvsr_offset_blocks", p["off"], P["ob_w1"].data_ptr(), P["ob_w2"].data_ptr(), P["ob_prelu"].data_ptr(),
-                P["ob_ca"].data_ptr(), p["sim"], 4, p["t1"], p["t2"], p["ob_partial"], p["z"], B, H, Wf, A)
+                P["ob_ca"].data_ptr(), p["sim"], 4, p["ob_t1"], p["ob_t2"], p["ob_partial"], p["z"], B, H, Wf, A)
         self._k("fcvsr_fft_c2c_h", p["z"], p["z"], p["tw_h"], 0, B, H, Wf, 4 * A, 1, 1.0)
         self._k("fcvsr_fft_c2r_w", p["z"], p["offs"], 4 * A, p["tw_w"], B, H, W, 4 * A, 1.0 / (H * W))
         # kernel predictor (:1522-1523)
