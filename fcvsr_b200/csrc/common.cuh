@@ -39,3 +39,12 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+
+// Round an fp32 value to the nearest TF32 (10-bit mantissa, ties away), kept in fp32 storage.  The
+// tensor cores truncate kind::tf32 operands, so tensors that feed the tcgen05 convolutions are stored
+// pre-rounded: truncation of an already-rounded value is exact and the truncation bias disappears.
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}

@@ -32,17 +32,19 @@
 #define TC_TW 16
 #define TC_KCH 32                      // channels per K chunk (128 bytes of fp32)
 #define TC_NA 2                        // A ring stages
-#define TC_NB 4                        // B ring stages
+#define TC_NB_MAX 16                   // B ring: as many stages as fit in TC_B_RING_BYTES, at most 16
+#define TC_B_RING_BYTES (96 * 1024)
 #define TC_ROW_BYTES 128
 #define TC_A_COPY_BYTES ((TC_TH + 2) * TC_TW * TC_ROW_BYTES)      // 20480
 #define TC_A_STAGE_BYTES (3 * TC_A_COPY_BYTES)                    // 61440
-#define TC_B_STAGE_BYTES (128 * TC_ROW_BYTES)                     // 16384 (N <= 128)
+
 #define TC_THREADS 224
 #define TC_SPIN_LIMIT (1u << 26)
 
 struct ConvTcParams {
     const float* bias; const float* res; int ldres; const float* res2; int ldres2;
     float* y; int ldy;
+    float* y2; int ldy2; int round_out;  // y2: optional TF32-rounded copy of y (non-shuffled outputs only)
     int B, H, W, Cin, Cout, ks;          // Cout = padded (multiple of 16) GEMM N
     int cout_valid;                      // channels actually stored (== Cout, or < 16 for thin heads)
     int n_tile, n_tiles;               // N per pass, number of passes
@@ -137,13 +139,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* a_buf = smem;                                        // TC_NA x 61440
-    uint8_t* b_buf = smem + TC_NA * TC_A_STAGE_BYTES;             // TC_NB x 16384
-    uint64_t* bars = (uint64_t*)(b_buf + TC_NB * TC_B_STAGE_BYTES);
+    uint8_t* b_buf = smem + TC_NA * TC_A_STAGE_BYTES;             // weight ring, TC_B_RING_BYTES
+    uint64_t* bars = (uint64_t*)(b_buf + TC_B_RING_BYTES);
     uint64_t* full_a = bars;            // [TC_NA]
     uint64_t* empty_a = bars + TC_NA;   // [TC_NA]
-    uint64_t* full_b = bars + 2 * TC_NA;            // [TC_NB]
-    uint64_t* empty_b = bars + 2 * TC_NA + TC_NB;   // [TC_NB]
-    uint64_t* tm_full = bars + 2 * TC_NA + 2 * TC_NB;   // [2]
+    uint64_t* full_b = bars + 2 * TC_NA;            // [TC_NB_MAX]
+    uint64_t* empty_b = bars + 2 * TC_NA + TC_NB_MAX;   // [TC_NB_MAX]
+    uint64_t* tm_full = bars + 2 * TC_NA + 2 * TC_NB_MAX;   // [2]
     uint64_t* tm_empty = tm_full + 2;                    // [2]
     uint32_t* tmem_slot = (uint32_t*)(tm_empty + 2);
 
@@ -153,12 +155,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int nrows = p.ks == 3 ? TC_TH + 2 : TC_TH;
     const int kchunks = p.Cin / TC_KCH;
     const uint32_t a_copy_bytes = (uint32_t)nrows * TC_TW * TC_ROW_BYTES;
-    const uint32_t b_bytes = (uint32_t)p.n_tile * TC_ROW_BYTES;
+    const uint32_t b_bytes = (uint32_t)p.n_tile * TC_ROW_BYTES;      // multiple of 2048 (n_tile % 16 == 0): stays 1024-aligned
+    const int nb_stages = min(TC_NB_MAX, (int)(TC_B_RING_BYTES / b_bytes));
     const uint32_t tmem_cols = p.n_tile <= 16 ? 32 : (p.n_tile <= 32 ? 64 : (p.n_tile <= 64 ? 128 : 256));
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
-        for (int i = 0; i < TC_NB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+        for (int i = 0; i < TC_NB_MAX; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -199,9 +202,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     for (int tap = 0; tap < taps; ++tap) {
                         mbar_wait(&empty_b[stage], phase ^ 1, p.err, 2);
                         mbar_expect_tx(&full_b[stage], b_bytes);
-                        tma_load_2d(b_buf + stage * TC_B_STAGE_BYTES, &map_w, &full_b[stage], tap * p.Cin + kc * TC_KCH,
+                        tma_load_2d(b_buf + stage * b_bytes, &map_w, &full_b[stage], tap * p.Cin + kc * TC_KCH,
                                     tc.nt * p.n_tile);
-                        if (++stage == TC_NB) { stage = 0; phase ^= 1; }
+                        if (++stage == nb_stages) { stage = 0; phase ^= 1; }
                     }
             }
         }
@@ -225,14 +228,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         tc_fence_after();
                         const int ky = tap / p.ks, kx = tap - ky * p.ks;
                         const uint32_t a_addr = a_base + (uint32_t)kx * TC_A_COPY_BYTES + (uint32_t)ky * (TC_TW * TC_ROW_BYTES);
-                        const uint32_t b_addr = smem_u32(b_buf + sb * TC_B_STAGE_BYTES);
+                        const uint32_t b_addr = smem_u32(b_buf + sb * b_bytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             umma_tf32(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, first ? 0u : 1u);
                             first = 0;
                         }
                         umma_commit(&empty_b[sb]);
-                        if (++sb == TC_NB) { sb = 0; pb ^= 1; }
+                        if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                     }
                     umma_commit(&empty_a[sa]);
                     if (++sa == TC_NA) { sa = 0; pa ^= 1; }
@@ -301,6 +304,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             v[4 * j] -= rv.x; v[4 * j + 1] -= rv.y; v[4 * j + 2] -= rv.z; v[4 * j + 3] -= rv.w;
                         }
                     }
+                    if (p.y2) {
+                        float4* d2 = reinterpret_cast<float4*>(p.y2 + pix * p.ldy2 + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            d2[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]),
+                                                round_tf32(v[4 * j + 3]));
+                    }
+                    if (p.round_out) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+                    }
                     float* dst;
                     if (p.ps) {
                         const int ij = n0 / c4, c = n0 - ij * c4;
@@ -357,7 +371,7 @@ static int* tc_err_flag() {
 extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
                                const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
                                int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
-                               cudaStream_t st) {
+                               float* y2, int ldy2, int round_out, cudaStream_t st) {
     if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
     if ((ksize != 1 && ksize != 3) || Cin % TC_KCH || Cin <= 0 || Cout <= 0) return FCVSR_ERR_UNSUPPORTED;
     const int cout_valid = Cout;
@@ -368,7 +382,8 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     if (!thin && ((ldy & 3) || (res && (ldres & 3)) || (res2 && (ldres2 & 3)))) return FCVSR_ERR_UNSUPPORTED;
     if (((uintptr_t)x | (uintptr_t)w) & 15) return FCVSR_ERR_UNSUPPORTED;
     if (!thin && (((uintptr_t)y | (uintptr_t)res | (uintptr_t)res2) & 15)) return FCVSR_ERR_UNSUPPORTED;
-    if (thin && pixel_shuffle) return FCVSR_ERR_UNSUPPORTED;
+    if (thin && (pixel_shuffle || y2 || round_out)) return FCVSR_ERR_UNSUPPORTED;
+    if (y2 && (pixel_shuffle || (ldy2 & 3) || ((uintptr_t)y2 & 15))) return FCVSR_ERR_UNSUPPORTED;
     if (act == FCVSR_ACT_PRELU && !slope_ptr) return FCVSR_ERR_ARG;
     int n_tile = Cout, n_tiles = 1;
     if (Cout > 128) {       // largest N tile <= 128 that is a multiple of 16 and divides Cout
@@ -403,7 +418,7 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
             return FCVSR_ERR_CUDA;
     }
     ConvTcParams p;
-    p.bias = bias; p.res = res; p.ldres = ldres; p.res2 = res2; p.ldres2 = ldres2; p.y = y; p.ldy = ldy;
+    p.bias = bias; p.res = res; p.ldres = ldres; p.res2 = res2; p.ldres2 = ldres2; p.y = y; p.ldy = ldy; p.y2 = y2; p.ldy2 = ldy2; p.round_out = round_out;
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ksize; p.cout_valid = cout_valid;
     p.n_tile = n_tile; p.n_tiles = n_tiles;
     p.tiles_x = (W + TC_TW - 1) / TC_TW; p.tiles_y = (H + TC_TH - 1) / TC_TH;
@@ -413,7 +428,7 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
 
     static int num_sms = 0;
     static bool attr_set = false;
-    const size_t smem = 1024 + TC_NA * TC_A_STAGE_BYTES + TC_NB * TC_B_STAGE_BYTES + 256;
+    const size_t smem = 1024 + TC_NA * TC_A_STAGE_BYTES + TC_B_RING_BYTES + 512;
     if (!attr_set) {
         int dev = 0;
         cudaGetDevice(&dev);

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_r2c_w_kernel(const float* __r
 __global__ void __launch_bounds__(FFT_THREADS) fft_c2c_h_kernel(const float2* in, float2* out,
                                                                 const float2* __restrict__ tw,
                                                                 const float* __restrict__ mask, int H, int Wf, int C,
-                                                                int cb_log2, int inverse, float scale, FftPlan plan) {
+                                                                int cb_log2, int inverse, float scale, int round_out, FftPlan plan) {
     extern __shared__ float2 sm[];
     const int cb = 1 << cb_log2, n = H;
     float2* a = sm;
@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_c2c_h_kernel(const float2* in
     for (int idx = threadIdx.x; idx < (n << cb_log2); idx += blockDim.x) {
         const int i = idx >> cb_log2, ch = idx & (cb - 1);
         float2 v = r[idx];
-        out[base + (size_t)i * Wf * C + ch] = make_float2(v.x * scale, v.y * scale);
+        v = make_float2(v.x * scale, v.y * scale);
+        if (round_out) v = make_float2(round_tf32(v.x), round_tf32(v.y));
+        out[base + (size_t)i * Wf * C + ch] = v;
     }
 }
 
@@ -257,7 +259,7 @@ extern "C" int fcvsr_fft_r2c_w(const float* x, int ldx, float* out, const float*
 }
 
 extern "C" int fcvsr_fft_c2c_h(const float* in, float* out, const float* tw, const float* mask, int B, int H, int Wf,
-                               int C, int inverse, float scale, cudaStream_t st) {
+                               int C, int inverse, float scale, int round_out, cudaStream_t st) {
     FftPlan plan;
     if (!in || !out || !tw || !make_plan(H, &plan)) return FCVSR_ERR_ARG;
     const int cbl = pick_cb_log2(H, C);
@@ -265,7 +267,7 @@ extern "C" int fcvsr_fft_c2c_h(const float* in, float* out, const float* tw, con
     if (set_smem(fft_c2c_h_kernel, smem)) return FCVSR_ERR_CUDA;
     dim3 grid(B * Wf, C >> cbl);
     fft_c2c_h_kernel<<<grid, FFT_THREADS, smem, st>>>((const float2*)in, (float2*)out, (const float2*)tw, mask, H, Wf,
-                                                      C, cbl, inverse, scale, plan);
+                                                      C, cbl, inverse, scale, round_out, plan);
     return fcvsr_launch_status();
 }
 

@@ -197,7 +197,7 @@ struct IacArgs {
     float* next[2];       int ldnext[2];
     const float* offs; int ldoffs; int offs_ch[2];   // channel of dx for each direction
     const float* taps; int ldtaps;                   // already offset to this iteration's 192 channels
-    int B, H, W;
+    int B, H, W; int round_out;
 };
 
 __global__ void __launch_bounds__(256) iac_step_kernel(IacArgs a) {
@@ -281,6 +281,7 @@ __global__ void __launch_bounds__(256) iac_step_kernel(IacArgs a) {
         }
         acc.x = acc.x >= 0.f ? acc.x : 0.1f * acc.x;
         acc.y = acc.y >= 0.f ? acc.y : 0.1f * acc.y;
+        if (a.round_out) acc = make_float2(round_tf32(acc.x), round_tf32(acc.y));
         *reinterpret_cast<float2*>(next + (img + (size_t)y * W + x) * a.ldnext[dir] + 2 * lane) = acc;
     }
 }
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(256) iac_step_kernel(IacArgs a) {
 extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int ldprev_b, const float* xin_f,
                               int ldxin_f, const float* xin_b, int ldxin_b, float* next_f, int ldnext_f, float* next_b,
                               int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps,
-                              int ldtaps, int B, int H, int W, cudaStream_t st) {
+                              int ldtaps, int B, int H, int W, int round_out, cudaStream_t st) {
     if (!prev_f || !prev_b || !xin_f || !xin_b || !next_f || !next_b || !offs || !taps) return FCVSR_ERR_ARG;
     if ((ldprev_f | ldprev_b | ldxin_f | ldxin_b | ldnext_f | ldnext_b | ldoffs | ldtaps | ch_f | ch_b) & 1)
         return FCVSR_ERR_ARG;
@@ -297,7 +298,7 @@ extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* pr
     a.xin[0] = xin_f; a.xin[1] = xin_b; a.ldxin[0] = ldxin_f; a.ldxin[1] = ldxin_b;
     a.next[0] = next_f; a.next[1] = next_b; a.ldnext[0] = ldnext_f; a.ldnext[1] = ldnext_b;
     a.offs = offs; a.ldoffs = ldoffs; a.offs_ch[0] = ch_f; a.offs_ch[1] = ch_b;
-    a.taps = taps; a.ldtaps = ldtaps; a.B = B; a.H = H; a.W = W;
+    a.taps = taps; a.ldtaps = ldtaps; a.B = B; a.H = H; a.W = W; a.round_out = round_out;
     const size_t smem = ((IAC_TH + 2) * (IAC_TW + 2) + IAC_TH * (IAC_TW + 2)) * IAC_C * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -307,5 +308,23 @@ extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* pr
     }
     dim3 grid(((H + IAC_TH - 1) / IAC_TH) * ((W + IAC_TW - 1) / IAC_TW), B, 2);
     iac_step_kernel<<<grid, 256, smem, st>>>(a);
+    return fcvsr_launch_status();
+}
+
+// y[pix, 0:C] = round_tf32(x[pix, 0:C])  -- TF32-rounded copy of a tensor that is both a tensor-core conv
+// input and a full-precision residual (C % 4 == 0)
+__global__ void round_copy_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int c4, size_t total4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const size_t pix = i / c4;
+    const int c = (int)(i - pix * c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + pix * ldx + c);
+    *reinterpret_cast<float4*>(y + pix * ldy + c) = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+}
+
+extern "C" int fcvsr_round_copy(const float* x, int ldx, float* y, int ldy, int C, long long npix, cudaStream_t st) {
+    if (!x || !y || (C & 3) || (ldx & 3) || (ldy & 3)) return FCVSR_ERR_ARG;
+    const size_t total4 = (size_t)npix * (C / 4);
+    round_copy_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, ldx, y, ldy, C / 4, total4);
     return fcvsr_launch_status();
 }

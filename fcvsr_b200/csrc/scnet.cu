@@ -10,9 +10,11 @@
 //                                bilinear, align_corners=False; td/tu are the 1x1 down/up conv outputs)
 #include "common.cuh"
 
-#define CTX_PIX_PER_BLOCK 512
+#define CTX_PIX_PER_BLOCK 128
 #define CTX_STRIDE 66          // m, z, acc[64]
 
+// One block = 128 pixels, 8 warps x 16 pixels, 4 pixels in flight per warp (lane owns 2 channels, so a
+// pixel is one coalesced 256-byte load and its logit one 5-step shuffle reduction).
 __global__ void __launch_bounds__(256) ctx_partial_kernel(const float* __restrict__ x, int ldx,
                                                           const float* __restrict__ wmask, float* __restrict__ partial,
                                                           int P) {
@@ -22,16 +24,33 @@ __global__ void __launch_bounds__(256) ctx_partial_kernel(const float* __restric
     const float2 w = *reinterpret_cast<const float2*>(wmask + c);
     float m = -INFINITY, z = 0.f;
     float2 acc = make_float2(0.f, 0.f);
-    const int p_end = min(P, (int)(blockIdx.x + 1) * CTX_PIX_PER_BLOCK);
-    for (int p = blockIdx.x * CTX_PIX_PER_BLOCK + warp; p < p_end; p += 8) {
-        const float2 v = *reinterpret_cast<const float2*>(x + ((size_t)b * P + p) * ldx + c);
-        const float logit = warp_sum(v.x * w.x + v.y * w.y);
-        const float mn = fmaxf(m, logit);
-        const float sc = __expf(m - mn), e = __expf(logit - mn);
-        z = z * sc + e;
-        acc.x = acc.x * sc + e * v.x;
-        acc.y = acc.y * sc + e * v.y;
-        m = mn;
+    const int p0 = blockIdx.x * CTX_PIX_PER_BLOCK + warp * 16;
+    const float* xb = x + (size_t)b * P * ldx + c;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        float2 v[4];
+        float lg[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + it * 4 + u;
+            v[u] = p < P ? *reinterpret_cast<const float2*>(xb + (size_t)p * ldx) : make_float2(0.f, 0.f);
+            lg[u] = v[u].x * w.x + v[u].y * w.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) lg[u] += __shfl_xor_sync(0xffffffffu, lg[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (p0 + it * 4 + u >= P) continue;
+            const float mn = fmaxf(m, lg[u]);
+            const float sc = __expf(m - mn), e = __expf(lg[u] - mn);
+            z = z * sc + e;
+            acc.x = acc.x * sc + e * v[u].x;
+            acc.y = acc.y * sc + e * v[u].y;
+            m = mn;
+        }
     }
     if (lane == 0) { sm_m[warp] = m; sm_z[warp] = z; }
     sm_acc[warp][c] = acc.x; sm_acc[warp][c + 1] = acc.y;
@@ -53,30 +72,52 @@ __global__ void __launch_bounds__(256) ctx_partial_kernel(const float* __restric
     }
 }
 
-// grid B, 64 threads: merge partials -> context[64] -> add = W2 lrelu_0.2(W1 ctx)
-__global__ void __launch_bounds__(64) ctx_finalize_kernel(const float* __restrict__ partial, int nblk,
-                                                          const float* __restrict__ w1, const float* __restrict__ w2,
-                                                          float* __restrict__ add) {
+// grid B, 256 threads: merge the block partials (fixed order) -> context[64] -> add = W2 lrelu_0.2(W1 ctx)
+__global__ void __launch_bounds__(256) ctx_finalize_kernel(const float* __restrict__ partial, int nblk,
+                                                           const float* __restrict__ w1, const float* __restrict__ w2,
+                                                           float* __restrict__ add) {
+    __shared__ float red[256];
+    __shared__ float part[4][64];
     __shared__ float ctx[64], hid[64];
     const int b = blockIdx.x, t = threadIdx.x;
     const float* pp = partial + (size_t)b * nblk * CTX_STRIDE;
     float M = -INFINITY;
-    for (int k = 0; k < nblk; ++k) M = fmaxf(M, pp[k * CTX_STRIDE]);
-    float Z = 0.f, A = 0.f;
-    for (int k = 0; k < nblk; ++k) {
-        const float s = __expf(pp[k * CTX_STRIDE] - M);
-        Z += pp[k * CTX_STRIDE + 1] * s;
-        A += pp[k * CTX_STRIDE + 2 + t] * s;
+    for (int k = t; k < nblk; k += 256) M = fmaxf(M, pp[k * CTX_STRIDE]);
+    red[t] = M;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (t < s) red[t] = fmaxf(red[t], red[t + s]);
+        __syncthreads();
     }
-    ctx[t] = A / Z;
+    M = red[0];
     __syncthreads();
-    float h = 0.f;
-    for (int c = 0; c < 64; ++c) h += w1[t * 64 + c] * ctx[c];
-    hid[t] = h >= 0.f ? h : 0.2f * h;
+    float Z = 0.f;
+    for (int k = t; k < nblk; k += 256) Z += pp[k * CTX_STRIDE + 1] * __expf(pp[k * CTX_STRIDE] - M);
+    red[t] = Z;
     __syncthreads();
-    float o = 0.f;
-    for (int c = 0; c < 64; ++c) o += w2[t * 64 + c] * hid[c];
-    add[(size_t)b * 64 + t] = o;
+    for (int s = 128; s > 0; s >>= 1) {
+        if (t < s) red[t] += red[t + s];
+        __syncthreads();
+    }
+    Z = red[0];
+    const int c = t & 63, q = t >> 6;
+    float A = 0.f;
+    for (int k = q; k < nblk; k += 4) A += pp[k * CTX_STRIDE + 2 + c] * __expf(pp[k * CTX_STRIDE] - M);
+    part[q][c] = A;
+    __syncthreads();
+    if (t < 64) ctx[t] = (part[0][t] + part[1][t] + part[2][t] + part[3][t]) / Z;
+    __syncthreads();
+    if (t < 64) {
+        float h = 0.f;
+        for (int k = 0; k < 64; ++k) h += w1[t * 64 + k] * ctx[k];
+        hid[t] = h >= 0.f ? h : 0.2f * h;
+    }
+    __syncthreads();
+    if (t < 64) {
+        float o = 0.f;
+        for (int k = 0; k < 64; ++k) o += w2[t * 64 + k] * hid[k];
+        add[(size_t)b * 64 + t] = o;
+    }
 }
 
 extern "C" int fcvsr_context_block(const float* x, int ldx, const float* wmask, const float* w1, const float* w2,
@@ -84,13 +125,13 @@ extern "C" int fcvsr_context_block(const float* x, int ldx, const float* wmask, 
     if (!x || !wmask || !w1 || !w2 || !partial || !add || (ldx & 1)) return FCVSR_ERR_ARG;
     const int nblk = (P + CTX_PIX_PER_BLOCK - 1) / CTX_PIX_PER_BLOCK;
     ctx_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, ldx, wmask, partial, P);
-    ctx_finalize_kernel<<<B, 64, 0, st>>>(partial, nblk, w1, w2, add);
+    ctx_finalize_kernel<<<B, 256, 0, st>>>(partial, nblk, w1, w2, add);
     return fcvsr_launch_status();
 }
 
 // r = lrelu_0.2(res + add[b]) + r0     (all 64 channels, float4 per thread)
 __global__ void rcb_finish_kernel(const float* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
-                                  float* __restrict__ r, int P, size_t total4) {
+                                  float* __restrict__ r, int P, size_t total4, int round_out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)(i & 15) * 4;
@@ -105,21 +146,23 @@ __global__ void rcb_finish_kernel(const float* __restrict__ res, const float* __
     o.y = (o.y >= 0.f ? o.y : 0.2f * o.y) + q.y;
     o.z = (o.z >= 0.f ? o.z : 0.2f * o.z) + q.z;
     o.w = (o.w >= 0.f ? o.w : 0.2f * o.w) + q.w;
+    if (round_out) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
     *reinterpret_cast<float4*>(r + pix * 64 + c) = o;
 }
 
 extern "C" int fcvsr_rcb_finish(const float* res, const float* add, const float* r0, float* r, int B, int P,
-                                cudaStream_t st) {
+                                int round_out, cudaStream_t st) {
     if (!res || !add || !r0 || !r) return FCVSR_ERR_ARG;
     const size_t total4 = (size_t)B * P * 16;
-    rcb_finish_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(res, add, r0, r, P, total4);
+    rcb_finish_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(res, add, r0, r, P, total4, round_out);
     return fcvsr_launch_status();
 }
 
 // x[b,y,x,:] += coef * r + mean2x2(td) + bilinear_x2(tu)      (64 channels, ld 64 everywhere except x/y)
 __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* __restrict__ xout, int ldo,
                                  const float* __restrict__ r, float coef, const float* __restrict__ td,
-                                 const float* __restrict__ tu, int H, int W, size_t total4) {
+                                 const float* __restrict__ tu, int H, int W, size_t total4, float* __restrict__ xout_r, int ldr,
+                                 int round_main) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)(i & 15) * 4;
@@ -158,13 +201,16 @@ __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* 
         o.z += w00 * a00.z + w01 * a01.z + w10 * a10.z + w11 * a11.z;
         o.w += w00 * a00.w + w01 * a01.w + w10 * a10.w + w11 * a11.w;
     }
-    *reinterpret_cast<float4*>(xout + pix * ldo + c) = o;
+    const float4 orr = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+    if (xout_r) *reinterpret_cast<float4*>(xout_r + pix * ldr + c) = orr;
+    *reinterpret_cast<float4*>(xout + pix * ldo + c) = round_main ? orr : o;
 }
 
 extern "C" int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float* r, float coef,
-                               const float* td, const float* tu, int B, int H, int W, cudaStream_t st) {
-    if (!xin || !xout || !r || (ldx & 3) || (ldo & 3) || (tu && ((H | W) & 1))) return FCVSR_ERR_ARG;
+                               const float* td, const float* tu, int B, int H, int W, float* xout_r, int ldr,
+                               int round_main, cudaStream_t st) {
+    if (!xin || !xout || !r || (ldx & 3) || (ldo & 3) || (tu && ((H | W) & 1)) || (xout_r && (ldr & 3))) return FCVSR_ERR_ARG;
     const size_t total4 = (size_t)B * H * W * 16;
-    level_mix_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(xin, ldx, xout, ldo, r, coef, td, tu, H, W, total4);
+    level_mix_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(xin, ldx, xout, ldo, r, coef, td, tu, H, W, total4, xout_r, ldr, round_main);
     return fcvsr_launch_status();
 }

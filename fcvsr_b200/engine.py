@@ -29,6 +29,12 @@ def _spec_perm(n: int = 64) -> torch.Tensor:
     return torch.where(j < n, 2 * j + 1, 2 * (j - n))
 
 
+def _round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """Round fp32 to the nearest TF32 value (ties away from zero), keeping fp32 storage."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & -8192).view(torch.float32)
+
+
 class _ConvPack:
     """One convolution's weights in both kernel layouts."""
 
@@ -65,7 +71,9 @@ class _ConvPack:
         wt = w.permute(0, 2, 3, 1).reshape(cout, k * k * cin)              # [Cout][k*k*Cin]
         if cout < 16:
             wt = torch.cat([wt, wt.new_zeros(16 - cout, wt.shape[1])], 0)
-        self.w_tc = wt.contiguous()
+        # tcgen05 kind::tf32 truncates its operands to 10 mantissa bits; rounding the weights to
+        # nearest here (cvt.rna semantics) removes their share of the truncation bias for free.
+        self.w_tc = _round_tf32(wt.contiguous())
         self.tc_ok = stride == 1 and k in (1, 3) and cin % 32 == 0 and (cout < 16 or cout % 16 == 0)
 
 
@@ -212,6 +220,7 @@ class Engine:
         buf("ob_partial", A * 2 * B * ((Pf + 127) // 128) * 4)
         buf("z", B, Pf, 8 * A)
         buf("offs", B, P, 4 * A)
+        buf("x2r", B, P, 64)
         buf("kp1", B, P, 64)
         buf("kp2", B, P, 64)
         buf("pk", B, P, A * 192)
@@ -229,12 +238,12 @@ class Engine:
         dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
         for l, (h, w) in enumerate(dims):
             p = h * w
-            for nm in ("xs", "cur", "t", "r0", "c1", "res", "rr"):
+            for nm in ("xs", "cur", "t", "r0", "c1", "res", "rr", "xsr", "curr", "tr"):
                 buf(f"{nm}{l}", B, p, 64)
             buf(f"a128_{l}", B, p, 128)
             buf(f"td{l}", B, p, 64)
             buf(f"tu{l}", B, p, 64)
-            buf(f"ctxp{l}", B * ((p + 511) // 512) * 66)
+            buf(f"ctxp{l}", B * ((p + 127) // 128) * 66)
             buf(f"add{l}", B, 64)
         buf("o2", B, dims[1][0] * dims[1][1], 64)
         buf("o3", B, dims[2][0] * dims[2][1], 64)
@@ -255,7 +264,7 @@ class Engine:
     # launch helpers
     # -------------------------------------------------------------------------------------------
     def _conv(self, pk: _ConvPack, x, ldx, y, ldy, B, H, W, act=C.ACT_NONE, slope=0.0, slope_ptr=0, res=0, ldres=0,
-              res2=0, ldres2=0, nchw=False, cin=None):
+              res2=0, ldres2=0, nchw=False, cin=None, y2=0, ldy2=0, rnd=False):
         """x, y, res*: integer device addresses.  `cin`: logical Cin for the direct kernel when the pack
         was padded for the tensor-core path."""
         st = self.st
@@ -267,7 +276,8 @@ class Engine:
             e0.record()
             try:
                 self.profile = None
-                self._conv(pk, x, ldx, y, ldy, B, H, W, act, slope, slope_ptr, res, ldres, res2, ldres2, nchw, cin)
+                self._conv(pk, x, ldx, y, ldy, B, H, W, act, slope, slope_ptr, res, ldres, res2, ldres2, nchw, cin, y2,
+                           ldy2, rnd)
             finally:
                 self.profile = prof
             self.launches -= 1
@@ -276,10 +286,12 @@ class Engine:
             prof.append((kind, 2.0 * B * ho * wo * pk.cin_logical * pk.cout * pk.k * pk.k,
                          4.0 * B * (H * W * pk.cin_logical + ho * wo * pk.cout), e0, e1))
             return
+        if not self.use_tc:          # exact-fp32 mode: nothing is rounded to TF32
+            y2, ldy2, rnd = 0, 0, False
         if self.use_tc and pk.tc_ok and not nchw:
             rc = C.try_call("fcvsr_conv2d_tc", x, ldx, pk.w_tc.data_ptr(), pk.bias.data_ptr() if pk.bias is not None else 0,
                             res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin, pk.cout, pk.k, act, slope, slope_ptr,
-                            int(pk.ps), st)
+                            int(pk.ps), y2, ldy2, int(rnd), st)
             if rc == 0:
                 self.tc_launches += 1
                 return
@@ -287,7 +299,7 @@ class Engine:
                 raise RuntimeError(f"fcvsr_conv2d_tc failed with status {rc}")
         C.call("fcvsr_conv2d_direct", x, ldx, int(nchw), pk.w_direct.data_ptr(),
                pk.bias.data_ptr() if pk.bias is not None else 0, res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin,
-               pk.cout, pk.k, pk.stride, act, slope, slope_ptr, int(pk.ps), 0, st)
+               pk.cout, pk.k, pk.stride, act, slope, slope_ptr, int(pk.ps), 0, y2, ldy2, int(rnd), st)
 
     def _k(self, name, *args):
         self.launches += 1
@@ -354,8 +366,8 @@ class Engine:
         self._mgaa(ws, p, f + 256 * 4, 448, f + 256 * 4, 448, B, H, W)
         self._mgaa(ws, p, f + 128 * 4, 448, p["m2"], 64, B, H, W)
         self._mffr(ws, p, B, H, W)                                   # m2 -> xs0
-        self._conv(P["rc1"], p["xs0"], 64, p["xs1"], 64, B, H, W)                      # :2735
-        self._conv(P["rc2"], p["xs1"], 64, p["xs2"], 64, B, H // 2, W // 2)            # :2736
+        self._conv(P["rc1"], p["xs0"], 64, p["xs1"], 64, B, H, W, y2=p["xsr1"], ldy2=64)                  # :2735
+        self._conv(P["rc2"], p["xs1"], 64, p["xs2"], 64, B, H // 2, W // 2, y2=p["xsr2"], ldy2=64)        # :2736
         self._scnet(ws, p, B, H, W)
         self._tail(x, out, ws, p, B, H, W)
 
@@ -369,35 +381,40 @@ class Engine:
         RELU = C.ACT_RELU
         # rfft2 of x1|x2|x3 (:1452-1454)
         self._k("fcvsr_fft_r2c_w", src, lds, spec, p["tw_w"], B, H, W, 192)
-        self._k("fcvsr_fft_c2c_h", spec, spec, p["tw_h"], 0, B, H, Wf, 192, 0, 1.0)
+        R = int(self.use_tc)     # tensors that feed tcgen05 convs are stored TF32-rounded (see common.cuh)
+        self._k("fcvsr_fft_c2c_h", spec, spec, p["tw_h"], 0, B, H, Wf, 192, 0, 1.0, R)
         h1, h2, cc = p["h1"], p["h2"], p["cc"]
         half = B * Pf
         # convfuse (:1472-1473); the diff skip rides in the last layer's epilogue (res - res2)
-        self._conv(P["fuse0_f"], spec, 384, h1, 128, B, H, Wf, act=RELU)
-        self._conv(P["fuse0_b"], spec + 128 * 4, 384, h1 + half * 128 * 4, 128, B, H, Wf, act=RELU)
-        self._conv(P["fuse2"], h1, 128, h2, 128, 2 * B, H, Wf, act=RELU)
-        self._conv(P["fuse4"], h2, 128, cc, 224, B, H, Wf, res=spec, ldres=384, res2=spec + 128 * 4, ldres2=384)
+        self._conv(P["fuse0_f"], spec, 384, h1, 128, B, H, Wf, act=RELU, rnd=True)
+        self._conv(P["fuse0_b"], spec + 128 * 4, 384, h1 + half * 128 * 4, 128, B, H, Wf, act=RELU, rnd=True)
+        self._conv(P["fuse2"], h1, 128, h2, 128, 2 * B, H, Wf, act=RELU, rnd=True)
+        self._conv(P["fuse4"], h2, 128, cc, 224, B, H, Wf, res=spec, ldres=384, res2=spec + 128 * 4, ldres2=384, rnd=True)
         self._conv(P["fuse4"], h2 + half * 128 * 4, 128, cc + half * 224 * 4, 224, B, H, Wf,
-                   res=spec + 256 * 4, ldres=384, res2=spec + 128 * 4, ldres2=384)
+                   res=spec + 256 * 4, ldres=384, res2=spec + 128 * 4, ldres2=384, rnd=True)
         # convcrt (:1474)
-        self._conv(P["crt0"], spec + 128 * 4, 384, p["simh"], 64, B, H, Wf, act=RELU)
+        self._conv(P["crt0"], spec + 128 * 4, 384, p["simh"], 64, B, H, Wf, act=RELU, rnd=True)
         self._conv(P["crt2"], p["simh"], 64, p["sim"], 4, B, H, Wf)
         # CorrBlock lookup (:1475-1483); corr_f feeds both branches (:1487-1488)
         self._k("fcvsr_corr_gather", spec, 384, 0, 128, cc + 128 * 4, 224, B, H, Wf, 128)
         self._k("fcvsr_corr_gather", spec, 384, 0, 128, cc + (half * 224 + 128) * 4, 224, B, H, Wf, 128)
         # convcorr (:1487-1488), both branches as a batch of 2B
-        self._conv(P["corr0"], cc, 224, p["c1"], 64, 2 * B, H, Wf, act=RELU)
-        self._conv(P["corr2"], p["c1"], 64, p["c2"], 64, 2 * B, H, Wf, act=RELU)
+        self._conv(P["corr0"], cc, 224, p["c1"], 64, 2 * B, H, Wf, act=RELU, rnd=True)
+        self._conv(P["corr2"], p["c1"], 64, p["c2"], 64, 2 * B, H, Wf, act=RELU, rnd=True)
         self._conv(P["corr4"], p["c2"], 64, p["off"], 4, 2 * B, H, Wf)
         # ConvBlk_i * x2_f_sim for all i (:1494-1498), then irfft2 (:1499-1505)
         self.launches += 2
         self._k("fcvsr_offset_blocks", p["off"], P["ob_w1"].data_ptr(), P["ob_w2"].data_ptr(), P["ob_prelu"].data_ptr(),
                 P["ob_ca"].data_ptr(), p["sim"], 4, p["ob_t1"], p["ob_t2"], p["ob_partial"], p["z"], B, H, Wf, A)
-        self._k("fcvsr_fft_c2c_h", p["z"], p["z"], p["tw_h"], 0, B, H, Wf, 4 * A, 1, 1.0)
+        self._k("fcvsr_fft_c2c_h", p["z"], p["z"], p["tw_h"], 0, B, H, Wf, 4 * A, 1, 1.0, 0)
         self._k("fcvsr_fft_c2r_w", p["z"], p["offs"], 4 * A, p["tw_w"], B, H, W, 4 * A, 1.0 / (H * W))
         # kernel predictor (:1522-1523)
-        self._conv(P["kp"], src + 64 * 4, lds, p["kp1"], 64, B, H, W)
-        self._conv(P["F0"], p["kp1"], 64, p["kp2"], 64, B, H, W)
+        x2, ldx2 = src + 64 * 4, lds
+        if R:                       # x2 is both the conv_KP operand and the full-precision skip of conv3
+            self._k("fcvsr_round_copy", x2, lds, p["x2r"], 64, 64, B * H * W)
+            x2, ldx2 = p["x2r"], 64
+        self._conv(P["kp"], x2, ldx2, p["kp1"], 64, B, H, W, rnd=True)
+        self._conv(P["F0"], p["kp1"], 64, p["kp2"], 64, B, H, W, rnd=True)
         self._conv(P["F1"], p["kp2"], 64, p["pk"], A * 192, B, H, W)
         # IAC (:1526-1527)
         ping = p["ping"]
@@ -409,7 +426,8 @@ class Engine:
             else:
                 nf, nb, ldn = ping + (i % 2) * 2 * sz, ping + ((i % 2) * 2 + 1) * sz, 64
             self._k("fcvsr_iac_step", prev_f, ldpf, prev_b, ldpb, src, lds, src + 128 * 4, lds, nf, ldn, nb, ldn,
-                    p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["pk"] + i * 192 * 4, A * 192, B, H, W)
+                    p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["pk"] + i * 192 * 4, A * 192, B, H, W,
+                    R if i == A - 1 else 0)
             prev_f, ldpf, prev_b, ldpb = nf, ldn, nb, ldn
         # conv3(cat) + x2 (:1529)
         self._conv(P["conv3"], p["cat128"], 128, dst, ldd, B, H, W, res=src + 64 * 4, ldres=lds)
@@ -422,10 +440,10 @@ class Engine:
         nblk = (npix + 255) // 256
         x = p["m2"]
         self._k("fcvsr_fft_r2c_w", x, 64, p["specx"], p["tw_w"], B, H, W, 64)
-        self._k("fcvsr_fft_c2c_h", p["specx"], p["specx"], p["tw_h"], 0, B, H, Wf, 64, 0, 1.0)
+        self._k("fcvsr_fft_c2c_h", p["specx"], p["specx"], p["tw_h"], 0, B, H, Wf, 64, 0, 1.0, 0)
         bsz = B * npix * 64 * 4
         for q in range(Q):      # Split_freq (:2075-2101): band_q = irfft2(spectrum * Msym_q)
-            self._k("fcvsr_fft_c2c_h", p["specx"], p["tmpc"], p["tw_h"], p["masks"] + q * H * Wf * 4, B, H, Wf, 64, 1, 1.0)
+            self._k("fcvsr_fft_c2c_h", p["specx"], p["tmpc"], p["tw_h"], p["masks"] + q * H * Wf * 4, B, H, Wf, 64, 1, 1.0, 0)
             self._k("fcvsr_fft_c2r_w", p["tmpc"], p["bands"] + q * bsz, 64, p["tw_w"], B, H, W, 64, 1.0 / npix)
         band = lambda i: p["bands"] + (Q - 1 - i) * bsz            # freq[::-1] (:2204-2205)
         gate = lambda i: p["gates"] + i * B * 128 * 4
@@ -445,40 +463,47 @@ class Engine:
         self._k("fcvsr_reduce_finalize", p["mf_partial"], nblk, 1, inv, 1, P["mffr.w1"].data_ptr(),
                 P["mffr.w2"].data_ptr(), gate(Q), B)
         self._k("fcvsr_mffr_final", p["so"], gate(Q), x, 64, p["xs0"], 64, B, npix)
+        if self.use_tc:
+            self._k("fcvsr_round_copy", p["xs0"], 64, p["xsr0"], 64, 64, B * npix)
 
     # SCNetbk (:807-822)
     def _scnet(self, ws, p, B, H, W):
         P, G = self.packs, self.model.SCGroupN
         dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
         LK = C.ACT_LEAKY
+        R = int(self.use_tc)
         for g in range(G):
             inp = [p[f"xs{l}"] if g == 0 else p[f"cur{l}"] for l in range(3)]
+            inp_r = [p[f"xsr{l}"] if g == 0 else p[f"curr{l}"] for l in range(3)] if R else inp
             for k in range(3):
                 q = f"g{g}.b{k}."
                 src = inp if k == 0 else [p[f"t{l}"] for l in range(3)]
+                src_r = (inp_r if k == 0 else [p[f"tr{l}"] for l in range(3)]) if R else src
                 for l, (h, w) in enumerate(dims):      # BlockRCB body (:729-751) + RCB (:705-725)
-                    self._conv(P[q + "c0"], src[l], 64, p[f"a128_{l}"], 128, B, h, w, act=LK, slope=0.1)
-                    self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w)
-                    self._conv(P[q + "r0"], p[f"r0{l}"], 64, p[f"c1{l}"], 64, B, h, w, act=LK, slope=0.2)
+                    self._conv(P[q + "c0"], src_r[l], 64, p[f"a128_{l}"], 128, B, h, w, act=LK, slope=0.1, rnd=True)
+                    self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w, rnd=True)
+                    self._conv(P[q + "r0"], p[f"r0{l}"], 64, p[f"c1{l}"], 64, B, h, w, act=LK, slope=0.2, rnd=True)
                     self._conv(P[q + "r2"], p[f"c1{l}"], 64, p[f"res{l}"], 64, B, h, w)
                     self.launches += 1
                     self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
                             P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w)
-                    self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w)
+                    self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w, R)
                 for l in (0, 1):                        # down: 1x1 conv, pooled in level_mix (:753-757)
                     self._conv(P[q + "down"], p[f"rr{l}"], 64, p[f"td{l}"], 64, B, dims[l][0], dims[l][1])
                 for l in (1, 2):                        # up: 1x1 conv, interpolated in level_mix (:759-763)
                     self._conv(P[q + "up"], p[f"rr{l}"], 64, p[f"tu{l}"], 64, B, dims[l][0], dims[l][1])
                 # x + r + d + u (:771-776): level 0 has d = r, level 2 has u = r
-                self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0])
-                self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1])
-                self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2])
+                tr = [p[f"tr{l}"] if R else 0 for l in range(3)]
+                self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0)
+                self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0)
+                self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0)
             for l, (h, w) in enumerate(dims):           # SCGroupbk tail: x + conv(res) (:797-803)
-                self._conv(P[f"g{g}.conv"], p[f"t{l}"], 64, p[f"cur{l}"], 64, B, h, w, res=inp[l], ldres=64)
+                self._conv(P[f"g{g}.conv"], p[f"tr{l}"] if R else p[f"t{l}"], 64, p[f"cur{l}"], 64, B, h, w, res=inp[l],
+                           ldres=64, y2=p[f"curr{l}"], ldy2=64)
         # SCNetbk skip (:816-822): level 0 lands in the 84(96)-channel fuse buffer
-        self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], 96, p["cur0"], 1.0, 0, 0, B, *dims[0])
-        self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1])
-        self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2])
+        self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], 96, p["cur0"], 1.0, 0, 0, B, *dims[0], 0, 0, R)
+        self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1], 0, 0, R)
+        self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2], 0, 0, R)
 
     # pyramid fuse + up-sampler (:2739-2751)
     def _tail(self, x, out, ws, p, B, H, W):
@@ -488,16 +513,16 @@ class Engine:
         sl = P["prelu"].data_ptr()
         cat2, fuse = p["cat2"], p["fuse"]
         # out_L3 -> PS -> cat2[64:80] (L2 res) -> PS -> fuse[80:84]
-        self._conv(P["up_l3"], p["o3"], 64, cat2 + 64 * 4, 96, B, h3, w3, act=PR, slope_ptr=sl)
+        self._conv(P["up_l3"], p["o3"], 64, cat2 + 64 * 4, 96, B, h3, w3, act=PR, slope_ptr=sl, rnd=True)
         self._k("fcvsr_pixel_shuffle", cat2 + 64 * 4, 96, fuse + 80 * 4, 96, B, h2, w2, 4)
         # out_L2 (kept in shuffle order) -> cat2[0:64]
-        self._conv(P["up_l2"], p["o2"], 64, cat2, 96, B, h2, w2, act=PR, slope_ptr=sl)
+        self._conv(P["up_l2"], p["o2"], 64, cat2, 96, B, h2, w2, act=PR, slope_ptr=sl, rnd=True)
         # PS(out_L2 + upconv1_L2_2(cat)) -> fuse[64:80]
-        self._conv(P["up_l2_2"], cat2, 96, fuse + 64 * 4, 96, B, h2, w2, res=cat2, ldres=96)
-        self._conv(P["fuse"], fuse, 96, p["f1"], 64, B, H, W)
-        self._conv(P["rec0"], p["f1"], 64, p["f2"], 64, B, H, W)
-        self._conv(P["up1"], p["f2"], 64, p["up1"], 64, B, H, W, act=PR, slope_ptr=sl)
-        self._conv(P["up2"], p["up1"], 64, p["up2"], 64, B, 2 * H, 2 * W, act=PR, slope_ptr=sl)
+        self._conv(P["up_l2_2"], cat2, 96, fuse + 64 * 4, 96, B, h2, w2, res=cat2, ldres=96, rnd=True)
+        self._conv(P["fuse"], fuse, 96, p["f1"], 64, B, H, W, rnd=True)
+        self._conv(P["rec0"], p["f1"], 64, p["f2"], 64, B, H, W, rnd=True)
+        self._conv(P["up1"], p["f2"], 64, p["up1"], 64, B, H, W, act=PR, slope_ptr=sl, rnd=True)
+        self._conv(P["up2"], p["up1"], 64, p["up2"], 64, B, 2 * H, 2 * W, act=PR, slope_ptr=sl, rnd=True)
         # bilinear x4 of the centre LR frame (:2750) rides in conv_last0's epilogue as the residual
         self._k("fcvsr_bilinear_up4", x.data_ptr() + 3 * H * W * 4, 7 * H * W, p["base"], B, H, W)
         self._conv(P["last"], p["up2"], 64, out.data_ptr(), 1, B, 4 * H, 4 * W, res=p["base"], ldres=1)

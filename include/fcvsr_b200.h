@@ -38,11 +38,13 @@ extern "C" {
  * w packed [k*k][Cin][Cout].  x may be NCHW (x_nchw=1, ldx ignored), y may be NCHW (y_nchw=1, ldy ignored).
  * Replaces F.conv2d at CVSR_train/arch/CVSR_freq.py:2663 (feat_extract), :2671-2672 (stride 2),
  * :2684 (conv_last0), :1380-1395 (per-bin MLP heads) and is the fp32 cross-check of the tensor-core
- * kernel. */
+ * kernel.  round_out=1 stores y rounded to TF32 (for tensors that only feed tensor-core convs); y2 != NULL
+ * additionally stores a TF32-rounded copy (for tensors that are also full-precision residuals). */
 int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const float* w, const float* bias,
                         const float* res, int ldres, const float* res2, int ldres2, float* y, int ldy,
                         int B, int H, int W, int Cin, int Cout, int ksize, int stride, int act, float slope,
-                        const float* slope_ptr, int pixel_shuffle, int y_nchw, cudaStream_t stream);
+                        const float* slope_ptr, int pixel_shuffle, int y_nchw, float* y2, int ldy2,
+                        int round_out, cudaStream_t stream);
 
 /* tcgen05/TMEM implicit-GEMM convolution fed by TMA (stride 1, k in {1,3}, Cin % 32 == 0, Cout % 16 == 0,
  * Cout <= 256), TF32 operands / fp32 accumulate, same fused epilogue as above.
@@ -52,7 +54,7 @@ int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const float* w, con
 int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
                     const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
                     int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
-                    cudaStream_t stream);
+                    float* y2, int ldy2, int round_out, cudaStream_t stream);
 
 /* ---- FFT (torch.fft.rfft2 / irfft2 / fftn / ifftn of CVSR_freq.py:1452-1454, :1499-1504, :2082-2088) */
 
@@ -62,7 +64,7 @@ int fcvsr_fft_r2c_w(const float* x, int ldx, float* out_c, const float* tw, int 
 /* in/out complex [B,H,Wf,C] (C complex channels); optional real mask [H*Wf] multiplied at load;
  * in == out allowed.  inverse: 0 forward, 1 inverse (unnormalised); result * scale. */
 int fcvsr_fft_c2c_h(const float* in_c, float* out_c, const float* tw, const float* mask, int B, int H, int Wf,
-                    int C, int inverse, float scale, cudaStream_t stream);
+                    int C, int inverse, float scale, int round_out, cudaStream_t stream);
 /* complex [B,H,Wf,C] -> real [B,H,W,ldy] (C real channels), torch c2r semantics, result * scale. */
 int fcvsr_fft_c2r_w(const float* in_c, float* y, int ldy, const float* tw, int B, int H, int W, int C,
                     float scale, cudaStream_t stream);
@@ -88,7 +90,10 @@ int fcvsr_offset_blocks(const float* off, const float* w1, const float* w2, cons
 int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int ldprev_b, const float* xin_f,
                    int ldxin_f, const float* xin_b, int ldxin_b, float* next_f, int ldnext_f, float* next_b,
                    int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps, int ldtaps,
-                   int B, int H, int W, cudaStream_t stream);
+                   int B, int H, int W, int round_out, cudaStream_t stream);
+
+/* y[pix,0:C] = TF32-rounded x[pix,0:C] (tensor-core operand copy of a tensor that is also a residual) */
+int fcvsr_round_copy(const float* x, int ldx, float* y, int ldy, int C, long long npix, cudaStream_t stream);
 
 /* ---- MultiFreq_Refinment (CVSR_freq.py:2104-2133, :2183-2254) ---------------------------------- */
 
@@ -106,15 +111,16 @@ int fcvsr_mffr_final(const float* so, const float* gate, const float* x, int ldx
 
 /* ---- SCNetbk helpers (CVSR_freq.py:657-777) ----------------------------------------------------- */
 
-/* ContextBlock (:657-701): add[b][64] = W2 lrelu_0.2(W1 softmax-pool(x)); partial [B][ceil(P/512)][66] */
+/* ContextBlock (:657-701): add[b][64] = W2 lrelu_0.2(W1 softmax-pool(x)); partial [B][ceil(P/128)][66] */
 int fcvsr_context_block(const float* x, int ldx, const float* wmask, const float* w1, const float* w2,
                         float* partial, float* add, int B, int P, cudaStream_t stream);
 /* RCB tail (:720-724): r = lrelu_0.2(res + add[b]) + r0 (64 ch, ld 64) */
 int fcvsr_rcb_finish(const float* res, const float* add, const float* r0, float* r, int B, int P,
-                     cudaStream_t stream);
+                     int round_out, cudaStream_t stream);
 /* BlockRCB cross-level sum (:766-777): xout = xin + coef*r + mean2x2(td[B,2H,2W,64]) + bilinear_x2(tu[B,H/2,W/2,64]) */
 int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float* r, float coef, const float* td,
-                    const float* tu, int B, int H, int W, cudaStream_t stream);
+                    const float* tu, int B, int H, int W, float* xout_r, int ldr, int round_main,
+                    cudaStream_t stream);
 
 /* ---- tail (CVSR_freq.py:2739-2751) -------------------------------------------------------------- */
 int fcvsr_pixel_shuffle(const float* in, int ldi, float* out, int ldo, int B, int H, int W, int Co,

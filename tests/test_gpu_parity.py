@@ -51,7 +51,7 @@ def test_fft_kernels_match_torch_fft(dev, H, W, Cc):
     spec = torch.empty(2, H, Wf, Cc, 2, device=dev)
     tw_w, tw_h = bands.twiddles(W, dev), bands.twiddles(H, dev)
     C.call("fcvsr_fft_r2c_w", xd.data_ptr(), Cc, spec.data_ptr(), tw_w.data_ptr(), 2, H, W, Cc, _st())
-    C.call("fcvsr_fft_c2c_h", spec.data_ptr(), spec.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 0, 1.0, _st())
+    C.call("fcvsr_fft_c2c_h", spec.data_ptr(), spec.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 0, 1.0, 0, _st())
     ref = torch.fft.rfft2(x)
     got = torch.view_as_complex(spec.cpu()).permute(0, 3, 1, 2)
     assert float((got - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
@@ -59,7 +59,7 @@ def test_fft_kernels_match_torch_fft(dev, H, W, Cc):
     z = torch.randn(2, Cc, H, Wf, dtype=torch.complex64, generator=g)
     zd = torch.view_as_real(z.permute(0, 2, 3, 1).contiguous()).contiguous().to(dev)
     y = torch.empty(2, H, W, Cc, device=dev)
-    C.call("fcvsr_fft_c2c_h", zd.data_ptr(), zd.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 1, 1.0, _st())
+    C.call("fcvsr_fft_c2c_h", zd.data_ptr(), zd.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 1, 1.0, 0, _st())
     C.call("fcvsr_fft_c2r_w", zd.data_ptr(), y.data_ptr(), Cc, tw_w.data_ptr(), 2, H, W, Cc, 1.0 / (H * W), _st())
     ref2 = torch.fft.irfft2(z, s=(H, W))
     assert float((nchw(y.cpu()) - ref2).abs().max()) <= 2e-6 * float(ref2.abs().max())
@@ -85,10 +85,10 @@ def _run_conv(dev, x, w, b, tc, act=0, slope=0.0, res=None, ps=False, stride=1):
     rptr = rd.data_ptr() if rd is not None else 0
     if tc:
         C.call("fcvsr_conv2d_tc", xd.data_ptr(), Cin, pk.w_tc.data_ptr(), bias, rptr, cout, 0, 0, y.data_ptr(),
-               y.shape[-1], B, H, W, Cin, cout, w.shape[-1], act, slope, 0, int(ps), _st())
+               y.shape[-1], B, H, W, Cin, cout, w.shape[-1], act, slope, 0, int(ps), 0, 0, 0, _st())
     else:
         C.call("fcvsr_conv2d_direct", xd.data_ptr(), Cin, 0, pk.w_direct.data_ptr(), bias, rptr, cout, 0, 0,
-               y.data_ptr(), y.shape[-1], B, H, W, Cin, cout, w.shape[-1], stride, act, slope, 0, int(ps), 0, _st())
+               y.data_ptr(), y.shape[-1], B, H, W, Cin, cout, w.shape[-1], stride, act, slope, 0, int(ps), 0, 0, 0, 0, _st())
     torch.cuda.synchronize()
     return nchw(y.cpu())
 
@@ -143,7 +143,7 @@ def test_conv_tc_reports_unsupported_shapes(dev):
     w = torch.zeros(64, 48, device=dev)
     y = torch.zeros(1, 8, 8, 64, device=dev)
     rc = C.try_call("fcvsr_conv2d_tc", x.data_ptr(), 48, w.data_ptr(), 0, 0, 0, 0, 0, y.data_ptr(), 64, 1, 8, 8, 48, 64, 1,
-                    0, 0.0, 0, 0, _st())
+                    0, 0.0, 0, 0, 0, 0, 0, _st())
     assert rc == C.ERR_UNSUPPORTED          # Cin % 32 != 0 -> caller must use fcvsr_conv2d_direct
 
 
