@@ -27,6 +27,7 @@
 // = 2 * Cin * Cout * k * k; algorithmic HBM bytes per pixel = 4 * (Cin + Cout) (+4*Cout per residual).
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 #define TC_TH 8
 #define TC_TW 16
@@ -51,6 +52,7 @@ struct ConvTcParams {
     int tiles_x, tiles_y, total_tiles;
     int act; float slope; const float* slope_ptr; int ps;
     int* err;
+    int dbg;                             // bring-up only (FCVSR_TC_DBG): 1 no MMA, 2 no A loads, 4 no B loads, 8 no stores
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -134,6 +136,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const ConvTcParams& p) {
     return c;
 }
 
+template <int KS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -150,13 +153,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint32_t* tmem_slot = (uint32_t*)(tm_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int taps = p.ks * p.ks;
-    const int ncopies = p.ks == 3 ? 3 : 1;
-    const int nrows = p.ks == 3 ? TC_TH + 2 : TC_TH;
+    const int ncopies = KS == 3 ? 3 : 1;
+    const int nrows = KS == 3 ? TC_TH + 2 : TC_TH;
     const int kchunks = p.Cin / TC_KCH;
     const uint32_t a_copy_bytes = (uint32_t)nrows * TC_TW * TC_ROW_BYTES;
     const uint32_t b_bytes = (uint32_t)p.n_tile * TC_ROW_BYTES;      // multiple of 2048 (n_tile % 16 == 0): stays 1024-aligned
-    const int nb_stages = min(TC_NB_MAX, (int)(TC_B_RING_BYTES / b_bytes));
+    const uint32_t b_stage_bytes = b_bytes * KS;                    // one filter row of taps per stage
+    const int nb_stages = min(TC_NB_MAX, (int)(TC_B_RING_BYTES / b_stage_bytes));
     const uint32_t tmem_cols = p.n_tile <= 16 ? 32 : (p.n_tile <= 32 ? 64 : (p.n_tile <= 64 ? 128 : 256));
 
     if (threadIdx.x == 0) {
@@ -181,9 +184,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
-                const int y0 = tc.ty * TC_TH - (p.ks == 3 ? 1 : 0), x0 = tc.tx * TC_TW - (p.ks == 3 ? 1 : 0);
+                const int y0 = tc.ty * TC_TH - (KS == 3 ? 1 : 0), x0 = tc.tx * TC_TW - (KS == 3 ? 1 : 0);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&empty_a[stage], phase ^ 1, p.err, 1);
+                    if (p.dbg & 2) { mbar_arrive(&full_a[stage]); if (++stage == TC_NA) { stage = 0; phase ^= 1; } continue; }
                     mbar_expect_tx(&full_a[stage], a_copy_bytes * ncopies);
                     uint8_t* dst = a_buf + stage * TC_A_STAGE_BYTES;
                     for (int cpy = 0; cpy < ncopies; ++cpy)
@@ -193,46 +197,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===== B producer: one [n_tile][32] weight slice per (chunk, tap) =====
+        // ===== B producer: one stage = the KS taps of one filter row for one 32-channel chunk =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
                 for (int kc = 0; kc < kchunks; ++kc)
-                    for (int tap = 0; tap < taps; ++tap) {
+                    for (int ky = 0; ky < KS; ++ky) {
                         mbar_wait(&empty_b[stage], phase ^ 1, p.err, 2);
-                        mbar_expect_tx(&full_b[stage], b_bytes);
-                        tma_load_2d(b_buf + stage * b_bytes, &map_w, &full_b[stage], tap * p.Cin + kc * TC_KCH,
-                                    tc.nt * p.n_tile);
+                        if (p.dbg & 4) { mbar_arrive(&full_b[stage]); if (++stage == nb_stages) { stage = 0; phase ^= 1; } continue; }
+                        mbar_expect_tx(&full_b[stage], b_bytes * KS);
+#pragma unroll
+                        for (int kx = 0; kx < KS; ++kx)
+                            tma_load_2d(b_buf + stage * b_stage_bytes + kx * b_bytes, &map_w, &full_b[stage],
+                                        (ky * KS + kx) * p.Cin + kc * TC_KCH, tc.nt * p.n_tile);
                         if (++stage == nb_stages) { stage = 0; phase ^= 1; }
                     }
             }
         }
     } else if (warp == 2) {
         // ===== MMA issuer (one elected lane) =====
+        // Descriptors are formed once per stage and advanced by constant adds: the uniform-datapath chain
+        // of a full make_desc() per instruction costs ~130 clk/MMA, 3x the tensor pipe's 48 clk (N=64).
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t b_step = b_bytes >> 4;
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int acc = 0; uint32_t pacc = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 mbar_wait(&tm_empty[acc], pacc ^ 1, p.err, 3);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-                uint32_t first = 1;
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&full_a[sa], pa, p.err, 4);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_buf + sa * TC_A_STAGE_BYTES);
-                    for (int tap = 0; tap < taps; ++tap) {
+                    const uint64_t a_desc0 = make_desc(smem_u32(a_buf + sa * TC_A_STAGE_BYTES));
+#pragma unroll
+                    for (int ky = 0; ky < KS; ++ky) {
                         mbar_wait(&full_b[sb], pb, p.err, 5);
                         tc_fence_after();
-                        const int ky = tap / p.ks, kx = tap - ky * p.ks;
-                        const uint32_t a_addr = a_base + (uint32_t)kx * TC_A_COPY_BYTES + (uint32_t)ky * (TC_TW * TC_ROW_BYTES);
-                        const uint32_t b_addr = smem_u32(b_buf + sb * b_bytes);
+                        const uint64_t b_desc0 = make_desc(smem_u32(b_buf + sb * b_stage_bytes));
+                        if (!(p.dbg & 1)) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_tf32(d_tmem, make_desc(a_addr + k * 32), make_desc(b_addr + k * 32), idesc, first ? 0u : 1u);
-                            first = 0;
+                            for (int kx = 0; kx < KS; ++kx) {
+                                const uint64_t a_d = a_desc0 + (uint64_t)((kx * TC_A_COPY_BYTES + ky * (TC_TW * TC_ROW_BYTES)) >> 4);
+                                const uint64_t b_d = b_desc0 + (uint64_t)(kx * b_step);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_tf32(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc, (kc | ky | kx | k) ? 1u : 0u);
+                            }
                         }
                         umma_commit(&empty_b[sb]);
                         if (++sb == nb_stages) { sb = 0; pb ^= 1; }
@@ -264,6 +277,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 uint32_t r[16];
                 tmem_ld16(taddr + cb, r);
                 tmem_ld_wait();
+                if (p.dbg & 8) continue;
                 if (valid && p.cout_valid < p.Cout) {
                     // thin head (Cout in {1,4}): scalar stores of the first cout_valid columns
                     const int n0 = tc.nt * p.n_tile + cb;
@@ -425,6 +439,7 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     p.total_tiles = p.tiles_x * p.tiles_y * B * n_tiles;
     p.act = act; p.slope = slope; p.slope_ptr = slope_ptr; p.ps = pixel_shuffle;
     p.err = tc_err_flag();
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FCVSR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
 
     static int num_sms = 0;
     static bool attr_set = false;
@@ -433,11 +448,13 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return FCVSR_ERR_CUDA;
         attr_set = true;
     }
     const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+    if (ksize == 3) conv_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+    else conv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
     return fcvsr_launch_status();
 }

@@ -1,0 +1,33 @@
+"""Bring-up helper: time conv_tc on the trunk shapes (CUDA events, 20 reps)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fcvsr_b200 import _capi as C  # noqa: E402
+from fcvsr_b200.engine import _ConvPack  # noqa: E402
+
+dev = torch.device("cuda:0")
+st = torch.cuda.current_stream().cuda_stream
+shapes = [(1, 64, 64, 180, 320, 3), (1, 64, 128, 180, 320, 3), (1, 128, 64, 180, 320, 3), (1, 64, 64, 90, 160, 3),
+          (1, 64, 64, 45, 80, 3), (1, 64, 64, 180, 320, 1), (1, 64, 1152, 180, 320, 1), (1, 64, 256, 360, 640, 3),
+          (4, 64, 64, 180, 320, 3)]
+print("FCVSR_TC_DBG =", os.environ.get("FCVSR_TC_DBG", "0"))
+for (B, ci, co, H, W, k) in shapes:
+    x = torch.randn(B, H, W, ci, device=dev)
+    w = torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5
+    pk = _ConvPack(w, None)
+    y = torch.empty(B, H, W, co, device=dev)
+    args = (x.data_ptr(), ci, pk.w_tc.data_ptr(), 0, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, k, 0, 0.0, 0, 0, 0, 0, 0, st)
+    for _ in range(3):
+        C.call("fcvsr_conv2d_tc", *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        C.call("fcvsr_conv2d_tc", *args)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    fl = 2.0 * B * H * W * ci * co * k * k
+    print(f"B{B} {ci}->{co} {H}x{W} k{k}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s")
