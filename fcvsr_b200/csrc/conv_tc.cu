@@ -385,7 +385,7 @@ static int* tc_err_flag() {
 extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
                                const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
                                int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
-                               float* y2, int ldy2, int round_out, cudaStream_t st) {
+                               float* y2, int ldy2, int round_out, int max_ctas, cudaStream_t st) {
     if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
     if ((ksize != 1 && ksize != 3) || Cin % TC_KCH || Cin <= 0 || Cout <= 0) return FCVSR_ERR_UNSUPPORTED;
     const int cout_valid = Cout;
@@ -453,7 +453,8 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
             return FCVSR_ERR_CUDA;
         attr_set = true;
     }
-    const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;   // leave SMs to kernels running on other streams
     if (ksize == 3) conv_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
     else conv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
     return fcvsr_launch_status();

@@ -72,50 +72,67 @@ __global__ void __launch_bounds__(256) ctx_partial_kernel(const float* __restric
     }
 }
 
-// grid B, 256 threads: merge the block partials (fixed order) -> context[64] -> add = W2 lrelu_0.2(W1 ctx)
-__global__ void __launch_bounds__(256) ctx_finalize_kernel(const float* __restrict__ partial, int nblk,
-                                                           const float* __restrict__ w1, const float* __restrict__ w2,
-                                                           float* __restrict__ add) {
-    __shared__ float red[256];
-    __shared__ float part[4][64];
+// grid B, 1024 threads: merge the block partials (fixed order) -> context[64] -> add = W2 lrelu_0.2(W1 ctx).
+// 16 thread groups x 64 channels walk the partial list with 4 independent loads in flight each.
+__global__ void __launch_bounds__(1024) ctx_finalize_kernel(const float* __restrict__ partial, int nblk,
+                                                            const float* __restrict__ w1, const float* __restrict__ w2,
+                                                            float* __restrict__ add) {
+    __shared__ float red[1024];
+    __shared__ float part[16][64];
     __shared__ float ctx[64], hid[64];
     const int b = blockIdx.x, t = threadIdx.x;
     const float* pp = partial + (size_t)b * nblk * CTX_STRIDE;
     float M = -INFINITY;
-    for (int k = t; k < nblk; k += 256) M = fmaxf(M, pp[k * CTX_STRIDE]);
+    for (int k = t; k < nblk; k += 1024) M = fmaxf(M, pp[k * CTX_STRIDE]);
     red[t] = M;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = 512; s > 0; s >>= 1) {
         if (t < s) red[t] = fmaxf(red[t], red[t + s]);
         __syncthreads();
     }
     M = red[0];
     __syncthreads();
     float Z = 0.f;
-    for (int k = t; k < nblk; k += 256) Z += pp[k * CTX_STRIDE + 1] * __expf(pp[k * CTX_STRIDE] - M);
+    for (int k = t; k < nblk; k += 1024) Z += pp[k * CTX_STRIDE + 1] * __expf(pp[k * CTX_STRIDE] - M);
     red[t] = Z;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = 512; s > 0; s >>= 1) {
         if (t < s) red[t] += red[t + s];
         __syncthreads();
     }
     Z = red[0];
     const int c = t & 63, q = t >> 6;
     float A = 0.f;
-    for (int k = q; k < nblk; k += 4) A += pp[k * CTX_STRIDE + 2 + c] * __expf(pp[k * CTX_STRIDE] - M);
+    int k = q;
+    for (; k + 48 < nblk; k += 64) {
+        const float m0 = pp[k * CTX_STRIDE], m1 = pp[(k + 16) * CTX_STRIDE], m2 = pp[(k + 32) * CTX_STRIDE],
+                    m3 = pp[(k + 48) * CTX_STRIDE];
+        const float a0 = pp[k * CTX_STRIDE + 2 + c], a1 = pp[(k + 16) * CTX_STRIDE + 2 + c],
+                    a2 = pp[(k + 32) * CTX_STRIDE + 2 + c], a3 = pp[(k + 48) * CTX_STRIDE + 2 + c];
+        A += a0 * __expf(m0 - M);
+        A += a1 * __expf(m1 - M);
+        A += a2 * __expf(m2 - M);
+        A += a3 * __expf(m3 - M);
+    }
+    for (; k < nblk; k += 16) A += pp[k * CTX_STRIDE + 2 + c] * __expf(pp[k * CTX_STRIDE] - M);
     part[q][c] = A;
     __syncthreads();
-    if (t < 64) ctx[t] = (part[0][t] + part[1][t] + part[2][t] + part[3][t]) / Z;
+    if (t < 64) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += part[j][t];
+        ctx[t] = s / Z;
+    }
     __syncthreads();
     if (t < 64) {
         float h = 0.f;
-        for (int k = 0; k < 64; ++k) h += w1[t * 64 + k] * ctx[k];
+        for (int j = 0; j < 64; ++j) h += w1[t * 64 + j] * ctx[j];
         hid[t] = h >= 0.f ? h : 0.2f * h;
     }
     __syncthreads();
     if (t < 64) {
         float o = 0.f;
-        for (int k = 0; k < 64; ++k) o += w2[t * 64 + k] * hid[k];
+        for (int j = 0; j < 64; ++j) o += w2[t * 64 + j] * hid[j];
         add[(size_t)b * 64 + t] = o;
     }
 }
@@ -125,7 +142,7 @@ extern "C" int fcvsr_context_block(const float* x, int ldx, const float* wmask, 
     if (!x || !wmask || !w1 || !w2 || !partial || !add || (ldx & 1)) return FCVSR_ERR_ARG;
     const int nblk = (P + CTX_PIX_PER_BLOCK - 1) / CTX_PIX_PER_BLOCK;
     ctx_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, ldx, wmask, partial, P);
-    ctx_finalize_kernel<<<B, 256, 0, st>>>(partial, nblk, w1, w2, add);
+    ctx_finalize_kernel<<<B, 1024, 0, st>>>(partial, nblk, w1, w2, add);
     return fcvsr_launch_status();
 }
 

@@ -88,6 +88,9 @@ class Engine:
         self.tc_launches = 0
         self.use_graph = False       # replay the launch sequence from a CUDA graph (one per input shape)
         self._graphs: Dict[tuple, tuple] = {}
+        self.max_ctas = 0            # grid cap of the tensor-core convs on the current stream (0 = all SMs)
+        self.multi_stream = True     # run the three pyramid levels of SCNetbk on three streams
+        self._streams = {}
         self.profile = None          # optional list: (kind, flops, start_event, end_event) per conv launch
         C.lib()                      # fail loudly now if the library is missing
 
@@ -291,7 +294,7 @@ class Engine:
         if self.use_tc and pk.tc_ok and not nchw:
             rc = C.try_call("fcvsr_conv2d_tc", x, ldx, pk.w_tc.data_ptr(), pk.bias.data_ptr() if pk.bias is not None else 0,
                             res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin, pk.cout, pk.k, act, slope, slope_ptr,
-                            int(pk.ps), y2, ldy2, int(rnd), st)
+                            int(pk.ps), y2, ldy2, int(rnd), self.max_ctas, st)
             if rc == 0:
                 self.tc_launches += 1
                 return
@@ -466,12 +469,43 @@ class Engine:
         if self.use_tc:
             self._k("fcvsr_round_copy", p["xs0"], 64, p["xsr0"], 64, 64, B * npix)
 
-    # SCNetbk (:807-822)
+    # SCNetbk (:807-822).  The three pyramid levels of a BlockRCB are independent until the cross-level
+    # sum, so each level runs on its own stream (fork/join with events; also valid under graph capture):
+    # the small levels (1/4 and 1/16 of the pixels) are latency-bound launches that hide behind level 0.
     def _scnet(self, ws, p, B, H, W):
         P, G = self.packs, self.model.SCGroupN
         dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
         LK = C.ACT_LEAKY
         R = int(self.use_tc)
+        main = torch.cuda.current_stream()
+        ms = self.multi_stream and self.profile is None
+        if ms:
+            dev = main.device
+            if dev not in self._streams:
+                self._streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            streams = (main,) + self._streams[dev]
+            caps = (116, 24, 8)          # SMs left to each level's persistent conv grid (sum = 148)
+            for s_ in streams[1:]:
+                s_.wait_stream(main)
+        else:
+            streams, caps = (main, main, main), (0, 0, 0)
+
+        def on(l):
+            self.st = streams[l].cuda_stream
+            self.max_ctas = caps[l]
+            return torch.cuda.stream(streams[l])
+
+        def cross_join():
+            if not ms:
+                return
+            evs = [torch.cuda.Event() for _ in range(3)]
+            for l in range(3):
+                evs[l].record(streams[l])
+            for l in range(3):
+                for o in range(3):
+                    if o != l:
+                        streams[l].wait_event(evs[o])
+
         for g in range(G):
             inp = [p[f"xs{l}"] if g == 0 else p[f"cur{l}"] for l in range(3)]
             inp_r = [p[f"xsr{l}"] if g == 0 else p[f"curr{l}"] for l in range(3)] if R else inp
@@ -480,30 +514,45 @@ class Engine:
                 src = inp if k == 0 else [p[f"t{l}"] for l in range(3)]
                 src_r = (inp_r if k == 0 else [p[f"tr{l}"] for l in range(3)]) if R else src
                 for l, (h, w) in enumerate(dims):      # BlockRCB body (:729-751) + RCB (:705-725)
-                    self._conv(P[q + "c0"], src_r[l], 64, p[f"a128_{l}"], 128, B, h, w, act=LK, slope=0.1, rnd=True)
-                    self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w, rnd=True)
-                    self._conv(P[q + "r0"], p[f"r0{l}"], 64, p[f"c1{l}"], 64, B, h, w, act=LK, slope=0.2, rnd=True)
-                    self._conv(P[q + "r2"], p[f"c1{l}"], 64, p[f"res{l}"], 64, B, h, w)
-                    self.launches += 1
-                    self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
-                            P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w)
-                    self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w, R)
-                for l in (0, 1):                        # down: 1x1 conv, pooled in level_mix (:753-757)
-                    self._conv(P[q + "down"], p[f"rr{l}"], 64, p[f"td{l}"], 64, B, dims[l][0], dims[l][1])
-                for l in (1, 2):                        # up: 1x1 conv, interpolated in level_mix (:759-763)
-                    self._conv(P[q + "up"], p[f"rr{l}"], 64, p[f"tu{l}"], 64, B, dims[l][0], dims[l][1])
+                    with on(l):
+                        self._conv(P[q + "c0"], src_r[l], 64, p[f"a128_{l}"], 128, B, h, w, act=LK, slope=0.1, rnd=True)
+                        self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w, rnd=True)
+                        self._conv(P[q + "r0"], p[f"r0{l}"], 64, p[f"c1{l}"], 64, B, h, w, act=LK, slope=0.2, rnd=True)
+                        self._conv(P[q + "r2"], p[f"c1{l}"], 64, p[f"res{l}"], 64, B, h, w)
+                        self.launches += 1
+                        self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
+                                P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w)
+                        self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w, R)
+                        if l < 2:                       # down: 1x1 conv, pooled in level_mix (:753-757)
+                            self._conv(P[q + "down"], p[f"rr{l}"], 64, p[f"td{l}"], 64, B, h, w)
+                        if l > 0:                       # up: 1x1 conv, interpolated in level_mix (:759-763)
+                            self._conv(P[q + "up"], p[f"rr{l}"], 64, p[f"tu{l}"], 64, B, h, w)
+                cross_join()
                 # x + r + d + u (:771-776): level 0 has d = r, level 2 has u = r
                 tr = [p[f"tr{l}"] if R else 0 for l in range(3)]
-                self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0)
-                self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0)
-                self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0)
+                with on(0):
+                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0)
+                with on(1):
+                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0)
+                with on(2):
+                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0)
+                cross_join()                            # td/tu/rr of this block are overwritten by the next one
             for l, (h, w) in enumerate(dims):           # SCGroupbk tail: x + conv(res) (:797-803)
-                self._conv(P[f"g{g}.conv"], p[f"tr{l}"] if R else p[f"t{l}"], 64, p[f"cur{l}"], 64, B, h, w, res=inp[l],
-                           ldres=64, y2=p[f"curr{l}"], ldy2=64)
+                with on(l):
+                    self._conv(P[f"g{g}.conv"], p[f"tr{l}"] if R else p[f"t{l}"], 64, p[f"cur{l}"], 64, B, h, w, res=inp[l],
+                               ldres=64, y2=p[f"curr{l}"], ldy2=64)
         # SCNetbk skip (:816-822): level 0 lands in the 84(96)-channel fuse buffer
-        self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], 96, p["cur0"], 1.0, 0, 0, B, *dims[0], 0, 0, R)
-        self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1], 0, 0, R)
-        self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2], 0, 0, R)
+        with on(0):
+            self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], 96, p["cur0"], 1.0, 0, 0, B, *dims[0], 0, 0, R)
+        with on(1):
+            self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1], 0, 0, R)
+        with on(2):
+            self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2], 0, 0, R)
+        if ms:
+            for s_ in streams[1:]:
+                main.wait_stream(s_)
+        self.st = main.cuda_stream
+        self.max_ctas = 0
 
     # pyramid fuse + up-sampler (:2739-2751)
     def _tail(self, x, out, ws, p, B, H, W):

@@ -50,11 +50,12 @@ int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const float* w, con
  * Cout <= 256), TF32 operands / fp32 accumulate, same fused epilogue as above.
  * w packed [Cout][k*k][Cin] (K-major).  x, y, w, res must be 16-byte aligned, ld multiples of 4.
  * Replaces every 3x3 / 1x1 nn.Conv2d of MGAAbk (CVSR_freq.py:1371-1430), SCNetbk (:705-822) and the
- * up-sampling tail (:2739-2749).  Returns FCVSR_ERR_UNSUPPORTED for shapes outside the envelope. */
+ * up-sampling tail (:2739-2749).  Returns FCVSR_ERR_UNSUPPORTED for shapes outside the envelope.
+ * max_ctas > 0 caps the persistent grid (pyramid levels run concurrently on separate streams). */
 int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
                     const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
                     int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
-                    float* y2, int ldy2, int round_out, cudaStream_t stream);
+                    float* y2, int ldy2, int round_out, int max_ctas, cudaStream_t stream);
 
 /* ---- FFT (torch.fft.rfft2 / irfft2 / fftn / ifftn of CVSR_freq.py:1452-1454, :1499-1504, :2082-2088) */
 

@@ -85,7 +85,7 @@ def _run_conv(dev, x, w, b, tc, act=0, slope=0.0, res=None, ps=False, stride=1):
     rptr = rd.data_ptr() if rd is not None else 0
     if tc:
         C.call("fcvsr_conv2d_tc", xd.data_ptr(), Cin, pk.w_tc.data_ptr(), bias, rptr, cout, 0, 0, y.data_ptr(),
-               y.shape[-1], B, H, W, Cin, cout, w.shape[-1], act, slope, 0, int(ps), 0, 0, 0, _st())
+               y.shape[-1], B, H, W, Cin, cout, w.shape[-1], act, slope, 0, int(ps), 0, 0, 0, 0, _st())
     else:
         C.call("fcvsr_conv2d_direct", xd.data_ptr(), Cin, 0, pk.w_direct.data_ptr(), bias, rptr, cout, 0, 0,
                y.data_ptr(), y.shape[-1], B, H, W, Cin, cout, w.shape[-1], stride, act, slope, 0, int(ps), 0, 0, 0, 0, _st())
@@ -143,7 +143,7 @@ def test_conv_tc_reports_unsupported_shapes(dev):
     w = torch.zeros(64, 48, device=dev)
     y = torch.zeros(1, 8, 8, 64, device=dev)
     rc = C.try_call("fcvsr_conv2d_tc", x.data_ptr(), 48, w.data_ptr(), 0, 0, 0, 0, 0, y.data_ptr(), 64, 1, 8, 8, 48, 64, 1,
-                    0, 0.0, 0, 0, 0, 0, 0, _st())
+                    0, 0.0, 0, 0, 0, 0, 0, 0, _st())
     assert rc == C.ERR_UNSUPPORTED          # Cin % 32 != 0 -> caller must use fcvsr_conv2d_direct
 
 

@@ -19,7 +19,7 @@ for (B, ci, co, H, W, k) in shapes:
     w = torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5
     pk = _ConvPack(w, None)
     y = torch.empty(B, H, W, co, device=dev)
-    args = (x.data_ptr(), ci, pk.w_tc.data_ptr(), 0, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, k, 0, 0.0, 0, 0, 0, 0, 0, st)
+    args = (x.data_ptr(), ci, pk.w_tc.data_ptr(), 0, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, k, 0, 0.0, 0, 0, 0, 0, 0, 0, st)
     for _ in range(3):
         C.call("fcvsr_conv2d_tc", *args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -72,7 +72,7 @@ def run_conv(x, w, b, tc, act=0, slope=0.0, res=None, ps=False, stride=1):
     if tc:
         C.call("fcvsr_conv2d_tc", xd.data_ptr(), Cin, pk.w_tc.data_ptr(), pk.bias.data_ptr() if b is not None else 0,
                rd.data_ptr() if rd is not None else 0, cout, 0, 0, y.data_ptr(), y.shape[-1], B, H, W, Cin, cout,
-               w.shape[-1], act, slope, 0, int(ps), 0, 0, 0, st())
+               w.shape[-1], act, slope, 0, int(ps), 0, 0, 0, 0, st())
     else:
         C.call("fcvsr_conv2d_direct", xd.data_ptr(), Cin, 0, pk.w_direct.data_ptr(),
                pk.bias.data_ptr() if b is not None else 0, rd.data_ptr() if rd is not None else 0, cout, 0, 0,
