@@ -200,10 +200,43 @@ struct IacArgs {
     int B, H, W; int round_out;
 };
 
-__global__ void __launch_bounds__(256) iac_step_kernel(IacArgs a) {
+#define IAC_THREADS 512
+#define IAC_WARPS (IAC_THREADS / 32)
+#define IAC_HALO ((IAC_TH + 2) * (IAC_TW + 2))
+
+// bilinear gather of one (pixel, 2-channel) sample; corners outside the image contribute zero
+__device__ __forceinline__ float2 iac_gather(const float* __restrict__ prev, int ldp, size_t img, int H, int W, float sx,
+                                             float sy, int lane) {
+    float2 acc = make_float2(0.f, 0.f);
+    if (!(sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H)) return acc;   // also rejects NaN / inf offsets
+    const float fx0 = floorf(sx), fy0 = floorf(sy);
+    const float lx = sx - fx0, ly = sy - fy0;
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    float2 v[4];
+    float wg[4];
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy)
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+            const int y = y0 + cy, x = x0 + cx;
+            const bool ok = y >= 0 && y < H && x >= 0 && x < W;
+            wg[cy * 2 + cx] = ok ? (cy ? ly : 1.f - ly) * (cx ? lx : 1.f - lx) : 0.f;
+            v[cy * 2 + cx] = ok ? *reinterpret_cast<const float2*>(prev + (img + (size_t)y * W + x) * ldp + 2 * lane)
+                                : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc.x = fmaf(wg[i], v[i].x, acc.x);
+        acc.y = fmaf(wg[i], v[i].y, acc.y);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(IAC_THREADS) iac_step_kernel(IacArgs a) {
     extern __shared__ float smem[];
     float* samp = smem;                                             // [(TH+2)*(TW+2)][64]
-    float* vbuf = smem + (IAC_TH + 2) * (IAC_TW + 2) * IAC_C;       // [TH*(TW+2)][64]
+    float* vbuf = smem + IAC_HALO * IAC_C;                          // [TH*(TW+2)][64]
+    float2* offs_s = reinterpret_cast<float2*>(vbuf + IAC_TH * (IAC_TW + 2) * IAC_C);   // [(TH+2)*(TW+2)] sample coords
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_x = (a.W + IAC_TW - 1) / IAC_TW;
     const int ty0 = (blockIdx.x / tiles_x) * IAC_TH, tx0 = (blockIdx.x % tiles_x) * IAC_TW;
@@ -213,51 +246,41 @@ __global__ void __launch_bounds__(256) iac_step_kernel(IacArgs a) {
     const int H = a.H, W = a.W;
     const size_t img = (size_t)b * H * W;
 
-    // phase 1: warped samples on the haloed tile (coordinates clamped == replicate padding)
-    for (int hp = warp; hp < (IAC_TH + 2) * (IAC_TW + 2); hp += 8) {
+    // phase 0: sample coordinates of the haloed tile (clamped pixel == replicate padding), one per thread
+    for (int hp = threadIdx.x; hp < IAC_HALO; hp += IAC_THREADS) {
         const int hy = hp / (IAC_TW + 2), hx = hp - hy * (IAC_TW + 2);
         const int yy = min(max(ty0 - 1 + hy, 0), H - 1), xx = min(max(tx0 - 1 + hx, 0), W - 1);
         const float2 d = *reinterpret_cast<const float2*>(a.offs + (img + (size_t)yy * W + xx) * a.ldoffs + a.offs_ch[dir]);
-        const float sx = (float)xx + d.x, sy = (float)yy + d.y;
-        const float fx0 = floorf(sx), fy0 = floorf(sy);
-        const float lx = sx - fx0, ly = sy - fy0;
-        float2 acc = make_float2(0.f, 0.f);
-        // guard against inf/nan/huge offsets: anything outside contributes zero
-        if (sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H) {
-            const int x0 = (int)fx0, y0 = (int)fy0;
-#pragma unroll
-            for (int cy = 0; cy < 2; ++cy) {
-                const int y = y0 + cy;
-                if (y < 0 || y >= H) continue;
-                const float wy = cy ? ly : 1.f - ly;
-#pragma unroll
-                for (int cx = 0; cx < 2; ++cx) {
-                    const int x = x0 + cx;
-                    if (x < 0 || x >= W) continue;
-                    const float wgt = wy * (cx ? lx : 1.f - lx);
-                    const float2 v = *reinterpret_cast<const float2*>(prev + (img + (size_t)y * W + x) * ldp + 2 * lane);
-                    acc.x = fmaf(wgt, v.x, acc.x);
-                    acc.y = fmaf(wgt, v.y, acc.y);
-                }
-            }
-        }
-        *reinterpret_cast<float2*>(samp + hp * IAC_C + 2 * lane) = acc;
+        offs_s[hp] = make_float2((float)xx + d.x, (float)yy + d.y);
+    }
+    __syncthreads();
+    // phase 1: warped samples, two halo pixels (8 independent 256-byte gathers) in flight per warp
+    for (int hp = warp; hp < IAC_HALO; hp += 2 * IAC_WARPS) {
+        const int hp2 = hp + IAC_WARPS;
+        const float2 c0 = offs_s[hp];
+        const float2 c1 = hp2 < IAC_HALO ? offs_s[hp2] : make_float2(-2.f, -2.f);
+        const float2 s0 = iac_gather(prev, ldp, img, H, W, c0.x, c0.y, lane);
+        const float2 s1 = iac_gather(prev, ldp, img, H, W, c1.x, c1.y, lane);
+        *reinterpret_cast<float2*>(samp + hp * IAC_C + 2 * lane) = s0;
+        if (hp2 < IAC_HALO) *reinterpret_cast<float2*>(samp + hp2 * IAC_C + 2 * lane) = s1;
     }
     __syncthreads();
     // phase 2: vertical pass for TH rows x (TW+2) columns
-    for (int vp = warp; vp < IAC_TH * (IAC_TW + 2); vp += 8) {
+    for (int vp = warp; vp < IAC_TH * (IAC_TW + 2); vp += IAC_WARPS) {
         const int ly = vp / (IAC_TW + 2), hx = vp - ly * (IAC_TW + 2);
         const int y = ty0 + ly;
         const int xx = min(max(tx0 - 1 + hx, 0), W - 1);
         float2 acc = make_float2(0.f, 0.f);
         if (y < H) {
             const float* kp = a.taps + (img + (size_t)y * W + xx) * a.ldtaps + 2 * lane;
+            float2 k[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) k[t] = *reinterpret_cast<const float2*>(kp + t * IAC_C);
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
-                const float2 k = *reinterpret_cast<const float2*>(kp + t * IAC_C);
                 const float2 s = *reinterpret_cast<const float2*>(samp + ((ly + t) * (IAC_TW + 2) + hx) * IAC_C + 2 * lane);
-                acc.x = fmaf(k.x, s.x, acc.x);
-                acc.y = fmaf(k.y, s.y, acc.y);
+                acc.x = fmaf(k[t].x, s.x, acc.x);
+                acc.y = fmaf(k[t].y, s.y, acc.y);
             }
         }
         *reinterpret_cast<float2*>(vbuf + vp * IAC_C + 2 * lane) = acc;
@@ -266,18 +289,20 @@ __global__ void __launch_bounds__(256) iac_step_kernel(IacArgs a) {
     // phase 3: horizontal pass + residual + LeakyReLU(0.1)
     const float* xin = a.xin[dir];
     float* next = a.next[dir];
-    for (int op = warp; op < IAC_TH * IAC_TW; op += 8) {
+    for (int op = warp; op < IAC_TH * IAC_TW; op += IAC_WARPS) {
         const int ly = op / IAC_TW, lxp = op - ly * IAC_TW;
         const int y = ty0 + ly, x = tx0 + lxp;
         if (y >= H || x >= W) continue;
         const float* kp = a.taps + (img + (size_t)y * W + x) * a.ldtaps + 2 * lane;
+        float2 k[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) k[t] = *reinterpret_cast<const float2*>(kp + t * IAC_C);
         float2 acc = *reinterpret_cast<const float2*>(xin + (img + (size_t)y * W + x) * a.ldxin[dir] + 2 * lane);
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            const float2 k = *reinterpret_cast<const float2*>(kp + t * IAC_C);
             const float2 v = *reinterpret_cast<const float2*>(vbuf + (ly * (IAC_TW + 2) + lxp + t) * IAC_C + 2 * lane);
-            acc.x = fmaf(k.x, v.x, acc.x);
-            acc.y = fmaf(k.y, v.y, acc.y);
+            acc.x = fmaf(k[t].x, v.x, acc.x);
+            acc.y = fmaf(k[t].y, v.y, acc.y);
         }
         acc.x = acc.x >= 0.f ? acc.x : 0.1f * acc.x;
         acc.y = acc.y >= 0.f ? acc.y : 0.1f * acc.y;
@@ -299,7 +324,7 @@ extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* pr
     a.next[0] = next_f; a.next[1] = next_b; a.ldnext[0] = ldnext_f; a.ldnext[1] = ldnext_b;
     a.offs = offs; a.ldoffs = ldoffs; a.offs_ch[0] = ch_f; a.offs_ch[1] = ch_b;
     a.taps = taps; a.ldtaps = ldtaps; a.B = B; a.H = H; a.W = W; a.round_out = round_out;
-    const size_t smem = ((IAC_TH + 2) * (IAC_TW + 2) + IAC_TH * (IAC_TW + 2)) * IAC_C * sizeof(float);
+    const size_t smem = (IAC_HALO + IAC_TH * (IAC_TW + 2)) * IAC_C * sizeof(float) + IAC_HALO * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(iac_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -307,7 +332,7 @@ extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* pr
         attr_set = true;
     }
     dim3 grid(((H + IAC_TH - 1) / IAC_TH) * ((W + IAC_TW - 1) / IAC_TW), B, 2);
-    iac_step_kernel<<<grid, 256, smem, st>>>(a);
+    iac_step_kernel<<<grid, IAC_THREADS, smem, st>>>(a);
     return fcvsr_launch_status();
 }
 
