@@ -38,6 +38,7 @@ SIGNATURES = {
     "fcvsr_pixel_shuffle": "pi pi iiii s",
     "fcvsr_bilinear_up4": "p l p iii s",
     "fcvsr_fill_channels": "p iii f l s",
+    "fcvsr_pack_clip": "p p iiii s",
     "fcvsr_modulated_deform_conv_forward": "ppppp p iiii i ii ii ii ii ii ll i s",
 }
 

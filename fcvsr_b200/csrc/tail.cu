@@ -61,3 +61,21 @@ extern "C" int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, lo
     fill_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, ld, c0, nc, v, total);
     return fcvsr_launch_status();
 }
+
+// NCHW clip [B,T,H,W] (T = 7 frames, C = 1) -> NHWC [B,H,W,32] with channels >= T zeroed, TF32-rounded:
+// the tensor-core operand of feat_extract (CVSR_freq.py:2663), whose Cin = 7 is padded to one 32-channel chunk.
+__global__ void pack_clip_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int P, size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx & 31);
+    const size_t pix = idx >> 5;
+    const size_t b = pix / P, p = pix - b * P;
+    y[idx] = c < T ? round_tf32(x[(b * T + c) * P + p]) : 0.f;
+}
+
+extern "C" int fcvsr_pack_clip(const float* x, float* y, int B, int T, int H, int W, cudaStream_t st) {
+    if (!x || !y || T < 1 || T > 32) return FCVSR_ERR_ARG;
+    const size_t total = (size_t)B * H * W * 32;
+    pack_clip_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, y, T, H * W, total);
+    return fcvsr_launch_status();
+}

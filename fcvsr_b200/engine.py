@@ -115,6 +115,7 @@ class Engine:
             return _ConvPack(sd[name + ".weight"], sd.get(name + ".bias"), **kw)
 
         P["feat"] = cp("feat_extract.0")
+        P["feat_tc"] = cp("feat_extract.0", cin_pad=32)      # tensor-core path: clip packed to NHWC-32
         # --- MGAA per-bin MLPs (:1371-1396) on the interleaved spectrum ---
         ar = torch.arange(2 * n, device=device)
         perm_f = torch.cat([pi, 2 * n + pi])                     # cat[x1_f, x2_f] -> [grp0 | grp1]
@@ -209,6 +210,7 @@ class Engine:
             ws[name] = (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=F32)
 
         buf("feat", B, P, 448)
+        buf("clip32", B, P, 32)
         buf("spec", B, Pf, 384)
         buf("h1", 2 * B, Pf, 128)
         buf("h2", 2 * B, Pf, 128)
@@ -362,7 +364,11 @@ class Engine:
         npix = H * W
         f = p["feat"]
         # feat_extract (:2663): NCHW clip -> NHWC 448 channels
-        self._conv(P["feat"], x.data_ptr(), 0, f, 448, B, H, W, nchw=True)
+        if self.use_tc:
+            self._k("fcvsr_pack_clip", x.data_ptr(), p["clip32"], B, 7, H, W)
+            self._conv(P["feat_tc"], p["clip32"], 32, f, 448, B, H, W)
+        else:
+            self._conv(P["feat"], x.data_ptr(), 0, f, 448, B, H, W, nchw=True)
         # MGAA(f1) -> feat[128:192], MGAA(f3) -> feat[256:320]: cat[o1, f2, o3] (:2720) is then the
         # contiguous channel slice feat[128:320] and no concatenation is materialised.
         self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)

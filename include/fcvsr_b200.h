@@ -127,6 +127,8 @@ int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float
 int fcvsr_pixel_shuffle(const float* in, int ldi, float* out, int ldo, int B, int H, int W, int Co,
                         cudaStream_t stream);
 int fcvsr_bilinear_up4(const float* in, long long bstride, float* out, int B, int H, int W, cudaStream_t stream);
+/* NCHW clip [B,T,H,W] -> NHWC [B,H,W,32] (channels >= T zero, TF32-rounded): tensor-core operand of feat_extract */
+int fcvsr_pack_clip(const float* x, float* y, int B, int T, int H, int W, cudaStream_t stream);
 int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npix, cudaStream_t stream);
 
 /* ---- deformable convolution operator (CVSR_train/ops/dcn) --------------------------------------- */

@@ -275,3 +275,62 @@ def test_modulated_dcn_matches_oracle(dev, cfg):
         y = modulated_deform_conv(x.to(dev), off.to(dev), msk.to(dev), w.to(dev), b.to(dev), cfg["stride"], cfg["pad"],
                                   cfg["dil"], cfg["g"], dg)
     assert float((y.cpu() - ref).abs().max()) <= 1e-4
+
+
+def test_modulated_dcn_pack_module(dev):
+    """ModulatedDeformConvPack (deform_conv.py:311-337): conv_offset_mask -> chunk/cat/sigmoid -> DCN."""
+    from fcvsr_b200.ops.dcn import ModulatedDeformConvPack
+    torch.manual_seed(3)
+    m = ModulatedDeformConvPack(16, 16, 3, stride=1, padding=1, deformable_groups=4).to(dev)
+    with torch.no_grad():
+        m.conv_offset_mask.weight.normal_(0, 0.05)
+        m.conv_offset_mask.bias.normal_(0, 0.5)
+        m.bias.normal_(0, 0.1)
+        x = torch.randn(2, 16, 10, 12, device=dev)
+        y = m(x).cpu()
+        o = F.conv2d(x.cpu(), m.conv_offset_mask.weight.cpu(), m.conv_offset_mask.bias.cpu(), padding=1)
+        o1, o2, mk = torch.chunk(o, 3, dim=1)
+        ref = O.modulated_deform_conv(x.cpu(), torch.cat((o1, o2), 1), torch.sigmoid(mk), m.weight.cpu(), m.bias.cpu(),
+                                      1, 1, 1, 1, 4)
+    assert float((y - ref).abs().max()) <= 1e-4
+
+
+def test_sequence_inference_matches_oracle(dev):
+    """Sliding-window driver (replicate edges, 30 -> 32 row padding and crop) against per-window oracle calls."""
+    from fcvsr_b200 import sequence as S
+    sd = arch.seeded_state_dict("S", 2)
+    frames = make_clip(9, 1, 30, 36)[0][:5]                # 5 frames [5,1,30,36]; 30 rows -> padded to 32
+    m = _model("S", sd, dev, use_tc=False)
+    out, (lo, hi) = S.super_resolve_sequence(m, frames, batch=2)
+    assert (lo, hi) == (0, 5) and out.shape == (5, 1, 120, 144)
+    padded, _, _ = S.pad_to_multiple(frames)
+    for t in (0, 2, 4):
+        clip = padded[S.window_indices(t, 5)].unsqueeze(0)
+        with torch.no_grad():
+            ref = O.forward(sd, clip)[..., :120, :144]
+        assert float((out[t].cpu() - ref[0]).abs().max()) <= 2e-5
+
+
+def test_radix17_height_in_the_model(dev):
+    """272-row inputs (270 padded) need the radix-17 FFT pass inside MGAA / MFFR."""
+    sd = arch.seeded_state_dict("S", 4)
+    x = make_clip(11, 1, 272, 16)
+    with torch.no_grad():
+        ref = O.forward(sd, x)
+    m = _model("S", sd, dev, use_tc=False)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    assert float((y - ref).abs().max()) <= 2e-5
+
+
+def test_cuda_graph_replay_is_bit_identical(dev):
+    sd = arch.seeded_state_dict("S", 0)
+    x = make_clip(1234, 1, 32, 32).to(dev)
+    m = _model("S", sd, dev)
+    with torch.no_grad():
+        y0 = m(x).clone()
+        m._engine.use_graph = True
+        y1 = m(x).clone()
+        y2 = m(x * 0.5).clone()
+        y3 = m(x).clone()
+    assert torch.equal(y0, y1) and torch.equal(y1, y3) and not torch.equal(y1, y2)
