@@ -25,8 +25,7 @@
 //
 // Roofline: tensor (TF32: K=8 per instruction, half the bf16 rate).  Algorithmic FLOPs per output pixel
 // = 2 * Cin * Cout * k * k; algorithmic HBM bytes per pixel = 4 * (Cin + Cout) (+4*Cout per residual).
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 #define TC_TH 8
@@ -40,7 +39,6 @@
 #define TC_A_STAGE_BYTES (3 * TC_A_COPY_BYTES)                    // 61440
 
 #define TC_THREADS 224
-#define TC_SPIN_LIMIT (1u << 26)
 
 struct ConvTcParams {
     const float* bias; const float* res; int ldres; const float* res2; int ldres2;
@@ -54,78 +52,6 @@ struct ConvTcParams {
     int* err;
     int dbg;                             // bring-up only (FCVSR_TC_DBG): 1 no MMA, 2 no A loads, 4 no B loads, 8 no stores
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > TC_SPIN_LIMIT) {
-            if (err) atomicExch(err, code);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-// K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct TileCoord { int nt, tx, ty, b; };
 __device__ __forceinline__ TileCoord decode_tile(int t, const ConvTcParams& p) {
@@ -270,14 +196,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const int y = tc.ty * TC_TH + ly, x = tc.tx * TC_TW + lx;
             const bool valid = y < p.H && x < p.W;
             const size_t pix = ((size_t)tc.b * p.H + y) * p.W + x;
-            mbar_wait(&tm_full[acc], pacc, p.err, 6);
+            mbar_wait_warp(&tm_full[acc], pacc, p.err, 6);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile);
-            for (int cb = 0; cb < p.n_tile; cb += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + cb, r);
-                tmem_ld_wait();
-                if (p.dbg & 8) continue;
+            // Software-pipelined TMEM reads: the tcgen05.ld of chunk c+1 is in flight while chunk c is
+            // post-processed and stored (tcgen05.wait::ld sits right before the data is needed).
+            auto process = [&](const uint32_t* r, const int cb) {
+                if (p.dbg & 8) return;
                 if (valid && p.cout_valid < p.Cout) {
                     // thin head (Cout in {1,4}): scalar stores of the first cout_valid columns
                     const int n0 = tc.nt * p.n_tile + cb;
@@ -340,6 +265,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     float4* dp = reinterpret_cast<float4*>(dst);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            };
+            {
+                uint32_t ra[16], rb[16];
+                tmem_ld16(taddr, ra);
+                for (int cb = 0; cb < p.n_tile; cb += 32) {
+                    tmem_ld_wait();
+                    const bool has_b = cb + 16 < p.n_tile;
+                    if (has_b) tmem_ld16(taddr + cb + 16, rb);
+                    process(ra, cb);
+                    if (has_b) {
+                        tmem_ld_wait();
+                        if (cb + 32 < p.n_tile) tmem_ld16(taddr + cb + 32, ra);
+                        process(rb, cb + 16);
+                    }
                 }
             }
             tc_fence_before();

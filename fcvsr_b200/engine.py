@@ -75,6 +75,12 @@ class _ConvPack:
         # nearest here (cvt.rna semantics) removes their share of the truncation bias for free.
         self.w_tc = _round_tf32(wt.contiguous())
         self.tc_ok = stride == 1 and k in (1, 3) and cin % 32 == 0 and (cout < 16 or cout % 16 == 0)
+        # resident-weight kernel (conv_tc2.cu): k = 3, Cin in {32, 64} per launch, Cout % 64 == 0; Cin = 128 runs as
+        # two K-halves chained through the `pre` addend
+        self.tc2_ok = stride == 1 and k == 3 and cin in (32, 64, 128) and cout % 64 == 0
+        if self.tc2_ok and cin == 128:
+            w4 = self.w_tc.view(cout, 9, cin)
+            self.w_tc_halves = [w4[:, :, :64].reshape(cout, 9 * 64).contiguous(), w4[:, :, 64:].reshape(cout, 9 * 64).contiguous()]
 
 
 class Engine:
@@ -88,6 +94,8 @@ class Engine:
         self.tc_launches = 0
         self.use_graph = False       # replay the launch sequence from a CUDA graph (one per input shape)
         self._graphs: Dict[tuple, tuple] = {}
+        self.use_tc2 = False         # resident-weight 3x3 kernel (conv_tc2.cu): correct but not faster yet (profiles/r1_notes.md)
+        self._ksplit = {}
         self.max_ctas = 0            # grid cap of the tensor-core convs on the current stream (0 = all SMs)
         self.multi_stream = True     # run the three pyramid levels of SCNetbk on three streams
         self._streams = {}
@@ -293,6 +301,25 @@ class Engine:
             return
         if not self.use_tc:          # exact-fp32 mode: nothing is rounded to TF32
             y2, ldy2, rnd = 0, 0, False
+        if self.use_tc and self.use_tc2 and pk.tc2_ok and not nchw:
+            bias = pk.bias.data_ptr() if pk.bias is not None else 0
+            common = (B, H, W)
+            if pk.cin == 128:
+                tmp = self._ksplit_buf(B * H * W * pk.cout, x)
+                C.call("fcvsr_conv3x3_tc_resident", x, ldx, pk.w_tc_halves[0].data_ptr(), 576, 0, 0, 0, 0, 0, tmp, pk.cout,
+                       *common, 64, pk.cout, C.ACT_NONE, 0.0, 0, 0, 0, 0, 0, self.max_ctas, st)
+                C.call("fcvsr_conv3x3_tc_resident", x + 64 * 4, ldx, pk.w_tc_halves[1].data_ptr(), 576, bias, tmp, pk.cout,
+                       res, ldres, y, ldy, *common, 64, pk.cout, act, slope, slope_ptr, int(pk.ps), y2, ldy2, int(rnd),
+                       self.max_ctas, st)
+                self.launches += 1
+                self.tc_launches += 2
+                assert not res2
+                return
+            assert not res2
+            C.call("fcvsr_conv3x3_tc_resident", x, ldx, pk.w_tc.data_ptr(), 9 * pk.cin, bias, 0, 0, res, ldres, y, ldy,
+                   *common, pk.cin, pk.cout, act, slope, slope_ptr, int(pk.ps), y2, ldy2, int(rnd), self.max_ctas, st)
+            self.tc_launches += 1
+            return
         if self.use_tc and pk.tc_ok and not nchw:
             rc = C.try_call("fcvsr_conv2d_tc", x, ldx, pk.w_tc.data_ptr(), pk.bias.data_ptr() if pk.bias is not None else 0,
                             res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin, pk.cout, pk.k, act, slope, slope_ptr,
@@ -305,6 +332,15 @@ class Engine:
         C.call("fcvsr_conv2d_direct", x, ldx, int(nchw), pk.w_direct.data_ptr(),
                pk.bias.data_ptr() if pk.bias is not None else 0, res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin,
                pk.cout, pk.k, pk.stride, act, slope, slope_ptr, int(pk.ps), 0, y2, ldy2, int(rnd), st)
+
+    def _ksplit_buf(self, numel, x_ptr):
+        """Scratch for the first K-half of a Cin = 128 convolution, one per stream (levels run concurrently)."""
+        key = self.st
+        t = self._ksplit.get(key)
+        if t is None or t.numel() < numel:
+            t = torch.empty(numel, device=self._dev, dtype=F32)
+            self._ksplit[key] = t
+        return t.data_ptr()
 
     def _k(self, name, *args):
         self.launches += 1
@@ -323,6 +359,7 @@ class Engine:
             raise TypeError("fcvsr_b200 expects float32 input")
         x = x.contiguous()
         dev = x.device
+        self._dev = dev
         with torch.cuda.device(dev):
             self._ensure_packs(dev)
             ws = self._workspace(B, H, W, dev)

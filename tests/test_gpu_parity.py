@@ -334,3 +334,37 @@ def test_cuda_graph_replay_is_bit_identical(dev):
         y2 = m(x * 0.5).clone()
         y3 = m(x).clone()
     assert torch.equal(y0, y1) and torch.equal(y1, y3) and not torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("case", [(1, 64, 64, 16, 16), (2, 64, 128, 20, 36), (1, 64, 64, 45, 80), (1, 32, 448, 12, 20),
+                                  (1, 64, 256, 9, 17), (1, 128, 64, 24, 30), (2, 128, 64, 45, 80)])
+def test_conv_tc_resident_matches_fp32_reference(dev, case):
+    """conv_tc2.cu (resident weights, single-copy halo tile) incl. the chained K-halves of Cin = 128, residual,
+    pixel shuffle and ragged tiles (widths not multiples of 14)."""
+    B, ci, co, H, W = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, 3, 3, generator=g) / (ci * 9) ** 0.5
+    b = torch.randn(co, generator=g)
+    res = torch.randn(B, co, H, W, generator=g)
+    m = arch.GShiftNet_S()
+    eng = Engine(m)
+    eng.use_tc2 = True
+    eng._dev = dev
+    eng.st = _st()
+    pk = _ConvPack(w.to(dev), b.to(dev))
+    assert pk.tc2_ok
+    xd, rd = nhwc(x).to(dev), nhwc(res).to(dev)
+    y = torch.empty(B, H, W, co, device=dev)
+    eng._conv(pk, xd.data_ptr(), ci, y.data_ptr(), co, B, H, W, act=C.ACT_LEAKY, slope=0.1, res=rd.data_ptr(), ldres=co)
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.1) + res
+    assert eng.tc_launches >= 1
+    assert float((nchw(y.cpu()) - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+    if co % 64 == 0 and (co // 4) % 16 == 0:
+        pk2 = _ConvPack(w.to(dev), b.to(dev), ps=True)
+        y2 = torch.empty(B, 2 * H, 2 * W, co // 4, device=dev)
+        eng._conv(pk2, xd.data_ptr(), ci, y2.data_ptr(), co // 4, B, H, W)
+        torch.cuda.synchronize()
+        ref2 = F.pixel_shuffle(F.conv2d(x, w, b, padding=1), 2)
+        assert float((nchw(y2.cpu()) - ref2).abs().max()) <= 2e-3 * max(1.0, float(ref2.abs().max()))

@@ -42,7 +42,20 @@ __global__ void __launch_bounds__(128, 1) k(int N, int iters, int same_addr, lon
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
         const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 96 * 1024);
         long long t0 = clock64();
-        if (same_addr == 2) {
+        if (same_addr == 3) {
+            // A in the NO-SWIZZLE K-major layout (16-byte granule planes 2608 B apart, rows 16 B apart), B SW128
+            const uint64_t ad = (uint64_t)((a0 >> 4) & 0x3FFF) | ((uint64_t)(2608 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+            const uint64_t bd = make_desc(b0);
+            for (int i = 0; i < iters; i += 36) {
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint64_t at = ad + (uint64_t)((tap / 3) * 16 + (tap % 3));
+                    const uint64_t bt = bd + (uint64_t)((tap * 8192) >> 4);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) mma<KIND>(tmem, at + (uint64_t)(kk * 2 * (2608 >> 4)), bt + 2 * kk, idesc, (i | tap | kk) ? 1u : 0u);
+                }
+            }
+        } else if (same_addr == 2) {
             // cheapest possible issue loop: descriptors precomputed, +2 per k-step (32 B >> 4), 9 taps unrolled by offset
             const uint64_t ad = make_desc(a0), bd = make_desc(b0);
             for (int i = 0; i < iters; i += 36) {
@@ -85,13 +98,13 @@ int main() {
     const int iters = 2052;
     for (int grid : {148})
         for (int kind = 0; kind < 2; ++kind)
-            for (int N : {32, 64, 128, 256})
-                for (int same : {2, 0}) {
+            for (int N : {64, 128})
+                for (int same : {2, 3}) {
                     if (kind == 0) k<0><<<grid, 128, smem>>>(N, iters, same, out); else k<1><<<grid, 128, smem>>>(N, iters, same, out);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                     printf("grid %3d %s N=%3d %s: issue %.1f clk/mma, complete %.1f clk/mma (ideal %d)\n", grid, kind ? "bf16" : "tf32", N,
-                           same == 2 ? "precomp  " : "walk     ", (double)out[0] / iters, (double)out[1] / iters, 128 * N / 256);
+                           same == 2 ? "sw128 A  " : "noswz A  ", (double)out[0] / iters, (double)out[1] / iters, 128 * N / 256);
                 }
     return 0;
 }
