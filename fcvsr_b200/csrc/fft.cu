@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_c2c_h_kernel(const float2* in
     const int c0 = blockIdx.y * cb;
     load_twiddles(tws, tw, n, inverse != 0);
     const size_t base = ((size_t)bidx * H * Wf + wf) * C + c0;
+    if (mask) mask += (size_t)blockIdx.z * H * Wf;                     // replica z: its own mask ...
+    out += (size_t)blockIdx.z * gridDim.x * H * C;                     // ... and output ([nrep][B,H,Wf,C])
     for (int idx = threadIdx.x; idx < (n << cb_log2); idx += blockDim.x) {
         const int i = idx >> cb_log2, ch = idx & (cb - 1);
         float2 v = in[base + (size_t)i * Wf * C + ch];
@@ -259,13 +261,13 @@ extern "C" int fcvsr_fft_r2c_w(const float* x, int ldx, float* out, const float*
 }
 
 extern "C" int fcvsr_fft_c2c_h(const float* in, float* out, const float* tw, const float* mask, int B, int H, int Wf,
-                               int C, int inverse, float scale, int round_out, cudaStream_t st) {
+                               int C, int inverse, float scale, int round_out, int nrep, cudaStream_t st) {
     FftPlan plan;
-    if (!in || !out || !tw || !make_plan(H, &plan)) return FCVSR_ERR_ARG;
+    if (!in || !out || !tw || nrep < 1 || (nrep > 1 && in == out) || !make_plan(H, &plan)) return FCVSR_ERR_ARG;
     const int cbl = pick_cb_log2(H, C);
     const size_t smem = (2 * (size_t)H * (1 << cbl) + H) * sizeof(float2);
     if (set_smem(fft_c2c_h_kernel, smem)) return FCVSR_ERR_CUDA;
-    dim3 grid(B * Wf, C >> cbl);
+    dim3 grid(B * Wf, C >> cbl, nrep);
     fft_c2c_h_kernel<<<grid, FFT_THREADS, smem, st>>>((const float2*)in, (float2*)out, (const float2*)tw, mask, H, Wf,
                                                       C, cbl, inverse, scale, round_out, plan);
     return fcvsr_launch_status();

@@ -219,29 +219,30 @@ class Engine:
 
         buf("feat", B, P, 448)
         buf("clip32", B, P, 32)
-        buf("spec", B, Pf, 384)
-        buf("h1", 2 * B, Pf, 128)
-        buf("h2", 2 * B, Pf, 128)
-        buf("cc", 2 * B, Pf, 224, zero=True)
-        buf("c1", 2 * B, Pf, 64)
-        buf("c2", 2 * B, Pf, 64)
-        buf("off", 2 * B, Pf, 4)
-        buf("simh", B, Pf, 64)
-        buf("sim", B, Pf, 4)
-        buf("ob_t1", A, 2 * B, Pf, 4)
-        buf("ob_t2", A, 2 * B, Pf, 4)
-        buf("ob_partial", A * 2 * B * ((Pf + 127) // 128) * 4)
-        buf("z", B, Pf, 8 * A)
-        buf("offs", B, P, 4 * A)
-        buf("x2r", B, P, 64)
-        buf("kp1", B, P, 64)
-        buf("kp2", B, P, 64)
-        buf("pk", B, P, A * 192)
-        buf("ping", 2, 2, B, P, 64)
-        buf("cat128", B, P, 128)
+        for sfx in ("", "_b"):         # two scratch sets: MGAA(f1) and MGAA(f3) run concurrently
+            buf("spec" + sfx, B, Pf, 384)
+            buf("h1" + sfx, 2 * B, Pf, 128)
+            buf("h2" + sfx, 2 * B, Pf, 128)
+            buf("cc" + sfx, 2 * B, Pf, 224, zero=True)
+            buf("c1" + sfx, 2 * B, Pf, 64)
+            buf("c2" + sfx, 2 * B, Pf, 64)
+            buf("off" + sfx, 2 * B, Pf, 4)
+            buf("simh" + sfx, B, Pf, 64)
+            buf("sim" + sfx, B, Pf, 4)
+            buf("ob_t1" + sfx, A, 2 * B, Pf, 4)
+            buf("ob_t2" + sfx, A, 2 * B, Pf, 4)
+            buf("ob_partial" + sfx, A * 2 * B * ((Pf + 127) // 128) * 4)
+            buf("z" + sfx, B, Pf, 8 * A)
+            buf("offs" + sfx, B, P, 4 * A)
+            buf("x2r" + sfx, B, P, 64)
+            buf("kp1" + sfx, B, P, 64)
+            buf("kp2" + sfx, B, P, 64)
+            buf("pk" + sfx, B, P, A * 192)
+            buf("ping" + sfx, 2, 2, B, P, 64)
+            buf("cat128" + sfx, B, P, 128)
         buf("m2", B, P, 64)
         buf("specx", B, Pf, 128)
-        buf("tmpc", B, Pf, 128)
+        buf("tmpc", Q, B, Pf, 128)
         buf("bands", Q, B, P, 64)
         buf("sb", B, P, 64)
         buf("so", B, P, 64)
@@ -408,8 +409,24 @@ class Engine:
             self._conv(P["feat"], x.data_ptr(), 0, f, 448, B, H, W, nchw=True)
         # MGAA(f1) -> feat[128:192], MGAA(f3) -> feat[256:320]: cat[o1, f2, o3] (:2720) is then the
         # contiguous channel slice feat[128:320] and no concatenation is materialised.
-        self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)
-        self._mgaa(ws, p, f + 256 * 4, 448, f + 256 * 4, 448, B, H, W)
+        main = torch.cuda.current_stream()
+        if self.multi_stream and self.profile is None:
+            dev = main.device
+            if dev not in self._streams:
+                self._streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            side = self._streams[dev][0]
+            side.wait_stream(main)
+            self.max_ctas = 74                      # two tensor-core conv grids share the 148 SMs
+            self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)
+            with torch.cuda.stream(side):
+                self.st = side.cuda_stream
+                self._mgaa(ws, p, f + 256 * 4, 448, f + 256 * 4, 448, B, H, W, sfx="_b")
+            self.st = main.cuda_stream
+            self.max_ctas = 0
+            main.wait_stream(side)
+        else:
+            self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)
+            self._mgaa(ws, p, f + 256 * 4, 448, f + 256 * 4, 448, B, H, W)
         self._mgaa(ws, p, f + 128 * 4, 448, p["m2"], 64, B, H, W)
         self._mffr(ws, p, B, H, W)                                   # m2 -> xs0
         self._conv(P["rc1"], p["xs0"], 64, p["xs1"], 64, B, H, W, y2=p["xsr1"], ldy2=64)                  # :2735
@@ -417,18 +434,21 @@ class Engine:
         self._scnet(ws, p, B, H, W)
         self._tail(x, out, ws, p, B, H, W)
 
-    # MGAAbk.forward (:1442-1547) on the 192-channel slice at `src`; result (64 ch) to `dst`
-    def _mgaa(self, ws, p, src, lds, dst, ldd, B, H, W):
+    # MGAAbk.forward (:1442-1547) on the 192-channel slice at `src`; result (64 ch) to `dst`.
+    # `sfx` selects the scratch set ("" or "_b"): MGAA(f1) and MGAA(f3) are independent and run concurrently.
+    def _mgaa(self, ws, p0, src, lds, dst, ldd, B, H, W, sfx=""):
         P, A = self.packs, self.model.ACNum
         Wf = W // 2 + 1
         Pf = H * Wf
-        st = self.st
+        shared = ("tw_w", "tw_h")
+        p = {k[: -len(sfx)] if sfx and k.endswith(sfx) else k: v for k, v in p0.items()
+             if (not sfx) or k.endswith(sfx) or k in shared}
         spec = p["spec"]
         RELU = C.ACT_RELU
+        R = int(self.use_tc)     # tensors that feed tcgen05 convs are stored TF32-rounded (see common.cuh)
         # rfft2 of x1|x2|x3 (:1452-1454)
         self._k("fcvsr_fft_r2c_w", src, lds, spec, p["tw_w"], B, H, W, 192)
-        R = int(self.use_tc)     # tensors that feed tcgen05 convs are stored TF32-rounded (see common.cuh)
-        self._k("fcvsr_fft_c2c_h", spec, spec, p["tw_h"], 0, B, H, Wf, 192, 0, 1.0, R)
+        self._k("fcvsr_fft_c2c_h", spec, spec, p["tw_h"], 0, B, H, Wf, 192, 0, 1.0, R, 1)
         h1, h2, cc = p["h1"], p["h2"], p["cc"]
         half = B * Pf
         # convfuse (:1472-1473); the diff skip rides in the last layer's epilogue (res - res2)
@@ -449,11 +469,12 @@ class Engine:
         self._conv(P["corr2"], p["c1"], 64, p["c2"], 64, 2 * B, H, Wf, act=RELU, rnd=True)
         self._conv(P["corr4"], p["c2"], 64, p["off"], 4, 2 * B, H, Wf)
         # ConvBlk_i * x2_f_sim for all i (:1494-1498), then irfft2 (:1499-1505)
+        z = p["z"]
         self.launches += 2
         self._k("fcvsr_offset_blocks", p["off"], P["ob_w1"].data_ptr(), P["ob_w2"].data_ptr(), P["ob_prelu"].data_ptr(),
-                P["ob_ca"].data_ptr(), p["sim"], 4, p["ob_t1"], p["ob_t2"], p["ob_partial"], p["z"], B, H, Wf, A)
-        self._k("fcvsr_fft_c2c_h", p["z"], p["z"], p["tw_h"], 0, B, H, Wf, 4 * A, 1, 1.0, 0)
-        self._k("fcvsr_fft_c2r_w", p["z"], p["offs"], 4 * A, p["tw_w"], B, H, W, 4 * A, 1.0 / (H * W))
+                P["ob_ca"].data_ptr(), p["sim"], 4, p["ob_t1"], p["ob_t2"], p["ob_partial"], z, B, H, Wf, A)
+        self._k("fcvsr_fft_c2c_h", z, z, p["tw_h"], 0, B, H, Wf, 4 * A, 1, 1.0, 0, 1)
+        self._k("fcvsr_fft_c2r_w", z, p["offs"], 4 * A, p["tw_w"], B, H, W, 4 * A, 1.0 / (H * W))
         # kernel predictor (:1522-1523)
         x2, ldx2 = src + 64 * 4, lds
         if R:                       # x2 is both the conv_KP operand and the full-precision skip of conv3
@@ -486,11 +507,11 @@ class Engine:
         nblk = (npix + 255) // 256
         x = p["m2"]
         self._k("fcvsr_fft_r2c_w", x, 64, p["specx"], p["tw_w"], B, H, W, 64)
-        self._k("fcvsr_fft_c2c_h", p["specx"], p["specx"], p["tw_h"], 0, B, H, Wf, 64, 0, 1.0, 0)
+        self._k("fcvsr_fft_c2c_h", p["specx"], p["specx"], p["tw_h"], 0, B, H, Wf, 64, 0, 1.0, 0, 1)
         bsz = B * npix * 64 * 4
-        for q in range(Q):      # Split_freq (:2075-2101): band_q = irfft2(spectrum * Msym_q)
-            self._k("fcvsr_fft_c2c_h", p["specx"], p["tmpc"], p["tw_h"], p["masks"] + q * H * Wf * 4, B, H, Wf, 64, 1, 1.0, 0)
-            self._k("fcvsr_fft_c2r_w", p["tmpc"], p["bands"] + q * bsz, 64, p["tw_w"], B, H, W, 64, 1.0 / npix)
+        # Split_freq (:2075-2101): band_q = irfft2(spectrum * Msym_q), all Q bands in one launch per pass
+        self._k("fcvsr_fft_c2c_h", p["specx"], p["tmpc"], p["tw_h"], p["masks"], B, H, Wf, 64, 1, 1.0, 0, Q)
+        self._k("fcvsr_fft_c2r_w", p["tmpc"], p["bands"], 64, p["tw_w"], Q * B, H, W, 64, 1.0 / npix)
         band = lambda i: p["bands"] + (Q - 1 - i) * bsz            # freq[::-1] (:2204-2205)
         gate = lambda i: p["gates"] + i * B * 128 * 4
         inv = 1.0 / npix

@@ -73,9 +73,10 @@ int fcvsr_conv3x3_tc_resident(const float* x, int ldx, const float* w, int ldw, 
 int fcvsr_fft_r2c_w(const float* x, int ldx, float* out_c, const float* tw, int B, int H, int W, int C,
                     cudaStream_t stream);
 /* in/out complex [B,H,Wf,C] (C complex channels); optional real mask [H*Wf] multiplied at load;
- * in == out allowed.  inverse: 0 forward, 1 inverse (unnormalised); result * scale. */
+ * in == out allowed.  inverse: 0 forward, 1 inverse (unnormalised); result * scale.  nrep > 1 transforms the
+ * same input nrep times with mask + r*H*Wf into out + r*B*H*Wf*C (all band masks of Split_freq in one launch). */
 int fcvsr_fft_c2c_h(const float* in_c, float* out_c, const float* tw, const float* mask, int B, int H, int Wf,
-                    int C, int inverse, float scale, int round_out, cudaStream_t stream);
+                    int C, int inverse, float scale, int round_out, int nrep, cudaStream_t stream);
 /* complex [B,H,Wf,C] -> real [B,H,W,ldy] (C real channels), torch c2r semantics, result * scale. */
 int fcvsr_fft_c2r_w(const float* in_c, float* y, int ldy, const float* tw, int B, int H, int W, int C,
                     float scale, cudaStream_t stream);
