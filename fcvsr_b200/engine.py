@@ -334,6 +334,21 @@ class Engine:
                pk.bias.data_ptr() if pk.bias is not None else 0, res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin,
                pk.cout, pk.k, pk.stride, act, slope, slope_ptr, int(pk.ps), 0, y2, ldy2, int(rnd), st)
 
+    @staticmethod
+    def _level_caps(B, dims, sms=148):
+        """Split the SMs over the three concurrently running pyramid levels so that the number of 8x16-pixel
+        tile rounds of the slowest level is minimal (levels hold 1, 1/4, 1/16 of the pixels)."""
+        tiles = [B * ((h + 7) // 8) * ((w + 15) // 16) for h, w in dims]
+        best = None
+        for c2 in range(1, sms - 1):
+            for c1 in range(1, sms - c2):
+                c0 = sms - c1 - c2
+                rounds = max(-(-tiles[0] // c0), -(-tiles[1] // c1), -(-tiles[2] // c2))
+                key = (rounds, -c0)
+                if best is None or key < best[0]:
+                    best = (key, (c0, c1, c2))
+        return best[1]
+
     def _ksplit_buf(self, numel, x_ptr):
         """Scratch for the first K-half of a Cin = 128 convolution, one per stream (levels run concurrently)."""
         key = self.st
@@ -548,7 +563,7 @@ class Engine:
             if dev not in self._streams:
                 self._streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
             streams = (main,) + self._streams[dev]
-            caps = (116, 24, 8)          # SMs left to each level's persistent conv grid (sum = 148)
+            caps = self._level_caps(B, dims)   # SMs given to each level's persistent conv grid (sum = 148)
             for s_ in streams[1:]:
                 s_.wait_stream(main)
         else:
