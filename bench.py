@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--variant", default="full", choices=["full", "S"])
     ap.add_argument("--height", type=int, default=180)
     ap.add_argument("--width", type=int, default=320)
+    ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"],
+                    help="tensor-core operand type: tf32 (fp32 storage; the contract's fp32 mode) or bf16")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -111,7 +113,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     workload = (f"{'FCVSR' if args.variant == 'full' else 'FCVSR-S'} forward, synthetic 7-frame "
-                f"{args.height}x{args.width} clips x4, fp32 storage")
+                f"{args.height}x{args.width} clips x4, {'fp32 storage, TF32 operands' if args.dtype == 'tf32' else 'bf16 operand tensors, fp32 accumulate'}")
 
     if args.impl == "reference":
         if rank != 0:
@@ -139,6 +141,7 @@ def main():
     sd = arch.seeded_state_dict(args.variant, 0)
     model = (arch.GShiftNet if args.variant == "full" else arch.GShiftNet_S)().to(dev).eval()
     model.load_state_dict(sd)
+    model.compute_dtype = args.dtype
     x_host = make_clip(1234 + rank, B, H, W).pin_memory()
     y_host = torch.empty(B, 1, 4 * H, 4 * W).pin_memory()
     x_dev = x_host.to(dev)
@@ -205,11 +208,12 @@ def main():
             torch.cuda.synchronize()
             hbm, tfl, src = peaks()
             ach = fl_tc / (t_tc * 1e-3) / 1e12 if t_tc > 0 else 0.0
-            roof = {"kernel": "conv_tc_kernel (tcgen05 TF32 implicit GEMM)", "bound": "tensor", "achieved": ach,
+            roof = {"kernel": f"conv_tc_kernel (tcgen05 {args.dtype} implicit GEMM)", "bound": "tensor", "achieved": ach,
                     "peak": tfl, "unit": "TFLOP/s", "frac": ach / tfl, "traffic": None, "peak_source": src,
                     "launches": len(tc), "avg_launch_us": 1e3 * t_tc / max(len(tc), 1),
                     "share_of_step": t_tc / t0.elapsed_time(t1),
-                    "note": "TF32 operands run at half the bf16 tensor rate; peak is the measured bf16 dense figure"}
+                    "note": ("TF32 operands run at half the bf16 tensor rate; " if args.dtype == "tf32" else "") +
+                            "peak is the measured bf16 dense figure"}
             eng.use_graph = not args.no_graph
 
     frames = B * world * args.steps
@@ -221,7 +225,7 @@ def main():
         return
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload, "batch_per_step_per_gpu": B, "parallelism": f"window-sharded x{world}",
                        "l2": "working set per step (~1.5 GB of NHWC feature maps) exceeds the 126 MB L2; no flush needed",
                        "cuda_graph": not args.no_graph},

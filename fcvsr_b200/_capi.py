@@ -19,27 +19,27 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.
 
 # name -> argument codes, in the order of include/fcvsr_b200.h
 SIGNATURES = {
-    "fcvsr_conv2d_direct": "pii pp pi pi pi iiiiiii if p ii pii s",
-    "fcvsr_conv2d_tc": "pi pp pi pi pi iiiiii if p i pii i s",
+    "fcvsr_conv2d_direct": "pii pp pi pi pi iiiiiii if p ii pii i s",
+    "fcvsr_conv2d_tc": "pi pp pi pi pi iiiiii if p i pii i i s",
     "fcvsr_conv3x3_tc_resident": "pi pi p pi pi pi iiiii if p i pii i s",
     "fcvsr_fft_r2c_w": "pi p p iiii s",
     "fcvsr_fft_c2c_h": "p p p p iiii i f ii s",
     "fcvsr_fft_c2r_w": "p pi p iiii f s",
-    "fcvsr_corr_gather": "piii pi iiii s",
+    "fcvsr_corr_gather": "piii pi iiii i s",
     "fcvsr_offset_blocks": "ppppp pi pppp iiii s",
     "fcvsr_iac_step": "pi pi pi pi pi pi pi ii pi iii i s",
-    "fcvsr_round_copy": "pi pi i l s",
+    "fcvsr_round_copy": "pi pi ii l i s",
     "fcvsr_chansum64": "pi p ii s",
     "fcvsr_reduce_finalize": "p ii f i pp p i s",
     "fcvsr_divenh_step": "ppppp i ii pppp ppp ii s",
     "fcvsr_mffr_final": "pp pi pi ii s",
     "fcvsr_context_block": "pi ppp pp ii s",
-    "fcvsr_rcb_finish": "ppp p ii i s",
-    "fcvsr_level_mix": "pi pi p f pp iii pi i s",
-    "fcvsr_pixel_shuffle": "pi pi iiii s",
+    "fcvsr_rcb_finish": "ppp p ii p i s",
+    "fcvsr_level_mix": "pi pi p f pp iii pi i i s",
+    "fcvsr_pixel_shuffle": "pi pi iiii i s",
     "fcvsr_bilinear_up4": "p l p iii s",
     "fcvsr_fill_channels": "p iii f l s",
-    "fcvsr_pack_clip": "p p iiii s",
+    "fcvsr_pack_clip": "p p iiii i s",
     "fcvsr_modulated_deform_conv_forward": "ppppp p iiii i ii ii ii ii ii ll i s",
 }
 

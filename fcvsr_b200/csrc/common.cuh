@@ -48,3 +48,35 @@ __device__ __forceinline__ float round_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
+
+// Operand-typed store of 4 consecutive channels: TF32-rounded fp32 (op16 = 0) or bf16 (op16 = 1).
+// `base` is the tensor base in its own element type, `idx` the element index.
+__device__ __forceinline__ void store_operand4(void* base, size_t idx, float4 v, int op16) {
+    if (op16) {
+        uint32_t lo, hi;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v.w), "f"(v.z));
+        *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(base) + idx) = make_uint2(lo, hi);
+    } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) =
+            make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    }
+}
+__device__ __forceinline__ void store_operand2(void* base, size_t idx, float2 v, int op16) {
+    if (op16) {
+        uint32_t w;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(v.y), "f"(v.x));
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned short*>(base) + idx) = w;
+    } else {
+        *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + idx) = make_float2(round_tf32(v.x), round_tf32(v.y));
+    }
+}
+__device__ __forceinline__ void store_operand1(void* base, size_t idx, float v, int op16) {
+    if (op16) {
+        unsigned short h;
+        asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(v));
+        reinterpret_cast<unsigned short*>(base)[idx] = h;
+    } else {
+        reinterpret_cast<float*>(base)[idx] = round_tf32(v);
+    }
+}

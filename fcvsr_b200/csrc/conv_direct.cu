@@ -22,7 +22,7 @@ struct ConvDirectArgs {
     int B, H, W, Cin, Cout, ks, stride, Ho, Wo;
     int act; float slope; const float* slope_ptr;
     int ps; int y_nchw;
-    float* y2; int ldy2; int round_out;
+    void* y2; int ldy2; int round_out; int op16;
 };
 
 __global__ void __launch_bounds__(256) conv_direct_kernel(ConvDirectArgs a) {
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(ConvDirectArgs a) {
             v = fcvsr_act(v, a.act, slope);
             if (a.res) v += a.res[pix * a.ldres + n];
             if (a.res2) v -= a.res2[pix * a.ldres2 + n];
-            if (a.y2) a.y2[pix * a.ldy2 + n] = round_tf32(v);
+            if (a.y2) store_operand1(a.y2, pix * a.ldy2 + n, v, a.op16);
             if (a.round_out) v = round_tf32(v);
             if (a.ps) {
                 const int ij = n / c4, c = n - ij * c4;
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(ConvDirectArgs a) {
 extern "C" int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const float* w, const float* bias,
                                    const float* res, int ldres, const float* res2, int ldres2, float* y, int ldy,
                                    int B, int H, int W, int Cin, int Cout, int ksize, int stride, int act, float slope,
-                                   const float* slope_ptr, int pixel_shuffle, int y_nchw, float* y2, int ldy2,
-                                   int round_out, cudaStream_t st) {
+                                   const float* slope_ptr, int pixel_shuffle, int y_nchw, void* y2, int ldy2,
+                                   int round_out, int op16, cudaStream_t st) {
     if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || !(ksize & 1) || stride < 1)
         return FCVSR_ERR_ARG;
     if (act == FCVSR_ACT_PRELU && !slope_ptr) return FCVSR_ERR_ARG;
@@ -134,7 +134,7 @@ extern "C" int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const fl
     const int pad = ksize / 2;
     a.Ho = (H + 2 * pad - ksize) / stride + 1;
     a.Wo = (W + 2 * pad - ksize) / stride + 1;
-    a.act = act; a.slope = slope; a.slope_ptr = slope_ptr; a.ps = pixel_shuffle; a.y_nchw = y_nchw; a.y2 = y2; a.ldy2 = ldy2; a.round_out = round_out;
+    a.act = act; a.slope = slope; a.slope_ptr = slope_ptr; a.ps = pixel_shuffle; a.y_nchw = y_nchw; a.y2 = y2; a.ldy2 = ldy2; a.round_out = round_out; a.op16 = op16;
     dim3 grid(((a.Ho + 7) / 8) * ((a.Wo + 7) / 8), (Cout + CD_TN - 1) / CD_TN, B);
     conv_direct_kernel<<<grid, 256, 0, st>>>(a);
     return fcvsr_launch_status();

@@ -26,11 +26,12 @@
 // Roofline: tensor (TF32: K=8 per instruction, half the bf16 rate).  Algorithmic FLOPs per output pixel
 // = 2 * Cin * Cout * k * k; algorithmic HBM bytes per pixel = 4 * (Cin + Cout) (+4*Cout per residual).
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #define TC_TH 8
 #define TC_TW 16
-#define TC_KCH 32                      // channels per K chunk (128 bytes of fp32)
+#define TC_KCH 32                      // channels per K chunk in TF32 mode (128 bytes of fp32); 64 in bf16 mode
 #define TC_NA 2                        // A ring stages
 #define TC_NB_MAX 16                   // B ring: as many stages as fit in TC_B_RING_BYTES, at most 16
 #define TC_B_RING_BYTES (96 * 1024)
@@ -62,7 +63,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const ConvTcParams& p) {
     return c;
 }
 
-template <int KS>
+template <int KS, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -81,7 +82,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncopies = KS == 3 ? 3 : 1;
     const int nrows = KS == 3 ? TC_TH + 2 : TC_TH;
-    const int kchunks = p.Cin / TC_KCH;
+    constexpr int KCH = BF16 ? 64 : 32;                 // channels per 128-byte operand row
+    const int kchunks = p.Cin / KCH;
     const uint32_t a_copy_bytes = (uint32_t)nrows * TC_TW * TC_ROW_BYTES;
     const uint32_t b_bytes = (uint32_t)p.n_tile * TC_ROW_BYTES;      // multiple of 2048 (n_tile % 16 == 0): stays 1024-aligned
     const uint32_t b_stage_bytes = b_bytes * KS;                    // one filter row of taps per stage
@@ -117,7 +119,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     mbar_expect_tx(&full_a[stage], a_copy_bytes * ncopies);
                     uint8_t* dst = a_buf + stage * TC_A_STAGE_BYTES;
                     for (int cpy = 0; cpy < ncopies; ++cpy)
-                        tma_load_4d(dst + cpy * TC_A_COPY_BYTES, &map_x, &full_a[stage], kc * TC_KCH, x0 + cpy, y0, tc.b);
+                        tma_load_4d(dst + cpy * TC_A_COPY_BYTES, &map_x, &full_a[stage], kc * KCH, x0 + cpy, y0, tc.b);
                     if (++stage == TC_NA) { stage = 0; phase ^= 1; }
                 }
             }
@@ -136,7 +138,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                         for (int kx = 0; kx < KS; ++kx)
                             tma_load_2d(b_buf + stage * b_stage_bytes + kx * b_bytes, &map_w, &full_b[stage],
-                                        (ky * KS + kx) * p.Cin + kc * TC_KCH, tc.nt * p.n_tile);
+                                        (ky * KS + kx) * p.Cin + kc * KCH, tc.nt * p.n_tile);
                         if (++stage == nb_stages) { stage = 0; phase ^= 1; }
                     }
             }
@@ -146,7 +148,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // Descriptors are formed once per stage and advanced by constant adds: the uniform-datapath chain
         // of a full make_desc() per instruction costs ~130 clk/MMA, 3x the tensor pipe's 48 clk (N=64).
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t FMT = BF16 ? 1u : 2u;            // F16F32Format: 1 = BF16, 2 = TF32
+            const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t b_step = b_bytes >> 4;
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int acc = 0; uint32_t pacc = 0;
@@ -170,7 +173,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                                 const uint64_t b_d = b_desc0 + (uint64_t)(kx * b_step);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    umma_tf32(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc, (kc | ky | kx | k) ? 1u : 0u);
+                                    if (BF16) umma_f16(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc, (kc | ky | kx | k) ? 1u : 0u);
+                                    else umma_tf32(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc, (kc | ky | kx | k) ? 1u : 0u);
                             }
                         }
                         umma_commit(&empty_b[sb]);
@@ -243,28 +247,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             v[4 * j] -= rv.x; v[4 * j + 1] -= rv.y; v[4 * j + 2] -= rv.z; v[4 * j + 3] -= rv.w;
                         }
                     }
+                    // operand-typed outputs: TF32-rounded fp32, or bf16 in bf16 mode
                     if (p.y2) {
-                        float4* d2 = reinterpret_cast<float4*>(p.y2 + pix * p.ldy2 + n0);
+                        if (BF16) {
+                            store_bf16x16(reinterpret_cast<__nv_bfloat16*>(p.y2) + pix * p.ldy2 + n0, v);
+                        } else {
+                            float4* d2 = reinterpret_cast<float4*>(p.y2 + pix * p.ldy2 + n0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            d2[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]),
-                                                round_tf32(v[4 * j + 3]));
+                            for (int j = 0; j < 4; ++j)
+                                d2[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]),
+                                                    round_tf32(v[4 * j + 3]));
+                        }
                     }
-                    if (p.round_out) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
-                    }
-                    float* dst;
+                    size_t off;
                     if (p.ps) {
                         const int ij = n0 / c4, c = n0 - ij * c4;
                         const size_t opix = ((size_t)tc.b * 2 * p.H + 2 * y + (ij >> 1)) * (2 * (size_t)p.W) + 2 * x + (ij & 1);
-                        dst = p.y + opix * p.ldy + c;
+                        off = opix * p.ldy + c;
                     } else {
-                        dst = p.y + pix * p.ldy + n0;
+                        off = pix * p.ldy + n0;
                     }
-                    float4* dp = reinterpret_cast<float4*>(dst);
+                    if (BF16 && p.round_out) {
+                        store_bf16x16(reinterpret_cast<__nv_bfloat16*>(p.y) + off, v);
+                    } else {
+                        if (p.round_out) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+                        }
+                        float4* dp = reinterpret_cast<float4*>(p.y + off);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
                 }
             };
             {
@@ -325,9 +338,11 @@ static int* tc_err_flag() {
 extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
                                const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
                                int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
-                               float* y2, int ldy2, int round_out, int max_ctas, cudaStream_t st) {
+                               float* y2, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t st) {
     if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
-    if ((ksize != 1 && ksize != 3) || Cin % TC_KCH || Cin <= 0 || Cout <= 0) return FCVSR_ERR_UNSUPPORTED;
+    const int kch = op16 ? 64 : 32, esz = op16 ? 2 : 4;
+    if ((ksize != 1 && ksize != 3) || Cin % kch || Cin <= 0 || Cout <= 0) return FCVSR_ERR_UNSUPPORTED;
+    if (op16 && (ldx & 7)) return FCVSR_ERR_UNSUPPORTED;
     const int cout_valid = Cout;
     const bool thin = Cout < 16;            // thin heads: w is zero-padded to 16 rows by the packer
     if (thin) Cout = 16;
@@ -338,6 +353,7 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     if (!thin && (((uintptr_t)y | (uintptr_t)res | (uintptr_t)res2) & 15)) return FCVSR_ERR_UNSUPPORTED;
     if (thin && (pixel_shuffle || y2 || round_out)) return FCVSR_ERR_UNSUPPORTED;
     if (y2 && (pixel_shuffle || (ldy2 & 3) || ((uintptr_t)y2 & 15))) return FCVSR_ERR_UNSUPPORTED;
+    if (op16 && ((round_out && (ldy & 7)) || (y2 && (ldy2 & 7)))) return FCVSR_ERR_UNSUPPORTED;
     if (act == FCVSR_ACT_PRELU && !slope_ptr) return FCVSR_ERR_ARG;
     int n_tile = Cout, n_tiles = 1;
     if (Cout > 128) {       // largest N tile <= 128 that is a multiple of 16 and divides Cout
@@ -354,20 +370,20 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     CUtensorMap map_x, map_w;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)W * ldx * 4, (cuuint64_t)H * W * ldx * 4};
-        cuuint32_t box[4] = {TC_KCH, TC_TW, (cuuint32_t)(ksize == 3 ? TC_TH + 2 : TC_TH), 1};
+        cuuint64_t strides[3] = {(cuuint64_t)ldx * esz, (cuuint64_t)W * ldx * esz, (cuuint64_t)H * W * ldx * esz};
+        cuuint32_t box[4] = {(cuuint32_t)kch, TC_TW, (cuuint32_t)(ksize == 3 ? TC_TH + 2 : TC_TH), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        if (enc(&map_x, op16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FCVSR_ERR_CUDA;
     }
     {
         const int ktot = ksize * ksize * Cin;
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)Cout};
-        cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
-        cuuint32_t box[2] = {TC_KCH, (cuuint32_t)n_tile};
+        cuuint64_t strides[1] = {(cuuint64_t)ktot * esz};
+        cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)n_tile};
         cuuint32_t estr[2] = {1, 1};
-        if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        if (enc(&map_w, op16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FCVSR_ERR_CUDA;
     }
@@ -388,14 +404,21 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return FCVSR_ERR_CUDA;
         attr_set = true;
     }
     int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;   // leave SMs to kernels running on other streams
-    if (ksize == 3) conv_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
-    else conv_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+    if (op16) {
+        if (ksize == 3) conv_tc_kernel<3, true><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+        else conv_tc_kernel<1, true><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+    } else {
+        if (ksize == 3) conv_tc_kernel<3, false><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+        else conv_tc_kernel<1, false><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+    }
     return fcvsr_launch_status();
 }

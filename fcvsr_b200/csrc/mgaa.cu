@@ -17,8 +17,8 @@
 // CorrBlock gather.  S: [B, P, ldS] floats (P = H*Wf), groups a_off / b_off (float offsets) hold the
 // two spectra.  out: [B, P, ldo], 81 channels.  prod (reference layout [C2][P]) flat index F = p*C2
 // + row*2 + col  ->  ref channel F / P, position F % P.
-__global__ void corr_gather_kernel(const float* __restrict__ S, int ldS, int a_off, int b_off, float* __restrict__ out,
-                                   int ldo, int H, int Wf, int C2, float inv_sqrt_c, int total) {
+__global__ void corr_gather_kernel(const float* __restrict__ S, int ldS, int a_off, int b_off, void* __restrict__ out,
+                                   int ldo, int H, int Wf, int C2, float inv_sqrt_c, int total, int op_mode) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int P = H * Wf;
@@ -37,16 +37,18 @@ __global__ void corr_gather_kernel(const float* __restrict__ S, int ldS, int a_o
         const float* s = S + ((size_t)b * P + p2) * ldS;
         v = s[a_off + mi] * s[b_off + mi] * inv_sqrt_c;
     }
-    out[((size_t)b * P + p) * ldo + o] = v;
+    // op_mode: 0 plain fp32, 1 TF32-rounded fp32, 2 bf16 (the lookup feeds convcorr[0] on the tensor cores)
+    if (op_mode == 0) reinterpret_cast<float*>(out)[((size_t)b * P + p) * ldo + o] = v;
+    else store_operand1(out, ((size_t)b * P + p) * ldo + o, v, op_mode == 2);
 }
 
-extern "C" int fcvsr_corr_gather(const float* S, int ldS, int a_off, int b_off, float* out, int ldo, int B, int H,
-                                 int Wf, int C2, cudaStream_t st) {
+extern "C" int fcvsr_corr_gather(const float* S, int ldS, int a_off, int b_off, void* out, int ldo, int B, int H,
+                                 int Wf, int C2, int op_mode, cudaStream_t st) {
     if (!S || !out || C2 <= 0) return FCVSR_ERR_ARG;
     const long long total = (long long)B * H * Wf * 81;
     if (total > 0x7fffffffLL) return FCVSR_ERR_ARG;
     corr_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, ldS, a_off, b_off, out, ldo, H, Wf, C2,
-                                                                      rsqrtf((float)C2), (int)total);
+                                                                      rsqrtf((float)C2), (int)total, op_mode);
     return fcvsr_launch_status();
 }
 
@@ -197,7 +199,7 @@ struct IacArgs {
     float* next[2];       int ldnext[2];
     const float* offs; int ldoffs; int offs_ch[2];   // channel of dx for each direction
     const float* taps; int ldtaps;                   // already offset to this iteration's 192 channels
-    int B, H, W; int round_out;
+    int B, H, W; int round_out;      // 0 fp32, 1 TF32-rounded fp32, 2 bf16 (next[] is then a bf16 tensor)
 };
 
 #define IAC_THREADS 512
@@ -306,8 +308,8 @@ __global__ void __launch_bounds__(IAC_THREADS) iac_step_kernel(IacArgs a) {
         }
         acc.x = acc.x >= 0.f ? acc.x : 0.1f * acc.x;
         acc.y = acc.y >= 0.f ? acc.y : 0.1f * acc.y;
-        if (a.round_out) acc = make_float2(round_tf32(acc.x), round_tf32(acc.y));
-        *reinterpret_cast<float2*>(next + (img + (size_t)y * W + x) * a.ldnext[dir] + 2 * lane) = acc;
+        if (a.round_out) store_operand2(next, (img + (size_t)y * W + x) * a.ldnext[dir] + 2 * lane, acc, a.round_out == 2);
+        else *reinterpret_cast<float2*>(next + (img + (size_t)y * W + x) * a.ldnext[dir] + 2 * lane) = acc;
     }
 }
 
@@ -336,20 +338,22 @@ extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* pr
     return fcvsr_launch_status();
 }
 
-// y[pix, 0:C] = round_tf32(x[pix, 0:C])  -- TF32-rounded copy of a tensor that is both a tensor-core conv
-// input and a full-precision residual (C % 4 == 0)
-__global__ void round_copy_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int c4, size_t total4) {
+// y[pix, 0:Cy] = operand-typed copy of x[pix, 0:C] (TF32-rounded fp32 or bf16), channels C..Cy-1 zero-filled:
+// the tensor-core operand copy of a tensor that is also a full-precision residual, padded to the K chunk.
+__global__ void round_copy_kernel(const float* __restrict__ x, int ldx, void* __restrict__ y, int ldy, int c4, int cy4,
+                                  size_t total4, int op16) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
-    const size_t pix = i / c4;
-    const int c = (int)(i - pix * c4) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(x + pix * ldx + c);
-    *reinterpret_cast<float4*>(y + pix * ldy + c) = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+    const size_t pix = i / cy4;
+    const int c = (int)(i - pix * cy4) * 4;
+    const float4 v = c < c4 * 4 ? *reinterpret_cast<const float4*>(x + pix * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    store_operand4(y, pix * ldy + c, v, op16);
 }
 
-extern "C" int fcvsr_round_copy(const float* x, int ldx, float* y, int ldy, int C, long long npix, cudaStream_t st) {
-    if (!x || !y || (C & 3) || (ldx & 3) || (ldy & 3)) return FCVSR_ERR_ARG;
-    const size_t total4 = (size_t)npix * (C / 4);
-    round_copy_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, ldx, y, ldy, C / 4, total4);
+extern "C" int fcvsr_round_copy(const float* x, int ldx, void* y, int ldy, int C, int Cy, long long npix, int op16,
+                                cudaStream_t st) {
+    if (!x || !y || (C & 3) || (Cy & 3) || Cy < C || (ldx & 3) || (ldy & 3)) return FCVSR_ERR_ARG;
+    const size_t total4 = (size_t)npix * (Cy / 4);
+    round_copy_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, ldx, y, ldy, C / 4, Cy / 4, total4, op16);
     return fcvsr_launch_status();
 }

@@ -148,7 +148,7 @@ extern "C" int fcvsr_context_block(const float* x, int ldx, const float* wmask, 
 
 // r = lrelu_0.2(res + add[b]) + r0     (all 64 channels, float4 per thread)
 __global__ void rcb_finish_kernel(const float* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
-                                  float* __restrict__ r, int P, size_t total4, int round_out) {
+                                  float* __restrict__ r, int P, size_t total4, void* __restrict__ r_op, int op16) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)(i & 15) * 4;
@@ -163,23 +163,23 @@ __global__ void rcb_finish_kernel(const float* __restrict__ res, const float* __
     o.y = (o.y >= 0.f ? o.y : 0.2f * o.y) + q.y;
     o.z = (o.z >= 0.f ? o.z : 0.2f * o.z) + q.z;
     o.w = (o.w >= 0.f ? o.w : 0.2f * o.w) + q.w;
-    if (round_out) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+    if (r_op) store_operand4(r_op, pix * 64 + c, o, op16);     // tensor-core operand copy for the 1x1 down/up convs
     *reinterpret_cast<float4*>(r + pix * 64 + c) = o;
 }
 
 extern "C" int fcvsr_rcb_finish(const float* res, const float* add, const float* r0, float* r, int B, int P,
-                                int round_out, cudaStream_t st) {
+                                void* r_op, int op16, cudaStream_t st) {
     if (!res || !add || !r0 || !r) return FCVSR_ERR_ARG;
     const size_t total4 = (size_t)B * P * 16;
-    rcb_finish_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(res, add, r0, r, P, total4, round_out);
+    rcb_finish_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(res, add, r0, r, P, total4, r_op, op16);
     return fcvsr_launch_status();
 }
 
 // x[b,y,x,:] += coef * r + mean2x2(td) + bilinear_x2(tu)      (64 channels, ld 64 everywhere except x/y)
 __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* __restrict__ xout, int ldo,
                                  const float* __restrict__ r, float coef, const float* __restrict__ td,
-                                 const float* __restrict__ tu, int H, int W, size_t total4, float* __restrict__ xout_r, int ldr,
-                                 int round_main) {
+                                 const float* __restrict__ tu, int H, int W, size_t total4, void* __restrict__ xout_r, int ldr,
+                                 int round_main, int op16) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)(i & 15) * 4;
@@ -218,16 +218,16 @@ __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* 
         o.z += w00 * a00.z + w01 * a01.z + w10 * a10.z + w11 * a11.z;
         o.w += w00 * a00.w + w01 * a01.w + w10 * a10.w + w11 * a11.w;
     }
-    const float4 orr = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
-    if (xout_r) *reinterpret_cast<float4*>(xout_r + pix * ldr + c) = orr;
-    *reinterpret_cast<float4*>(xout + pix * ldo + c) = round_main ? orr : o;
+    if (xout_r) store_operand4(xout_r, pix * ldr + c, o, op16);
+    if (round_main) store_operand4(xout, pix * ldo + c, o, op16);      // xout itself is an operand-typed tensor
+    else *reinterpret_cast<float4*>(xout + pix * ldo + c) = o;
 }
 
 extern "C" int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float* r, float coef,
-                               const float* td, const float* tu, int B, int H, int W, float* xout_r, int ldr,
-                               int round_main, cudaStream_t st) {
+                               const float* td, const float* tu, int B, int H, int W, void* xout_r, int ldr,
+                               int round_main, int op16, cudaStream_t st) {
     if (!xin || !xout || !r || (ldx & 3) || (ldo & 3) || (tu && ((H | W) & 1)) || (xout_r && (ldr & 3))) return FCVSR_ERR_ARG;
     const size_t total4 = (size_t)B * H * W * 16;
-    level_mix_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(xin, ldx, xout, ldo, r, coef, td, tu, H, W, total4, xout_r, ldr, round_main);
+    level_mix_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(xin, ldx, xout, ldo, r, coef, td, tu, H, W, total4, xout_r, ldr, round_main, op16);
     return fcvsr_launch_status();
 }

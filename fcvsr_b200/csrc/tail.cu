@@ -5,22 +5,24 @@
 #include "common.cuh"
 
 // in [B,H,W,ldi] with 4*Co channels (channel co*4 + i*2 + j) -> out [B,2H,2W,ldo] with Co channels
-__global__ void pixel_shuffle_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int H, int W,
-                                     int Co, size_t total) {
+__global__ void pixel_shuffle_kernel(const void* __restrict__ in, int ldi, void* __restrict__ out, int ldo, int H, int W,
+                                     int Co, size_t total, int half) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int ci = (int)(idx % (4 * Co));
     const size_t pix = idx / (4 * Co);
     const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
     const int co = ci >> 2, i = (ci >> 1) & 1, j = ci & 1;
-    out[(((size_t)b * 2 * H + 2 * y + i) * (2 * W) + 2 * x + j) * ldo + co] = in[pix * ldi + ci];
+    const size_t o = (((size_t)b * 2 * H + 2 * y + i) * (2 * W) + 2 * x + j) * ldo + co;
+    if (half) reinterpret_cast<unsigned short*>(out)[o] = reinterpret_cast<const unsigned short*>(in)[pix * ldi + ci];
+    else reinterpret_cast<float*>(out)[o] = reinterpret_cast<const float*>(in)[pix * ldi + ci];
 }
 
-extern "C" int fcvsr_pixel_shuffle(const float* in, int ldi, float* out, int ldo, int B, int H, int W, int Co,
-                                   cudaStream_t st) {
+extern "C" int fcvsr_pixel_shuffle(const void* in, int ldi, void* out, int ldo, int B, int H, int W, int Co,
+                                   int half, cudaStream_t st) {
     if (!in || !out || Co <= 0) return FCVSR_ERR_ARG;
     const size_t total = (size_t)B * H * W * 4 * Co;
-    pixel_shuffle_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, ldi, out, ldo, H, W, Co, total);
+    pixel_shuffle_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, ldi, out, ldo, H, W, Co, total, half);
     return fcvsr_launch_status();
 }
 
@@ -64,18 +66,20 @@ extern "C" int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, lo
 
 // NCHW clip [B,T,H,W] (T = 7 frames, C = 1) -> NHWC [B,H,W,32] with channels >= T zeroed, TF32-rounded:
 // the tensor-core operand of feat_extract (CVSR_freq.py:2663), whose Cin = 7 is padded to one 32-channel chunk.
-__global__ void pack_clip_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int P, size_t total) {
+__global__ void pack_clip_kernel(const float* __restrict__ x, void* __restrict__ y, int T, int P, int cpad, size_t total,
+                                 int op16) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int c = (int)(idx & 31);
-    const size_t pix = idx >> 5;
+    const int c = (int)(idx % cpad);
+    const size_t pix = idx / cpad;
     const size_t b = pix / P, p = pix - b * P;
-    y[idx] = c < T ? round_tf32(x[(b * T + c) * P + p]) : 0.f;
+    store_operand1(y, idx, c < T ? x[(b * T + c) * P + p] : 0.f, op16);
 }
 
-extern "C" int fcvsr_pack_clip(const float* x, float* y, int B, int T, int H, int W, cudaStream_t st) {
+extern "C" int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int W, int op16, cudaStream_t st) {
     if (!x || !y || T < 1 || T > 32) return FCVSR_ERR_ARG;
-    const size_t total = (size_t)B * H * W * 32;
-    pack_clip_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, y, T, H * W, total);
+    const int cpad = op16 ? 64 : 32;                  // one K chunk of the tensor-core conv
+    const size_t total = (size_t)B * H * W * cpad;
+    pack_clip_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, y, T, H * W, cpad, total, op16);
     return fcvsr_launch_status();
 }

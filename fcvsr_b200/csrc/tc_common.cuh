@@ -68,6 +68,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// kind::f16 (bf16 / fp16 operands, K = 16 per instruction, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// 16 fp32 -> 16 bf16 (round to nearest even), stored as two 16-byte vectors
+__device__ __forceinline__ void store_bf16x16(void* dst, const float* v) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+    }
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
 // Same instruction with the descriptors given as (lo, hi) words: the start-address field lives in the low
 // word, so walking K / taps is one 32-bit add per operand instead of a 64-bit add chain on the uniform datapath.
 __device__ __forceinline__ void umma_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,

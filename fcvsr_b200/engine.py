@@ -40,8 +40,11 @@ class _ConvPack:
 
     def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, ps: bool = False,
                  cin_pad: Optional[int] = None, in_perm: Optional[torch.Tensor] = None,
-                 out_perm: Optional[torch.Tensor] = None):
+                 out_perm: Optional[torch.Tensor] = None, op16: bool = False):
+        """op16: pack the tensor-core weights as bf16 with Cin padded to a multiple of 64 (one 128-byte operand row);
+        otherwise TF32-rounded fp32 with Cin padded to a multiple of 32 when `cin_pad` asks for it."""
         w = w.detach().to(F32)
+        self.op16 = op16
         if in_perm is not None:       # new input position in_perm[j] <- reference input channel j
             w2 = torch.zeros_like(w)
             w2[:, in_perm] = w
@@ -62,6 +65,8 @@ class _ConvPack:
             w = w[idx]
             if b is not None:
                 b = b.detach()[idx]
+        if op16 and cin_pad is None and cin % 64 and cin >= 32:
+            cin_pad = -(-cin // 64) * 64
         if cin_pad is not None and cin_pad > cin:
             w = torch.cat([w, w.new_zeros(cout, cin_pad - cin, k, k)], 1)
             cin = cin_pad
@@ -73,20 +78,30 @@ class _ConvPack:
             wt = torch.cat([wt, wt.new_zeros(16 - cout, wt.shape[1])], 0)
         # tcgen05 kind::tf32 truncates its operands to 10 mantissa bits; rounding the weights to
         # nearest here (cvt.rna semantics) removes their share of the truncation bias for free.
-        self.w_tc = _round_tf32(wt.contiguous())
-        self.tc_ok = stride == 1 and k in (1, 3) and cin % 32 == 0 and (cout < 16 or cout % 16 == 0)
+        self.w_tc = wt.contiguous().to(torch.bfloat16) if op16 else _round_tf32(wt.contiguous())
+        self.tc_ok = stride == 1 and k in (1, 3) and cin % (64 if op16 else 32) == 0 and (cout < 16 or cout % 16 == 0)
         # resident-weight kernel (conv_tc2.cu): k = 3, Cin in {32, 64} per launch, Cout % 64 == 0; Cin = 128 runs as
         # two K-halves chained through the `pre` addend
-        self.tc2_ok = stride == 1 and k == 3 and cin in (32, 64, 128) and cout % 64 == 0
+        self.tc2_ok = (not op16) and stride == 1 and k == 3 and cin in (32, 64, 128) and cout % 64 == 0
         if self.tc2_ok and cin == 128:
             w4 = self.w_tc.view(cout, 9, cin)
             self.w_tc_halves = [w4[:, :, :64].reshape(cout, 9 * 64).contiguous(), w4[:, :, 64:].reshape(cout, 9 * 64).contiguous()]
 
 
 class Engine:
-    def __init__(self, model, use_tc: bool = True):
+    def __init__(self, model, use_tc: bool = True, mode: Optional[str] = None):
+        """mode: "fp32" (CUDA-core FFMA convolutions, exact fp32), "tf32" (tcgen05, fp32 storage, TF32 operands;
+        the contract's fp32 mode) or "bf16" (tcgen05, bf16 operand tensors, fp32 accumulate / residual streams)."""
         self.model = model
-        self.use_tc = use_tc
+        self.mode = mode or ("tf32" if use_tc else "fp32")
+        if self.mode not in ("fp32", "tf32", "bf16"):
+            raise ValueError(f"unknown compute mode {self.mode!r}")
+        self.use_tc = self.mode != "fp32"
+        self.op16 = self.mode == "bf16"
+        self.OPD = torch.bfloat16 if self.op16 else F32       # dtype of tensors that only feed tensor-core convs
+        self.E = 2 if self.op16 else 4
+        self.cc_ld = 256 if self.op16 else 224                # convcorr[0] input: 128 + 81 channels padded to the K chunk
+        self.cat_ld = 128 if self.op16 else 96                # 80 / 84-channel concat buffers of the tail
         self.packs: Optional[Dict[str, object]] = None
         self._pack_key = None
         self._ws: Dict[tuple, Dict[str, torch.Tensor]] = {}
@@ -119,11 +134,16 @@ class Engine:
         n = m.n_feats
         pi = _spec_perm(n).to(device)
 
+        op16 = self.op16
+        kch = 64 if op16 else 32
+
         def cp(name, **kw):
-            return _ConvPack(sd[name + ".weight"], sd.get(name + ".bias"), **kw)
+            return _ConvPack(sd[name + ".weight"], sd.get(name + ".bias"), op16=op16, **kw)
 
         P["feat"] = cp("feat_extract.0")
-        P["feat_tc"] = cp("feat_extract.0", cin_pad=32)      # tensor-core path: clip packed to NHWC-32
+        # tensor-core path: clip packed to one NHWC-32 chunk; kept on TF32 operands in bf16 mode too (the 8-bit
+        # pixel values / 255 would lose three bits as bf16 and the conv is 1 % of the FLOPs)
+        P["feat_tc"] = _ConvPack(sd["feat_extract.0.weight"], sd["feat_extract.0.bias"], cin_pad=32)
         # --- MGAA per-bin MLPs (:1371-1396) on the interleaved spectrum ---
         ar = torch.arange(2 * n, device=device)
         perm_f = torch.cat([pi, 2 * n + pi])                     # cat[x1_f, x2_f] -> [grp0 | grp1]
@@ -136,7 +156,7 @@ class Engine:
         P["crt2"] = cp("MGAA.convcrt.2")
         wcc = sd["MGAA.convcorr.0.weight"][:, : 2 * n + 81]       # the 2 flow channels are zeros (:1484-1485)
         perm_cc = torch.cat([pi, 2 * n + torch.arange(81, device=device)])
-        P["corr0"] = _ConvPack(wcc, None, in_perm=perm_cc, cin_pad=224)
+        P["corr0"] = _ConvPack(wcc, None, in_perm=perm_cc, cin_pad=self.cc_ld, op16=op16)
         P["corr2"] = cp("MGAA.convcorr.2")
         P["corr4"] = cp("MGAA.convcorr.4")
         # ConvBlk stack (:344-357): weights [tap][ci][co] per iteration, back to back
@@ -154,7 +174,7 @@ class Engine:
         # re-ordered to [i][t][c] so the IAC kernel reads 64 contiguous channels per tap
         ii, tt, cc = torch.meshgrid(torch.arange(A), torch.arange(3), torch.arange(n), indexing="ij")
         rows = (ii * 6 * n + cc * 3 + tt).reshape(-1).to(device)
-        P["F1"] = _ConvPack(sd["MGAA.F.1.weight"][rows], sd["MGAA.F.1.bias"][rows])
+        P["F1"] = _ConvPack(sd["MGAA.F.1.weight"][rows], sd["MGAA.F.1.bias"][rows], op16=op16)
         P["conv3"] = cp("MGAA.conv3")
         # --- MFFR (:2104-2133) ---
         for i in range(m.Freq_Inv):
@@ -190,8 +210,8 @@ class Engine:
         # shuffled GEMM columns of upconv1_L2_2 (:2743)
         P["up_l2"] = cp("upconv1_L2", out_perm=ps_pos)
         perm_l22 = torch.cat([ps_pos, n + torch.arange(c4, device=device)])
-        P["up_l2_2"] = cp("upconv1_L2_2", in_perm=perm_l22, cin_pad=96, ps=True)
-        P["fuse"] = cp("upconv_fuse", cin_pad=96)
+        P["up_l2_2"] = cp("upconv1_L2_2", in_perm=perm_l22, cin_pad=self.cat_ld, ps=True)
+        P["fuse"] = cp("upconv_fuse", cin_pad=self.cat_ld)
         P["rec0"] = cp("recorb0")
         P["up1"] = cp("upconv1", ps=True)
         P["up2"] = cp("upconv2", ps=True)
@@ -212,34 +232,38 @@ class Engine:
         Wf = W // 2 + 1
         P, Pf = H * W, H * Wf
         ws: Dict[str, torch.Tensor] = {}
+        OPD = self.OPD
 
-        def buf(name, *shape, zero=False):
+        def buf(name, *shape, zero=False, op=False):
+            """op=True: tensor-core operand tensor (TF32-rounded fp32, or bf16 in bf16 mode)."""
             assert name not in ws, f"workspace name collision: {name}"
-            ws[name] = (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=F32)
+            ws[name] = (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=OPD if op else F32)
 
         buf("feat", B, P, 448)
-        buf("clip32", B, P, 32)
+        buf("clip", B, P, 32)
         for sfx in ("", "_b"):         # two scratch sets: MGAA(f1) and MGAA(f3) run concurrently
             buf("spec" + sfx, B, Pf, 384)
-            buf("h1" + sfx, 2 * B, Pf, 128)
-            buf("h2" + sfx, 2 * B, Pf, 128)
-            buf("cc" + sfx, 2 * B, Pf, 224, zero=True)
-            buf("c1" + sfx, 2 * B, Pf, 64)
-            buf("c2" + sfx, 2 * B, Pf, 64)
+            if self.op16:
+                buf("spec_op" + sfx, B, Pf, 384, op=True)
+            buf("h1" + sfx, 2 * B, Pf, 128, op=True)
+            buf("h2" + sfx, 2 * B, Pf, 128, op=True)
+            buf("cc" + sfx, 2 * B, Pf, self.cc_ld, zero=True, op=True)
+            buf("c1" + sfx, 2 * B, Pf, 64, op=True)
+            buf("c2" + sfx, 2 * B, Pf, 64, op=True)
             buf("off" + sfx, 2 * B, Pf, 4)
-            buf("simh" + sfx, B, Pf, 64)
+            buf("simh" + sfx, B, Pf, 64, op=True)
             buf("sim" + sfx, B, Pf, 4)
             buf("ob_t1" + sfx, A, 2 * B, Pf, 4)
             buf("ob_t2" + sfx, A, 2 * B, Pf, 4)
             buf("ob_partial" + sfx, A * 2 * B * ((Pf + 127) // 128) * 4)
             buf("z" + sfx, B, Pf, 8 * A)
             buf("offs" + sfx, B, P, 4 * A)
-            buf("x2r" + sfx, B, P, 64)
-            buf("kp1" + sfx, B, P, 64)
-            buf("kp2" + sfx, B, P, 64)
+            buf("x2r" + sfx, B, P, 64, op=True)
+            buf("kp1" + sfx, B, P, 64, op=True)
+            buf("kp2" + sfx, B, P, 64, op=True)
             buf("pk" + sfx, B, P, A * 192)
             buf("ping" + sfx, 2, 2, B, P, 64)
-            buf("cat128" + sfx, B, P, 128)
+            buf("cat128" + sfx, B, P, 128, op=self.use_tc)
         buf("m2", B, P, 64)
         buf("specx", B, Pf, 128)
         buf("tmpc", Q, B, Pf, 128)
@@ -252,21 +276,25 @@ class Engine:
         dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
         for l, (h, w) in enumerate(dims):
             p = h * w
-            for nm in ("xs", "cur", "t", "r0", "c1", "res", "rr", "xsr", "curr", "tr"):
+            for nm in ("xs", "cur", "t", "r0", "res", "rr"):          # fp32 streams / residual inputs
                 buf(f"{nm}{l}", B, p, 64)
-            buf(f"a128_{l}", B, p, 128)
+            for nm in ("xsr", "curr", "tr", "r0h", "rrh", "c1"):      # tensor-core operand copies / conv-only tensors
+                buf(f"{nm}{l}", B, p, 64, op=True)
+            buf(f"a128_{l}", B, p, 128, op=True)
             buf(f"td{l}", B, p, 64)
             buf(f"tu{l}", B, p, 64)
             buf(f"ctxp{l}", B * ((p + 127) // 128) * 66)
             buf(f"add{l}", B, 64)
-        buf("o2", B, dims[1][0] * dims[1][1], 64)
-        buf("o3", B, dims[2][0] * dims[2][1], 64)
-        buf("cat2", B, dims[1][0] * dims[1][1], 96, zero=True)
-        buf("fuse", B, P, 96, zero=True)
-        buf("f1", B, P, 64)
-        buf("f2", B, P, 64)
-        buf("up1", B, 4 * P, 64)
-        buf("up2", B, 16 * P, 64)
+        p2, p3 = dims[1][0] * dims[1][1], dims[2][0] * dims[2][1]
+        buf("o2", B, p2, 64, op=self.use_tc)
+        buf("o3", B, p3, 64, op=self.use_tc)
+        buf("u2", B, p2, 64)                                       # out_L2 in full precision (residual of upconv1_L2_2)
+        buf("cat2", B, p2, self.cat_ld, zero=True, op=self.use_tc)
+        buf("fuse", B, P, self.cat_ld, zero=True, op=self.use_tc)
+        buf("f1", B, P, 64, op=self.use_tc)
+        buf("f2", B, P, 64, op=self.use_tc)
+        buf("up1", B, 4 * P, 64, op=self.use_tc)
+        buf("up2", B, 16 * P, 64, op=self.use_tc)
         buf("base", B, 16 * P)
         ws["masks"] = bands.symmetric_half_masks(Q, H, W, device)
         ws["tw_w"] = bands.twiddles(W, device)
@@ -278,7 +306,7 @@ class Engine:
     # launch helpers
     # -------------------------------------------------------------------------------------------
     def _conv(self, pk: _ConvPack, x, ldx, y, ldy, B, H, W, act=C.ACT_NONE, slope=0.0, slope_ptr=0, res=0, ldres=0,
-              res2=0, ldres2=0, nchw=False, cin=None, y2=0, ldy2=0, rnd=False):
+              res2=0, ldres2=0, nchw=False, cin=None, y2=0, ldy2=0, rnd=False, op16=None):
         """x, y, res*: integer device addresses.  `cin`: logical Cin for the direct kernel when the pack
         was padded for the tensor-core path."""
         st = self.st
@@ -291,7 +319,7 @@ class Engine:
             try:
                 self.profile = None
                 self._conv(pk, x, ldx, y, ldy, B, H, W, act, slope, slope_ptr, res, ldres, res2, ldres2, nchw, cin, y2,
-                           ldy2, rnd)
+                           ldy2, rnd, op16)
             finally:
                 self.profile = prof
             self.launches -= 1
@@ -300,6 +328,7 @@ class Engine:
             prof.append((kind, 2.0 * B * ho * wo * pk.cin_logical * pk.cout * pk.k * pk.k,
                          4.0 * B * (H * W * pk.cin_logical + ho * wo * pk.cout), e0, e1))
             return
+        o16 = int(self.op16 if op16 is None else op16)
         if not self.use_tc:          # exact-fp32 mode: nothing is rounded to TF32
             y2, ldy2, rnd = 0, 0, False
         if self.use_tc and self.use_tc2 and pk.tc2_ok and not nchw:
@@ -321,18 +350,21 @@ class Engine:
                    *common, pk.cin, pk.cout, act, slope, slope_ptr, int(pk.ps), y2, ldy2, int(rnd), self.max_ctas, st)
             self.tc_launches += 1
             return
+        if self.op16 and (rnd or y2) and not (pk.tc_ok and not nchw) and rnd:
+            raise RuntimeError("bf16 operand output requested from a convolution the tensor-core kernel cannot run")
         if self.use_tc and pk.tc_ok and not nchw:
             rc = C.try_call("fcvsr_conv2d_tc", x, ldx, pk.w_tc.data_ptr(), pk.bias.data_ptr() if pk.bias is not None else 0,
                             res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin, pk.cout, pk.k, act, slope, slope_ptr,
-                            int(pk.ps), y2, ldy2, int(rnd), self.max_ctas, st)
+                            int(pk.ps), y2, ldy2, int(rnd), self.max_ctas, o16, st)
             if rc == 0:
                 self.tc_launches += 1
                 return
-            if rc != C.ERR_UNSUPPORTED:
+            if rc != C.ERR_UNSUPPORTED or o16:           # bf16 operand tensors cannot fall back to the fp32 kernel
                 raise RuntimeError(f"fcvsr_conv2d_tc failed with status {rc}")
         C.call("fcvsr_conv2d_direct", x, ldx, int(nchw), pk.w_direct.data_ptr(),
                pk.bias.data_ptr() if pk.bias is not None else 0, res, ldres, res2, ldres2, y, ldy, B, H, W, pk.cin,
-               pk.cout, pk.k, pk.stride, act, slope, slope_ptr, int(pk.ps), 0, y2, ldy2, int(rnd), st)
+               pk.cout, pk.k, pk.stride, act, slope, slope_ptr, int(pk.ps), 0, y2, ldy2, int(rnd and not self.op16),
+               int(self.op16), st)
 
     @staticmethod
     def _level_caps(B, dims, sms=148):
@@ -412,14 +444,13 @@ class Engine:
 
     def _run(self, x, out, ws, B, H, W):
         m, P = self.model, self.packs
-        A = m.ACNum
         p = {k: v.data_ptr() for k, v in ws.items()}
-        npix = H * W
+        O16 = int(self.op16)
         f = p["feat"]
         # feat_extract (:2663): NCHW clip -> NHWC 448 channels
         if self.use_tc:
-            self._k("fcvsr_pack_clip", x.data_ptr(), p["clip32"], B, 7, H, W)
-            self._conv(P["feat_tc"], p["clip32"], 32, f, 448, B, H, W)
+            self._k("fcvsr_pack_clip", x.data_ptr(), p["clip"], B, 7, H, W, 0)
+            self._conv(P["feat_tc"], p["clip"], 32, f, 448, B, H, W, op16=0)
         else:
             self._conv(P["feat"], x.data_ptr(), 0, f, 448, B, H, W, nchw=True)
         # MGAA(f1) -> feat[128:192], MGAA(f3) -> feat[256:320]: cat[o1, f2, o3] (:2720) is then the
@@ -443,7 +474,7 @@ class Engine:
             self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)
             self._mgaa(ws, p, f + 256 * 4, 448, f + 256 * 4, 448, B, H, W)
         self._mgaa(ws, p, f + 128 * 4, 448, p["m2"], 64, B, H, W)
-        self._mffr(ws, p, B, H, W)                                   # m2 -> xs0
+        self._mffr(ws, p, B, H, W)                                   # m2 -> xs0 (+ operand copy xsr0)
         self._conv(P["rc1"], p["xs0"], 64, p["xs1"], 64, B, H, W, y2=p["xsr1"], ldy2=64)                  # :2735
         self._conv(P["rc2"], p["xs1"], 64, p["xs2"], 64, B, H // 2, W // 2, y2=p["xsr2"], ldy2=64)        # :2736
         self._scnet(ws, p, B, H, W)
@@ -460,27 +491,34 @@ class Engine:
              if (not sfx) or k.endswith(sfx) or k in shared}
         spec = p["spec"]
         RELU = C.ACT_RELU
-        R = int(self.use_tc)     # tensors that feed tcgen05 convs are stored TF32-rounded (see common.cuh)
-        # rfft2 of x1|x2|x3 (:1452-1454)
+        R, O16, E = int(self.use_tc), int(self.op16), self.E
+        CC = self.cc_ld
+        # rfft2 of x1|x2|x3 (:1452-1454).  TF32 mode rounds the spectrum in place (it is operand and residual at
+        # once); bf16 mode keeps it in fp32 and makes a bf16 operand copy.
         self._k("fcvsr_fft_r2c_w", src, lds, spec, p["tw_w"], B, H, W, 192)
-        self._k("fcvsr_fft_c2c_h", spec, spec, p["tw_h"], 0, B, H, Wf, 192, 0, 1.0, R, 1)
+        self._k("fcvsr_fft_c2c_h", spec, spec, p["tw_h"], 0, B, H, Wf, 192, 0, 1.0, int(R and not O16), 1)
+        sop = spec
+        if O16:
+            sop = p["spec_op"]
+            self._k("fcvsr_round_copy", spec, 384, sop, 384, 384, 384, B * Pf, 1)
         h1, h2, cc = p["h1"], p["h2"], p["cc"]
         half = B * Pf
         # convfuse (:1472-1473); the diff skip rides in the last layer's epilogue (res - res2)
-        self._conv(P["fuse0_f"], spec, 384, h1, 128, B, H, Wf, act=RELU, rnd=True)
-        self._conv(P["fuse0_b"], spec + 128 * 4, 384, h1 + half * 128 * 4, 128, B, H, Wf, act=RELU, rnd=True)
+        self._conv(P["fuse0_f"], sop, 384, h1, 128, B, H, Wf, act=RELU, rnd=True)
+        self._conv(P["fuse0_b"], sop + 128 * E, 384, h1 + half * 128 * E, 128, B, H, Wf, act=RELU, rnd=True)
         self._conv(P["fuse2"], h1, 128, h2, 128, 2 * B, H, Wf, act=RELU, rnd=True)
-        self._conv(P["fuse4"], h2, 128, cc, 224, B, H, Wf, res=spec, ldres=384, res2=spec + 128 * 4, ldres2=384, rnd=True)
-        self._conv(P["fuse4"], h2 + half * 128 * 4, 128, cc + half * 224 * 4, 224, B, H, Wf,
+        self._conv(P["fuse4"], h2, 128, cc, CC, B, H, Wf, res=spec, ldres=384, res2=spec + 128 * 4, ldres2=384, rnd=True)
+        self._conv(P["fuse4"], h2 + half * 128 * E, 128, cc + half * CC * E, CC, B, H, Wf,
                    res=spec + 256 * 4, ldres=384, res2=spec + 128 * 4, ldres2=384, rnd=True)
         # convcrt (:1474)
-        self._conv(P["crt0"], spec + 128 * 4, 384, p["simh"], 64, B, H, Wf, act=RELU, rnd=True)
+        self._conv(P["crt0"], sop + 128 * E, 384, p["simh"], 64, B, H, Wf, act=RELU, rnd=True)
         self._conv(P["crt2"], p["simh"], 64, p["sim"], 4, B, H, Wf)
         # CorrBlock lookup (:1475-1483); corr_f feeds both branches (:1487-1488)
-        self._k("fcvsr_corr_gather", spec, 384, 0, 128, cc + 128 * 4, 224, B, H, Wf, 128)
-        self._k("fcvsr_corr_gather", spec, 384, 0, 128, cc + (half * 224 + 128) * 4, 224, B, H, Wf, 128)
+        om = 2 if O16 else R
+        self._k("fcvsr_corr_gather", spec, 384, 0, 128, cc + 128 * E, CC, B, H, Wf, 128, om)
+        self._k("fcvsr_corr_gather", spec, 384, 0, 128, cc + (half * CC + 128) * E, CC, B, H, Wf, 128, om)
         # convcorr (:1487-1488), both branches as a batch of 2B
-        self._conv(P["corr0"], cc, 224, p["c1"], 64, 2 * B, H, Wf, act=RELU, rnd=True)
+        self._conv(P["corr0"], cc, CC, p["c1"], 64, 2 * B, H, Wf, act=RELU, rnd=True)
         self._conv(P["corr2"], p["c1"], 64, p["c2"], 64, 2 * B, H, Wf, act=RELU, rnd=True)
         self._conv(P["corr4"], p["c2"], 64, p["off"], 4, 2 * B, H, Wf)
         # ConvBlk_i * x2_f_sim for all i (:1494-1498), then irfft2 (:1499-1505)
@@ -493,23 +531,23 @@ class Engine:
         # kernel predictor (:1522-1523)
         x2, ldx2 = src + 64 * 4, lds
         if R:                       # x2 is both the conv_KP operand and the full-precision skip of conv3
-            self._k("fcvsr_round_copy", x2, lds, p["x2r"], 64, 64, B * H * W)
+            self._k("fcvsr_round_copy", x2, lds, p["x2r"], 64, 64, 64, B * H * W, O16)
             x2, ldx2 = p["x2r"], 64
         self._conv(P["kp"], x2, ldx2, p["kp1"], 64, B, H, W, rnd=True)
         self._conv(P["F0"], p["kp1"], 64, p["kp2"], 64, B, H, W, rnd=True)
         self._conv(P["F1"], p["kp2"], 64, p["pk"], A * 192, B, H, W)
-        # IAC (:1526-1527)
+        # IAC (:1526-1527); the last iteration writes the operand-typed conv3 input
         ping = p["ping"]
         sz = B * H * W * 64 * 4
         prev_f, ldpf, prev_b, ldpb = src, lds, src + 128 * 4, lds
         for i in range(A):
             if i == A - 1:
-                nf, nb, ldn = p["cat128"], p["cat128"] + 64 * 4, 128
+                nf, nb, ldn = p["cat128"], p["cat128"] + 64 * (E if R else 4), 128
             else:
                 nf, nb, ldn = ping + (i % 2) * 2 * sz, ping + ((i % 2) * 2 + 1) * sz, 64
             self._k("fcvsr_iac_step", prev_f, ldpf, prev_b, ldpb, src, lds, src + 128 * 4, lds, nf, ldn, nb, ldn,
                     p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["pk"] + i * 192 * 4, A * 192, B, H, W,
-                    R if i == A - 1 else 0)
+                    (2 if O16 else R) if i == A - 1 else 0)
             prev_f, ldpf, prev_b, ldpb = nf, ldn, nb, ldn
         # conv3(cat) + x2 (:1529)
         self._conv(P["conv3"], p["cat128"], 128, dst, ldd, B, H, W, res=src + 64 * 4, ldres=lds)
@@ -546,16 +584,18 @@ class Engine:
                 P["mffr.w2"].data_ptr(), gate(Q), B)
         self._k("fcvsr_mffr_final", p["so"], gate(Q), x, 64, p["xs0"], 64, B, npix)
         if self.use_tc:
-            self._k("fcvsr_round_copy", p["xs0"], 64, p["xsr0"], 64, 64, B * npix)
+            self._k("fcvsr_round_copy", p["xs0"], 64, p["xsr0"], 64, 64, 64, B * npix, int(self.op16))
 
     # SCNetbk (:807-822).  The three pyramid levels of a BlockRCB are independent until the cross-level
     # sum, so each level runs on its own stream (fork/join with events; also valid under graph capture):
     # the small levels (1/4 and 1/16 of the pixels) are latency-bound launches that hide behind level 0.
+    # Full-precision streams (xs, cur, t, r0, rr) stay fp32; every tensor-core convolution reads the operand-typed
+    # copy written next to it (xsr, curr, tr, r0h, rrh: TF32-rounded fp32 or bf16).
     def _scnet(self, ws, p, B, H, W):
         P, G = self.packs, self.model.SCGroupN
         dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
         LK = C.ACT_LEAKY
-        R = int(self.use_tc)
+        R, O16 = int(self.use_tc), int(self.op16)
         main = torch.cuda.current_stream()
         ms = self.multi_stream and self.profile is None
         if ms:
@@ -594,39 +634,43 @@ class Engine:
                 src_r = (inp_r if k == 0 else [p[f"tr{l}"] for l in range(3)]) if R else src
                 for l, (h, w) in enumerate(dims):      # BlockRCB body (:729-751) + RCB (:705-725)
                     with on(l):
+                        r0_op = p[f"r0h{l}"] if R else p[f"r0{l}"]
+                        rr_op = p[f"rrh{l}"] if R else p[f"rr{l}"]
                         self._conv(P[q + "c0"], src_r[l], 64, p[f"a128_{l}"], 128, B, h, w, act=LK, slope=0.1, rnd=True)
-                        self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w, rnd=True)
-                        self._conv(P[q + "r0"], p[f"r0{l}"], 64, p[f"c1{l}"], 64, B, h, w, act=LK, slope=0.2, rnd=True)
+                        self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w, y2=p[f"r0h{l}"], ldy2=64)
+                        self._conv(P[q + "r0"], r0_op, 64, p[f"c1{l}"], 64, B, h, w, act=LK, slope=0.2, rnd=True)
                         self._conv(P[q + "r2"], p[f"c1{l}"], 64, p[f"res{l}"], 64, B, h, w)
                         self.launches += 1
                         self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
                                 P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w)
-                        self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w, R)
+                        self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w,
+                                p[f"rrh{l}"] if R else 0, O16)
                         if l < 2:                       # down: 1x1 conv, pooled in level_mix (:753-757)
-                            self._conv(P[q + "down"], p[f"rr{l}"], 64, p[f"td{l}"], 64, B, h, w)
+                            self._conv(P[q + "down"], rr_op, 64, p[f"td{l}"], 64, B, h, w)
                         if l > 0:                       # up: 1x1 conv, interpolated in level_mix (:759-763)
-                            self._conv(P[q + "up"], p[f"rr{l}"], 64, p[f"tu{l}"], 64, B, h, w)
+                            self._conv(P[q + "up"], rr_op, 64, p[f"tu{l}"], 64, B, h, w)
                 cross_join()
                 # x + r + d + u (:771-776): level 0 has d = r, level 2 has u = r
                 tr = [p[f"tr{l}"] if R else 0 for l in range(3)]
                 with on(0):
-                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0)
+                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0, O16)
                 with on(1):
-                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0)
+                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0, O16)
                 with on(2):
-                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0)
+                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0, O16)
                 cross_join()                            # td/tu/rr of this block are overwritten by the next one
             for l, (h, w) in enumerate(dims):           # SCGroupbk tail: x + conv(res) (:797-803)
                 with on(l):
                     self._conv(P[f"g{g}.conv"], p[f"tr{l}"] if R else p[f"t{l}"], 64, p[f"cur{l}"], 64, B, h, w, res=inp[l],
                                ldres=64, y2=p[f"curr{l}"], ldy2=64)
-        # SCNetbk skip (:816-822): level 0 lands in the 84(96)-channel fuse buffer
+        # SCNetbk skip (:816-822): outputs feed only convolutions -> operand-typed; level 0 lands in the concat buffer
+        CL = self.cat_ld
         with on(0):
-            self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], 96, p["cur0"], 1.0, 0, 0, B, *dims[0], 0, 0, R)
+            self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], CL, p["cur0"], 1.0, 0, 0, B, *dims[0], 0, 0, R, O16)
         with on(1):
-            self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1], 0, 0, R)
+            self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1], 0, 0, R, O16)
         with on(2):
-            self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2], 0, 0, R)
+            self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2], 0, 0, R, O16)
         if ms:
             for s_ in streams[1:]:
                 main.wait_stream(s_)
@@ -639,15 +683,23 @@ class Engine:
         h2, w2, h3, w3 = H // 2, W // 2, H // 4, W // 4
         PR = C.ACT_PRELU
         sl = P["prelu"].data_ptr()
+        R, O16 = int(self.use_tc), int(self.op16)
+        E = self.E if R else 4
+        CL = self.cat_ld
         cat2, fuse = p["cat2"], p["fuse"]
         # out_L3 -> PS -> cat2[64:80] (L2 res) -> PS -> fuse[80:84]
-        self._conv(P["up_l3"], p["o3"], 64, cat2 + 64 * 4, 96, B, h3, w3, act=PR, slope_ptr=sl, rnd=True)
-        self._k("fcvsr_pixel_shuffle", cat2 + 64 * 4, 96, fuse + 80 * 4, 96, B, h2, w2, 4)
-        # out_L2 (kept in shuffle order) -> cat2[0:64]
-        self._conv(P["up_l2"], p["o2"], 64, cat2, 96, B, h2, w2, act=PR, slope_ptr=sl, rnd=True)
+        self._conv(P["up_l3"], p["o3"], 64, cat2 + 64 * E, CL, B, h3, w3, act=PR, slope_ptr=sl, rnd=True)
+        self._k("fcvsr_pixel_shuffle", cat2 + 64 * E, CL, fuse + 80 * E, CL, B, h2, w2, 4, O16)
+        # out_L2 (kept in shuffle order): full precision in u2 (residual below), operand copy in cat2[0:64]
+        if R:
+            self._conv(P["up_l2"], p["o2"], 64, p["u2"], 64, B, h2, w2, act=PR, slope_ptr=sl, y2=cat2, ldy2=CL)
+            u2, ldu2 = p["u2"], 64
+        else:
+            self._conv(P["up_l2"], p["o2"], 64, cat2, CL, B, h2, w2, act=PR, slope_ptr=sl)
+            u2, ldu2 = cat2, CL
         # PS(out_L2 + upconv1_L2_2(cat)) -> fuse[64:80]
-        self._conv(P["up_l2_2"], cat2, 96, fuse + 64 * 4, 96, B, h2, w2, res=cat2, ldres=96, rnd=True)
-        self._conv(P["fuse"], fuse, 96, p["f1"], 64, B, H, W, rnd=True)
+        self._conv(P["up_l2_2"], cat2, CL, fuse + 64 * E, CL, B, h2, w2, res=u2, ldres=ldu2, rnd=True)
+        self._conv(P["fuse"], fuse, CL, p["f1"], 64, B, H, W, rnd=True)
         self._conv(P["rec0"], p["f1"], 64, p["f2"], 64, B, H, W, rnd=True)
         self._conv(P["up1"], p["f2"], 64, p["up1"], 64, B, H, W, act=PR, slope_ptr=sl, rnd=True)
         self._conv(P["up2"], p["up1"], 64, p["up2"], 64, B, 2 * H, 2 * W, act=PR, slope_ptr=sl, rnd=True)

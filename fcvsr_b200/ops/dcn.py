@@ -106,7 +106,7 @@ def _offset_conv(x, conv: nn.Conv2d):
     wp = w.permute(2, 3, 1, 0).contiguous()
     with torch.cuda.device(x.device):
         C.call("fcvsr_conv2d_direct", x.data_ptr(), 0, 1, wp.data_ptr(), conv.bias.data_ptr() if conv.bias is not None else 0,
-               0, 0, 0, 0, y.data_ptr(), 0, b, h, wd, cin, cout, kh, s, C.ACT_NONE, 0.0, 0, 0, 1, 0, 0, 0,
+               0, 0, 0, 0, y.data_ptr(), 0, b, h, wd, cin, cout, kh, s, C.ACT_NONE, 0.0, 0, 0, 1, 0, 0, 0, 0,
                torch.cuda.current_stream().cuda_stream)
     return y
 

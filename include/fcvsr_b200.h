@@ -43,19 +43,21 @@ extern "C" {
 int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const float* w, const float* bias,
                         const float* res, int ldres, const float* res2, int ldres2, float* y, int ldy,
                         int B, int H, int W, int Cin, int Cout, int ksize, int stride, int act, float slope,
-                        const float* slope_ptr, int pixel_shuffle, int y_nchw, float* y2, int ldy2,
-                        int round_out, cudaStream_t stream);
+                        const float* slope_ptr, int pixel_shuffle, int y_nchw, void* y2, int ldy2,
+                        int round_out, int op16, cudaStream_t stream);
 
 /* tcgen05/TMEM implicit-GEMM convolution fed by TMA (stride 1, k in {1,3}, Cin % 32 == 0, Cout % 16 == 0,
  * Cout <= 256), TF32 operands / fp32 accumulate, same fused epilogue as above.
  * w packed [Cout][k*k][Cin] (K-major).  x, y, w, res must be 16-byte aligned, ld multiples of 4.
  * Replaces every 3x3 / 1x1 nn.Conv2d of MGAAbk (CVSR_freq.py:1371-1430), SCNetbk (:705-822) and the
  * up-sampling tail (:2739-2749).  Returns FCVSR_ERR_UNSUPPORTED for shapes outside the envelope.
- * max_ctas > 0 caps the persistent grid (pyramid levels run concurrently on separate streams). */
+ * max_ctas > 0 caps the persistent grid (pyramid levels run concurrently on separate streams).
+ * op16 = 1 selects bf16 operands (kind::f16, K = 16): x and w are bf16 (Cin % 64 == 0), a `round_out` y and y2 are
+ * bf16 tensors (ld in elements); op16 = 0: TF32 operands, `round_out` / y2 store TF32-rounded fp32. */
 int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
                     const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
                     int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
-                    float* y2, int ldy2, int round_out, int max_ctas, cudaStream_t stream);
+                    float* y2, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t stream);
 
 /* Second-generation tcgen05 3x3 convolution: the [64 x 9*Cin] weight slab of each 64-column pass stays
  * RESIDENT in shared memory and the haloed input tile is loaded once (no-swizzle K-major layout, cp.async),
@@ -85,8 +87,8 @@ int fcvsr_fft_c2r_w(const float* in_c, float* y, int ldy, const float* tw, int B
 
 /* CorrBlock lookup (:1279-1337): S [B,H*Wf,ldS] floats with the two packed spectra at float offsets
  * a_off / b_off (C2 floats each, complex-interleaved); out [B,H*Wf,ldo], 81 channels. */
-int fcvsr_corr_gather(const float* S, int ldS, int a_off, int b_off, float* out, int ldo, int B, int H, int Wf,
-                      int C2, cudaStream_t stream);
+int fcvsr_corr_gather(const float* S, int ldS, int a_off, int b_off, void* out, int ldo, int B, int H, int Wf,
+                      int C2, int op_mode /* 0 fp32, 1 TF32-rounded, 2 bf16 */, cudaStream_t stream);
 
 /* ConvBlk(4, index=i) for i < A and both directions (:344-357, :1494-1498):
  * off [2][B][H*Wf][4] (dir-major), w1/w2 packed per iteration [k*k][ci][co] back to back, prelu [A],
@@ -104,8 +106,10 @@ int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int l
                    int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps, int ldtaps,
                    int B, int H, int W, int round_out, cudaStream_t stream);
 
-/* y[pix,0:C] = TF32-rounded x[pix,0:C] (tensor-core operand copy of a tensor that is also a residual) */
-int fcvsr_round_copy(const float* x, int ldx, float* y, int ldy, int C, long long npix, cudaStream_t stream);
+/* y[pix,0:Cy] = operand-typed copy (TF32-rounded fp32 or bf16) of x[pix,0:C], channels C..Cy-1 zero: the
+ * tensor-core operand copy of a tensor that is also a full-precision residual */
+int fcvsr_round_copy(const float* x, int ldx, void* y, int ldy, int C, int Cy, long long npix, int op16,
+                     cudaStream_t stream);
 
 /* ---- MultiFreq_Refinment (CVSR_freq.py:2104-2133, :2183-2254) ---------------------------------- */
 
@@ -128,18 +132,18 @@ int fcvsr_context_block(const float* x, int ldx, const float* wmask, const float
                         float* partial, float* add, int B, int P, cudaStream_t stream);
 /* RCB tail (:720-724): r = lrelu_0.2(res + add[b]) + r0 (64 ch, ld 64) */
 int fcvsr_rcb_finish(const float* res, const float* add, const float* r0, float* r, int B, int P,
-                     int round_out, cudaStream_t stream);
+                     void* r_operand_copy, int op16, cudaStream_t stream);
 /* BlockRCB cross-level sum (:766-777): xout = xin + coef*r + mean2x2(td[B,2H,2W,64]) + bilinear_x2(tu[B,H/2,W/2,64]) */
 int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float* r, float coef, const float* td,
-                    const float* tu, int B, int H, int W, float* xout_r, int ldr, int round_main,
+                    const float* tu, int B, int H, int W, void* xout_r, int ldr, int round_main, int op16,
                     cudaStream_t stream);
 
 /* ---- tail (CVSR_freq.py:2739-2751) -------------------------------------------------------------- */
-int fcvsr_pixel_shuffle(const float* in, int ldi, float* out, int ldo, int B, int H, int W, int Co,
+int fcvsr_pixel_shuffle(const void* in, int ldi, void* out, int ldo, int B, int H, int W, int Co, int half,
                         cudaStream_t stream);
 int fcvsr_bilinear_up4(const float* in, long long bstride, float* out, int B, int H, int W, cudaStream_t stream);
 /* NCHW clip [B,T,H,W] -> NHWC [B,H,W,32] (channels >= T zero, TF32-rounded): tensor-core operand of feat_extract */
-int fcvsr_pack_clip(const float* x, float* y, int B, int T, int H, int W, cudaStream_t stream);
+int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int W, int op16, cudaStream_t stream);
 int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npix, cudaStream_t stream);
 
 /* ---- deformable convolution operator (CVSR_train/ops/dcn) --------------------------------------- */

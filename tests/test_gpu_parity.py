@@ -36,6 +36,7 @@ def _model(variant, sd, dev, use_tc=True):
     m = (arch.GShiftNet_S if variant == "S" else arch.GShiftNet)().to(dev).eval()
     m.load_state_dict(sd)
     m._engine = Engine(m, use_tc=use_tc)
+    m.compute_dtype = m._engine.mode
     return m
 
 
@@ -85,10 +86,10 @@ def _run_conv(dev, x, w, b, tc, act=0, slope=0.0, res=None, ps=False, stride=1):
     rptr = rd.data_ptr() if rd is not None else 0
     if tc:
         C.call("fcvsr_conv2d_tc", xd.data_ptr(), Cin, pk.w_tc.data_ptr(), bias, rptr, cout, 0, 0, y.data_ptr(),
-               y.shape[-1], B, H, W, Cin, cout, w.shape[-1], act, slope, 0, int(ps), 0, 0, 0, 0, _st())
+               y.shape[-1], B, H, W, Cin, cout, w.shape[-1], act, slope, 0, int(ps), 0, 0, 0, 0, 0, _st())
     else:
         C.call("fcvsr_conv2d_direct", xd.data_ptr(), Cin, 0, pk.w_direct.data_ptr(), bias, rptr, cout, 0, 0,
-               y.data_ptr(), y.shape[-1], B, H, W, Cin, cout, w.shape[-1], stride, act, slope, 0, int(ps), 0, 0, 0, 0, _st())
+               y.data_ptr(), y.shape[-1], B, H, W, Cin, cout, w.shape[-1], stride, act, slope, 0, int(ps), 0, 0, 0, 0, 0, _st())
     torch.cuda.synchronize()
     return nchw(y.cpu())
 
@@ -143,7 +144,7 @@ def test_conv_tc_reports_unsupported_shapes(dev):
     w = torch.zeros(64, 48, device=dev)
     y = torch.zeros(1, 8, 8, 64, device=dev)
     rc = C.try_call("fcvsr_conv2d_tc", x.data_ptr(), 48, w.data_ptr(), 0, 0, 0, 0, 0, y.data_ptr(), 64, 1, 8, 8, 48, 64, 1,
-                    0, 0.0, 0, 0, 0, 0, 0, 0, _st())
+                    0, 0.0, 0, 0, 0, 0, 0, 0, 0, _st())
     assert rc == C.ERR_UNSUPPORTED          # Cin % 32 != 0 -> caller must use fcvsr_conv2d_direct
 
 
@@ -368,3 +369,57 @@ def test_conv_tc_resident_matches_fp32_reference(dev, case):
         torch.cuda.synchronize()
         ref2 = F.pixel_shuffle(F.conv2d(x, w, b, padding=1), 2)
         assert float((nchw(y2.cpu()) - ref2).abs().max()) <= 2e-3 * max(1.0, float(ref2.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 operand mode (BASELINE config 2 "fp32 and bf16"): bf16 operand tensors, fp32 accumulate / residual streams.
+# Tolerance stated separately from fp32: max-abs <= 5e-3 and PSNR(ours, reference) >= 60 dB.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(1, 64, 64, 16, 16, 3), (2, 64, 128, 20, 36, 3), (1, 128, 64, 45, 80, 3),
+                                  (1, 64, 256, 12, 20, 3), (2, 256, 128, 10, 33, 1), (1, 64, 4, 11, 19, 1),
+                                  (1, 64, 1, 24, 40, 3), (1, 64, 576, 8, 16, 1)])
+def test_conv_tcgen05_bf16_operands(dev, case):
+    B, ci, co, H, W, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+    b = torch.randn(co, generator=g)
+    res = torch.randn(B, co, H, W, generator=g)
+    pk = _ConvPack(w.to(dev), b.to(dev), op16=True)
+    xd = nhwc(x).to(dev).to(torch.bfloat16)
+    rd = nhwc(res).to(dev)
+    y = torch.empty(B, H, W, co, device=dev)
+    C.call("fcvsr_conv2d_tc", xd.data_ptr(), ci, pk.w_tc.data_ptr(), pk.bias.data_ptr(), rd.data_ptr(), co, 0, 0,
+           y.data_ptr(), co, B, H, W, ci, co, k, 2, 0.1, 0, 0, 0, 0, 0, 0, 1, _st())
+    torch.cuda.synchronize()
+    xr, wr = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()      # the kernel is exact on bf16-rounded operands
+    ref = F.leaky_relu(F.conv2d(xr, wr, b, padding=k // 2), 0.1) + res
+    assert float((nchw(y.cpu()) - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
+    if co % 64 == 0:                                                        # bf16 output through pixel shuffle
+        pk2 = _ConvPack(w.to(dev), b.to(dev), ps=True, op16=True)
+        y2 = torch.empty(B, 2 * H, 2 * W, co // 4, device=dev, dtype=torch.bfloat16)
+        C.call("fcvsr_conv2d_tc", xd.data_ptr(), ci, pk2.w_tc.data_ptr(), pk2.bias.data_ptr(), 0, 0, 0, 0,
+               y2.data_ptr(), co // 4, B, H, W, ci, co, k, 0, 0.0, 0, 1, 0, 0, 1, 0, 1, _st())
+        torch.cuda.synchronize()
+        ref2 = F.pixel_shuffle(F.conv2d(xr, wr, b, padding=k // 2), 2)
+        assert float((nchw(y2.float().cpu()) - ref2).abs().max()) <= 1e-2 * max(1.0, float(ref2.abs().max()))
+
+
+@pytest.mark.parametrize("name", ["fcvsr_s_64", "fcvsr_s_36x40", "fcvsr_full_64"])
+def test_bf16_path_matches_reference_golden(dev, name):
+    g = load_golden(name)
+    c = g["case"]
+    sd = arch.seeded_state_dict(c["variant"], c["seed"])
+    x = make_clip(c["clip_seed"], c["b"], c["h"], c["w"])
+    m = (arch.GShiftNet_S if c["variant"] == "S" else arch.GShiftNet)().to(dev).eval()
+    m.load_state_dict(sd)
+    m.compute_dtype = "bf16"
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    ref = g["out"]
+    assert m._engine.mode == "bf16" and m._engine.tc_launches > 100
+    err = float((y - ref).abs().max())
+    mse = float(((y - ref) ** 2).mean())
+    psnr_vs_ref = 10.0 * torch.log10(torch.tensor(1.0 / max(mse, 1e-20))).item()
+    assert err <= 5e-3, err
+    assert psnr_vs_ref >= 60.0, psnr_vs_ref

@@ -19,7 +19,7 @@ for (B, ci, co, H, W, k) in shapes:
     w = torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5
     pk = _ConvPack(w, None)
     y = torch.empty(B, H, W, co, device=dev)
-    args = (x.data_ptr(), ci, pk.w_tc.data_ptr(), 0, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, k, 0, 0.0, 0, 0, 0, 0, 0, 0, st)
+    args = (x.data_ptr(), ci, pk.w_tc.data_ptr(), 0, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, k, 0, 0.0, 0, 0, 0, 0, 0, 0, 0, st)
     for _ in range(3):
         C.call("fcvsr_conv2d_tc", *args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -42,4 +42,19 @@ for (B, ci, co, H, W, k) in shapes:
         torch.cuda.synchronize()
         us2 = e0.elapsed_time(e1) / 20 * 1e3
         line += f"   | resident: {us2:8.1f} us  {fl / us2 / 1e6:7.1f} TFLOP/s"
+    # bf16 operands
+    pk16 = _ConvPack(w, None, op16=True)
+    x16 = x.to(torch.bfloat16)
+    y16 = torch.empty(B, H, W, co, device=dev, dtype=torch.bfloat16)
+    a3 = (x16.data_ptr(), ci, pk16.w_tc.data_ptr(), 0, 0, 0, 0, 0, y16.data_ptr(), co, B, H, W, ci, co, k, 0, 0.0, 0, 0, 0, 0, 1, 0, 1, st)
+    if ci % 64 == 0:
+        for _ in range(3):
+            C.call("fcvsr_conv2d_tc", *a3)
+        e0.record()
+        for _ in range(20):
+            C.call("fcvsr_conv2d_tc", *a3)
+        e1.record()
+        torch.cuda.synchronize()
+        us3 = e0.elapsed_time(e1) / 20 * 1e3
+        line += f"   | bf16: {us3:8.1f} us  {fl / us3 / 1e6:7.1f} TFLOP/s"
     print(line)

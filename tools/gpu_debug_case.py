@@ -19,6 +19,7 @@ for (seed, cseed, B, H, W) in ((3, 77, 2, 36, 40), (3, 77, 1, 36, 40), (0, 77, 2
     m = arch.GShiftNet_S().to(dev).eval()
     m.load_state_dict(sd)
     m._engine = Engine(m, use_tc=False)
+    m.compute_dtype = 'fp32'
     with torch.no_grad():
         y = m(x.to(dev)).cpu()
     ws = m._engine._ws[(B, H, W, str(dev))]

@@ -23,6 +23,7 @@ def run(seed, cseed, B, H, W):
     m = arch.GShiftNet_S().to(dev).eval()
     m.load_state_dict(sd)
     m._engine = Engine(m, use_tc=False)
+    m.compute_dtype = 'fp32'
     with torch.no_grad():
         y = m(x.to(dev)).cpu()
     ws = m._engine._ws[(B, H, W, str(dev))]

@@ -72,11 +72,11 @@ def run_conv(x, w, b, tc, act=0, slope=0.0, res=None, ps=False, stride=1):
     if tc:
         C.call("fcvsr_conv2d_tc", xd.data_ptr(), Cin, pk.w_tc.data_ptr(), pk.bias.data_ptr() if b is not None else 0,
                rd.data_ptr() if rd is not None else 0, cout, 0, 0, y.data_ptr(), y.shape[-1], B, H, W, Cin, cout,
-               w.shape[-1], act, slope, 0, int(ps), 0, 0, 0, 0, st())
+               w.shape[-1], act, slope, 0, int(ps), 0, 0, 0, 0, 0, st())
     else:
         C.call("fcvsr_conv2d_direct", xd.data_ptr(), Cin, 0, pk.w_direct.data_ptr(),
                pk.bias.data_ptr() if b is not None else 0, rd.data_ptr() if rd is not None else 0, cout, 0, 0,
-               y.data_ptr(), y.shape[-1], B, H, W, Cin, cout, w.shape[-1], stride, act, slope, 0, int(ps), 0, 0, 0, 0, st())
+               y.data_ptr(), y.shape[-1], B, H, W, Cin, cout, w.shape[-1], stride, act, slope, 0, int(ps), 0, 0, 0, 0, 0, st())
     torch.cuda.synchronize()
     return nchw(y.cpu())
 
@@ -109,7 +109,7 @@ def check_conv(tc):
         print("conv_direct stride 2: max err %.2e" % err(y, F.conv2d(x, w, None, stride=2, padding=1))[0])
 
 
-def check_model(variant, H, W, use_tc, B=1):
+def check_model(variant, H, W, use_tc, B=1, mode=None):
     sd = arch.seeded_state_dict(variant, 0)
     x = make_clip(1234, B, H, W)
     t0 = time.time()
@@ -118,7 +118,8 @@ def check_model(variant, H, W, use_tc, B=1):
     t_cpu = time.time() - t0
     model = (arch.GShiftNet_S if variant == "S" else arch.GShiftNet)().to(dev).eval()
     model.load_state_dict(sd)
-    model._engine = Engine(model, use_tc=use_tc)
+    model._engine = Engine(model, use_tc=use_tc, mode=mode)
+    model.compute_dtype = model._engine.mode
     with torch.no_grad():
         y = model(x.to(dev))
         torch.cuda.synchronize()
@@ -136,7 +137,7 @@ def check_model(variant, H, W, use_tc, B=1):
     stages = [("mgaa1", tap(ws["feat"], 128, 192, H, W)), ("mgaa2", tap(ws["m2"], 0, 64, H, W)),
               ("mffr", tap(ws["xs0"], 0, 64, H, W)), ("sc_l1", tap(ws["fuse"], 0, 64, H, W)),
               ("sc_l3", tap(ws["o3"], 0, 64, H // 4, W // 4)), ("fuse", tap(ws["f2"], 0, 64, H, W))]
-    print(f"model {variant} {H}x{W} tc={use_tc}: cpu oracle {t_cpu:.2f}s, gpu eager {t_gpu * 1e3:.1f} ms, "
+    print(f"model {variant} {H}x{W} mode={model._engine.mode}: cpu oracle {t_cpu:.2f}s, gpu eager {t_gpu * 1e3:.1f} ms, "
           f"launches {eng.launches} (tc {eng.tc_launches})")
     for name, got in stages:
         e = err(got, taps[name])
@@ -161,3 +162,4 @@ if __name__ == "__main__":
     check_model(a.variant, a.hw[0], a.hw[1], False)
     if not a.no_tc:
         check_model(a.variant, a.hw[0], a.hw[1], True)
+        check_model(a.variant, a.hw[0], a.hw[1], True, mode="bf16")
