@@ -198,7 +198,7 @@ def main():
             model(x_dev)
             torch.cuda.synchronize()
             prof, eng.profile = eng.profile, None
-            tc = [(f, by, a.elapsed_time(b)) for (k, f, by, a, b) in prof if k == "tc"]
+            tc = [(f, by, a.elapsed_time(b)) for (k, f, by, a, b) in prof if k.startswith("tc")]
             t_tc = sum(t for _, _, t in tc)
             fl_tc = sum(f for f, _, _ in tc)
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -50,6 +50,7 @@ struct ConvTcParams {
     int n_tile, n_tiles;               // N per pass, number of passes
     int tiles_x, tiles_y, total_tiles;
     int act; float slope; const float* slope_ptr; int ps;
+    int wide;                            // 32-byte aligned tensors: use 256-bit loads / stores in the epilogue
     int* err;
     int dbg;                             // bring-up only (FCVSR_TC_DBG): 1 no MMA, 2 no A loads, 4 no B loads, 8 no stores
 };
@@ -232,12 +233,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         v[j] = fcvsr_act(f, p.act, slope);
                     }
                     if (p.res) {
-                        const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.ldres + n0);
+                        float rv[16];
+                        if (p.wide) {
+                            ld_global_v8(p.res + pix * p.ldres + n0, rv);
+                            ld_global_v8(p.res + pix * p.ldres + n0 + 8, rv + 8);
+                        } else {
+                            const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.ldres + n0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 rv = rp[j];
-                            v[4 * j] += rv.x; v[4 * j + 1] += rv.y; v[4 * j + 2] += rv.z; v[4 * j + 3] += rv.w;
+                            for (int j = 0; j < 4; ++j) { const float4 t4 = rp[j]; rv[4 * j] = t4.x; rv[4 * j + 1] = t4.y; rv[4 * j + 2] = t4.z; rv[4 * j + 3] = t4.w; }
                         }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += rv[j];
                     }
                     if (p.res2) {
                         const float4* rp = reinterpret_cast<const float4*>(p.res2 + pix * p.ldres2 + n0);
@@ -250,7 +256,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     // operand-typed outputs: TF32-rounded fp32, or bf16 in bf16 mode
                     if (p.y2) {
                         if (BF16) {
-                            store_bf16x16(reinterpret_cast<__nv_bfloat16*>(p.y2) + pix * p.ldy2 + n0, v);
+                            if (p.wide) store_bf16x16_v8(reinterpret_cast<__nv_bfloat16*>(p.y2) + pix * p.ldy2 + n0, v);
+                            else store_bf16x16(reinterpret_cast<__nv_bfloat16*>(p.y2) + pix * p.ldy2 + n0, v);
+                        } else if (p.wide) {
+                            float vr[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) vr[j] = round_tf32(v[j]);
+                            st_global_v8(p.y2 + pix * p.ldy2 + n0, vr);
+                            st_global_v8(p.y2 + pix * p.ldy2 + n0 + 8, vr + 8);
                         } else {
                             float4* d2 = reinterpret_cast<float4*>(p.y2 + pix * p.ldy2 + n0);
 #pragma unroll
@@ -268,15 +281,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         off = pix * p.ldy + n0;
                     }
                     if (BF16 && p.round_out) {
-                        store_bf16x16(reinterpret_cast<__nv_bfloat16*>(p.y) + off, v);
+                        if (p.wide) store_bf16x16_v8(reinterpret_cast<__nv_bfloat16*>(p.y) + off, v);
+                        else store_bf16x16(reinterpret_cast<__nv_bfloat16*>(p.y) + off, v);
                     } else {
                         if (p.round_out) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
                         }
-                        float4* dp = reinterpret_cast<float4*>(p.y + off);
+                        if (p.wide) {
+                            st_global_v8(p.y + off, v);
+                            st_global_v8(p.y + off + 8, v + 8);
+                        } else {
+                            float4* dp = reinterpret_cast<float4*>(p.y + off);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int j = 0; j < 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
                     }
                 }
             };
@@ -395,6 +414,13 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     p.total_tiles = p.tiles_x * p.tiles_y * B * n_tiles;
     p.act = act; p.slope = slope; p.slope_ptr = slope_ptr; p.ps = pixel_shuffle;
     p.err = tc_err_flag();
+    {   // 256-bit epilogue accesses need 32-byte aligned rows for every tensor the epilogue touches
+        const uintptr_t a = (uintptr_t)y | (uintptr_t)res | (uintptr_t)y2;
+        const int esz_y = (op16 && round_out) ? 2 : 4, esz_y2 = op16 ? 2 : 4;
+        p.wide = !thin && !(a & 31) && !((ldy * esz_y) & 31) && (!res || !((ldres * 4) & 31)) && (!y2 || !((ldy2 * esz_y2) & 31)) &&
+                 (!pixel_shuffle || !(((Cout >> 2) * esz_y) & 31));
+        if (getenv("FCVSR_TC_NARROW")) p.wide = 0;
+    }
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FCVSR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
 
     static int num_sms = 0;

@@ -145,3 +145,25 @@ __device__ __forceinline__ void epi_store16(float* stg, const float* v, float* m
     }
     __syncwarp();
 }
+
+// 256-bit global accesses (sm_100: LDG/STG.256).  A conv epilogue lane owns one pixel, so every warp-level store
+// touches 32 different lines; the LSU retires roughly one line per 3 clk, so bytes-per-line-visit is what counts.
+__device__ __forceinline__ void st_global_v8(float* dst, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const float* src, float* v) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(src));
+}
+// 16 fp32 -> 16 bf16 in one 32-byte store
+__device__ __forceinline__ void store_bf16x16_v8(void* dst, const float* v) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}

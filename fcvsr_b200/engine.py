@@ -325,6 +325,8 @@ class Engine:
             self.launches -= 1
             e1.record()
             kind = "tc" if (self.use_tc and pk.tc_ok and not nchw) else "direct"
+            if kind == "tc":
+                kind = f"tc {pk.cin_logical}->{pk.cout} k{pk.k} {H}x{W}"
             prof.append((kind, 2.0 * B * ho * wo * pk.cin_logical * pk.cout * pk.k * pk.k,
                          4.0 * B * (H * W * pk.cin_logical + ho * wo * pk.cout), e0, e1))
             return
@@ -392,6 +394,14 @@ class Engine:
 
     def _k(self, name, *args):
         self.launches += 1
+        prof = self.profile
+        if prof is not None:        # per-launch CUDA events (bench.py roofline pass / tools/gpu_breakdown.py)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            C.call(name, *args, self.st)
+            e1.record()
+            prof.append((name, 0.0, 0.0, e0, e1))
+            return
         C.call(name, *args, self.st)
 
     # -------------------------------------------------------------------------------------------
