@@ -59,9 +59,10 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* 
     float2 wr[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) wr[t] = tw[t * nb];
+    const float inv_s = 1.0f / (float)s;        // bf < 2^20: (bf + 0.5) * (1/s) truncates to the exact quotient
     for (int idx = threadIdx.x; idx < (nb << cb_log2); idx += blockDim.x) {
         const int bf = idx >> cb_log2, ch = idx & (cb - 1);
-        const int p = bf / s, q = bf - p * s;
+        const int p = (int)(((float)bf + 0.5f) * inv_s), q = bf - p * s;
         float2 v[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) v[k] = in[((q + s * (p + m * k)) << cb_log2) + ch];
@@ -139,9 +140,20 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_r2c_w_kernel(const float* __r
     const int c0 = blockIdx.y * cb;          // first complex lane == real channel pair index
     load_twiddles(tws, tw, n, false);
     const float* src = x + line * (size_t)W * ldx + 2 * c0;
-    for (int idx = threadIdx.x; idx < (n << cb_log2); idx += blockDim.x) {
-        const int i = idx >> cb_log2, ch = idx & (cb - 1);
-        a[idx] = *reinterpret_cast<const float2*>(src + (size_t)i * ldx + 2 * ch);
+    // batches of 8 independent loads per thread: the line must be in flight as a whole, not one element at a time
+    for (int idx0 = threadIdx.x; idx0 < (n << cb_log2); idx0 += 8 * FFT_THREADS) {
+        float2 t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * FFT_THREADS;
+            const int i = idx >> cb_log2, ch = idx & (cb - 1);
+            if (idx < (n << cb_log2)) t[u] = *reinterpret_cast<const float2*>(src + (size_t)i * ldx + 2 * ch);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * FFT_THREADS;
+            if (idx < (n << cb_log2)) a[idx] = t[u];
+        }
     }
     __syncthreads();
     const float2* r = fft_line(a, b, plan, cb_log2, tws, false);
@@ -176,15 +188,24 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_c2c_h_kernel(const float2* in
     const size_t base = ((size_t)bidx * H * Wf + wf) * C + c0;
     if (mask) mask += (size_t)blockIdx.z * H * Wf;                     // replica z: its own mask ...
     out += (size_t)blockIdx.z * gridDim.x * H * C;                     // ... and output ([nrep][B,H,Wf,C])
-    for (int idx = threadIdx.x; idx < (n << cb_log2); idx += blockDim.x) {
-        const int i = idx >> cb_log2, ch = idx & (cb - 1);
-        float2 v = in[base + (size_t)i * Wf * C + ch];
-        if (mask) {
-            const float mk = mask[i * Wf + wf];
-            v.x *= mk;
-            v.y *= mk;
+    for (int idx0 = threadIdx.x; idx0 < (n << cb_log2); idx0 += 8 * FFT_THREADS) {
+        float2 t[8];
+        float mk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * FFT_THREADS;
+            const int i = idx >> cb_log2, ch = idx & (cb - 1);
+            mk[u] = 1.f;
+            if (idx < (n << cb_log2)) {
+                t[u] = in[base + (size_t)i * Wf * C + ch];
+                if (mask) mk[u] = mask[i * Wf + wf];
+            }
         }
-        a[idx] = v;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * FFT_THREADS;
+            if (idx < (n << cb_log2)) a[idx] = make_float2(t[u].x * mk[u], t[u].y * mk[u]);
+        }
     }
     __syncthreads();
     const float2* r = fft_line(a, b, plan, cb_log2, tws, inverse != 0);
@@ -211,15 +232,27 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_c2r_w_kernel(const float2* __
     const int c0 = blockIdx.y * cb;
     load_twiddles(tws, tw, n, true);
     const float2* src = in + line * (size_t)wf * C + 2 * c0;
-    for (int idx = threadIdx.x; idx < (wf << cb_log2); idx += blockDim.x) {
-        const int k = idx >> cb_log2, ch = idx & (cb - 1);
-        float4 ab = *reinterpret_cast<const float4*>(src + (size_t)k * C + 2 * ch);   // A = (x,y), B = (z,w)
-        if (k == 0 || 2 * k == n) {
-            ab.y = 0.f;
-            ab.w = 0.f;
+    for (int idx0 = threadIdx.x; idx0 < (wf << cb_log2); idx0 += 4 * FFT_THREADS) {
+        float4 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * FFT_THREADS;
+            const int k = idx >> cb_log2, ch = idx & (cb - 1);
+            if (idx < (wf << cb_log2)) t[u] = *reinterpret_cast<const float4*>(src + (size_t)k * C + 2 * ch);   // A = (x,y), B = (z,w)
         }
-        a[idx] = make_float2(ab.x - ab.w, ab.y + ab.z);                 // A + iB
-        if (k != 0 && 2 * k != n) a[((n - k) << cb_log2) + ch] = make_float2(ab.x + ab.w, ab.z - ab.y);  // conj(A) + i conj(B)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * FFT_THREADS;
+            if (idx >= (wf << cb_log2)) continue;
+            const int k = idx >> cb_log2, ch = idx & (cb - 1);
+            float4 ab = t[u];
+            if (k == 0 || 2 * k == n) {
+                ab.y = 0.f;
+                ab.w = 0.f;
+            }
+            a[idx] = make_float2(ab.x - ab.w, ab.y + ab.z);                 // A + iB
+            if (k != 0 && 2 * k != n) a[((n - k) << cb_log2) + ch] = make_float2(ab.x + ab.w, ab.z - ab.y);  // conj(A) + i conj(B)
+        }
     }
     __syncthreads();
     const float2* r = fft_line(a, b, plan, cb_log2, tws, true);
