@@ -27,7 +27,7 @@ SIGNATURES = {
     "fcvsr_fft_c2r_w": "p pi p iiii f s",
     "fcvsr_corr_gather": "piii pi iiii i s",
     "fcvsr_offset_blocks": "ppppp pi pppp iiii s",
-    "fcvsr_iac_step": "pi pi pi pi pi pi pi ii pi iii i s",
+    "fcvsr_iac_step": "pi pi pi pi pi pi pi ii pi i iii i s",
     "fcvsr_round_copy": "pi pi ii l i s",
     "fcvsr_chansum64": "pi p ii s",
     "fcvsr_reduce_finalize": "p ii f i pp p i s",

@@ -280,7 +280,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     } else {
                         off = pix * p.ldy + n0;
                     }
-                    if (BF16 && p.round_out) {
+                    if (p.round_out == 2) {          // fp16 output tensor (ld in elements, 32-byte aligned rows)
+                        store_f16x16_v8(reinterpret_cast<unsigned short*>(p.y) + off, v);
+                    } else if (BF16 && p.round_out) {
                         if (p.wide) store_bf16x16_v8(reinterpret_cast<__nv_bfloat16*>(p.y) + off, v);
                         else store_bf16x16(reinterpret_cast<__nv_bfloat16*>(p.y) + off, v);
                     } else {
@@ -373,6 +375,7 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     if (thin && (pixel_shuffle || y2 || round_out)) return FCVSR_ERR_UNSUPPORTED;
     if (y2 && (pixel_shuffle || (ldy2 & 3) || ((uintptr_t)y2 & 15))) return FCVSR_ERR_UNSUPPORTED;
     if (op16 && ((round_out && (ldy & 7)) || (y2 && (ldy2 & 7)))) return FCVSR_ERR_UNSUPPORTED;
+    if (round_out == 2 && (thin || pixel_shuffle || (ldy & 15) || ((uintptr_t)y & 31))) return FCVSR_ERR_UNSUPPORTED;
     if (act == FCVSR_ACT_PRELU && !slope_ptr) return FCVSR_ERR_ARG;
     int n_tile = Cout, n_tiles = 1;
     if (Cout > 128) {       // largest N tile <= 128 that is a multiple of 16 and divides Cout
@@ -416,7 +419,7 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     p.err = tc_err_flag();
     {   // 256-bit epilogue accesses need 32-byte aligned rows for every tensor the epilogue touches
         const uintptr_t a = (uintptr_t)y | (uintptr_t)res | (uintptr_t)y2;
-        const int esz_y = (op16 && round_out) ? 2 : 4, esz_y2 = op16 ? 2 : 4;
+        const int esz_y = ((op16 && round_out) || round_out == 2) ? 2 : 4, esz_y2 = op16 ? 2 : 4;
         p.wide = !thin && !(a & 31) && !((ldy * esz_y) & 31) && (!res || !((ldres * 4) & 31)) && (!y2 || !((ldy2 * esz_y2) & 31)) &&
                  (!pixel_shuffle || !(((Cout >> 2) * esz_y) & 31));
         if (getenv("FCVSR_TC_NARROW")) p.wide = 0;

@@ -12,6 +12,7 @@
 // (2c: real, 2c+1: imag).  The reference's xk_f = cat([imag, real]) channel j therefore maps to
 // float index  j < 64 ? 2j+1 : 2(j-64)  -- the host applies that permutation to the 1x1 weights.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 // ------------------------------------------------------------------------------------------------
 // CorrBlock gather.  S: [B, P, ldS] floats (P = H*Wf), groups a_off / b_off (float offsets) hold the
@@ -199,6 +200,7 @@ struct IacArgs {
     float* next[2];       int ldnext[2];
     const float* offs; int ldoffs; int offs_ch[2];   // channel of dx for each direction
     const float* taps; int ldtaps;                   // already offset to this iteration's 192 channels
+    int taps_half;                                   // taps are fp16 (ld / offsets in elements)
     int B, H, W; int round_out;      // 0 fp32, 1 TF32-rounded fp32, 2 bf16 (next[] is then a bf16 tensor)
 };
 
@@ -232,6 +234,19 @@ __device__ __forceinline__ float2 iac_gather(const float* __restrict__ prev, int
         acc.y = fmaf(wg[i], v[i].y, acc.y);
     }
     return acc;
+}
+
+// the three taps of channels (2*lane, 2*lane+1) of one pixel; `idx` is the element index of tap 0
+__device__ __forceinline__ void iac_load_taps(const IacArgs& a, size_t idx, float2* k) {
+    if (a.taps_half) {
+        const __half* kp = reinterpret_cast<const __half*>(a.taps) + idx;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) k[t] = __half22float2(*reinterpret_cast<const __half2*>(kp + t * IAC_C));
+    } else {
+        const float* kp = a.taps + idx;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) k[t] = *reinterpret_cast<const float2*>(kp + t * IAC_C);
+    }
 }
 
 __global__ void __launch_bounds__(IAC_THREADS) iac_step_kernel(IacArgs a) {
@@ -274,10 +289,8 @@ __global__ void __launch_bounds__(IAC_THREADS) iac_step_kernel(IacArgs a) {
         const int xx = min(max(tx0 - 1 + hx, 0), W - 1);
         float2 acc = make_float2(0.f, 0.f);
         if (y < H) {
-            const float* kp = a.taps + (img + (size_t)y * W + xx) * a.ldtaps + 2 * lane;
             float2 k[3];
-#pragma unroll
-            for (int t = 0; t < 3; ++t) k[t] = *reinterpret_cast<const float2*>(kp + t * IAC_C);
+            iac_load_taps(a, (img + (size_t)y * W + xx) * a.ldtaps + 2 * lane, k);
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
                 const float2 s = *reinterpret_cast<const float2*>(samp + ((ly + t) * (IAC_TW + 2) + hx) * IAC_C + 2 * lane);
@@ -295,10 +308,8 @@ __global__ void __launch_bounds__(IAC_THREADS) iac_step_kernel(IacArgs a) {
         const int ly = op / IAC_TW, lxp = op - ly * IAC_TW;
         const int y = ty0 + ly, x = tx0 + lxp;
         if (y >= H || x >= W) continue;
-        const float* kp = a.taps + (img + (size_t)y * W + x) * a.ldtaps + 2 * lane;
         float2 k[3];
-#pragma unroll
-        for (int t = 0; t < 3; ++t) k[t] = *reinterpret_cast<const float2*>(kp + t * IAC_C);
+        iac_load_taps(a, (img + (size_t)y * W + x) * a.ldtaps + 2 * lane, k);
         float2 acc = *reinterpret_cast<const float2*>(xin + (img + (size_t)y * W + x) * a.ldxin[dir] + 2 * lane);
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
@@ -316,7 +327,7 @@ __global__ void __launch_bounds__(IAC_THREADS) iac_step_kernel(IacArgs a) {
 extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int ldprev_b, const float* xin_f,
                               int ldxin_f, const float* xin_b, int ldxin_b, float* next_f, int ldnext_f, float* next_b,
                               int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps,
-                              int ldtaps, int B, int H, int W, int round_out, cudaStream_t st) {
+                              int ldtaps, int taps_half, int B, int H, int W, int round_out, cudaStream_t st) {
     if (!prev_f || !prev_b || !xin_f || !xin_b || !next_f || !next_b || !offs || !taps) return FCVSR_ERR_ARG;
     if ((ldprev_f | ldprev_b | ldxin_f | ldxin_b | ldnext_f | ldnext_b | ldoffs | ldtaps | ch_f | ch_b) & 1)
         return FCVSR_ERR_ARG;
@@ -325,7 +336,7 @@ extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* pr
     a.xin[0] = xin_f; a.xin[1] = xin_b; a.ldxin[0] = ldxin_f; a.ldxin[1] = ldxin_b;
     a.next[0] = next_f; a.next[1] = next_b; a.ldnext[0] = ldnext_f; a.ldnext[1] = ldnext_b;
     a.offs = offs; a.ldoffs = ldoffs; a.offs_ch[0] = ch_f; a.offs_ch[1] = ch_b;
-    a.taps = taps; a.ldtaps = ldtaps; a.B = B; a.H = H; a.W = W; a.round_out = round_out;
+    a.taps = taps; a.ldtaps = ldtaps; a.taps_half = taps_half; a.B = B; a.H = H; a.W = W; a.round_out = round_out;
     const size_t smem = (IAC_HALO + IAC_TH * (IAC_TW + 2)) * IAC_C * sizeof(float) + IAC_HALO * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {

@@ -158,6 +158,16 @@ __device__ __forceinline__ void ld_global_v8(const float* src, float* v) {
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(src));
 }
+// 16 fp32 -> 16 fp16 in one 32-byte store (10-bit mantissa = TF32 precision at half the bytes; used for the
+// per-pixel filter taps, the largest tensor of the forward)
+__device__ __forceinline__ void store_f16x16_v8(void* dst, const float* v) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
 // 16 fp32 -> 16 bf16 in one 32-byte store
 __device__ __forceinline__ void store_bf16x16_v8(void* dst, const float* v) {
     uint32_t w[8];

@@ -261,7 +261,8 @@ class Engine:
             buf("x2r" + sfx, B, P, 64, op=True)
             buf("kp1" + sfx, B, P, 64, op=True)
             buf("kp2" + sfx, B, P, 64, op=True)
-            buf("pk" + sfx, B, P, A * 192)
+            # per-pixel filter taps (the largest tensor): fp16 in the tensor-core modes (10-bit mantissa = TF32)
+            ws["pk" + sfx] = torch.empty(B, P, A * 192, device=device, dtype=torch.float16 if self.use_tc else F32)
             buf("ping" + sfx, 2, 2, B, P, 64)
             buf("cat128" + sfx, B, P, 128, op=self.use_tc)
         buf("m2", B, P, 64)
@@ -545,7 +546,8 @@ class Engine:
             x2, ldx2 = p["x2r"], 64
         self._conv(P["kp"], x2, ldx2, p["kp1"], 64, B, H, W, rnd=True)
         self._conv(P["F0"], p["kp1"], 64, p["kp2"], 64, B, H, W, rnd=True)
-        self._conv(P["F1"], p["kp2"], 64, p["pk"], A * 192, B, H, W)
+        self._conv(P["F1"], p["kp2"], 64, p["pk"], A * 192, B, H, W, rnd=2 if R else False)
+        TE = 2 if R else 4                                # bytes per tap element
         # IAC (:1526-1527); the last iteration writes the operand-typed conv3 input
         ping = p["ping"]
         sz = B * H * W * 64 * 4
@@ -556,7 +558,7 @@ class Engine:
             else:
                 nf, nb, ldn = ping + (i % 2) * 2 * sz, ping + ((i % 2) * 2 + 1) * sz, 64
             self._k("fcvsr_iac_step", prev_f, ldpf, prev_b, ldpb, src, lds, src + 128 * 4, lds, nf, ldn, nb, ldn,
-                    p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["pk"] + i * 192 * 4, A * 192, B, H, W,
+                    p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["pk"] + i * 192 * TE, A * 192, R, B, H, W,
                     (2 if O16 else R) if i == A - 1 else 0)
             prev_f, ldpf, prev_b, ldpb = nf, ldn, nb, ldn
         # conv3(cat) + x2 (:1529)

@@ -53,7 +53,8 @@ int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const float* w, con
  * up-sampling tail (:2739-2749).  Returns FCVSR_ERR_UNSUPPORTED for shapes outside the envelope.
  * max_ctas > 0 caps the persistent grid (pyramid levels run concurrently on separate streams).
  * op16 = 1 selects bf16 operands (kind::f16, K = 16): x and w are bf16 (Cin % 64 == 0), a `round_out` y and y2 are
- * bf16 tensors (ld in elements); op16 = 0: TF32 operands, `round_out` / y2 store TF32-rounded fp32. */
+ * bf16 tensors (ld in elements); op16 = 0: TF32 operands, `round_out` / y2 store TF32-rounded fp32.
+ * round_out = 2 stores y as fp16 (ld in elements) in either mode (the per-pixel filter taps). */
 int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
                     const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
                     int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
@@ -100,11 +101,12 @@ int fcvsr_offset_blocks(const float* off, const float* w1, const float* w2, cons
 
 /* One IAC iteration (:1230-1250 = flow_warp :1188-1227 + SAC :1253-1276 + residual + LeakyReLU 0.1) for
  * the forward (f) and backward (b) neighbour, 64 channels.  offs [B,H,W,ldoffs]: (dx,dy) at channel
- * ch_f / ch_b.  taps [B,H,W,ldtaps]: 192 channels [t][c] of this iteration. */
+ * ch_f / ch_b.  taps [B,H,W,ldtaps]: 192 channels [t][c] of this iteration (fp16 when taps_half = 1).
+ * round_out: 0 fp32 outputs, 1 TF32-rounded fp32, 2 bf16 (next_* are then bf16 tensors). */
 int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int ldprev_b, const float* xin_f,
                    int ldxin_f, const float* xin_b, int ldxin_b, float* next_f, int ldnext_f, float* next_b,
                    int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps, int ldtaps,
-                   int B, int H, int W, int round_out, cudaStream_t stream);
+                   int taps_half, int B, int H, int W, int round_out, cudaStream_t stream);
 
 /* y[pix,0:Cy] = operand-typed copy (TF32-rounded fp32 or bf16) of x[pix,0:C], channels C..Cy-1 zero: the
  * tensor-core operand copy of a tensor that is also a full-precision residual */
