@@ -21,7 +21,7 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.
 SIGNATURES = {
     "fcvsr_conv2d_direct": "pii pp pi pi pi iiiiiii if p ii pii i s",
     "fcvsr_conv2d_tc": "pi pp pi pi pi iiiiii if p i pii i i s",
-    "fcvsr_conv3x3_tc_resident": "pi pi p pi pi pi iiiii if p i pii i s",
+    "fcvsr_conv3x3_tc_resident": "pi pi p pi pi pi iiiii if p i pii i i s",
     "fcvsr_fft_r2c_w": "pi p p iiii s",
     "fcvsr_fft_c2c_h": "p p p p iiii i f ii s",
     "fcvsr_fft_c2r_w": "p pi p iiii f s",

@@ -39,7 +39,9 @@
 #define TC_A_COPY_BYTES ((TC_TH + 2) * TC_TW * TC_ROW_BYTES)      // 20480
 #define TC_A_STAGE_BYTES (3 * TC_A_COPY_BYTES)                    // 61440
 
-#define TC_THREADS 224
+#define TC_EPI_WARPS 16                 // epilogue warps: TC_EPI_WARPS / 4 per TMEM lane quarter, each a share of the columns
+#define TC_THREADS (32 * (3 + TC_EPI_WARPS))
+#define TC_MAX_COUT 2048               // bias staging in shared memory
 
 struct ConvTcParams {
     const float* bias; const float* res; int ldres; const float* res2; int ldres2;
@@ -79,6 +81,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t* tm_full = bars + 2 * TC_NA + 2 * TC_NB_MAX;   // [2]
     uint64_t* tm_empty = tm_full + 2;                    // [2]
     uint32_t* tmem_slot = (uint32_t*)(tm_empty + 2);
+    // bias staged in shared memory: the epilogue reads it with broadcast ld.shared.v4 (4 per 16-column chunk).  Per-lane
+    // global loads here cost more than the tile's MMAs: the tensor core's operand fetches saturate the L1/shared pipe
+    // and every LDG queues behind them (measured: 64->128 bf16 conv 60 us without bias, 147 us with __ldg bias).
+    float* bias_s = (float*)((uint8_t*)bars + 512);
+    for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) bias_s[i] = (p.bias && i < p.cout_valid) ? p.bias[i] : 0.f;
+    const uint32_t bias_sa = smem_u32(bias_s);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncopies = KS == 3 ? 3 : 1;
@@ -94,7 +102,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
         for (int i = 0; i < TC_NB_MAX; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -189,8 +197,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             }
         }
     } else {
-        // ===== epilogue warps 3..6: TMEM lane quarter = warp % 4 =====
+        // ===== epilogue warps 3..: TMEM lane quarter = warp % 4; the warps of a quarter split the tile's 16-column
+        // chunks.  The epilogue is a latency chain (tcgen05.ld -> scattered 32-byte stores that queue behind the
+        // tensor core's operand fetches), so more warps in flight shorten it almost linearly. =====
         const int q = warp & 3;
+        const int eh = (warp - 3) >> 2;                // which share of the columns
+        const int nchunk = p.n_tile >> 4, cper = (nchunk + TC_EPI_WARPS / 4 - 1) / (TC_EPI_WARPS / 4);
+        const int c_begin = min(eh * cper, nchunk), c_end = min(c_begin + cper, nchunk);
         const int m = q * 32 + lane;                   // pixel within the tile == TMEM lane
         const int ly = m / TC_TW, lx = m - ly * TC_TW;
         const float slope = p.act == FCVSR_ACT_PRELU ? p.slope_ptr[0] : p.slope;
@@ -215,8 +228,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     for (int j = 0; j < 16; ++j) {
                         const int n = n0 + j;
                         if (n < p.cout_valid) {
-                            float f = __uint_as_float(r[j]);
-                            if (p.bias) f += __ldg(p.bias + n);
+                            float f = __uint_as_float(r[j]) + bias_s[n];
                             f = fcvsr_act(f, p.act, slope);
                             if (p.res) f += p.res[pix * p.ldres + n];
                             if (p.res2) f -= p.res2[pix * p.ldres2 + n];
@@ -226,12 +238,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 } else if (valid) {
                     const int n0 = tc.nt * p.n_tile + cb;
                     float v[16];
+                    lds_bias16(bias_sa + n0 * 4, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float f = __uint_as_float(r[j]);
-                        if (p.bias) f += __ldg(p.bias + n0 + j);
-                        v[j] = fcvsr_act(f, p.act, slope);
-                    }
+                    for (int j = 0; j < 16; ++j) v[j] = fcvsr_act(__uint_as_float(r[j]) + v[j], p.act, slope);
                     if (p.res) {
                         float rv[16];
                         if (p.wide) {
@@ -303,16 +312,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             };
             {
                 uint32_t ra[16], rb[16];
-                tmem_ld16(taddr, ra);
-                for (int cb = 0; cb < p.n_tile; cb += 32) {
+                if (c_begin < c_end) tmem_ld16(taddr + c_begin * 16, ra);
+                for (int c = c_begin; c < c_end; c += 2) {
                     tmem_ld_wait();
-                    const bool has_b = cb + 16 < p.n_tile;
-                    if (has_b) tmem_ld16(taddr + cb + 16, rb);
-                    process(ra, cb);
+                    const bool has_b = c + 1 < c_end;
+                    if (has_b) tmem_ld16(taddr + (c + 1) * 16, rb);
+                    process(ra, c * 16);
                     if (has_b) {
                         tmem_ld_wait();
-                        if (cb + 32 < p.n_tile) tmem_ld16(taddr + cb + 32, ra);
-                        process(rb, cb + 16);
+                        if (c + 2 < c_end) tmem_ld16(taddr + (c + 2) * 16, ra);
+                        process(rb, (c + 1) * 16);
                     }
                 }
             }
@@ -386,6 +395,7 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
         n_tiles = Cout / n_tile;
     }
     if (pixel_shuffle && ((Cout & 3) || ((Cout >> 2) % 16))) return FCVSR_ERR_UNSUPPORTED;
+    if (Cout > TC_MAX_COUT) return FCVSR_ERR_UNSUPPORTED;
     EncodeTiledFn enc = get_encode();
     if (!enc) return FCVSR_ERR_CUDA;
 
@@ -428,15 +438,16 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
 
     static int num_sms = 0;
     static bool attr_set = false;
-    const size_t smem = 1024 + TC_NA * TC_A_STAGE_BYTES + TC_B_RING_BYTES + 512;
+    const size_t smem_max = 1024 + TC_NA * TC_A_STAGE_BYTES + TC_B_RING_BYTES + 512 + 4 * TC_MAX_COUT;
+    const size_t smem = smem_max - 4 * TC_MAX_COUT + 4 * (size_t)p.Cout;
     if (!attr_set) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max) != cudaSuccess)
             return FCVSR_ERR_CUDA;
         attr_set = true;
     }

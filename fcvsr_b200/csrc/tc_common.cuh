@@ -177,3 +177,101 @@ __device__ __forceinline__ void store_bf16x16_v8(void* dst, const float* v) {
                  "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                  : "memory");
 }
+
+// 16 consecutive floats from shared memory, same address in every lane (broadcast: one wavefront per instruction)
+__device__ __forceinline__ void lds_bias16(uint32_t saddr, float* b) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b[4 * j]), "=f"(b[4 * j + 1]), "=f"(b[4 * j + 2]), "=f"(b[4 * j + 3]) : "r"(saddr + 16 * j));
+}
+
+// ---- shared epilogue for one 16-column chunk of one output pixel -----------------------------------------
+//   v = act(acc + bias + pre) + res - res2;  y2 <- operand-typed copy;  y <- fp32 | TF32-rounded | bf16 | fp16,
+//   optionally through pixel_shuffle(2) (GEMM columns ordered (i,j,c)).
+struct EpiArgs {
+    const float* bias; uint32_t bias_sa;      // bias_sa: shared-memory copy of bias (zeros when bias == nullptr), set by the kernel
+    const float* pre; int ldpre; const float* res; int ldres; const float* res2; int ldres2;
+    float* y; int ldy; float* y2; int ldy2;
+    int round_out;      // 0 fp32, 1 operand-typed (TF32-rounded fp32 / bf16), 2 fp16
+    int act; float slope; int ps; int wide; int c4; int H, W;
+};
+
+template <bool BF16>
+__device__ __forceinline__ void epi_chunk16(const EpiArgs& e, const uint32_t* r, size_t pix, int n0, int b, int y, int x) {
+    float v[16];
+    lds_bias16(e.bias_sa + n0 * 4, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+    if (e.pre) {
+        float rv[16];
+        ld_global_v8(e.pre + pix * e.ldpre + n0, rv);
+        ld_global_v8(e.pre + pix * e.ldpre + n0 + 8, rv + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += rv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fcvsr_act(v[j], e.act, e.slope);
+    if (e.res) {
+        float rv[16];
+        if (e.wide) {
+            ld_global_v8(e.res + pix * e.ldres + n0, rv);
+            ld_global_v8(e.res + pix * e.ldres + n0 + 8, rv + 8);
+        } else {
+            const float4* rp = reinterpret_cast<const float4*>(e.res + pix * e.ldres + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float4 t4 = rp[j]; rv[4 * j] = t4.x; rv[4 * j + 1] = t4.y; rv[4 * j + 2] = t4.z; rv[4 * j + 3] = t4.w; }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += rv[j];
+    }
+    if (e.res2) {
+        const float4* rp = reinterpret_cast<const float4*>(e.res2 + pix * e.ldres2 + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float4 t4 = rp[j]; v[4 * j] -= t4.x; v[4 * j + 1] -= t4.y; v[4 * j + 2] -= t4.z; v[4 * j + 3] -= t4.w; }
+    }
+    if (e.y2) {
+        if (BF16) {
+            if (e.wide) store_bf16x16_v8(reinterpret_cast<unsigned short*>(e.y2) + pix * e.ldy2 + n0, v);
+            else store_bf16x16(reinterpret_cast<unsigned short*>(e.y2) + pix * e.ldy2 + n0, v);
+        } else {
+            float vr[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vr[j] = round_tf32(v[j]);
+            if (e.wide) {
+                st_global_v8(e.y2 + pix * e.ldy2 + n0, vr);
+                st_global_v8(e.y2 + pix * e.ldy2 + n0 + 8, vr + 8);
+            } else {
+                float4* d2 = reinterpret_cast<float4*>(e.y2 + pix * e.ldy2 + n0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d2[j] = make_float4(vr[4 * j], vr[4 * j + 1], vr[4 * j + 2], vr[4 * j + 3]);
+            }
+        }
+    }
+    size_t off;
+    if (e.ps) {
+        const int ij = n0 / e.c4, c = n0 - ij * e.c4;
+        const size_t opix = ((size_t)b * 2 * e.H + 2 * y + (ij >> 1)) * (2 * (size_t)e.W) + 2 * x + (ij & 1);
+        off = opix * e.ldy + c;
+    } else {
+        off = pix * e.ldy + n0;
+    }
+    if (e.round_out == 2) {
+        store_f16x16_v8(reinterpret_cast<unsigned short*>(e.y) + off, v);
+    } else if (BF16 && e.round_out) {
+        if (e.wide) store_bf16x16_v8(reinterpret_cast<unsigned short*>(e.y) + off, v);
+        else store_bf16x16(reinterpret_cast<unsigned short*>(e.y) + off, v);
+    } else {
+        if (e.round_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+        }
+        if (e.wide) {
+            st_global_v8(e.y + off, v);
+            st_global_v8(e.y + off + 8, v + 8);
+        } else {
+            float4* dp = reinterpret_cast<float4*>(e.y + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+    }
+}

@@ -12,6 +12,8 @@ Line numbers in comments refer to CVSR_train/arch/CVSR_freq.py.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional
 
 import torch
@@ -80,10 +82,12 @@ class _ConvPack:
         # nearest here (cvt.rna semantics) removes their share of the truncation bias for free.
         self.w_tc = wt.contiguous().to(torch.bfloat16) if op16 else _round_tf32(wt.contiguous())
         self.tc_ok = stride == 1 and k in (1, 3) and cin % (64 if op16 else 32) == 0 and (cout < 16 or cout % 16 == 0)
-        # resident-weight kernel (conv_tc2.cu): k = 3, Cin in {32, 64} per launch, Cout % 64 == 0; Cin = 128 runs as
-        # two K-halves chained through the `pre` addend
-        self.tc2_ok = (not op16) and stride == 1 and k == 3 and cin in (32, 64, 128) and cout % 64 == 0
-        if self.tc2_ok and cin == 128:
+        # resident-weight kernel (conv_tc2.cu): k = 3, Cout % 64 == 0 and a weight slab of one 64/128-column pass that
+        # fits in shared memory: Cin in {64, 128} (bf16) or {32, 64} (TF32); TF32 Cin = 128 runs as two K-halves
+        # chained through the `pre` addend
+        self.tc2_ok = stride == 1 and k == 3 and cout % 64 == 0 and cin in ((64, 128) if op16 else (32, 64, 128))
+        self.w_tc_halves = None
+        if self.tc2_ok and cin == 128 and not op16:
             w4 = self.w_tc.view(cout, 9, cin)
             self.w_tc_halves = [w4[:, :, :64].reshape(cout, 9 * 64).contiguous(), w4[:, :, 64:].reshape(cout, 9 * 64).contiguous()]
 
@@ -109,7 +113,9 @@ class Engine:
         self.tc_launches = 0
         self.use_graph = False       # replay the launch sequence from a CUDA graph (one per input shape)
         self._graphs: Dict[tuple, tuple] = {}
-        self.use_tc2 = False         # resident-weight 3x3 kernel (conv_tc2.cu): correct but not faster yet (profiles/r1_notes.md)
+        # resident-weight 3x3 kernel (conv_tc2.cu): "auto" = where it measured at least as fast as conv_tc.cu
+        # (Cout = 64 passes: 64->64 and bf16 128->64, profiles/r1_notes.md); True = wherever eligible; False = never
+        self.use_tc2 = {"0": False, "1": True}.get(os.environ.get("FCVSR_TC2", ""), "auto")
         self._ksplit = {}
         self.max_ctas = 0            # grid cap of the tensor-core convs on the current stream (0 = all SMs)
         self.multi_stream = True     # run the three pyramid levels of SCNetbk on three streams
@@ -334,25 +340,30 @@ class Engine:
         o16 = int(self.op16 if op16 is None else op16)
         if not self.use_tc:          # exact-fp32 mode: nothing is rounded to TF32
             y2, ldy2, rnd = 0, 0, False
-        if self.use_tc and self.use_tc2 and pk.tc2_ok and not nchw:
+        tc2 = self.use_tc2 and pk.tc2_ok
+        if tc2 and self.use_tc2 == "auto":
+            tc2 = pk.cout == 64 and pk.w_tc_halves is None and not pk.ps
+        if self.use_tc and tc2 and not nchw and not res2 and o16 == int(self.op16):
             bias = pk.bias.data_ptr() if pk.bias is not None else 0
             common = (B, H, W)
-            if pk.cin == 128:
+            if pk.w_tc_halves is not None:
                 tmp = self._ksplit_buf(B * H * W * pk.cout, x)
                 C.call("fcvsr_conv3x3_tc_resident", x, ldx, pk.w_tc_halves[0].data_ptr(), 576, 0, 0, 0, 0, 0, tmp, pk.cout,
-                       *common, 64, pk.cout, C.ACT_NONE, 0.0, 0, 0, 0, 0, 0, self.max_ctas, st)
+                       *common, 64, pk.cout, C.ACT_NONE, 0.0, 0, 0, 0, 0, 0, self.max_ctas, 0, st)
                 C.call("fcvsr_conv3x3_tc_resident", x + 64 * 4, ldx, pk.w_tc_halves[1].data_ptr(), 576, bias, tmp, pk.cout,
                        res, ldres, y, ldy, *common, 64, pk.cout, act, slope, slope_ptr, int(pk.ps), y2, ldy2, int(rnd),
-                       self.max_ctas, st)
+                       self.max_ctas, 0, st)
                 self.launches += 1
                 self.tc_launches += 2
-                assert not res2
                 return
-            assert not res2
-            C.call("fcvsr_conv3x3_tc_resident", x, ldx, pk.w_tc.data_ptr(), 9 * pk.cin, bias, 0, 0, res, ldres, y, ldy,
-                   *common, pk.cin, pk.cout, act, slope, slope_ptr, int(pk.ps), y2, ldy2, int(rnd), self.max_ctas, st)
-            self.tc_launches += 1
-            return
+            rc = C.try_call("fcvsr_conv3x3_tc_resident", x, ldx, pk.w_tc.data_ptr(), 9 * pk.cin, bias, 0, 0, res, ldres, y,
+                            ldy, *common, pk.cin, pk.cout, act, slope, slope_ptr, int(pk.ps), y2, ldy2, int(rnd),
+                            self.max_ctas, o16, st)
+            if rc == 0:
+                self.tc_launches += 1
+                return
+            if rc != C.ERR_UNSUPPORTED:
+                raise RuntimeError(f"fcvsr_conv3x3_tc_resident failed with status {rc}")
         if self.op16 and (rnd or y2) and not (pk.tc_ok and not nchw) and rnd:
             raise RuntimeError("bf16 operand output requested from a convolution the tensor-core kernel cannot run")
         if self.use_tc and pk.tc_ok and not nchw:

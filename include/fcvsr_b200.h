@@ -60,15 +60,17 @@ int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, 
                     int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
                     float* y2, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t stream);
 
-/* Second-generation tcgen05 3x3 convolution: the [64 x 9*Cin] weight slab of each 64-column pass stays
- * RESIDENT in shared memory and the haloed input tile is loaded once (no-swizzle K-major layout, cp.async),
- * so L2->SM traffic drops from ~8x to ~1.4x the input bytes.  k = 3, stride 1, Cin in {32, 64}, Cout % 64 == 0;
- * w is [Cout][ldw] K-major with columns (ky,kx,cin).  v = act(acc + bias + pre) + res, same store options as
- * fcvsr_conv2d_tc (`pre` chains the two K-halves of a Cin = 128 convolution).  Same reference call sites. */
-int fcvsr_conv3x3_tc_resident(const float* x, int ldx, const float* w, int ldw, const float* bias, const float* pre,
+/* Second-generation tcgen05 3x3 convolution: the [NP x 9*Cin] weight slab of each NP-column pass (NP = 128 or 64,
+ * whichever fits) stays RESIDENT in shared memory and the haloed input tile is loaded once (no-swizzle K-major
+ * layout, cp.async), so L2->SM traffic drops from ~8x to ~1.4x the input bytes.  k = 3, stride 1, Cout % 64 == 0,
+ * Cin in {32, 64} (op16 = 0, TF32 operands) or {64, 128} (op16 = 1, bf16 operands); other shapes return
+ * FCVSR_ERR_UNSUPPORTED.  w is [Cout][ldw] K-major with columns (ky,kx,cin).  v = act(acc + bias + pre) + res,
+ * same store options as fcvsr_conv2d_tc (`pre` chains the two K-halves of a TF32 Cin = 128 convolution).
+ * Same reference call sites as fcvsr_conv2d_tc. */
+int fcvsr_conv3x3_tc_resident(const void* x, int ldx, const void* w, int ldw, const float* bias, const float* pre,
                               int ldpre, const float* res, int ldres, float* y, int ldy, int B, int H, int W, int Cin,
                               int Cout, int act, float slope, const float* slope_ptr, int pixel_shuffle, float* y2,
-                              int ldy2, int round_out, int max_ctas, cudaStream_t stream);
+                              int ldy2, int round_out, int max_ctas, int op16, cudaStream_t stream);
 
 /* ---- FFT (torch.fft.rfft2 / irfft2 / fftn / ifftn of CVSR_freq.py:1452-1454, :1499-1504, :2082-2088) */
 
