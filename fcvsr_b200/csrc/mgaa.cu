@@ -185,12 +185,16 @@ extern "C" int fcvsr_offset_blocks(const float* off, const float* w1, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// One IAC iteration for both directions.  Tile = 8 x 16 output pixels x 64 channels; a warp owns a
-// pixel at a time and a lane owns channels (2*lane, 2*lane+1).
+// One IAC iteration for both directions.  Tile = 8 x 16 output pixels x 64 channels; a half-warp owns a
+// pixel at a time and a lane owns 4 consecutive channels (16-byte accesses, two pixels per warp instruction).
 //   samp(y',x')  = bilinear(prev, x'+dx(y',x'), y'+dy(y',x'))        zeros outside, align_corners
 //   v(y,x')      = sum_t K[t](y,x') * samp(clamp(y+t-1), x')         (vertical pass, replicate pad)
 //   out(y,x)     = lrelu_0.1( sum_t K[t](y,x) * v(y, clamp(x+t-1)) + xin(y,x) )
 // K[t] of this iteration = taps[..., t*64 + c] (host packs F.1's live rows as [iter][t][c]).
+// The kernel is a chain of dependent global loads (offsets -> gathers; taps -> passes), so it is organised for
+// memory-level parallelism: every thread has 8 gather loads in flight in phase 1, and in phases 2/3 a half-warp
+// owns up to five columns of ONE tile row, loads their taps once (kept in registers for both the vertical and
+// the horizontal pass -- the reference applies kernel1 twice, :1253-1276) with all loads issued up front.
 #define IAC_TH 8
 #define IAC_TW 16
 #define IAC_C 64
@@ -200,23 +204,23 @@ struct IacArgs {
     float* next[2];       int ldnext[2];
     const float* offs; int ldoffs; int offs_ch[2];   // channel of dx for each direction
     const float* taps; int ldtaps;                   // already offset to this iteration's 192 channels
-    int taps_half;                                   // taps are fp16 (ld / offsets in elements)
     int B, H, W; int round_out;      // 0 fp32, 1 TF32-rounded fp32, 2 bf16 (next[] is then a bf16 tensor)
 };
 
 #define IAC_THREADS 512
-#define IAC_WARPS (IAC_THREADS / 32)
+#define IAC_HW (IAC_THREADS / 16)                   // half-warps
 #define IAC_HALO ((IAC_TH + 2) * (IAC_TW + 2))
+#define IAC_NCOL 5                                   // columns of the 18-wide haloed row owned by a half-warp
 
-// bilinear gather of one (pixel, 2-channel) sample; corners outside the image contribute zero
-__device__ __forceinline__ float2 iac_gather(const float* __restrict__ prev, int ldp, size_t img, int H, int W, float sx,
-                                             float sy, int lane) {
-    float2 acc = make_float2(0.f, 0.f);
+// bilinear gather of one (pixel, 4-channel) sample; corners outside the image contribute zero
+__device__ __forceinline__ float4 iac_gather(const float* __restrict__ prev, int ldp, size_t img, int H, int W, float sx,
+                                             float sy, int c0) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!(sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H)) return acc;   // also rejects NaN / inf offsets
     const float fx0 = floorf(sx), fy0 = floorf(sy);
     const float lx = sx - fx0, ly = sy - fy0;
     const int x0 = (int)fx0, y0 = (int)fy0;
-    float2 v[4];
+    float4 v[4];
     float wg[4];
 #pragma unroll
     for (int cy = 0; cy < 2; ++cy)
@@ -225,102 +229,144 @@ __device__ __forceinline__ float2 iac_gather(const float* __restrict__ prev, int
             const int y = y0 + cy, x = x0 + cx;
             const bool ok = y >= 0 && y < H && x >= 0 && x < W;
             wg[cy * 2 + cx] = ok ? (cy ? ly : 1.f - ly) * (cx ? lx : 1.f - lx) : 0.f;
-            v[cy * 2 + cx] = ok ? *reinterpret_cast<const float2*>(prev + (img + (size_t)y * W + x) * ldp + 2 * lane)
-                                : make_float2(0.f, 0.f);
+            v[cy * 2 + cx] = ok ? __ldg(reinterpret_cast<const float4*>(prev + (img + (size_t)y * W + x) * ldp + c0))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         acc.x = fmaf(wg[i], v[i].x, acc.x);
         acc.y = fmaf(wg[i], v[i].y, acc.y);
+        acc.z = fmaf(wg[i], v[i].z, acc.z);
+        acc.w = fmaf(wg[i], v[i].w, acc.w);
     }
     return acc;
 }
 
-// the three taps of channels (2*lane, 2*lane+1) of one pixel; `idx` is the element index of tap 0
-__device__ __forceinline__ void iac_load_taps(const IacArgs& a, size_t idx, float2* k) {
-    if (a.taps_half) {
-        const __half* kp = reinterpret_cast<const __half*>(a.taps) + idx;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) k[t] = __half22float2(*reinterpret_cast<const __half2*>(kp + t * IAC_C));
-    } else {
-        const float* kp = a.taps + idx;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) k[t] = *reinterpret_cast<const float2*>(kp + t * IAC_C);
+// one tap (4 channels) as stored in registers: fp16 pairs in tensor-core modes, fp32 in the exact mode
+template <bool HALF> struct IacTap;
+template <> struct IacTap<true> {
+    uint2 r;
+    __device__ __forceinline__ void load(const void* taps, size_t idx) {
+        r = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(taps) + idx));
     }
-}
+    __device__ __forceinline__ float4 get() const {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+template <> struct IacTap<false> {
+    float4 r;
+    __device__ __forceinline__ void load(const void* taps, size_t idx) {
+        r = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(taps) + idx));
+    }
+    __device__ __forceinline__ float4 get() const { return r; }
+};
 
-__global__ void __launch_bounds__(IAC_THREADS) iac_step_kernel(IacArgs a) {
+template <bool HALF>
+__global__ void __launch_bounds__(IAC_THREADS, HALF ? 2 : 1) iac_step_kernel(IacArgs a) {
     extern __shared__ float smem[];
     float* samp = smem;                                             // [(TH+2)*(TW+2)][64]
     float* vbuf = smem + IAC_HALO * IAC_C;                          // [TH*(TW+2)][64]
     float2* offs_s = reinterpret_cast<float2*>(vbuf + IAC_TH * (IAC_TW + 2) * IAC_C);   // [(TH+2)*(TW+2)] sample coords
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hw = threadIdx.x >> 4, c0 = (threadIdx.x & 15) * 4;
     const int tiles_x = (a.W + IAC_TW - 1) / IAC_TW;
     const int ty0 = (blockIdx.x / tiles_x) * IAC_TH, tx0 = (blockIdx.x % tiles_x) * IAC_TW;
     const int b = blockIdx.y, dir = blockIdx.z;
-    const float* prev = a.prev[dir];
-    const int ldp = a.ldprev[dir];
+    const float* prev = dir ? a.prev[1] : a.prev[0];
+    const int ldp = dir ? a.ldprev[1] : a.ldprev[0];
+    const int offs_ch = dir ? a.offs_ch[1] : a.offs_ch[0];
+    const int ldxin = dir ? a.ldxin[1] : a.ldxin[0], ldnext = dir ? a.ldnext[1] : a.ldnext[0];
     const int H = a.H, W = a.W;
     const size_t img = (size_t)b * H * W;
 
+    // phases 2/3 ownership: tile row `row`, haloed columns cg, cg+4, ... ; taps requested before anything else
+    const int row = hw >> 2, cg = hw & 3;
+    const int y = ty0 + row;
+    IacTap<HALF> k[IAC_NCOL][3];
+#pragma unroll
+    for (int j = 0; j < IAC_NCOL; ++j) {
+        const int hx = cg + 4 * j;
+        if (hx < IAC_TW + 2 && y < H) {
+            const int xx = min(max(tx0 - 1 + hx, 0), W - 1);
+            const size_t idx = (img + (size_t)y * W + xx) * a.ldtaps + c0;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) k[j][t].load(a.taps, idx + t * IAC_C);
+        }
+    }
     // phase 0: sample coordinates of the haloed tile (clamped pixel == replicate padding), one per thread
     for (int hp = threadIdx.x; hp < IAC_HALO; hp += IAC_THREADS) {
         const int hy = hp / (IAC_TW + 2), hx = hp - hy * (IAC_TW + 2);
         const int yy = min(max(ty0 - 1 + hy, 0), H - 1), xx = min(max(tx0 - 1 + hx, 0), W - 1);
-        const float2 d = *reinterpret_cast<const float2*>(a.offs + (img + (size_t)yy * W + xx) * a.ldoffs + a.offs_ch[dir]);
+        const float2 d = *reinterpret_cast<const float2*>(a.offs + (img + (size_t)yy * W + xx) * a.ldoffs + offs_ch);
         offs_s[hp] = make_float2((float)xx + d.x, (float)yy + d.y);
     }
     __syncthreads();
-    // phase 1: warped samples, two halo pixels (8 independent 256-byte gathers) in flight per warp
-    for (int hp = warp; hp < IAC_HALO; hp += 2 * IAC_WARPS) {
-        const int hp2 = hp + IAC_WARPS;
-        const float2 c0 = offs_s[hp];
-        const float2 c1 = hp2 < IAC_HALO ? offs_s[hp2] : make_float2(-2.f, -2.f);
-        const float2 s0 = iac_gather(prev, ldp, img, H, W, c0.x, c0.y, lane);
-        const float2 s1 = iac_gather(prev, ldp, img, H, W, c1.x, c1.y, lane);
-        *reinterpret_cast<float2*>(samp + hp * IAC_C + 2 * lane) = s0;
-        if (hp2 < IAC_HALO) *reinterpret_cast<float2*>(samp + hp2 * IAC_C + 2 * lane) = s1;
+    // phase 1: warped samples, two halo pixels (8 independent 16-byte gathers) in flight per thread
+    for (int hp = hw; hp < IAC_HALO; hp += 2 * IAC_HW) {
+        const int hp2 = hp + IAC_HW;
+        const float2 p0 = offs_s[hp];
+        const float2 p1 = hp2 < IAC_HALO ? offs_s[hp2] : make_float2(-2.f, -2.f);
+        const float4 s0 = iac_gather(prev, ldp, img, H, W, p0.x, p0.y, c0);
+        const float4 s1 = iac_gather(prev, ldp, img, H, W, p1.x, p1.y, c0);
+        *reinterpret_cast<float4*>(samp + hp * IAC_C + c0) = s0;
+        if (hp2 < IAC_HALO) *reinterpret_cast<float4*>(samp + hp2 * IAC_C + c0) = s1;
     }
     __syncthreads();
-    // phase 2: vertical pass for TH rows x (TW+2) columns
-    for (int vp = warp; vp < IAC_TH * (IAC_TW + 2); vp += IAC_WARPS) {
-        const int ly = vp / (IAC_TW + 2), hx = vp - ly * (IAC_TW + 2);
-        const int y = ty0 + ly;
-        const int xx = min(max(tx0 - 1 + hx, 0), W - 1);
-        float2 acc = make_float2(0.f, 0.f);
-        if (y < H) {
-            float2 k[3];
-            iac_load_taps(a, (img + (size_t)y * W + xx) * a.ldtaps + 2 * lane, k);
+    // phase 2: vertical pass for this half-warp's columns of its row
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const float2 s = *reinterpret_cast<const float2*>(samp + ((ly + t) * (IAC_TW + 2) + hx) * IAC_C + 2 * lane);
-                acc.x = fmaf(k[t].x, s.x, acc.x);
-                acc.y = fmaf(k[t].y, s.y, acc.y);
+    for (int j = 0; j < IAC_NCOL; ++j) {
+        const int hx = cg + 4 * j;
+        if (hx < IAC_TW + 2) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y < H) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const float4 kk = k[j][t].get();
+                    const float4 sv = *reinterpret_cast<const float4*>(samp + ((row + t) * (IAC_TW + 2) + hx) * IAC_C + c0);
+                    acc.x = fmaf(kk.x, sv.x, acc.x);
+                    acc.y = fmaf(kk.y, sv.y, acc.y);
+                    acc.z = fmaf(kk.z, sv.z, acc.z);
+                    acc.w = fmaf(kk.w, sv.w, acc.w);
+                }
             }
+            *reinterpret_cast<float4*>(vbuf + (row * (IAC_TW + 2) + hx) * IAC_C + c0) = acc;
         }
-        *reinterpret_cast<float2*>(vbuf + vp * IAC_C + 2 * lane) = acc;
+    }
+    // residual input of the owned output pixels (haloed column hx <-> x = tx0 + hx - 1), in flight across the barrier
+    const float* xin = dir ? a.xin[1] : a.xin[0];
+    float4 xi[IAC_NCOL];
+#pragma unroll
+    for (int j = 0; j < IAC_NCOL; ++j) {
+        const int hx = cg + 4 * j, x = tx0 + hx - 1;
+        if (hx >= 1 && hx <= IAC_TW && x < W && y < H)
+            xi[j] = __ldg(reinterpret_cast<const float4*>(xin + (img + (size_t)y * W + x) * ldxin + c0));
     }
     __syncthreads();
     // phase 3: horizontal pass + residual + LeakyReLU(0.1)
-    const float* xin = a.xin[dir];
-    float* next = a.next[dir];
-    for (int op = warp; op < IAC_TH * IAC_TW; op += IAC_WARPS) {
-        const int ly = op / IAC_TW, lxp = op - ly * IAC_TW;
-        const int y = ty0 + ly, x = tx0 + lxp;
-        if (y >= H || x >= W) continue;
-        float2 k[3];
-        iac_load_taps(a, (img + (size_t)y * W + x) * a.ldtaps + 2 * lane, k);
-        float2 acc = *reinterpret_cast<const float2*>(xin + (img + (size_t)y * W + x) * a.ldxin[dir] + 2 * lane);
+    float* next = dir ? a.next[1] : a.next[0];
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const float2 v = *reinterpret_cast<const float2*>(vbuf + (ly * (IAC_TW + 2) + lxp + t) * IAC_C + 2 * lane);
-            acc.x = fmaf(k[t].x, v.x, acc.x);
-            acc.y = fmaf(k[t].y, v.y, acc.y);
+    for (int j = 0; j < IAC_NCOL; ++j) {
+        const int hx = cg + 4 * j, x = tx0 + hx - 1;
+        if (hx >= 1 && hx <= IAC_TW && x < W && y < H) {
+            float4 acc = xi[j];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const float4 kk = k[j][t].get();
+                const float4 v = *reinterpret_cast<const float4*>(vbuf + (row * (IAC_TW + 2) + hx - 1 + t) * IAC_C + c0);
+                acc.x = fmaf(kk.x, v.x, acc.x);
+                acc.y = fmaf(kk.y, v.y, acc.y);
+                acc.z = fmaf(kk.z, v.z, acc.z);
+                acc.w = fmaf(kk.w, v.w, acc.w);
+            }
+            acc.x = acc.x >= 0.f ? acc.x : 0.1f * acc.x;
+            acc.y = acc.y >= 0.f ? acc.y : 0.1f * acc.y;
+            acc.z = acc.z >= 0.f ? acc.z : 0.1f * acc.z;
+            acc.w = acc.w >= 0.f ? acc.w : 0.1f * acc.w;
+            const size_t o = (img + (size_t)y * W + x) * ldnext + c0;
+            if (a.round_out) store_operand4(next, o, acc, a.round_out == 2);
+            else *reinterpret_cast<float4*>(next + o) = acc;
         }
-        acc.x = acc.x >= 0.f ? acc.x : 0.1f * acc.x;
-        acc.y = acc.y >= 0.f ? acc.y : 0.1f * acc.y;
-        if (a.round_out) store_operand2(next, (img + (size_t)y * W + x) * a.ldnext[dir] + 2 * lane, acc, a.round_out == 2);
-        else *reinterpret_cast<float2*>(next + (img + (size_t)y * W + x) * a.ldnext[dir] + 2 * lane) = acc;
     }
 }
 
@@ -329,23 +375,28 @@ extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* pr
                               int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps,
                               int ldtaps, int taps_half, int B, int H, int W, int round_out, cudaStream_t st) {
     if (!prev_f || !prev_b || !xin_f || !xin_b || !next_f || !next_b || !offs || !taps) return FCVSR_ERR_ARG;
-    if ((ldprev_f | ldprev_b | ldxin_f | ldxin_b | ldnext_f | ldnext_b | ldoffs | ldtaps | ch_f | ch_b) & 1)
+    if (((ldprev_f | ldprev_b | ldxin_f | ldxin_b | ldnext_f | ldnext_b | ldtaps) & 3) || ((ldoffs | ch_f | ch_b) & 1))
         return FCVSR_ERR_ARG;
+    if (((uintptr_t)prev_f | (uintptr_t)prev_b | (uintptr_t)xin_f | (uintptr_t)xin_b | (uintptr_t)next_f | (uintptr_t)next_b) & 15)
+        return FCVSR_ERR_ARG;
+    if ((uintptr_t)taps & (taps_half ? 7 : 15)) return FCVSR_ERR_ARG;
     IacArgs a;
     a.prev[0] = prev_f; a.prev[1] = prev_b; a.ldprev[0] = ldprev_f; a.ldprev[1] = ldprev_b;
     a.xin[0] = xin_f; a.xin[1] = xin_b; a.ldxin[0] = ldxin_f; a.ldxin[1] = ldxin_b;
     a.next[0] = next_f; a.next[1] = next_b; a.ldnext[0] = ldnext_f; a.ldnext[1] = ldnext_b;
     a.offs = offs; a.ldoffs = ldoffs; a.offs_ch[0] = ch_f; a.offs_ch[1] = ch_b;
-    a.taps = taps; a.ldtaps = ldtaps; a.taps_half = taps_half; a.B = B; a.H = H; a.W = W; a.round_out = round_out;
+    a.taps = taps; a.ldtaps = ldtaps; a.B = B; a.H = H; a.W = W; a.round_out = round_out;
     const size_t smem = (IAC_HALO + IAC_TH * (IAC_TW + 2)) * IAC_C * sizeof(float) + IAC_HALO * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(iac_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(iac_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(iac_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return FCVSR_ERR_CUDA;
         attr_set = true;
     }
     dim3 grid(((H + IAC_TH - 1) / IAC_TH) * ((W + IAC_TW - 1) / IAC_TW), B, 2);
-    iac_step_kernel<<<grid, IAC_THREADS, smem, st>>>(a);
+    if (taps_half) iac_step_kernel<true><<<grid, IAC_THREADS, smem, st>>>(a);
+    else iac_step_kernel<false><<<grid, IAC_THREADS, smem, st>>>(a);
     return fcvsr_launch_status();
 }
 
