@@ -17,17 +17,16 @@
 // pixel is one coalesced 256-byte load and its logit one 5-step shuffle reduction).
 __global__ void __launch_bounds__(256) ctx_partial_kernel(const float* __restrict__ x, int ldx,
                                                           const float* __restrict__ wmask, float* __restrict__ partial,
-                                                          int P) {
+                                                          int P, int ppb) {
     __shared__ float sm_m[8], sm_z[8];
     __shared__ float sm_acc[8][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, c = 2 * lane;
     const float2 w = *reinterpret_cast<const float2*>(wmask + c);
     float m = -INFINITY, z = 0.f;
     float2 acc = make_float2(0.f, 0.f);
-    const int p0 = blockIdx.x * CTX_PIX_PER_BLOCK + warp * 16;
+    const int p0 = blockIdx.x * ppb + warp * (ppb >> 3);        // ppb pixels per block (multiple of 128), 1/8 per warp
     const float* xb = x + (size_t)b * P * ldx + c;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < (ppb >> 5); ++it) {
         float2 v[4];
         float lg[4];
 #pragma unroll
@@ -73,48 +72,55 @@ __global__ void __launch_bounds__(256) ctx_partial_kernel(const float* __restric
 }
 
 // grid B, 1024 threads: merge the block partials (fixed order) -> context[64] -> add = W2 lrelu_0.2(W1 ctx).
-// 16 thread groups x 64 channels walk the partial list with 4 independent loads in flight each.
+// The kernel is pure latency (4 CTAs on the whole GPU), so every stage is one round of independent loads:
+// warp-shuffle reductions for max / sum, the per-partial scale exp(m_k - M) computed once into shared memory,
+// 16 thread groups x 64 channels walking the partial list with 8 loads in flight, and the two 64x64 mat-vecs done
+// one warp per output row (coalesced 256-byte row reads + shuffle reduction).
+#define CTX_MAX_NBLK 4096
 __global__ void __launch_bounds__(1024) ctx_finalize_kernel(const float* __restrict__ partial, int nblk,
                                                             const float* __restrict__ w1, const float* __restrict__ w2,
                                                             float* __restrict__ add) {
-    __shared__ float red[1024];
+    __shared__ float red[32];
+    __shared__ float esc[CTX_MAX_NBLK];
     __shared__ float part[16][64];
     __shared__ float ctx[64], hid[64];
-    const int b = blockIdx.x, t = threadIdx.x;
+    const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const float* pp = partial + (size_t)b * nblk * CTX_STRIDE;
     float M = -INFINITY;
     for (int k = t; k < nblk; k += 1024) M = fmaxf(M, pp[k * CTX_STRIDE]);
-    red[t] = M;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    if (lane == 0) red[warp] = M;
     __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) {
-        if (t < s) red[t] = fmaxf(red[t], red[t + s]);
-        __syncthreads();
-    }
-    M = red[0];
+    M = red[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
     __syncthreads();
     float Z = 0.f;
-    for (int k = t; k < nblk; k += 1024) Z += pp[k * CTX_STRIDE + 1] * __expf(pp[k * CTX_STRIDE] - M);
-    red[t] = Z;
-    __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) {
-        if (t < s) red[t] += red[t + s];
-        __syncthreads();
+    for (int k = t; k < nblk; k += 1024) {
+        const float e = __expf(pp[k * CTX_STRIDE] - M);
+        esc[k] = e;
+        Z += pp[k * CTX_STRIDE + 1] * e;
     }
-    Z = red[0];
+    // fixed-order (deterministic) tree: lanes, then warps
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
+    if (lane == 0) red[warp] = Z;
+    __syncthreads();
+    Z = red[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
     const int c = t & 63, q = t >> 6;
     float A = 0.f;
     int k = q;
-    for (; k + 48 < nblk; k += 64) {
-        const float m0 = pp[k * CTX_STRIDE], m1 = pp[(k + 16) * CTX_STRIDE], m2 = pp[(k + 32) * CTX_STRIDE],
-                    m3 = pp[(k + 48) * CTX_STRIDE];
-        const float a0 = pp[k * CTX_STRIDE + 2 + c], a1 = pp[(k + 16) * CTX_STRIDE + 2 + c],
-                    a2 = pp[(k + 32) * CTX_STRIDE + 2 + c], a3 = pp[(k + 48) * CTX_STRIDE + 2 + c];
-        A += a0 * __expf(m0 - M);
-        A += a1 * __expf(m1 - M);
-        A += a2 * __expf(m2 - M);
-        A += a3 * __expf(m3 - M);
+    for (; k + 112 < nblk; k += 128) {
+        float av[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) av[u] = pp[(k + 16 * u) * CTX_STRIDE + 2 + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) A += av[u] * esc[k + 16 * u];
     }
-    for (; k < nblk; k += 16) A += pp[k * CTX_STRIDE + 2 + c] * __expf(pp[k * CTX_STRIDE] - M);
+    for (; k < nblk; k += 16) A += pp[k * CTX_STRIDE + 2 + c] * esc[k];
     part[q][c] = A;
     __syncthreads();
     if (t < 64) {
@@ -124,24 +130,29 @@ __global__ void __launch_bounds__(1024) ctx_finalize_kernel(const float* __restr
         ctx[t] = s / Z;
     }
     __syncthreads();
-    if (t < 64) {
-        float h = 0.f;
-        for (int j = 0; j < 64; ++j) h += w1[t * 64 + j] * ctx[j];
-        hid[t] = h >= 0.f ? h : 0.2f * h;
+    for (int r = warp; r < 64; r += 32) {            // hid[r] = lrelu_0.2(W1[r,:] . ctx)
+        float h = w1[r * 64 + lane] * ctx[lane] + w1[r * 64 + 32 + lane] * ctx[32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+        if (lane == 0) hid[r] = h >= 0.f ? h : 0.2f * h;
     }
     __syncthreads();
-    if (t < 64) {
-        float o = 0.f;
-        for (int j = 0; j < 64; ++j) o += w2[t * 64 + j] * hid[j];
-        add[(size_t)b * 64 + t] = o;
+    for (int r = warp; r < 64; r += 32) {            // add[r] = W2[r,:] . hid
+        float o2 = w2[r * 64 + lane] * hid[lane] + w2[r * 64 + 32 + lane] * hid[32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) o2 += __shfl_xor_sync(0xffffffffu, o2, o);
+        if (lane == 0) add[(size_t)b * 64 + r] = o2;
     }
 }
 
 extern "C" int fcvsr_context_block(const float* x, int ldx, const float* wmask, const float* w1, const float* w2,
                                    float* partial, float* add, int B, int P, cudaStream_t st) {
     if (!x || !wmask || !w1 || !w2 || !partial || !add || (ldx & 1)) return FCVSR_ERR_ARG;
-    const int nblk = (P + CTX_PIX_PER_BLOCK - 1) / CTX_PIX_PER_BLOCK;
-    ctx_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, ldx, wmask, partial, P);
+    // 128 pixels per block (as sized by the caller's `partial` buffer) unless that needs more than CTX_MAX_NBLK blocks
+    int ppb = CTX_PIX_PER_BLOCK;
+    while ((P + ppb - 1) / ppb > CTX_MAX_NBLK) ppb += CTX_PIX_PER_BLOCK;
+    const int nblk = (P + ppb - 1) / ppb;
+    ctx_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, ldx, wmask, partial, P, ppb);
     ctx_finalize_kernel<<<B, 1024, 0, st>>>(partial, nblk, w1, w2, add);
     return fcvsr_launch_status();
 }
@@ -167,9 +178,56 @@ __global__ void rcb_finish_kernel(const float* __restrict__ res, const float* __
     *reinterpret_cast<float4*>(r + pix * 64 + c) = o;
 }
 
+// Same, one thread per 2x2 pixel quad x 4 channels, additionally writing the quad mean: the 1x1 `down` convolution
+// commutes with the 2x2 average that follows it in the reference (:753-757, Interpolate(0.5) of an even-sized map),
+// so it runs on this pooled tensor at a quarter of the pixels.  pool_plain: store the mean as plain fp32 (exact mode)
+// instead of the operand type.
+__global__ void rcb_finish_pool_kernel(const float* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
+                                       float* __restrict__ r, int H, int W, size_t total, void* __restrict__ r_op, int op16,
+                                       void* __restrict__ r_pool, int pool_plain) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i & 15) * 4;
+    const size_t quad = i >> 4;
+    const int w2 = W >> 1, h2 = H >> 1;
+    const int qx = (int)(quad % w2), qy = (int)((quad / w2) % h2), b = (int)(quad / ((size_t)w2 * h2));
+    const size_t p00 = ((size_t)b * H + 2 * qy) * W + 2 * qx;
+    const size_t pix[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+    const float4 a = *reinterpret_cast<const float4*>(add + (size_t)b * 64 + c);
+    float4 v[4], q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = *reinterpret_cast<const float4*>(res + pix[k] * 64 + c);
+        q[k] = *reinterpret_cast<const float4*>(r0 + pix[k] * 64 + c);
+    }
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float4 o;
+        o.x = v[k].x + a.x; o.y = v[k].y + a.y; o.z = v[k].z + a.z; o.w = v[k].w + a.w;
+        o.x = (o.x >= 0.f ? o.x : 0.2f * o.x) + q[k].x;
+        o.y = (o.y >= 0.f ? o.y : 0.2f * o.y) + q[k].y;
+        o.z = (o.z >= 0.f ? o.z : 0.2f * o.z) + q[k].z;
+        o.w = (o.w >= 0.f ? o.w : 0.2f * o.w) + q[k].w;
+        if (r_op) store_operand4(r_op, pix[k] * 64 + c, o, op16);
+        *reinterpret_cast<float4*>(r + pix[k] * 64 + c) = o;
+        m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+    }
+    m.x *= 0.25f; m.y *= 0.25f; m.z *= 0.25f; m.w *= 0.25f;
+    if (pool_plain) *reinterpret_cast<float4*>(reinterpret_cast<float*>(r_pool) + quad * 64 + c) = m;
+    else store_operand4(r_pool, quad * 64 + c, m, op16);
+}
+
 extern "C" int fcvsr_rcb_finish(const float* res, const float* add, const float* r0, float* r, int B, int P,
-                                void* r_op, int op16, cudaStream_t st) {
+                                void* r_op, int op16, void* r_pool, int H, int W, int pool_plain, cudaStream_t st) {
     if (!res || !add || !r0 || !r) return FCVSR_ERR_ARG;
+    if (r_pool) {
+        if (H <= 0 || W <= 0 || ((H | W) & 1) || (size_t)H * W != (size_t)P) return FCVSR_ERR_ARG;
+        const size_t total = (size_t)B * (P / 4) * 16;
+        rcb_finish_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(res, add, r0, r, H, W, total, r_op, op16, r_pool,
+                                                                              pool_plain);
+        return fcvsr_launch_status();
+    }
     const size_t total4 = (size_t)B * P * 16;
     rcb_finish_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(res, add, r0, r, P, total4, r_op, op16);
     return fcvsr_launch_status();
@@ -179,7 +237,7 @@ extern "C" int fcvsr_rcb_finish(const float* res, const float* add, const float*
 __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* __restrict__ xout, int ldo,
                                  const float* __restrict__ r, float coef, const float* __restrict__ td,
                                  const float* __restrict__ tu, int H, int W, size_t total4, void* __restrict__ xout_r, int ldr,
-                                 int round_main, int op16) {
+                                 int round_main, int op16, int td_pooled) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)(i & 15) * 4;
@@ -190,7 +248,10 @@ __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* 
     float4 o = *reinterpret_cast<const float4*>(xin + pix * ldx + c);
     const float4 rv = *reinterpret_cast<const float4*>(r + pix * 64 + c);
     o.x = fmaf(coef, rv.x, o.x); o.y = fmaf(coef, rv.y, o.y); o.z = fmaf(coef, rv.z, o.z); o.w = fmaf(coef, rv.w, o.w);
-    if (td) {   // td is [B,2H,2W,64]
+    if (td && td_pooled) {   // td is [B,H,W,64]: the down conv already ran on the 2x2 mean (see rcb_finish_pool_kernel)
+        const float4 a0 = *reinterpret_cast<const float4*>(td + pix * 64 + c);
+        o.x += a0.x; o.y += a0.y; o.z += a0.z; o.w += a0.w;
+    } else if (td) {   // td is [B,2H,2W,64]
         const size_t base = (((size_t)b * 2 * H + 2 * y) * (2 * W) + 2 * x) * 64 + c;
         const float4 a0 = *reinterpret_cast<const float4*>(td + base);
         const float4 a1 = *reinterpret_cast<const float4*>(td + base + 64);
@@ -225,9 +286,9 @@ __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* 
 
 extern "C" int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float* r, float coef,
                                const float* td, const float* tu, int B, int H, int W, void* xout_r, int ldr,
-                               int round_main, int op16, cudaStream_t st) {
+                               int round_main, int op16, int td_pooled, cudaStream_t st) {
     if (!xin || !xout || !r || (ldx & 3) || (ldo & 3) || (tu && ((H | W) & 1)) || (xout_r && (ldr & 3))) return FCVSR_ERR_ARG;
     const size_t total4 = (size_t)B * H * W * 16;
-    level_mix_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(xin, ldx, xout, ldo, r, coef, td, tu, H, W, total4, xout_r, ldr, round_main, op16);
+    level_mix_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(xin, ldx, xout, ldo, r, coef, td, tu, H, W, total4, xout_r, ldr, round_main, op16, td_pooled);
     return fcvsr_launch_status();
 }

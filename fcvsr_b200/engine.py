@@ -288,7 +288,8 @@ class Engine:
             for nm in ("xsr", "curr", "tr", "r0h", "rrh", "c1"):      # tensor-core operand copies / conv-only tensors
                 buf(f"{nm}{l}", B, p, 64, op=True)
             buf(f"a128_{l}", B, p, 128, op=True)
-            buf(f"td{l}", B, p, 64)
+            buf(f"td{l}", B, p // 4, 64)                           # down conv output, already at the next level's size
+            buf(f"rrp{l}", B, p // 4, 64, op=self.use_tc)          # 2x2 mean of rr: input of the down conv
             buf(f"tu{l}", B, p, 64)
             buf(f"ctxp{l}", B * ((p + 127) // 128) * 66)
             buf(f"add{l}", B, 64)
@@ -667,20 +668,20 @@ class Engine:
                         self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
                                 P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w)
                         self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w,
-                                p[f"rrh{l}"] if R else 0, O16)
-                        if l < 2:                       # down: 1x1 conv, pooled in level_mix (:753-757)
-                            self._conv(P[q + "down"], rr_op, 64, p[f"td{l}"], 64, B, h, w)
+                                p[f"rrh{l}"] if R else 0, O16, p[f"rrp{l}"] if l < 2 else 0, h, w, int(not R))
+                        if l < 2:                       # down: 1x1 conv on the 2x2 mean == mean of the conv (:753-757)
+                            self._conv(P[q + "down"], p[f"rrp{l}"], 64, p[f"td{l}"], 64, B, h // 2, w // 2)
                         if l > 0:                       # up: 1x1 conv, interpolated in level_mix (:759-763)
                             self._conv(P[q + "up"], rr_op, 64, p[f"tu{l}"], 64, B, h, w)
                 cross_join()
                 # x + r + d + u (:771-776): level 0 has d = r, level 2 has u = r
                 tr = [p[f"tr{l}"] if R else 0 for l in range(3)]
                 with on(0):
-                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0, O16)
+                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0, O16, 0)
                 with on(1):
-                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0, O16)
+                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0, O16, 1)
                 with on(2):
-                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0, O16)
+                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0, O16, 1)
                 cross_join()                            # td/tu/rr of this block are overwritten by the next one
             for l, (h, w) in enumerate(dims):           # SCGroupbk tail: x + conv(res) (:797-803)
                 with on(l):
@@ -689,11 +690,11 @@ class Engine:
         # SCNetbk skip (:816-822): outputs feed only convolutions -> operand-typed; level 0 lands in the concat buffer
         CL = self.cat_ld
         with on(0):
-            self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], CL, p["cur0"], 1.0, 0, 0, B, *dims[0], 0, 0, R, O16)
+            self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], CL, p["cur0"], 1.0, 0, 0, B, *dims[0], 0, 0, R, O16, 0)
         with on(1):
-            self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1], 0, 0, R, O16)
+            self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1], 0, 0, R, O16, 0)
         with on(2):
-            self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2], 0, 0, R, O16)
+            self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2], 0, 0, R, O16, 0)
         if ms:
             for s_ in streams[1:]:
                 main.wait_stream(s_)
