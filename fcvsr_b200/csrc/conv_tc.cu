@@ -162,22 +162,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const uint32_t b_step = b_bytes >> 4;
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int acc = 0; uint32_t pacc = 0;
+            uint32_t pre_t = 0, pre_a = 0, pre_b = 0;          // early polls of the upcoming step's barriers (1 = already complete)
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                mbar_wait(&tm_empty[acc], pacc ^ 1, p.err, 3);
+                if (!pre_t) mbar_wait(&tm_empty[acc], pacc ^ 1, p.err, 3);
+                pre_t = 0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
                 for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(&full_a[sa], pa, p.err, 4);
+                    if (!pre_a) mbar_wait(&full_a[sa], pa, p.err, 4);
+                    pre_a = 0;
                     tc_fence_after();
                     const uint64_t a_desc0 = make_desc(smem_u32(a_buf + sa * TC_A_STAGE_BYTES));
 #pragma unroll
                     for (int ky = 0; ky < KS; ++ky) {
-                        mbar_wait(&full_b[sb], pb, p.err, 5);
+                        if (!pre_b) mbar_wait(&full_b[sb], pb, p.err, 5);
+                        pre_b = 0;
                         tc_fence_after();
                         const uint64_t b_desc0 = make_desc(smem_u32(b_buf + sb * b_stage_bytes));
                         if (!(p.dbg & 1)) {
 #pragma unroll
                             for (int kx = 0; kx < KS; ++kx) {
+                                if (kx == KS - 1) {
+                                    // poll the next step's barriers now; the answers are read after this tap's MMAs are queued
+                                    const int nsb = sb + 1 == nb_stages ? 0 : sb + 1;
+                                    pre_b = mbar_test_wait(&full_b[nsb], nsb ? pb : pb ^ 1);
+                                    if (ky == KS - 1) {
+                                        const int nsa = sa + 1 == TC_NA ? 0 : sa + 1;
+                                        pre_a = mbar_test_wait(&full_a[nsa], nsa ? pa : pa ^ 1);
+                                        if (kc == kchunks - 1) pre_t = mbar_test_wait(&tm_empty[acc ^ 1], acc ? pacc : pacc ^ 1);
+                                    }
+                                }
                                 const uint64_t a_d = a_desc0 + (uint64_t)((kx * TC_A_COPY_BYTES + ky * (TC_TW * TC_ROW_BYTES)) >> 4);
                                 const uint64_t b_d = b_desc0 + (uint64_t)(kx * b_step);
 #pragma unroll

@@ -147,6 +147,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
             int sa = 0; uint32_t pa = 0;
             int acc = 0; uint32_t pacc = 0;
             int tn = 0;
+            uint32_t pre_t = 0, pre_a = 0;                  // early polls of the upcoming step's barriers (1 = already complete)
             for (int pass = 0; pass < p.npass; ++pass) {
                 if (pass > 0) mbar_wait(w_free, (uint32_t)((pass - 1) & 1), p.err, 12);
                 mbar_expect_tx(w_full, w_bytes);
@@ -156,12 +157,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
                 mbar_wait(w_full, (uint32_t)(pass & 1), p.err, 13);
                 tc_fence_after();
                 for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
-                    mbar_wait(&tm_empty[acc], pacc ^ 1, p.err, 14);
+                    if (!pre_t) mbar_wait(&tm_empty[acc], pacc ^ 1, p.err, 14);
+                    pre_t = 0;
                     tc_fence_after();
                     T2_STAMP(tn, 4);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.np);
                     for (int kc = 0; kc < p.kch; ++kc) {
-                        mbar_wait(&a_full[sa], pa, p.err, 15);
+                        if (!pre_a) mbar_wait(&a_full[sa], pa, p.err, 15);
+                        pre_a = 0;
                         tc_fence_after();
                         T2_STAMP(tn, kc == 0 ? 5 : 6);
                         const uint64_t a_desc0 = make_desc_a(smem_u32(a_buf + sa * T2_STAGE));
@@ -170,6 +173,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
                         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx) {
+                                if (ky == 2 && kx == 2) {
+                                    // poll the next step's barriers before the last tap is queued; read the answers after
+                                    // (a shared-memory round trip takes 250-400 clk under MMA load, see tc_common.cuh)
+                                    const int nsa = sa + 1 == p.nstage ? 0 : sa + 1;
+                                    pre_a = mbar_test_wait(&a_full[nsa], nsa ? pa : pa ^ 1);
+                                    if (kc == p.kch - 1) pre_t = mbar_test_wait(&tm_empty[acc ^ 1], acc ? pacc : pacc ^ 1);
+                                }
                                 const uint64_t a_d = a_desc0 + (uint64_t)(ky * T2_TWP + kx);          // 16 B per row
                                 const uint64_t b_d = b_desc0 + (uint64_t)((ky * 3 + kx) * wstep);
 #pragma unroll

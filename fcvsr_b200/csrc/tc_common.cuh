@@ -27,6 +27,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking poll.  Under MMA load every shared-memory round trip (mbarrier polls included) takes 250-400 clk
+// because the tensor core's operand fetches saturate the pipe, so the MMA issuer polls the NEXT step's barriers
+// before it issues the last MMAs of the current step and only reads the answer afterwards.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
     uint32_t spins = 0;

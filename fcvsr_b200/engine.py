@@ -113,9 +113,10 @@ class Engine:
         self.tc_launches = 0
         self.use_graph = False       # replay the launch sequence from a CUDA graph (one per input shape)
         self._graphs: Dict[tuple, tuple] = {}
-        # resident-weight 3x3 kernel (conv_tc2.cu): "auto" = where it measured at least as fast as conv_tc.cu
-        # (Cout = 64 passes: 64->64 and bf16 128->64, profiles/r1_notes.md); True = wherever eligible; False = never
-        self.use_tc2 = {"0": False, "1": True}.get(os.environ.get("FCVSR_TC2", ""), "auto")
+        # resident-weight 3x3 kernel (conv_tc2.cu): off by default -- after the epilogue / barrier-poll fixes conv_tc.cu
+        # is as fast or faster on every trunk shape (profiles/r1_notes.md).  FCVSR_TC2=1: wherever eligible;
+        # FCVSR_TC2=auto: Cout = 64 passes only
+        self.use_tc2 = {"1": True, "auto": "auto"}.get(os.environ.get("FCVSR_TC2", ""), False)
         self._ksplit = {}
         self.max_ctas = 0            # grid cap of the tensor-core convs on the current stream (0 = all SMs)
         self.multi_stream = True     # run the three pyramid levels of SCNetbk on three streams
