@@ -69,6 +69,10 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const ConvTcParams& p) {
 template <int KS, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
+    // Programmatic dependent launch: let the next convolution's CTAs take each SM as soon as this grid's CTA leaves it
+    // and run their prologue (barriers, TMEM, bias, first weight stages) while the rest of this grid drains; everything
+    // that touches activations sits behind griddepcontrol.wait (a no-op for a normally serialized launch).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* a_buf = smem;                                        // TC_NA x 61440
@@ -118,6 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (warp == 0) {
         // ===== A producer: haloed input windows, 3 x-shifted copies per 32-channel chunk =====
         if (lane == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");      // x is the previous kernel's output
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
@@ -223,6 +228,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const float slope = p.act == FCVSR_ACT_PRELU ? p.slope_ptr[0] : p.slope;
         const int c4 = p.Cout >> 2;
         int acc = 0; uint32_t pacc = 0;
+        asm volatile("griddepcontrol.wait;" ::: "memory");          // res may be, and y may still be read by, earlier kernels
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(t, p);
             const int y = tc.ty * TC_TH + ly, x = tc.tx * TC_TW + lx;
@@ -467,12 +473,22 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     }
     int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;   // leave SMs to kernels running on other streams
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("FCVSR_PDL"); pdl = e ? atoi(e) : 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t le;
     if (op16) {
-        if (ksize == 3) conv_tc_kernel<3, true><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
-        else conv_tc_kernel<1, true><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, true>, map_x, map_w, p);
+        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, map_x, map_w, p);
     } else {
-        if (ksize == 3) conv_tc_kernel<3, false><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
-        else conv_tc_kernel<1, false><<<grid, TC_THREADS, smem, st>>>(map_x, map_w, p);
+        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, false>, map_x, map_w, p);
+        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, map_x, map_w, p);
     }
+    if (le != cudaSuccess) return FCVSR_ERR_CUDA;
     return fcvsr_launch_status();
 }

@@ -28,18 +28,24 @@
 #define T2_PLANE 2608                  // bytes per 16-byte-granule plane: 163 rows (bank rotation 12 words)
 #define T2_STAGE (8 * T2_PLANE)        // one 128-byte K chunk (32 fp32 / 64 bf16 channels) of a haloed tile
 #define T2_MAXSTAGE 8
-#define T2_EPI_WARPS 8
-#define T2_THREADS (32 * (5 + T2_EPI_WARPS))   // 4 producer warps, 1 MMA warp, T2_EPI_WARPS epilogue warps
+#define T2_PROD_WARPS 2
+#define T2_EPI_WARPS 16
+#define T2_MMA_WARP T2_PROD_WARPS
+#define T2_EPI0 (T2_PROD_WARPS + 1)     // first epilogue warp
+#define T2_THREADS (32 * (T2_PROD_WARPS + 1 + T2_EPI_WARPS))
 #define T2_SMEM_MAX (227 * 1024)
 
 #ifdef T2_TRACE      // bring-up only (tools/gpu_conv_trace.py builds its own copy of this file with -DT2_TRACE)
 __device__ long long t2_trace[64 * 16];
 #define T2_STAMP(n, slot) do { if (blockIdx.x == 0 && (n) < 64) t2_trace[(n) * 16 + (slot)] = clock64(); } while (0)
+#define T2_STAMP_NS(n) do { if (blockIdx.x == 0) { unsigned long long ns_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_)); \
+        t2_trace[(n) * 16 + 15] = (long long)ns_; t2_trace[(n) * 16 + 14] = clock64(); } } while (0)
 extern "C" int fcvsr_debug_conv_trace(long long* host, int n) {
     return cudaMemcpyFromSymbol(host, t2_trace, sizeof(long long) * (n < 1024 ? n : 1024)) == cudaSuccess ? 0 : 1;
 }
 #else
 #define T2_STAMP(n, slot) do {} while (0)
+#define T2_STAMP_NS(n) do {} while (0)
 #endif
 
 struct ConvTc2Params {
@@ -88,13 +94,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_cols = p.np == 64 ? 128u : 256u;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < T2_MAXSTAGE; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < T2_MAXSTAGE; ++i) { mbar_init(&a_full[i], 32 * T2_PROD_WARPS); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], T2_EPI_WARPS); }
         mbar_init(w_full, 1);
         mbar_init(w_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == T2_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -102,11 +108,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) T2_STAMP_NS(62);
 
-    if (warp < 4) {
-        // ===== A producers: 128 threads, thread i owns granule plane (i & 7) of window column (i >> 3) =====
+    if (warp < T2_PROD_WARPS) {
+        // ===== A producers: thread i owns granule plane (i & 7) of window columns (i >> 3) + 8h =====
         const int i = threadIdx.x;
-        const int col = i >> 3, plane = i & 7;
+        constexpr int CPT = 16 / (4 * T2_PROD_WARPS);           // window columns per thread
+        const int plane = i & 7;
         int stage = 0; uint32_t phase = 0;
         int tn = 0;
         const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x);
@@ -115,21 +123,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
             for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
                 const int tx = t % p.tiles_x, r_ = t / p.tiles_x;
                 const int ty = r_ % p.tiles_y, b = r_ / p.tiles_y;
-                const int xx = tx * T2_TWV - 1 + col;
-                const bool xok = xx >= 0 && xx < p.W;
                 const int y0 = ty * T2_TH - 1;
                 const uint8_t* img = xb + (size_t)b * p.H * p.W * pix_bytes;
                 for (int kc = 0; kc < p.kch; ++kc) {
                     mbar_wait_warp(&a_empty[stage], phase ^ 1, p.err, 11);
                     if (i == 0 && kc == 0) T2_STAMP(tn, 0);
-                    const uint32_t dst0 = smem_u32(a_buf + stage * T2_STAGE) + plane * T2_PLANE + col * 16;
-                    const uint8_t* src0 = img + (size_t)xx * pix_bytes + kc * 128 + plane * 16;
 #pragma unroll
-                    for (int j = 0; j < T2_TH + 2; ++j) {
-                        const int yy = y0 + j;
-                        const bool ok = xok && yy >= 0 && yy < p.H;
-                        const void* src = ok ? (const void*)(src0 + (size_t)yy * p.W * pix_bytes) : p.x;
-                        cp_async16(dst0 + j * (T2_TWP * 16), src, ok ? 16u : 0u);
+                    for (int h = 0; h < CPT; ++h) {
+                        const int col = (i >> 3) + h * (4 * T2_PROD_WARPS);
+                        const int xx = tx * T2_TWV - 1 + col;
+                        const bool xok = xx >= 0 && xx < p.W;
+                        const uint32_t dst0 = smem_u32(a_buf + stage * T2_STAGE) + plane * T2_PLANE + col * 16;
+                        const uint8_t* src0 = img + (size_t)xx * pix_bytes + kc * 128 + plane * 16;
+#pragma unroll
+                        for (int j = 0; j < T2_TH + 2; ++j) {
+                            const int yy = y0 + j;
+                            const bool ok = xok && yy >= 0 && yy < p.H;
+                            const void* src = ok ? (const void*)(src0 + (size_t)yy * p.W * pix_bytes) : p.x;
+                            cp_async16(dst0 + j * (T2_TWP * 16), src, ok ? 16u : 0u);
+                        }
                     }
                     cp_async_arrive_noinc(&a_full[stage]);
                     if (i == 0 && kc == p.kch - 1) T2_STAMP(tn, 1);
@@ -137,7 +149,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
                 }
                 ++tn;
             }
-    } else if (warp == 4) {
+    } else if (warp == T2_MMA_WARP) {
         // ===== weight loader + MMA issuer (one lane) =====
         if (lane == 0) {
             constexpr uint32_t FMT = BF16 ? 1u : 2u;
@@ -203,7 +215,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
     } else {
         // ===== epilogue warps 5..: TMEM lane quarter = warp % 4; the warps of a quarter split the columns =====
         const int q = warp & 3;
-        const int eh = (warp - 5) >> 2;
+        const int eh = (warp - T2_EPI0) >> 2;
         const int nchunk = p.np >> 4, cper = nchunk / (T2_EPI_WARPS / 4);
         const int c_begin = eh * cper, c_end = c_begin + cper;
         const int m = q * 32 + lane;
@@ -222,36 +234,37 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
                 const size_t pix = ((size_t)b * p.H + y) * p.W + x;
                 mbar_wait_warp(&tm_full[acc], pacc, p.err, 16);
                 tc_fence_after();
-                if (warp == 5 && lane == 0) T2_STAMP(tn, 8);
+                if (warp == T2_EPI0 && lane == 0) T2_STAMP(tn, 8);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.np);
                 uint32_t ra[16], rb[16];
                 tmem_ld16(taddr + c_begin * 16, ra);
                 for (int c = c_begin; c < c_end; c += 2) {      // tcgen05.ld of chunk c+1 in flight while chunk c is stored
                     tmem_ld_wait();
-                    if (warp == 5 && lane == 0 && c == 0) T2_STAMP(tn, 10);
+                    if (warp == T2_EPI0 && lane == 0 && c == 0) T2_STAMP(tn, 10);
                     const bool has_b = c + 1 < c_end;
                     if (has_b) tmem_ld16(taddr + (c + 1) * 16, rb);
                     if (valid) epi_chunk16<BF16>(e, ra, pix, pass * p.np + c * 16, b, y, x);
-                    if (warp == 5 && lane == 0 && c == 0) T2_STAMP(tn, 11);
+                    if (warp == T2_EPI0 && lane == 0 && c == 0) T2_STAMP(tn, 11);
                     if (has_b) {
                         tmem_ld_wait();
-                        if (warp == 5 && lane == 0 && c == 0) T2_STAMP(tn, 12);
+                        if (warp == T2_EPI0 && lane == 0 && c == 0) T2_STAMP(tn, 12);
                         if (c + 2 < c_end) tmem_ld16(taddr + (c + 2) * 16, ra);
                         if (valid) epi_chunk16<BF16>(e, rb, pix, pass * p.np + (c + 1) * 16, b, y, x);
-                        if (warp == 5 && lane == 0 && c == 0) T2_STAMP(tn, 13);
+                        if (warp == T2_EPI0 && lane == 0 && c == 0) T2_STAMP(tn, 13);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tm_empty[acc]);
-                if (warp == 5 && lane == 0) T2_STAMP(tn, 9);
+                if (warp == T2_EPI0 && lane == 0) T2_STAMP(tn, 9);
                 ++tn;
                 if (++acc == 2) { acc = 0; pacc ^= 1; }
             }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (threadIdx.x == 0) T2_STAMP_NS(63);
+    if (warp == T2_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }

@@ -42,16 +42,22 @@ for _ in range(3):
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(10):
+for _ in range(200):
     lib.fcvsr_conv3x3_tc_resident(*args)
 e1.record()
 torch.cuda.synchronize()
-print(os.environ.get("T2_DEFS", ""), f"{mode} {ci}->{co} B{B}: {e0.elapsed_time(e1) * 100:.1f} us per launch (traced build)")
+print(os.environ.get("T2_DEFS", ""), f"{mode} {ci}->{co} B{B}: {e0.elapsed_time(e1) * 5:.1f} us per launch (traced build)")
 n = 64 * 16
 buf = (ctypes.c_longlong * n)()
 lib.fcvsr_debug_conv_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert lib.fcvsr_debug_conv_trace(buf, n) == 0
 v = list(buf)
+clk = v[63 * 16 + 14] - v[62 * 16 + 14]
+ns = v[63 * 16 + 15] - v[62 * 16 + 15]
+print(f"CTA 0 body: {clk} clk in {ns} ns -> SM clock {clk / max(ns, 1) * 1e3:.0f} MHz")
+for t_ in (62, 63):
+    for s_ in range(16):
+        v[t_ * 16 + s_] = 0
 t0 = min(t for t in v if t > 0)
 names = {0: "pr_aE", 1: "pr_iss", 4: "mma_tmE", 5: "aF_first", 6: "aF_last", 7: "mma_iss", 8: "epi_tmF", 10: "ld0", 11: "st0", 12: "ld1", 13: "st1", 9: "epi_done"}
 print("clk since first stamp, CTA 0, per tile: ", " ".join(f"{names[k]:>9s}" for k in sorted(names)))
