@@ -42,8 +42,8 @@ def parse():
     ap.add_argument("--variant", default="full", choices=["full", "S"])
     ap.add_argument("--height", type=int, default=180)
     ap.add_argument("--width", type=int, default=320)
-    ap.add_argument("--dtype", default="tf32", choices=["tf32", "bf16"],
-                    help="tensor-core operand type: tf32 (fp32 storage; the contract's fp32 mode) or bf16")
+    ap.add_argument("--dtype", default="bf16", choices=["tf32", "bf16"],
+                    help="tensor-core operand type: bf16 (default; fp32 accumulate and residual streams) or tf32 (fp32 storage; the contract's fp32 mode)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -112,8 +112,9 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    workload = (f"{'FCVSR' if args.variant == 'full' else 'FCVSR-S'} forward, synthetic 7-frame "
-                f"{args.height}x{args.width} clips x4, {'fp32 storage, TF32 operands' if args.dtype == 'tf32' else 'bf16 operand tensors, fp32 accumulate'}")
+    base_workload = (f"{'FCVSR' if args.variant == 'full' else 'FCVSR-S'} forward, synthetic 7-frame "
+                     f"{args.height}x{args.width} clips x4")
+    workload = base_workload + (", fp32 storage, TF32 operands" if args.dtype == "tf32" else ", bf16 operand tensors, fp32 accumulate")
 
     if args.impl == "reference":
         if rank != 0:
@@ -123,7 +124,8 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload + " (CPU, oracle port of the reference forward)", "batch_per_step": 1},
+                "config": {"workload": base_workload + ", fp32 on the host CPU cores (oracle port of the reference forward)",
+                           "batch_per_step": 1},
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": f"{args.steps} forwards of one 7x{args.height}x{args.width} clip"},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -43,6 +43,19 @@
 #define TC_THREADS (32 * (3 + TC_EPI_WARPS))
 #define TC_MAX_COUT 2048               // bias staging in shared memory
 
+#ifdef TC_TRACE      // bring-up only (tools/gpu_conv_trace.py builds its own copy of this file with -DTC_TRACE)
+__device__ long long tc_trace[64 * 16];
+#define TC_STAMP(n, slot) do { if (blockIdx.x == 0 && (n) < 62) tc_trace[(n) * 16 + (slot)] = clock64(); } while (0)
+#define TC_STAMP_NS(n) do { if (blockIdx.x == 0) { unsigned long long ns_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_)); \
+        tc_trace[(n) * 16 + 15] = (long long)ns_; tc_trace[(n) * 16 + 14] = clock64(); } } while (0)
+extern "C" int fcvsr_debug_conv_trace(long long* host, int n) {
+    return cudaMemcpyFromSymbol(host, tc_trace, sizeof(long long) * (n < 1024 ? n : 1024)) == cudaSuccess ? 0 : 1;
+}
+#else
+#define TC_STAMP(n, slot) do {} while (0)
+#define TC_STAMP_NS(n) do {} while (0)
+#endif
+
 struct ConvTcParams {
     const float* bias; const float* res; int ldres; const float* res2; int ldres2;
     float* y; int ldy;
@@ -101,6 +114,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t b_bytes = (uint32_t)p.n_tile * TC_ROW_BYTES;      // multiple of 2048 (n_tile % 16 == 0): stays 1024-aligned
     const uint32_t b_stage_bytes = b_bytes * KS;                    // one filter row of taps per stage
     const int nb_stages = min(TC_NB_MAX, (int)(TC_B_RING_BYTES / b_stage_bytes));
+    // Weights resident: with a single N pass and every (K chunk, filter row) stage fitting in the ring at once, the
+    // stages are loaded once per CTA and never released (bf16 64->64 3x3: 72 KB).  ncu showed the L2->SM read path
+    // at 97 % of peak with the weights re-streamed per tile; this halves that traffic for the most common shape.
+    const bool b_resident = p.n_tiles == 1 && kchunks * KS <= nb_stages;
     const uint32_t tmem_cols = p.n_tile <= 16 ? 32 : (p.n_tile <= 32 ? 64 : (p.n_tile <= 64 ? 128 : 256));
 
     if (threadIdx.x == 0) {
@@ -118,22 +135,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_STAMP_NS(62);
 
     if (warp == 0) {
         // ===== A producer: haloed input windows, 3 x-shifted copies per 32-channel chunk =====
         if (lane == 0) {
             asm volatile("griddepcontrol.wait;" ::: "memory");      // x is the previous kernel's output
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            int tn = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tn) {
                 const TileCoord tc = decode_tile(t, p);
                 const int y0 = tc.ty * TC_TH - (KS == 3 ? 1 : 0), x0 = tc.tx * TC_TW - (KS == 3 ? 1 : 0);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&empty_a[stage], phase ^ 1, p.err, 1);
+                    if (kc == 0) TC_STAMP(tn, 0);
                     if (p.dbg & 2) { mbar_arrive(&full_a[stage]); if (++stage == TC_NA) { stage = 0; phase ^= 1; } continue; }
                     mbar_expect_tx(&full_a[stage], a_copy_bytes * ncopies);
                     uint8_t* dst = a_buf + stage * TC_A_STAGE_BYTES;
                     for (int cpy = 0; cpy < ncopies; ++cpy)
                         tma_load_4d(dst + cpy * TC_A_COPY_BYTES, &map_x, &full_a[stage], kc * KCH, x0 + cpy, y0, tc.b);
+                    if (kc == kchunks - 1) TC_STAMP(tn, 1);
                     if (++stage == TC_NA) { stage = 0; phase ^= 1; }
                 }
             }
@@ -144,9 +165,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
+                if (b_resident && t != (int)blockIdx.x) break;          // loaded with the first tile, kept for all
                 for (int kc = 0; kc < kchunks; ++kc)
                     for (int ky = 0; ky < KS; ++ky) {
-                        mbar_wait(&empty_b[stage], phase ^ 1, p.err, 2);
+                        if (!b_resident) mbar_wait(&empty_b[stage], phase ^ 1, p.err, 2);
                         if (p.dbg & 4) { mbar_arrive(&full_b[stage]); if (++stage == nb_stages) { stage = 0; phase ^= 1; } continue; }
                         mbar_expect_tx(&full_b[stage], b_bytes * KS);
 #pragma unroll
@@ -161,57 +183,67 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // ===== MMA issuer (one elected lane) =====
         // Descriptors are formed once per stage and advanced by constant adds: the uniform-datapath chain
         // of a full make_desc() per instruction costs ~130 clk/MMA, 3x the tensor pipe's 48 clk (N=64).
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t FMT = BF16 ? 1u : 2u;            // F16F32Format: 1 = BF16, 2 = TF32
             const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t b_step = b_bytes >> 4;
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
             int acc = 0; uint32_t pacc = 0;
             uint32_t pre_t = 0, pre_a = 0, pre_b = 0;          // early polls of the upcoming step's barriers (1 = already complete)
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            int tn = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tn) {
                 if (!pre_t) mbar_wait(&tm_empty[acc], pacc ^ 1, p.err, 3);
                 pre_t = 0;
                 tc_fence_after();
+                TC_STAMP(tn, 4);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+                const bool b_ready = b_resident && t != (int)blockIdx.x;   // resident stages were waited for on the first tile
+                if (b_resident) { sb = 0; pb = 0; }
                 for (int kc = 0; kc < kchunks; ++kc) {
                     if (!pre_a) mbar_wait(&full_a[sa], pa, p.err, 4);
                     pre_a = 0;
                     tc_fence_after();
+                    TC_STAMP(tn, kc == 0 ? 5 : 6);
                     const uint64_t a_desc0 = make_desc(smem_u32(a_buf + sa * TC_A_STAGE_BYTES));
 #pragma unroll
                     for (int ky = 0; ky < KS; ++ky) {
-                        if (!pre_b) mbar_wait(&full_b[sb], pb, p.err, 5);
+                        if (!pre_b && !b_ready) mbar_wait(&full_b[sb], pb, p.err, 5);
                         pre_b = 0;
                         tc_fence_after();
                         const uint64_t b_desc0 = make_desc(smem_u32(b_buf + sb * b_stage_bytes));
                         if (!(p.dbg & 1)) {
 #pragma unroll
                             for (int kx = 0; kx < KS; ++kx) {
-                                if (kx == KS - 1) {
-                                    // poll the next step's barriers now; the answers are read after this tap's MMAs are queued
-                                    const int nsb = sb + 1 == nb_stages ? 0 : sb + 1;
-                                    pre_b = mbar_test_wait(&full_b[nsb], nsb ? pb : pb ^ 1);
-                                    if (ky == KS - 1) {
-                                        const int nsa = sa + 1 == TC_NA ? 0 : sa + 1;
-                                        pre_a = mbar_test_wait(&full_a[nsa], nsa ? pa : pa ^ 1);
-                                        if (kc == kchunks - 1) pre_t = mbar_test_wait(&tm_empty[acc ^ 1], acc ? pacc : pacc ^ 1);
-                                    }
-                                }
                                 const uint64_t a_d = a_desc0 + (uint64_t)((kx * TC_A_COPY_BYTES + ky * (TC_TW * TC_ROW_BYTES)) >> 4);
                                 const uint64_t b_d = b_desc0 + (uint64_t)(kx * b_step);
+                                if (kx == KS - 1) {
+                                    // last tap of the step: poll the NEXT step's barriers in the same asm block as its MMAs
+                                    const int nsb = sb + 1 == nb_stages ? 0 : sb + 1;
+                                    const int nsa = sa + 1 == TC_NA ? 0 : sa + 1;
+                                    const uint32_t ok = umma_x4_poll3<BF16>(d_tmem, a_d, 2, b_d, idesc, (kc | ky | kx) ? 1u : 0u,
+                                                                            &full_b[nsb], nsb ? pb : pb ^ 1, &full_a[nsa], nsa ? pa : pa ^ 1,
+                                                                            &tm_empty[acc ^ 1], acc ? pacc : pacc ^ 1);
+                                    pre_b = ok & 1;
+                                    if (ky == KS - 1) {
+                                        pre_a = ok & 2;
+                                        if (kc == kchunks - 1) pre_t = ok & 4;
+                                    }
+                                } else {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if (BF16) umma_f16(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc, (kc | ky | kx | k) ? 1u : 0u);
-                                    else umma_tf32(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc, (kc | ky | kx | k) ? 1u : 0u);
+                                    for (int k = 0; k < 4; ++k)
+                                        if (BF16) umma_f16(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc, (kc | ky | kx | k) ? 1u : 0u);
+                                        else umma_tf32(d_tmem, a_d + 2 * k, b_d + 2 * k, idesc, (kc | ky | kx | k) ? 1u : 0u);
+                                }
                             }
                         }
-                        umma_commit(&empty_b[sb]);
+                        if (!b_resident) umma_commit(&empty_b[sb]);
                         if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                     }
                     umma_commit(&empty_a[sa]);
                     if (++sa == TC_NA) { sa = 0; pa ^= 1; }
                 }
                 umma_commit(&tm_full[acc]);
+                TC_STAMP(tn, 7);
                 if (++acc == 2) { acc = 0; pacc ^= 1; }
             }
         }
@@ -229,13 +261,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int c4 = p.Cout >> 2;
         int acc = 0; uint32_t pacc = 0;
         asm volatile("griddepcontrol.wait;" ::: "memory");          // res may be, and y may still be read by, earlier kernels
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int tn = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tn) {
             const TileCoord tc = decode_tile(t, p);
             const int y = tc.ty * TC_TH + ly, x = tc.tx * TC_TW + lx;
             const bool valid = y < p.H && x < p.W;
             const size_t pix = ((size_t)tc.b * p.H + y) * p.W + x;
             mbar_wait_warp(&tm_full[acc], pacc, p.err, 6);
             tc_fence_after();
+            if (warp == 3 && lane == 0) TC_STAMP(tn, 8);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile);
             // Software-pipelined TMEM reads: the tcgen05.ld of chunk c+1 is in flight while chunk c is
             // post-processed and stored (tcgen05.wait::ld sits right before the data is needed).
@@ -348,11 +382,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tm_empty[acc]);
+            if (warp == 3 && lane == 0) TC_STAMP(tn, 9);
             if (++acc == 2) { acc = 0; pacc ^= 1; }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TC_STAMP_NS(63);
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");

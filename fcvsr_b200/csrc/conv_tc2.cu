@@ -151,7 +151,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
             }
     } else if (warp == T2_MMA_WARP) {
         // ===== weight loader + MMA issuer (one lane) =====
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t FMT = BF16 ? 1u : 2u;
             const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(p.np >> 3) << 17) | ((128u >> 4) << 24);
             const uint64_t w_desc0 = make_desc(smem_u32(w_buf));
@@ -185,20 +185,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const ConvTc2Params p
                         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx) {
-                                if (ky == 2 && kx == 2) {
-                                    // poll the next step's barriers before the last tap is queued; read the answers after
-                                    // (a shared-memory round trip takes 250-400 clk under MMA load, see tc_common.cuh)
-                                    const int nsa = sa + 1 == p.nstage ? 0 : sa + 1;
-                                    pre_a = mbar_test_wait(&a_full[nsa], nsa ? pa : pa ^ 1);
-                                    if (kc == p.kch - 1) pre_t = mbar_test_wait(&tm_empty[acc ^ 1], acc ? pacc : pacc ^ 1);
-                                }
                                 const uint64_t a_d = a_desc0 + (uint64_t)(ky * T2_TWP + kx);          // 16 B per row
                                 const uint64_t b_d = b_desc0 + (uint64_t)((ky * 3 + kx) * wstep);
+                                if (ky == 2 && kx == 2) {
+                                    // last tap: the NEXT step's barriers are polled in the same asm block as its MMAs
+                                    // (a shared-memory round trip takes 250-400 clk under MMA load, see tc_common.cuh)
+                                    const int nsa = sa + 1 == p.nstage ? 0 : sa + 1;
+                                    const uint32_t ok = umma_x4_poll3<BF16>(d_tmem, a_d, (uint64_t)(2 * (T2_PLANE >> 4)), b_d, idesc, 1u,
+                                                                            &a_full[nsa], nsa ? pa : pa ^ 1, &tm_empty[acc ^ 1],
+                                                                            acc ? pacc : pacc ^ 1, &a_full[nsa], nsa ? pa : pa ^ 1);
+                                    pre_a = ok & 1;
+                                    if (kc == p.kch - 1) pre_t = ok & 2;
+                                } else {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint64_t ad = a_d + (uint64_t)(k * 2 * (T2_PLANE >> 4)), bd = b_d + 2 * k;
-                                    if (BF16) umma_f16(d_tmem, ad, bd, idesc, (kc | ky | kx | k) ? 1u : 0u);
-                                    else umma_tf32(d_tmem, ad, bd, idesc, (kc | ky | kx | k) ? 1u : 0u);
+                                    for (int k = 0; k < 4; ++k) {
+                                        const uint64_t ad = a_d + (uint64_t)(k * 2 * (T2_PLANE >> 4)), bd = b_d + 2 * k;
+                                        if (BF16) umma_f16(d_tmem, ad, bd, idesc, (kc | ky | kx | k) ? 1u : 0u);
+                                        else umma_tf32(d_tmem, ad, bd, idesc, (kc | ky | kx | k) ? 1u : 0u);
+                                    }
                                 }
                             }
                         umma_commit(&a_empty[sa]);

@@ -7,6 +7,20 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp.  Unlike `lane == 0`, ptxas knows that code predicated on elect.sync runs in exactly one
+// lane, so vector-register operands of the tensor-core instructions (TMEM address, descriptors) move to the uniform
+// datapath with a plain R2UR instead of an ELECT / R2UR.BROADCAST / BRA waterfall around every UTCHMMA (measured: ~40 clk
+// per MMA, which made the issuing thread, not the tensor pipe, the bottleneck of the convolution).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -39,6 +53,53 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parit
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok;
+}
+// Four MMAs (the k-steps of one 128-byte K chunk: descriptors advance by 2 x 16 bytes, or by `a_kstep` for A) with three
+// barrier polls issued BEFORE them and read AFTER them, in one asm block: a separate poll statement ends in a selp
+// that stalls the in-order issuing thread for the whole shared-memory round trip (250-400 clk under MMA load) before
+// the next MMA can be queued.  Returns bit i = poll i complete.
+template <bool BF16>
+__device__ __forceinline__ uint32_t umma_x4_poll3(uint32_t d_tmem, uint64_t a0, uint64_t a_kstep, uint64_t b0, uint32_t idesc,
+                                                  uint32_t accum0, uint64_t* bar0, uint32_t par0, uint64_t* bar1, uint32_t par1,
+                                                  uint64_t* bar2, uint32_t par2) {
+    uint32_t ok;
+    const uint64_t a1 = a0 + a_kstep, a2 = a1 + a_kstep, a3 = a2 + a_kstep;
+    const uint64_t b1 = b0 + 2, b2 = b0 + 4, b3 = b0 + 6;
+    if (BF16)
+        asm volatile(
+            "{\n\t.reg .pred p, pt, q0, q1, q2;\n\t.reg .b32 t0, t1, t2;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 q0, [%12], %13;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 q1, [%14], %15;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 q2, [%16], %17;\n\t"
+            "setp.ne.b32 p, %11, 0;\n\tsetp.eq.b32 pt, %11, %11;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %6, %10, p;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %7, %10, pt;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%1], %4, %8, %10, pt;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%1], %5, %9, %10, pt;\n\t"
+            "selp.u32 t0, 1, 0, q0;\n\tselp.u32 t1, 2, 0, q1;\n\tselp.u32 t2, 4, 0, q2;\n\t"
+            "or.b32 t0, t0, t1;\n\tor.b32 %0, t0, t2;\n\t}"
+            : "=r"(ok)
+            : "r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accum0),
+              "r"(smem_u32(bar0)), "r"(par0), "r"(smem_u32(bar1)), "r"(par1), "r"(smem_u32(bar2)), "r"(par2)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p, pt, q0, q1, q2;\n\t.reg .b32 t0, t1, t2;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 q0, [%12], %13;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 q1, [%14], %15;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 q2, [%16], %17;\n\t"
+            "setp.ne.b32 p, %11, 0;\n\tsetp.eq.b32 pt, %11, %11;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %6, %10, p;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%1], %3, %7, %10, pt;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%1], %4, %8, %10, pt;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%1], %5, %9, %10, pt;\n\t"
+            "selp.u32 t0, 1, 0, q0;\n\tselp.u32 t1, 2, 0, q1;\n\tselp.u32 t2, 4, 0, q2;\n\t"
+            "or.b32 t0, t0, t1;\n\tor.b32 %0, t0, t2;\n\t}"
+            : "=r"(ok)
+            : "r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"(accum0),
+              "r"(smem_u32(bar0)), "r"(par0), "r"(smem_u32(bar1)), "r"(par1), "r"(smem_u32(bar2)), "r"(par2)
+            : "memory");
     return ok;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
