@@ -139,7 +139,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     if (warp == 0) {
         // ===== A producer: haloed input windows, 3 x-shifted copies per 32-channel chunk =====
-        if (lane == 0) {
+        if (elect_one()) {
             asm volatile("griddepcontrol.wait;" ::: "memory");      // x is the previous kernel's output
             int stage = 0; uint32_t phase = 0;
             int tn = 0;
@@ -161,7 +161,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== B producer: one stage = the KS taps of one filter row for one 32-channel chunk =====
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
