@@ -33,6 +33,7 @@
 #define TC_TW 16
 #define TC_KCH 32                      // channels per K chunk in TF32 mode (128 bytes of fp32); 64 in bf16 mode
 #define TC_NA 2                        // A ring stages
+#define TC_NACC 4                      // TMEM accumulator tiles (n_tile <= 128 columns each)
 #define TC_NB_MAX 16                   // B ring: as many stages as fit in TC_B_RING_BYTES, at most 16
 #define TC_B_RING_BYTES (96 * 1024)
 #define TC_ROW_BYTES 128
@@ -95,9 +96,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t* empty_a = bars + TC_NA;   // [TC_NA]
     uint64_t* full_b = bars + 2 * TC_NA;            // [TC_NB_MAX]
     uint64_t* empty_b = bars + 2 * TC_NA + TC_NB_MAX;   // [TC_NB_MAX]
-    uint64_t* tm_full = bars + 2 * TC_NA + 2 * TC_NB_MAX;   // [2]
-    uint64_t* tm_empty = tm_full + 2;                    // [2]
-    uint32_t* tmem_slot = (uint32_t*)(tm_empty + 2);
+    uint64_t* tm_full = bars + 2 * TC_NA + 2 * TC_NB_MAX;   // [TC_NACC]
+    uint64_t* tm_empty = tm_full + TC_NACC;               // [TC_NACC]
+    uint32_t* tmem_slot = (uint32_t*)(tm_empty + TC_NACC);
     // bias staged in shared memory: the epilogue reads it with broadcast ld.shared.v4 (4 per 16-column chunk).  Per-lane
     // global loads here cost more than the tile's MMAs: the tensor core's operand fetches saturate the L1/shared pipe
     // and every LDG queues behind them (measured: 64->128 bf16 conv 60 us without bias, 147 us with __ldg bias).
@@ -118,12 +119,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // stages are loaded once per CTA and never released (bf16 64->64 3x3: 72 KB).  ncu showed the L2->SM read path
     // at 97 % of peak with the weights re-streamed per tile; this halves that traffic for the most common shape.
     const bool b_resident = p.n_tiles == 1 && kchunks * KS <= nb_stages;
-    const uint32_t tmem_cols = p.n_tile <= 16 ? 32 : (p.n_tile <= 32 ? 64 : (p.n_tile <= 64 ? 128 : 256));
+    // TC_NACC accumulator tiles in TMEM (all 512 columns at n_tile = 128): with two, the MMAs of tile t wait for the
+    // epilogue of tile t-2, a chain of MMA drain + barrier wake-ups + store latency that idled the tensor pipe ~30 %
+    const int nacc = TC_NACC;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(nacc * p.n_tile)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
         for (int i = 0; i < TC_NB_MAX; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], TC_EPI_WARPS); }
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -222,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                                     const int nsa = sa + 1 == TC_NA ? 0 : sa + 1;
                                     const uint32_t ok = umma_x4_poll3<BF16>(d_tmem, a_d, 2, b_d, idesc, (kc | ky | kx) ? 1u : 0u,
                                                                             &full_b[nsb], nsb ? pb : pb ^ 1, &full_a[nsa], nsa ? pa : pa ^ 1,
-                                                                            &tm_empty[acc ^ 1], acc ? pacc : pacc ^ 1);
+                                                                            &tm_empty[acc + 1 == nacc ? 0 : acc + 1], acc + 1 == nacc ? pacc : pacc ^ 1);
                                     pre_b = ok & 1;
                                     if (ky == KS - 1) {
                                         pre_a = ok & 2;
@@ -244,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 }
                 umma_commit(&tm_full[acc]);
                 TC_STAMP(tn, 7);
-                if (++acc == 2) { acc = 0; pacc ^= 1; }
+                if (++acc == nacc) { acc = 0; pacc ^= 1; }
             }
         }
     } else {
@@ -383,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tm_empty[acc]);
             if (warp == 3 && lane == 0) TC_STAMP(tn, 9);
-            if (++acc == 2) { acc = 0; pacc ^= 1; }
+            if (++acc == nacc) { acc = 0; pacc ^= 1; }
         }
     }
     tc_fence_before();
