@@ -46,6 +46,12 @@ def _out_hw(h, w, kh, kw, stride, padding, dilation):
     return ho, wo
 
 
+# "tf32": shapes in the tensor-core kernel's class (groups == 1, Cin % 32 == 0, Cout % 16 == 0, Cout <= 256) run on
+# tcgen05 with TF32-rounded operands and fp32 accumulation (csrc/dcn_tc.cu, |error| <~ 1e-3 of the output scale, the same
+# contract as the model's "tf32" mode); everything else, and everything under "fp32", runs the exact CUDA-core kernel.
+PRECISION = "tf32"
+
+
 def _launch(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, off_bs=0, mask_bs=0, sigmoid=0):
     b, cin, h, w = x.shape
     cout, cin_g, kh, kw = weight.shape
@@ -54,11 +60,20 @@ def _launch(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg
     ho, wo = _out_hw(h, w, kh, kw, stride, padding, dilation)
     y = x.new_empty(b, cout, ho, wo)
     st = torch.cuda.current_stream().cuda_stream
+    args = (x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else 0, offset.data_ptr(),
+            mask.data_ptr() if mask is not None else 0, y.data_ptr(), b, cin, h, w, cout, kh, kw, stride[0], stride[1],
+            padding[0], padding[1], dilation[0], dilation[1], groups, dg, off_bs, mask_bs, sigmoid, st)
+    if PRECISION not in ("tf32", "fp32"):
+        raise ValueError(f"unknown DCN precision {PRECISION!r}")
     with torch.cuda.device(x.device):
-        C.call("fcvsr_modulated_deform_conv_forward", x.data_ptr(), weight.data_ptr(),
-               bias.data_ptr() if bias is not None else 0, offset.data_ptr(), mask.data_ptr() if mask is not None else 0,
-               y.data_ptr(), b, cin, h, w, cout, kh, kw, stride[0], stride[1], padding[0], padding[1], dilation[0],
-               dilation[1], groups, dg, off_bs, mask_bs, sigmoid, st)
+        if PRECISION == "tf32" and groups == 1 and cin % 32 == 0 and (cin // dg) % 4 == 0 and cout % 16 == 0 and 16 <= cout <= 256:
+            scratch = x.new_empty(x.numel())             # NHWC copy of the input made by the kernel
+            rc = C.try_call("fcvsr_modulated_deform_conv_forward_tc", *args[:-1], scratch.data_ptr(), st)
+            if rc == 0:
+                return y
+            if rc != C.ERR_UNSUPPORTED:
+                raise RuntimeError(f"fcvsr_modulated_deform_conv_forward_tc failed with status {rc}")
+        C.call("fcvsr_modulated_deform_conv_forward", *args)
     return y
 
 

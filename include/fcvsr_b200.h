@@ -170,6 +170,18 @@ int fcvsr_modulated_deform_conv_forward(const float* input, const float* weight,
                                         int deformable_groups, long long offset_batch_stride,
                                         long long mask_batch_stride, int mask_sigmoid, cudaStream_t stream);
 
+/* Same operator on the tensor cores (csrc/dcn_tc.cu): bilinear gather straight into the tcgen05 operand layout,
+ * TF32-rounded operands, fp32 accumulate in TMEM, NCHW fp32 in and out.  groups == 1, Cin % 32 == 0, Cout % 16 == 0,
+ * (Cin / deformable_groups) % 4 == 0, Cout <= 256; other shapes return FCVSR_ERR_UNSUPPORTED (use the exact-fp32 entry
+ * above).  scratch_nhwc: caller-provided B*Cin*H*W floats (the kernel gathers from an NHWC copy of the input it makes
+ * there).  Same reference call sites. */
+int fcvsr_modulated_deform_conv_forward_tc(const float* input, const float* weight, const float* bias,
+                                        const float* offset, const float* mask, float* output, int B, int Cin,
+                                        int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w,
+                                        int pad_h, int pad_w, int dil_h, int dil_w, int groups,
+                                        int deformable_groups, long long offset_batch_stride,
+                                        long long mask_batch_stride, int mask_sigmoid, float* scratch_nhwc, cudaStream_t stream);
+
 /* library / build info: returns a static string "fcvsr_b200 <version> sm_100a" */
 const char* fcvsr_version(void);
 

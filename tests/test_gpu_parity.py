@@ -260,8 +260,11 @@ def test_dcn_known_answer(dev):
                                  dict(B=1, cin=64, cout=64, H=20, W=24, k=3, g=1, dg=16, pad=1, stride=1, dil=1),
                                  dict(B=2, cin=8, cout=6, H=9, W=11, k=3, g=2, dg=4, pad=1, stride=2, dil=1),
                                  dict(B=1, cin=4, cout=4, H=12, W=10, k=5, g=1, dg=4, pad=4, stride=1, dil=2)])
-def test_modulated_dcn_matches_oracle(dev, cfg):
+def test_modulated_dcn_matches_oracle(dev, cfg, monkeypatch):
+    """Exact-fp32 kernel (dcn.cu) against the loop oracle."""
+    import fcvsr_b200.ops.dcn as dcn_mod
     from fcvsr_b200.ops.dcn import modulated_deform_conv
+    monkeypatch.setattr(dcn_mod, "PRECISION", "fp32")
     g = torch.Generator().manual_seed(cfg["H"] * cfg["W"])
     k, dg = cfg["k"], cfg["dg"]
     x = torch.randn(cfg["B"], cfg["cin"], cfg["H"], cfg["W"], generator=g)
@@ -278,10 +281,58 @@ def test_modulated_dcn_matches_oracle(dev, cfg):
     assert float((y.cpu() - ref).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("cfg", [dict(B=1, cin=64, cout=64, H=20, W=24, k=3, dg=16, pad=1, stride=1, dil=1, mask=True),
+                                 dict(B=2, cin=32, cout=48, H=17, W=23, k=3, dg=1, pad=2, stride=2, dil=2, mask=True),
+                                 dict(B=2, cin=64, cout=128, H=13, W=9, k=1, dg=8, pad=0, stride=1, dil=1, mask=True),
+                                 dict(B=1, cin=96, cout=16, H=30, W=31, k=3, dg=3, pad=1, stride=1, dil=1, mask=False),
+                                 dict(B=1, cin=32, cout=256, H=12, W=20, k=5, dg=2, pad=2, stride=1, dil=1, mask=True)])
+def test_modulated_dcn_tensor_core_path(dev, cfg):
+    """dcn_tc.cu (tcgen05, TF32-rounded operands, fp32 accumulate) against the loop oracle: the tolerance is the
+    model's "tf32" contract, 1e-3 of the output scale; ragged last tiles, stride / dilation, v1 (no mask), all
+    deformable-group widths (several groups per 16-channel run, one group for all channels)."""
+    import fcvsr_b200.ops.dcn as dcn_mod
+    from fcvsr_b200.ops.dcn import deform_conv, modulated_deform_conv
+    assert dcn_mod.PRECISION == "tf32"
+    g = torch.Generator().manual_seed(cfg["H"] * cfg["W"] + cfg["cin"])
+    k, dg = cfg["k"], cfg["dg"]
+    x = torch.randn(cfg["B"], cfg["cin"], cfg["H"], cfg["W"], generator=g)
+    w = torch.randn(cfg["cout"], cfg["cin"], k, k, generator=g) / (cfg["cin"] * k * k) ** 0.5
+    b = torch.randn(cfg["cout"], generator=g)
+    ho = (cfg["H"] + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    wo = (cfg["W"] + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    off = 3.0 * torch.randn(cfg["B"], dg * 2 * k * k, ho, wo, generator=g)
+    if cfg["mask"]:
+        msk = torch.rand(cfg["B"], dg * k * k, ho, wo, generator=g)
+        ref = O.modulated_deform_conv(x, off, msk, w, b, cfg["stride"], cfg["pad"], cfg["dil"], 1, dg)
+        with torch.no_grad():
+            y = modulated_deform_conv(x.to(dev), off.to(dev), msk.to(dev), w.to(dev), b.to(dev), cfg["stride"], cfg["pad"],
+                                      cfg["dil"], 1, dg)
+    else:
+        ref = O.modulated_deform_conv(x, off, torch.ones(cfg["B"], dg * k * k, ho, wo), w, None, cfg["stride"], cfg["pad"],
+                                      cfg["dil"], 1, dg)
+        with torch.no_grad():
+            y = deform_conv(x.to(dev), off.to(dev), w.to(dev), cfg["stride"], cfg["pad"], cfg["dil"], 1, dg, 64)
+    err = float((y.cpu() - ref).abs().max())
+    assert err <= 1e-3 * max(1.0, float(ref.abs().max())), err
+    # and the two kernels agree with each other to the same bound
+    dcn_mod.PRECISION = "fp32"
+    try:
+        with torch.no_grad():
+            if cfg["mask"]:
+                y32 = modulated_deform_conv(x.to(dev), off.to(dev), msk.to(dev), w.to(dev), b.to(dev), cfg["stride"],
+                                            cfg["pad"], cfg["dil"], 1, dg)
+            else:
+                y32 = deform_conv(x.to(dev), off.to(dev), w.to(dev), cfg["stride"], cfg["pad"], cfg["dil"], 1, dg, 64)
+    finally:
+        dcn_mod.PRECISION = "tf32"
+    assert float((y32.cpu() - ref).abs().max()) <= 1e-4
+    assert not torch.equal(y32, y)            # the tensor-core kernel really ran
+
+
 def test_modulated_dcn_pack_module(dev):
     """ModulatedDeformConvPack (deform_conv.py:311-337): conv_offset_mask -> chunk/cat/sigmoid -> DCN."""
     from fcvsr_b200.ops.dcn import ModulatedDeformConvPack
-    torch.manual_seed(3)
+    torch.manual_seed(3)                       # 16 channels: outside the tensor-core kernel's class -> exact kernel
     m = ModulatedDeformConvPack(16, 16, 3, stride=1, padding=1, deformable_groups=4).to(dev)
     with torch.no_grad():
         m.conv_offset_mask.weight.normal_(0, 0.05)
