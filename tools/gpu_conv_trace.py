@@ -27,20 +27,22 @@ lib = ctypes.CDLL(so)
 op16 = mode == "bf16"
 dev = torch.device("cuda:0")
 st = torch.cuda.current_stream().cuda_stream
-H, W = 180, 320
+H, W = [int(v) for v in os.environ.get("HW", "180x320").split("x")]
 x = torch.randn(B, H, W, ci, device=dev)
 w = torch.randn(co, ci, 3, 3, device=dev) / (9 * ci) ** 0.5
 bias = torch.randn(co, device=dev)
 pk = _ConvPack(w, None, op16=op16)
 if op16:
     x = x.to(torch.bfloat16)
-y = torch.empty(B, H, W, co, device=dev, dtype=torch.bfloat16 if op16 else torch.float32)
+f32out = bool(os.environ.get("F32OUT"))
+y = torch.empty(B, H, W, co, device=dev, dtype=torch.bfloat16 if (op16 and not f32out) else torch.float32)
+y2 = torch.empty(B, H, W, co, device=dev, dtype=torch.bfloat16 if op16 else torch.float32) if f32out else None
 V, I, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 if ver == "v1":
     fn = lib.fcvsr_conv2d_tc
     fn.argtypes = [V, I, V, V, V, I, V, I, V, I, I, I, I, I, I, I, I, F, V, I, V, I, I, I, I, V]
     args = (x.data_ptr(), ci, pk.w_tc.data_ptr(), bias.data_ptr(), None, 0, None, 0, y.data_ptr(), co, B, H, W, ci, co, 3, 2, 0.1,
-            None, 0, None, 0, 1 if op16 else 0, 0, int(op16), st)
+            None, 0, y2.data_ptr() if f32out else None, co if f32out else 0, 0 if f32out else (1 if op16 else 0), 0, int(op16), st)
 else:
     fn = lib.fcvsr_conv3x3_tc_resident
     fn.argtypes = [V, I, V, I, V, V, I, V, I, V, I, I, I, I, I, I, I, F, V, I, V, I, I, I, I, V]
