@@ -32,7 +32,9 @@
 #define TC_TH 8
 #define TC_TW 16
 #define TC_KCH 32                      // channels per K chunk in TF32 mode (128 bytes of fp32); 64 in bf16 mode
-#define TC_NA 2                        // A ring stages
+#define TC_NA 2                        // A ring stages of a 3x3 conv (61 KB each); a 1x1 conv's stage is 16 KB: TC_NA1 stages
+#define TC_NA1 7                       // ... in the same TC_NA * TC_A_STAGE_BYTES: its tiles are 4-16 MMAs, so load latency is the limit
+#define TC_NA_MAX 8
 #define TC_NACC 4                      // TMEM accumulator tiles (n_tile <= 128 columns each)
 #define TC_NB_MAX 16                   // B ring: as many stages as fit in TC_B_RING_BYTES, at most 16
 #define TC_B_RING_BYTES (96 * 1024)
@@ -92,11 +94,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint8_t* a_buf = smem;                                        // TC_NA x 61440
     uint8_t* b_buf = smem + TC_NA * TC_A_STAGE_BYTES;             // weight ring, TC_B_RING_BYTES
     uint64_t* bars = (uint64_t*)(b_buf + TC_B_RING_BYTES);
-    uint64_t* full_a = bars;            // [TC_NA]
-    uint64_t* empty_a = bars + TC_NA;   // [TC_NA]
-    uint64_t* full_b = bars + 2 * TC_NA;            // [TC_NB_MAX]
-    uint64_t* empty_b = bars + 2 * TC_NA + TC_NB_MAX;   // [TC_NB_MAX]
-    uint64_t* tm_full = bars + 2 * TC_NA + 2 * TC_NB_MAX;   // [TC_NACC]
+    uint64_t* full_a = bars;                // [TC_NA_MAX]
+    uint64_t* empty_a = bars + TC_NA_MAX;   // [TC_NA_MAX]
+    uint64_t* full_b = bars + 2 * TC_NA_MAX;            // [TC_NB_MAX]
+    uint64_t* empty_b = bars + 2 * TC_NA_MAX + TC_NB_MAX;   // [TC_NB_MAX]
+    uint64_t* tm_full = bars + 2 * TC_NA_MAX + 2 * TC_NB_MAX;   // [TC_NACC]
+    constexpr int NA = KS == 3 ? TC_NA : TC_NA1;                          // A ring depth
+    constexpr uint32_t A_STAGE = KS == 3 ? TC_A_STAGE_BYTES : TC_TH * TC_TW * TC_ROW_BYTES;
     uint64_t* tm_empty = tm_full + TC_NACC;               // [TC_NACC]
     uint32_t* tmem_slot = (uint32_t*)(tm_empty + TC_NACC);
     // bias staged in shared memory: the epilogue reads it with broadcast ld.shared.v4 (4 per 16-column chunk).  Per-lane
@@ -126,9 +130,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     while (tmem_cols < (uint32_t)(nacc * p.n_tile)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_NA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+        for (int i = 0; i < TC_NA_MAX; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
         for (int i = 0; i < TC_NB_MAX; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], TC_EPI_WARPS); }
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], KS == 1 ? 4 : TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -154,13 +158,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&empty_a[stage], phase ^ 1, p.err, 1);
                     if (kc == 0) TC_STAMP(tn, 0);
-                    if (p.dbg & 2) { mbar_arrive(&full_a[stage]); if (++stage == TC_NA) { stage = 0; phase ^= 1; } continue; }
+                    if (p.dbg & 2) { mbar_arrive(&full_a[stage]); if (++stage == NA) { stage = 0; phase ^= 1; } continue; }
                     mbar_expect_tx(&full_a[stage], a_copy_bytes * ncopies);
-                    uint8_t* dst = a_buf + stage * TC_A_STAGE_BYTES;
+                    uint8_t* dst = a_buf + stage * A_STAGE;
                     for (int cpy = 0; cpy < ncopies; ++cpy)
                         tma_load_4d(dst + cpy * TC_A_COPY_BYTES, &map_x, &full_a[stage], kc * KCH, x0 + cpy, y0, tc.b);
                     if (kc == kchunks - 1) TC_STAMP(tn, 1);
-                    if (++stage == TC_NA) { stage = 0; phase ^= 1; }
+                    if (++stage == NA) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -209,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     pre_a = 0;
                     tc_fence_after();
                     TC_STAMP(tn, kc == 0 ? 5 : 6);
-                    const uint64_t a_desc0 = make_desc(smem_u32(a_buf + sa * TC_A_STAGE_BYTES));
+                    const uint64_t a_desc0 = make_desc(smem_u32(a_buf + sa * A_STAGE));
 #pragma unroll
                     for (int ky = 0; ky < KS; ++ky) {
                         if (!pre_b && !b_ready) mbar_wait(&full_b[sb], pb, p.err, 5);
@@ -224,7 +228,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                                 if (kx == KS - 1) {
                                     // last tap of the step: poll the NEXT step's barriers in the same asm block as its MMAs
                                     const int nsb = sb + 1 == nb_stages ? 0 : sb + 1;
-                                    const int nsa = sa + 1 == TC_NA ? 0 : sa + 1;
+                                    const int nsa = sa + 1 == NA ? 0 : sa + 1;
                                     const uint32_t ok = umma_x4_poll3<BF16>(d_tmem, a_d, 2, b_d, idesc, (kc | ky | kx) ? 1u : 0u,
                                                                             &full_b[nsb], nsb ? pb : pb ^ 1, &full_a[nsa], nsa ? pa : pa ^ 1,
                                                                             &tm_empty[acc + 1 == nacc ? 0 : acc + 1], acc + 1 == nacc ? pacc : pacc ^ 1);
@@ -245,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         if (++sb == nb_stages) { sb = 0; pb ^= 1; }
                     }
                     umma_commit(&empty_a[sa]);
-                    if (++sa == TC_NA) { sa = 0; pa ^= 1; }
+                    if (++sa == NA) { sa = 0; pa ^= 1; }
                 }
                 umma_commit(&tm_full[acc]);
                 TC_STAMP(tn, 7);
@@ -256,18 +260,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // ===== epilogue warps 3..: TMEM lane quarter = warp % 4; the warps of a quarter split the tile's 16-column
         // chunks.  The epilogue is a latency chain (tcgen05.ld -> scattered 32-byte stores that queue behind the
         // tensor core's operand fetches), so more warps in flight shorten it almost linearly. =====
+        // 1x1 convolutions (4-16 MMAs per tile, epilogue-bound): the 16 warps form four SETS of four (one warp per lane
+        // quarter); set s owns accumulator tile s, i.e. every fourth tile, and drains all of its columns.  A warp's per-tile
+        // time is a latency chain (barrier wake-up -> tcgen05.ld -> bias -> scattered stores) that more columns barely
+        // lengthen, so four tiles in their epilogue at once raise the drain rate (64->64 1x1: 10.0 -> 8.3 us, 64->1152:
+        // 69.5 -> 59.5 us).  3x3 convolutions: all warps on the same tile, columns split (measured 2-7 % faster there).
+        constexpr int TC_EPI_MODE = KS == 1 ? 1 : 0;
         const int q = warp & 3;
-        const int eh = (warp - 3) >> 2;                // which share of the columns
+        const int eh = (warp - 3) >> 2;                // set (mode 1) / share of the columns (mode 0)
         const int nchunk = p.n_tile >> 4, cper = (nchunk + TC_EPI_WARPS / 4 - 1) / (TC_EPI_WARPS / 4);
-        const int c_begin = min(eh * cper, nchunk), c_end = min(c_begin + cper, nchunk);
+        const int c_begin = TC_EPI_MODE ? 0 : min(eh * cper, nchunk), c_end = TC_EPI_MODE ? nchunk : min(c_begin + cper, nchunk);
         const int m = q * 32 + lane;                   // pixel within the tile == TMEM lane
         const int ly = m / TC_TW, lx = m - ly * TC_TW;
         const float slope = p.act == FCVSR_ACT_PRELU ? p.slope_ptr[0] : p.slope;
         const int c4 = p.Cout >> 2;
-        int acc = 0; uint32_t pacc = 0;
+        int acc = TC_EPI_MODE ? eh : 0; uint32_t pacc = 0;
         asm volatile("griddepcontrol.wait;" ::: "memory");          // res may be, and y may still be read by, earlier kernels
-        int tn = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++tn) {
+        int tn = TC_EPI_MODE ? eh : 0;
+        constexpr int TSTEP = TC_EPI_MODE ? TC_NACC : 1;
+        for (int t = blockIdx.x + tn * gridDim.x; t < p.total_tiles; t += TSTEP * gridDim.x, tn += TSTEP) {
             const TileCoord tc = decode_tile(t, p);
             const int y = tc.ty * TC_TH + ly, x = tc.tx * TC_TW + lx;
             const bool valid = y < p.H && x < p.W;
@@ -388,7 +399,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tm_empty[acc]);
             if (warp == 3 && lane == 0) TC_STAMP(tn, 9);
-            if (++acc == nacc) { acc = 0; pacc ^= 1; }
+            if (TC_EPI_MODE) pacc ^= 1;                                // same accumulator, next phase
+            else if (++acc == nacc) { acc = 0; pacc ^= 1; }
         }
     }
     tc_fence_before();
