@@ -203,6 +203,32 @@ class GShiftNet_S(_FCVSRBase):
         super().__init__(n_features, wiF, AC_Ks, ACNum, Freq_Inv, SCGroupN)
 
 
+class GShiftNet_ETC(GShiftNet):
+    """GShiftNet_ETC (CVSR_freq.py:2760-2843): the FCVSR parameters applied to the 7 sliding windows of a 13-frame clip
+    in one call.  forward(x[B,13,1,H,W]) -> (out_seq[B,7,1,4H,4W], x_up[B,7,1,4H,4W]) where x_up is the bilinear x4
+    up-sampling of each window's centre frame (:2834-2842).  The windows are independent, so they run as one batch of
+    7B clips through the same engine."""
+
+    def forward(self, x: torch.Tensor):
+        if x.dim() != 5:
+            raise ValueError(f"expected [B,T,C,H,W], got {tuple(x.shape)}")
+        b, t, c, h, w = x.shape
+        if t < 13 or c != 1:
+            raise ValueError("GShiftNet_ETC expects [B, 13, 1, H, W] (seven 7-frame windows)")
+        if not x.is_cuda:
+            raise RuntimeError("fcvsr_b200 runs only on CUDA (sm_100a); there is no CPU fallback")
+        from . import _capi as C
+        x = x.contiguous()
+        clips = torch.stack([x[:, i:i + 7] for i in range(7)], dim=1).reshape(b * 7, 7, 1, h, w)
+        out = super().forward(clips).view(b, 7, 1, 4 * h, 4 * w)
+        centres = x[:, 3:10, 0].contiguous()                                  # centre frame of window i is frame i + 3
+        up = torch.empty(b * 7, 1, 4 * h, 4 * w, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            C.call("fcvsr_bilinear_up4", centres.data_ptr(), h * w, up.data_ptr(), b * 7, h, w,
+                   torch.cuda.current_stream().cuda_stream)
+        return out, up.view(b, 7, 1, 4 * h, 4 * w)
+
+
 def seeded_state_dict(variant: str = "S", seed: int = 0, **kw):
     """Deterministic random-init weights shared by the tests, the golden generator and bench.py
     (SURVEY 8d): construct on CPU under torch.manual_seed(seed); every parameter whose init is

@@ -347,6 +347,25 @@ def test_modulated_dcn_pack_module(dev):
     assert float((y - ref).abs().max()) <= 1e-4
 
 
+def test_gshiftnet_etc_matches_per_window_forward(dev):
+    """GShiftNet_ETC (CVSR_freq.py:2760-2843): 7 windows of a 13-frame clip == 7 GShiftNet forwards, x_up == bilinear x4."""
+    sd = arch.seeded_state_dict("full", 2, ACNum=2, Freq_Inv=2, SCGroupN=1)
+    m = arch.GShiftNet_ETC(ACNum=2, Freq_Inv=2, SCGroupN=1).to(dev).eval()
+    m.load_state_dict(sd)
+    ref_m = arch.GShiftNet(ACNum=2, Freq_Inv=2, SCGroupN=1).to(dev).eval()
+    ref_m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1, 13, 1, 16, 20, generator=g).to(dev)
+    with torch.no_grad():
+        out, up = m(x)
+        assert out.shape == (1, 7, 1, 64, 80) and up.shape == (1, 7, 1, 64, 80)
+        for i in (0, 3, 6):
+            yi = ref_m(x[:, i:i + 7])
+            assert float((out[:, i] - yi).abs().max()) <= 1e-5
+            base = F.interpolate(x[:, i + 3].cpu(), scale_factor=4, mode="bilinear")
+            assert float((up[:, i].cpu() - base).abs().max()) <= 1e-6
+
+
 def test_sequence_inference_matches_oracle(dev):
     """Sliding-window driver (replicate edges, 30 -> 32 row padding and crop) against per-window oracle calls."""
     from fcvsr_b200 import sequence as S
