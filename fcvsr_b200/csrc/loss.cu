@@ -1,0 +1,90 @@
+// Charbonnier loss forward (CVSR_train/opt/loss.py:20-31): sum over all elements of sqrt((x - y)^2 + eps), eps = 1e-4,
+// with the optional mean_res variant (the per-sample mean of the difference first, :27-29).
+// Two deterministic stages: a fixed grid of blocks accumulates grid-strided partial sums in double precision (the
+// reference's fp32 torch.sum uses pairwise summation; a double accumulator is at least as accurate and order-independent
+// results would need atomics), the last stage sums the block partials in index order.  HBM-bound: 8 bytes per element.
+#include "common.cuh"
+
+#define CH_BLOCKS 592          // 4 x 148 SMs
+#define CH_THREADS 256
+
+__global__ void __launch_bounds__(CH_THREADS) charbonnier_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                       size_t n, float eps, double* __restrict__ partial) {
+    __shared__ double red[CH_THREADS / 32];
+    double acc = 0.0;
+    const size_t n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    for (size_t i = (size_t)blockIdx.x * CH_THREADS + threadIdx.x; i < n4; i += (size_t)CH_BLOCKS * CH_THREADS) {
+        const float4 a = x4[i], b = y4[i];
+        const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+        acc += (double)(sqrtf(d0 * d0 + eps) + sqrtf(d1 * d1 + eps)) + (double)(sqrtf(d2 * d2 + eps) + sqrtf(d3 * d3 + eps));
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = (n4 << 2) + threadIdx.x; i < n; i += CH_THREADS) {
+            const float d = x[i] - y[i];
+            acc += (double)sqrtf(d * d + eps);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < CH_THREADS / 32; ++w) s += red[w];
+        partial[blockIdx.x] = s;
+    }
+}
+
+__global__ void charbonnier_final_kernel(const double* __restrict__ partial, float* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < CH_BLOCKS; ++i) s += partial[i];
+        out[0] = (float)s;
+    }
+}
+
+// mean_res: one block per sample reduces mean(x - y), then the loss is sum_b sqrt(mean_b^2 + eps)
+__global__ void __launch_bounds__(CH_THREADS) charbonnier_meanres_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                       size_t per_sample, double* __restrict__ partial) {
+    __shared__ double red[CH_THREADS / 32];
+    const float* xb = x + (size_t)blockIdx.x * per_sample;
+    const float* yb = y + (size_t)blockIdx.x * per_sample;
+    double acc = 0.0;
+    for (size_t i = threadIdx.x; i < per_sample; i += CH_THREADS) acc += (double)(xb[i] - yb[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < CH_THREADS / 32; ++w) s += red[w];
+        partial[blockIdx.x] = s / (double)per_sample;
+    }
+}
+
+__global__ void charbonnier_meanres_final_kernel(const double* __restrict__ partial, int B, float eps, float* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < B; ++i) {
+            const float m = (float)partial[i];
+            s += (double)sqrtf(m * m + eps);
+        }
+        out[0] = (float)s;
+    }
+}
+
+// scratch: at least max(CH_BLOCKS, B) doubles.  out: one float on the device.
+extern "C" int fcvsr_charbonnier_loss(const float* x, const float* y, long long numel, int batch, int mean_res, float eps,
+                                      double* scratch, float* out, cudaStream_t st) {
+    if (!x || !y || !scratch || !out || numel <= 0 || batch <= 0 || numel % batch) return FCVSR_ERR_ARG;
+    if (((uintptr_t)x | (uintptr_t)y) & 15) return FCVSR_ERR_ARG;
+    if (mean_res) {
+        charbonnier_meanres_kernel<<<batch, CH_THREADS, 0, st>>>(x, y, (size_t)(numel / batch), scratch);
+        charbonnier_meanres_final_kernel<<<1, 32, 0, st>>>(scratch, batch, eps, out);
+    } else {
+        charbonnier_partial_kernel<<<CH_BLOCKS, CH_THREADS, 0, st>>>(x, y, (size_t)numel, eps, scratch);
+        charbonnier_final_kernel<<<1, 32, 0, st>>>(scratch, out);
+    }
+    return fcvsr_launch_status();
+}

@@ -153,6 +153,14 @@ int fcvsr_bilinear_up4(const float* in, long long bstride, float* out, int B, in
 int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int W, int op16, cudaStream_t stream);
 int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npix, cudaStream_t stream);
 
+/* ---- training loss forward (CVSR_train/opt/loss.py:20-31) ---------------------------------------- */
+
+/* CharbonnierLoss(x, y, mean_res): out[0] = sum sqrt((x - y)^2 + eps) over `numel` fp32 elements, or with mean_res the
+ * per-sample mean of x - y first (:27-29; `batch` samples of numel / batch elements).  Deterministic two-stage reduction
+ * with double-precision partials; scratch: max(592, batch) doubles; out: one float on the device. */
+int fcvsr_charbonnier_loss(const float* x, const float* y, long long numel, int batch, int mean_res, float eps,
+                           double* scratch, float* out, cudaStream_t stream);
+
 /* ---- deformable convolution operator (CVSR_train/ops/dcn) --------------------------------------- */
 
 /* Fused bilinear-gather + GEMM modulated deformable convolution forward, NCHW fp32 exactly as the

@@ -347,6 +347,23 @@ def test_modulated_dcn_pack_module(dev):
     assert float((y - ref).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("shape", [(8, 1, 256, 256), (3, 1, 37, 53), (2, 7, 1, 16, 20)])
+def test_charbonnier_loss_matches_oracle(dev, shape):
+    """CharbonnierLoss forward (opt/loss.py:20-31), sum reduction and the mean_res variant; relative 1e-6 (fp32 sum)."""
+    from fcvsr_b200.ops.loss import CharbonnierLoss
+    g = torch.Generator().manual_seed(sum(shape))
+    x, y = torch.rand(*shape, generator=g), torch.rand(*shape, generator=g)
+    with torch.no_grad():
+        got = CharbonnierLoss(x.to(dev), y.to(dev)).item()
+        got_m = CharbonnierLoss(x.to(dev), y.to(dev), mean_res=True).item()
+    ref = O.charbonnier_sum(x.double(), y.double()).item()
+    d = (x - y).double().view(shape[0], -1).mean(1)
+    ref_m = torch.sqrt(d * d + 1e-4).sum().item()
+    assert abs(got - ref) <= 1e-6 * ref and abs(got_m - ref_m) <= 1e-6 * ref_m
+    with pytest.raises(NotImplementedError):
+        CharbonnierLoss(x.to(dev).requires_grad_(), y.to(dev))
+
+
 def test_gshiftnet_etc_matches_per_window_forward(dev):
     """GShiftNet_ETC (CVSR_freq.py:2760-2843): 7 windows of a 13-frame clip == 7 GShiftNet forwards, x_up == bilinear x4."""
     sd = arch.seeded_state_dict("full", 2, ACNum=2, Freq_Inv=2, SCGroupN=1)
