@@ -336,6 +336,8 @@ class Engine:
             kind = "tc" if (self.use_tc and pk.tc_ok and not nchw) else "direct"
             if kind == "tc":
                 kind = f"tc {pk.cin_logical}->{pk.cout} k{pk.k} {H}x{W}"
+                if os.environ.get("FCVSR_PROFILE_FLAVOR"):
+                    kind += f" out={'op' if rnd is True or rnd == 1 else ('f16' if rnd == 2 else 'f32')}{'+y2' if y2 else ''}{'+res' if res else ''}"
             prof.append((kind, 2.0 * B * ho * wo * pk.cin_logical * pk.cout * pk.k * pk.k,
                          4.0 * B * (H * W * pk.cin_logical + ho * wo * pk.cout), e0, e1))
             return
@@ -486,7 +488,7 @@ class Engine:
                 self._streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
             side = self._streams[dev][0]
             side.wait_stream(main)
-            self.max_ctas = 74                      # two tensor-core conv grids share the 148 SMs
+            self.max_ctas = int(os.environ.get("FCVSR_MGAA_CTAS", "74"))      # two tensor-core conv grids share the 148 SMs
             self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)
             with torch.cuda.stream(side):
                 self.st = side.cuda_stream
@@ -629,6 +631,8 @@ class Engine:
                 self._streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
             streams = (main,) + self._streams[dev]
             caps = self._level_caps(B, dims)   # SMs given to each level's persistent conv grid (sum = 148)
+            if os.environ.get("FCVSR_CAPS"):
+                caps = tuple(int(v) for v in os.environ["FCVSR_CAPS"].split(","))
             for s_ in streams[1:]:
                 s_.wait_stream(main)
         else:
