@@ -66,17 +66,24 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], False
 
     def run(self):
+        # one long-running nvidia-smi sampling every 50 ms (a fresh process per sample takes ~150 ms and would see a 0.4 s
+        # timed region once or twice)
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([t.strip() for t in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                                     "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        try:
+            for line in proc.stdout:
+                if self.stop_flag:
+                    break
+                line = line.strip()
+                if line:
+                    self.samples.append([t.strip() for t in line.split(",")])
+        finally:
+            proc.kill()
 
     def summary(self):
         if not self.samples:
