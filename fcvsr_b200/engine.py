@@ -499,11 +499,20 @@ class Engine:
         else:
             self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)
             self._mgaa(ws, p, f + 256 * 4, 448, f + 256 * 4, 448, B, H, W)
+        stop = os.environ.get("FCVSR_STOP_AFTER", "")              # bring-up: cumulative phase timing (tools/gpu_phase_times.py)
+        if stop == "mgaa_pair":
+            return
         self._mgaa(ws, p, f + 128 * 4, 448, p["m2"], 64, B, H, W)
+        if stop == "mgaa":
+            return
         self._mffr(ws, p, B, H, W)                                   # m2 -> xs0 (+ operand copy xsr0)
+        if stop == "mffr":
+            return
         self._conv(P["rc1"], p["xs0"], 64, p["xs1"], 64, B, H, W, y2=p["xsr1"], ldy2=64)                  # :2735
         self._conv(P["rc2"], p["xs1"], 64, p["xs2"], 64, B, H // 2, W // 2, y2=p["xsr2"], ldy2=64)        # :2736
         self._scnet(ws, p, B, H, W)
+        if stop == "scnet":
+            return
         self._tail(x, out, ws, p, B, H, W)
 
     # MGAAbk.forward (:1442-1547) on the 192-channel slice at `src`; result (64 ch) to `dst`.

@@ -364,6 +364,25 @@ def test_charbonnier_loss_matches_oracle(dev, shape):
         CharbonnierLoss(x.to(dev).requires_grad_(), y.to(dev))
 
 
+@pytest.mark.parametrize("variant,b,h,w", [("full", 1, 180, 320), ("S", 2, 96, 128), ("S", 1, 272, 480)])
+def test_baseline_size_parity_against_oracle(dev, variant, b, h, w):
+    """BASELINE config 2 at its full size (FCVSR, 7x180x320 -> 720x1280) and two more shapes the goldens do not cover
+    (two-phase FFT radix pairs 15*12 / 20*16, 12*8 / 16*8, 17*16 / 24*20), all three compute modes against the CPU oracle
+    (itself pinned to the reference by tests/test_oracle.py): fp32 <= 2e-5, tf32 <= 1e-3, bf16 <= 5e-3."""
+    sd = arch.seeded_state_dict(variant, 0)
+    x = make_clip(4321 + h, b, h, w)
+    with torch.no_grad():
+        ref = O.forward(sd, x)
+    for mode, tol in (("fp32", 2e-5), ("tf32", 1e-3), ("bf16", 5e-3)):
+        m = (arch.GShiftNet_S if variant == "S" else arch.GShiftNet)().to(dev).eval()
+        m.load_state_dict(sd)
+        m.compute_dtype = mode
+        with torch.no_grad():
+            y = m(x.to(dev)).cpu()
+        assert float((y - ref).abs().max()) <= tol, mode
+        del m
+
+
 def test_gshiftnet_etc_matches_per_window_forward(dev):
     """GShiftNet_ETC (CVSR_freq.py:2760-2843): 7 windows of a 13-frame clip == 7 GShiftNet forwards, x_up == bilinear x4."""
     sd = arch.seeded_state_dict("full", 2, ACNum=2, Freq_Inv=2, SCGroupN=1)
