@@ -220,7 +220,12 @@ def main():
             hbm, tfl, src = peaks()
             ach = fl_tc / (t_tc * 1e-3) / 1e12 if t_tc > 0 else 0.0
             roof = {"kernel": f"conv_tc_kernel<3> (tcgen05 {args.dtype} implicit-GEMM 3x3 convolution, every launch of the step)", "bound": "tensor", "achieved": ach,
-                    "peak": tfl, "unit": "TFLOP/s", "frac": ach / tfl, "traffic": None, "peak_source": src,
+                    "peak": tfl, "unit": "TFLOP/s", "frac": ach / tfl,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one level-0 64->64 launch of this kernel (bf16, 4 windows)
+                    # in profiles/r1_conv_tc_full_summary.txt (launch 0): 29.6 MB read = the input tensor once, 9.1 MB written
+                    # (the rest of the 29.5 MB output still sits in the 126 MB L2): no re-reads beyond the algorithmic bytes
+                    "traffic": 38761728 if (args.dtype == "bf16" and B == 4 and (H, W) == (180, 320)) else None,
+                    "peak_source": src,
                     "launches": len(tc), "avg_launch_us": 1e3 * t_tc / max(len(tc), 1),
                     "share_of_step": t_tc / t0.elapsed_time(t1),
                     "note": ("TF32 operands run at half the bf16 tensor rate; " if args.dtype == "tf32" else "") +
