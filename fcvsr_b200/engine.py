@@ -682,7 +682,7 @@ class Engine:
                         self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
                                 P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w)
                         self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w,
-                                p[f"rrh{l}"] if R else 0, O16, p[f"rrp{l}"] if l < 2 else 0, h, w, int(not R))
+                                p[f"rrh{l}"] if (R and l > 0) else 0, O16, p[f"rrp{l}"] if l < 2 else 0, h, w, int(not R))
                         if l < 2:                       # down: 1x1 conv on the 2x2 mean == mean of the conv (:753-757)
                             self._conv(P[q + "down"], p[f"rrp{l}"], 64, p[f"td{l}"], 64, B, h // 2, w // 2)
                         if l > 0:                       # up: 1x1 conv, interpolated in level_mix (:759-763)
