@@ -23,7 +23,7 @@ SIGNATURES = {
     "fcvsr_conv2d_tc": "pi pp pi pi pi iiiiii if p i pii i i s",
     "fcvsr_conv3x3_tc_resident": "pi pi p pi pi pi iiiii if p i pii i i s",
     "fcvsr_fft_r2c_w": "pi p p iiii s",
-    "fcvsr_fft_c2c_h": "p p p p iiii i f ii s",
+    "fcvsr_fft_c2c_h": "p p p p iiii i f ii p s",
     "fcvsr_fft_c2r_w": "p pi p iiii f s",
     "fcvsr_corr_gather": "piii pi iiii i s",
     "fcvsr_offset_blocks": "ppppp pi pppp iiii s",

@@ -42,6 +42,11 @@ static bool make_plan(int n, FftPlan* p) {
     return rem == 1 && n >= 2;
 }
 
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
+    unsigned w;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+    return w;
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_r2c_w_kernel(const float* __r
 __global__ void __launch_bounds__(FFT_THREADS) fft_c2c_h_kernel(const float2* in, float2* out,
                                                                 const float2* __restrict__ tw,
                                                                 const float* __restrict__ mask, int H, int Wf, int C,
-                                                                int cb_log2, int inverse, float scale, int round_out, FftPlan plan) {
+                                                                int cb_log2, int inverse, float scale, int round_out, FftPlan plan, unsigned* out_bf16) {
     extern __shared__ float2 sm[];
     const int cb = 1 << cb_log2, n = H;
     float2* a = sm;
@@ -217,6 +222,7 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_c2c_h_kernel(const float2* in
         v = make_float2(v.x * scale, v.y * scale);
         if (round_out) v = make_float2(round_tf32(v.x), round_tf32(v.y));
         out[base + (size_t)i * Wf * C + ch] = v;
+        if (out_bf16) out_bf16[base + (size_t)i * Wf * C + ch] = pack_bf16x2(v.x, v.y);
     }
 }
 
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_c2r_w_kernel(const float2* __
 template <bool INV>
 __global__ void __launch_bounds__(FFT2_THREADS_MAX) fft2_c2c_h_kernel(const float2* in, float2* out, const float2* __restrict__ tw,
                                                                      const float* __restrict__ mask, int H, int Wf, int C,
-                                                                     int cb_log2, float scale, int round_out, int r1, int r2) {
+                                                                     int cb_log2, float scale, int round_out, int r1, int r2, unsigned* out_bf16) {
     extern __shared__ float2 sm[];
     const int cb = 1 << cb_log2, n = H;
     float2* S = sm;
@@ -306,6 +312,7 @@ __global__ void __launch_bounds__(FFT2_THREADS_MAX) fft2_c2c_h_kernel(const floa
             v = make_float2(v.x * scale, v.y * scale);
             if (round_out) v = make_float2(round_tf32(v.x), round_tf32(v.y));
             out[base + (size_t)k * rs + ch] = v;
+            if (out_bf16) out_bf16[base + (size_t)k * rs + ch] = pack_bf16x2(v.x, v.y);   // operand copy (one complex = one word)
         };
         switch (r2) { FFT2_FOR_EACH_RADIX(FFT2_CASE_B) }
     }
@@ -461,9 +468,9 @@ extern "C" int fcvsr_fft_r2c_w(const float* x, int ldx, float* out, const float*
 }
 
 extern "C" int fcvsr_fft_c2c_h(const float* in, float* out, const float* tw, const float* mask, int B, int H, int Wf,
-                               int C, int inverse, float scale, int round_out, int nrep, cudaStream_t st) {
+                               int C, int inverse, float scale, int round_out, int nrep, void* out_bf16, cudaStream_t st) {
     FftPlan plan;
-    if (!in || !out || !tw || nrep < 1 || (nrep > 1 && in == out) || !make_plan(H, &plan)) return FCVSR_ERR_ARG;
+    if (!in || !out || !tw || nrep < 1 || (nrep > 1 && (in == out || out_bf16)) || !make_plan(H, &plan)) return FCVSR_ERR_ARG;
     int r1, r2;
     const bool two = make_plan2(H, &r1, &r2);
     const int cbl = pick_cb_log2(H, C, two);
@@ -475,15 +482,15 @@ extern "C" int fcvsr_fft_c2c_h(const float* in, float* out, const float* tw, con
         const int nt = fft2_threads(r1, r2, cbl);
         if (inverse)
             fft2_c2c_h_kernel<true><<<grid, nt, smem2, st>>>((const float2*)in, (float2*)out, (const float2*)tw, mask, H, Wf, C, cbl,
-                                                             scale, round_out, r1, r2);
+                                                             scale, round_out, r1, r2, (unsigned*)out_bf16);
         else
             fft2_c2c_h_kernel<false><<<grid, nt, smem2, st>>>((const float2*)in, (float2*)out, (const float2*)tw, mask, H, Wf, C, cbl,
-                                                              scale, round_out, r1, r2);
+                                                              scale, round_out, r1, r2, (unsigned*)out_bf16);
         return fcvsr_launch_status();
     }
     if (set_smem(fft_c2c_h_kernel, smem)) return FCVSR_ERR_CUDA;
     fft_c2c_h_kernel<<<grid, FFT_THREADS, smem, st>>>((const float2*)in, (float2*)out, (const float2*)tw, mask, H, Wf,
-                                                      C, cbl, inverse, scale, round_out, plan);
+                                                      C, cbl, inverse, scale, round_out, plan, (unsigned*)out_bf16);
     return fcvsr_launch_status();
 }
 

@@ -531,11 +531,8 @@ class Engine:
         # rfft2 of x1|x2|x3 (:1452-1454).  TF32 mode rounds the spectrum in place (it is operand and residual at
         # once); bf16 mode keeps it in fp32 and makes a bf16 operand copy.
         self._k("fcvsr_fft_r2c_w", src, lds, spec, p["tw_w"], B, H, W, 192)
-        self._k("fcvsr_fft_c2c_h", spec, spec, p["tw_h"], 0, B, H, Wf, 192, 0, 1.0, int(R and not O16), 1)
-        sop = spec
-        if O16:
-            sop = p["spec_op"]
-            self._k("fcvsr_round_copy", spec, 384, sop, 384, 384, 384, B * Pf, 1)
+        sop = p["spec_op"] if O16 else spec                      # bf16 operand copy written by the same pass
+        self._k("fcvsr_fft_c2c_h", spec, spec, p["tw_h"], 0, B, H, Wf, 192, 0, 1.0, int(R and not O16), 1, sop if O16 else 0)
         h1, h2, cc = p["h1"], p["h2"], p["cc"]
         half = B * Pf
         # convfuse (:1472-1473); the diff skip rides in the last layer's epilogue (res - res2)
@@ -561,7 +558,7 @@ class Engine:
         self.launches += 2
         self._k("fcvsr_offset_blocks", p["off"], P["ob_w1"].data_ptr(), P["ob_w2"].data_ptr(), P["ob_prelu"].data_ptr(),
                 P["ob_ca"].data_ptr(), p["sim"], 4, p["ob_t1"], p["ob_t2"], p["ob_partial"], z, B, H, Wf, A)
-        self._k("fcvsr_fft_c2c_h", z, z, p["tw_h"], 0, B, H, Wf, 4 * A, 1, 1.0, 0, 1)
+        self._k("fcvsr_fft_c2c_h", z, z, p["tw_h"], 0, B, H, Wf, 4 * A, 1, 1.0, 0, 1, 0)
         self._k("fcvsr_fft_c2r_w", z, p["offs"], 4 * A, p["tw_w"], B, H, W, 4 * A, 1.0 / (H * W))
         # kernel predictor (:1522-1523)
         x2, ldx2 = src + 64 * 4, lds
@@ -596,10 +593,10 @@ class Engine:
         nblk = (npix + 255) // 256
         x = p["m2"]
         self._k("fcvsr_fft_r2c_w", x, 64, p["specx"], p["tw_w"], B, H, W, 64)
-        self._k("fcvsr_fft_c2c_h", p["specx"], p["specx"], p["tw_h"], 0, B, H, Wf, 64, 0, 1.0, 0, 1)
+        self._k("fcvsr_fft_c2c_h", p["specx"], p["specx"], p["tw_h"], 0, B, H, Wf, 64, 0, 1.0, 0, 1, 0)
         bsz = B * npix * 64 * 4
         # Split_freq (:2075-2101): band_q = irfft2(spectrum * Msym_q), all Q bands in one launch per pass
-        self._k("fcvsr_fft_c2c_h", p["specx"], p["tmpc"], p["tw_h"], p["masks"], B, H, Wf, 64, 1, 1.0, 0, Q)
+        self._k("fcvsr_fft_c2c_h", p["specx"], p["tmpc"], p["tw_h"], p["masks"], B, H, Wf, 64, 1, 1.0, 0, Q, 0)
         self._k("fcvsr_fft_c2r_w", p["tmpc"], p["bands"], 64, p["tw_w"], Q * B, H, W, 64, 1.0 / npix)
         band = lambda i: p["bands"] + (Q - 1 - i) * bsz            # freq[::-1] (:2204-2205)
         gate = lambda i: p["gates"] + i * B * 128 * 4

@@ -79,9 +79,10 @@ int fcvsr_fft_r2c_w(const float* x, int ldx, float* out_c, const float* tw, int 
                     cudaStream_t stream);
 /* in/out complex [B,H,Wf,C] (C complex channels); optional real mask [H*Wf] multiplied at load;
  * in == out allowed.  inverse: 0 forward, 1 inverse (unnormalised); result * scale.  nrep > 1 transforms the
- * same input nrep times with mask + r*H*Wf into out + r*B*H*Wf*C (all band masks of Split_freq in one launch). */
+ * same input nrep times with mask + r*H*Wf into out + r*B*H*Wf*C (all band masks of Split_freq in one launch).
+ * out_bf16 (optional, nrep == 1): bf16 copy of the result, same layout (the operand tensor of the per-bin 1x1 convs). */
 int fcvsr_fft_c2c_h(const float* in_c, float* out_c, const float* tw, const float* mask, int B, int H, int Wf,
-                    int C, int inverse, float scale, int round_out, int nrep, cudaStream_t stream);
+                    int C, int inverse, float scale, int round_out, int nrep, void* out_bf16, cudaStream_t stream);
 /* complex [B,H,Wf,C] -> real [B,H,W,ldy] (C real channels), torch c2r semantics, result * scale. */
 int fcvsr_fft_c2r_w(const float* in_c, float* y, int ldy, const float* tw, int B, int H, int W, int C,
                     float scale, cudaStream_t stream);

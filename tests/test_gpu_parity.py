@@ -52,7 +52,7 @@ def test_fft_kernels_match_torch_fft(dev, H, W, Cc):
     spec = torch.empty(2, H, Wf, Cc, 2, device=dev)
     tw_w, tw_h = bands.twiddles(W, dev), bands.twiddles(H, dev)
     C.call("fcvsr_fft_r2c_w", xd.data_ptr(), Cc, spec.data_ptr(), tw_w.data_ptr(), 2, H, W, Cc, _st())
-    C.call("fcvsr_fft_c2c_h", spec.data_ptr(), spec.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 0, 1.0, 0, 1, _st())
+    C.call("fcvsr_fft_c2c_h", spec.data_ptr(), spec.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 0, 1.0, 0, 1, 0, _st())
     ref = torch.fft.rfft2(x)
     got = torch.view_as_complex(spec.cpu()).permute(0, 3, 1, 2)
     assert float((got - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
@@ -60,7 +60,7 @@ def test_fft_kernels_match_torch_fft(dev, H, W, Cc):
     z = torch.randn(2, Cc, H, Wf, dtype=torch.complex64, generator=g)
     zd = torch.view_as_real(z.permute(0, 2, 3, 1).contiguous()).contiguous().to(dev)
     y = torch.empty(2, H, W, Cc, device=dev)
-    C.call("fcvsr_fft_c2c_h", zd.data_ptr(), zd.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 1, 1.0, 0, 1, _st())
+    C.call("fcvsr_fft_c2c_h", zd.data_ptr(), zd.data_ptr(), tw_h.data_ptr(), 0, 2, H, Wf, Cc, 1, 1.0, 0, 1, 0, _st())
     C.call("fcvsr_fft_c2r_w", zd.data_ptr(), y.data_ptr(), Cc, tw_w.data_ptr(), 2, H, W, Cc, 1.0 / (H * W), _st())
     ref2 = torch.fft.irfft2(z, s=(H, W))
     assert float((nchw(y.cpu()) - ref2).abs().max()) <= 2e-6 * float(ref2.abs().max())

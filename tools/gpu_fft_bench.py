@@ -30,7 +30,7 @@ for (B, H, W, Cc) in ((1, 180, 320, 192), (4, 180, 320, 192), (4, 180, 320, 64),
     y = torch.empty(B, H, W, Cc, device=dev)
     tw_w, tw_h = bands.twiddles(W, dev), bands.twiddles(H, dev)
     t1 = timeit(lambda: C.call("fcvsr_fft_r2c_w", x.data_ptr(), Cc, spec.data_ptr(), tw_w.data_ptr(), B, H, W, Cc, st))
-    t2 = timeit(lambda: C.call("fcvsr_fft_c2c_h", spec.data_ptr(), spec.data_ptr(), tw_h.data_ptr(), 0, B, H, Wf, Cc, 0, 1.0, 0, 1, st))
+    t2 = timeit(lambda: C.call("fcvsr_fft_c2c_h", spec.data_ptr(), spec.data_ptr(), tw_h.data_ptr(), 0, B, H, Wf, Cc, 0, 1.0, 0, 1, 0, st))
     t3 = timeit(lambda: C.call("fcvsr_fft_c2r_w", spec.data_ptr(), y.data_ptr(), Cc, tw_w.data_ptr(), B, H, W, Cc, 1.0, st))
     b_real, b_spec = x.numel() * 4, spec.numel() * 4
     print(f"B{B} {H}x{W} C={Cc}: r2c_w {t1:7.1f} us {(b_real + b_spec) / t1 / 1e3:7.0f} GB/s | c2c_h {t2:7.1f} us {2 * b_spec / t2 / 1e3:7.0f} GB/s | "
