@@ -255,36 +255,6 @@ struct IacArgs {
 #define IAC_HALO ((IAC_TH + 2) * (IAC_TW + 2))
 #define IAC_NCOL 5                                   // columns of the 18-wide haloed row owned by a half-warp
 
-// bilinear gather of one (pixel, 4-channel) sample; corners outside the image contribute zero
-__device__ __forceinline__ float4 iac_gather(const float* __restrict__ prev, int ldp, size_t img, int H, int W, float sx,
-                                             float sy, int c0) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!(sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H)) return acc;   // also rejects NaN / inf offsets
-    const float fx0 = floorf(sx), fy0 = floorf(sy);
-    const float lx = sx - fx0, ly = sy - fy0;
-    const int x0 = (int)fx0, y0 = (int)fy0;
-    float4 v[4];
-    float wg[4];
-#pragma unroll
-    for (int cy = 0; cy < 2; ++cy)
-#pragma unroll
-        for (int cx = 0; cx < 2; ++cx) {
-            const int y = y0 + cy, x = x0 + cx;
-            const bool ok = y >= 0 && y < H && x >= 0 && x < W;
-            wg[cy * 2 + cx] = ok ? (cy ? ly : 1.f - ly) * (cx ? lx : 1.f - lx) : 0.f;
-            v[cy * 2 + cx] = ok ? __ldg(reinterpret_cast<const float4*>(prev + (img + (size_t)y * W + x) * ldp + c0))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        acc.x = fmaf(wg[i], v[i].x, acc.x);
-        acc.y = fmaf(wg[i], v[i].y, acc.y);
-        acc.z = fmaf(wg[i], v[i].z, acc.z);
-        acc.w = fmaf(wg[i], v[i].w, acc.w);
-    }
-    return acc;
-}
-
 // one tap (4 channels) as stored in registers: fp16 pairs in tensor-core modes, fp32 in the exact mode
 template <bool HALF> struct IacTap;
 template <> struct IacTap<true> {
@@ -311,7 +281,10 @@ __global__ void __launch_bounds__(IAC_THREADS, HALF ? 2 : 1) iac_step_kernel(Iac
     extern __shared__ float smem[];
     float* samp = smem;                                             // [(TH+2)*(TW+2)][64]
     float* vbuf = smem + IAC_HALO * IAC_C;                          // [TH*(TW+2)][64]
-    float2* offs_s = reinterpret_cast<float2*>(vbuf + IAC_TH * (IAC_TW + 2) * IAC_C);   // [(TH+2)*(TW+2)] sample coords
+    // per halo pixel: the four bilinear corners as pixel indices (clamped into the image) and their weights (zero for corners
+    // or samples outside it): computed once per pixel in phase 0 instead of by each of the 16 channel lanes in phase 1
+    int4* geo_i = reinterpret_cast<int4*>(vbuf + IAC_TH * (IAC_TW + 2) * IAC_C);         // [(TH+2)*(TW+2)]
+    float4* geo_w = reinterpret_cast<float4*>(geo_i + IAC_HALO);
     const int hw = threadIdx.x >> 4, c0 = (threadIdx.x & 15) * 4;
     const int tiles_x = (a.W + IAC_TW - 1) / IAC_TW;
     const int ty0 = (blockIdx.x / tiles_x) * IAC_TH, tx0 = (blockIdx.x % tiles_x) * IAC_TW;
@@ -337,23 +310,54 @@ __global__ void __launch_bounds__(IAC_THREADS, HALF ? 2 : 1) iac_step_kernel(Iac
             for (int t = 0; t < 3; ++t) k[j][t].load(a.taps, idx + t * IAC_C);
         }
     }
-    // phase 0: sample coordinates of the haloed tile (clamped pixel == replicate padding), one per thread
+    // phase 0: sample geometry of the haloed tile (clamped pixel == replicate padding), one halo pixel per thread
     for (int hp = threadIdx.x; hp < IAC_HALO; hp += IAC_THREADS) {
         const int hy = hp / (IAC_TW + 2), hx = hp - hy * (IAC_TW + 2);
         const int yy = min(max(ty0 - 1 + hy, 0), H - 1), xx = min(max(tx0 - 1 + hx, 0), W - 1);
         const float2 d = *reinterpret_cast<const float2*>(a.offs + (img + (size_t)yy * W + xx) * a.ldoffs + offs_ch);
-        offs_s[hp] = make_float2((float)xx + d.x, (float)yy + d.y);
+        const float sx = (float)xx + d.x, sy = (float)yy + d.y;
+        int4 gi = make_int4(0, 0, 0, 0);
+        float4 gw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H) {        // also rejects NaN / inf offsets
+            const float fx0 = floorf(sx), fy0 = floorf(sy);
+            const float lx = sx - fx0, ly = sy - fy0;
+            const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+            const bool vx0 = x0 >= 0, vx1 = x1 < W, vy0 = y0 >= 0, vy1 = y1 < H;
+            const int r0 = (vy0 ? y0 : 0) * W, r1 = (vy1 ? y1 : H - 1) * W, q0 = vx0 ? x0 : 0, q1 = vx1 ? x1 : W - 1;
+            gi = make_int4(r0 + q0, r0 + q1, r1 + q0, r1 + q1);
+            gw = make_float4((vy0 && vx0) ? (1.f - ly) * (1.f - lx) : 0.f, (vy0 && vx1) ? (1.f - ly) * lx : 0.f,
+                             (vy1 && vx0) ? ly * (1.f - lx) : 0.f, (vy1 && vx1) ? ly * lx : 0.f);
+        }
+        geo_i[hp] = gi;
+        geo_w[hp] = gw;
     }
     __syncthreads();
     // phase 1: warped samples, two halo pixels (8 independent 16-byte gathers) in flight per thread
+    const float* pbase = prev + img * ldp + c0;
     for (int hp = hw; hp < IAC_HALO; hp += 2 * IAC_HW) {
-        const int hp2 = hp + IAC_HW;
-        const float2 p0 = offs_s[hp];
-        const float2 p1 = hp2 < IAC_HALO ? offs_s[hp2] : make_float2(-2.f, -2.f);
-        const float4 s0 = iac_gather(prev, ldp, img, H, W, p0.x, p0.y, c0);
-        const float4 s1 = iac_gather(prev, ldp, img, H, W, p1.x, p1.y, c0);
+        const int hp2 = min(hp + IAC_HW, IAC_HALO - 1);
+        const int4 i0 = geo_i[hp], i1 = geo_i[hp2];
+        const float4 w0 = geo_w[hp], w1 = geo_w[hp2];
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.x * ldp));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.y * ldp));
+        const float4 a2 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.z * ldp));
+        const float4 a3 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.w * ldp));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.x * ldp));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.y * ldp));
+        const float4 b2 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.z * ldp));
+        const float4 b3 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.w * ldp));
+        // same accumulation order as before (corner 00, 01, 10, 11 with fmaf): bit-identical samples
+        float4 s0, s1;
+        s0.x = fmaf(w0.w, a3.x, fmaf(w0.z, a2.x, fmaf(w0.y, a1.x, w0.x * a0.x)));
+        s0.y = fmaf(w0.w, a3.y, fmaf(w0.z, a2.y, fmaf(w0.y, a1.y, w0.x * a0.y)));
+        s0.z = fmaf(w0.w, a3.z, fmaf(w0.z, a2.z, fmaf(w0.y, a1.z, w0.x * a0.z)));
+        s0.w = fmaf(w0.w, a3.w, fmaf(w0.z, a2.w, fmaf(w0.y, a1.w, w0.x * a0.w)));
+        s1.x = fmaf(w1.w, b3.x, fmaf(w1.z, b2.x, fmaf(w1.y, b1.x, w1.x * b0.x)));
+        s1.y = fmaf(w1.w, b3.y, fmaf(w1.z, b2.y, fmaf(w1.y, b1.y, w1.x * b0.y)));
+        s1.z = fmaf(w1.w, b3.z, fmaf(w1.z, b2.z, fmaf(w1.y, b1.z, w1.x * b0.z)));
+        s1.w = fmaf(w1.w, b3.w, fmaf(w1.z, b2.w, fmaf(w1.y, b1.w, w1.x * b0.w)));
         *reinterpret_cast<float4*>(samp + hp * IAC_C + c0) = s0;
-        if (hp2 < IAC_HALO) *reinterpret_cast<float4*>(samp + hp2 * IAC_C + c0) = s1;
+        if (hp + IAC_HW < IAC_HALO) *reinterpret_cast<float4*>(samp + hp2 * IAC_C + c0) = s1;
     }
     __syncthreads();
     // phase 2: vertical pass for this half-warp's columns of its row
@@ -429,7 +433,7 @@ extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* pr
     a.next[0] = next_f; a.next[1] = next_b; a.ldnext[0] = ldnext_f; a.ldnext[1] = ldnext_b;
     a.offs = offs; a.ldoffs = ldoffs; a.offs_ch[0] = ch_f; a.offs_ch[1] = ch_b;
     a.taps = taps; a.ldtaps = ldtaps; a.B = B; a.H = H; a.W = W; a.round_out = round_out;
-    const size_t smem = (IAC_HALO + IAC_TH * (IAC_TW + 2)) * IAC_C * sizeof(float) + IAC_HALO * sizeof(float2);
+    const size_t smem = (IAC_HALO + IAC_TH * (IAC_TW + 2)) * IAC_C * sizeof(float) + IAC_HALO * (sizeof(int4) + sizeof(float4));
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(iac_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
