@@ -277,13 +277,16 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_c2r_w_kernel(const float2* __
 // Same tensor layouts, arguments and semantics as the Stockham kernels above, which remain the path for
 // every other length.
 // =================================================================================================
-#define FFT2_THREADS_MAX 512
+// Register budget: the kernels are half issue-bound, half latency-bound (ncu: issue slots ~50 %, occupancy 23 % at 128
+// registers).  Capping at 80 (W passes, 3 blocks of <= 256 threads) / 64 (H pass, 4 blocks) registers costs a few spills in
+// the radix-20+ butterflies but measured +5-12 % bandwidth.
+#define FFT2_THREADS_MAX 256
 
 #define FFT2_CASE_A(R) case R: fftreg::phase_a<R, INV>(load, S, tws, r2, cb_log2); break;
 #define FFT2_CASE_B(R) case R: fftreg::phase_b<R, INV>(S, r1, cb_log2, store); break;
 
 template <bool INV>
-__global__ void __launch_bounds__(FFT2_THREADS_MAX) fft2_c2c_h_kernel(const float2* in, float2* out, const float2* __restrict__ tw,
+__global__ void __launch_bounds__(FFT2_THREADS_MAX, 4) fft2_c2c_h_kernel(const float2* in, float2* out, const float2* __restrict__ tw,
                                                                      const float* __restrict__ mask, int H, int Wf, int C,
                                                                      int cb_log2, float scale, int round_out, int r1, int r2, unsigned* out_bf16) {
     extern __shared__ float2 sm[];
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(FFT2_THREADS_MAX) fft2_c2c_h_kernel(const floa
     }
 }
 
-__global__ void __launch_bounds__(FFT2_THREADS_MAX) fft2_r2c_w_kernel(const float* __restrict__ x, int ldx, float2* __restrict__ out,
+__global__ void __launch_bounds__(FFT2_THREADS_MAX, 3) fft2_r2c_w_kernel(const float* __restrict__ x, int ldx, float2* __restrict__ out,
                                                                      const float2* __restrict__ tw, int W, int C, int cb_log2,
                                                                      int r1, int r2) {
     constexpr bool INV = false;
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(FFT2_THREADS_MAX) fft2_r2c_w_kernel(const floa
     }
 }
 
-__global__ void __launch_bounds__(FFT2_THREADS_MAX) fft2_c2r_w_kernel(const float2* __restrict__ in, float* __restrict__ y, int ldy,
+__global__ void __launch_bounds__(FFT2_THREADS_MAX, 3) fft2_c2r_w_kernel(const float2* __restrict__ in, float* __restrict__ y, int ldy,
                                                                      const float2* __restrict__ tw, int W, int C, int cb_log2,
                                                                      float scale, int r1, int r2) {
     constexpr bool INV = true;
