@@ -13,7 +13,8 @@ st = torch.cuda.current_stream().cuda_stream
 shapes = [(1, 64, 64, 180, 320, 3), (1, 64, 128, 180, 320, 3), (1, 128, 64, 180, 320, 3), (1, 64, 64, 90, 160, 3),
           (1, 64, 64, 45, 80, 3), (1, 64, 64, 180, 320, 1), (1, 64, 1152, 180, 320, 1), (1, 64, 256, 360, 640, 3),
           (4, 64, 64, 180, 320, 3), (4, 64, 128, 180, 320, 3), (4, 128, 64, 180, 320, 3), (4, 64, 256, 360, 640, 3),
-          (4, 64, 64, 90, 160, 3)]
+          (4, 64, 64, 90, 160, 3), (8, 128, 128, 180, 161, 1), (8, 128, 128, 180, 160, 1), (4, 256, 128, 180, 161, 1),
+          (4, 64, 64, 180, 320, 1), (4, 64, 64, 90, 160, 1)]
 print("FCVSR_TC_DBG =", os.environ.get("FCVSR_TC_DBG", "0"))
 for (B, ci, co, H, W, k) in shapes:
     x = torch.randn(B, H, W, ci, device=dev)
