@@ -69,6 +69,7 @@ struct ConvTcParams {
     int tiles_x, tiles_y, total_tiles;
     int act; float slope; const float* slope_ptr; int ps;
     int wide;                            // 32-byte aligned tensors: use 256-bit loads / stores in the epilogue
+    int epi_sets;                        // 1, 2 or 4 epilogue warp sets (see the epilogue)
     int* err;
     int dbg;                             // bring-up only (FCVSR_TC_DBG): 1 no MMA, 2 no A loads, 4 no B loads, 8 no stores
 };
@@ -132,7 +133,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_NA_MAX; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
         for (int i = 0; i < TC_NB_MAX; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
-        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], KS == 1 ? 4 : TC_EPI_WARPS); }
+        for (int i = 0; i < TC_NACC; ++i) { mbar_init(&tm_full[i], 1); mbar_init(&tm_empty[i], TC_EPI_WARPS / p.epi_sets); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -260,25 +261,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // ===== epilogue warps 3..: TMEM lane quarter = warp % 4; the warps of a quarter split the tile's 16-column
         // chunks.  The epilogue is a latency chain (tcgen05.ld -> scattered 32-byte stores that queue behind the
         // tensor core's operand fetches), so more warps in flight shorten it almost linearly. =====
-        // 1x1 convolutions (4-16 MMAs per tile, epilogue-bound): the 16 warps form four SETS of four (one warp per lane
-        // quarter); set s owns accumulator tile s, i.e. every fourth tile, and drains all of its columns.  A warp's per-tile
-        // time is a latency chain (barrier wake-up -> tcgen05.ld -> bias -> scattered stores) that more columns barely
-        // lengthen, so four tiles in their epilogue at once raise the drain rate (64->64 1x1: 10.0 -> 8.3 us, 64->1152:
-        // 69.5 -> 59.5 us).  3x3 convolutions: all warps on the same tile, columns split (measured 2-7 % faster there).
-        constexpr int TC_EPI_MODE = KS == 1 ? 1 : 0;
+        // p.epi_sets = S in {1, 2, 4}: the 16 warps form S sets; set s drains tiles s, s + S, ... (accumulator tile = tile
+        // index mod 4), and inside a set the 4 / S warps of a lane quarter split the tile's 16-column chunks.  A warp's
+        // per-tile time is a latency chain (barrier wake-up -> tcgen05.ld -> bias -> scattered stores) that more columns
+        // barely lengthen, so several tiles in their epilogue at once raise the drain rate when the epilogue is the limit.
+        const int S = p.epi_sets;
         const int q = warp & 3;
-        const int eh = (warp - 3) >> 2;                // set (mode 1) / share of the columns (mode 0)
-        const int nchunk = p.n_tile >> 4, cper = (nchunk + TC_EPI_WARPS / 4 - 1) / (TC_EPI_WARPS / 4);
-        const int c_begin = TC_EPI_MODE ? 0 : min(eh * cper, nchunk), c_end = TC_EPI_MODE ? nchunk : min(c_begin + cper, nchunk);
+        const int g = (warp - 3) >> 2;                 // 0..3 among the warps of this lane quarter
+        const int eset = g % S, eh = g / S;            // set, share of the columns inside the set
+        const int nchunk = p.n_tile >> 4, wps = (TC_EPI_WARPS / 4) / S, cper = (nchunk + wps - 1) / wps;
+        const int c_begin = min(eh * cper, nchunk), c_end = min(c_begin + cper, nchunk);
         const int m = q * 32 + lane;                   // pixel within the tile == TMEM lane
         const int ly = m / TC_TW, lx = m - ly * TC_TW;
         const float slope = p.act == FCVSR_ACT_PRELU ? p.slope_ptr[0] : p.slope;
         const int c4 = p.Cout >> 2;
-        int acc = TC_EPI_MODE ? eh : 0; uint32_t pacc = 0;
+        int acc = 0; uint32_t pacc = 0;
         asm volatile("griddepcontrol.wait;" ::: "memory");          // res may be, and y may still be read by, earlier kernels
-        int tn = TC_EPI_MODE ? eh : 0;
-        constexpr int TSTEP = TC_EPI_MODE ? TC_NACC : 1;
-        for (int t = blockIdx.x + tn * gridDim.x; t < p.total_tiles; t += TSTEP * gridDim.x, tn += TSTEP) {
+        int tn = eset;
+        for (int t = blockIdx.x + tn * gridDim.x; t < p.total_tiles; t += S * gridDim.x, tn += S) {
+            acc = tn & (TC_NACC - 1);
+            pacc = (uint32_t)(tn >> 2) & 1u;
             const TileCoord tc = decode_tile(t, p);
             const int y = tc.ty * TC_TH + ly, x = tc.tx * TC_TW + lx;
             const bool valid = y < p.H && x < p.W;
@@ -399,8 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tm_empty[acc]);
             if (warp == 3 && lane == 0) TC_STAMP(tn, 9);
-            if (TC_EPI_MODE) pacc ^= 1;                                // same accumulator, next phase
-            else if (++acc == nacc) { acc = 0; pacc ^= 1; }
+
         }
     }
     tc_fence_before();
@@ -496,6 +497,12 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     p.bias = bias; p.res = res; p.ldres = ldres; p.res2 = res2; p.ldres2 = ldres2; p.y = y; p.ldy = ldy; p.y2 = y2; p.ldy2 = ldy2; p.round_out = round_out;
     p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ksize; p.cout_valid = cout_valid;
     p.n_tile = n_tile; p.n_tiles = n_tiles;
+    {   // 1x1: four sets (epilogue-bound, 4-16 MMAs per tile); 3x3 bf16: two sets (64->64 24.8 -> 22.0 us, 64->256 at 360x640
+        // 296 -> 272 us = 1.0 PFLOP/s); 3x3 TF32 (twice the MMAs per tile): one set, all warps on the same tile
+        static int es = -1;
+        if (es < 0) { const char* e = getenv("FCVSR_EPI_SETS"); es = e ? atoi(e) : 0; }
+        p.epi_sets = es == 1 || es == 2 || es == 4 ? es : (ksize == 1 ? 4 : (op16 ? 2 : 1));
+    }
     p.tiles_x = (W + TC_TW - 1) / TC_TW; p.tiles_y = (H + TC_TH - 1) / TC_TH;
     p.total_tiles = p.tiles_x * p.tiles_y * B * n_tiles;
     p.act = act; p.slope = slope; p.slope_ptr = slope_ptr; p.ps = pixel_shuffle;
