@@ -512,7 +512,9 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
         const int esz_y = ((op16 && round_out) || round_out == 2) ? 2 : 4, esz_y2 = op16 ? 2 : 4;
         p.wide = !thin && !(a & 31) && !((ldy * esz_y) & 31) && (!res || !((ldres * 4) & 31)) && (!y2 || !((ldy2 * esz_y2) & 31)) &&
                  (!pixel_shuffle || !(((Cout >> 2) * esz_y) & 31));
-        if (getenv("FCVSR_TC_NARROW")) p.wide = 0;
+        static int narrow = -1;                     // bring-up: force the 128-bit epilogue accesses
+        if (narrow < 0) narrow = getenv("FCVSR_TC_NARROW") ? 1 : 0;
+        if (narrow) p.wide = 0;
     }
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FCVSR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
 

@@ -10,6 +10,11 @@
  * lives at base[((b*H + y)*W + x)*ld + c]; a channel slice is base+offset with the same ld.
  * Spectra are complex-interleaved NHWC: [B,H,Wf,C] float2, Wf = W/2+1.
  *
+ * Process model: one process per GPU (the bench and the sequence driver launch one rank per device).  The library keeps a
+ * few per-process statics (SM count, function attributes, a 4-byte device error word for the tensor-core kernels), so a
+ * process must not drive more than one device through it.  All entries are asynchronous on `stream`, never allocate
+ * (except that error word, once) and never synchronise.
+ *
  * Reference files are relative to /root/reference (QZ1-boy/FCVSR).
  */
 #ifndef FCVSR_B200_H
