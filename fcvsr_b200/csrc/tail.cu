@@ -83,3 +83,100 @@ extern "C" int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int
     pack_clip_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, y, T, H * W, cpad, total, op16);
     return fcvsr_launch_status();
 }
+
+// ---- conv_last0: 3x3, 64 -> 1 channel, bf16 NHWC input, + bias + residual plane (CVSR_freq.py:2749-2751) -------------
+// On the tensor cores this is an N = 16 MMA with one useful column: A-operand bound (369 us at 720x1280, batch 4, for 73 us
+// of HBM time).  Here a thread computes 4 horizontally adjacent outputs: per filter row it reads the 6 input pixels of its
+// window once (8 x 16-byte ld.shared per pixel) and feeds all taps that use them; the 576 weights ride in the kernel
+// parameter space, so every FFMA takes its weight from the constant bank.  Tile = 8 x 64 outputs, haloed input tile
+// (10 x 66 pixels x 128 B) loaded with zero-filling cp.async, 16-byte chunks XOR-swizzled with (pixel >> 2) so that the
+// 64-byte thread stride is conflict-free.
+#define L1_TH 8
+#define L1_TW 64
+#define L1_THREADS 128
+struct ToOneParams {
+    const unsigned short* x; int ldx;
+    const float* res; float* y;
+    int B, H, W;
+    float bias;
+    float w[9 * 64];           // [ky][kx][c]
+};
+
+__global__ void __launch_bounds__(L1_THREADS) conv3x3_c64_to1_kernel(const __grid_constant__ ToOneParams p) {
+    extern __shared__ __align__(16) unsigned char l1_smem[];
+    const int tx0 = blockIdx.x * L1_TW, ty0 = blockIdx.y * L1_TH, b = blockIdx.z;
+    const unsigned short* xb = p.x + (size_t)b * p.H * p.W * p.ldx;
+    constexpr int TWP = L1_TW + 2, NPX = (L1_TH + 2) * TWP;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(l1_smem);
+    for (int e = threadIdx.x; e < NPX * 8; e += L1_THREADS) {
+        const int px = e >> 3, c8 = e & 7;
+        const int r = px / TWP, c = px - r * TWP;
+        const int yy = ty0 - 1 + r, xx = tx0 - 1 + c;
+        const bool ok = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        const void* src = ok ? (const void*)(xb + ((size_t)yy * p.W + xx) * p.ldx + c8 * 8) : (const void*)p.x;
+        const unsigned dst = sbase + px * 128 + ((c8 ^ ((px >> 2) & 7)) << 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, x0 = (threadIdx.x & 15) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int px = (ty + ky) * TWP + x0 + i;
+            const unsigned char* pp = l1_smem + px * 128;
+            const int sw = (px >> 2) & 7;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(pp + ((c8 ^ sw) << 4));
+                float f[8];
+                f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+                f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+                f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+                f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int kx = i - j;
+                    if (kx >= 0 && kx < 3) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[j] = fmaf(f[c], p.w[(ky * 3 + kx) * 64 + c8 * 8 + c], acc[j]);
+                    }
+                }
+            }
+        }
+    }
+    const int y = ty0 + ty, x = tx0 + x0;
+    if (y < p.H && x < p.W) {
+        const size_t o = ((size_t)b * p.H + y) * p.W + x;
+        if (x + 3 < p.W && !(o & 3)) {
+            float4 r = p.res ? *reinterpret_cast<const float4*>(p.res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(p.y + o) =
+                make_float4(acc[0] + p.bias + r.x, acc[1] + p.bias + r.y, acc[2] + p.bias + r.z, acc[3] + p.bias + r.w);
+        } else {
+            for (int j = 0; j < 4 && x + j < p.W; ++j) p.y[o + j] = acc[j] + p.bias + (p.res ? p.res[o + j] : 0.f);
+        }
+    }
+}
+
+// x: bf16 NHWC [B,H,W,ldx] (64 channels used); w_host: HOST pointer to 9*64 floats [ky][kx][c] (they travel as kernel
+// parameters); res / y: fp32 planes [B,H,W].  Replaces conv_last0 + the bilinear-skip add (CVSR_freq.py:2749-2751).
+extern "C" int fcvsr_conv3x3_c64_to1(const void* x, int ldx, const float* w_host, float bias, const float* res, float* y, int B,
+                                     int H, int W, cudaStream_t st) {
+    if (!x || !w_host || !y || B <= 0 || H <= 0 || W <= 0 || (ldx & 7) || ((uintptr_t)x & 15)) return FCVSR_ERR_ARG;
+    ToOneParams p;
+    p.x = (const unsigned short*)x; p.ldx = ldx; p.res = res; p.y = y; p.B = B; p.H = H; p.W = W; p.bias = bias;
+    for (int i = 0; i < 9 * 64; ++i) p.w[i] = w_host[i];
+    const size_t smem = (size_t)(L1_TH + 2) * (L1_TW + 2) * 128;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(conv3x3_c64_to1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return FCVSR_ERR_CUDA;
+        attr = true;
+    }
+    dim3 grid((W + L1_TW - 1) / L1_TW, (H + L1_TH - 1) / L1_TH, B);
+    conv3x3_c64_to1_kernel<<<grid, L1_THREADS, smem, st>>>(p);
+    return fcvsr_launch_status();
+}

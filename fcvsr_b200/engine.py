@@ -12,6 +12,7 @@ Line numbers in comments refer to CVSR_train/arch/CVSR_freq.py.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 from typing import Dict, Optional
@@ -120,6 +121,7 @@ class Engine:
         self._ksplit = {}
         self.max_ctas = 0            # grid cap of the tensor-core convs on the current stream (0 = all SMs)
         self.multi_stream = True     # run the three pyramid levels of SCNetbk on three streams
+        self.use_last_kernel = os.environ.get("FCVSR_LAST_KERNEL", "1") != "0"   # dedicated Cout = 1 kernel (bf16 mode)
         self._streams = {}
         self.profile = None          # optional list: (kind, flops, start_event, end_event) per conv launch
         C.lib()                      # fail loudly now if the library is missing
@@ -223,6 +225,10 @@ class Engine:
         P["up1"] = cp("upconv1", ps=True)
         P["up2"] = cp("upconv2", ps=True)
         P["last"] = cp("conv_last0")
+        if self.op16:                 # Cout = 1: CUDA-core kernel, weights as kernel parameters (host copy [ky][kx][c])
+            wl = sd["conv_last0.weight"].cpu()                                          # [1, 64, 3, 3]
+            self._last_w = (ctypes.c_float * 576)(*wl[0].permute(1, 2, 0).reshape(-1).tolist())
+            self._last_b = float(sd["conv_last0.bias"].cpu()[0])
         P["prelu"] = sd["lrelu.weight"].reshape(1).contiguous()
         self.packs = P
         self._pack_key = key
@@ -740,4 +746,8 @@ class Engine:
         self._conv(P["up2"], p["up1"], 64, p["up2"], 64, B, 2 * H, 2 * W, act=PR, slope_ptr=sl, rnd=True)
         # bilinear x4 of the centre LR frame (:2750) rides in conv_last0's epilogue as the residual
         self._k("fcvsr_bilinear_up4", x.data_ptr() + 3 * H * W * 4, 7 * H * W, p["base"], B, H, W)
-        self._conv(P["last"], p["up2"], 64, out.data_ptr(), 1, B, 4 * H, 4 * W, res=p["base"], ldres=1)
+        if self.op16 and self.use_last_kernel:
+            self._k("fcvsr_conv3x3_c64_to1", p["up2"], 64, ctypes.addressof(self._last_w), self._last_b, p["base"],
+                    out.data_ptr(), B, 4 * H, 4 * W)
+        else:
+            self._conv(P["last"], p["up2"], 64, out.data_ptr(), 1, B, 4 * H, 4 * W, res=p["base"], ldres=1)

@@ -155,6 +155,11 @@ int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float
 int fcvsr_pixel_shuffle(const void* in, int ldi, void* out, int ldo, int B, int H, int W, int Co, int half,
                         cudaStream_t stream);
 int fcvsr_bilinear_up4(const float* in, long long bstride, float* out, int B, int H, int W, cudaStream_t stream);
+/* conv_last0 + skip (CVSR_freq.py:2749-2751) in bf16 mode: y[b,y,x] = bias + res[b,y,x] + sum_{ky,kx,c} w[ky][kx][c] *
+ * x[b, y+ky-1, x+kx-1, c] for a bf16 NHWC input with 64 channels (zero padding).  w_host is a HOST pointer to 9*64 floats:
+ * the weights travel in the kernel parameter space.  CUDA cores: the tensor-core path needs an N = 16 MMA for one column. */
+int fcvsr_conv3x3_c64_to1(const void* x_bf16, int ldx, const float* w_host, float bias, const float* res, float* y, int B,
+                          int H, int W, cudaStream_t stream);
 /* NCHW clip [B,T,H,W] -> NHWC [B,H,W,32] (channels >= T zero, TF32-rounded): tensor-core operand of feat_extract */
 int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int W, int op16, cudaStream_t stream);
 int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npix, cudaStream_t stream);

@@ -383,6 +383,24 @@ def test_baseline_size_parity_against_oracle(dev, variant, b, h, w):
         del m
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 8, 64), (2, 19, 70), (1, 40, 200)])
+def test_conv_last_to1_kernel(dev, B, H, W):
+    """fcvsr_conv3x3_c64_to1 (conv_last0 + skip, bf16 input): exact on the bf16-rounded input up to fp32 summation order."""
+    import ctypes
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(B, 64, H, W, generator=g)
+    w = torch.randn(1, 64, 3, 3, generator=g) / 24
+    res = torch.randn(B, 1, H, W, generator=g)
+    xd = nhwc(x).to(dev).to(torch.bfloat16)
+    rd = res.to(dev).contiguous()
+    y = torch.empty(B, 1, H, W, device=dev)
+    wh = (ctypes.c_float * 576)(*w[0].permute(1, 2, 0).reshape(-1).tolist())
+    C.call("fcvsr_conv3x3_c64_to1", xd.data_ptr(), 64, ctypes.addressof(wh), 0.25, rd.data_ptr(), y.data_ptr(), B, H, W, _st())
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w, torch.tensor([0.25]), padding=1) + res
+    assert float((y.cpu() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
 def test_gshiftnet_etc_matches_per_window_forward(dev):
     """GShiftNet_ETC (CVSR_freq.py:2760-2843): 7 windows of a 13-frame clip == 7 GShiftNet forwards, x_up == bilinear x4."""
     sd = arch.seeded_state_dict("full", 2, ACNum=2, Freq_Inv=2, SCGroupN=1)
