@@ -12,7 +12,13 @@ entry it binds is ``fcvsr_modulated_deform_conv_forward`` (include/fcvsr_b200.h)
 kernel that replaces deform_conv_forward_cuda / modulated_deform_conv_cuda_forward
 (ops/dcn/src/deform_conv_cuda.cpp:151,486) without the HBM column buffer.  ``im2col_step`` is accepted for
 API compatibility (v1 still validates that it divides the batch, :49-51) but there is no column buffer
-to chunk.  Forward only in this round: tensors that require grad raise NotImplementedError.
+to chunk.
+
+Autograd: ``deform_conv`` / ``modulated_deform_conv`` (and the DeformConv / ModulatedDeformConv modules) are
+``torch.autograd.Function``s like the reference's (deform_conv.py:14-98,:114-183); their backward binds
+``fcvsr_modulated_deform_conv_backward`` (csrc/dcn_bwd.cu), which replaces modulated_deform_conv_cuda_backward /
+deform_conv_backward_input_cuda / deform_conv_backward_parameters_cuda (deform_conv_cuda.cpp:566,260,373).  The *Pack
+modules run their offset convolution on the forward-only convolution kernel, so they still raise under autograd.
 """
 from __future__ import annotations
 
@@ -25,7 +31,7 @@ from torch.nn.modules.utils import _pair
 from .. import _capi as C
 
 
-def _check(*tensors):
+def _check(*tensors, allow_grad=False):
     for t in tensors:
         if t is None:
             continue
@@ -33,9 +39,10 @@ def _check(*tensors):
             raise NotImplementedError("deformable convolution is CUDA-only (as the reference, deform_conv.py:46-47)")
         if t.dtype != torch.float32:
             raise TypeError("fcvsr_b200 DCN kernels are fp32")
-        if torch.is_grad_enabled() and t.requires_grad:
-            raise NotImplementedError("fcvsr_b200: DCN backward kernels are not implemented in this round; "
-                                      "call under torch.no_grad()")
+        if not allow_grad and torch.is_grad_enabled() and t.requires_grad:
+            raise NotImplementedError("fcvsr_b200: the *Pack modules' offset convolution has no backward kernel yet; "
+                                      "call under torch.no_grad() (the functional ops and DeformConv / "
+                                      "ModulatedDeformConv are autograd-capable)")
 
 
 def _out_hw(h, w, kh, kw, stride, padding, dilation):
@@ -77,33 +84,104 @@ def _launch(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg
     return y
 
 
+def _backward(x, offset, mask, weight, grad_out, stride, padding, dilation, groups, dg, need, with_bias):
+    """One call of fcvsr_modulated_deform_conv_backward; need = (input, offset, mask, weight) flags.  Gradients are
+    zero-filled here and accumulated by the kernels (deform_conv.py:155-159)."""
+    b, cin, h, w = x.shape
+    cout, _, kh, kw = weight.shape
+    grad_out = grad_out.contiguous()
+    gx = torch.zeros_like(x) if need[0] else None
+    goff = torch.zeros_like(offset) if need[1] else None
+    gmask = torch.zeros_like(mask) if (mask is not None and need[2]) else None
+    gw = torch.zeros_like(weight) if need[3] else None
+    gb = x.new_zeros(cout) if with_bias else None
+    ptr = lambda t: t.data_ptr() if t is not None else 0  # noqa: E731
+    with torch.cuda.device(x.device):
+        C.call("fcvsr_modulated_deform_conv_backward", x.data_ptr(), weight.data_ptr(), offset.data_ptr(), ptr(mask),
+               grad_out.data_ptr(), ptr(gx), ptr(gw), ptr(gb), ptr(goff), ptr(gmask), b, cin, h, w, cout, kh, kw,
+               stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], groups, dg,
+               torch.cuda.current_stream().cuda_stream)
+    return gx, goff, gmask, gw, gb
+
+
+class DeformConvFunction(torch.autograd.Function):
+    """deform_conv.py:14-98."""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
+                im2col_step=64):
+        if input is not None and input.dim() != 4:
+            raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
+        _check(input, offset, weight, allow_grad=True)
+        cur = min(im2col_step, input.shape[0])
+        assert input.shape[0] % cur == 0, "im2col step must divide batchsize"
+        stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)
+        kh, kw = weight.shape[2:]
+        ho, wo = _out_hw(input.shape[2], input.shape[3], kh, kw, stride, padding, dilation)
+        if tuple(offset.shape) != (input.shape[0], deformable_groups * 2 * kh * kw, ho, wo):
+            raise ValueError(f"invalid offset shape {tuple(offset.shape)}")
+        input, offset, weight = input.contiguous(), offset.contiguous(), weight.contiguous()
+        ctx.cfg = (stride, padding, dilation, groups, deformable_groups)
+        ctx.save_for_backward(input, offset, weight)
+        return _launch(input, offset, None, weight, None, stride, padding, dilation, groups, deformable_groups)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        input, offset, weight = ctx.saved_tensors
+        stride, padding, dilation, groups, dg = ctx.cfg
+        n = ctx.needs_input_grad
+        need_data = n[0] or n[1]                      # the reference computes both together (:76-82)
+        gx, goff, _, gw, _ = _backward(input, offset, None, weight, grad_output, stride, padding, dilation, groups, dg,
+                                       (need_data, need_data, False, n[2]), False)
+        return gx, goff, gw, None, None, None, None, None, None
+
+
+class ModulatedDeformConvFunction(torch.autograd.Function):
+    """deform_conv.py:114-183."""
+
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                deformable_groups=1):
+        _check(input, offset, mask, weight, bias, allow_grad=True)
+        stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)   # scalars in the reference (:179-182)
+        kh, kw = weight.shape[2:]
+        ho, wo = _out_hw(input.shape[2], input.shape[3], kh, kw, stride, padding, dilation)
+        if tuple(offset.shape) != (input.shape[0], deformable_groups * 2 * kh * kw, ho, wo):
+            raise ValueError(f"invalid offset shape {tuple(offset.shape)}")
+        if tuple(mask.shape) != (input.shape[0], deformable_groups * kh * kw, ho, wo):
+            raise ValueError(f"invalid mask shape {tuple(mask.shape)}")
+        input, offset, mask, weight = input.contiguous(), offset.contiguous(), mask.contiguous(), weight.contiguous()
+        bias = bias.contiguous() if bias is not None else None
+        ctx.cfg = (stride, padding, dilation, groups, deformable_groups, bias is not None)
+        ctx.save_for_backward(input, offset, mask, weight)
+        return _launch(input, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        input, offset, mask, weight = ctx.saved_tensors
+        stride, padding, dilation, groups, dg, with_bias = ctx.cfg
+        n = ctx.needs_input_grad
+        gx, goff, gmask, gw, gb = _backward(input, offset, mask, weight, grad_output, stride, padding, dilation, groups,
+                                            dg, (n[0], n[1], n[2], n[3]), with_bias and n[4])
+        return gx, goff, gmask, gw, gb, None, None, None, None, None
+
+
 def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64):
-    if input is not None and input.dim() != 4:
-        raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
-    _check(input, offset, weight)
-    cur = min(im2col_step, input.shape[0])
-    assert input.shape[0] % cur == 0, "im2col step must divide batchsize"
-    stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)
-    kh, kw = weight.shape[2:]
-    ho, wo = _out_hw(input.shape[2], input.shape[3], kh, kw, stride, padding, dilation)
-    if tuple(offset.shape) != (input.shape[0], deformable_groups * 2 * kh * kw, ho, wo):
-        raise ValueError(f"invalid offset shape {tuple(offset.shape)}")
-    return _launch(input.contiguous(), offset.contiguous(), None, weight.contiguous(), None, stride, padding, dilation,
-                   groups, deformable_groups)
+    """deform_conv.py:186 (``DeformConvFunction.apply``; keywords accepted as well)."""
+    return DeformConvFunction.apply(input, offset, weight, stride, padding, dilation, groups, deformable_groups, im2col_step)
 
 
 def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
                           deformable_groups=1):
-    _check(input, offset, mask, weight, bias)
-    stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)   # scalars in the reference (:179-182)
-    kh, kw = weight.shape[2:]
-    ho, wo = _out_hw(input.shape[2], input.shape[3], kh, kw, stride, padding, dilation)
-    if tuple(offset.shape) != (input.shape[0], deformable_groups * 2 * kh * kw, ho, wo):
-        raise ValueError(f"invalid offset shape {tuple(offset.shape)}")
-    if tuple(mask.shape) != (input.shape[0], deformable_groups * kh * kw, ho, wo):
-        raise ValueError(f"invalid mask shape {tuple(mask.shape)}")
-    return _launch(input.contiguous(), offset.contiguous(), mask.contiguous(), weight.contiguous(),
-                   bias.contiguous() if bias is not None else None, stride, padding, dilation, groups, deformable_groups)
+    """deform_conv.py:187 (``ModulatedDeformConvFunction.apply``; keywords accepted as well)."""
+    return ModulatedDeformConvFunction.apply(input, offset, mask, weight, bias, stride, padding, dilation, groups,
+                                             deformable_groups)
 
 
 def _offset_conv(x, conv: nn.Conv2d):

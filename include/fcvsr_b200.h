@@ -201,6 +201,20 @@ int fcvsr_modulated_deform_conv_forward_tc(const float* input, const float* weig
                                         int deformable_groups, long long offset_batch_stride,
                                         long long mask_batch_stride, int mask_sigmoid, float* scratch_nhwc, cudaStream_t stream);
 
+/* Backward of the operator above (csrc/dcn_bwd.cu), NCHW fp32: replaces modulated_deform_conv_cuda_backward
+ * (ops/dcn/src/deform_conv_cuda.cpp:566-700; call site ops/dcn/deform_conv.py:161-166) and, with mask == NULL,
+ * deform_conv_backward_input_cuda + deform_conv_backward_parameters_cuda (:260-484; call sites deform_conv.py:76-82,:86-92,
+ * scale = 1).  No column buffer.  Every grad_* pointer may be NULL (that gradient is skipped); the ones given ACCUMULATE,
+ * so the caller zero-fills them first (as deform_conv.py:155-159 does with zeros_like).  grad_input [B,Cin,H,W],
+ * grad_weight [Cout,Cin/groups,kh,kw], grad_bias [Cout], grad_offset / grad_mask dense, shaped like offset / mask.
+ * grad_input, grad_offset, grad_mask and grad_weight are combined with fp32 atomics (as the reference's col2im is):
+ * run-to-run differences are at rounding level. */
+int fcvsr_modulated_deform_conv_backward(const float* input, const float* weight, const float* offset, const float* mask,
+                                         const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
+                                         float* grad_offset, float* grad_mask, int B, int Cin, int H, int W, int Cout,
+                                         int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h,
+                                         int dil_w, int groups, int deformable_groups, cudaStream_t stream);
+
 /* library / build info: returns a static string "fcvsr_b200 <version> sm_100a" */
 const char* fcvsr_version(void);
 

@@ -281,6 +281,96 @@ def test_modulated_dcn_matches_oracle(dev, cfg, monkeypatch):
     assert float((y.cpu() - ref).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("cfg", [dict(B=2, cin=16, cout=16, H=9, W=11, k=3, g=1, dg=16, pad=1, stride=1, dil=1, mask=True),
+                                 dict(B=1, cin=64, cout=64, H=20, W=24, k=3, g=1, dg=16, pad=1, stride=1, dil=1, mask=True),
+                                 dict(B=2, cin=8, cout=6, H=9, W=11, k=3, g=2, dg=4, pad=1, stride=2, dil=1, mask=True),
+                                 dict(B=1, cin=4, cout=4, H=12, W=10, k=5, g=1, dg=4, pad=4, stride=1, dil=2, mask=True),
+                                 dict(B=3, cin=6, cout=10, H=14, W=13, k=3, g=1, dg=2, pad=1, stride=1, dil=1, mask=True),
+                                 dict(B=2, cin=12, cout=72, H=11, W=17, k=3, g=1, dg=1, pad=0, stride=1, dil=1, mask=False),
+                                 dict(B=1, cin=2, cout=1, H=4, W=4, k=3, g=1, dg=2, pad=1, stride=1, dil=1, mask=False)])
+def test_dcn_backward_matches_oracle(dev, cfg, monkeypatch):
+    """fcvsr_modulated_deform_conv_backward (dcn_bwd.cu) through the autograd Functions of ops.dcn against autograd through
+    the CPU oracle (pinned to torchvision's deform_conv2d backward in tests/test_oracle.py): all five gradients, groups,
+    stride / dilation, ragged tiles, deformable-group widths 1, 2, 3, 4 and 12, DCNv1 (no mask).  fp32 with atomics:
+    max-abs <= 2e-4 of each gradient's scale."""
+    import fcvsr_b200.ops.dcn as dcn_mod
+    monkeypatch.setattr(dcn_mod, "PRECISION", "fp32")
+    g = torch.Generator().manual_seed(cfg["H"] * cfg["W"] + 7)
+    k, dg = cfg["k"], cfg["dg"]
+    x = torch.randn(cfg["B"], cfg["cin"], cfg["H"], cfg["W"], generator=g)
+    w = torch.randn(cfg["cout"], cfg["cin"] // cfg["g"], k, k, generator=g) / 6
+    b = torch.randn(cfg["cout"], generator=g)
+    ho = (cfg["H"] + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    wo = (cfg["W"] + 2 * cfg["pad"] - (cfg["dil"] * (k - 1) + 1)) // cfg["stride"] + 1
+    off = 3.0 * torch.randn(cfg["B"], dg * 2 * k * k, ho, wo, generator=g)
+    msk = torch.rand(cfg["B"], dg * k * k, ho, wo, generator=g)
+    gy = torch.randn(cfg["B"], cfg["cout"], ho, wo, generator=g)
+    if cfg["mask"]:
+        names = ("input", "offset", "mask", "weight", "bias")
+        cpu = [t.clone().requires_grad_(True) for t in (x, off, msk, w, b)]
+        (O.modulated_deform_conv(cpu[0], cpu[1], cpu[2], cpu[3], cpu[4], cfg["stride"], cfg["pad"], cfg["dil"], cfg["g"],
+                                 dg) * gy).sum().backward()
+        gpu = [t.to(dev).requires_grad_(True) for t in (x, off, msk, w, b)]
+        y = dcn_mod.modulated_deform_conv(gpu[0], gpu[1], gpu[2], gpu[3], gpu[4], cfg["stride"], cfg["pad"], cfg["dil"],
+                                          cfg["g"], dg)
+    else:
+        names = ("input", "offset", "weight")
+        cpu = [t.clone().requires_grad_(True) for t in (x, off, w)]
+        (O.modulated_deform_conv(cpu[0], cpu[1], None, cpu[2], None, cfg["stride"], cfg["pad"], cfg["dil"], cfg["g"], dg)
+         * gy).sum().backward()
+        gpu = [t.to(dev).requires_grad_(True) for t in (x, off, w)]
+        y = dcn_mod.deform_conv(gpu[0], gpu[1], gpu[2], cfg["stride"], cfg["pad"], cfg["dil"], cfg["g"], dg, 64)
+    (y * gy.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    for name, a, r in zip(names, gpu, cpu):
+        err = float((a.grad.cpu() - r.grad).abs().max())
+        assert err <= 2e-4 * max(1.0, float(r.grad.abs().max())), (name, err)
+
+
+def test_dcn_backward_partial_needs_and_module(dev, monkeypatch):
+    """Only the requested gradients are produced (frozen offset / mask), and the ModulatedDeformConv module trains."""
+    import fcvsr_b200.ops.dcn as dcn_mod
+    monkeypatch.setattr(dcn_mod, "PRECISION", "fp32")
+    g = torch.Generator().manual_seed(5)
+    m = dcn_mod.ModulatedDeformConv(8, 8, 3, padding=1, deformable_groups=2).to(dev)
+    x = torch.randn(1, 8, 10, 12, generator=g).to(dev)
+    off = torch.randn(1, 36, 10, 12, generator=g).to(dev)
+    msk = torch.rand(1, 18, 10, 12, generator=g).to(dev)
+    y = m(x, off, msk)
+    y.square().sum().backward()
+    assert m.weight.grad is not None and m.bias.grad is not None and x.grad is None and off.grad is None
+    wr = m.weight.detach().cpu().clone().requires_grad_(True)
+    br = m.bias.detach().cpu().clone().requires_grad_(True)
+    O.modulated_deform_conv(x.cpu(), off.cpu(), msk.cpu(), wr, br, 1, 1, 1, 1, 2).square().sum().backward()
+    assert float((m.weight.grad.cpu() - wr.grad).abs().max()) <= 2e-4 * float(wr.grad.abs().max())
+    assert float((m.bias.grad.cpu() - br.grad).abs().max()) <= 2e-4 * float(br.grad.abs().max())
+
+
+def test_dcn_backward_adjoint_identity_full_size(dev, monkeypatch):
+    """Size-independent property at the benchmark shape (64 -> 64, 3x3, dg 16, 180x320): the operator is linear in its
+    input and in its weight, so <gy, DCN(dx; w)> == <grad_input, dx> and <gy, DCN(x; dw)> == <grad_weight, dw> (no bias)."""
+    import fcvsr_b200.ops.dcn as dcn_mod
+    monkeypatch.setattr(dcn_mod, "PRECISION", "fp32")
+    g = torch.Generator(device=dev).manual_seed(3)
+    B, Cc, H, W, dg = 1, 64, 180, 320, 16
+    x = torch.randn(B, Cc, H, W, device=dev, generator=g, requires_grad=True)
+    w = (torch.randn(Cc, Cc, 3, 3, device=dev, generator=g) / 24).requires_grad_(True)
+    off = 2.0 * torch.randn(B, dg * 18, H, W, device=dev, generator=g)
+    msk = torch.rand(B, dg * 9, H, W, device=dev, generator=g)
+    gy = torch.randn(B, Cc, H, W, device=dev, generator=g)
+    dx = torch.randn(B, Cc, H, W, device=dev, generator=g)
+    dw = torch.randn(Cc, Cc, 3, 3, device=dev, generator=g) / 24
+    y = dcn_mod.modulated_deform_conv(x, off, msk, w, None, 1, 1, 1, 1, dg)
+    (y * gy).sum().backward()
+    with torch.no_grad():
+        lhs_x = float((gy.double() * dcn_mod.modulated_deform_conv(dx, off, msk, w, None, 1, 1, 1, 1, dg).double()).sum())
+        rhs_x = float((x.grad.double() * dx.double()).sum())
+        lhs_w = float((gy.double() * dcn_mod.modulated_deform_conv(x, off, msk, dw, None, 1, 1, 1, 1, dg).double()).sum())
+        rhs_w = float((w.grad.double() * dw.double()).sum())
+    assert abs(lhs_x - rhs_x) <= 1e-4 * max(1.0, abs(lhs_x)), (lhs_x, rhs_x)
+    assert abs(lhs_w - rhs_w) <= 1e-4 * max(1.0, abs(lhs_w)), (lhs_w, rhs_w)
+
+
 @pytest.mark.parametrize("cfg", [dict(B=1, cin=64, cout=64, H=20, W=24, k=3, dg=16, pad=1, stride=1, dil=1, mask=True),
                                  dict(B=2, cin=32, cout=48, H=17, W=23, k=3, dg=1, pad=2, stride=2, dil=2, mask=True),
                                  dict(B=2, cin=64, cout=128, H=13, W=9, k=1, dg=8, pad=0, stride=1, dil=1, mask=True),

@@ -98,3 +98,26 @@ def test_oracle_blocks_against_live_reference():
     b = torch.randn(1, 128, 10, 9, generator=g)
     coords = ref.coords_grid(1, 10, 9, "cpu")
     assert torch.allclose(O.corr_lookup(a, b), ref.CorrBlock(a, b)(coords), atol=1e-5)
+
+
+def test_dcn_oracle_gradients_match_torchvision():
+    """Backward pin: autograd through the oracle restatement gives the gradients of the reference's backward kernels
+    (dmcn_get_gradient_weight / dmcn_get_coordinate_weight, deform_conv_cuda_kernel.cu:499-567); checked here against the
+    autograd of torchvision.ops.deform_conv2d, which shares the reference's layout.  float64: exact up to
+    summation order."""
+    import torchvision.ops as tv
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 8, 9, 11, generator=g, dtype=torch.float64)
+    w = torch.randn(6, 4, 3, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(6, generator=g, dtype=torch.float64)
+    off = 2.5 * torch.randn(2, 4 * 2 * 9, 9, 11, generator=g, dtype=torch.float64)
+    msk = torch.rand(2, 4 * 9, 9, 11, generator=g, dtype=torch.float64)
+    gy = torch.randn(2, 6, 9, 11, generator=g, dtype=torch.float64)
+    grads = []
+    for fn in (lambda *a: O.modulated_deform_conv(a[0], a[1], a[2], a[3], a[4], padding=1, groups=2, deformable_groups=4),
+               lambda *a: tv.deform_conv2d(a[0], a[1], a[3], a[4], padding=1, mask=a[2])):
+        leaves = [t.clone().requires_grad_(True) for t in (x, off, msk, w, b)]
+        (fn(*leaves) * gy).sum().backward()
+        grads.append([t.grad for t in leaves])
+    for name, a, r in zip(("input", "offset", "mask", "weight", "bias"), *grads):
+        assert (a - r).abs().max().item() <= 1e-10 * max(1.0, r.abs().max().item()), name
