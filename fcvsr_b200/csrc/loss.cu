@@ -1,4 +1,4 @@
-// Charbonnier loss forward (CVSR_train/opt/loss.py:20-31): sum over all elements of sqrt((x - y)^2 + eps), eps = 1e-4,
+// Charbonnier loss forward and backward (CVSR_train/opt/loss.py:20-31): sum over all elements of sqrt((x - y)^2 + eps), eps = 1e-4,
 // with the optional mean_res variant (the per-sample mean of the difference first, :27-29).
 // Two deterministic stages: a fixed grid of blocks accumulates grid-strided partial sums in double precision (the
 // reference's fp32 torch.sum uses pairwise summation; a double accumulator is at least as accurate and order-independent
@@ -86,5 +86,41 @@ extern "C" int fcvsr_charbonnier_loss(const float* x, const float* y, long long 
         charbonnier_partial_kernel<<<CH_BLOCKS, CH_THREADS, 0, st>>>(x, y, (size_t)numel, eps, scratch);
         charbonnier_final_kernel<<<1, 32, 0, st>>>(scratch, out);
     }
+    return fcvsr_launch_status();
+}
+
+// ---- backward: d loss / d x = g * d / sqrt(d^2 + eps) (d = x - y), d loss / d y = -that; with mean_res the per-sample mean
+// m_b (kept in `scratch` by the forward call) gives g * m_b / sqrt(m_b^2 + eps) / per_sample for every element of sample b.
+// `grad_out` is the upstream gradient of the scalar loss, read from the device (no host synchronisation).
+__global__ void __launch_bounds__(CH_THREADS) charbonnier_backward_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                        size_t n, size_t per_sample, int mean_res, float eps,
+                                                                        const float* __restrict__ grad_out,
+                                                                        const double* __restrict__ means, float* __restrict__ gx,
+                                                                        float* __restrict__ gy) {
+    const float g = grad_out[0];
+    for (size_t i = (size_t)blockIdx.x * CH_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * CH_THREADS) {
+        float v;
+        if (mean_res) {
+            const float m = (float)means[i / per_sample];
+            v = g * m / sqrtf(m * m + eps) / (float)per_sample;
+        } else {
+            const float d = x[i] - y[i];
+            v = g * d / sqrtf(d * d + eps);
+        }
+        if (gx) gx[i] = v;
+        if (gy) gy[i] = -v;
+    }
+}
+
+// scratch: the buffer the forward call filled (only read when mean_res); grad_x / grad_y may each be NULL.
+extern "C" int fcvsr_charbonnier_loss_backward(const float* x, const float* y, long long numel, int batch, int mean_res, float eps,
+                                               const float* grad_out, const double* scratch, float* grad_x, float* grad_y,
+                                               cudaStream_t st) {
+    if (!x || !y || !grad_out || numel <= 0 || batch <= 0 || numel % batch || (mean_res && !scratch)) return FCVSR_ERR_ARG;
+    if (!grad_x && !grad_y) return FCVSR_OK;
+    const long long want = (numel + CH_THREADS - 1) / CH_THREADS;
+    const int blocks = (int)(want < 8 * CH_BLOCKS ? want : 8 * CH_BLOCKS);
+    charbonnier_backward_kernel<<<blocks, CH_THREADS, 0, st>>>(x, y, (size_t)numel, (size_t)(numel / batch), mean_res, eps, grad_out,
+                                                               scratch, grad_x, grad_y);
     return fcvsr_launch_status();
 }

@@ -164,13 +164,20 @@ int fcvsr_conv3x3_c64_to1(const void* x_bf16, int ldx, const float* w_host, floa
 int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int W, int op16, cudaStream_t stream);
 int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npix, cudaStream_t stream);
 
-/* ---- training loss forward (CVSR_train/opt/loss.py:20-31) ---------------------------------------- */
+/* ---- training loss (CVSR_train/opt/loss.py:20-31)       ---------------------------------------- */
 
 /* CharbonnierLoss(x, y, mean_res): out[0] = sum sqrt((x - y)^2 + eps) over `numel` fp32 elements, or with mean_res the
  * per-sample mean of x - y first (:27-29; `batch` samples of numel / batch elements).  Deterministic two-stage reduction
  * with double-precision partials; scratch: max(592, batch) doubles; out: one float on the device. */
 int fcvsr_charbonnier_loss(const float* x, const float* y, long long numel, int batch, int mean_res, float eps,
                            double* scratch, float* out, cudaStream_t stream);
+
+/* Backward of CharbonnierLoss: grad_x[i] = grad_out[0] * d / sqrt(d^2 + eps), d = x[i] - y[i]; grad_y = -grad_x (either may be
+ * NULL).  grad_out: the upstream gradient of the scalar loss on the DEVICE.  With mean_res, `scratch` must be the buffer the
+ * forward call filled (it holds the per-sample means).  What autograd derives for opt/loss.py:20-31 in the reference. */
+int fcvsr_charbonnier_loss_backward(const float* x, const float* y, long long numel, int batch, int mean_res, float eps,
+                                    const float* grad_out, const double* scratch, float* grad_x, float* grad_y,
+                                    cudaStream_t stream);
 
 /* ---- deformable convolution operator (CVSR_train/ops/dcn) --------------------------------------- */
 

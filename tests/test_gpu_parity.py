@@ -439,7 +439,7 @@ def test_modulated_dcn_pack_module(dev):
 
 @pytest.mark.parametrize("shape", [(8, 1, 256, 256), (3, 1, 37, 53), (2, 7, 1, 16, 20)])
 def test_charbonnier_loss_matches_oracle(dev, shape):
-    """CharbonnierLoss forward (opt/loss.py:20-31), sum reduction and the mean_res variant; relative 1e-6 (fp32 sum)."""
+    """CharbonnierLoss forward and backward (opt/loss.py:20-31), sum reduction and the mean_res variant; relative 1e-6 (fp32 sum)."""
     from fcvsr_b200.ops.loss import CharbonnierLoss
     g = torch.Generator().manual_seed(sum(shape))
     x, y = torch.rand(*shape, generator=g), torch.rand(*shape, generator=g)
@@ -450,8 +450,18 @@ def test_charbonnier_loss_matches_oracle(dev, shape):
     d = (x - y).double().view(shape[0], -1).mean(1)
     ref_m = torch.sqrt(d * d + 1e-4).sum().item()
     assert abs(got - ref) <= 1e-6 * ref and abs(got_m - ref_m) <= 1e-6 * ref_m
-    with pytest.raises(NotImplementedError):
-        CharbonnierLoss(x.to(dev).requires_grad_(), y.to(dev))
+    # backward (fcvsr_charbonnier_loss_backward) against autograd through the oracle expression, both variants
+    for mean_res in (False, True):
+        xg, yg = x.to(dev).requires_grad_(), y.to(dev).requires_grad_()
+        (3.0 * CharbonnierLoss(xg, yg, mean_res)).backward()
+        xr, yr = x.clone().requires_grad_(), y.clone().requires_grad_()
+        if mean_res:
+            dr = (xr - yr).view(shape[0], -1).mean(1, keepdim=True)
+            (3.0 * torch.sqrt(dr * dr + 1e-4).sum()).backward()
+        else:
+            (3.0 * O.charbonnier_sum(xr, yr)).backward()
+        assert float((xg.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
+        assert float((yg.grad.cpu() - yr.grad).abs().max()) <= 1e-5 * float(yr.grad.abs().max())
 
 
 @pytest.mark.parametrize("variant,b,h,w", [("full", 1, 180, 320), ("S", 2, 96, 128), ("S", 1, 272, 480)])
