@@ -18,12 +18,17 @@
 // (Cin / deformable_groups) % 4 == 0, the deformable group: the sample geometry is computed once per thread and pixel.
 // Derivatives follow dmcn_get_gradient_weight (.cu:499-523) and dmcn_get_coordinate_weight (.cu:526-567): a sample
 // outside (-1, H) x (-1, W) has zero gradient everywhere, out-of-image corners contribute nothing.
+// NHWC fast path (caller passes `scratch`, Cin_g % 4 == 0 and (Cin / deformable_groups) % 4 == 0): the input is transposed to
+// NHWC and grad_input is accumulated in an NHWC buffer, so the four channels a thread owns are ONE 16-byte corner: four
+// float4 loads instead of 16 scalar ones and four `red.global.add.v4.f32` (sm_90+ vector reductions) instead of 16 scalar
+// atomics per (pixel, tap, 4 channels); a transpose-add pass returns grad_input to NCHW.
 // All five outputs ACCUMULATE (the caller zero-fills them, as deform_conv.py:155-159 does with zeros_like).
 #include "common.cuh"
 
 struct DcnBwdArgs {
     const float* x; const float* w; const float* offset; const float* mask; const float* gy;
     float* gx; float* gw; float* goff; float* gmask;
+    const float* xt; float* gxt;     // NHWC copy of x / NHWC accumulator of grad_input (fast path), else NULL
     int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, groups, dg, Ho, Wo;
     long long chunk;             // pixels (of the flattened B*Ho*Wo range) per weight-kernel slice
 };
@@ -54,13 +59,29 @@ __device__ __forceinline__ void dcn_corners(const float* __restrict__ img, int H
     v[3] = (h1 <= H - 1 && w1 <= W - 1) ? img[h1 * W + w1] : 0.f;
 }
 
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// four consecutive channels of the four bilinear corners from the NHWC image `img` (already offset to the first channel)
+__device__ __forceinline__ void dcn_corners4(const float* __restrict__ img, int H, int W, int Cin, const DcnGeo& q, float4 v[4]) {
+    const int h1 = q.h0 + 1, w1 = q.w0 + 1;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    v[0] = (q.h0 >= 0 && q.w0 >= 0) ? __ldg(reinterpret_cast<const float4*>(img + (size_t)(q.h0 * W + q.w0) * Cin)) : z;
+    v[1] = (q.h0 >= 0 && w1 <= W - 1) ? __ldg(reinterpret_cast<const float4*>(img + (size_t)(q.h0 * W + w1) * Cin)) : z;
+    v[2] = (h1 <= H - 1 && q.w0 >= 0) ? __ldg(reinterpret_cast<const float4*>(img + (size_t)(h1 * W + q.w0) * Cin)) : z;
+    v[3] = (h1 <= H - 1 && w1 <= W - 1) ? __ldg(reinterpret_cast<const float4*>(img + (size_t)(h1 * W + w1) * Cin)) : z;
+}
+
 #define DB_TP 64
 #define DB_TK 64
 #define DB_TO 16
 
+template <bool NHWC>
 __global__ void __launch_bounds__(256) dcn_backward_data_kernel(DcnBwdArgs a) {
-    __shared__ float Gs[DB_TO][DB_TP + 4];
-    __shared__ float Ws[DB_TO][DB_TK + 4];
+    __shared__ __align__(16) float Gs[DB_TO][DB_TP + 4];
+    __shared__ __align__(16) float Ws[DB_TO][DB_TK + 4];
     const int tid = threadIdx.x;
     const int P = a.Ho * a.Wo, kk2 = a.kh * a.kw;
     const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups, K = cin_g * kk2;
@@ -109,6 +130,54 @@ __global__ void __launch_bounds__(256) dcn_backward_data_kernel(DcnBwdArgs a) {
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
+    }
+    if (NHWC) {
+        // fast path: the thread's four k' are four consecutive channels of one tap and one deformable group
+        const int kq = k0 + ng * 4;
+        if (kq >= K) return;
+        const int tap = kq / cin_g, cl = kq - tap * cin_g;
+        const int c = grp * cin_g + cl, g = c / ch_per_dg;
+        const size_t img_off = (size_t)b * a.H * a.W * a.Cin + c;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int p = p0 + pg * 4 + i;
+            if (p >= P) continue;
+            const int ho = p / a.Wo, wo = p - ho * a.Wo;
+            DcnGeo q;
+            dcn_geo(a, b, g, tap, p, ho, wo, q);
+            if (!q.valid) continue;
+            const float hh = 1.f - q.lh, hw = 1.f - q.lw;
+            const int h1 = q.h0 + 1, w1 = q.w0 + 1;
+            const float t0 = acc[i][0] * q.m, t1 = acc[i][1] * q.m, t2 = acc[i][2] * q.m, t3 = acc[i][3] * q.m;
+            if (a.gxt) {
+                float* gimg = a.gxt + img_off;
+                float wgt;
+                if (q.h0 >= 0 && q.w0 >= 0) { wgt = hh * hw; red_add_v4(gimg + (size_t)(q.h0 * a.W + q.w0) * a.Cin, t0 * wgt, t1 * wgt, t2 * wgt, t3 * wgt); }
+                if (q.h0 >= 0 && w1 <= a.W - 1) { wgt = hh * q.lw; red_add_v4(gimg + (size_t)(q.h0 * a.W + w1) * a.Cin, t0 * wgt, t1 * wgt, t2 * wgt, t3 * wgt); }
+                if (h1 <= a.H - 1 && q.w0 >= 0) { wgt = q.lh * hw; red_add_v4(gimg + (size_t)(h1 * a.W + q.w0) * a.Cin, t0 * wgt, t1 * wgt, t2 * wgt, t3 * wgt); }
+                if (h1 <= a.H - 1 && w1 <= a.W - 1) { wgt = q.lh * q.lw; red_add_v4(gimg + (size_t)(h1 * a.W + w1) * a.Cin, t0 * wgt, t1 * wgt, t2 * wgt, t3 * wgt); }
+            }
+            if (a.goff || a.gmask) {
+                float4 v[4];
+                dcn_corners4(a.xt + img_off, a.H, a.W, a.Cin, q, v);
+                const float dhx = hw * (v[2].x - v[0].x) + q.lw * (v[3].x - v[1].x), dhy = hw * (v[2].y - v[0].y) + q.lw * (v[3].y - v[1].y);
+                const float dhz = hw * (v[2].z - v[0].z) + q.lw * (v[3].z - v[1].z), dhw = hw * (v[2].w - v[0].w) + q.lw * (v[3].w - v[1].w);
+                const float dwx = hh * (v[1].x - v[0].x) + q.lh * (v[3].x - v[2].x), dwy = hh * (v[1].y - v[0].y) + q.lh * (v[3].y - v[2].y);
+                const float dwz = hh * (v[1].z - v[0].z) + q.lh * (v[3].z - v[2].z), dww = hh * (v[1].w - v[0].w) + q.lh * (v[3].w - v[2].w);
+                const float w00 = hh * hw, w01 = hh * q.lw, w10 = q.lh * hw, w11 = q.lh * q.lw;
+                const float sx = w00 * v[0].x + w01 * v[1].x + w10 * v[2].x + w11 * v[3].x, sy = w00 * v[0].y + w01 * v[1].y + w10 * v[2].y + w11 * v[3].y;
+                const float sz = w00 * v[0].z + w01 * v[1].z + w10 * v[2].z + w11 * v[3].z, sw = w00 * v[0].w + w01 * v[1].w + w10 * v[2].w + w11 * v[3].w;
+                const size_t ob = ((size_t)(b * a.dg + g) * 2 * kk2 + 2 * tap) * P + p;
+                if (a.goff) {
+                    atomicAdd(a.goff + ob, t0 * dhx + t1 * dhy + t2 * dhz + t3 * dhw);
+                    atomicAdd(a.goff + ob + P, t0 * dwx + t1 * dwy + t2 * dwz + t3 * dww);
+                }
+                if (a.gmask)
+                    atomicAdd(a.gmask + ((size_t)(b * a.dg + g) * kk2 + tap) * P + p,
+                              acc[i][0] * sx + acc[i][1] * sy + acc[i][2] * sz + acc[i][3] * sw);
+            }
+        }
+        return;
     }
     // epilogue: adjoint of the modulated bilinear sampling for the thread's 4 pixels x 4 k'
     const size_t HW = (size_t)a.H * a.W;
@@ -167,9 +236,10 @@ __global__ void __launch_bounds__(256) dcn_backward_data_kernel(DcnBwdArgs a) {
 #define DW_TK 64
 #define DW_TP 16
 
+template <bool NHWC>
 __global__ void __launch_bounds__(256) dcn_backward_weight_kernel(DcnBwdArgs a) {
-    __shared__ float Gs[DW_TP][DW_TO + 4];
-    __shared__ float As[DW_TP][DW_TK + 4];
+    __shared__ __align__(16) float Gs[DW_TP][DW_TO + 4];
+    __shared__ __align__(16) float As[DW_TP][DW_TK + 4];
     const int tid = threadIdx.x;
     const int P = a.Ho * a.Wo, kk2 = a.kh * a.kw;
     const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups, K = cin_g * kk2;
@@ -208,6 +278,25 @@ __global__ void __launch_bounds__(256) dcn_backward_weight_kernel(DcnBwdArgs a) 
             const int o = o0 + lq + u;
             Gs[lp][lq + u] = (ok && o < cout_g) ? a.gy[((size_t)b * a.Cout + grp * cout_g + o) * P + p] : 0.f;
         }
+        if (NHWC) {
+            // the sampler's four k' are four consecutive channels of one tap and one deformable group: one geometry, 4 x float4
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && s_tap[0] >= 0) {
+                DcnGeo q;
+                dcn_geo(a, b, s_g[0], s_tap[0], p, ho, wo, q);
+                if (q.valid) {
+                    float4 cv[4];
+                    dcn_corners4(a.xt + (size_t)b * HW * a.Cin + s_c[0], a.H, a.W, a.Cin, q, cv);
+                    const float w00 = (1.f - q.lh) * (1.f - q.lw) * q.m, w01 = (1.f - q.lh) * q.lw * q.m;
+                    const float w10 = q.lh * (1.f - q.lw) * q.m, w11 = q.lh * q.lw * q.m;
+                    o.x = w00 * cv[0].x + w01 * cv[1].x + w10 * cv[2].x + w11 * cv[3].x;
+                    o.y = w00 * cv[0].y + w01 * cv[1].y + w10 * cv[2].y + w11 * cv[3].y;
+                    o.z = w00 * cv[0].z + w01 * cv[1].z + w10 * cv[2].z + w11 * cv[3].z;
+                    o.w = w00 * cv[0].w + w01 * cv[1].w + w10 * cv[2].w + w11 * cv[3].w;
+                }
+            }
+            *reinterpret_cast<float4*>(&As[lp][lq]) = o;
+        } else {
         int cur_tap = -1, cur_g = -1;
         DcnGeo q;
         q.valid = false; q.h0 = q.w0 = 0; q.lh = q.lw = 0.f; q.m = 1.f;
@@ -227,6 +316,7 @@ __global__ void __launch_bounds__(256) dcn_backward_weight_kernel(DcnBwdArgs a) 
                 }
             }
             As[lp][lq + u] = v;
+        }
         }
         __syncthreads();
 #pragma unroll
@@ -277,12 +367,46 @@ __global__ void __launch_bounds__(256) dcn_backward_bias_kernel(const float* __r
     }
 }
 
+// NCHW [B][C][P] -> NHWC [B][P][C] through a 32x33 shared tile (coalesced on both sides)
+__global__ void dcn_bwd_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int P) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* xb = x + (size_t)b * C * P;
+    float* yb = y + (size_t)b * C * P;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < P) ? xb[(size_t)c * P + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        if (p < P && c < C) yb[(size_t)p * C + c] = tile[threadIdx.x][i];
+    }
+}
+
+// grad_input[b][c][p] += gxt[b][p][c]
+__global__ void dcn_bwd_from_nhwc_add_kernel(const float* __restrict__ gxt, float* __restrict__ gx, int C, int P) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* sb = gxt + (size_t)b * C * P;
+    float* db = gx + (size_t)b * C * P;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (p < P && c < C) ? sb[(size_t)p * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < P) db[(size_t)c * P + p] += tile[threadIdx.x][i];
+    }
+}
+
 extern "C" int fcvsr_modulated_deform_conv_backward(const float* input, const float* weight, const float* offset,
                                                     const float* mask, const float* grad_output, float* grad_input,
                                                     float* grad_weight, float* grad_bias, float* grad_offset,
                                                     float* grad_mask, int B, int Cin, int H, int W, int Cout, int kh, int kw,
                                                     int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
-                                                    int groups, int deformable_groups, cudaStream_t st) {
+                                                    int groups, int deformable_groups, float* scratch, cudaStream_t st) {
     if (!input || !weight || !offset || !grad_output) return FCVSR_ERR_ARG;
     if (B <= 0 || groups <= 0 || deformable_groups <= 0 || Cin % groups || Cout % groups || Cin % deformable_groups)
         return FCVSR_ERR_ARG;
@@ -296,10 +420,27 @@ extern "C" int fcvsr_modulated_deform_conv_backward(const float* input, const fl
     a.Wo = (W + 2 * pad_w - (dil_w * (kw - 1) + 1)) / stride_w + 1;
     if (a.Ho <= 0 || a.Wo <= 0) return FCVSR_ERR_ARG;
     a.chunk = 0;
+    a.xt = nullptr; a.gxt = nullptr;
     const int P = a.Ho * a.Wo, cin_g = Cin / groups, cout_g = Cout / groups, K = cin_g * kh * kw;
+    const size_t n_in = (size_t)B * Cin * H * W;
+    const bool nhwc = scratch && !((uintptr_t)scratch & 15) && (cin_g & 3) == 0 && ((Cin / deformable_groups) & 3) == 0;
+    const dim3 tgrid((H * W + 31) / 32, (Cin + 31) / 32, B), tblock(32, 8);
+    if (nhwc) {
+        dcn_bwd_to_nhwc_kernel<<<tgrid, tblock, 0, st>>>(input, scratch, Cin, H * W);
+        a.xt = scratch;
+        if (grad_input) {
+            a.gxt = scratch + n_in;
+            if (cudaMemsetAsync(a.gxt, 0, n_in * sizeof(float), st) != cudaSuccess) return FCVSR_ERR_CUDA;
+        }
+    }
     if (grad_input || grad_offset || grad_mask) {
         dim3 grid((P + DB_TP - 1) / DB_TP, groups * ((K + DB_TK - 1) / DB_TK), B);
-        dcn_backward_data_kernel<<<grid, 256, 0, st>>>(a);
+        if (nhwc) {
+            dcn_backward_data_kernel<true><<<grid, 256, 0, st>>>(a);
+            if (grad_input) dcn_bwd_from_nhwc_add_kernel<<<tgrid, tblock, 0, st>>>(a.gxt, grad_input, Cin, H * W);
+        } else {
+            dcn_backward_data_kernel<false><<<grid, 256, 0, st>>>(a);
+        }
     }
     if (grad_weight) {
         const int tiles = ((K + DW_TK - 1) / DW_TK) * groups * ((cout_g + DW_TO - 1) / DW_TO);
@@ -313,7 +454,8 @@ extern "C" int fcvsr_modulated_deform_conv_backward(const float* input, const fl
         nsplit = (total + chunk - 1) / chunk;
         a.chunk = chunk;
         dim3 grid((K + DW_TK - 1) / DW_TK, groups * ((cout_g + DW_TO - 1) / DW_TO), (unsigned)nsplit);
-        dcn_backward_weight_kernel<<<grid, 256, 0, st>>>(a);
+        if (nhwc) dcn_backward_weight_kernel<true><<<grid, 256, 0, st>>>(a);
+        else dcn_backward_weight_kernel<false><<<grid, 256, 0, st>>>(a);
     }
     if (grad_bias) dcn_backward_bias_kernel<<<Cout, 256, 0, st>>>(grad_output, grad_bias, B, Cout, P);
     return fcvsr_launch_status();

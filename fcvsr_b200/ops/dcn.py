@@ -57,6 +57,7 @@ def _out_hw(h, w, kh, kw, stride, padding, dilation):
 # tcgen05 with TF32-rounded operands and fp32 accumulation (csrc/dcn_tc.cu, |error| <~ 1e-3 of the output scale, the same
 # contract as the model's "tf32" mode); everything else, and everything under "fp32", runs the exact CUDA-core kernel.
 PRECISION = "tf32"
+BACKWARD_NHWC = True      # backward: NHWC scratch copies + red.global.add.v4.f32 when the channel counts allow (dcn_bwd.cu)
 
 
 def _launch(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg, off_bs=0, mask_bs=0, sigmoid=0):
@@ -96,10 +97,12 @@ def _backward(x, offset, mask, weight, grad_out, stride, padding, dilation, grou
     gw = torch.zeros_like(weight) if need[3] else None
     gb = x.new_zeros(cout) if with_bias else None
     ptr = lambda t: t.data_ptr() if t is not None else 0  # noqa: E731
+    fast = BACKWARD_NHWC and (cin // groups) % 4 == 0 and (cin // dg) % 4 == 0
+    scratch = x.new_empty(2 * x.numel()) if fast else None      # NHWC copies of input / grad_input (vector reductions)
     with torch.cuda.device(x.device):
         C.call("fcvsr_modulated_deform_conv_backward", x.data_ptr(), weight.data_ptr(), offset.data_ptr(), ptr(mask),
                grad_out.data_ptr(), ptr(gx), ptr(gw), ptr(gb), ptr(goff), ptr(gmask), b, cin, h, w, cout, kh, kw,
-               stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], groups, dg,
+               stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], groups, dg, ptr(scratch),
                torch.cuda.current_stream().cuda_stream)
     return gx, goff, gmask, gw, gb
 

@@ -215,12 +215,14 @@ int fcvsr_modulated_deform_conv_forward_tc(const float* input, const float* weig
  * so the caller zero-fills them first (as deform_conv.py:155-159 does with zeros_like).  grad_input [B,Cin,H,W],
  * grad_weight [Cout,Cin/groups,kh,kw], grad_bias [Cout], grad_offset / grad_mask dense, shaped like offset / mask.
  * grad_input, grad_offset, grad_mask and grad_weight are combined with fp32 atomics (as the reference's col2im is):
- * run-to-run differences are at rounding level. */
+ * run-to-run differences are at rounding level.  scratch: NULL, or 2*B*Cin*H*W floats (16-byte aligned) that enable the
+ * NHWC fast path for (Cin/groups) % 4 == 0 and (Cin/deformable_groups) % 4 == 0: 16-byte corner loads and vector
+ * reductions (red.global.add.v4.f32) on an NHWC copy of input / grad_input. */
 int fcvsr_modulated_deform_conv_backward(const float* input, const float* weight, const float* offset, const float* mask,
                                          const float* grad_output, float* grad_input, float* grad_weight, float* grad_bias,
                                          float* grad_offset, float* grad_mask, int B, int Cin, int H, int W, int Cout,
                                          int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h,
-                                         int dil_w, int groups, int deformable_groups, cudaStream_t stream);
+                                         int dil_w, int groups, int deformable_groups, float* scratch, cudaStream_t stream);
 
 /* library / build info: returns a static string "fcvsr_b200 <version> sm_100a" */
 const char* fcvsr_version(void);

@@ -287,12 +287,14 @@ def test_modulated_dcn_matches_oracle(dev, cfg, monkeypatch):
                                  dict(B=1, cin=4, cout=4, H=12, W=10, k=5, g=1, dg=4, pad=4, stride=1, dil=2, mask=True),
                                  dict(B=3, cin=6, cout=10, H=14, W=13, k=3, g=1, dg=2, pad=1, stride=1, dil=1, mask=True),
                                  dict(B=2, cin=12, cout=72, H=11, W=17, k=3, g=1, dg=1, pad=0, stride=1, dil=1, mask=False),
-                                 dict(B=1, cin=2, cout=1, H=4, W=4, k=3, g=1, dg=2, pad=1, stride=1, dil=1, mask=False)])
+                                 dict(B=1, cin=2, cout=1, H=4, W=4, k=3, g=1, dg=2, pad=1, stride=1, dil=1, mask=False),
+                                 dict(B=2, cin=16, cout=12, H=15, W=18, k=3, g=2, dg=2, pad=2, stride=2, dil=2, mask=True)])
 def test_dcn_backward_matches_oracle(dev, cfg, monkeypatch):
     """fcvsr_modulated_deform_conv_backward (dcn_bwd.cu) through the autograd Functions of ops.dcn against autograd through
     the CPU oracle (pinned to torchvision's deform_conv2d backward in tests/test_oracle.py): all five gradients, groups,
-    stride / dilation, ragged tiles, deformable-group widths 1, 2, 3, 4 and 12, DCNv1 (no mask).  fp32 with atomics:
-    max-abs <= 2e-4 of each gradient's scale."""
+    stride / dilation, ragged tiles, deformable-group widths 1, 2, 3, 4, 8 and 12, DCNv1 (no mask); shapes with
+    (Cin/groups) % 4 == 0 and (Cin/dg) % 4 == 0 take the NHWC vector-reduction path, and are run on the scalar NCHW path as
+    well.  fp32 with atomics: max-abs <= 2e-4 of each gradient's scale."""
     import fcvsr_b200.ops.dcn as dcn_mod
     monkeypatch.setattr(dcn_mod, "PRECISION", "fp32")
     g = torch.Generator().manual_seed(cfg["H"] * cfg["W"] + 7)
@@ -320,11 +322,15 @@ def test_dcn_backward_matches_oracle(dev, cfg, monkeypatch):
          * gy).sum().backward()
         gpu = [t.to(dev).requires_grad_(True) for t in (x, off, w)]
         y = dcn_mod.deform_conv(gpu[0], gpu[1], gpu[2], cfg["stride"], cfg["pad"], cfg["dil"], cfg["g"], dg, 64)
-    (y * gy.to(dev)).sum().backward()
-    torch.cuda.synchronize()
-    for name, a, r in zip(names, gpu, cpu):
-        err = float((a.grad.cpu() - r.grad).abs().max())
-        assert err <= 2e-4 * max(1.0, float(r.grad.abs().max())), (name, err)
+    for fast in (True, False):
+        monkeypatch.setattr(dcn_mod, "BACKWARD_NHWC", fast)
+        for t in gpu:
+            t.grad = None
+        (y * gy.to(dev)).sum().backward(retain_graph=True)
+        torch.cuda.synchronize()
+        for name, a, r in zip(names, gpu, cpu):
+            err = float((a.grad.cpu() - r.grad).abs().max())
+            assert err <= 2e-4 * max(1.0, float(r.grad.abs().max())), (name, fast, err)
 
 
 def test_dcn_backward_partial_needs_and_module(dev, monkeypatch):

@@ -36,11 +36,13 @@ for (B, H, W) in ((1, 180, 320), (4, 180, 320)):
 
     def run(gx_, gw_, gb_, goff_, gm_):
         C.call("fcvsr_modulated_deform_conv_backward", x.data_ptr(), w.data_ptr(), off.data_ptr(), msk.data_ptr(),
-               gy.data_ptr(), gx_, gw_, gb_, goff_, gm_, B, 64, H, W, 64, 3, 3, 1, 1, 1, 1, 1, 1, 1, 16, st)
+               gy.data_ptr(), gx_, gw_, gb_, goff_, gm_, B, 64, H, W, 64, 3, 3, 1, 1, 1, 1, 1, 1, 1, 16, SCR, st)
 
     fl = 2.0 * B * H * W * 64 * 64 * 9
-    t_data = timed(lambda: run(gx.data_ptr(), 0, 0, goff.data_ptr(), gm.data_ptr()))
-    t_w = timed(lambda: run(0, gw.data_ptr(), 0, 0, 0))
-    t_b = timed(lambda: run(0, 0, gb.data_ptr(), 0, 0))
-    print(f"DCN backward B{B} 64->64 3x3 dg16 {H}x{W}: data {t_data:8.1f} us ({fl / t_data / 1e6:5.2f} TFLOP/s)  "
-          f"weight {t_w:8.1f} us ({fl / t_w / 1e6:5.2f} TFLOP/s)  bias {t_b:6.1f} us")
+    scratch = torch.empty(2 * x.numel(), device=dev)
+    for SCR, tag in ((0, "NCHW scalar atomics"), (scratch.data_ptr(), "NHWC + red.v4")):
+      t_data = timed(lambda: run(gx.data_ptr(), 0, 0, goff.data_ptr(), gm.data_ptr()))
+      t_w = timed(lambda: run(0, gw.data_ptr(), 0, 0, 0))
+      t_b = timed(lambda: run(0, 0, gb.data_ptr(), 0, 0))
+      print(f"DCN backward [{tag}] B{B} 64->64 3x3 dg16 {H}x{W}: data {t_data:8.1f} us ({fl / t_data / 1e6:5.2f} TFLOP/s)  "
+            f"weight {t_w:8.1f} us ({fl / t_w / 1e6:5.2f} TFLOP/s)  bias {t_b:6.1f} us")
