@@ -40,6 +40,7 @@ SIGNATURES = {
     "fcvsr_bilinear_up4": "p l p iii s",
     "fcvsr_fill_channels": "p iii f l s",
     "fcvsr_pack_clip": "p p iiii i s",
+    "fcvsr_subsample2": "pi pi pi iiii i s",
     "fcvsr_conv3x3_c64_to1": "pi p f p p iii s",
     "fcvsr_charbonnier_loss": "pp li i f pp s",
     "fcvsr_charbonnier_loss_backward": "pp li i f pp pp s",

@@ -37,11 +37,12 @@ __global__ void __launch_bounds__(CH_THREADS) charbonnier_partial_kernel(const f
 }
 
 __global__ void charbonnier_final_kernel(const double* __restrict__ partial, float* __restrict__ out) {
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < CH_BLOCKS; ++i) s += partial[i];
-        out[0] = (float)s;
-    }
+    // one warp, fixed order: lane l sums partial[l], partial[l + 32], ... and the lanes are combined by a shuffle tree
+    double s = 0.0;
+    for (int i = threadIdx.x; i < CH_BLOCKS; i += 32) s += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = (float)s;
 }
 
 // mean_res: one block per sample reduces mean(x - y), then the loss is sum_b sqrt(mean_b^2 + eps)

@@ -180,3 +180,34 @@ extern "C" int fcvsr_conv3x3_c64_to1(const void* x, int ldx, const float* w_host
     conv3x3_c64_to1_kernel<<<grid, L1_THREADS, smem, st>>>(p);
     return fcvsr_launch_status();
 }
+
+// ---- stride-2 3x3 convolutions of the pyramid (rconcat1/2, CVSR_freq.py:2671-2672, :2735-2736) on the tensor cores -------
+// A stride-2, pad-1 3x3 convolution is the stride-1 convolution sampled at the even pixels: the stride-1 tcgen05 kernel
+// produces the full-resolution map (4x the useful FLOPs at ~40x the CUDA-core kernel's rate) and this pass keeps
+// y[b, i, j, :] = x[b, 2i, 2j, :], writing the fp32 stream and its operand-typed copy.  One thread per 4 channels.
+__global__ void subsample2_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, void* __restrict__ y2,
+                                  int ldy2, int H, int W, int c4, size_t total, int op16) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int c = (int)(e % c4) * 4;
+    size_t px = e / c4;
+    const int Wo = W >> 1, Ho = H >> 1;
+    const int j = (int)(px % Wo);
+    px /= Wo;
+    const int i = (int)(px % Ho), b = (int)(px / Ho);
+    const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)b * H + 2 * i) * W + 2 * j) * ldx + c);
+    const size_t o = ((size_t)b * Ho + i) * Wo + j;
+    if (y) *reinterpret_cast<float4*>(y + o * ldy + c) = v;
+    if (y2) store_operand4(y2, o * ldy2 + c, v, op16);
+}
+
+// x: fp32 NHWC [B,H,W,ldx] (H, W even, C % 4 == 0 channels used); y: fp32 [B,H/2,W/2,ldy] or NULL; y2: operand-typed copy
+// (TF32-rounded fp32 or bf16) [B,H/2,W/2,ldy2] or NULL.
+extern "C" int fcvsr_subsample2(const float* x, int ldx, float* y, int ldy, void* y2, int ldy2, int B, int H, int W, int C,
+                                int op16, cudaStream_t st) {
+    if (!x || (!y && !y2) || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || (C & 3) || (ldx & 3) || (ldy & 3) || (ldy2 & 3))
+        return FCVSR_ERR_ARG;
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 4);
+    subsample2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, ldx, y, ldy, y2, ldy2, H, W, C / 4, total, op16);
+    return fcvsr_launch_status();
+}

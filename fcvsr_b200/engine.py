@@ -121,6 +121,7 @@ class Engine:
         self._ksplit = {}
         self.max_ctas = 0            # grid cap of the tensor-core convs on the current stream (0 = all SMs)
         self.multi_stream = True     # run the three pyramid levels of SCNetbk on three streams
+        self.tc_pyramid = os.environ.get("FCVSR_TC_PYRAMID", "1") != "0"   # rconcat1/2 as stride-1 tcgen05 convs + sampling
         self.use_last_kernel = os.environ.get("FCVSR_LAST_KERNEL", "1") != "0"   # dedicated Cout = 1 kernel (bf16 mode)
         self._streams = {}
         self.profile = None          # optional list: (kind, flops, start_event, end_event) per conv launch
@@ -195,6 +196,9 @@ class Engine:
         P["mffr.w2"] = sd["MFFRblock.ca.conv_du.2.weight"].reshape(n, 4).contiguous()
         P["rc1"] = cp("rconcat1", stride=2)
         P["rc2"] = cp("rconcat2", stride=2)
+        # tensor-core path: the same weights as stride-1 convolutions, sampled at the even pixels afterwards (tail.cu)
+        P["rc1_s1"] = cp("rconcat1")
+        P["rc2_s1"] = cp("rconcat2")
         # --- SCNetbk (:705-822) ---
         for g in range(m.SCGroupN):
             P[f"g{g}.conv"] = cp(f"recorb1.body.{g}.conv")
@@ -514,8 +518,16 @@ class Engine:
         self._mffr(ws, p, B, H, W)                                   # m2 -> xs0 (+ operand copy xsr0)
         if stop == "mffr":
             return
-        self._conv(P["rc1"], p["xs0"], 64, p["xs1"], 64, B, H, W, y2=p["xsr1"], ldy2=64)                  # :2735
-        self._conv(P["rc2"], p["xs1"], 64, p["xs2"], 64, B, H // 2, W // 2, y2=p["xsr2"], ldy2=64)        # :2736
+        if self.use_tc and self.tc_pyramid:
+            # stride 2 = stride 1 on the tensor cores + even-pixel sampling; t0 / t1 are free until SCNetbk starts
+            O16 = int(self.op16)
+            self._conv(P["rc1_s1"], p["xsr0"], 64, p["t0"], 64, B, H, W)                                      # :2735
+            self._k("fcvsr_subsample2", p["t0"], 64, p["xs1"], 64, p["xsr1"], 64, B, H, W, 64, O16)
+            self._conv(P["rc2_s1"], p["xsr1"], 64, p["t1"], 64, B, H // 2, W // 2)                            # :2736
+            self._k("fcvsr_subsample2", p["t1"], 64, p["xs2"], 64, p["xsr2"], 64, B, H // 2, W // 2, 64, O16)
+        else:
+            self._conv(P["rc1"], p["xs0"], 64, p["xs1"], 64, B, H, W, y2=p["xsr1"], ldy2=64)                  # :2735
+            self._conv(P["rc2"], p["xs1"], 64, p["xs2"], 64, B, H // 2, W // 2, y2=p["xsr2"], ldy2=64)        # :2736
         self._scnet(ws, p, B, H, W)
         if stop == "scnet":
             return

@@ -160,6 +160,10 @@ int fcvsr_bilinear_up4(const float* in, long long bstride, float* out, int B, in
  * the weights travel in the kernel parameter space.  CUDA cores: the tensor-core path needs an N = 16 MMA for one column. */
 int fcvsr_conv3x3_c64_to1(const void* x_bf16, int ldx, const float* w_host, float bias, const float* res, float* y, int B,
                           int H, int W, cudaStream_t stream);
+/* y[b,i,j,0:C] = x[b,2i,2j,0:C] (fp32 NHWC, H and W even, C % 4 == 0) plus an optional operand-typed copy y2: turns the
+ * stride-1 tensor-core convolution into the stride-2 rconcat1/2 of the pyramid (CVSR_freq.py:2671-2672, :2735-2736). */
+int fcvsr_subsample2(const float* x, int ldx, float* y, int ldy, void* y2, int ldy2, int B, int H, int W, int C, int op16,
+                     cudaStream_t stream);
 /* NCHW clip [B,T,H,W] -> NHWC [B,H,W,32] (channels >= T zero, TF32-rounded): tensor-core operand of feat_extract */
 int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int W, int op16, cudaStream_t stream);
 int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npix, cudaStream_t stream);
