@@ -248,6 +248,7 @@ struct IacArgs {
     const float* offs; int ldoffs; int offs_ch[2];   // channel of dx for each direction
     const float* taps; int ldtaps;                   // already offset to this iteration's 192 channels
     int B, H, W; int round_out;      // 0 fp32, 1 TF32-rounded fp32, 2 bf16 (next[] is then a bf16 tensor)
+    int prev16;                      // prev[] are bf16 tensors (ld in elements): the IAC ping-pong of the bf16 mode
 };
 
 #define IAC_THREADS 512
@@ -275,6 +276,11 @@ template <> struct IacTap<false> {
     }
     __device__ __forceinline__ float4 get() const { return r; }
 };
+
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 u) {
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                       __uint_as_float(u.y & 0xffff0000u));
+}
 
 template <bool HALF>
 __global__ void __launch_bounds__(IAC_THREADS, HALF ? 2 : 1) iac_step_kernel(IacArgs a) {
@@ -334,18 +340,34 @@ __global__ void __launch_bounds__(IAC_THREADS, HALF ? 2 : 1) iac_step_kernel(Iac
     __syncthreads();
     // phase 1: warped samples, two halo pixels (8 independent 16-byte gathers) in flight per thread
     const float* pbase = prev + img * ldp + c0;
+    const unsigned short* pbase16 = reinterpret_cast<const unsigned short*>(prev) + img * ldp + c0;
+    const bool p16 = a.prev16 != 0;
     for (int hp = hw; hp < IAC_HALO; hp += 2 * IAC_HW) {
         const int hp2 = min(hp + IAC_HW, IAC_HALO - 1);
         const int4 i0 = geo_i[hp], i1 = geo_i[hp2];
         const float4 w0 = geo_w[hp], w1 = geo_w[hp2];
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.x * ldp));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.y * ldp));
-        const float4 a2 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.z * ldp));
-        const float4 a3 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.w * ldp));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.x * ldp));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.y * ldp));
-        const float4 b2 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.z * ldp));
-        const float4 b3 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.w * ldp));
+        float4 a0, a1, a2, a3, b0, b1, b2, b3;
+        if (p16) {          // 8-byte gathers of 4 bf16 channels
+            const uint2 u0 = __ldg(reinterpret_cast<const uint2*>(pbase16 + (size_t)i0.x * ldp));
+            const uint2 u1 = __ldg(reinterpret_cast<const uint2*>(pbase16 + (size_t)i0.y * ldp));
+            const uint2 u2 = __ldg(reinterpret_cast<const uint2*>(pbase16 + (size_t)i0.z * ldp));
+            const uint2 u3 = __ldg(reinterpret_cast<const uint2*>(pbase16 + (size_t)i0.w * ldp));
+            const uint2 v0 = __ldg(reinterpret_cast<const uint2*>(pbase16 + (size_t)i1.x * ldp));
+            const uint2 v1 = __ldg(reinterpret_cast<const uint2*>(pbase16 + (size_t)i1.y * ldp));
+            const uint2 v2 = __ldg(reinterpret_cast<const uint2*>(pbase16 + (size_t)i1.z * ldp));
+            const uint2 v3 = __ldg(reinterpret_cast<const uint2*>(pbase16 + (size_t)i1.w * ldp));
+            a0 = bf16x4_to_float4(u0); a1 = bf16x4_to_float4(u1); a2 = bf16x4_to_float4(u2); a3 = bf16x4_to_float4(u3);
+            b0 = bf16x4_to_float4(v0); b1 = bf16x4_to_float4(v1); b2 = bf16x4_to_float4(v2); b3 = bf16x4_to_float4(v3);
+        } else {
+            a0 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.x * ldp));
+            a1 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.y * ldp));
+            a2 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.z * ldp));
+            a3 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i0.w * ldp));
+            b0 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.x * ldp));
+            b1 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.y * ldp));
+            b2 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.z * ldp));
+            b3 = __ldg(reinterpret_cast<const float4*>(pbase + (size_t)i1.w * ldp));
+        }
         // same accumulation order as before (corner 00, 01, 10, 11 with fmaf): bit-identical samples
         float4 s0, s1;
         s0.x = fmaf(w0.w, a3.x, fmaf(w0.z, a2.x, fmaf(w0.y, a1.x, w0.x * a0.x)));
@@ -432,7 +454,7 @@ extern "C" int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* pr
     a.xin[0] = xin_f; a.xin[1] = xin_b; a.ldxin[0] = ldxin_f; a.ldxin[1] = ldxin_b;
     a.next[0] = next_f; a.next[1] = next_b; a.ldnext[0] = ldnext_f; a.ldnext[1] = ldnext_b;
     a.offs = offs; a.ldoffs = ldoffs; a.offs_ch[0] = ch_f; a.offs_ch[1] = ch_b;
-    a.taps = taps; a.ldtaps = ldtaps; a.B = B; a.H = H; a.W = W; a.round_out = round_out;
+    a.taps = taps; a.ldtaps = ldtaps; a.B = B; a.H = H; a.W = W; a.round_out = round_out & 3; a.prev16 = (round_out >> 2) & 1;
     const size_t smem = (IAC_HALO + IAC_TH * (IAC_TW + 2)) * IAC_C * sizeof(float) + IAC_HALO * (sizeof(int4) + sizeof(float4));
     static bool attr_set = false;
     if (!attr_set) {

@@ -122,6 +122,7 @@ class Engine:
         self.max_ctas = 0            # grid cap of the tensor-core convs on the current stream (0 = all SMs)
         self.multi_stream = True     # run the three pyramid levels of SCNetbk on three streams
         self.tc_pyramid = os.environ.get("FCVSR_TC_PYRAMID", "1") != "0"   # rconcat1/2 as stride-1 tcgen05 convs + sampling
+        self.iac16 = os.environ.get("FCVSR_IAC16", "1") != "0"      # IAC ping-pong tensors in bf16 (bf16 mode only)
         self.use_last_kernel = os.environ.get("FCVSR_LAST_KERNEL", "1") != "0"   # dedicated Cout = 1 kernel (bf16 mode)
         self._streams = {}
         self.profile = None          # optional list: (kind, flops, start_event, end_event) per conv launch
@@ -591,14 +592,16 @@ class Engine:
         ping = p["ping"]
         sz = B * H * W * 64 * 4
         prev_f, ldpf, prev_b, ldpb = src, lds, src + 128 * 4, lds
+        iac16 = bool(O16) and self.iac16       # bf16 mode: the intermediate iterations ping-pong through bf16 tensors
         for i in range(A):
             if i == A - 1:
                 nf, nb, ldn = p["cat128"], p["cat128"] + 64 * (E if R else 4), 128
             else:
                 nf, nb, ldn = ping + (i % 2) * 2 * sz, ping + ((i % 2) * 2 + 1) * sz, 64
+            ro = (2 if O16 else R) if i == A - 1 else (2 if iac16 else 0)     # + 4: prev is a bf16 ping buffer
             self._k("fcvsr_iac_step", prev_f, ldpf, prev_b, ldpb, src, lds, src + 128 * 4, lds, nf, ldn, nb, ldn,
                     p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["pk"] + i * 192 * TE, A * 192, R, B, H, W,
-                    (2 if O16 else R) if i == A - 1 else 0)
+                    ro | (4 if (iac16 and i > 0) else 0))
             prev_f, ldpf, prev_b, ldpb = nf, ldn, nb, ldn
         # conv3(cat) + x2 (:1529)
         self._conv(P["conv3"], p["cat128"], 128, dst, ldd, B, H, W, res=src + 64 * 4, ldres=lds)

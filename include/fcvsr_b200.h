@@ -110,7 +110,8 @@ int fcvsr_offset_blocks(const float* off, const float* w1, const float* w2, cons
 /* One IAC iteration (:1230-1250 = flow_warp :1188-1227 + SAC :1253-1276 + residual + LeakyReLU 0.1) for
  * the forward (f) and backward (b) neighbour, 64 channels.  offs [B,H,W,ldoffs]: (dx,dy) at channel
  * ch_f / ch_b.  taps [B,H,W,ldtaps]: 192 channels [t][c] of this iteration (fp16 when taps_half = 1).
- * round_out: 0 fp32 outputs, 1 TF32-rounded fp32, 2 bf16 (next_* are then bf16 tensors). */
+ * round_out: 0 fp32 outputs, 1 TF32-rounded fp32, 2 bf16 (next_* are then bf16 tensors); + 4: prev_* are bf16 tensors
+ * (ld in elements) -- the ping-pong between iterations of the bf16 mode. */
 int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int ldprev_b, const float* xin_f,
                    int ldxin_f, const float* xin_b, int ldxin_b, float* next_f, int ldnext_f, float* next_b,
                    int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps, int ldtaps,
