@@ -33,8 +33,8 @@ SIGNATURES = {
     "fcvsr_reduce_finalize": "p ii f i pp p i s",
     "fcvsr_divenh_step": "ppppp i ii pppp ppp ii s",
     "fcvsr_mffr_final": "pp pi pi ii s",
-    "fcvsr_context_block": "pi ppp pp ii s",
-    "fcvsr_rcb_finish": "ppp p ii p i p ii i s",
+    "fcvsr_context_block": "pi ppp pp ii i s",
+    "fcvsr_rcb_finish": "ppp p ii p i p ii i i s",
     "fcvsr_level_mix": "pi pi p f pp iii pi i i i s",
     "fcvsr_pixel_shuffle": "pi pi iiii i s",
     "fcvsr_bilinear_up4": "p l p iii s",

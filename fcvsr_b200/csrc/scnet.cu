@@ -10,6 +10,16 @@
 //                                bilinear, align_corners=False; td/tu are the 1x1 down/up conv outputs)
 #include "common.cuh"
 
+// 4 consecutive channels at element index idx of an fp32 tensor, or of a bf16 tensor (b16) with the same element indexing
+__device__ __forceinline__ float4 load4_any(const void* base, size_t idx, int b16) {
+    if (b16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(base) + idx);
+        return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                           __uint_as_float(u.y & 0xffff0000u));
+    }
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+}
+
 #define CTX_PIX_PER_BLOCK 128
 #define CTX_STRIDE 66          // m, z, acc[64]
 
@@ -17,7 +27,7 @@
 // pixel is one coalesced 256-byte load and its logit one 5-step shuffle reduction).
 __global__ void __launch_bounds__(256) ctx_partial_kernel(const float* __restrict__ x, int ldx,
                                                           const float* __restrict__ wmask, float* __restrict__ partial,
-                                                          int P, int ppb) {
+                                                          int P, int ppb, int x16) {
     __shared__ float sm_m[8], sm_z[8];
     __shared__ float sm_acc[8][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, c = 2 * lane;
@@ -26,13 +36,18 @@ __global__ void __launch_bounds__(256) ctx_partial_kernel(const float* __restric
     float2 acc = make_float2(0.f, 0.f);
     const int p0 = blockIdx.x * ppb + warp * (ppb >> 3);        // ppb pixels per block (multiple of 128), 1/8 per warp
     const float* xb = x + (size_t)b * P * ldx + c;
+    const unsigned short* xb16 = reinterpret_cast<const unsigned short*>(x) + (size_t)b * P * ldx + c;   // x16: bf16 tensor
     for (int it = 0; it < (ppb >> 5); ++it) {
         float2 v[4];
         float lg[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int p = p0 + it * 4 + u;
-            v[u] = p < P ? *reinterpret_cast<const float2*>(xb + (size_t)p * ldx) : make_float2(0.f, 0.f);
+            if (p >= P) v[u] = make_float2(0.f, 0.f);
+            else if (x16) {
+                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(xb16 + (size_t)p * ldx);
+                v[u] = make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u));
+            } else v[u] = *reinterpret_cast<const float2*>(xb + (size_t)p * ldx);
             lg[u] = v[u].x * w.x + v[u].y * w.y;
         }
 #pragma unroll
@@ -145,27 +160,27 @@ __global__ void __launch_bounds__(1024) ctx_finalize_kernel(const float* __restr
     }
 }
 
-extern "C" int fcvsr_context_block(const float* x, int ldx, const float* wmask, const float* w1, const float* w2,
-                                   float* partial, float* add, int B, int P, cudaStream_t st) {
+extern "C" int fcvsr_context_block(const void* x, int ldx, const float* wmask, const float* w1, const float* w2,
+                                   float* partial, float* add, int B, int P, int x_bf16, cudaStream_t st) {
     if (!x || !wmask || !w1 || !w2 || !partial || !add || (ldx & 1)) return FCVSR_ERR_ARG;
     // 128 pixels per block (as sized by the caller's `partial` buffer) unless that needs more than CTX_MAX_NBLK blocks
     int ppb = CTX_PIX_PER_BLOCK;
     while ((P + ppb - 1) / ppb > CTX_MAX_NBLK) ppb += CTX_PIX_PER_BLOCK;
     const int nblk = (P + ppb - 1) / ppb;
-    ctx_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(x, ldx, wmask, partial, P, ppb);
+    ctx_partial_kernel<<<dim3(nblk, B), 256, 0, st>>>(reinterpret_cast<const float*>(x), ldx, wmask, partial, P, ppb, x_bf16);
     ctx_finalize_kernel<<<B, 1024, 0, st>>>(partial, nblk, w1, w2, add);
     return fcvsr_launch_status();
 }
 
 // r = lrelu_0.2(res + add[b]) + r0     (all 64 channels, float4 per thread)
-__global__ void rcb_finish_kernel(const float* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
-                                  float* __restrict__ r, int P, size_t total4, void* __restrict__ r_op, int op16) {
+__global__ void rcb_finish_kernel(const void* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
+                                  float* __restrict__ r, int P, size_t total4, void* __restrict__ r_op, int op16, int res16) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)(i & 15) * 4;
     const size_t pix = i >> 4;
     const int b = (int)(pix / P);
-    const float4 v = *reinterpret_cast<const float4*>(res + pix * 64 + c);
+    const float4 v = load4_any(res, pix * 64 + c, res16);
     const float4 a = *reinterpret_cast<const float4*>(add + (size_t)b * 64 + c);
     const float4 q = *reinterpret_cast<const float4*>(r0 + pix * 64 + c);
     float4 o;
@@ -182,9 +197,9 @@ __global__ void rcb_finish_kernel(const float* __restrict__ res, const float* __
 // commutes with the 2x2 average that follows it in the reference (:753-757, Interpolate(0.5) of an even-sized map),
 // so it runs on this pooled tensor at a quarter of the pixels.  pool_plain: store the mean as plain fp32 (exact mode)
 // instead of the operand type.
-__global__ void rcb_finish_pool_kernel(const float* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
+__global__ void rcb_finish_pool_kernel(const void* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
                                        float* __restrict__ r, int H, int W, size_t total, void* __restrict__ r_op, int op16,
-                                       void* __restrict__ r_pool, int pool_plain) {
+                                       void* __restrict__ r_pool, int pool_plain, int res16) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = (int)(i & 15) * 4;
@@ -197,7 +212,7 @@ __global__ void rcb_finish_pool_kernel(const float* __restrict__ res, const floa
     float4 v[4], q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        v[k] = *reinterpret_cast<const float4*>(res + pix[k] * 64 + c);
+        v[k] = load4_any(res, pix[k] * 64 + c, res16);
         q[k] = *reinterpret_cast<const float4*>(r0 + pix[k] * 64 + c);
     }
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -218,18 +233,18 @@ __global__ void rcb_finish_pool_kernel(const float* __restrict__ res, const floa
     else store_operand4(r_pool, quad * 64 + c, m, op16);
 }
 
-extern "C" int fcvsr_rcb_finish(const float* res, const float* add, const float* r0, float* r, int B, int P,
-                                void* r_op, int op16, void* r_pool, int H, int W, int pool_plain, cudaStream_t st) {
+extern "C" int fcvsr_rcb_finish(const void* res, const float* add, const float* r0, float* r, int B, int P,
+                                void* r_op, int op16, void* r_pool, int H, int W, int pool_plain, int res_bf16, cudaStream_t st) {
     if (!res || !add || !r0 || !r) return FCVSR_ERR_ARG;
     if (r_pool) {
         if (H <= 0 || W <= 0 || ((H | W) & 1) || (size_t)H * W != (size_t)P) return FCVSR_ERR_ARG;
         const size_t total = (size_t)B * (P / 4) * 16;
         rcb_finish_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(res, add, r0, r, H, W, total, r_op, op16, r_pool,
-                                                                              pool_plain);
+                                                                              pool_plain, res_bf16);
         return fcvsr_launch_status();
     }
     const size_t total4 = (size_t)B * P * 16;
-    rcb_finish_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(res, add, r0, r, P, total4, r_op, op16);
+    rcb_finish_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(res, add, r0, r, P, total4, r_op, op16, res_bf16);
     return fcvsr_launch_status();
 }
 

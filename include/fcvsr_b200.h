@@ -138,14 +138,16 @@ int fcvsr_mffr_final(const float* so, const float* gate, const float* x, int ldx
 
 /* ---- SCNetbk helpers (CVSR_freq.py:657-777) ----------------------------------------------------- */
 
-/* ContextBlock (:657-701): add[b][64] = W2 lrelu_0.2(W1 softmax-pool(x)); partial [B][ceil(P/128)][66] */
-int fcvsr_context_block(const float* x, int ldx, const float* wmask, const float* w1, const float* w2,
-                        float* partial, float* add, int B, int P, cudaStream_t stream);
+/* ContextBlock (:657-701): add[b][64] = W2 lrelu_0.2(W1 softmax-pool(x)); partial [B][ceil(P/128)][66].
+ * x_bf16 = 1: x is a bf16 tensor (ld in elements) -- the bf16 mode stores the RCB's second conv output that way. */
+int fcvsr_context_block(const void* x, int ldx, const float* wmask, const float* w1, const float* w2,
+                        float* partial, float* add, int B, int P, int x_bf16, cudaStream_t stream);
 /* RCB tail (:720-724): r = lrelu_0.2(res + add[b]) + r0 (64 ch, ld 64).  r_pool (optional, needs even H, W with
  * H*W == P): 2x2 mean of r, [B,H/2,W/2,64], operand-typed or plain fp32 (pool_plain) -- the input of the 1x1 `down`
- * convolution, which commutes with the reference's Interpolate(0.5) (:753-757). */
-int fcvsr_rcb_finish(const float* res, const float* add, const float* r0, float* r, int B, int P,
-                     void* r_operand_copy, int op16, void* r_pool, int H, int W, int pool_plain, cudaStream_t stream);
+ * convolution, which commutes with the reference's Interpolate(0.5) (:753-757).  res_bf16 = 1: res is a bf16 tensor. */
+int fcvsr_rcb_finish(const void* res, const float* add, const float* r0, float* r, int B, int P,
+                     void* r_operand_copy, int op16, void* r_pool, int H, int W, int pool_plain, int res_bf16,
+                     cudaStream_t stream);
 /* BlockRCB cross-level sum (:766-777): xout = xin + coef*r + d + bilinear_x2(tu[B,H/2,W/2,64]) with
  * d = mean2x2(td[B,2H,2W,64]), or d = td[B,H,W,64] when td_pooled (down conv applied to the pooled tensor). */
 int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float* r, float coef, const float* td,
