@@ -173,16 +173,16 @@ extern "C" int fcvsr_context_block(const void* x, int ldx, const float* wmask, c
 }
 
 // r = lrelu_0.2(res + add[b]) + r0     (all 64 channels, float4 per thread)
-__global__ void rcb_finish_kernel(const void* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
+__global__ void rcb_finish_kernel(const void* __restrict__ res, const float* __restrict__ add, const void* __restrict__ r0,
                                   float* __restrict__ r, int P, size_t total4, void* __restrict__ r_op, int op16, int res16) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
     const int c = (int)(i & 15) * 4;
     const size_t pix = i >> 4;
     const int b = (int)(pix / P);
-    const float4 v = load4_any(res, pix * 64 + c, res16);
+    const float4 v = load4_any(res, pix * 64 + c, res16 & 1);
     const float4 a = *reinterpret_cast<const float4*>(add + (size_t)b * 64 + c);
-    const float4 q = *reinterpret_cast<const float4*>(r0 + pix * 64 + c);
+    const float4 q = load4_any(r0, pix * 64 + c, res16 & 2);
     float4 o;
     o.x = v.x + a.x; o.y = v.y + a.y; o.z = v.z + a.z; o.w = v.w + a.w;
     o.x = (o.x >= 0.f ? o.x : 0.2f * o.x) + q.x;
@@ -197,7 +197,7 @@ __global__ void rcb_finish_kernel(const void* __restrict__ res, const float* __r
 // commutes with the 2x2 average that follows it in the reference (:753-757, Interpolate(0.5) of an even-sized map),
 // so it runs on this pooled tensor at a quarter of the pixels.  pool_plain: store the mean as plain fp32 (exact mode)
 // instead of the operand type.
-__global__ void rcb_finish_pool_kernel(const void* __restrict__ res, const float* __restrict__ add, const float* __restrict__ r0,
+__global__ void rcb_finish_pool_kernel(const void* __restrict__ res, const float* __restrict__ add, const void* __restrict__ r0,
                                        float* __restrict__ r, int H, int W, size_t total, void* __restrict__ r_op, int op16,
                                        void* __restrict__ r_pool, int pool_plain, int res16) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,8 +212,8 @@ __global__ void rcb_finish_pool_kernel(const void* __restrict__ res, const float
     float4 v[4], q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        v[k] = load4_any(res, pix[k] * 64 + c, res16);
-        q[k] = *reinterpret_cast<const float4*>(r0 + pix[k] * 64 + c);
+        v[k] = load4_any(res, pix[k] * 64 + c, res16 & 1);
+        q[k] = load4_any(r0, pix[k] * 64 + c, res16 & 2);
     }
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -233,7 +233,7 @@ __global__ void rcb_finish_pool_kernel(const void* __restrict__ res, const float
     else store_operand4(r_pool, quad * 64 + c, m, op16);
 }
 
-extern "C" int fcvsr_rcb_finish(const void* res, const float* add, const float* r0, float* r, int B, int P,
+extern "C" int fcvsr_rcb_finish(const void* res, const float* add, const void* r0, float* r, int B, int P,
                                 void* r_op, int op16, void* r_pool, int H, int W, int pool_plain, int res_bf16, cudaStream_t st) {
     if (!res || !add || !r0 || !r) return FCVSR_ERR_ARG;
     if (r_pool) {

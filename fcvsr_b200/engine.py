@@ -124,6 +124,7 @@ class Engine:
         self.tc_pyramid = os.environ.get("FCVSR_TC_PYRAMID", "1") != "0"   # rconcat1/2 as stride-1 tcgen05 convs + sampling
         self.iac16 = os.environ.get("FCVSR_IAC16", "1") != "0"      # IAC ping-pong tensors in bf16 (bf16 mode only)
         self.res16 = os.environ.get("FCVSR_RES16", "1") != "0"      # RCB body output as a bf16 tensor (bf16 mode only)
+        self.r016 = os.environ.get("FCVSR_R016", "1") != "0"        # RCB input / skip r0 only as a bf16 tensor (bf16 mode)
         self.use_last_kernel = os.environ.get("FCVSR_LAST_KERNEL", "1") != "0"   # dedicated Cout = 1 kernel (bf16 mode)
         self._streams = {}
         self.profile = None          # optional list: (kind, flops, start_event, end_event) per conv launch
@@ -652,6 +653,7 @@ class Engine:
         LK = C.ACT_LEAKY
         R, O16 = int(self.use_tc), int(self.op16)
         res16 = int(bool(O16) and self.res16)
+        r016 = bool(O16) and self.r016
         main = torch.cuda.current_stream()
         ms = self.multi_stream and self.profile is None
         if ms:
@@ -695,15 +697,19 @@ class Engine:
                         r0_op = p[f"r0h{l}"] if R else p[f"r0{l}"]
                         rr_op = p[f"rrh{l}"] if R else p[f"rr{l}"]
                         self._conv(P[q + "c0"], src_r[l], 64, p[f"a128_{l}"], 128, B, h, w, act=LK, slope=0.1, rnd=True)
-                        self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w, y2=p[f"r0h{l}"], ldy2=64)
+                        if r016:                        # RCB input r0 only as the bf16 operand tensor (also the RCB skip)
+                            self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0h{l}"], 64, B, h, w, rnd=True)
+                        else:
+                            self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w, y2=p[f"r0h{l}"], ldy2=64)
                         self._conv(P[q + "r0"], r0_op, 64, p[f"c1{l}"], 64, B, h, w, act=LK, slope=0.2, rnd=True)
                         # res (RCB body output, consumed by the ContextBlock and the RCB tail only) is a bf16 tensor in bf16 mode
                         self._conv(P[q + "r2"], p[f"c1{l}"], 64, p[f"res{l}"], 64, B, h, w, rnd=bool(res16))
                         self.launches += 1
                         self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
                                 P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w, res16)
-                        self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0{l}"], p[f"rr{l}"], B, h * w,
-                                p[f"rrh{l}"] if (R and l > 0) else 0, O16, p[f"rrp{l}"] if l < 2 else 0, h, w, int(not R), res16)
+                        self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0h{l}"] if r016 else p[f"r0{l}"], p[f"rr{l}"],
+                                B, h * w, p[f"rrh{l}"] if (R and l > 0) else 0, O16, p[f"rrp{l}"] if l < 2 else 0, h, w,
+                                int(not R), res16 | (2 if r016 else 0))
                         if l < 2:                       # down: 1x1 conv on the 2x2 mean == mean of the conv (:753-757)
                             self._conv(P[q + "down"], p[f"rrp{l}"], 64, p[f"td{l}"], 64, B, h // 2, w // 2)
                         if l > 0:                       # up: 1x1 conv, interpolated in level_mix (:759-763)

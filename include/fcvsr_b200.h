@@ -144,8 +144,8 @@ int fcvsr_context_block(const void* x, int ldx, const float* wmask, const float*
                         float* partial, float* add, int B, int P, int x_bf16, cudaStream_t stream);
 /* RCB tail (:720-724): r = lrelu_0.2(res + add[b]) + r0 (64 ch, ld 64).  r_pool (optional, needs even H, W with
  * H*W == P): 2x2 mean of r, [B,H/2,W/2,64], operand-typed or plain fp32 (pool_plain) -- the input of the 1x1 `down`
- * convolution, which commutes with the reference's Interpolate(0.5) (:753-757).  res_bf16 = 1: res is a bf16 tensor. */
-int fcvsr_rcb_finish(const void* res, const float* add, const float* r0, float* r, int B, int P,
+ * convolution, which commutes with the reference's Interpolate(0.5) (:753-757).  res_bf16: bit 0 = res is a bf16 tensor, bit 1 = r0 is. */
+int fcvsr_rcb_finish(const void* res, const float* add, const void* r0, float* r, int B, int P,
                      void* r_operand_copy, int op16, void* r_pool, int H, int W, int pool_plain, int res_bf16,
                      cudaStream_t stream);
 /* BlockRCB cross-level sum (:766-777): xout = xin + coef*r + d + bilinear_x2(tu[B,H/2,W/2,64]) with
