@@ -190,7 +190,7 @@ __global__ void rcb_finish_kernel(const void* __restrict__ res, const float* __r
     o.z = (o.z >= 0.f ? o.z : 0.2f * o.z) + q.z;
     o.w = (o.w >= 0.f ? o.w : 0.2f * o.w) + q.w;
     if (r_op) store_operand4(r_op, pix * 64 + c, o, op16);     // tensor-core operand copy for the 1x1 down/up convs
-    *reinterpret_cast<float4*>(r + pix * 64 + c) = o;
+    if (r) *reinterpret_cast<float4*>(r + pix * 64 + c) = o;
 }
 
 // Same, one thread per 2x2 pixel quad x 4 channels, additionally writing the quad mean: the 1x1 `down` convolution
@@ -225,7 +225,7 @@ __global__ void rcb_finish_pool_kernel(const void* __restrict__ res, const float
         o.z = (o.z >= 0.f ? o.z : 0.2f * o.z) + q[k].z;
         o.w = (o.w >= 0.f ? o.w : 0.2f * o.w) + q[k].w;
         if (r_op) store_operand4(r_op, pix[k] * 64 + c, o, op16);
-        *reinterpret_cast<float4*>(r + pix[k] * 64 + c) = o;
+        if (r) *reinterpret_cast<float4*>(r + pix[k] * 64 + c) = o;
         m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
     }
     m.x *= 0.25f; m.y *= 0.25f; m.z *= 0.25f; m.w *= 0.25f;
@@ -235,7 +235,7 @@ __global__ void rcb_finish_pool_kernel(const void* __restrict__ res, const float
 
 extern "C" int fcvsr_rcb_finish(const void* res, const float* add, const void* r0, float* r, int B, int P,
                                 void* r_op, int op16, void* r_pool, int H, int W, int pool_plain, int res_bf16, cudaStream_t st) {
-    if (!res || !add || !r0 || !r) return FCVSR_ERR_ARG;
+    if (!res || !add || !r0 || (!r && !r_op)) return FCVSR_ERR_ARG;
     if (r_pool) {
         if (H <= 0 || W <= 0 || ((H | W) & 1) || (size_t)H * W != (size_t)P) return FCVSR_ERR_ARG;
         const size_t total = (size_t)B * (P / 4) * 16;
@@ -250,7 +250,7 @@ extern "C" int fcvsr_rcb_finish(const void* res, const float* add, const void* r
 
 // x[b,y,x,:] += coef * r + mean2x2(td) + bilinear_x2(tu)      (64 channels, ld 64 everywhere except x/y)
 __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* __restrict__ xout, int ldo,
-                                 const float* __restrict__ r, float coef, const float* __restrict__ td,
+                                 const void* __restrict__ r, float coef, const float* __restrict__ td,
                                  const float* __restrict__ tu, int H, int W, size_t total4, void* __restrict__ xout_r, int ldr,
                                  int round_main, int op16, int td_pooled) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,9 +261,9 @@ __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* 
     const int y = (int)((pix / W) % H);
     const int b = (int)(pix / ((size_t)W * H));
     float4 o = *reinterpret_cast<const float4*>(xin + pix * ldx + c);
-    const float4 rv = *reinterpret_cast<const float4*>(r + pix * 64 + c);
+    const float4 rv = load4_any(r, pix * 64 + c, td_pooled & 2);
     o.x = fmaf(coef, rv.x, o.x); o.y = fmaf(coef, rv.y, o.y); o.z = fmaf(coef, rv.z, o.z); o.w = fmaf(coef, rv.w, o.w);
-    if (td && td_pooled) {   // td is [B,H,W,64]: the down conv already ran on the 2x2 mean (see rcb_finish_pool_kernel)
+    if (td && (td_pooled & 1)) {   // td is [B,H,W,64]: the down conv already ran on the 2x2 mean (see rcb_finish_pool_kernel)
         const float4 a0 = *reinterpret_cast<const float4*>(td + pix * 64 + c);
         o.x += a0.x; o.y += a0.y; o.z += a0.z; o.w += a0.w;
     } else if (td) {   // td is [B,2H,2W,64]
@@ -299,7 +299,7 @@ __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* 
     else *reinterpret_cast<float4*>(xout + pix * ldo + c) = o;
 }
 
-extern "C" int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const float* r, float coef,
+extern "C" int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const void* r, float coef,
                                const float* td, const float* tu, int B, int H, int W, void* xout_r, int ldr,
                                int round_main, int op16, int td_pooled, cudaStream_t st) {
     if (!xin || !xout || !r || (ldx & 3) || (ldo & 3) || (tu && ((H | W) & 1)) || (xout_r && (ldr & 3))) return FCVSR_ERR_ARG;

@@ -125,6 +125,7 @@ class Engine:
         self.iac16 = os.environ.get("FCVSR_IAC16", "1") != "0"      # IAC ping-pong tensors in bf16 (bf16 mode only)
         self.res16 = os.environ.get("FCVSR_RES16", "1") != "0"      # RCB body output as a bf16 tensor (bf16 mode only)
         self.r016 = os.environ.get("FCVSR_R016", "1") != "0"        # RCB input / skip r0 only as a bf16 tensor (bf16 mode)
+        self.rr16 = os.environ.get("FCVSR_RR16", "1") != "0"        # RCB output rr only as a bf16 tensor (bf16 mode)
         self.use_last_kernel = os.environ.get("FCVSR_LAST_KERNEL", "1") != "0"   # dedicated Cout = 1 kernel (bf16 mode)
         self._streams = {}
         self.profile = None          # optional list: (kind, flops, start_event, end_event) per conv launch
@@ -654,6 +655,7 @@ class Engine:
         R, O16 = int(self.use_tc), int(self.op16)
         res16 = int(bool(O16) and self.res16)
         r016 = bool(O16) and self.r016
+        rr16 = int(bool(O16) and self.rr16)
         main = torch.cuda.current_stream()
         ms = self.multi_stream and self.profile is None
         if ms:
@@ -707,9 +709,9 @@ class Engine:
                         self.launches += 1
                         self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
                                 P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w, res16)
-                        self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0h{l}"] if r016 else p[f"r0{l}"], p[f"rr{l}"],
-                                B, h * w, p[f"rrh{l}"] if (R and l > 0) else 0, O16, p[f"rrp{l}"] if l < 2 else 0, h, w,
-                                int(not R), res16 | (2 if r016 else 0))
+                        self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0h{l}"] if r016 else p[f"r0{l}"],
+                                0 if rr16 else p[f"rr{l}"], B, h * w, p[f"rrh{l}"] if (R and (l > 0 or rr16)) else 0, O16,
+                                p[f"rrp{l}"] if l < 2 else 0, h, w, int(not R), res16 | (2 if r016 else 0))
                         if l < 2:                       # down: 1x1 conv on the 2x2 mean == mean of the conv (:753-757)
                             self._conv(P[q + "down"], p[f"rrp{l}"], 64, p[f"td{l}"], 64, B, h // 2, w // 2)
                         if l > 0:                       # up: 1x1 conv, interpolated in level_mix (:759-763)
@@ -718,11 +720,11 @@ class Engine:
                 # x + r + d + u (:771-776): level 0 has d = r, level 2 has u = r
                 tr = [p[f"tr{l}"] if R else 0 for l in range(3)]
                 with on(0):
-                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0, O16, 0)
+                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rrh0" if rr16 else "rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0, O16, 2 * rr16)
                 with on(1):
-                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0, O16, 1)
+                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rrh1" if rr16 else "rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0, O16, 1 + 2 * rr16)
                 with on(2):
-                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0, O16, 1)
+                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rrh2" if rr16 else "rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0, O16, 1 + 2 * rr16)
                 cross_join()                            # td/tu/rr of this block are overwritten by the next one
             for l, (h, w) in enumerate(dims):           # SCGroupbk tail: x + conv(res) (:797-803)
                 with on(l):
