@@ -250,8 +250,8 @@ extern "C" int fcvsr_rcb_finish(const void* res, const float* add, const void* r
 
 // x[b,y,x,:] += coef * r + mean2x2(td) + bilinear_x2(tu)      (64 channels, ld 64 everywhere except x/y)
 __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* __restrict__ xout, int ldo,
-                                 const void* __restrict__ r, float coef, const float* __restrict__ td,
-                                 const float* __restrict__ tu, int H, int W, size_t total4, void* __restrict__ xout_r, int ldr,
+                                 const void* __restrict__ r, float coef, const void* __restrict__ td,
+                                 const void* __restrict__ tu, int H, int W, size_t total4, void* __restrict__ xout_r, int ldr,
                                  int round_main, int op16, int td_pooled) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total4) return;
@@ -261,17 +261,18 @@ __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* 
     const int y = (int)((pix / W) % H);
     const int b = (int)(pix / ((size_t)W * H));
     float4 o = *reinterpret_cast<const float4*>(xin + pix * ldx + c);
+    const int t16 = td_pooled & 4;
     const float4 rv = load4_any(r, pix * 64 + c, td_pooled & 2);
     o.x = fmaf(coef, rv.x, o.x); o.y = fmaf(coef, rv.y, o.y); o.z = fmaf(coef, rv.z, o.z); o.w = fmaf(coef, rv.w, o.w);
     if (td && (td_pooled & 1)) {   // td is [B,H,W,64]: the down conv already ran on the 2x2 mean (see rcb_finish_pool_kernel)
-        const float4 a0 = *reinterpret_cast<const float4*>(td + pix * 64 + c);
+        const float4 a0 = load4_any(td, pix * 64 + c, t16);
         o.x += a0.x; o.y += a0.y; o.z += a0.z; o.w += a0.w;
     } else if (td) {   // td is [B,2H,2W,64]
         const size_t base = (((size_t)b * 2 * H + 2 * y) * (2 * W) + 2 * x) * 64 + c;
-        const float4 a0 = *reinterpret_cast<const float4*>(td + base);
-        const float4 a1 = *reinterpret_cast<const float4*>(td + base + 64);
-        const float4 a2 = *reinterpret_cast<const float4*>(td + base + (size_t)2 * W * 64);
-        const float4 a3 = *reinterpret_cast<const float4*>(td + base + (size_t)2 * W * 64 + 64);
+        const float4 a0 = load4_any(td, base, t16);
+        const float4 a1 = load4_any(td, base + 64, t16);
+        const float4 a2 = load4_any(td, base + (size_t)2 * W * 64, t16);
+        const float4 a3 = load4_any(td, base + (size_t)2 * W * 64 + 64, t16);
         o.x += 0.25f * (a0.x + a1.x + a2.x + a3.x);
         o.y += 0.25f * (a0.y + a1.y + a2.y + a3.y);
         o.z += 0.25f * (a0.z + a1.z + a2.z + a3.z);
@@ -283,11 +284,11 @@ __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* 
         const int y0 = (int)sy, x0 = (int)sx;
         const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
         const float ly = sy - y0, lx = sx - x0;
-        const float* tb = tu + (size_t)b * hs * ws * 64 + c;
-        const float4 a00 = *reinterpret_cast<const float4*>(tb + ((size_t)y0 * ws + x0) * 64);
-        const float4 a01 = *reinterpret_cast<const float4*>(tb + ((size_t)y0 * ws + x1) * 64);
-        const float4 a10 = *reinterpret_cast<const float4*>(tb + ((size_t)y1 * ws + x0) * 64);
-        const float4 a11 = *reinterpret_cast<const float4*>(tb + ((size_t)y1 * ws + x1) * 64);
+        const size_t tb = (size_t)b * hs * ws * 64 + c;
+        const float4 a00 = load4_any(tu, tb + ((size_t)y0 * ws + x0) * 64, t16);
+        const float4 a01 = load4_any(tu, tb + ((size_t)y0 * ws + x1) * 64, t16);
+        const float4 a10 = load4_any(tu, tb + ((size_t)y1 * ws + x0) * 64, t16);
+        const float4 a11 = load4_any(tu, tb + ((size_t)y1 * ws + x1) * 64, t16);
         const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
         o.x += w00 * a00.x + w01 * a01.x + w10 * a10.x + w11 * a11.x;
         o.y += w00 * a00.y + w01 * a01.y + w10 * a10.y + w11 * a11.y;
@@ -300,7 +301,7 @@ __global__ void level_mix_kernel(const float* __restrict__ xin, int ldx, float* 
 }
 
 extern "C" int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const void* r, float coef,
-                               const float* td, const float* tu, int B, int H, int W, void* xout_r, int ldr,
+                               const void* td, const void* tu, int B, int H, int W, void* xout_r, int ldr,
                                int round_main, int op16, int td_pooled, cudaStream_t st) {
     if (!xin || !xout || !r || (ldx & 3) || (ldo & 3) || (tu && ((H | W) & 1)) || (xout_r && (ldr & 3))) return FCVSR_ERR_ARG;
     const size_t total4 = (size_t)B * H * W * 16;

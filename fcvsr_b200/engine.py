@@ -126,6 +126,7 @@ class Engine:
         self.res16 = os.environ.get("FCVSR_RES16", "1") != "0"      # RCB body output as a bf16 tensor (bf16 mode only)
         self.r016 = os.environ.get("FCVSR_R016", "1") != "0"        # RCB input / skip r0 only as a bf16 tensor (bf16 mode)
         self.rr16 = os.environ.get("FCVSR_RR16", "1") != "0"        # RCB output rr only as a bf16 tensor (bf16 mode)
+        self.t16 = os.environ.get("FCVSR_T16", "1") != "0"          # cross-level terms td / tu as bf16 tensors (bf16 mode)
         self.use_last_kernel = os.environ.get("FCVSR_LAST_KERNEL", "1") != "0"   # dedicated Cout = 1 kernel (bf16 mode)
         self._streams = {}
         self.profile = None          # optional list: (kind, flops, start_event, end_event) per conv launch
@@ -656,6 +657,7 @@ class Engine:
         res16 = int(bool(O16) and self.res16)
         r016 = bool(O16) and self.r016
         rr16 = int(bool(O16) and self.rr16)
+        t16 = 4 if (O16 and self.t16) else 0      # down / up conv outputs td, tu as bf16 tensors (flag bit of level_mix)
         main = torch.cuda.current_stream()
         ms = self.multi_stream and self.profile is None
         if ms:
@@ -713,18 +715,18 @@ class Engine:
                                 0 if rr16 else p[f"rr{l}"], B, h * w, p[f"rrh{l}"] if (R and (l > 0 or rr16)) else 0, O16,
                                 p[f"rrp{l}"] if l < 2 else 0, h, w, int(not R), res16 | (2 if r016 else 0))
                         if l < 2:                       # down: 1x1 conv on the 2x2 mean == mean of the conv (:753-757)
-                            self._conv(P[q + "down"], p[f"rrp{l}"], 64, p[f"td{l}"], 64, B, h // 2, w // 2)
+                            self._conv(P[q + "down"], p[f"rrp{l}"], 64, p[f"td{l}"], 64, B, h // 2, w // 2, rnd=bool(t16))
                         if l > 0:                       # up: 1x1 conv, interpolated in level_mix (:759-763)
-                            self._conv(P[q + "up"], rr_op, 64, p[f"tu{l}"], 64, B, h, w)
+                            self._conv(P[q + "up"], rr_op, 64, p[f"tu{l}"], 64, B, h, w, rnd=bool(t16))
                 cross_join()
                 # x + r + d + u (:771-776): level 0 has d = r, level 2 has u = r
                 tr = [p[f"tr{l}"] if R else 0 for l in range(3)]
                 with on(0):
-                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rrh0" if rr16 else "rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0, O16, 2 * rr16)
+                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rrh0" if rr16 else "rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0, O16, 2 * rr16 + t16)
                 with on(1):
-                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rrh1" if rr16 else "rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0, O16, 1 + 2 * rr16)
+                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rrh1" if rr16 else "rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0, O16, 1 + 2 * rr16 + t16)
                 with on(2):
-                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rrh2" if rr16 else "rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0, O16, 1 + 2 * rr16)
+                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rrh2" if rr16 else "rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0, O16, 1 + 2 * rr16 + t16)
                 cross_join()                            # td/tu/rr of this block are overwritten by the next one
             for l, (h, w) in enumerate(dims):           # SCGroupbk tail: x + conv(res) (:797-803)
                 with on(l):

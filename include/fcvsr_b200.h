@@ -150,9 +150,9 @@ int fcvsr_rcb_finish(const void* res, const float* add, const void* r0, float* r
                      cudaStream_t stream);
 /* BlockRCB cross-level sum (:766-777): xout = xin + coef*r + d + bilinear_x2(tu[B,H/2,W/2,64]) with
  * d = mean2x2(td[B,2H,2W,64]), or d = td[B,H,W,64] when td_pooled & 1 (down conv applied to the pooled tensor);
- * td_pooled & 2: r is a bf16 tensor.  fcvsr_rcb_finish: r may be NULL when r_operand_copy is given. */
-int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const void* r, float coef, const float* td,
-                    const float* tu, int B, int H, int W, void* xout_r, int ldr, int round_main, int op16,
+ * td_pooled & 2: r is a bf16 tensor; td_pooled & 4: td and tu are.  fcvsr_rcb_finish: r may be NULL when r_operand_copy is given. */
+int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const void* r, float coef, const void* td,
+                    const void* tu, int B, int H, int W, void* xout_r, int ldr, int round_main, int op16,
                     int td_pooled, cudaStream_t stream);
 
 /* ---- tail (CVSR_freq.py:2739-2751) -------------------------------------------------------------- */
