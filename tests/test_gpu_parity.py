@@ -694,3 +694,79 @@ def test_bf16_path_matches_reference_golden(dev, name):
     psnr_vs_ref = 10.0 * torch.log10(torch.tensor(1.0 / max(mse, 1e-20))).item()
     assert err <= 5e-3, err
     assert psnr_vs_ref >= 60.0, psnr_vs_ref
+
+
+def _bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 8, 12), (2, 18, 22)])
+def test_subsample2_kernel(dev, B, H, W):
+    """fcvsr_subsample2: y[b,i,j,:] = x[b,2i,2j,:] (fp32 stream) and its bf16 / TF32-rounded operand copy -- with the stride-1
+    tcgen05 convolution in front this is rconcat1/2 (CVSR_freq.py:2671-2672): checked against F.conv2d(stride=2)."""
+    g = torch.Generator().manual_seed(B * H * W)
+    x = torch.randn(B, 64, H, W, generator=g)
+    xd = nhwc(x).to(dev)
+    y = torch.zeros(B, H // 2, W // 2, 64, device=dev)
+    y2 = torch.zeros(B, H // 2, W // 2, 64, device=dev, dtype=torch.bfloat16)
+    C.call("fcvsr_subsample2", xd.data_ptr(), 64, y.data_ptr(), 64, y2.data_ptr(), 64, B, H, W, 64, 1, _st())
+    torch.cuda.synchronize()
+    ref = nhwc(x)[:, ::2, ::2, :]
+    assert torch.equal(y.cpu(), ref)
+    assert torch.equal(y2.float().cpu(), _bf16r(ref))
+    w = torch.randn(64, 64, 3, 3, generator=g) / 24
+    full = F.conv2d(x, w, padding=1)
+    assert torch.allclose(full[:, :, ::2, ::2], F.conv2d(x, w, padding=1, stride=2), atol=1e-5)
+
+
+@pytest.mark.parametrize("b16", [0, 1])
+def test_scnet_helpers_bf16_inputs(dev, b16):
+    """ContextBlock / RCB tail / cross-level mix (CVSR_freq.py:657-777) through the C ABI with fp32 and with bf16 side tensors
+    (the bf16 mode's res, r0, rr, td, tu): exact formulas on the (rounded) inputs, fp32 arithmetic."""
+    g = torch.Generator().manual_seed(17 + b16)
+    B, H, W = 2, 12, 20
+    P = H * W
+    rnd = _bf16r if b16 else (lambda t: t)
+    res, r0 = rnd(torch.randn(B, P, 64, generator=g)), rnd(torch.randn(B, P, 64, generator=g))
+    wm = torch.randn(64, generator=g) / 8
+    w1, w2 = torch.randn(64, 64, generator=g) / 8, torch.randn(64, 64, generator=g) / 8
+    dt = torch.bfloat16 if b16 else torch.float32
+    res_d, r0_d = res.to(dev).to(dt), r0.to(dev).to(dt)
+    nblk = (P + 127) // 128
+    part = torch.zeros(B * nblk * 66, device=dev)
+    add = torch.zeros(B, 64, device=dev)
+    C.call("fcvsr_context_block", res_d.data_ptr(), 64, wm.to(dev).data_ptr(), w1.to(dev).data_ptr(), w2.to(dev).data_ptr(),
+           part.data_ptr(), add.data_ptr(), B, P, b16, _st())
+    att = torch.softmax(res @ wm, dim=1)                                   # [B,P]
+    ctx = torch.einsum("bp,bpc->bc", att, res)
+    add_ref = F.leaky_relu(ctx @ w1.t(), 0.2) @ w2.t()
+    torch.cuda.synchronize()
+    assert float((add.cpu() - add_ref).abs().max()) <= 1e-4 * max(1.0, float(add_ref.abs().max()))
+    # RCB tail: rr = lrelu_0.2(res + add) + r0, with the 2x2 mean; fp32 output and / or the bf16 operand copy
+    rr = torch.zeros(B, P, 64, device=dev)
+    rrh = torch.zeros(B, P, 64, device=dev, dtype=torch.bfloat16)
+    rrp = torch.zeros(B, P // 4, 64, device=dev, dtype=torch.bfloat16)
+    add_d = add_ref.to(dev)
+    C.call("fcvsr_rcb_finish", res_d.data_ptr(), add_d.data_ptr(), r0_d.data_ptr(), 0 if b16 else rr.data_ptr(), B, P,
+           rrh.data_ptr(), 1, rrp.data_ptr(), H, W, 0, 3 * b16, _st())
+    rr_ref = F.leaky_relu(res + add_ref[:, None, :], 0.2) + r0
+    pool_ref = rr_ref.view(B, H // 2, 2, W // 2, 2, 64).mean(dim=(2, 4)).reshape(B, P // 4, 64)
+    torch.cuda.synchronize()
+    if not b16:
+        assert float((rr.cpu() - rr_ref).abs().max()) <= 1e-5
+    assert float((rrh.float().cpu() - rr_ref).abs().max()) <= 2 ** -8 * float(rr_ref.abs().max())
+    assert float((rrp.float().cpu() - pool_ref).abs().max()) <= 2 ** -8 * float(pool_ref.abs().max())
+    # cross-level mix at the middle level: x + 1.0 * rr + td (already pooled) + bilinear_x2(tu)
+    xin = torch.randn(B, P, 64, generator=g)
+    rrv = rnd(rr_ref)
+    td = rnd(torch.randn(B, P, 64, generator=g))
+    tu = rnd(torch.randn(B, (H // 2) * (W // 2), 64, generator=g))
+    out = torch.zeros(B, P, 64, device=dev)
+    out_r = torch.zeros(B, P, 64, device=dev, dtype=torch.bfloat16)
+    C.call("fcvsr_level_mix", xin.to(dev).data_ptr(), 64, out.data_ptr(), 64, rrv.to(dev).to(dt).data_ptr(), 1.0,
+           td.to(dev).to(dt).data_ptr(), tu.to(dev).to(dt).data_ptr(), B, H, W, out_r.data_ptr(), 64, 0, 1, 1 + 6 * b16, _st())
+    up = F.interpolate(tu.view(B, H // 2, W // 2, 64).permute(0, 3, 1, 2), scale_factor=2, mode="bilinear")
+    ref = xin + rrv + td + up.permute(0, 2, 3, 1).reshape(B, P, 64)
+    torch.cuda.synchronize()
+    assert float((out.cpu() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+    assert float((out_r.float().cpu() - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max())
