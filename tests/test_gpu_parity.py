@@ -735,7 +735,8 @@ def test_scnet_helpers_bf16_inputs(dev, b16):
     nblk = (P + 127) // 128
     part = torch.zeros(B * nblk * 66, device=dev)
     add = torch.zeros(B, 64, device=dev)
-    C.call("fcvsr_context_block", res_d.data_ptr(), 64, wm.to(dev).data_ptr(), w1.to(dev).data_ptr(), w2.to(dev).data_ptr(),
+    wm_d, w1_d, w2_d = wm.to(dev), w1.to(dev), w2.to(dev)
+    C.call("fcvsr_context_block", res_d.data_ptr(), 64, wm_d.data_ptr(), w1_d.data_ptr(), w2_d.data_ptr(),
            part.data_ptr(), add.data_ptr(), B, P, b16, _st())
     att = torch.softmax(res @ wm, dim=1)                                   # [B,P]
     ctx = torch.einsum("bp,bpc->bc", att, res)
@@ -763,8 +764,9 @@ def test_scnet_helpers_bf16_inputs(dev, b16):
     tu = rnd(torch.randn(B, (H // 2) * (W // 2), 64, generator=g))
     out = torch.zeros(B, P, 64, device=dev)
     out_r = torch.zeros(B, P, 64, device=dev, dtype=torch.bfloat16)
-    C.call("fcvsr_level_mix", xin.to(dev).data_ptr(), 64, out.data_ptr(), 64, rrv.to(dev).to(dt).data_ptr(), 1.0,
-           td.to(dev).to(dt).data_ptr(), tu.to(dev).to(dt).data_ptr(), B, H, W, out_r.data_ptr(), 64, 0, 1, 1 + 6 * b16, _st())
+    xin_d, rr_d, td_d, tu_d = xin.to(dev), rrv.to(dev).to(dt), td.to(dev).to(dt), tu.to(dev).to(dt)
+    C.call("fcvsr_level_mix", xin_d.data_ptr(), 64, out.data_ptr(), 64, rr_d.data_ptr(), 1.0, td_d.data_ptr(), tu_d.data_ptr(),
+           B, H, W, out_r.data_ptr(), 64, 0, 1, 1 + 6 * b16, _st())
     up = F.interpolate(tu.view(B, H // 2, W // 2, 64).permute(0, 3, 1, 2), scale_factor=2, mode="bilinear")
     ref = xin + rrv + td + up.permute(0, 2, 3, 1).reshape(B, P, 64)
     torch.cuda.synchronize()
