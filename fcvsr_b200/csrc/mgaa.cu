@@ -88,10 +88,11 @@ __device__ __forceinline__ void ob_conv_quad(const float* __restrict__ src, cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 v = row[j + kx];
-                acc[j][0] += v.x * w0.x + v.y * w1.x + v.z * w2.x + v.w * w3.x;
-                acc[j][1] += v.x * w0.y + v.y * w1.y + v.z * w2.y + v.w * w3.y;
-                acc[j][2] += v.x * w0.z + v.y * w1.z + v.z * w2.z + v.w * w3.z;
-                acc[j][3] += v.x * w0.w + v.y * w1.w + v.z * w2.w + v.w * w3.w;
+                // one FMA per MAC, chained into the accumulator (the sum-then-add form costs a fifth instruction per 4 MACs)
+                acc[j][0] = fmaf(v.w, w3.x, fmaf(v.z, w2.x, fmaf(v.y, w1.x, fmaf(v.x, w0.x, acc[j][0]))));
+                acc[j][1] = fmaf(v.w, w3.y, fmaf(v.z, w2.y, fmaf(v.y, w1.y, fmaf(v.x, w0.y, acc[j][1]))));
+                acc[j][2] = fmaf(v.w, w3.z, fmaf(v.z, w2.z, fmaf(v.y, w1.z, fmaf(v.x, w0.z, acc[j][2]))));
+                acc[j][3] = fmaf(v.w, w3.w, fmaf(v.z, w2.w, fmaf(v.y, w1.w, fmaf(v.x, w0.w, acc[j][3]))));
             }
         }
     }
