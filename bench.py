@@ -234,6 +234,18 @@ def main():
 
     frames = B * world * args.steps
     fps = frames / (ms * 1e-3)
+    if roof is not None:
+        # whole-forward roofline of SURVEY 8(d): live conv FLOPs per LR pixel (22.50 M FCVSR / 9.61 M FCVSR-S) on the tensor
+        # pipe plus the compulsory HBM bytes of the non-GEMM stages (0.48 GB per 180x320 FCVSR frame) -- the
+        # frames/s the forward could reach if every kernel sat on its own roofline; per GPU
+        hbm, tfl, _ = peaks()
+        mflop_px = 22.50 if args.variant == "full" else 9.61
+        t_tensor = mflop_px * 1e6 * H * W / (tfl * 1e12)
+        # bytes per LR pixel: 3 x MGAAbk (768 in + 16A offsets out; IAC 768 + 16A in, 512 out) + MFFR 512 + up-sampler 1092
+        bytes_px = 7748 + 96 * (6 if args.variant == "full" else 3)
+        t_hbm = bytes_px * H * W / (hbm * 1e9)
+        roof["forward"] = {"alg_tflop_per_frame": mflop_px * 1e6 * H * W / 1e12, "alg_gb_per_frame": bytes_px * H * W / 1e9,
+                           "bound_frames_per_s": 1.0 / (t_tensor + t_hbm), "frac": (fps / world) * (t_tensor + t_hbm)}
     fps_e2e = frames / (ms_e2e * 1e-3)
     if rank != 0:
         if world > 1:
