@@ -39,8 +39,9 @@ __device__ __forceinline__ void dcn_geo(const DcnBwdArgs& a, int b, int g, int t
     const int kk2 = a.kh * a.kw, P = a.Ho * a.Wo;
     const int i = tap / a.kw, j = tap - i * a.kw;
     const size_t ob = ((size_t)(b * a.dg + g) * 2 * kk2 + 2 * tap) * P + p;
-    const float h = (float)(ho * a.sh - a.ph + i * a.dh) + a.offset[ob];
-    const float w = (float)(wo * a.sw - a.pw + j * a.dw) + a.offset[ob + P];
+    // offset == NULL: zero offsets, i.e. the plain convolution (backward of the *Pack modules' conv_offset layers)
+    const float h = (float)(ho * a.sh - a.ph + i * a.dh) + (a.offset ? a.offset[ob] : 0.f);
+    const float w = (float)(wo * a.sw - a.pw + j * a.dw) + (a.offset ? a.offset[ob + P] : 0.f);
     q.valid = (h > -1.f && w > -1.f && h < (float)a.H && w < (float)a.W);
     if (q.valid) {
         const float fh = floorf(h), fw = floorf(w);
@@ -407,10 +408,10 @@ extern "C" int fcvsr_modulated_deform_conv_backward(const float* input, const fl
                                                     float* grad_mask, int B, int Cin, int H, int W, int Cout, int kh, int kw,
                                                     int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
                                                     int groups, int deformable_groups, float* scratch, cudaStream_t st) {
-    if (!input || !weight || !offset || !grad_output) return FCVSR_ERR_ARG;
+    if (!input || !weight || !grad_output) return FCVSR_ERR_ARG;
     if (B <= 0 || groups <= 0 || deformable_groups <= 0 || Cin % groups || Cout % groups || Cin % deformable_groups)
         return FCVSR_ERR_ARG;
-    if (grad_mask && !mask) return FCVSR_ERR_ARG;
+    if ((grad_mask && !mask) || (grad_offset && !offset)) return FCVSR_ERR_ARG;
     DcnBwdArgs a;
     a.x = input; a.w = weight; a.offset = offset; a.mask = mask; a.gy = grad_output;
     a.gx = grad_input; a.gw = grad_weight; a.goff = grad_offset; a.gmask = grad_mask;

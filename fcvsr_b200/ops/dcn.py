@@ -18,7 +18,8 @@ Autograd: ``deform_conv`` / ``modulated_deform_conv`` (and the DeformConv / Modu
 ``torch.autograd.Function``s like the reference's (deform_conv.py:14-98,:114-183); their backward binds
 ``fcvsr_modulated_deform_conv_backward`` (csrc/dcn_bwd.cu), which replaces modulated_deform_conv_cuda_backward /
 deform_conv_backward_input_cuda / deform_conv_backward_parameters_cuda (deform_conv_cuda.cpp:566,260,373).  The *Pack
-modules run their offset convolution on the forward-only convolution kernel, so they still raise under autograd.
+modules train as well: their conv_offset / conv_offset_mask layer is an autograd op whose backward is the same entry with
+zero offsets (a deformable convolution with zero offsets is the convolution).
 """
 from __future__ import annotations
 
@@ -40,9 +41,7 @@ def _check(*tensors, allow_grad=False):
         if t.dtype != torch.float32:
             raise TypeError("fcvsr_b200 DCN kernels are fp32")
         if not allow_grad and torch.is_grad_enabled() and t.requires_grad:
-            raise NotImplementedError("fcvsr_b200: the *Pack modules' offset convolution has no backward kernel yet; "
-                                      "call under torch.no_grad() (the functional ops and DeformConv / "
-                                      "ModulatedDeformConv are autograd-capable)")
+            raise NotImplementedError("fcvsr_b200: this path has no backward kernel; call under torch.no_grad()")
 
 
 def _out_hw(h, w, kh, kw, stride, padding, dilation):
@@ -92,7 +91,7 @@ def _backward(x, offset, mask, weight, grad_out, stride, padding, dilation, grou
     cout, _, kh, kw = weight.shape
     grad_out = grad_out.contiguous()
     gx = torch.zeros_like(x) if need[0] else None
-    goff = torch.zeros_like(offset) if need[1] else None
+    goff = torch.zeros_like(offset) if (offset is not None and need[1]) else None
     gmask = torch.zeros_like(mask) if (mask is not None and need[2]) else None
     gw = torch.zeros_like(weight) if need[3] else None
     gb = x.new_zeros(cout) if with_bias else None
@@ -100,7 +99,7 @@ def _backward(x, offset, mask, weight, grad_out, stride, padding, dilation, grou
     fast = BACKWARD_NHWC and (cin // groups) % 4 == 0 and (cin // dg) % 4 == 0
     scratch = x.new_empty(2 * x.numel()) if fast else None      # NHWC copies of input / grad_input (vector reductions)
     with torch.cuda.device(x.device):
-        C.call("fcvsr_modulated_deform_conv_backward", x.data_ptr(), weight.data_ptr(), offset.data_ptr(), ptr(mask),
+        C.call("fcvsr_modulated_deform_conv_backward", x.data_ptr(), weight.data_ptr(), ptr(offset), ptr(mask),
                grad_out.data_ptr(), ptr(gx), ptr(gw), ptr(gb), ptr(goff), ptr(gmask), b, cin, h, w, cout, kh, kw,
                stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], groups, dg, ptr(scratch),
                torch.cuda.current_stream().cuda_stream)
@@ -187,24 +186,50 @@ def modulated_deform_conv(input, offset, mask, weight, bias=None, stride=1, padd
                                              deformable_groups)
 
 
-def _offset_conv(x, conv: nn.Conv2d):
-    """conv_offset / conv_offset_mask of the *Pack modules (deform_conv.py:243-250,:315-323) on our own
-    convolution kernel (NCHW in, NCHW out)."""
-    _check(x, conv.weight, conv.bias)
-    w = conv.weight.detach()
+def _offset_conv_raw(x, w, bias, s):
     cout, cin, kh, kw = w.shape
-    if kh != kw or conv.stride[0] != conv.stride[1] or conv.padding[0] != kh // 2 or conv.padding[1] != kw // 2:
-        raise NotImplementedError("conv_offset: only square kernels with 'same' padding k//2 are supported")
     b, _, h, wd = x.shape
-    s = conv.stride[0]
     ho, wo = (h + 2 * (kh // 2) - kh) // s + 1, (wd + 2 * (kw // 2) - kw) // s + 1
     y = x.new_empty(b, cout, ho, wo)
-    wp = w.permute(2, 3, 1, 0).contiguous()
+    wp = w.detach().permute(2, 3, 1, 0).contiguous()
     with torch.cuda.device(x.device):
-        C.call("fcvsr_conv2d_direct", x.data_ptr(), 0, 1, wp.data_ptr(), conv.bias.data_ptr() if conv.bias is not None else 0,
+        C.call("fcvsr_conv2d_direct", x.data_ptr(), 0, 1, wp.data_ptr(), bias.data_ptr() if bias is not None else 0,
                0, 0, 0, 0, y.data_ptr(), 0, b, h, wd, cin, cout, kh, s, C.ACT_NONE, 0.0, 0, 0, 1, 0, 0, 0, 0,
                torch.cuda.current_stream().cuda_stream)
     return y
+
+
+class _OffsetConvFunction(torch.autograd.Function):
+    """conv_offset / conv_offset_mask as an autograd op: forward on fcvsr_conv2d_direct; backward on the DCN backward kernels
+    with zero offsets and no mask -- a deformable convolution with zero offsets IS the convolution, so grad_input,
+    grad_weight and grad_bias come from fcvsr_modulated_deform_conv_backward(offset = NULL)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride):
+        x, weight = x.contiguous(), weight.contiguous()
+        ctx.stride, ctx.with_bias = stride, bias is not None
+        ctx.save_for_backward(x, weight)
+        return _offset_conv_raw(x, weight, bias, stride)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        x, weight = ctx.saved_tensors
+        k, s = weight.shape[2], ctx.stride
+        n = ctx.needs_input_grad
+        gx, _, _, gw, gb = _backward(x, None, None, weight, grad_output, (s, s), (k // 2, k // 2), (1, 1), 1, 1,
+                                     (n[0], False, False, n[1]), ctx.with_bias and n[2])
+        return gx, gw, gb, None
+
+
+def _offset_conv(x, conv: nn.Conv2d):
+    """conv_offset / conv_offset_mask of the *Pack modules (deform_conv.py:243-250,:315-323) on our own
+    convolution kernel (NCHW in, NCHW out), autograd-capable."""
+    _check(x, conv.weight, conv.bias, allow_grad=True)
+    kh, kw = conv.weight.shape[2:]
+    if kh != kw or conv.stride[0] != conv.stride[1] or conv.padding[0] != kh // 2 or conv.padding[1] != kw // 2:
+        raise NotImplementedError("conv_offset: only square kernels with 'same' padding k//2 are supported")
+    return _OffsetConvFunction.apply(x, conv.weight, conv.bias, conv.stride[0])
 
 
 class DeformConv(nn.Module):
@@ -287,7 +312,13 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
     def forward(self, x):
         """chunk -> cat(o1, o2) -> sigmoid(mask) (:331-334) are fused away: offset is the first 2/3 of the
         conv_offset_mask output, the mask the last third (sigmoid applied inside the DCN kernel)."""
-        _check(x, self.weight, self.bias)
+        _check(x, self.weight, self.bias, allow_grad=True)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # training: the reference's own sequence (:331-336) on autograd-capable ops
+            out = _offset_conv(x, self.conv_offset_mask)
+            o1, o2, mask = torch.chunk(out, 3, dim=1)
+            return modulated_deform_conv(x, torch.cat((o1, o2), dim=1), torch.sigmoid(mask), self.weight, self.bias, self.stride,
+                                         self.padding, self.dilation, self.groups, self.deformable_groups)
         out = _offset_conv(x, self.conv_offset_mask)
         b, c3, ho, wo = out.shape
         kk = self.kernel_size[0] * self.kernel_size[1]

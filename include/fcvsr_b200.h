@@ -223,7 +223,9 @@ int fcvsr_modulated_deform_conv_forward_tc(const float* input, const float* weig
  * so the caller zero-fills them first (as deform_conv.py:155-159 does with zeros_like).  grad_input [B,Cin,H,W],
  * grad_weight [Cout,Cin/groups,kh,kw], grad_bias [Cout], grad_offset / grad_mask dense, shaped like offset / mask.
  * grad_input, grad_offset, grad_mask and grad_weight are combined with fp32 atomics (as the reference's col2im is):
- * run-to-run differences are at rounding level.  scratch: NULL, or 2*B*Cin*H*W floats (16-byte aligned) that enable the
+ * run-to-run differences are at rounding level.  offset == NULL (with grad_offset == NULL) means zero offsets: the backward of
+ * a plain convolution, used for the conv_offset / conv_offset_mask layers of the *Pack modules (deform_conv.py:243-250,
+ * :315-323).  scratch: NULL, or 2*B*Cin*H*W floats (16-byte aligned) that enable the
  * NHWC fast path for (Cin/groups) % 4 == 0 and (Cin/deformable_groups) % 4 == 0: 16-byte corner loads and vector
  * reductions (red.global.add.v4.f32) on an NHWC copy of input / grad_input. */
 int fcvsr_modulated_deform_conv_backward(const float* input, const float* weight, const float* offset, const float* mask,

@@ -772,3 +772,51 @@ def test_scnet_helpers_bf16_inputs(dev, b16):
     torch.cuda.synchronize()
     assert float((out.cpu() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
     assert float((out_r.float().cpu() - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("kind,cin,cout,stride", [("v2", 6, 4, 1), ("v2", 8, 8, 1), ("v1", 8, 6, 2)])
+def test_dcn_pack_modules_train(dev, monkeypatch, kind, cin, cout, stride):
+    """DeformConvPack / ModulatedDeformConvPack (deform_conv.py:239-261,:311-337) under autograd: gradients of the input, the DCN
+    weight / bias and the conv_offset[_mask] layer (its backward = the DCN backward entry with zero offsets) against autograd
+    through F.conv2d + the oracle DCN on the CPU."""
+    import fcvsr_b200.ops.dcn as dcn_mod
+    monkeypatch.setattr(dcn_mod, "PRECISION", "fp32")
+    torch.manual_seed(11 + cin)
+    dg = 2
+    if kind == "v2":
+        m = dcn_mod.ModulatedDeformConvPack(cin, cout, 3, stride=stride, padding=1, deformable_groups=dg).to(dev)
+        off_layer = m.conv_offset_mask
+    else:
+        m = dcn_mod.DeformConvPack(cin, cout, 3, stride=stride, padding=1, deformable_groups=dg).to(dev)
+        off_layer = m.conv_offset
+    with torch.no_grad():
+        off_layer.weight.normal_(0, 0.08)
+        off_layer.bias.normal_(0, 0.4)
+        if kind == "v2":
+            m.bias.normal_(0, 0.1)
+    x = torch.randn(2, cin, 10, 12, device=dev, requires_grad=True)
+    y = m(x)
+    gy = torch.randn_like(y)
+    (y * gy).sum().backward()
+    torch.cuda.synchronize()
+    # CPU reference
+    xr = x.detach().cpu().requires_grad_()
+    w = m.weight.detach().cpu().requires_grad_()
+    cw, cb = off_layer.weight.detach().cpu().requires_grad_(), off_layer.bias.detach().cpu().requires_grad_()
+    o = F.conv2d(xr, cw, cb, stride=stride, padding=1)
+    if kind == "v2":
+        b = m.bias.detach().cpu().requires_grad_()
+        o1, o2, mk = torch.chunk(o, 3, dim=1)
+        ref = O.modulated_deform_conv(xr, torch.cat((o1, o2), 1), torch.sigmoid(mk), w, b, stride, 1, 1, 1, dg)
+    else:
+        ref = O.modulated_deform_conv(xr, o, None, w, None, stride, 1, 1, 1, dg)
+    assert float((y.detach().cpu() - ref.detach()).abs().max()) <= 1e-4
+    (ref * gy.cpu()).sum().backward()
+    pairs = [("input", x.grad, xr.grad), ("weight", m.weight.grad, w.grad), ("conv_offset.weight", off_layer.weight.grad, cw.grad),
+             ("conv_offset.bias", off_layer.bias.grad, cb.grad)]
+    if kind == "v2":
+        pairs.append(("bias", m.bias.grad, b.grad))
+    for name, a, r in pairs:
+        assert a is not None, name
+        err = float((a.cpu() - r).abs().max())
+        assert err <= 3e-4 * max(1.0, float(r.abs().max())), (name, err)
