@@ -1,0 +1,71 @@
+"""CPU tests (gloo, world size 2) of the data-parallel gradient all-reduce (BASELINE config 4)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fcvsr_b200.gradsync import GradAllReducer
+
+
+class _Net(torch.nn.Module):
+    """Small stand-in with the two quirks of the reference model: an aliased sub-module (registered twice, as
+    recorb1...RCB == body.3, CVSR_freq.py:736,751) and parameters that never receive a gradient (DivEnh.Conv, :2104-2133)."""
+
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Conv2d(3, 8, 3, padding=1)
+        self.b = torch.nn.Conv2d(8, 8, 3, padding=1)
+        self.alias = self.b
+        self.unused = torch.nn.Conv2d(8, 8, 3, padding=1)
+        self.c = torch.nn.Conv2d(8, 1, 1)
+
+    def forward(self, x):
+        return self.c(torch.relu(self.alias(torch.relu(self.a(x)))))
+
+
+def _worker(rank, world, port, overlap, bucket_mb):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = _Net()                                               # same weights on every rank
+    red = GradAllReducer(net.parameters(), bucket_mb=bucket_mb, overlap=overlap)
+    assert sum(len(b) for b in red.buckets) == 8               # a, b, unused, c (weight + bias each); the alias counted once
+    for step in range(2):
+        g = torch.Generator().manual_seed(100 * step + rank)
+        x = torch.randn(4, 3, 8, 8, generator=g)
+        net.zero_grad(set_to_none=True)
+        torch.sqrt(net(x) ** 2 + 1e-4).sum().backward()        # Charbonnier-sum on this rank's batch
+        local = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+        red.finish()
+        for n, p in net.named_parameters():
+            if n.startswith("unused"):
+                assert p.grad is None                          # no rank produced one: stays None (find_unused_parameters)
+                continue
+            parts = [torch.zeros_like(local[n]) for _ in range(world)]
+            dist.all_gather(parts, local[n])
+            want = sum(parts) / world
+            assert torch.allclose(p.grad, want, rtol=1e-6, atol=1e-7), (step, n)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap,bucket_mb", [(True, 9.0), (False, 9.0), (True, 0.001)])
+def test_gradient_allreduce_two_ranks_gloo(overlap, bucket_mb):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, overlap, bucket_mb), nprocs=2, join=True)
+
+
+def test_buckets_follow_reverse_parameter_order():
+    net = _Net()
+    red = GradAllReducer(net.parameters(), bucket_mb=0.001, overlap=False)
+    order = [id(p) for b in red.buckets for p in b]
+    want = []
+    for p in net.parameters():
+        if id(p) not in want:
+            want.append(id(p))
+    assert order == want[::-1] and len(red.buckets) > 1
