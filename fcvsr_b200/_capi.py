@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libfcvsr_b200.so")
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_PRELU = 0, 1, 2, 3
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 
-_T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "l": ctypes.c_longlong, "s": ctypes.c_void_p}
+_T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "d": ctypes.c_double, "l": ctypes.c_longlong, "s": ctypes.c_void_p}
 
 # name -> argument codes, in the order of include/fcvsr_b200.h
 SIGNATURES = {
@@ -43,6 +43,7 @@ SIGNATURES = {
     "fcvsr_subsample2": "pi pi pi iiii i s",
     "fcvsr_conv3x3_c64_to1": "pi p f p p iii s",
     "fcvsr_charbonnier_loss": "pp li i f pp s",
+    "fcvsr_adam_step": "pppp p i dddd d i s",
     "fcvsr_charbonnier_loss_backward": "pp li i f pp pp s",
     "fcvsr_modulated_deform_conv_forward": "ppppp p iiii i ii ii ii ii ii ll i s",
     "fcvsr_modulated_deform_conv_backward": "ppppp ppppp iiii i ii ii ii ii ii p s",

@@ -187,6 +187,14 @@ int fcvsr_charbonnier_loss_backward(const float* x, const float* y, long long nu
                                     const float* grad_out, const double* scratch, float* grad_x, float* grad_y,
                                     cudaStream_t stream);
 
+/* Adam step of the reference's training loop (train_LD_freqCVSR_22.py:204,251: torch.optim.Adam with L2 weight decay, no
+ * amsgrad), multi-tensor: params / grads / exp_avg / exp_avg_sq are HOST arrays of `count` device pointers (fp32), numels
+ * their element counts, step the 1-based step number; hyper-parameters as doubles (1 - beta and the bias corrections are formed
+ * in double on the host, as torch does).  One launch per 64 tensors. */
+int fcvsr_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                    const long long* numels, int count, double lr, double beta1, double beta2, double eps,
+                    double weight_decay, int step, cudaStream_t stream);
+
 /* ---- deformable convolution operator (CVSR_train/ops/dcn) --------------------------------------- */
 
 /* Fused bilinear-gather + GEMM modulated deformable convolution forward, NCHW fp32 exactly as the

@@ -820,3 +820,35 @@ def test_dcn_pack_modules_train(dev, monkeypatch, kind, cin, cout, stride):
         assert a is not None, name
         err = float((a.cpu() - r).abs().max())
         assert err <= 3e-4 * max(1.0, float(r.abs().max())), (name, err)
+
+
+def test_adam_step_matches_torch_adam(dev):
+    """fcvsr_adam_step (multi-tensor, csrc/optim.cu) behind ops.optim.Adam against torch.optim.Adam with the reference's
+    settings (train_LD_freqCVSR_22.py:204: lr 5e-6 scaled up here so that the updates are visible, weight_decay 1e-5), over 70
+    tensors (two launches) of ragged sizes incl. unaligned views and a parameter without gradient, 3 steps + an lr change."""
+    from fcvsr_b200.ops.optim import Adam
+    g = torch.Generator().manual_seed(9)
+    shapes = [(64, 64, 3, 3), (1152, 64, 1, 1), (64,), (1,), (4, 4, 11, 11), (7, 3), (4097,)] * 10
+    ours = [torch.nn.Parameter(torch.randn(*s, generator=g).to(dev)) for s in shapes]
+    refs = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    opt = Adam(ours, lr=2e-3, weight_decay=1e-5)
+    ref = torch.optim.Adam(refs, lr=2e-3, weight_decay=1e-5, foreach=False, fused=False)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[2], gamma=0.25)
+    sched_ref = torch.optim.lr_scheduler.MultiStepLR(ref, milestones=[2], gamma=0.25)
+    for step in range(3):
+        for i, (p, r) in enumerate(zip(ours, refs)):
+            if i == 5:                       # never gets a gradient: skipped by both
+                continue
+            gr = torch.randn(p.shape, generator=g).to(dev)
+            p.grad, r.grad = gr.clone(), gr.clone()
+        opt.step()
+        ref.step()
+        sched.step()
+        sched_ref.step()
+    torch.cuda.synchronize()
+    for i, (p, r) in enumerate(zip(ours, refs)):
+        assert float((p.detach() - r.detach()).abs().max()) <= 2e-6 * max(1.0, float(r.detach().abs().max())), i
+        if i != 5:
+            assert torch.allclose(opt.state[p]["exp_avg_sq"], ref.state[r]["exp_avg_sq"], rtol=2e-6, atol=1e-12)
+            assert torch.allclose(opt.state[p]["exp_avg"], ref.state[r]["exp_avg"], rtol=2e-6, atol=1e-6)
+    assert opt.param_groups[0]["lr"] == ref.param_groups[0]["lr"] == 5e-4
