@@ -69,3 +69,43 @@ def test_buckets_follow_reverse_parameter_order():
         if id(p) not in want:
             want.append(id(p))
     assert order == want[::-1] and len(red.buckets) > 1
+
+
+def _charb(sr, hr):
+    d = sr - hr
+    return torch.sqrt(d * d + 1e-4).sum()                      # opt/loss.py:20-31
+
+
+def _train_worker(rank, world, port):
+    from fcvsr_b200.train import replicas_in_sync, train_step
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = _Net()
+    opt = torch.optim.Adam(net.parameters(), lr=5e-4, weight_decay=1e-5)
+    red = GradAllReducer(net.parameters())
+    # single-process twin: the concatenated batch with the learning rate divided by the world size (sum-reduced loss)
+    torch.manual_seed(0)
+    twin = _Net()
+    opt_twin = torch.optim.Adam(twin.parameters(), lr=5e-4, weight_decay=1e-5)
+    for step in range(3):
+        xs = [torch.randn(2, 3, 8, 8, generator=torch.Generator().manual_seed(10 * step + r)) for r in range(world)]
+        hs = [torch.rand(2, 1, 8, 8, generator=torch.Generator().manual_seed(77 * step + r)) for r in range(world)]
+        train_step(net, opt, xs[rank], hs[rank], _charb, red)
+        opt_twin.zero_grad(set_to_none=True)
+        (_charb(twin(torch.cat(xs)), torch.cat(hs)) / world).backward()
+        opt_twin.step()
+    assert replicas_in_sync(net)
+    for (n, p), q in zip(net.named_parameters(), twin.parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), n
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_train_step_two_ranks_gloo():
+    """Two replicas stepping through fcvsr_b200.train.train_step stay identical and equal a single process on the concatenated
+    batch whose (sum-reduced) loss is divided by the world size -- the 1/G effective learning rate of SURVEY 8e."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_train_worker, args=(2, port), nprocs=2, join=True)
