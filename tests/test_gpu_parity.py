@@ -852,3 +852,40 @@ def test_adam_step_matches_torch_adam(dev):
             assert torch.allclose(opt.state[p]["exp_avg_sq"], ref.state[r]["exp_avg_sq"], rtol=2e-6, atol=1e-12)
             assert torch.allclose(opt.state[p]["exp_avg"], ref.state[r]["exp_avg"], rtol=2e-6, atol=1e-6)
     assert opt.param_groups[0]["lr"] == ref.param_groups[0]["lr"] == 5e-4
+
+
+def test_cuda_train_step_on_dcn_pack_module(dev, monkeypatch):
+    """fcvsr_b200.train.train_step with every piece on this library's kernels -- ModulatedDeformConvPack forward / backward (DCN
+    + conv_offset_mask), CharbonnierLoss forward / backward, multi-tensor Adam -- against a CPU twin built from F.conv2d, the
+    oracle DCN and torch.optim.Adam: same loss trajectory over 4 steps, and the loss goes down."""
+    import fcvsr_b200.ops.dcn as dcn_mod
+    from fcvsr_b200.ops.loss import CharbonnierLoss
+    from fcvsr_b200.ops.optim import Adam
+    from fcvsr_b200.train import train_step
+    monkeypatch.setattr(dcn_mod, "PRECISION", "fp32")
+    torch.manual_seed(21)
+    m = dcn_mod.ModulatedDeformConvPack(8, 8, 3, stride=1, padding=1, deformable_groups=2).to(dev)
+    with torch.no_grad():
+        m.conv_offset_mask.weight.normal_(0, 0.05)
+        m.conv_offset_mask.bias.normal_(0, 0.3)
+    twin = {k: v.detach().cpu().clone().requires_grad_() for k, v in m.named_parameters()}
+    opt = Adam(m.parameters(), lr=2e-3, weight_decay=1e-5)
+    opt_twin = torch.optim.Adam(list(twin.values()), lr=2e-3, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 8, 12, 14, generator=g)
+    hr = torch.randn(2, 8, 12, 14, generator=g)
+    xd, hd = x.to(dev), hr.to(dev)
+    losses, losses_twin = [], []
+    for _ in range(4):
+        losses.append(float(train_step(m, opt, xd, hd, CharbonnierLoss)))
+        opt_twin.zero_grad(set_to_none=True)
+        o = F.conv2d(x, twin["conv_offset_mask.weight"], twin["conv_offset_mask.bias"], padding=1)
+        o1, o2, mk = torch.chunk(o, 3, dim=1)
+        y = O.modulated_deform_conv(x, torch.cat((o1, o2), 1), torch.sigmoid(mk), twin["weight"], twin["bias"], 1, 1, 1, 1, 2)
+        lt = O.charbonnier_sum(y, hr)
+        lt.backward()
+        opt_twin.step()
+        losses_twin.append(float(lt.detach()))
+    assert losses[-1] < losses[0]
+    for a, b in zip(losses, losses_twin):
+        assert abs(a - b) <= 2e-3 * abs(b), (losses, losses_twin)
