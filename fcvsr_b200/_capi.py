@@ -21,7 +21,6 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "d": ctypes.
 SIGNATURES = {
     "fcvsr_conv2d_direct": "pii pp pi pi pi iiiiiii if p ii pii i s",
     "fcvsr_conv2d_tc": "pi pp pi pi pi iiiiii if p i pii i i s",
-    "fcvsr_conv3x3_tc_resident": "pi pi p pi pi pi iiiii if p i pii i i s",
     "fcvsr_fft_r2c_w": "pi p p iiii s",
     "fcvsr_fft_c2c_h": "p p p p iiii i f ii p s",
     "fcvsr_fft_c2r_w": "p pi p iiii f s",
@@ -39,6 +38,7 @@ SIGNATURES = {
     "fcvsr_pixel_shuffle": "pi pi iiii i s",
     "fcvsr_bilinear_up4": "p l p iii s",
     "fcvsr_fill_channels": "p iii f l s",
+    "fcvsr_quantize_u8": "pp iiiii s",
     "fcvsr_pack_clip": "p p iiii i s",
     "fcvsr_subsample2": "pi pi pi iiii i s",
     "fcvsr_conv3x3_c64_to1": "pi p f p p iii s",

@@ -499,8 +499,10 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     p.n_tile = n_tile; p.n_tiles = n_tiles;
     {   // 1x1: four sets (epilogue-bound, 4-16 MMAs per tile); 3x3 bf16: two sets (64->64 24.8 -> 22.0 us, 64->256 at 360x640
         // 296 -> 272 us = 1.0 PFLOP/s); 3x3 TF32 (twice the MMAs per tile): one set, all warps on the same tile
-        static int es = -1;
-        if (es < 0) { const char* e = getenv("FCVSR_EPI_SETS"); es = e ? atoi(e) : 0; }
+        int es = 0;
+#ifdef FCVSR_BRINGUP
+        { static int es_env = -1; if (es_env < 0) { const char* e = getenv("FCVSR_EPI_SETS"); es_env = e ? atoi(e) : 0; } es = es_env; }
+#endif
         p.epi_sets = es == 1 || es == 2 || es == 4 ? es : (ksize == 1 ? 4 : (op16 ? 2 : 1));
     }
     p.tiles_x = (W + TC_TW - 1) / TC_TW; p.tiles_y = (H + TC_TH - 1) / TC_TH;
@@ -512,11 +514,12 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
         const int esz_y = ((op16 && round_out) || round_out == 2) ? 2 : 4, esz_y2 = op16 ? 2 : 4;
         p.wide = !thin && !(a & 31) && !((ldy * esz_y) & 31) && (!res || !((ldres * 4) & 31)) && (!y2 || !((ldy2 * esz_y2) & 31)) &&
                  (!pixel_shuffle || !(((Cout >> 2) * esz_y) & 31));
-        static int narrow = -1;                     // bring-up: force the 128-bit epilogue accesses
-        if (narrow < 0) narrow = getenv("FCVSR_TC_NARROW") ? 1 : 0;
-        if (narrow) p.wide = 0;
     }
+    p.dbg = 0;
+#ifdef FCVSR_BRINGUP      // bring-up switches (tools/gpu_conv_trace.py builds its own copy with -DFCVSR_BRINGUP); not in the product library
+    { static int narrow = -1; if (narrow < 0) narrow = getenv("FCVSR_TC_NARROW") ? 1 : 0; if (narrow) p.wide = 0; }
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FCVSR_TC_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+#endif
 
     static int num_sms = 0;
     static bool attr_set = false;
@@ -535,8 +538,10 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     }
     int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;   // leave SMs to kernels running on other streams
-    static int pdl = -1;
-    if (pdl < 0) { const char* e = getenv("FCVSR_PDL"); pdl = e ? atoi(e) : 1; }
+    int pdl = 1;
+#ifdef FCVSR_BRINGUP
+    { static int pdl_env = -1; if (pdl_env < 0) { const char* e = getenv("FCVSR_PDL"); pdl_env = e ? atoi(e) : 1; } pdl = pdl_env; }
+#endif
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];

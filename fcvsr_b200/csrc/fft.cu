@@ -413,9 +413,11 @@ __global__ void __launch_bounds__(FFT2_THREADS_MAX, 3) fft2_c2r_w_kernel(const f
 
 // N = r1 * r2 with both radices built (r1 >= r2, most balanced pair); false -> use the Stockham kernels
 static bool make_plan2(int n, int* r1, int* r2) {
+#ifdef FCVSR_BRINGUP
     static int legacy = -1;
     if (legacy < 0) { const char* e = getenv("FCVSR_FFT_LEGACY"); legacy = e ? atoi(e) : 0; }
     if (legacy) return false;
+#endif
 #define FFT2_LIST(R) R,
     static const int rad[] = {FFT2_FOR_EACH_RADIX(FFT2_LIST)};
 #undef FFT2_LIST
@@ -434,8 +436,10 @@ static int fft2_threads(int r1, int r2, int cbl) {
 // ------------------------------------------------------------------------------------------------
 static int pick_cb_log2(int n, int lanes, int two_phase = 0) {
     // largest power of two CB <= 16 that divides `lanes` and keeps 2*n*CB*8 + n*8 <= ~200 KB
-    static int cap = -1;
-    if (cap < 0) { const char* e = getenv("FCVSR_FFT_CBL"); cap = e ? atoi(e) : 4; }
+    int cap = 4;
+#ifdef FCVSR_BRINGUP
+    { static int cap_env = -1; if (cap_env < 0) { const char* e = getenv("FCVSR_FFT_CBL"); cap_env = e ? atoi(e) : 4; } cap = cap_env; }
+#endif
     // two-phase kernels: 8 lanes per block (64-byte segments) keep 3-4 blocks of ~100-register threads resident per SM
     int cbl = two_phase && cap > 3 ? 3 : cap;
     while (cbl > 0 && ((lanes % (1 << cbl)) != 0 || (size_t)(2 * (size_t)n * (1 << cbl) + n) * 8 > 200 * 1024)) --cbl;

@@ -211,3 +211,23 @@ extern "C" int fcvsr_subsample2(const float* x, int ldx, float* y, int ldy, void
     subsample2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, ldx, y, ldy, y2, ldy2, H, W, C / 4, total, op16);
     return fcvsr_launch_status();
 }
+
+// ---- 8-bit output of the evaluation drivers (CVSR_train/test_LD_freqCVSR.py:85-93) ----------------------------------------
+// out[b, y, x] = (uint8) trunc(clamp(v[b, y, x], 0, 1) * 255) for the top-left Ho x Wo crop of a [B, H, W] fp32 plane: the
+// reference crops the padded rows, clamps, scales and converts with numpy's astype(np.uint8) (truncation toward zero).
+__global__ void quantize_u8_kernel(const float* __restrict__ v, unsigned char* __restrict__ out, int H, int W, int Ho, int Wo,
+                                   size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % Wo), y = (int)((idx / Wo) % Ho);
+    const size_t b = idx / ((size_t)Wo * Ho);
+    const float f = fminf(fmaxf(v[(b * H + y) * W + x], 0.f), 1.f) * 255.0f;     // NaN -> 0 through fmaxf
+    out[idx] = (unsigned char)(int)f;
+}
+
+extern "C" int fcvsr_quantize_u8(const float* v, unsigned char* out, int B, int H, int W, int Ho, int Wo, cudaStream_t st) {
+    if (!v || !out || B <= 0 || Ho <= 0 || Wo <= 0 || Ho > H || Wo > W) return FCVSR_ERR_ARG;
+    const size_t total = (size_t)B * Ho * Wo;
+    quantize_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v, out, H, W, Ho, Wo, total);
+    return fcvsr_launch_status();
+}

@@ -83,14 +83,6 @@ class _ConvPack:
         # nearest here (cvt.rna semantics) removes their share of the truncation bias for free.
         self.w_tc = wt.contiguous().to(torch.bfloat16) if op16 else _round_tf32(wt.contiguous())
         self.tc_ok = stride == 1 and k in (1, 3) and cin % (64 if op16 else 32) == 0 and (cout < 16 or cout % 16 == 0)
-        # resident-weight kernel (conv_tc2.cu): k = 3, Cout % 64 == 0 and a weight slab of one 64/128-column pass that
-        # fits in shared memory: Cin in {64, 128} (bf16) or {32, 64} (TF32); TF32 Cin = 128 runs as two K-halves
-        # chained through the `pre` addend
-        self.tc2_ok = stride == 1 and k == 3 and cout % 64 == 0 and cin in ((64, 128) if op16 else (32, 64, 128))
-        self.w_tc_halves = None
-        if self.tc2_ok and cin == 128 and not op16:
-            w4 = self.w_tc.view(cout, 9, cin)
-            self.w_tc_halves = [w4[:, :, :64].reshape(cout, 9 * 64).contiguous(), w4[:, :, 64:].reshape(cout, 9 * 64).contiguous()]
 
 
 class Engine:
@@ -114,22 +106,26 @@ class Engine:
         self.tc_launches = 0
         self.use_graph = False       # replay the launch sequence from a CUDA graph (one per input shape)
         self._graphs: Dict[tuple, tuple] = {}
-        # resident-weight 3x3 kernel (conv_tc2.cu): off by default -- after the epilogue / barrier-poll fixes conv_tc.cu
-        # is as fast or faster on every trunk shape (profiles/r1_notes.md).  FCVSR_TC2=1: wherever eligible;
-        # FCVSR_TC2=auto: Cout = 64 passes only
-        self.use_tc2 = {"1": True, "auto": "auto"}.get(os.environ.get("FCVSR_TC2", ""), False)
-        self._ksplit = {}
         self.max_ctas = 0            # grid cap of the tensor-core convs on the current stream (0 = all SMs)
         self.multi_stream = True     # run the three pyramid levels of SCNetbk on three streams
-        self.tc_pyramid = os.environ.get("FCVSR_TC_PYRAMID", "1") != "0"   # rconcat1/2 as stride-1 tcgen05 convs + sampling
-        self.iac16 = os.environ.get("FCVSR_IAC16", "1") != "0"      # IAC ping-pong tensors in bf16 (bf16 mode only)
-        self.res16 = os.environ.get("FCVSR_RES16", "1") != "0"      # RCB body output as a bf16 tensor (bf16 mode only)
-        self.r016 = os.environ.get("FCVSR_R016", "1") != "0"        # RCB input / skip r0 only as a bf16 tensor (bf16 mode)
-        self.rr16 = os.environ.get("FCVSR_RR16", "1") != "0"        # RCB output rr only as a bf16 tensor (bf16 mode)
-        self.t16 = os.environ.get("FCVSR_T16", "1") != "0"          # cross-level terms td / tu as bf16 tensors (bf16 mode)
-        self.use_last_kernel = os.environ.get("FCVSR_LAST_KERNEL", "1") != "0"   # dedicated Cout = 1 kernel (bf16 mode)
+        # layout choices of the bf16 mode, each measured as an A/B in round 1 (profiles/r1_notes.md 6b); plain attributes so
+        # that the tools under tools/ can flip them -- nothing in the product path reads the environment
+        self.tc_pyramid = True       # rconcat1/2 as stride-1 tcgen05 convs + sampling
+        self.iac16 = True            # IAC ping-pong tensors in bf16
+        self.res16 = True            # RCB body output as a bf16 tensor
+        self.r016 = True             # RCB input / skip r0 only as a bf16 tensor
+        self.rr16 = True             # RCB output rr only as a bf16 tensor
+        self.t16 = True              # cross-level terms td / tu as bf16 tensors
+        self.use_last_kernel = True  # dedicated Cout = 1 kernel
+        self.mgaa_ctas = 74          # SM cap of each of the two concurrently running MGAA calls
+        self.level_caps = None       # SM split of the three SCNet pyramid streams (None: by tile count)
+        self.stop_after = None       # tools/gpu_phase_times.py: return after "mgaa_pair" | "mgaa" | "mffr" | "scnet"
+        self.profile_flavor = False  # tools: per-launch profile entries also name the output flavour
+        self.clone_output = True     # graph mode: return a copy of the static output buffer (False: the buffer itself,
+                                     # valid until the next call)
         self._streams = {}
-        self.profile = None          # optional list: (kind, flops, start_event, end_event) per conv launch
+        self.profile = None          # optional list: (kind, flops, bytes, start_event, end_event) per launch
+        self.profile_in_graph = False  # the events are graph nodes (external events) and the pyramid streams stay on
         C.lib()                      # fail loudly now if the library is missing
 
     # -------------------------------------------------------------------------------------------
@@ -338,7 +334,7 @@ class Engine:
         prof = self.profile
         if prof is not None:
             ho, wo = (H - 1) // pk.stride + 1, (W - 1) // pk.stride + 1
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0, e1 = self._event_pair()
             e0.record()
             try:
                 self.profile = None
@@ -351,7 +347,7 @@ class Engine:
             kind = "tc" if (self.use_tc and pk.tc_ok and not nchw) else "direct"
             if kind == "tc":
                 kind = f"tc {pk.cin_logical}->{pk.cout} k{pk.k} {H}x{W}"
-                if os.environ.get("FCVSR_PROFILE_FLAVOR"):
+                if self.profile_flavor:
                     kind += f" out={'op' if rnd is True or rnd == 1 else ('f16' if rnd == 2 else 'f32')}{'+y2' if y2 else ''}{'+res' if res else ''}"
             prof.append((kind, 2.0 * B * ho * wo * pk.cin_logical * pk.cout * pk.k * pk.k,
                          4.0 * B * (H * W * pk.cin_logical + ho * wo * pk.cout), e0, e1))
@@ -359,30 +355,6 @@ class Engine:
         o16 = int(self.op16 if op16 is None else op16)
         if not self.use_tc:          # exact-fp32 mode: nothing is rounded to TF32
             y2, ldy2, rnd = 0, 0, False
-        tc2 = self.use_tc2 and pk.tc2_ok
-        if tc2 and self.use_tc2 == "auto":
-            tc2 = pk.cout == 64 and pk.w_tc_halves is None and not pk.ps
-        if self.use_tc and tc2 and not nchw and not res2 and o16 == int(self.op16):
-            bias = pk.bias.data_ptr() if pk.bias is not None else 0
-            common = (B, H, W)
-            if pk.w_tc_halves is not None:
-                tmp = self._ksplit_buf(B * H * W * pk.cout, x)
-                C.call("fcvsr_conv3x3_tc_resident", x, ldx, pk.w_tc_halves[0].data_ptr(), 576, 0, 0, 0, 0, 0, tmp, pk.cout,
-                       *common, 64, pk.cout, C.ACT_NONE, 0.0, 0, 0, 0, 0, 0, self.max_ctas, 0, st)
-                C.call("fcvsr_conv3x3_tc_resident", x + 64 * 4, ldx, pk.w_tc_halves[1].data_ptr(), 576, bias, tmp, pk.cout,
-                       res, ldres, y, ldy, *common, 64, pk.cout, act, slope, slope_ptr, int(pk.ps), y2, ldy2, int(rnd),
-                       self.max_ctas, 0, st)
-                self.launches += 1
-                self.tc_launches += 2
-                return
-            rc = C.try_call("fcvsr_conv3x3_tc_resident", x, ldx, pk.w_tc.data_ptr(), 9 * pk.cin, bias, 0, 0, res, ldres, y,
-                            ldy, *common, pk.cin, pk.cout, act, slope, slope_ptr, int(pk.ps), y2, ldy2, int(rnd),
-                            self.max_ctas, o16, st)
-            if rc == 0:
-                self.tc_launches += 1
-                return
-            if rc != C.ERR_UNSUPPORTED:
-                raise RuntimeError(f"fcvsr_conv3x3_tc_resident failed with status {rc}")
         if self.op16 and (rnd or y2) and not (pk.tc_ok and not nchw) and rnd:
             raise RuntimeError("bf16 operand output requested from a convolution the tensor-core kernel cannot run")
         if self.use_tc and pk.tc_ok and not nchw:
@@ -414,20 +386,57 @@ class Engine:
                     best = (key, (c0, c1, c2))
         return best[1]
 
-    def _ksplit_buf(self, numel, x_ptr):
-        """Scratch for the first K-half of a Cin = 128 convolution, one per stream (levels run concurrently)."""
-        key = self.st
-        t = self._ksplit.get(key)
-        if t is None or t.numel() < numel:
-            t = torch.empty(numel, device=self._dev, dtype=F32)
-            self._ksplit[key] = t
-        return t.data_ptr()
+    def _event_pair(self):
+        # inside a graph capture only "external" events become event-record nodes whose times can be read after a replay
+        kw = dict(enable_timing=True, external=True) if self.profile_in_graph else dict(enable_timing=True)
+        return torch.cuda.Event(**kw), torch.cuda.Event(**kw)
+
+    def profile_graph_replay(self, x: torch.Tensor, reps: int = 5):
+        """Per-launch device times of the GRAPH-REPLAYED step: the launch sequence is captured once more with an event-record
+        node before and after every launch (on the stream it is launched on; the pyramid / MGAA streams stay concurrent, so
+        the times include the interference between concurrently running kernels), replayed `reps` times, and the elapsed
+        times of each pair are averaged.  Returns [(kind, flops, bytes, mean_ms)] in launch order plus the mean replay time.
+        Differences to the production graph: the event nodes cut the programmatic-dependent-launch edges between
+        back-to-back convolutions (~2 us per launch)."""
+        B, T, Cc, H, W = x.shape
+        dev = x.device
+        with torch.cuda.device(dev), torch.no_grad():
+            self._dev = dev
+            self._ensure_packs(dev)
+            ws = self._workspace(B, H, W, dev)
+            sx = x.clone()
+            so = torch.empty(B, 1, 4 * H, 4 * W, device=dev, dtype=F32)
+            self.st = torch.cuda.current_stream().cuda_stream
+            self._run(sx, so, ws, B, H, W)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            self.profile, self.profile_in_graph = [], True
+            try:
+                with torch.cuda.graph(g):
+                    self.st = torch.cuda.current_stream().cuda_stream
+                    self._run(sx, so, ws, B, H, W)
+            finally:
+                prof, self.profile, self.profile_in_graph = self.profile, None, False
+            g.replay()
+            torch.cuda.synchronize()
+            acc = [0.0] * len(prof)
+            total = 0.0
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(reps):
+                t0.record()
+                g.replay()
+                t1.record()
+                torch.cuda.synchronize()
+                total += t0.elapsed_time(t1)
+                for i, (_, _, _, e0, e1) in enumerate(prof):
+                    acc[i] += e0.elapsed_time(e1)
+        return [(k, fl, by, a / reps) for (k, fl, by, _, _), a in zip(prof, acc)], total / reps
 
     def _k(self, name, *args):
         self.launches += 1
         prof = self.profile
         if prof is not None:        # per-launch CUDA events (bench.py roofline pass / tools/gpu_breakdown.py)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0, e1 = self._event_pair()
             e0.record()
             C.call(name, *args, self.st)
             e1.record()
@@ -479,9 +488,18 @@ class Engine:
             self._graphs = {k: v for k, v in self._graphs.items() if k[-1] == self._pack_key}
             self._graphs[key] = (g, sx, so, self.launches, self.tc_launches)
         g, sx, so, self.launches, self.tc_launches = self._graphs[key]
-        sx.copy_(x)
+        if x.data_ptr() != sx.data_ptr():          # a caller that fills `static_input()` in place skips this copy
+            sx.copy_(x)
         g.replay()
-        return so.clone()
+        return so.clone() if self.clone_output else so
+
+    def static_input(self, B, H, W, device) -> Optional[torch.Tensor]:
+        """Graph mode: the captured input buffer of shape [B,7,1,H,W] (None before the first call with that shape).  Writing
+        the clip into it (e.g. the H2D copy of a streaming driver) and passing it to forward() avoids one device copy."""
+        for k, v in self._graphs.items():
+            if k[:4] == (B, H, W, str(device)):
+                return v[1]
+        return None
 
     def _run(self, x, out, ws, B, H, W):
         m, P = self.model, self.packs
@@ -497,13 +515,13 @@ class Engine:
         # MGAA(f1) -> feat[128:192], MGAA(f3) -> feat[256:320]: cat[o1, f2, o3] (:2720) is then the
         # contiguous channel slice feat[128:320] and no concatenation is materialised.
         main = torch.cuda.current_stream()
-        if self.multi_stream and self.profile is None:
+        if self.multi_stream and (self.profile is None or self.profile_in_graph):
             dev = main.device
             if dev not in self._streams:
                 self._streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
             side = self._streams[dev][0]
             side.wait_stream(main)
-            self.max_ctas = int(os.environ.get("FCVSR_MGAA_CTAS", "74"))      # two tensor-core conv grids share the 148 SMs
+            self.max_ctas = self.mgaa_ctas                                    # two tensor-core conv grids share the 148 SMs
             self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)
             with torch.cuda.stream(side):
                 self.st = side.cuda_stream
@@ -514,7 +532,7 @@ class Engine:
         else:
             self._mgaa(ws, p, f + 0 * 4, 448, f + 128 * 4, 448, B, H, W)
             self._mgaa(ws, p, f + 256 * 4, 448, f + 256 * 4, 448, B, H, W)
-        stop = os.environ.get("FCVSR_STOP_AFTER", "")              # bring-up: cumulative phase timing (tools/gpu_phase_times.py)
+        stop = self.stop_after
         if stop == "mgaa_pair":
             return
         self._mgaa(ws, p, f + 128 * 4, 448, p["m2"], 64, B, H, W)
@@ -659,15 +677,15 @@ class Engine:
         rr16 = int(bool(O16) and self.rr16)
         t16 = 4 if (O16 and self.t16) else 0      # down / up conv outputs td, tu as bf16 tensors (flag bit of level_mix)
         main = torch.cuda.current_stream()
-        ms = self.multi_stream and self.profile is None
+        ms = self.multi_stream and (self.profile is None or self.profile_in_graph)
         if ms:
             dev = main.device
             if dev not in self._streams:
                 self._streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
             streams = (main,) + self._streams[dev]
             caps = self._level_caps(B, dims)   # SMs given to each level's persistent conv grid (sum = 148)
-            if os.environ.get("FCVSR_CAPS"):
-                caps = tuple(int(v) for v in os.environ["FCVSR_CAPS"].split(","))
+            if self.level_caps is not None:
+                caps = tuple(self.level_caps)
             for s_ in streams[1:]:
                 s_.wait_stream(main)
         else:

@@ -17,6 +17,12 @@ class _Charbonnier(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, mean_res):
         x, y = x.contiguous(), y.contiguous()
+        # the forward kernel reads 16-byte lanes: a contiguous view with a storage offset (sr[1:], narrow()) can be
+        # misaligned, which the reference accepts -- realign it with a copy instead of failing
+        if x.data_ptr() % 16:
+            x = x.clone()
+        if y.data_ptr() % 16:
+            y = y.clone()
         scratch = torch.empty(max(592, x.shape[0]), device=x.device, dtype=torch.float64)
         out = torch.empty((), device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):

@@ -18,6 +18,17 @@ class Adam(torch.optim.Optimizer):
             raise ValueError("invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
+    def load_state_dict(self, state_dict):
+        """Accepts a torch.optim.Adam state dict: torch stores `step` as a tensor -- normalised to int here (a tensor key would
+        hash by identity and force one launch and one host sync per parameter); amsgrad / maximize groups are refused."""
+        for g in state_dict.get("param_groups", []):
+            if g.get("amsgrad") or g.get("maximize"):
+                raise ValueError("fcvsr_b200.ops.optim.Adam does not implement amsgrad / maximize (the reference uses neither)")
+        super().load_state_dict(state_dict)
+        for st in self.state.values():
+            if "step" in st:
+                st["step"] = int(st["step"])
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -38,7 +49,7 @@ class Adam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["step"] += 1
+                st["step"] = int(st["step"]) + 1
                 if not p.is_contiguous():
                     raise RuntimeError("Adam expects contiguous parameters")
                 by_step.setdefault((st["step"], p.device), []).append((p, p.grad.contiguous(), st["exp_avg"], st["exp_avg_sq"]))

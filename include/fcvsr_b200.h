@@ -65,18 +65,6 @@ int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, 
                     int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
                     float* y2, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t stream);
 
-/* Second-generation tcgen05 3x3 convolution: the [NP x 9*Cin] weight slab of each NP-column pass (NP = 128 or 64,
- * whichever fits) stays RESIDENT in shared memory and the haloed input tile is loaded once (no-swizzle K-major
- * layout, cp.async), so L2->SM traffic drops from ~8x to ~1.4x the input bytes.  k = 3, stride 1, Cout % 64 == 0,
- * Cin in {32, 64} (op16 = 0, TF32 operands) or {64, 128} (op16 = 1, bf16 operands); other shapes return
- * FCVSR_ERR_UNSUPPORTED.  w is [Cout][ldw] K-major with columns (ky,kx,cin).  v = act(acc + bias + pre) + res,
- * same store options as fcvsr_conv2d_tc (`pre` chains the two K-halves of a TF32 Cin = 128 convolution).
- * Same reference call sites as fcvsr_conv2d_tc. */
-int fcvsr_conv3x3_tc_resident(const void* x, int ldx, const void* w, int ldw, const float* bias, const float* pre,
-                              int ldpre, const float* res, int ldres, float* y, int ldy, int B, int H, int W, int Cin,
-                              int Cout, int act, float slope, const float* slope_ptr, int pixel_shuffle, float* y2,
-                              int ldy2, int round_out, int max_ctas, int op16, cudaStream_t stream);
-
 /* ---- FFT (torch.fft.rfft2 / irfft2 / fftn / ifftn of CVSR_freq.py:1452-1454, :1499-1504, :2082-2088) */
 
 /* tw: float2[N] = exp(-2 pi i k / N) for the transform length N (W for *_w, H for *_h). */
@@ -171,6 +159,9 @@ int fcvsr_subsample2(const float* x, int ldx, float* y, int ldy, void* y2, int l
 /* NCHW clip [B,T,H,W] -> NHWC [B,H,W,32] (channels >= T zero, TF32-rounded): tensor-core operand of feat_extract */
 int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int W, int op16, cudaStream_t stream);
 int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npix, cudaStream_t stream);
+/* 8-bit output of the evaluation driver (CVSR_train/test_LD_freqCVSR.py:85-93: crop the padded rows, clamp to [0,1], * 255,
+ * numpy astype(uint8) = truncation): out [B,Ho,Wo] uint8 = trunc(clamp(v[b, y < Ho, x < Wo], 0, 1) * 255) of v [B,H,W] fp32. */
+int fcvsr_quantize_u8(const float* v, unsigned char* out, int B, int H, int W, int Ho, int Wo, cudaStream_t stream);
 
 /* ---- training loss (CVSR_train/opt/loss.py:20-31)       ---------------------------------------- */
 

@@ -1,0 +1,270 @@
+"""GPU parity tests of single hot-path kernels against the oracle's block functions (run on the B200 box).
+
+Round 1 covered `corr_gather`, `offset_blocks`, `iac_step` and the DivEnh chain only through whole-model stage taps at
+64x64 / 36x40.  Here each kernel is called directly through the C ABI on seeded inputs at ragged sizes (tile remainders in
+both directions), with every storage flavour the engine uses (fp32 / TF32-rounded / bf16 tensors, fp16 filter taps), and
+compared with the matching function of oracle/fcvsr_oracle.py (itself pinned to the live reference in tests/test_oracle.py).
+Also: FCVSR-S at BASELINE config 5b's 540x960 (FFT radix pairs 27*20 and 32*30), and the DCN backward on the tensors the
+tcgen05 forward saved.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from fcvsr_b200 import _capi as C, arch
+from fcvsr_b200.engine import Engine
+from oracle import fcvsr_oracle as O
+from tests.util import make_clip, nchw, nhwc, psnr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# CorrBlock lookup (CVSR_freq.py:1279-1337)
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,mode", [(1, 12, 20, 0), (2, 70, 18, 0), (2, 9, 14, 1), (1, 70, 12, 2)])
+def test_corr_gather_kernel(dev, B, H, W, mode):
+    """fcvsr_corr_gather on an interleaved spectrum against oracle.corr_lookup on the reference's cat([imag, real]) packing;
+    H = 70 > 68 exercises the rows where the 64x2 'image' reinterpretation runs out; op_mode 1 / 2 store
+    TF32-rounded / bf16 values (the engine's tensor-core operand flavours)."""
+    Wf = W // 2 + 1
+    g = torch.Generator().manual_seed(B * 100 + H + mode)
+    z1 = torch.complex(torch.randn(B, 64, H, Wf, generator=g), torch.randn(B, 64, H, Wf, generator=g))
+    z2 = torch.complex(torch.randn(B, 64, H, Wf, generator=g), torch.randn(B, 64, H, Wf, generator=g))
+    ref = O.corr_lookup(torch.cat([z1.imag, z1.real], 1), torch.cat([z2.imag, z2.real], 1))        # [B,81,H,Wf]
+    S = torch.zeros(B, H * Wf, 384)
+    for k, z in ((0, z1), (1, z2)):
+        zz = z.permute(0, 2, 3, 1).reshape(B, H * Wf, 64)
+        S[:, :, 128 * k:128 * k + 128:2] = zz.real
+        S[:, :, 128 * k + 1:128 * k + 128:2] = zz.imag
+    Sd = S.to(dev)
+    ldo = 96
+    out = torch.zeros(B, H * Wf, ldo, device=dev, dtype=torch.bfloat16 if mode == 2 else torch.float32)
+    C.call("fcvsr_corr_gather", Sd.data_ptr(), 384, 0, 128, out.data_ptr() + 8 * out.element_size(), ldo, B, H, Wf, 128, mode, _st())
+    torch.cuda.synchronize()
+    got = out.float().cpu()[:, :, 8:89].reshape(B, H, Wf, 81).permute(0, 3, 1, 2)
+    tol = {0: 1e-6, 1: 2.0 ** -11, 2: 2.0 ** -8}[mode] * max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) <= tol
+    assert float(out.float().cpu()[:, :, :8].abs().max()) == 0.0 and float(out.float().cpu()[:, :, 89:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# ConvBlk x ACNum on the 4-channel frequency maps (CVSR_freq.py:344-357, :1494-1498)
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant,B,H,W", [("full", 1, 20, 24), ("S", 2, 13, 30), ("full", 2, 9, 10)])
+def test_offset_blocks_kernel(dev, variant, B, H, W):
+    """fcvsr_offset_blocks (all iterations, both directions, kernel sizes 1..11) against oracle.conv_blk * sim, incl. maps
+    smaller than the largest kernel (9x6 bins under an 11x11 filter) and quad / block remainders."""
+    Wf = W // 2 + 1
+    P = H * Wf
+    sd = arch.seeded_state_dict(variant, 0)
+    m = (arch.GShiftNet if variant == "full" else arch.GShiftNet_S)().to(dev).eval()
+    m.load_state_dict(sd)
+    eng = Engine(m, mode="fp32")
+    eng._ensure_packs(dev)
+    Pk, A = eng.packs, m.ACNum
+    g = torch.Generator().manual_seed(17 + H)
+    off = torch.randn(2, B, 4, H, Wf, generator=g)
+    sim = torch.randn(B, 4, H, Wf, generator=g)
+    offd = off.permute(0, 1, 3, 4, 2).contiguous().to(dev)                 # [2][B][P][4]
+    simd = nhwc(sim).to(dev)
+    t1 = torch.empty(A, 2 * B, P, 4, device=dev)
+    t2 = torch.empty_like(t1)
+    part = torch.empty(A * 2 * B * ((P + 127) // 128) * 4, device=dev)
+    z = torch.empty(B, P, 8 * A, device=dev)
+    C.call("fcvsr_offset_blocks", offd.data_ptr(), Pk["ob_w1"].data_ptr(), Pk["ob_w2"].data_ptr(), Pk["ob_prelu"].data_ptr(),
+           Pk["ob_ca"].data_ptr(), simd.data_ptr(), 4, t1.data_ptr(), t2.data_ptr(), part.data_ptr(), z.data_ptr(), B, H, Wf, A,
+           _st())
+    torch.cuda.synchronize()
+    zc = z.cpu().view(B, H, Wf, 2 * A, 2, 2)                               # [..., it*2+dir, m, (re, im)]
+    for i in range(A):
+        for d in range(2):
+            o = O.conv_blk(sd, f"MGAA.MConvB.{i}", off[d]) * sim           # [B,4,H,Wf]; complex(o[0:2], o[2:4]) (:1497-1498)
+            want = torch.stack([o[:, 0:2], o[:, 2:4]], -1).permute(0, 2, 3, 1, 4)       # [B,H,Wf,m,(re,im)]
+            err = float((zc[:, :, :, i * 2 + d] - want).abs().max())
+            assert err <= 2e-5 * max(1.0, float(want.abs().max())), (i, d, err)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# IAC iteration (flow_warp + SAC + residual + LeakyReLU, CVSR_freq.py:1188-1276)
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,taps_half,prev16,ro", [(1, 19, 37, 0, 0, 0), (2, 8, 16, 1, 0, 0), (1, 25, 18, 1, 0, 1),
+                                                      (1, 19, 37, 1, 1, 2), (2, 12, 20, 1, 1, 0), (1, 33, 35, 1, 0, 2)])
+def test_iac_step_kernel(dev, B, H, W, taps_half, prev16, ro):
+    """fcvsr_iac_step for both directions against oracle.warp_bilinear + oracle.sac (+ x_in, LeakyReLU 0.1) with offsets that
+    leave the image (zero fill), ragged 8x16 tiles, fp16 taps (the tensor-core modes), bf16 ping-pong inputs (flag 4) and
+    TF32-rounded / bf16 outputs -- every flavour engine._mgaa uses."""
+    g = torch.Generator().manual_seed(H * W + taps_half + 2 * prev16 + 4 * ro)
+    prev = [torch.randn(B, 64, H, W, generator=g) for _ in range(2)]
+    xin = [torch.randn(B, 64, H, W, generator=g) for _ in range(2)]
+    off = [3.0 * torch.randn(B, 2, H, W, generator=g) for _ in range(2)]
+    off[0][:, :, 0, 0] = torch.tensor([-40.0, 55.0])                      # far outside
+    taps = 0.6 * torch.randn(B, 64, 3, H, W, generator=g)                 # reference channel c*3 + t
+    if taps_half:
+        taps = taps.half().float()
+    if prev16:
+        prev = [_bf16r(p) for p in prev]
+    want = [F.leaky_relu(O.sac(O.warp_bilinear(prev[d], off[d]), taps.reshape(B, 192, H, W)) + xin[d], 0.1) for d in range(2)]
+    pdt = torch.bfloat16 if prev16 else torch.float32
+    prev_d = [nhwc(p).to(dev).to(pdt) for p in prev]
+    xin_d = [nhwc(t).to(dev) for t in xin]
+    offs_d = torch.zeros(B, H, W, 8, device=dev)
+    offs_d[..., 2:4] = nhwc(off[0]).to(dev)
+    offs_d[..., 6:8] = nhwc(off[1]).to(dev)
+    taps_d = taps.permute(0, 3, 4, 2, 1).reshape(B, H, W, 192).contiguous().to(dev)      # ours: [t][c]
+    if taps_half:
+        taps_d = taps_d.half()
+    odt = torch.bfloat16 if ro == 2 else torch.float32
+    nxt = [torch.empty(B, H, W, 64, device=dev, dtype=odt) for _ in range(2)]
+    C.call("fcvsr_iac_step", prev_d[0].data_ptr(), 64, prev_d[1].data_ptr(), 64, xin_d[0].data_ptr(), 64, xin_d[1].data_ptr(), 64,
+           nxt[0].data_ptr(), 64, nxt[1].data_ptr(), 64, offs_d.data_ptr(), 8, 2, 6, taps_d.data_ptr(), 192, taps_half, B, H, W,
+           ro | (4 if prev16 else 0), _st())
+    torch.cuda.synchronize()
+    for d in range(2):
+        got = nchw(nxt[d].float().cpu())
+        scale = max(1.0, float(want[d].abs().max()))
+        tol = {0: 2e-5, 1: 2.0 ** -11 + 2e-5, 2: 2.0 ** -8 + 2e-5}[ro] * scale
+        assert float((got - want[d]).abs().max()) <= tol, d
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# DivEnh chain + CALayer gates (CVSR_freq.py:2104-2133, :1812-1828, :2201-2254)
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant,B,H,W", [("S", 2, 12, 20), ("full", 1, 19, 27), ("full", 3, 16, 16)])
+def test_divenh_chain_kernels(dev, variant, B, H, W):
+    """chansum64 / divenh_step / reduce_finalize / mffr_final driven exactly as engine._mffr drives them, on band tensors taken
+    from the oracle's split_freq (so the FFT kernels are not in the loop): the running sum of the enhanced bands and the
+    block output against oracle.div_enh / oracle.mffr; P not a multiple of the 256-pixel block, Freq_Inv 4 and 8."""
+    sd = arch.seeded_state_dict(variant, 0)
+    m = (arch.GShiftNet if variant == "full" else arch.GShiftNet_S)().to(dev).eval()
+    m.load_state_dict(sd)
+    eng = Engine(m, mode="fp32")
+    eng._ensure_packs(dev)
+    Pk, Q = eng.packs, m.Freq_Inv
+    g = torch.Generator().manual_seed(3 + H)
+    x = torch.randn(B, 64, H, W, generator=g)
+    bands = O.split_freq(x, Q)[::-1]
+    outs = []
+    for i in range(Q):
+        outs.append(O.div_enh(sd, f"MFFRblock.DivEnh_block.{i}", bands[i], bands[:i], outs[:i]))
+    so_ref = torch.stack(outs, 0).sum(0)
+    y_ref = O.mffr(sd, x, Q)
+    npix = H * W
+    nblk = (npix + 255) // 256
+    bd = [nhwc(b).to(dev) for b in bands]
+    xd = nhwc(x).to(dev)
+    sb = torch.empty(B, npix, 64, device=dev)
+    so = torch.empty(B, npix, 64, device=dev)
+    part = torch.empty(B * nblk * 128, device=dev)
+    mean0 = torch.empty(B, 128, device=dev)
+    gates = torch.empty(Q + 1, B, 128, device=dev)
+    y = torch.empty(B, npix, 64, device=dev)
+    st = _st()
+    de = lambda i, s: Pk[f"de{i}.{s}"].data_ptr()  # noqa: E731
+    gate = lambda i: gates.data_ptr() + i * B * 128 * 4  # noqa: E731
+    inv = 1.0 / npix
+    C.call("fcvsr_chansum64", bd[0].data_ptr(), 64, part.data_ptr(), B, npix, st)
+    C.call("fcvsr_reduce_finalize", part.data_ptr(), nblk, 1, inv, 0, 0, 0, mean0.data_ptr(), B, st)
+    C.call("fcvsr_divenh_step", 0, 0, 0, 0, 0, 0, 1, 1, bd[0].data_ptr(), de(0, "a"), de(0, "b"), mean0.data_ptr(), sb.data_ptr(),
+           so.data_ptr(), part.data_ptr(), B, npix, st)
+    C.call("fcvsr_reduce_finalize", part.data_ptr(), nblk, 1, inv, 1, de(0, "w1"), de(0, "w2"), gate(0), B, st)
+    for i in range(1, Q):
+        C.call("fcvsr_divenh_step", bd[i - 1].data_ptr(), de(i - 1, "a"), de(i - 1, "b"), mean0.data_ptr(), gate(i - 1),
+               int(i - 1 == 0), 1, 0, bd[i].data_ptr(), de(i, "a"), de(i, "b"), 0, sb.data_ptr(), so.data_ptr(), part.data_ptr(),
+               B, npix, st)
+        C.call("fcvsr_reduce_finalize", part.data_ptr(), nblk, 2, inv, 1, de(i, "w1"), de(i, "w2"), gate(i), B, st)
+    C.call("fcvsr_divenh_step", bd[Q - 1].data_ptr(), de(Q - 1, "a"), de(Q - 1, "b"), mean0.data_ptr(), gate(Q - 1), int(Q == 1), 2,
+           0, 0, 0, 0, 0, sb.data_ptr(), so.data_ptr(), part.data_ptr(), B, npix, st)
+    C.call("fcvsr_reduce_finalize", part.data_ptr(), nblk, 1, inv, 1, Pk["mffr.w1"].data_ptr(), Pk["mffr.w2"].data_ptr(), gate(Q), B, st)
+    C.call("fcvsr_mffr_final", so.data_ptr(), gate(Q), xd.data_ptr(), 64, y.data_ptr(), 64, B, npix, st)
+    torch.cuda.synchronize()
+    so_got = nchw(so.cpu().view(B, H, W, 64))
+    y_got = nchw(y.cpu().view(B, H, W, 64))
+    assert float((so_got - so_ref).abs().max()) <= 2e-5 * max(1.0, float(so_ref.abs().max()))
+    assert float((y_got - y_ref).abs().max()) <= 2e-5 * max(1.0, float(y_ref.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# BASELINE config 5b: FCVSR-S at 540x960 -> 2160x3840
+# ------------------------------------------------------------------------------------------------------------------------
+def test_fcvsr_s_540x960_parity_against_oracle(dev):
+    """The 4K-output case benchmarked in round 1 without a parity test: H = 540 = 27*20 and W = 960 = 32*30 take FFT radix pairs
+    no other model-level test reaches.  All three compute modes against the CPU oracle with the tolerances of SURVEY 8(d)."""
+    sd = arch.seeded_state_dict("S", 0)
+    x = make_clip(77, 1, 540, 960)
+    with torch.no_grad():
+        ref = O.forward(sd, x)
+    tgt = torch.rand(ref.shape, generator=torch.Generator().manual_seed(5))
+    m = arch.GShiftNet_S().to(dev).eval()
+    m.load_state_dict(sd)
+    xd = x.to(dev)
+    for mode, tol in (("fp32", 2e-5), ("tf32", 1e-3), ("bf16", 5e-3)):
+        m.compute_dtype = mode
+        with torch.no_grad():
+            y = m(xd).cpu()
+        m._engine = None                                   # drop the 2.5 GB workspace before the next mode
+        torch.cuda.empty_cache()
+        err = float((y - ref).abs().max())
+        assert err <= tol, (mode, err)
+        if mode == "tf32":
+            assert abs(psnr(y, tgt) - psnr(ref, tgt)) <= 0.01
+        if mode == "bf16":
+            assert psnr(y, ref) >= 60.0
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# DCN: backward on the tensors saved by the tensor-core forward (the default forward)
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [dict(B=1, cin=64, cout=64, H=20, W=24, dg=16), dict(B=2, cin=32, cout=48, H=13, W=17, dg=4)])
+def test_dcn_backward_after_tensor_core_forward(dev, cfg):
+    """Default configuration of ops.dcn (PRECISION = "tf32"): the forward runs on tcgen05 with TF32 operands, the backward kernels
+    (fp32) consume the tensors it saved.  Forward within the TF32 bound, all five gradients within 2e-4 of their scale of the
+    oracle's autograd (the backward does not depend on the forward's rounding: it re-samples from the saved fp32 input)."""
+    import fcvsr_b200.ops.dcn as dcn_mod
+    assert dcn_mod.PRECISION == "tf32"
+    g = torch.Generator().manual_seed(cfg["H"] + cfg["dg"])
+    B, ci, co, H, W, dg = cfg["B"], cfg["cin"], cfg["cout"], cfg["H"], cfg["W"], cfg["dg"]
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, 3, 3, generator=g) / math.sqrt(ci * 9)
+    b = torch.randn(co, generator=g)
+    off = 2.0 * torch.randn(B, dg * 18, H, W, generator=g)
+    msk = torch.rand(B, dg * 9, H, W, generator=g)
+    gy = torch.randn(B, co, H, W, generator=g)
+    cpu = [t.clone().requires_grad_(True) for t in (x, off, msk, w, b)]
+    ref = O.modulated_deform_conv(cpu[0], cpu[1], cpu[2], cpu[3], cpu[4], 1, 1, 1, 1, dg)
+    (ref * gy).sum().backward()
+    gpu = [t.to(dev).requires_grad_(True) for t in (x, off, msk, w, b)]
+    y = dcn_mod.modulated_deform_conv(gpu[0], gpu[1], gpu[2], gpu[3], gpu[4], 1, 1, 1, 1, dg)
+    (y * gy.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert float((y.detach().cpu() - ref.detach()).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+    for name, a, r in zip(("input", "offset", "mask", "weight", "bias"), gpu, cpu):
+        err = float((a.grad.cpu() - r.grad).abs().max())
+        assert err <= 2e-4 * max(1.0, float(r.grad.abs().max())), (name, err)
+
+
+def test_quantize_u8_matches_numpy_truncation(dev):
+    """fcvsr_quantize_u8 = crop + clamp + *255 + astype(uint8) of the evaluation driver (test_LD_freqCVSR.py:85-93)."""
+    from fcvsr_b200.sequence import quantize_u8
+    g = torch.Generator().manual_seed(2)
+    y = torch.rand(3, 1, 40, 52, generator=g) * 1.4 - 0.2
+    y[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 254.9999 / 255.0, 0.5])
+    want = torch.from_numpy((torch.clamp(y[..., :36, :50], 0, 1).numpy() * 255.0).astype("uint8"))
+    got = quantize_u8(y.to(dev), 36, 50).cpu()
+    assert torch.equal(got, want)

@@ -109,3 +109,60 @@ def test_data_parallel_train_step_two_ranks_gloo():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_train_worker, args=(2, port), nprocs=2, join=True)
+
+
+class _TwoBranch(torch.nn.Module):
+    """Two independent branches whose backward order depends on the order they are summed in."""
+
+    def __init__(self):
+        super().__init__()
+        self.p = torch.nn.Linear(4, 4)
+        self.q = torch.nn.Linear(4, 4)
+        self.r = torch.nn.Linear(4, 4)
+
+    def forward(self, x, flip, use_r):
+        a, b = self.p(x), self.q(x)
+        y = (b.sum() + a.sum()) if flip else (a.sum() + b.sum())
+        return y + self.r(x).sum() if use_r else y
+
+
+def _order_worker(rank, world, port, mismatch):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)                                    # different initial weights: the constructor broadcasts rank 0's
+    net = _TwoBranch()
+    red = GradAllReducer(net.parameters(), bucket_mb=1e-5)     # one bucket per parameter
+    ref = [p.detach().clone() for p in net.parameters()]
+    for r in ref:
+        dist.broadcast(r, src=0)
+    assert all(torch.equal(p.detach(), r) for p, r in zip(net.parameters(), ref))
+    x = torch.randn(3, 4, generator=torch.Generator().manual_seed(5 + rank))
+    # rank 1 sums the branches in the other order (its hooks fire in another order); with `mismatch` branch r is used on
+    # rank 0 only, which the first-step consistency check must reject on every rank instead of hanging
+    use_r = (rank == 0) if mismatch else False
+    net(x, flip=bool(rank), use_r=use_r).backward()
+    local = [None if p.grad is None else p.grad.clone() for p in net.parameters()]
+    if mismatch:
+        with pytest.raises(RuntimeError, match="some ranks only"):
+            red.finish()
+    else:
+        red.finish()
+        for p, g in zip(net.parameters(), local):
+            if g is None:
+                assert p.grad is None
+                continue
+            parts = [torch.zeros_like(g) for _ in range(world)]
+            dist.all_gather(parts, g)
+            assert torch.allclose(p.grad, sum(parts) / world, rtol=1e-6, atol=1e-7)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mismatch", [False, True])
+def test_collective_order_is_rank_independent(mismatch):
+    """Hooks firing in different orders on different ranks must not reorder the collectives (strict bucket order), and a
+    rank-dependent set of unused parameters is detected on the first step."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_order_worker, args=(2, port, mismatch), nprocs=2, join=True)

@@ -36,17 +36,6 @@ for (B, ci, co, H, W, k) in shapes:
     us = e0.elapsed_time(e1) / 20 * 1e3
     fl = 2.0 * B * H * W * ci * co * k * k
     line = f"B{B} {ci}->{co} {H}x{W} k{k}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s"
-    if k == 3 and ci in (32, 64) and co % 64 == 0:
-        a2 = (x.data_ptr(), ci, pk.w_tc.data_ptr(), 9 * ci, bp, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, act, 0.1, 0, 0, 0, 0, 0, 0, 0, st)
-        for _ in range(3):
-            C.call("fcvsr_conv3x3_tc_resident", *a2)
-        e0.record()
-        for _ in range(20):
-            C.call("fcvsr_conv3x3_tc_resident", *a2)
-        e1.record()
-        torch.cuda.synchronize()
-        us2 = e0.elapsed_time(e1) / 20 * 1e3
-        line += f"   | resident: {us2:8.1f} us  {fl / us2 / 1e6:7.1f} TFLOP/s"
     # bf16 operands
     pk16 = _ConvPack(w, None, op16=True)
     x16 = x.to(torch.bfloat16)
@@ -62,15 +51,4 @@ for (B, ci, co, H, W, k) in shapes:
         torch.cuda.synchronize()
         us3 = e0.elapsed_time(e1) / 20 * 1e3
         line += f"   | bf16: {us3:8.1f} us  {fl / us3 / 1e6:7.1f} TFLOP/s"
-    if k == 3 and ci in (64, 128) and co % 64 == 0:
-        a4 = (x16.data_ptr(), ci, pk16.w_tc.data_ptr(), 9 * ci, bp, 0, 0, 0, 0, y16.data_ptr(), co, B, H, W, ci, co, act, 0.1, 0, 0, 0, 0, 1, 0, 1, st)
-        for _ in range(3):
-            C.call("fcvsr_conv3x3_tc_resident", *a4)
-        e0.record()
-        for _ in range(20):
-            C.call("fcvsr_conv3x3_tc_resident", *a4)
-        e1.record()
-        torch.cuda.synchronize()
-        us4 = e0.elapsed_time(e1) / 20 * 1e3
-        line += f"   | bf16 resident: {us4:8.1f} us  {fl / us4 / 1e6:7.1f} TFLOP/s"
     print(line)

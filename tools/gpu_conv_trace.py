@@ -16,11 +16,13 @@ mode = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 ci = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 co = int(sys.argv[4]) if len(sys.argv) > 4 else 64
 B = int(sys.argv[5]) if len(sys.argv) > 5 else 4
-src = "conv_tc.cu" if ver == "v1" else "conv_tc2.cu"
+if ver != "v1":
+    sys.exit("conv_tc2 (v2) was removed in round 2; only v1 = conv_tc.cu remains")
+src = "conv_tc.cu"
 so = os.path.join(ROOT, "gpurun_out", f"libtrace_{ver}.so")
 os.makedirs(os.path.dirname(so), exist_ok=True)
 extra = [f"-D{d}" for d in os.environ.get("T2_DEFS", "").split()]
-subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DT2_TRACE", "-DTC_TRACE", *extra,
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DTC_TRACE", "-DFCVSR_BRINGUP", *extra,
                        "-shared", "-Xcompiler", "-fPIC", "--cudart", "shared", os.path.join(ROOT, "fcvsr_b200/csrc", src), "-o", so,
                        "-Wno-deprecated-gpu-targets"])
 lib = ctypes.CDLL(so)
