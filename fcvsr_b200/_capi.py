@@ -42,6 +42,14 @@ SIGNATURES = {
     "fcvsr_pack_clip": "p p iiii i s",
     "fcvsr_subsample2": "pi pi pi iiii i s",
     "fcvsr_conv3x3_c64_to1": "pi p f p p iii s",
+    "fcvsr_conv2d_dgrad_direct": "pi p pi iiiiiii s",
+    "fcvsr_conv2d_wgrad": "pi pi p iiiiiii s",
+    "fcvsr_colsum": "pi i l pp i s",
+    "fcvsr_flow_warp": "pi pi pi iiii s",
+    "fcvsr_flow_warp_backward": "pi pi pi pi p iiii s",
+    "fcvsr_sac": "pi pi pi iiii s",
+    "fcvsr_sac_backward": "pi pi pi p pi pi iiii s",
+    "fcvsr_corr_gather_backward": "piii pi pi iiii s",
     "fcvsr_charbonnier_loss": "pp li i f pp s",
     "fcvsr_adam_step": "pppp p i dddd d i s",
     "fcvsr_charbonnier_loss_backward": "pp li i f pp pp s",

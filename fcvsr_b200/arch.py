@@ -173,15 +173,25 @@ class _FCVSRBase(nn.Module):
     # ------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x [B,7,1,H,W] float32 on a CUDA device, H % 4 == W % 4 == 0 -> [B,1,4H,4W]
-        (GShiftNet.forward :2688-2756).  Inference only in this round: the kernels have no
-        adjoints yet, so a call that would need autograd raises instead of silently detaching."""
+        (GShiftNet.forward :2688-2756).  Under torch.no_grad() the call runs the inference engine (one CUDA-graph-able launch
+        sequence); when autograd is recording and the input or a parameter requires grad it runs the differentiable forward
+        (fcvsr_b200.train_forward: the same kernels behind autograd Functions with backward kernels), so
+        `loss(model(x), hr).backward()` works as in the reference's training loop (train_LD_freqCVSR_22.py:243-251).  The
+        training forward computes in the contract's fp32 mode ("tf32": TF32 tensor-core operands, fp32 everywhere else) unless
+        compute_dtype is "fp32"."""
         if x.dim() != 5:
             raise ValueError(f"expected [B,T,C,H,W], got {tuple(x.shape)}")   # reference: unpack error :2690
         if not x.is_cuda:
             raise RuntimeError("fcvsr_b200 runs only on CUDA (sm_100a); there is no CPU fallback")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "fcvsr_b200: backward kernels are not implemented in this round; call under torch.no_grad()")
+            if x.shape[1] != 7 or x.shape[2] != 1 or x.shape[3] % 4 or x.shape[4] % 4:
+                raise ValueError("GShiftNet expects [B, 7, 1, H, W] with H and W multiples of 4")
+            if x.dtype != torch.float32:
+                raise TypeError("fcvsr_b200 expects float32 input")
+            from . import _capi
+            from .train_forward import forward_train
+            _capi.lib()                      # fail loudly if the kernel library is missing
+            return forward_train(self, x, "fp32" if self.compute_dtype == "fp32" else "tf32")
         from .engine import Engine
         if self._engine is None or self._engine.mode != self.compute_dtype:
             self._engine = Engine(self, mode=self.compute_dtype)

@@ -1,0 +1,330 @@
+"""Autograd-capable operators of the FCVSR training step, bound to the sm_100a kernel library.
+
+The reference trains with `sr = model(frames); loss.backward()` (CVSR_train/train_LD_freqCVSR_22.py:243-251): every gradient
+comes from ATen's autograd kernels (cuDNN dgrad / wgrad, cuFFT, grid_sampler_2d_backward).  Here the arithmetic-heavy
+operators of the forward -- convolutions, the 2-D real FFTs, the CorrBlock lookup, flow_warp and SAC -- are
+`torch.autograd.Function`s whose forward AND backward are calls into libfcvsr_b200.so (include/fcvsr_b200.h, "adjoints"
+section); `fcvsr_b200.train_forward` strings them together with PyTorch's elementwise glue, so that
+`fcvsr_b200.arch.GShiftNet(x)` is differentiable like the reference module.
+
+Tensor convention: every activation is an NHWC-contiguous buffer exposed to PyTorch as the NCHW-logical tensor
+`buf.permute(0, 3, 1, 2)` (= torch.channels_last), which is what the kernels read and what ATen's elementwise / interpolate
+kernels keep.  Spectra are complex-interleaved along the channel axis: logical channel 2c = Re, 2c + 1 = Im of complex
+channel c (the layout of fcvsr_fft_*).
+
+Compute modes (`mode` arguments): "fp32" runs every convolution on the CUDA-core kernel (exact fp32; used by the golden-
+gradient test), "tf32" runs forward and data-gradient convolutions whose shape fits on the tcgen05 kernel with operands
+rounded to nearest TF32 (the contract's fp32 mode); weight gradients are fp32 FFMA with fp32 atomics in both modes.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _capi as C
+from . import bands
+
+F32 = torch.float32
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _nhwc(t: torch.Tensor) -> torch.Tensor:
+    """NCHW-logical tensor -> contiguous [B,H,W,C] buffer (no copy when it already is channels_last)."""
+    if t.dtype != F32:
+        raise TypeError("fcvsr_b200 training operators are fp32")
+    v = t.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def _logical(buf: torch.Tensor) -> torch.Tensor:
+    return buf.permute(0, 3, 1, 2)
+
+
+def _round_tf32(t: torch.Tensor) -> torch.Tensor:
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & -8192).view(torch.float32)
+
+
+def _tc_ok(cin: int, cout: int, k: int, stride: int) -> bool:
+    """Shape envelope of fcvsr_conv2d_tc with TF32 operands (conv_tc.cu)."""
+    return stride == 1 and k in (1, 3) and cin % 32 == 0 and (cout % 16 == 0 or cout < 16) and cout <= 2048
+
+
+def _conv_launch(xh: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride: int, mode: str) -> torch.Tensor:
+    """y = conv(x, w) + bias on an NHWC buffer; w in the reference's [Cout, Cin, k, k] layout."""
+    B, H, W, ci = xh.shape
+    co, ci_w, k, _ = w.shape
+    assert ci_w == ci, (ci_w, ci)
+    pad = k // 2
+    ho, wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty(B, ho, wo, co, device=xh.device, dtype=F32)
+    bp = bias.contiguous().data_ptr() if bias is not None else 0
+    if mode == "tf32" and _tc_ok(ci, co, k, stride):
+        xr = torch.empty_like(xh)                            # tcgen05 truncates TF32 operands: round to nearest first
+        C.call("fcvsr_round_copy", xh.data_ptr(), ci, xr.data_ptr(), ci, ci, ci, B * H * W, 0, _st())
+        wt = w.permute(0, 2, 3, 1).reshape(co, k * k * ci)
+        if co < 16:
+            wt = torch.cat([wt, wt.new_zeros(16 - co, wt.shape[1])], 0)
+        wt = _round_tf32(wt)
+        C.call("fcvsr_conv2d_tc", xr.data_ptr(), ci, wt.data_ptr(), bp, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, k,
+               C.ACT_NONE, 0.0, 0, 0, 0, 0, 0, 0, 0, _st())
+    else:
+        wd = w.permute(2, 3, 1, 0).contiguous()              # [k*k][Cin][Cout]
+        C.call("fcvsr_conv2d_direct", xh.data_ptr(), ci, 0, wd.data_ptr(), bp, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, k,
+               stride, C.ACT_NONE, 0.0, 0, 0, 0, 0, 0, 0, 0, _st())
+    return y
+
+
+class _Conv2d(torch.autograd.Function):
+    """nn.Conv2d(k, stride, padding k // 2) of the reference (every convolution of CVSR_freq.py uses that padding)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, mode):
+        xh = _nhwc(x)
+        with torch.cuda.device(x.device):
+            y = _conv_launch(xh, w.detach(), None if bias is None else bias.detach(), stride, mode)
+        ctx.save_for_backward(xh, w)
+        ctx.stride, ctx.mode, ctx.has_bias = stride, mode, bias is not None
+        return _logical(y)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        xh, w = ctx.saved_tensors
+        w = w.detach()
+        stride, mode = ctx.stride, ctx.mode
+        g = _nhwc(gy)
+        B, H, W, ci = xh.shape
+        co, _, k, _ = w.shape
+        gx = gw = gb = None
+        with torch.cuda.device(xh.device):
+            if ctx.needs_input_grad[0]:
+                if mode == "tf32" and _tc_ok(co, ci, k, stride):
+                    # dx = conv(dy, w') with w'[ci][co][ky][kx] = w[co][ci][k-1-ky][k-1-kx]
+                    dx = _conv_launch(g, w.flip(2, 3).transpose(0, 1), None, 1, mode)
+                else:
+                    dx = torch.empty(B, H, W, ci, device=xh.device, dtype=F32)
+                    wt = w.permute(2, 3, 0, 1).contiguous()                      # [k*k][Cout][Cin]
+                    C.call("fcvsr_conv2d_dgrad_direct", g.data_ptr(), co, wt.data_ptr(), dx.data_ptr(), ci, B, H, W, ci, co, k,
+                           stride, _st())
+                gx = _logical(dx)
+            if ctx.needs_input_grad[1]:
+                dw = torch.zeros(k * k, ci, co, device=xh.device, dtype=F32)
+                C.call("fcvsr_conv2d_wgrad", xh.data_ptr(), ci, g.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, stride, _st())
+                gw = dw.view(k, k, ci, co).permute(3, 2, 0, 1)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                npix = g.shape[0] * g.shape[1] * g.shape[2]
+                scratch = torch.empty(((npix + 255) // 256) * co, device=xh.device, dtype=F32)
+                gb = torch.empty(co, device=xh.device, dtype=F32)
+                C.call("fcvsr_colsum", g.data_ptr(), co, co, npix, scratch.data_ptr(), gb.data_ptr(), 0, _st())
+        return gx, gw, gb, None, None
+
+
+def conv2d(x, w, bias=None, stride: int = 1, mode: str = "tf32"):
+    return _Conv2d.apply(x, w, bias, stride, mode)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# 2-D real FFTs (torch.fft.rfft2 / irfft2 with norm="backward", CVSR_freq.py:1452-1454, :1499-1504, :2082-2088)
+# ----------------------------------------------------------------------------------------------------------------------
+_COLW: Dict[Tuple[int, int, float, str], torch.Tensor] = {}
+
+
+def _col_weights(H: int, W: int, interior: float, device) -> torch.Tensor:
+    """[H, W/2+1] real mask: 1 on the DC and Nyquist columns, `interior` elsewhere (the r2c / c2r pair counts interior
+    columns once / twice, so their adjoints carry 1/2 / 2 there)."""
+    key = (H, W, interior, str(device))
+    if key not in _COLW:
+        wf = W // 2 + 1
+        m = torch.full((H, wf), interior, dtype=F32)
+        m[:, 0] = 1.0
+        m[:, wf - 1] = 1.0
+        _COLW[key] = m.contiguous().to(device)
+    return _COLW[key]
+
+
+def _rfft2_launch(xh: torch.Tensor) -> torch.Tensor:
+    B, H, W, c = xh.shape
+    wf = W // 2 + 1
+    dev = xh.device
+    spec = torch.empty(B, H, wf, 2 * c, device=dev, dtype=F32)
+    tw_w, tw_h = bands.twiddles(W, dev), bands.twiddles(H, dev)
+    C.call("fcvsr_fft_r2c_w", xh.data_ptr(), c, spec.data_ptr(), tw_w.data_ptr(), B, H, W, c, _st())
+    C.call("fcvsr_fft_c2c_h", spec.data_ptr(), spec.data_ptr(), tw_h.data_ptr(), 0, B, H, wf, c, 0, 1.0, 0, 1, 0, _st())
+    return spec
+
+
+def _c2r_launch(zh: torch.Tensor, W: int, mask: Optional[torch.Tensor], scale: float) -> torch.Tensor:
+    """inverse H pass (optional real column mask at load) + torch-semantics c2r W pass, result * scale"""
+    B, H, wf, c2 = zh.shape
+    c = c2 // 2
+    dev = zh.device
+    tmp = torch.empty_like(zh)
+    y = torch.empty(B, H, W, c, device=dev, dtype=F32)
+    tw_w, tw_h = bands.twiddles(W, dev), bands.twiddles(H, dev)
+    C.call("fcvsr_fft_c2c_h", zh.data_ptr(), tmp.data_ptr(), tw_h.data_ptr(), mask.data_ptr() if mask is not None else 0, B, H, wf,
+           c, 1, 1.0, 0, 1, 0, _st())
+    C.call("fcvsr_fft_c2r_w", tmp.data_ptr(), y.data_ptr(), c, tw_w.data_ptr(), B, H, W, c, scale, _st())
+    return y
+
+
+class _Rfft2(torch.autograd.Function):
+    """[B,C,H,W] real -> [B,2C,H,W/2+1] interleaved spectrum (unnormalised forward transform)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xh = _nhwc(x)
+        ctx.W = xh.shape[2]
+        with torch.cuda.device(x.device):
+            return _logical(_rfft2_launch(xh))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gz):
+        # X[k] = sum_n x[n] e^{-i theta k n}  =>  dx[n] = Re sum_{k=0}^{W/2} G[k] e^{+i theta k n}: the c2r pass with the interior
+        # columns halved (c2r counts them twice), after the conjugate-transpose (= unnormalised inverse) H pass
+        g = _nhwc(gz)
+        with torch.cuda.device(g.device):
+            dx = _c2r_launch(g, ctx.W, _col_weights(g.shape[1], ctx.W, 0.5, g.device), 1.0)
+        return _logical(dx)
+
+
+class _Irfft2(torch.autograd.Function):
+    """[B,2C,H,W/2+1] interleaved (any, not necessarily Hermitian) -> [B,C,H,W] = torch.fft.irfft2(z, s=(H, W))."""
+
+    @staticmethod
+    def forward(ctx, z, W):
+        zh = _nhwc(z)
+        ctx.W = W
+        with torch.cuda.device(z.device):
+            return _logical(_c2r_launch(zh, W, None, 1.0 / (zh.shape[1] * W)))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gx):
+        # x[n] = s [Re T_0 + (-1)^n Re T_{W/2} + 2 sum_{0<k<W/2} Re(T_k e^{i theta k n})], T = inverse H pass of z
+        #   =>  dT[k] = s c_k r2c(dx)[k] (c_k = 1 on the DC / Nyquist columns, whose imaginary gradient vanishes by itself, 2
+        #       elsewhere) and dz = forward H pass of dT
+        g = _nhwc(gx)
+        B, H, W, c = g.shape
+        wf = W // 2 + 1
+        dev = g.device
+        with torch.cuda.device(dev):
+            spec = torch.empty(B, H, wf, 2 * c, device=dev, dtype=F32)
+            tw_w, tw_h = bands.twiddles(W, dev), bands.twiddles(H, dev)
+            C.call("fcvsr_fft_r2c_w", g.data_ptr(), c, spec.data_ptr(), tw_w.data_ptr(), B, H, W, c, _st())
+            C.call("fcvsr_fft_c2c_h", spec.data_ptr(), spec.data_ptr(), tw_h.data_ptr(), _col_weights(H, W, 2.0, dev).data_ptr(), B, H,
+                   wf, c, 0, 1.0 / (H * W), 0, 1, 0, _st())
+        return _logical(spec), None
+
+
+def rfft2(x):
+    return _Rfft2.apply(x)
+
+
+def irfft2(z, W: int):
+    return _Irfft2.apply(z, W)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CorrBlock lookup (CVSR_freq.py:1279-1337)
+# ----------------------------------------------------------------------------------------------------------------------
+class _Corr(torch.autograd.Function):
+    """spec [B, >=256, H, Wf] interleaved with the two 64-channel spectra at channel offsets a_off / b_off -> [B,81,H,Wf]."""
+
+    @staticmethod
+    def forward(ctx, spec, a_off, b_off):
+        sh = _nhwc(spec)
+        B, H, wf, ld = sh.shape
+        out = torch.empty(B, H, wf, 81, device=sh.device, dtype=F32)
+        with torch.cuda.device(sh.device):
+            C.call("fcvsr_corr_gather", sh.data_ptr(), ld, a_off, b_off, out.data_ptr(), 81, B, H, wf, 128, 0, _st())
+        ctx.save_for_backward(sh)
+        ctx.offs = (a_off, b_off)
+        return _logical(out)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        (sh,) = ctx.saved_tensors
+        g = _nhwc(gout)
+        B, H, wf, ld = sh.shape
+        ds = torch.zeros_like(sh)
+        with torch.cuda.device(sh.device):
+            C.call("fcvsr_corr_gather_backward", sh.data_ptr(), ld, ctx.offs[0], ctx.offs[1], g.data_ptr(), 81, ds.data_ptr(), ld, B,
+                   H, wf, 128, _st())
+        return _logical(ds), None, None
+
+
+def corr_lookup(spec, a_off: int = 0, b_off: int = 128):
+    return _Corr.apply(spec, a_off, b_off)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# flow_warp (CVSR_freq.py:1188-1227) and SAC (:1253-1276)
+# ----------------------------------------------------------------------------------------------------------------------
+class _FlowWarp(torch.autograd.Function):
+    """x [B,C,H,W], off [B,2,H,W] (channel 0 = dx, 1 = dy in pixels) -> bilinear samples, zeros outside, align_corners=True."""
+
+    @staticmethod
+    def forward(ctx, x, off):
+        xh, oh = _nhwc(x), _nhwc(off)
+        B, H, W, c = xh.shape
+        y = torch.empty_like(xh)
+        with torch.cuda.device(xh.device):
+            C.call("fcvsr_flow_warp", xh.data_ptr(), c, oh.data_ptr(), 2, y.data_ptr(), c, B, H, W, c, _st())
+        ctx.save_for_backward(xh, oh)
+        return _logical(y)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        xh, oh = ctx.saved_tensors
+        g = _nhwc(gy)
+        B, H, W, c = xh.shape
+        dx = torch.zeros_like(xh) if ctx.needs_input_grad[0] else None
+        do = torch.empty_like(oh) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(xh.device):
+            C.call("fcvsr_flow_warp_backward", xh.data_ptr(), c, oh.data_ptr(), 2, g.data_ptr(), c,
+                   dx.data_ptr() if dx is not None else 0, c, do.data_ptr() if do is not None else 0, B, H, W, c, _st())
+        return (_logical(dx) if dx is not None else None), (_logical(do) if do is not None else None)
+
+
+class _Sac(torch.autograd.Function):
+    """wp [B,C,H,W], taps [B,3C,H,W] with channel t*C + c -> vertical then horizontal 3-tap pass with the same taps."""
+
+    @staticmethod
+    def forward(ctx, wp, taps):
+        wh, kh = _nhwc(wp), _nhwc(taps)
+        B, H, W, c = wh.shape
+        y = torch.empty_like(wh)
+        with torch.cuda.device(wh.device):
+            C.call("fcvsr_sac", wh.data_ptr(), c, kh.data_ptr(), 3 * c, y.data_ptr(), c, B, H, W, c, _st())
+        ctx.save_for_backward(wh, kh)
+        return _logical(y)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        wh, kh = ctx.saved_tensors
+        g = _nhwc(gy)
+        B, H, W, c = wh.shape
+        dw = torch.empty_like(wh) if ctx.needs_input_grad[0] else None
+        dk = torch.empty_like(kh) if ctx.needs_input_grad[1] else None
+        scratch = torch.empty_like(wh)
+        with torch.cuda.device(wh.device):
+            C.call("fcvsr_sac_backward", wh.data_ptr(), c, kh.data_ptr(), 3 * c, g.data_ptr(), c, scratch.data_ptr(),
+                   dk.data_ptr() if dk is not None else 0, 3 * c, dw.data_ptr() if dw is not None else 0, c, B, H, W, c, _st())
+        return (_logical(dw) if dw is not None else None), (_logical(dk) if dk is not None else None)
+
+
+def flow_warp(x, off):
+    return _FlowWarp.apply(x, off)
+
+
+def sac(wp, taps):
+    return _Sac.apply(wp, taps)

@@ -23,6 +23,7 @@ struct ConvDirectArgs {
     int act; float slope; const float* slope_ptr;
     int ps; int y_nchw;
     void* y2; int ldy2; int round_out; int op16;
+    int transposed;      // data-gradient mode: x is dy [B,H,W] of a stride-`stride` convolution, the tile domain (Ho, Wo) is dx
 };
 
 __global__ void __launch_bounds__(256) conv_direct_kernel(ConvDirectArgs a) {
@@ -50,8 +51,15 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(ConvDirectArgs a) {
     const int ntaps = a.ks * a.ks;
     for (int tap = 0; tap < ntaps; ++tap) {
         const int ky = tap / a.ks, kx = tap - ky * a.ks;
-        const int iy = loy * a.stride + ky - pad, ix = lox * a.stride + kx - pad;
-        const bool inb = (loy < a.Ho) && (lox < a.Wo) && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+        int iy = loy * a.stride + ky - pad, ix = lox * a.stride + kx - pad;
+        bool inb = (loy < a.Ho) && (lox < a.Wo);
+        if (a.transposed) {
+            // dx[loy, lox] += dy[(loy + pad - ky) / s, (lox + pad - kx) / s] * w[tap] where the divisions are exact
+            const int ty = loy + pad - ky, tx = lox + pad - kx;
+            inb = inb && ty >= 0 && tx >= 0 && (ty % a.stride) == 0 && (tx % a.stride) == 0;
+            iy = ty / a.stride; ix = tx / a.stride;
+        }
+        inb = inb && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
         for (int c0 = 0; c0 < a.Cin; c0 += CD_TK) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -135,7 +143,33 @@ extern "C" int fcvsr_conv2d_direct(const float* x, int ldx, int x_nchw, const fl
     a.Ho = (H + 2 * pad - ksize) / stride + 1;
     a.Wo = (W + 2 * pad - ksize) / stride + 1;
     a.act = act; a.slope = slope; a.slope_ptr = slope_ptr; a.ps = pixel_shuffle; a.y_nchw = y_nchw; a.y2 = y2; a.ldy2 = ldy2; a.round_out = round_out; a.op16 = op16;
+    a.transposed = 0;
     dim3 grid(((a.Ho + 7) / 8) * ((a.Wo + 7) / 8), (Cout + CD_TN - 1) / CD_TN, B);
+    conv_direct_kernel<<<grid, 256, 0, st>>>(a);
+    return fcvsr_launch_status();
+}
+
+// Data gradient of y = conv(x, w) (k x k, stride s, padding k/2) for any shape, on the CUDA cores:
+//     dx[b, iy, ix, ci] = sum_{ky, kx, co} dy[b, (iy + pad - ky) / s, (ix + pad - kx) / s, co] * w[co][ci][ky][kx]
+// over the taps for which both divisions are exact and the result lies inside dy.  wt is packed [k*k][Cout][Cin]
+// (w.permute(2, 3, 0, 1)); dy [B,Ho,Wo,lddy] with Ho = (H + 2 pad - k) / s + 1; dx [B,H,W,lddx] is written.  What autograd's
+// conv backward computes for the reference's nn.Conv2d layers (cuDNN dgrad there); stride-1 layers whose shapes fit use
+// fcvsr_conv2d_tc on flipped, transposed weights instead.
+extern "C" int fcvsr_conv2d_dgrad_direct(const float* dy, int lddy, const float* wt, float* dx, int lddx, int B, int H, int W,
+                                         int Cin, int Cout, int ksize, int stride, cudaStream_t st) {
+    if (!dy || !wt || !dx || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || !(ksize & 1) || stride < 1) return FCVSR_ERR_ARG;
+    const int pad = ksize / 2;
+    ConvDirectArgs a;
+    a.x = dy; a.ldx = lddy; a.x_nchw = 0; a.w = wt; a.bias = nullptr;
+    a.res = nullptr; a.ldres = 0; a.res2 = nullptr; a.ldres2 = 0; a.y = dx; a.ldy = lddx;
+    a.B = B;
+    a.H = (H + 2 * pad - ksize) / stride + 1;          // source = dy
+    a.W = (W + 2 * pad - ksize) / stride + 1;
+    a.Cin = Cout; a.Cout = Cin; a.ks = ksize; a.stride = stride;
+    a.Ho = H; a.Wo = W;                                // tile domain = dx
+    a.act = FCVSR_ACT_NONE; a.slope = 0.f; a.slope_ptr = nullptr; a.ps = 0; a.y_nchw = 0; a.y2 = nullptr; a.ldy2 = 0;
+    a.round_out = 0; a.op16 = 0; a.transposed = 1;
+    dim3 grid(((H + 7) / 8) * ((W + 7) / 8), (Cin + CD_TN - 1) / CD_TN, B);
     conv_direct_kernel<<<grid, 256, 0, st>>>(a);
     return fcvsr_launch_status();
 }

@@ -3,10 +3,10 @@
     optimizer.zero_grad(); sr = model(frames); loss = CharbonnierLoss(sr, hr); loss.backward(); optimizer.step()
 
 plus the gradient all-reduce that the mmedit configuration wraps around it (one replica per GPU,
-fcvsr_redsLD_QP22.py:144).  Host logic only: `model` is any autograd-capable module -- the FCVSR forward of this package is not
-yet, so today this runs the DCN modules / stand-ins and is covered by the 2-rank gloo test; the loss, the
-optimizer and the reducer it is meant to be used with are `fcvsr_b200.ops.loss.CharbonnierLoss`, `fcvsr_b200.ops.optim.Adam`
-and `fcvsr_b200.gradsync.GradAllReducer`.
+fcvsr_redsLD_QP22.py:144).  `model` is any autograd-capable module; with `fcvsr_b200.arch.GShiftNet[_S]` the forward and
+backward run on this repository's kernels (fcvsr_b200.train_forward / fcvsr_b200.autograd), the loss is
+`fcvsr_b200.ops.loss.CharbonnierLoss`, the optimizer `fcvsr_b200.ops.optim.Adam` and the reducer
+`fcvsr_b200.gradsync.GradAllReducer` (NCCL over NVLink on the GPU box, gloo in the CPU tests).
 
 Charbonnier is sum-reduced (opt/loss.py:30), so averaging the gradients over G ranks makes one step equal to a single-GPU
 step on the concatenated batch with the learning rate divided by G -- the reference behaves the same way; it is documented,
@@ -14,7 +14,7 @@ not "fixed" (SURVEY 8e).
 """
 from __future__ import annotations
 
-from typing import Callable, Optional
+from typing import Callable
 
 import torch
 
@@ -45,3 +45,67 @@ def replicas_in_sync(model: torch.nn.Module, group=None, atol: float = 0.0) -> b
     flag = torch.tensor([1.0 if ok else 0.0], device=next(model.parameters()).device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
     return bool(flag.item() > 0)
+
+
+def bench_train_step(dev, rank: int, world: int, steps: int = 5, warmup: int = 2, variant: str = "full", batch: int = 8,
+                     size: int = 64) -> dict:
+    """BASELINE config 4 for bench.py: FCVSR training step (forward + backward + Adam, Charbonnier-sum loss) on a per-GPU batch
+    of `batch` synthetic 7 x size x size crops, data parallel with the NCCL gradient all-reduce when world > 1.  Device time
+    (CUDA events), max over ranks; the all-reduce is timed separately in a second pass (`time_collectives`: every collective
+    bracketed by events, which serialises it with the backward) so that the overlapped step time is not perturbed."""
+    import torch.distributed as dist
+    from . import arch
+    from .gradsync import GradAllReducer
+    from .ops.loss import CharbonnierLoss
+    from .ops.optim import Adam
+    cls = arch.GShiftNet if variant == "full" else arch.GShiftNet_S
+    model = cls().to(dev).train()
+    model.load_state_dict(arch.seeded_state_dict(variant, 0))
+    model.compute_dtype = "tf32"
+    opt = Adam(model.parameters(), lr=5e-6, weight_decay=1e-5)              # train_LD_freqCVSR_22.py:35,42,204
+    red = GradAllReducer(model.parameters()) if world > 1 else None
+    g = torch.Generator().manual_seed(99 + rank)
+    frames = (torch.round(255 * torch.rand(batch, 7, 1, size, size, generator=g)) / 255).to(dev)
+    hr = torch.rand(batch, 1, 4 * size, 4 * size, generator=g).to(dev)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = None
+        for _ in range(n):
+            loss = train_step(model, opt, frames, hr, CharbonnierLoss, red)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync()
+        return float(ms) / n, float(loss)
+
+    run(warmup)
+    ms, loss = run(steps)
+    ar_ms = None
+    if red is not None:
+        red.time_collectives = True
+        train_step(model, opt, frames, hr, CharbonnierLoss, red)
+        t = torch.tensor([red.allreduce_ms()], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t)
+        red.time_collectives = False
+        red.remove_hooks()
+    nparam = sum(p.numel() for p in model.parameters())
+    return {"metric": "training steps/sec (fwd + bwd + Adam, per-GPU batch %d of 7x%dx%d crops)" % (batch, size, size),
+            "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "clips_per_s": world * batch * 1e3 / ms, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "loss": loss, "dtype": "tf32 (fp32 storage, TF32 tensor-core operands in forward and "
+            "data-gradient convolutions, fp32 weight gradients)", "variant": variant,
+            "allreduce": None if red is None else {"backend": "nccl", "buckets": len(red.buckets), "bytes": 4 * nparam,
+                                                   "ms_serialised": ar_ms,
+                                                   "note": "sum of the bucket collectives' device time in a pass where each is "
+                                                           "bracketed by events; in the timed steps they overlap the backward"},
+            "optimizer": "fcvsr_adam_step (multi-tensor), lr 5e-6, weight_decay 1e-5", "loss_fn": "Charbonnier sum (fcvsr_charbonnier_loss)"}

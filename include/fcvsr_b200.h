@@ -186,6 +186,40 @@ int fcvsr_adam_step(float* const* params, const float* const* grads, float* cons
                     const long long* numels, int count, double lr, double beta1, double beta2, double eps,
                     double weight_decay, int step, cudaStream_t stream);
 
+/* ---- adjoints of the forward kernels: the training step (CVSR_train/train_LD_freqCVSR_22.py:243-251, loss.backward()) -------
+ * The reference derives these with ATen's autograd (cuDNN dgrad / wgrad, grid_sampler_2d_backward, elementwise kernels); the
+ * entries below are what fcvsr_b200/autograd.py binds in their place. */
+
+/* Data gradient of y = conv(x, w) (k x k, stride s, padding k/2), any shape, CUDA cores: dy [B,Ho,Wo,lddy] (Cout channels),
+ * wt packed [k*k][Cout][Cin] (w.permute(2,3,0,1)), dx [B,H,W,lddx] (Cin channels) is WRITTEN.  Stride-1 layers whose shapes fit
+ * use fcvsr_conv2d_tc on flipped / transposed weights instead. */
+int fcvsr_conv2d_dgrad_direct(const float* dy, int lddy, const float* wt, float* dx, int lddx, int B, int H, int W, int Cin,
+                              int Cout, int ksize, int stride, cudaStream_t stream);
+/* Weight gradient: dw [k*k][Cin][Cout] += sum over output pixels of x[pix*s + tap - pad][ci] * dy[pix][co].  ACCUMULATES with
+ * fp32 atomics over pixel slices (zero-fill first; run-to-run differences at rounding level, as cuDNN's atomic wgrad). */
+int fcvsr_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
+                       int ksize, int stride, cudaStream_t stream);
+/* out[c] (+)= sum over npix rows of x[row*ldx + c] (bias gradient), deterministic; scratch: ceil(npix / 256) * C floats. */
+int fcvsr_colsum(const float* x, int ldx, int C, long long npix, float* scratch, float* out, int accumulate, cudaStream_t stream);
+/* flow_warp (CVSR_freq.py:1188-1227) on NHWC maps: y[b,py,px,:] = bilinear(x[b], px + off[b,py,px,0], py + off[b,py,px,1]), zero
+ * outside, align_corners=True; C % 4 == 0.  (The inference path fuses this into fcvsr_iac_step.) */
+int fcvsr_flow_warp(const float* x, int ldx, const float* off, int ldoff, float* y, int ldy, int B, int H, int W, int C,
+                    cudaStream_t stream);
+/* its adjoint: dx [B,H,W,lddx] is ACCUMULATED with atomics (zero-fill first; may be NULL), doff [B,H,W,2] is written (may be NULL) */
+int fcvsr_flow_warp_backward(const float* x, int ldx, const float* off, int ldoff, const float* dy, int lddy, float* dx, int lddx,
+                             float* doff, int B, int H, int W, int C, cudaStream_t stream);
+/* SAC (CVSR_freq.py:1253-1276): vertical then horizontal per-pixel, per-channel 3-tap filter, replicate padding, the SAME taps
+ * in both passes (the reference's kernel1); taps [B,H,W,ldk] with channel t*C + c. */
+int fcvsr_sac(const float* wp, int ldw, const float* taps, int ldk, float* out, int ldo, int B, int H, int W, int C,
+              cudaStream_t stream);
+/* its adjoint for upstream gradient g: dtaps [B,H,W,lddk] and dwp [B,H,W,lddw] are written (either may be NULL);
+ * scratch: B*H*W*C floats. */
+int fcvsr_sac_backward(const float* wp, int ldw, const float* taps, int ldk, const float* g, int ldg, float* scratch, float* dtaps,
+                       int lddk, float* dwp, int lddw, int B, int H, int W, int C, cudaStream_t stream);
+/* adjoint of fcvsr_corr_gather (fp32): dS [B,H*Wf,lddS] is written at the float ranges [a_off, a_off+C2) and [b_off, b_off+C2) */
+int fcvsr_corr_gather_backward(const float* S, int ldS, int a_off, int b_off, const float* dout, int ldo, float* dS, int lddS,
+                               int B, int H, int Wf, int C2, cudaStream_t stream);
+
 /* ---- deformable convolution operator (CVSR_train/ops/dcn) --------------------------------------- */
 
 /* Fused bilinear-gather + GEMM modulated deformable convolution forward, NCHW fp32 exactly as the

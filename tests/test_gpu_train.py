@@ -1,0 +1,225 @@
+"""GPU tests of the training path (BASELINE config 4): the autograd Functions of fcvsr_b200.autograd against autograd
+through the same operators of the CPU oracle / plain PyTorch, the differentiable forward against the oracle forward, and
+`CharbonnierLoss(model(x), T).backward()` against the gradients of the UNMODIFIED reference (tests/golden/*_grads.pt, made
+by oracle/make_golden_grads.py).
+
+Tolerances: "fp32" mode (CUDA-core convolutions) -- the bound of the oracle's own pin, 2e-3 of each gradient's scale;
+"tf32" mode (tcgen05 forward / data-gradient convolutions with TF32-rounded operands) -- 2e-2 of each gradient's scale
+(stated separately, like the forward's 1e-3).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from fcvsr_b200 import arch
+from fcvsr_b200 import autograd as A
+from fcvsr_b200.ops.loss import CharbonnierLoss
+from fcvsr_b200.train_forward import forward_train
+from oracle import fcvsr_oracle as O
+from tests.util import load_golden, make_clip
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _rel(a, r):
+    return float((a - r).abs().max()) / max(1e-12, float(r.abs().max()))
+
+
+@pytest.mark.parametrize("ci,co,k,stride,H,W", [(64, 64, 3, 1, 20, 24), (64, 128, 3, 1, 9, 17), (128, 64, 3, 1, 16, 16),
+                                               (7, 448, 3, 1, 12, 12), (64, 4, 1, 1, 11, 19), (4, 4, 7, 1, 10, 9),
+                                               (64, 64, 3, 2, 16, 20), (80, 64, 3, 1, 8, 12), (64, 1, 3, 1, 13, 15),
+                                               (256, 128, 1, 1, 10, 7), (64, 256, 1, 1, 6, 10)])
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_conv2d_function_forward_and_gradients(dev, ci, co, k, stride, H, W, mode):
+    """_Conv2d (forward: conv_tc / conv_direct; dgrad: conv_tc on flipped weights / conv_direct transposed; wgrad; bias colsum)
+    against F.conv2d + autograd on the CPU, incl. strided, thin (Cout 1 / 4), Cin 7 / 80 and the large ConvBlk kernel sizes."""
+    g = torch.Generator().manual_seed(ci * co + k)
+    x = torch.randn(2, ci, H, W, generator=g)
+    w = torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)
+    b = torch.randn(co, generator=g)
+    ho, wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    gy = torch.randn(2, co, ho, wo, generator=g)
+    ref_in = [t.clone().requires_grad_(True) for t in (x, w, b)]
+    yr = F.conv2d(ref_in[0], ref_in[1], ref_in[2], stride=stride, padding=k // 2)
+    (yr * gy).sum().backward()
+    ins = [t.to(dev).requires_grad_(True) for t in (x, w, b)]
+    y = A.conv2d(_cl(ins[0]), ins[1], ins[2], stride, mode)
+    (y * gy.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    tol = 2e-5 if mode == "fp32" else 2e-3
+    assert _rel(y.detach().cpu(), yr.detach()) <= tol
+    for name, a, r in zip(("x", "w", "b"), ins, ref_in):
+        # weight gradients are fp32 FFMA in both modes, but in tf32 mode they see the same fp32 inputs: exact-level agreement
+        t = 2e-5 if (mode == "fp32" or name != "x") else 2e-3
+        assert _rel(a.grad.cpu(), r.grad) <= t, (name, _rel(a.grad.cpu(), r.grad))
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 64, 64), (1, 12, 32, 32), (2, 24, 36, 40), (1, 192, 16, 20)])
+def test_fft_functions_forward_and_gradients(dev, B, C, H, W):
+    """_Rfft2 / _Irfft2 against torch.fft.rfft2 / irfft2 (norm='backward') and their autograd on the CPU; the irfft2 input is a
+    general (non-Hermitian) spectrum as in MGAAbk (:1497-1505)."""
+    g = torch.Generator().manual_seed(C + H)
+    wf = W // 2 + 1
+    x = torch.randn(B, C, H, W, generator=g)
+    gz = torch.randn(B, C, H, wf, 2, generator=g)
+    xr = x.clone().requires_grad_(True)
+    zr = torch.view_as_real(torch.fft.rfft2(xr, norm="backward"))
+    (zr * gz).sum().backward()
+    xd = x.to(dev).requires_grad_(True)
+    z = A.rfft2(_cl(xd))                                               # [B,2C,H,Wf], channel 2c = Re, 2c+1 = Im
+    zv = z.reshape(B, C, 2, H, wf).permute(0, 1, 3, 4, 2)
+    (zv * gz.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert _rel(zv.detach().cpu(), zr.detach()) <= 3e-6
+    assert _rel(xd.grad.cpu(), xr.grad) <= 3e-6
+    # irfft2
+    s = torch.randn(B, C, H, wf, 2, generator=g)
+    gx = torch.randn(B, C, H, W, generator=g)
+    sr = s.clone().requires_grad_(True)
+    yr = torch.fft.irfft2(torch.view_as_complex(sr), s=(H, W), norm="backward")
+    (yr * gx).sum().backward()
+    sd = s.to(dev).requires_grad_(True)
+    zin = sd.permute(0, 1, 4, 2, 3).reshape(B, 2 * C, H, wf)
+    y = A.irfft2(_cl(zin), W)
+    (y * gx.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert _rel(y.detach().cpu(), yr.detach()) <= 3e-6
+    assert _rel(sd.grad.cpu(), sr.grad) <= 3e-6
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 12, 20), (2, 70, 18)])
+def test_corr_function_gradients(dev, B, H, W):
+    """_Corr against autograd through oracle.corr_lookup (reference cat([imag, real]) packing) on the CPU."""
+    wf = W // 2 + 1
+    g = torch.Generator().manual_seed(H)
+    z = torch.randn(B, 3, 64, H, wf, 2, generator=g)                   # three spectra (x1, x2, x3), complex
+    gout = torch.randn(B, 81, H, wf, generator=g)
+    zr = z.clone().requires_grad_(True)
+    a = torch.cat([zr[:, 0, :, :, :, 1], zr[:, 0, :, :, :, 0]], 1)     # [imag, real]
+    b = torch.cat([zr[:, 1, :, :, :, 1], zr[:, 1, :, :, :, 0]], 1)
+    ref = O.corr_lookup(a, b)
+    (ref * gout).sum().backward()
+    zd = z.to(dev).requires_grad_(True)
+    spec = zd.permute(0, 1, 2, 5, 3, 4).reshape(B, 384, H, wf)         # channel g*128 + 2c + (re|im)
+    out = A.corr_lookup(_cl(spec), 0, 128)
+    (out * gout.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert _rel(out.detach().cpu(), ref.detach()) <= 1e-6
+    assert _rel(zd.grad.cpu(), zr.grad) <= 1e-6
+    assert float(zd.grad[:, 2].abs().max()) == 0.0                     # the third spectrum is not read
+
+
+@pytest.mark.parametrize("B,C,H,W", [(1, 64, 19, 37), (2, 64, 8, 16), (1, 8, 5, 4), (1, 20, 4, 6)])
+def test_flow_warp_and_sac_functions(dev, B, C, H, W):
+    """_FlowWarp / _Sac against autograd through oracle.warp_bilinear (grid_sample, align_corners=True, zeros) and oracle.sac on
+    the CPU: gradients with respect to the feature map, the offsets and the taps; offsets that leave the image; channel counts
+    whose per-pixel thread group is / is not a power of two (shuffle / atomic reduction of d/d offset)."""
+    g = torch.Generator().manual_seed(H * W + C)
+    x = torch.randn(B, C, H, W, generator=g)
+    off = 2.5 * torch.randn(B, 2, H, W, generator=g)
+    off[0, :, 0, 0] = torch.tensor([-30.0, 40.0])
+    taps = torch.randn(B, C, 3, H, W, generator=g)                     # reference order c*3 + t
+    gy = torch.randn(B, C, H, W, generator=g)
+    rx, ro, rt = (t.clone().requires_grad_(True) for t in (x, off, taps))
+    ref = O.sac(O.warp_bilinear(rx, ro), rt.reshape(B, 3 * C, H, W))
+    (ref * gy).sum().backward()
+    dx, do, dt = (t.to(dev).requires_grad_(True) for t in (x, off, taps))
+    ours_taps = dt.permute(0, 2, 1, 3, 4).reshape(B, 3 * C, H, W)      # [t][c]
+    out = A.sac(A.flow_warp(_cl(dx), _cl(do)), _cl(ours_taps))
+    (out * gy.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert _rel(out.detach().cpu(), ref.detach()) <= 2e-6
+    assert _rel(dx.grad.cpu(), rx.grad) <= 1e-5
+    assert _rel(dt.grad.cpu(), rt.grad) <= 1e-5
+    # d/d(offset) is discontinuous where a sample sits exactly on a pixel centre; random offsets never do
+    assert _rel(do.grad.cpu(), ro.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("variant", ["S", "full"])
+def test_training_forward_matches_oracle(dev, variant):
+    """forward_train (the differentiable path) against the oracle forward: fp32 mode 2e-5, tf32 mode 1e-3."""
+    sd = arch.seeded_state_dict(variant, 0)
+    x = make_clip(31, 2, 32, 36)
+    with torch.no_grad():
+        ref = O.forward(sd, x)
+    m = (arch.GShiftNet_S if variant == "S" else arch.GShiftNet)().to(dev)
+    m.load_state_dict(sd)
+    for mode, tol in (("fp32", 2e-5), ("tf32", 1e-3)):
+        y = forward_train(m, x.to(dev), mode)
+        assert y.requires_grad
+        err = float((y.detach().cpu() - ref).abs().max())
+        assert err <= tol, (mode, err)
+
+
+@pytest.mark.parametrize("name", ["fcvsr_s_32_grads", "fcvsr_full_32_grads"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_model_backward_matches_reference_gradients(dev, name, mode):
+    """CharbonnierLoss(arch.GShiftNet[_S](x), T).backward() on this repository's kernels against the gradients of the
+    unmodified reference: every parameter's strided samples and norm, the gradient-less DivEnh.Conv parameters, the exactly
+    zero dead rows of MGAA.F.1, and the gradient of the input clip."""
+    from oracle.make_golden_grads import strided, target
+    gold = load_golden(name)
+    c = gold["case"]
+    m = (arch.GShiftNet_S if c["variant"] == "S" else arch.GShiftNet)().to(dev).train()
+    m.load_state_dict(arch.seeded_state_dict(c["variant"], c["seed"]))
+    m.compute_dtype = mode
+    x = make_clip(c["clip_seed"], c["b"], c["h"], c["w"]).to(dev).requires_grad_()
+    hr = target(c["target_seed"], c["b"], c["h"], c["w"]).to(dev)
+    loss = CharbonnierLoss(m(x), hr)
+    loss.backward()
+    torch.cuda.synchronize()
+    rel = 2e-3 if mode == "fp32" else float(__import__("os").environ.get("FCVSR_TEST_TF32_GRAD_TOL", "2e-2"))
+    assert abs(float(loss) - gold["loss"]) <= (1e-5 if mode == "fp32" else 1e-3) * gold["loss"]
+    params = dict(m.named_parameters())          # de-duplicated like the reference's: the aliased RCB appears once
+    worst = (0.0, None)
+    for k, ref in gold["grads"].items():
+        p = params.get(k)
+        if p is None and ".RCB." in k:
+            p = params[k.replace(".RCB.", ".body.3.")]
+        assert p is not None and p.grad is not None, k
+        got = p.grad.detach().cpu()
+        e = float((strided(got) - ref["samples"]).abs().max()) / max(ref["amax"], 1e-6)
+        worst = max(worst, (e, k))
+        assert e <= rel, (k, e)
+        assert abs(float(got.norm()) - ref["norm"]) <= rel * max(ref["norm"], 1e-6), k
+    for k in gold["no_grad"]:
+        p = params.get(k)
+        if p is None and ".RCB." in k:
+            p = params[k.replace(".RCB.", ".body.3.")]
+        assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+    assert float((strided(x.grad.detach().cpu(), 64) - gold["dx"]).abs().max()) <= rel * float(gold["dx"].abs().max())
+    f1 = m.MGAA.F[1].weight.grad
+    a = f1.shape[0] // 384
+    dead = torch.cat([f1[i * 384 + 192:(i + 1) * 384] for i in range(a)])
+    assert float(dead.abs().max()) == 0.0
+    print(f"{name} {mode}: worst relative gradient error {worst[0]:.2e} at {worst[1]}")
+
+
+def test_train_step_on_the_fcvsr_model(dev):
+    """The reference's loop body (train_LD_freqCVSR_22.py:243-251) on the product model with this repository's loss, backward
+    kernels and Adam: three steps on one batch lower the Charbonnier loss and move every live parameter."""
+    from fcvsr_b200.ops.optim import Adam
+    from fcvsr_b200.train import train_step
+    m = arch.GShiftNet_S().to(dev).train()
+    m.load_state_dict(arch.seeded_state_dict("S", 0))
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    opt = Adam(m.parameters(), lr=2e-5, weight_decay=1e-5)
+    x = make_clip(3, 2, 32, 32).to(dev)
+    hr = torch.rand(2, 1, 128, 128, generator=torch.Generator().manual_seed(4)).to(dev)
+    losses = [float(train_step(m, opt, x, hr, CharbonnierLoss)) for _ in range(3)]
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0], losses
+    moved = sum(int(not torch.equal(p.detach(), before[k])) for k, p in m.named_parameters())
+    dead = sum(1 for k, _ in m.named_parameters() if ".Conv." in k)
+    assert moved == len(before) - dead, (moved, len(before), dead)
