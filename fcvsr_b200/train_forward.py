@@ -45,15 +45,10 @@ class _Ctx:
         pi = torch.where(j < n, 2 * j + 1, 2 * (j - n))          # reference xk_f channel j -> interleaved float index
         self.inv = torch.argsort(pi)                               # interleaved index i <- reference channel inv[i]
 
-    def conv(self, x, mod_or_w, bias=None, stride=1, exact=False):
-        """exact=True keeps the convolution on the fp32 CUDA-core kernel in "tf32" mode too: the per-bin MLPs of MGAAbk act on
-        spectra whose dynamic range spans the DC bin to the noise floor, and the offsets they produce are differentiated through
-        bilinear sampling, so TF32 operand rounding there costs gradient accuracy (3e-2 of a gradient's scale on the PReLU
-        slopes of the offset ConvBlks) for 2 % of the FLOPs."""
-        mode = "fp32" if exact else self.mode
+    def conv(self, x, mod_or_w, bias=None, stride=1):
         if isinstance(mod_or_w, torch.nn.Conv2d):
-            return A.conv2d(x, mod_or_w.weight, mod_or_w.bias, mod_or_w.stride[0], mode)
-        return A.conv2d(x, mod_or_w, bias, stride, mode)
+            return A.conv2d(x, mod_or_w.weight, mod_or_w.bias, mod_or_w.stride[0], self.mode)
+        return A.conv2d(x, mod_or_w, bias, stride, self.mode)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -72,21 +67,21 @@ def _mgaa(cx: _Ctx, x: torch.Tensor) -> torch.Tensor:
     w4 = mg.convfuse[4].weight[inv]
 
     def fuse(sa):
-        h = F.relu(cx.conv(_cl(torch.cat([sa, s2], 1)), w0, exact=True))
-        h = F.relu(cx.conv(h, mg.convfuse[2].weight, exact=True))
-        return cx.conv(h, w4, exact=True) + (sa - s2)              # :1472-1473
+        h = F.relu(cx.conv(_cl(torch.cat([sa, s2], 1)), w0))
+        h = F.relu(cx.conv(h, mg.convfuse[2].weight))
+        return cx.conv(h, w4) + (sa - s2)              # :1472-1473
 
     of, ob = fuse(s1), fuse(s3)
-    sim = cx.conv(F.relu(cx.conv(_cl(s2), mg.convcrt[0].weight[:, inv], exact=True)), mg.convcrt[2].weight, exact=True)   # :1474
+    sim = cx.conv(F.relu(cx.conv(_cl(s2), mg.convcrt[0].weight[:, inv])), mg.convcrt[2].weight)   # :1474
     corr = A.corr_lookup(spec, 0, 2 * n)                           # corr_f feeds both branches (:1488)
     wc = mg.convcorr[0].weight[:, :2 * n + 81]                     # the two flow channels are zeros (:1484-1485)
     wc = torch.cat([wc[:, :2 * n][:, inv], wc[:, 2 * n:], wc.new_zeros(wc.shape[0], 15, 1, 1)], 1)   # K padded to 224
     zpad = spec.new_zeros(B, 15, H, spec.shape[3])
 
     def corr_mlp(o):
-        h = F.relu(cx.conv(_cl(torch.cat([o, corr, zpad], 1)), wc, exact=True))
-        h = F.relu(cx.conv(h, mg.convcorr[2].weight, exact=True))
-        return cx.conv(h, mg.convcorr[4].weight, exact=True)       # [B,4,H,Wf]
+        h = F.relu(cx.conv(_cl(torch.cat([o, corr, zpad], 1)), wc))
+        h = F.relu(cx.conv(h, mg.convcorr[2].weight))
+        return cx.conv(h, mg.convcorr[4].weight)       # [B,4,H,Wf]
 
     off_f, off_b = corr_mlp(of), corr_mlp(ob)
     zs = []
