@@ -21,6 +21,7 @@ _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "f": ctypes.c_float, "d": ctypes.
 SIGNATURES = {
     "fcvsr_conv2d_direct": "pii pp pi pi pi iiiiiii if p ii pii i s",
     "fcvsr_conv2d_tc": "pi pp pi pi pi iiiiii if p i pii i i s",
+    "fcvsr_conv2d_tc_multi": "i pi pp pi pi pp iiii i f p pi i i s",
     "fcvsr_fft_r2c_w": "pi p p iiii s",
     "fcvsr_fft_c2c_h": "p p p p iiii i f ii p s",
     "fcvsr_fft_c2r_w": "p pi p iiii f s",
@@ -33,6 +34,9 @@ SIGNATURES = {
     "fcvsr_divenh_step": "ppppp i ii pppp ppp ii s",
     "fcvsr_mffr_final": "pp pi pi ii s",
     "fcvsr_context_block": "pi ppp pp ii i s",
+    "fcvsr_context_block_multi": "i pi ppp pp i p i s",
+    "fcvsr_rcb_finish_multi": "i ppp ppp pp i iii s",
+    "fcvsr_level_mix_multi": "i pi pi p p pp i pp pi iii s",
     "fcvsr_rcb_finish": "ppp p ii p i p ii i i s",
     "fcvsr_level_mix": "pi pi p f pp iii pi i i i s",
     "fcvsr_pixel_shuffle": "pi pi iiii i s",

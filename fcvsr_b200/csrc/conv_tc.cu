@@ -59,14 +59,24 @@ extern "C" int fcvsr_debug_conv_trace(long long* host, int n) {
 #define TC_STAMP_NS(n) do {} while (0)
 #endif
 
+#define TC_MAX_PROB 3
+// One launch can run the same convolution (same weights, bias, activation, strides) on up to three tensors of different
+// spatial size: the three pyramid levels of SCNetbk (BlockRCB applies one body to every level, CVSR_freq.py:766-770).  The
+// persistent CTAs walk ONE tile list that spans the levels, so the small levels (1/4 and 1/16 of the pixels) fill the SMs
+// next to level 0 instead of running as under-filled launches on side streams.
+struct ConvTcProblem {
+    const float* res; const float* res2; float* y; float* y2;
+    int H, W, tiles_x, tiles_y, tile_begin;    // tile_begin: index of the problem's first tile in the launch's tile list
+};
 struct ConvTcParams {
-    const float* bias; const float* res; int ldres; const float* res2; int ldres2;
-    float* y; int ldy;
-    float* y2; int ldy2; int round_out;  // y2: optional TF32-rounded copy of y (non-shuffled outputs only)
-    int B, H, W, Cin, Cout, ks;          // Cout = padded (multiple of 16) GEMM N
+    const float* bias; int ldres; int ldres2;
+    int ldy;
+    int ldy2; int round_out;             // y2: optional TF32-rounded copy of y (non-shuffled outputs only)
+    int B, Cin, Cout, ks;                // Cout = padded (multiple of 16) GEMM N
     int cout_valid;                      // channels actually stored (== Cout, or < 16 for thin heads)
     int n_tile, n_tiles;               // N per pass, number of passes
-    int tiles_x, tiles_y, total_tiles;
+    int nprob, total_tiles;
+    ConvTcProblem prob[TC_MAX_PROB];
     int act; float slope; const float* slope_ptr; int ps;
     int wide;                            // 32-byte aligned tensors: use 256-bit loads / stores in the epilogue
     int epi_sets;                        // 1, 2 or 4 epilogue warp sets (see the epilogue)
@@ -74,18 +84,22 @@ struct ConvTcParams {
     int dbg;                             // bring-up only (FCVSR_TC_DBG): 1 no MMA, 2 no A loads, 4 no B loads, 8 no stores
 };
 
-struct TileCoord { int nt, tx, ty, b; };
+struct TileCoord { int nt, tx, ty, b, pr; };
 __device__ __forceinline__ TileCoord decode_tile(int t, const ConvTcParams& p) {
     TileCoord c;
+    c.pr = (p.nprob > 1 && t >= p.prob[1].tile_begin) ? ((p.nprob > 2 && t >= p.prob[2].tile_begin) ? 2 : 1) : 0;
+    const ConvTcProblem& q = p.prob[c.pr];
+    t -= q.tile_begin;
     c.nt = t % p.n_tiles; t /= p.n_tiles;
-    c.tx = t % p.tiles_x; t /= p.tiles_x;
-    c.ty = t % p.tiles_y; c.b = t / p.tiles_y;
+    c.tx = t % q.tiles_x; t /= q.tiles_x;
+    c.ty = t % q.tiles_y; c.b = t / q.tiles_y;
     return c;
 }
 
 template <int KS, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x1,
+               const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
     // Programmatic dependent launch: let the next convolution's CTAs take each SM as soon as this grid's CTA leaves it
     // and run their prologue (barriers, TMEM, bias, first weight stages) while the rest of this grid drains; everything
     // that touches activations sits behind griddepcontrol.wait (a no-op for a normally serialized launch).
@@ -162,8 +176,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     if (p.dbg & 2) { mbar_arrive(&full_a[stage]); if (++stage == NA) { stage = 0; phase ^= 1; } continue; }
                     mbar_expect_tx(&full_a[stage], a_copy_bytes * ncopies);
                     uint8_t* dst = a_buf + stage * A_STAGE;
+                    const CUtensorMap* mx = tc.pr == 0 ? &map_x : (tc.pr == 1 ? &map_x1 : &map_x2);
                     for (int cpy = 0; cpy < ncopies; ++cpy)
-                        tma_load_4d(dst + cpy * TC_A_COPY_BYTES, &map_x, &full_a[stage], kc * KCH, x0 + cpy, y0, tc.b);
+                        tma_load_4d(dst + cpy * TC_A_COPY_BYTES, mx, &full_a[stage], kc * KCH, x0 + cpy, y0, tc.b);
                     if (kc == kchunks - 1) TC_STAMP(tn, 1);
                     if (++stage == NA) { stage = 0; phase ^= 1; }
                 }
@@ -282,9 +297,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             acc = tn & (TC_NACC - 1);
             pacc = (uint32_t)(tn >> 2) & 1u;
             const TileCoord tc = decode_tile(t, p);
+            const ConvTcProblem& pq = p.prob[tc.pr];
             const int y = tc.ty * TC_TH + ly, x = tc.tx * TC_TW + lx;
-            const bool valid = y < p.H && x < p.W;
-            const size_t pix = ((size_t)tc.b * p.H + y) * p.W + x;
+            const bool valid = y < pq.H && x < pq.W;
+            const size_t pix = ((size_t)tc.b * pq.H + y) * pq.W + x;
+
             mbar_wait_warp(&tm_full[acc], pacc, p.err, 6);
             tc_fence_after();
             if (warp == 3 && lane == 0) TC_STAMP(tn, 8);
@@ -302,9 +319,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         if (n < p.cout_valid) {
                             float f = __uint_as_float(r[j]) + bias_s[n];
                             f = fcvsr_act(f, p.act, slope);
-                            if (p.res) f += p.res[pix * p.ldres + n];
-                            if (p.res2) f -= p.res2[pix * p.ldres2 + n];
-                            p.y[pix * p.ldy + n] = f;
+                            if (pq.res) f += pq.res[pix * p.ldres + n];
+                            if (pq.res2) f -= pq.res2[pix * p.ldres2 + n];
+                            pq.y[pix * p.ldy + n] = f;
                         }
                     }
                 } else if (valid) {
@@ -313,21 +330,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     lds_bias16(bias_sa + n0 * 4, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fcvsr_act(__uint_as_float(r[j]) + v[j], p.act, slope);
-                    if (p.res) {
+                    if (pq.res) {
                         float rv[16];
                         if (p.wide) {
-                            ld_global_v8(p.res + pix * p.ldres + n0, rv);
-                            ld_global_v8(p.res + pix * p.ldres + n0 + 8, rv + 8);
+                            ld_global_v8(pq.res + pix * p.ldres + n0, rv);
+                            ld_global_v8(pq.res + pix * p.ldres + n0 + 8, rv + 8);
                         } else {
-                            const float4* rp = reinterpret_cast<const float4*>(p.res + pix * p.ldres + n0);
+                            const float4* rp = reinterpret_cast<const float4*>(pq.res + pix * p.ldres + n0);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) { const float4 t4 = rp[j]; rv[4 * j] = t4.x; rv[4 * j + 1] = t4.y; rv[4 * j + 2] = t4.z; rv[4 * j + 3] = t4.w; }
                         }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] += rv[j];
                     }
-                    if (p.res2) {
-                        const float4* rp = reinterpret_cast<const float4*>(p.res2 + pix * p.ldres2 + n0);
+                    if (pq.res2) {
+                        const float4* rp = reinterpret_cast<const float4*>(pq.res2 + pix * p.ldres2 + n0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 rv = rp[j];
@@ -335,18 +352,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         }
                     }
                     // operand-typed outputs: TF32-rounded fp32, or bf16 in bf16 mode
-                    if (p.y2) {
+                    if (pq.y2) {
                         if (BF16) {
-                            if (p.wide) store_bf16x16_v8(reinterpret_cast<__nv_bfloat16*>(p.y2) + pix * p.ldy2 + n0, v);
-                            else store_bf16x16(reinterpret_cast<__nv_bfloat16*>(p.y2) + pix * p.ldy2 + n0, v);
+                            if (p.wide) store_bf16x16_v8(reinterpret_cast<__nv_bfloat16*>(pq.y2) + pix * p.ldy2 + n0, v);
+                            else store_bf16x16(reinterpret_cast<__nv_bfloat16*>(pq.y2) + pix * p.ldy2 + n0, v);
                         } else if (p.wide) {
                             float vr[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) vr[j] = round_tf32(v[j]);
-                            st_global_v8(p.y2 + pix * p.ldy2 + n0, vr);
-                            st_global_v8(p.y2 + pix * p.ldy2 + n0 + 8, vr + 8);
+                            st_global_v8(pq.y2 + pix * p.ldy2 + n0, vr);
+                            st_global_v8(pq.y2 + pix * p.ldy2 + n0 + 8, vr + 8);
                         } else {
-                            float4* d2 = reinterpret_cast<float4*>(p.y2 + pix * p.ldy2 + n0);
+                            float4* d2 = reinterpret_cast<float4*>(pq.y2 + pix * p.ldy2 + n0);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 d2[j] = make_float4(round_tf32(v[4 * j]), round_tf32(v[4 * j + 1]), round_tf32(v[4 * j + 2]),
@@ -356,26 +373,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     size_t off;
                     if (p.ps) {
                         const int ij = n0 / c4, c = n0 - ij * c4;
-                        const size_t opix = ((size_t)tc.b * 2 * p.H + 2 * y + (ij >> 1)) * (2 * (size_t)p.W) + 2 * x + (ij & 1);
+                        const size_t opix = ((size_t)tc.b * 2 * pq.H + 2 * y + (ij >> 1)) * (2 * (size_t)pq.W) + 2 * x + (ij & 1);
                         off = opix * p.ldy + c;
                     } else {
                         off = pix * p.ldy + n0;
                     }
                     if (p.round_out == 2) {          // fp16 output tensor (ld in elements, 32-byte aligned rows)
-                        store_f16x16_v8(reinterpret_cast<unsigned short*>(p.y) + off, v);
+                        store_f16x16_v8(reinterpret_cast<unsigned short*>(pq.y) + off, v);
                     } else if (BF16 && p.round_out) {
-                        if (p.wide) store_bf16x16_v8(reinterpret_cast<__nv_bfloat16*>(p.y) + off, v);
-                        else store_bf16x16(reinterpret_cast<__nv_bfloat16*>(p.y) + off, v);
+                        if (p.wide) store_bf16x16_v8(reinterpret_cast<__nv_bfloat16*>(pq.y) + off, v);
+                        else store_bf16x16(reinterpret_cast<__nv_bfloat16*>(pq.y) + off, v);
                     } else {
                         if (p.round_out) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
                         }
                         if (p.wide) {
-                            st_global_v8(p.y + off, v);
-                            st_global_v8(p.y + off + 8, v + 8);
+                            st_global_v8(pq.y + off, v);
+                            st_global_v8(pq.y + off + 8, v + 8);
                         } else {
-                            float4* dp = reinterpret_cast<float4*>(p.y + off);
+                            float4* dp = reinterpret_cast<float4*>(pq.y + off);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) dp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
@@ -439,11 +456,12 @@ static int* tc_err_flag() {
     return flag;
 }
 
-extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
-                               const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
-                               int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
-                               float* y2, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t st) {
-    if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
+// Shared host side: `np` problems (same weights / epilogue, different spatial sizes) in one launch.
+static int conv_tc_launch(int np, const void* const* xs, const float* const* ress, const float* const* res2s, float* const* ys,
+                          float* const* y2s, const int* Hs, const int* Ws, int ldx, const float* w, const float* bias, int ldres,
+                          int ldres2, int ldy, int B, int Cin, int Cout, int ksize, int act, float slope, const float* slope_ptr,
+                          int pixel_shuffle, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t st) {
+    if (np < 1 || np > TC_MAX_PROB || !w || B <= 0) return FCVSR_ERR_ARG;
     const int kch = op16 ? 64 : 32, esz = op16 ? 2 : 4;
     if ((ksize != 1 && ksize != 3) || Cin % kch || Cin <= 0 || Cout <= 0) return FCVSR_ERR_UNSUPPORTED;
     if (op16 && (ldx & 7)) return FCVSR_ERR_UNSUPPORTED;
@@ -452,14 +470,27 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     if (thin) Cout = 16;
     if (Cout % 16) return FCVSR_ERR_UNSUPPORTED;
     if (ldx & 3) return FCVSR_ERR_UNSUPPORTED;
-    if (!thin && ((ldy & 3) || (res && (ldres & 3)) || (res2 && (ldres2 & 3)))) return FCVSR_ERR_UNSUPPORTED;
-    if (((uintptr_t)x | (uintptr_t)w) & 15) return FCVSR_ERR_UNSUPPORTED;
-    if (!thin && (((uintptr_t)y | (uintptr_t)res | (uintptr_t)res2) & 15)) return FCVSR_ERR_UNSUPPORTED;
-    if (thin && (pixel_shuffle || y2 || round_out)) return FCVSR_ERR_UNSUPPORTED;
-    if (y2 && (pixel_shuffle || (ldy2 & 3) || ((uintptr_t)y2 & 15))) return FCVSR_ERR_UNSUPPORTED;
-    if (op16 && ((round_out && (ldy & 7)) || (y2 && (ldy2 & 7)))) return FCVSR_ERR_UNSUPPORTED;
-    if (round_out == 2 && (thin || pixel_shuffle || (ldy & 15) || ((uintptr_t)y & 31))) return FCVSR_ERR_UNSUPPORTED;
+    if ((uintptr_t)w & 15) return FCVSR_ERR_UNSUPPORTED;
     if (act == FCVSR_ACT_PRELU && !slope_ptr) return FCVSR_ERR_ARG;
+    bool any_res = false, any_res2 = false, any_y2 = false;
+    uintptr_t align_or = 0;
+    for (int i = 0; i < np; ++i) {
+        if (!xs[i] || !ys[i] || Hs[i] <= 0 || Ws[i] <= 0) return FCVSR_ERR_ARG;
+        const float* res = ress ? ress[i] : nullptr;
+        const float* res2 = res2s ? res2s[i] : nullptr;
+        float* y2 = y2s ? y2s[i] : nullptr;
+        any_res |= res != nullptr; any_res2 |= res2 != nullptr; any_y2 |= y2 != nullptr;
+        if ((uintptr_t)xs[i] & 15) return FCVSR_ERR_UNSUPPORTED;
+        if (!thin && (((uintptr_t)ys[i] | (uintptr_t)res | (uintptr_t)res2) & 15)) return FCVSR_ERR_UNSUPPORTED;
+        if (y2 && ((uintptr_t)y2 & 15)) return FCVSR_ERR_UNSUPPORTED;
+        if (round_out == 2 && ((uintptr_t)ys[i] & 31)) return FCVSR_ERR_UNSUPPORTED;
+        align_or |= (uintptr_t)ys[i] | (uintptr_t)res | (uintptr_t)y2;
+    }
+    if (!thin && ((ldy & 3) || (any_res && (ldres & 3)) || (any_res2 && (ldres2 & 3)))) return FCVSR_ERR_UNSUPPORTED;
+    if (thin && (pixel_shuffle || any_y2 || round_out)) return FCVSR_ERR_UNSUPPORTED;
+    if (any_y2 && (pixel_shuffle || (ldy2 & 3))) return FCVSR_ERR_UNSUPPORTED;
+    if (op16 && ((round_out && (ldy & 7)) || (any_y2 && (ldy2 & 7)))) return FCVSR_ERR_UNSUPPORTED;
+    if (round_out == 2 && (thin || pixel_shuffle || (ldy & 15))) return FCVSR_ERR_UNSUPPORTED;
     int n_tile = Cout, n_tiles = 1;
     if (Cout > 128) {       // largest N tile <= 128 that is a multiple of 16 and divides Cout
         n_tile = 0;
@@ -473,13 +504,15 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     EncodeTiledFn enc = get_encode();
     if (!enc) return FCVSR_ERR_CUDA;
 
-    CUtensorMap map_x, map_w;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)ldx * esz, (cuuint64_t)W * ldx * esz, (cuuint64_t)H * W * ldx * esz};
+    CUtensorMap map_x[TC_MAX_PROB], map_w;
+    for (int i = 0; i < TC_MAX_PROB; ++i) {
+        const int j = i < np ? i : 0;           // unused slots repeat problem 0 (the kernel never reads them)
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Ws[j], (cuuint64_t)Hs[j], (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)ldx * esz, (cuuint64_t)Ws[j] * ldx * esz, (cuuint64_t)Hs[j] * Ws[j] * ldx * esz};
         cuuint32_t box[4] = {(cuuint32_t)kch, TC_TW, (cuuint32_t)(ksize == 3 ? TC_TH + 2 : TC_TH), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (enc(&map_x, op16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        if (i >= np) { map_x[i] = map_x[0]; continue; }
+        if (enc(&map_x[i], op16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)xs[j], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return FCVSR_ERR_CUDA;
     }
@@ -494,9 +527,21 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
             return FCVSR_ERR_CUDA;
     }
     ConvTcParams p;
-    p.bias = bias; p.res = res; p.ldres = ldres; p.res2 = res2; p.ldres2 = ldres2; p.y = y; p.ldy = ldy; p.y2 = y2; p.ldy2 = ldy2; p.round_out = round_out;
-    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ksize; p.cout_valid = cout_valid;
+    p.bias = bias; p.ldres = ldres; p.ldres2 = ldres2; p.ldy = ldy; p.ldy2 = ldy2; p.round_out = round_out;
+    p.B = B; p.Cin = Cin; p.Cout = Cout; p.ks = ksize; p.cout_valid = cout_valid;
     p.n_tile = n_tile; p.n_tiles = n_tiles;
+    p.nprob = np;
+    int tiles = 0;
+    for (int i = 0; i < TC_MAX_PROB; ++i) {
+        ConvTcProblem& q = p.prob[i];
+        const int j = i < np ? i : 0;
+        q.res = ress ? ress[j] : nullptr; q.res2 = res2s ? res2s[j] : nullptr; q.y = ys[j]; q.y2 = y2s ? y2s[j] : nullptr;
+        q.H = Hs[j]; q.W = Ws[j];
+        q.tiles_x = (q.W + TC_TW - 1) / TC_TW; q.tiles_y = (q.H + TC_TH - 1) / TC_TH;
+        q.tile_begin = tiles;
+        if (i < np) tiles += q.tiles_x * q.tiles_y * B * n_tiles;
+    }
+    p.total_tiles = tiles;
     {   // 1x1: four sets (epilogue-bound, 4-16 MMAs per tile); 3x3 bf16: two sets (64->64 24.8 -> 22.0 us, 64->256 at 360x640
         // 296 -> 272 us = 1.0 PFLOP/s); 3x3 TF32 (twice the MMAs per tile): one set, all warps on the same tile
         int es = 0;
@@ -505,15 +550,12 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
 #endif
         p.epi_sets = es == 1 || es == 2 || es == 4 ? es : (ksize == 1 ? 4 : (op16 ? 2 : 1));
     }
-    p.tiles_x = (W + TC_TW - 1) / TC_TW; p.tiles_y = (H + TC_TH - 1) / TC_TH;
-    p.total_tiles = p.tiles_x * p.tiles_y * B * n_tiles;
     p.act = act; p.slope = slope; p.slope_ptr = slope_ptr; p.ps = pixel_shuffle;
     p.err = tc_err_flag();
     {   // 256-bit epilogue accesses need 32-byte aligned rows for every tensor the epilogue touches
-        const uintptr_t a = (uintptr_t)y | (uintptr_t)res | (uintptr_t)y2;
         const int esz_y = ((op16 && round_out) || round_out == 2) ? 2 : 4, esz_y2 = op16 ? 2 : 4;
-        p.wide = !thin && !(a & 31) && !((ldy * esz_y) & 31) && (!res || !((ldres * 4) & 31)) && (!y2 || !((ldy2 * esz_y2) & 31)) &&
-                 (!pixel_shuffle || !(((Cout >> 2) * esz_y) & 31));
+        p.wide = !thin && !(align_or & 31) && !((ldy * esz_y) & 31) && (!any_res || !((ldres * 4) & 31)) &&
+                 (!any_y2 || !((ldy2 * esz_y2) & 31)) && (!pixel_shuffle || !(((Cout >> 2) * esz_y) & 31));
     }
     p.dbg = 0;
 #ifdef FCVSR_BRINGUP      // bring-up switches (tools/gpu_conv_trace.py builds its own copy with -DFCVSR_BRINGUP); not in the product library
@@ -550,12 +592,38 @@ extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const fl
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t le;
     if (op16) {
-        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, true>, map_x, map_w, p);
-        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, map_x, map_w, p);
+        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, true>, map_x[0], map_x[1], map_x[2], map_w, p);
+        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, map_x[0], map_x[1], map_x[2], map_w, p);
     } else {
-        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, false>, map_x, map_w, p);
-        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, map_x, map_w, p);
+        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, false>, map_x[0], map_x[1], map_x[2], map_w, p);
+        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, map_x[0], map_x[1], map_x[2], map_w, p);
     }
     if (le != cudaSuccess) return FCVSR_ERR_CUDA;
     return fcvsr_launch_status();
+}
+
+extern "C" int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, const float* res, int ldres,
+                               const float* res2, int ldres2, float* y, int ldy, int B, int H, int W, int Cin, int Cout,
+                               int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
+                               float* y2, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t st) {
+    if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
+    const void* xs[1] = {x};
+    const float* ress[1] = {res};
+    const float* res2s[1] = {res2};
+    float* ys[1] = {y};
+    float* y2s[1] = {y2};
+    return conv_tc_launch(1, xs, ress, res2s, ys, y2s, &H, &W, ldx, w, bias, ldres, ldres2, ldy, B, Cin, Cout, ksize, act, slope,
+                          slope_ptr, pixel_shuffle, ldy2, round_out, max_ctas, op16, st);
+}
+
+// The same convolution on up to three tensors of different spatial size in ONE launch (the pyramid levels of SCNetbk,
+// CVSR_freq.py:766-770: BlockRCB applies one body to every level).  x / res / y / y2: HOST arrays of nprob device pointers
+// (res, y2 may be NULL or hold NULL entries); H, W: HOST arrays; ld*, B, channels, epilogue as fcvsr_conv2d_tc.
+extern "C" int fcvsr_conv2d_tc_multi(int nprob, const void* const* x, int ldx, const float* w, const float* bias,
+                                     const float* const* res, int ldres, float* const* y, int ldy, const int* H, const int* W,
+                                     int B, int Cin, int Cout, int ksize, int act, float slope, const float* slope_ptr,
+                                     float* const* y2, int ldy2, int round_out, int op16, cudaStream_t st) {
+    if (!x || !y || !H || !W) return FCVSR_ERR_ARG;
+    return conv_tc_launch(nprob, x, res, nullptr, y, y2, H, W, ldx, w, bias, ldres, 0, ldy, B, Cin, Cout, ksize, act, slope,
+                          slope_ptr, 0, ldy2, round_out, 0, op16, st);
 }

@@ -303,8 +303,8 @@ class Engine:
             buf(f"td{l}", B, p // 4, 64)                           # down conv output, already at the next level's size
             buf(f"rrp{l}", B, p // 4, 64, op=self.use_tc)          # 2x2 mean of rr: input of the down conv
             buf(f"tu{l}", B, p, 64)
-            buf(f"ctxp{l}", B * ((p + 127) // 128) * 66)
-            buf(f"add{l}", B, 64)
+        buf("ctxall", sum(B * ((h * w + 127) // 128) * 66 for h, w in dims))       # ContextBlock partials of the three levels
+        buf("addall", 3, B, 64)
         p2, p3 = dims[1][0] * dims[1][1], dims[2][0] * dims[2][1]
         buf("o2", B, p2, 64, op=self.use_tc)
         buf("o3", B, p3, 64, op=self.use_tc)
@@ -371,20 +371,33 @@ class Engine:
                pk.cout, pk.k, pk.stride, act, slope, slope_ptr, int(pk.ps), 0, y2, ldy2, int(rnd and not self.op16),
                int(self.op16), st)
 
-    @staticmethod
-    def _level_caps(B, dims, sms=148):
-        """Split the SMs over the three concurrently running pyramid levels so that the number of 8x16-pixel
-        tile rounds of the slowest level is minimal (levels hold 1, 1/4, 1/16 of the pixels)."""
-        tiles = [B * ((h + 7) // 8) * ((w + 15) // 16) for h, w in dims]
-        best = None
-        for c2 in range(1, sms - 1):
-            for c1 in range(1, sms - c2):
-                c0 = sms - c1 - c2
-                rounds = max(-(-tiles[0] // c0), -(-tiles[1] // c1), -(-tiles[2] // c2))
-                key = (rounds, -c0)
-                if best is None or key < best[0]:
-                    best = (key, (c0, c1, c2))
-        return best[1]
+    def _conv_multi(self, pk: _ConvPack, xs, ldx, ys, ldy, B, dims, act=C.ACT_NONE, slope=0.0, res=None, ldres=0, y2=None,
+                    ldy2=0, rnd=False):
+        """The same convolution on several tensors of different spatial size (pyramid levels) in one launch.  xs / ys / res /
+        y2: lists of device addresses, dims: list of (H, W)."""
+        n = len(xs)
+        if not (self.use_tc and pk.tc_ok):          # exact-fp32 mode (CUDA-core kernel): one launch per level
+            for i in range(n):
+                self._conv(pk, xs[i], ldx, ys[i], ldy, B, dims[i][0], dims[i][1], act=act, slope=slope,
+                           res=res[i] if res else 0, ldres=ldres, y2=y2[i] if y2 else 0, ldy2=ldy2, rnd=rnd)
+            return
+        self.launches += 1
+        self.tc_launches += 1
+        vp = lambda ptrs: (ctypes.c_void_p * n)(*ptrs)  # noqa: E731
+        args = (n, vp(xs), ldx, pk.w_tc.data_ptr(), pk.bias.data_ptr() if pk.bias is not None else 0, vp(res) if res else None,
+                ldres, vp(ys), ldy, (ctypes.c_int * n)(*[d[0] for d in dims]), (ctypes.c_int * n)(*[d[1] for d in dims]), B,
+                pk.cin, pk.cout, pk.k, act, slope, 0, vp(y2) if y2 else None, ldy2, int(rnd), int(self.op16), self.st)
+        prof = self.profile
+        if prof is not None:
+            e0, e1 = self._event_pair()
+            e0.record()
+            C.call("fcvsr_conv2d_tc_multi", *args)
+            e1.record()
+            npix = sum(h * w for h, w in dims)
+            prof.append((f"tc {pk.cin_logical}->{pk.cout} k{pk.k} pyramid x{n}", 2.0 * B * npix * pk.cin_logical * pk.cout * pk.k * pk.k,
+                         4.0 * B * npix * (pk.cin_logical + pk.cout), e0, e1))
+            return
+        C.call("fcvsr_conv2d_tc_multi", *args)
 
     def _event_pair(self):
         # inside a graph capture only "external" events become event-record nodes whose times can be read after a replay
@@ -662,11 +675,12 @@ class Engine:
         if self.use_tc:
             self._k("fcvsr_round_copy", p["xs0"], 64, p["xsr0"], 64, 64, 64, B * npix, int(self.op16))
 
-    # SCNetbk (:807-822).  The three pyramid levels of a BlockRCB are independent until the cross-level
-    # sum, so each level runs on its own stream (fork/join with events; also valid under graph capture):
-    # the small levels (1/4 and 1/16 of the pixels) are latency-bound launches that hide behind level 0.
-    # Full-precision streams (xs, cur, t, r0, rr) stay fp32; every tensor-core convolution reads the operand-typed
-    # copy written next to it (xsr, curr, tr, r0h, rrh: TF32-rounded fp32 or bf16).
+    # SCNetbk (:807-822).  BlockRCB applies ONE body to the three pyramid levels (:766-770), so every convolution and every
+    # helper kernel of a block runs the three levels in one launch (fcvsr_conv2d_tc_multi / *_multi: one tile or thread list
+    # spanning the levels) on a single stream: the small levels (1/4 and 1/16 of the pixels) fill SMs next to level 0 instead
+    # of running as under-filled launches on side streams, and back-to-back convolutions keep their programmatic-dependent-
+    # launch overlap.  Full-precision streams (xs, cur, t, r0, rr) stay fp32; every tensor-core convolution reads the
+    # operand-typed copy written next to it (xsr, curr, tr, r0h, rrh: TF32-rounded fp32 or bf16).
     def _scnet(self, ws, p, B, H, W):
         P, G = self.packs, self.model.SCGroupN
         dims = [(H, W), (H // 2, W // 2), (H // 4, W // 4)]
@@ -676,93 +690,58 @@ class Engine:
         r016 = bool(O16) and self.r016
         rr16 = int(bool(O16) and self.rr16)
         t16 = 4 if (O16 and self.t16) else 0      # down / up conv outputs td, tu as bf16 tensors (flag bit of level_mix)
-        main = torch.cuda.current_stream()
-        ms = self.multi_stream and (self.profile is None or self.profile_in_graph)
-        if ms:
-            dev = main.device
-            if dev not in self._streams:
-                self._streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
-            streams = (main,) + self._streams[dev]
-            caps = self._level_caps(B, dims)   # SMs given to each level's persistent conv grid (sum = 148)
-            if self.level_caps is not None:
-                caps = tuple(self.level_caps)
-            for s_ in streams[1:]:
-                s_.wait_stream(main)
-        else:
-            streams, caps = (main, main, main), (0, 0, 0)
-
-        def on(l):
-            self.st = streams[l].cuda_stream
-            self.max_ctas = caps[l]
-            return torch.cuda.stream(streams[l])
-
-        def cross_join():
-            if not ms:
-                return
-            evs = [torch.cuda.Event() for _ in range(3)]
-            for l in range(3):
-                evs[l].record(streams[l])
-            for l in range(3):
-                for o in range(3):
-                    if o != l:
-                        streams[l].wait_event(evs[o])
-
+        L3 = (0, 1, 2)
+        vp = lambda *ptrs: (ctypes.c_void_p * len(ptrs))(*ptrs)  # noqa: E731
+        ia = lambda *v: (ctypes.c_int * len(v))(*v)  # noqa: E731
+        H3, W3 = ia(*[d[0] for d in dims]), ia(*[d[1] for d in dims])
+        P3 = ia(*[d[0] * d[1] for d in dims])
+        coef3 = (ctypes.c_float * 3)(2.0, 1.0, 2.0)              # level 0 has d = r, level 2 has u = r (:771-776)
+        adds = [p["addall"] + l * B * 64 * 4 for l in L3]
         for g in range(G):
-            inp = [p[f"xs{l}"] if g == 0 else p[f"cur{l}"] for l in range(3)]
-            inp_r = [p[f"xsr{l}"] if g == 0 else p[f"curr{l}"] for l in range(3)] if R else inp
+            inp = [p[f"xs{l}"] if g == 0 else p[f"cur{l}"] for l in L3]
+            inp_r = [p[f"xsr{l}"] if g == 0 else p[f"curr{l}"] for l in L3] if R else inp
             for k in range(3):
                 q = f"g{g}.b{k}."
-                src = inp if k == 0 else [p[f"t{l}"] for l in range(3)]
-                src_r = (inp_r if k == 0 else [p[f"tr{l}"] for l in range(3)]) if R else src
-                for l, (h, w) in enumerate(dims):      # BlockRCB body (:729-751) + RCB (:705-725)
-                    with on(l):
-                        r0_op = p[f"r0h{l}"] if R else p[f"r0{l}"]
-                        rr_op = p[f"rrh{l}"] if R else p[f"rr{l}"]
-                        self._conv(P[q + "c0"], src_r[l], 64, p[f"a128_{l}"], 128, B, h, w, act=LK, slope=0.1, rnd=True)
-                        if r016:                        # RCB input r0 only as the bf16 operand tensor (also the RCB skip)
-                            self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0h{l}"], 64, B, h, w, rnd=True)
-                        else:
-                            self._conv(P[q + "c2"], p[f"a128_{l}"], 128, p[f"r0{l}"], 64, B, h, w, y2=p[f"r0h{l}"], ldy2=64)
-                        self._conv(P[q + "r0"], r0_op, 64, p[f"c1{l}"], 64, B, h, w, act=LK, slope=0.2, rnd=True)
-                        # res (RCB body output, consumed by the ContextBlock and the RCB tail only) is a bf16 tensor in bf16 mode
-                        self._conv(P[q + "r2"], p[f"c1{l}"], 64, p[f"res{l}"], 64, B, h, w, rnd=bool(res16))
-                        self.launches += 1
-                        self._k("fcvsr_context_block", p[f"res{l}"], 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
-                                P[q + "a2"].data_ptr(), p[f"ctxp{l}"], p[f"add{l}"], B, h * w, res16)
-                        self._k("fcvsr_rcb_finish", p[f"res{l}"], p[f"add{l}"], p[f"r0h{l}"] if r016 else p[f"r0{l}"],
-                                0 if rr16 else p[f"rr{l}"], B, h * w, p[f"rrh{l}"] if (R and (l > 0 or rr16)) else 0, O16,
-                                p[f"rrp{l}"] if l < 2 else 0, h, w, int(not R), res16 | (2 if r016 else 0))
-                        if l < 2:                       # down: 1x1 conv on the 2x2 mean == mean of the conv (:753-757)
-                            self._conv(P[q + "down"], p[f"rrp{l}"], 64, p[f"td{l}"], 64, B, h // 2, w // 2, rnd=bool(t16))
-                        if l > 0:                       # up: 1x1 conv, interpolated in level_mix (:759-763)
-                            self._conv(P[q + "up"], rr_op, 64, p[f"tu{l}"], 64, B, h, w, rnd=bool(t16))
-                cross_join()
-                # x + r + d + u (:771-776): level 0 has d = r, level 2 has u = r
-                tr = [p[f"tr{l}"] if R else 0 for l in range(3)]
-                with on(0):
-                    self._k("fcvsr_level_mix", src[0], 64, p["t0"], 64, p["rrh0" if rr16 else "rr0"], 2.0, 0, p["tu1"], B, *dims[0], tr[0], 64, 0, O16, 2 * rr16 + t16)
-                with on(1):
-                    self._k("fcvsr_level_mix", src[1], 64, p["t1"], 64, p["rrh1" if rr16 else "rr1"], 1.0, p["td0"], p["tu2"], B, *dims[1], tr[1], 64, 0, O16, 1 + 2 * rr16 + t16)
-                with on(2):
-                    self._k("fcvsr_level_mix", src[2], 64, p["t2"], 64, p["rrh2" if rr16 else "rr2"], 2.0, p["td1"], 0, B, *dims[2], tr[2], 64, 0, O16, 1 + 2 * rr16 + t16)
-                cross_join()                            # td/tu/rr of this block are overwritten by the next one
-            for l, (h, w) in enumerate(dims):           # SCGroupbk tail: x + conv(res) (:797-803)
-                with on(l):
-                    self._conv(P[f"g{g}.conv"], p[f"tr{l}"] if R else p[f"t{l}"], 64, p[f"cur{l}"], 64, B, h, w, res=inp[l],
-                               ldres=64, y2=p[f"curr{l}"], ldy2=64)
+                src = inp if k == 0 else [p[f"t{l}"] for l in L3]
+                src_r = (inp_r if k == 0 else [p[f"tr{l}"] for l in L3]) if R else src
+                r0_op = [p[f"r0h{l}"] if R else p[f"r0{l}"] for l in L3]
+                rr_op = [p[f"rrh{l}"] if R else p[f"rr{l}"] for l in L3]
+                a128 = [p[f"a128_{l}"] for l in L3]
+                # BlockRCB body (:729-751) + RCB (:705-725)
+                self._conv_multi(P[q + "c0"], src_r, 64, a128, 128, B, dims, act=LK, slope=0.1, rnd=True)
+                if r016:                        # RCB input r0 only as the bf16 operand tensor (also the RCB skip)
+                    self._conv_multi(P[q + "c2"], a128, 128, [p[f"r0h{l}"] for l in L3], 64, B, dims, rnd=True)
+                else:
+                    self._conv_multi(P[q + "c2"], a128, 128, [p[f"r0{l}"] for l in L3], 64, B, dims,
+                                     y2=[p[f"r0h{l}"] for l in L3], ldy2=64)
+                self._conv_multi(P[q + "r0"], r0_op, 64, [p[f"c1{l}"] for l in L3], 64, B, dims, act=LK, slope=0.2, rnd=True)
+                # res (RCB body output, consumed by the ContextBlock and the RCB tail only) is a bf16 tensor in bf16 mode
+                res = [p[f"res{l}"] for l in L3]
+                self._conv_multi(P[q + "r2"], [p[f"c1{l}"] for l in L3], 64, res, 64, B, dims, rnd=bool(res16))
+                self.launches += 1
+                self._k("fcvsr_context_block_multi", 3, vp(*res), 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
+                        P[q + "a2"].data_ptr(), p["ctxall"], p["addall"], B, P3, res16)
+                self._k("fcvsr_rcb_finish_multi", 3, vp(*res), vp(*adds), vp(*[p[f"r0h{l}"] if r016 else p[f"r0{l}"] for l in L3]),
+                        vp(*[0 if rr16 else p[f"rr{l}"] for l in L3]),
+                        vp(*[p[f"rrh{l}"] if (R and (l > 0 or rr16)) else 0 for l in L3]),
+                        vp(p["rrp0"], p["rrp1"], 0), H3, W3, B, O16, int(not R), res16 | (2 if r016 else 0))
+                # down: 1x1 conv on the 2x2 mean == mean of the conv (:753-757); up: 1x1 conv, interpolated in level_mix (:759-763)
+                self._conv_multi(P[q + "down"], [p["rrp0"], p["rrp1"]], 64, [p["td0"], p["td1"]], 64, B, dims[1:], rnd=bool(t16))
+                self._conv_multi(P[q + "up"], rr_op[1:], 64, [p["tu1"], p["tu2"]], 64, B, dims[1:], rnd=bool(t16))
+                # x + r + d + u (:771-776)
+                self._k("fcvsr_level_mix_multi", 3, vp(*src), 64, vp(*[p[f"t{l}"] for l in L3]), 64,
+                        vp(*[p[f"rrh{l}" if rr16 else f"rr{l}"] for l in L3]), coef3, vp(0, p["td0"], p["td1"]),
+                        vp(p["tu1"], p["tu2"], 0), B, H3, W3, vp(*[p[f"tr{l}"] if R else 0 for l in L3]), 64, 0, O16,
+                        1 + 2 * rr16 + t16)
+            # SCGroupbk tail: x + conv(res) (:797-803)
+            self._conv_multi(P[f"g{g}.conv"], [p[f"tr{l}"] if R else p[f"t{l}"] for l in L3], 64, [p[f"cur{l}"] for l in L3], 64,
+                             B, dims, res=inp, ldres=64, y2=[p[f"curr{l}"] for l in L3], ldy2=64)
         # SCNetbk skip (:816-822): outputs feed only convolutions -> operand-typed; level 0 lands in the concat buffer
         CL = self.cat_ld
-        with on(0):
-            self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], CL, p["cur0"], 1.0, 0, 0, B, *dims[0], 0, 0, R, O16, 0)
-        with on(1):
-            self._k("fcvsr_level_mix", p["xs1"], 64, p["o2"], 64, p["cur1"], 1.0, 0, 0, B, *dims[1], 0, 0, R, O16, 0)
-        with on(2):
-            self._k("fcvsr_level_mix", p["xs2"], 64, p["o3"], 64, p["cur2"], 1.0, 0, 0, B, *dims[2], 0, 0, R, O16, 0)
-        if ms:
-            for s_ in streams[1:]:
-                main.wait_stream(s_)
-        self.st = main.cuda_stream
-        self.max_ctas = 0
+        self._k("fcvsr_level_mix", p["xs0"], 64, p["fuse"], CL, p["cur0"], 1.0, 0, 0, B, *dims[0], 0, 0, R, O16, 0)
+        self._k("fcvsr_level_mix_multi", 2, vp(p["xs1"], p["xs2"]), 64, vp(p["o2"], p["o3"]), 64, vp(p["cur1"], p["cur2"]),
+                (ctypes.c_float * 2)(1.0, 1.0), vp(0, 0), vp(0, 0), B, ia(*[d[0] for d in dims[1:]]), ia(*[d[1] for d in dims[1:]]),
+                vp(0, 0), 0, R, O16, 0)
 
     # pyramid fuse + up-sampler (:2739-2751)
     def _tail(self, x, out, ws, p, B, H, W):

@@ -65,6 +65,15 @@ int fcvsr_conv2d_tc(const float* x, int ldx, const float* w, const float* bias, 
                     int ksize, int act, float slope, const float* slope_ptr, int pixel_shuffle,
                     float* y2, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t stream);
 
+/* The same convolution (weights, bias, activation) on up to three NHWC tensors of different spatial size in ONE launch: the
+ * pyramid levels of SCNetbk (CVSR_freq.py:766-770, BlockRCB applies one body to every level).  The persistent CTAs walk one tile
+ * list that spans the levels.  x / res / y / y2: HOST arrays of nprob device pointers (res, y2 may be NULL or hold NULL
+ * entries); H, W: HOST arrays of nprob ints; everything else as fcvsr_conv2d_tc (no pixel shuffle, no res2). */
+int fcvsr_conv2d_tc_multi(int nprob, const void* const* x, int ldx, const float* w, const float* bias, const float* const* res,
+                          int ldres, float* const* y, int ldy, const int* H, const int* W, int B, int Cin, int Cout, int ksize,
+                          int act, float slope, const float* slope_ptr, float* const* y2, int ldy2, int round_out, int op16,
+                          cudaStream_t stream);
+
 /* ---- FFT (torch.fft.rfft2 / irfft2 / fftn / ifftn of CVSR_freq.py:1452-1454, :1499-1504, :2082-2088) */
 
 /* tw: float2[N] = exp(-2 pi i k / N) for the transform length N (W for *_w, H for *_h). */
@@ -142,6 +151,18 @@ int fcvsr_rcb_finish(const void* res, const float* add, const void* r0, float* r
 int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const void* r, float coef, const void* td,
                     const void* tu, int B, int H, int W, void* xout_r, int ldr, int round_main, int op16,
                     int td_pooled, cudaStream_t stream);
+
+/* The three SCNet helpers over up to three pyramid levels in one launch (same weights / flags for every level; pointer
+ * arguments are HOST arrays of nlev device pointers, H / W / P / coef HOST arrays).  partial: sum over levels of
+ * B*ceil(P_l/128)*66 floats; add: [nlev][B][64].  NULL entries in r / r_op / r_pool / td / tu / xout_r skip that output or term. */
+int fcvsr_context_block_multi(int nlev, const void* const* x, int ldx, const float* wmask, const float* w1, const float* w2,
+                              float* partial, float* add, int B, const int* P, int x_bf16, cudaStream_t stream);
+int fcvsr_rcb_finish_multi(int nlev, const void* const* res, const float* const* add, const void* const* r0, float* const* r,
+                           void* const* r_op, void* const* r_pool, const int* H, const int* W, int B, int op16, int pool_plain,
+                           int res_bf16, cudaStream_t stream);
+int fcvsr_level_mix_multi(int nlev, const float* const* xin, int ldx, float* const* xout, int ldo, const void* const* r,
+                          const float* coef, const void* const* td, const void* const* tu, int B, const int* H, const int* W,
+                          void* const* xout_r, int ldr, int round_main, int op16, int td_pooled, cudaStream_t stream);
 
 /* ---- tail (CVSR_freq.py:2739-2751) -------------------------------------------------------------- */
 int fcvsr_pixel_shuffle(const void* in, int ldi, void* out, int ldo, int B, int H, int W, int Co, int half,
