@@ -118,7 +118,6 @@ class Engine:
         self.t16 = True              # cross-level terms td / tu as bf16 tensors
         self.use_last_kernel = True  # dedicated Cout = 1 kernel
         self.mgaa_ctas = 74          # SM cap of each of the two concurrently running MGAA calls
-        self.level_caps = None       # SM split of the three SCNet pyramid streams (None: by tile count)
         self.stop_after = None       # tools/gpu_phase_times.py: return after "mgaa_pair" | "mgaa" | "mffr" | "scnet"
         self.profile_flavor = False  # tools: per-launch profile entries also name the output flavour
         self.clone_output = True     # graph mode: return a copy of the static output buffer (False: the buffer itself,

@@ -220,8 +220,10 @@ def test_drop_in_api_errors(dev):
             m(torch.zeros(1, 7, 1, 30, 32, device=dev))              # H % 4 != 0
         with pytest.raises(RuntimeError):
             m(torch.zeros(1, 7, 1, 32, 32))                          # CPU tensor: no fallback
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 7, 1, 32, 32, device=dev))                  # autograd not supported this round
+    y = m(torch.zeros(1, 7, 1, 32, 32, device=dev))                  # autograd recording: the differentiable forward runs
+    assert y.requires_grad and y.shape == (1, 1, 128, 128)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 7, 1, 30, 32, device=dev))                  # same shape contract under autograd
 
 
 def test_weights_repack_after_load(dev):
