@@ -43,6 +43,7 @@ SIGNATURES = {
     "fcvsr_bilinear_up4": "p l p iii s",
     "fcvsr_fill_channels": "p iii f l s",
     "fcvsr_quantize_u8": "pp iiiii s",
+    "fcvsr_rgb_tail": "pi p l p iiii s",
     "fcvsr_pack_clip": "p p iiii i s",
     "fcvsr_subsample2": "pi pi pi iiii i s",
     "fcvsr_conv3x3_c64_to1": "pi p f p p iii s",
@@ -54,7 +55,10 @@ SIGNATURES = {
     "fcvsr_sac": "pi pi pi iiii s",
     "fcvsr_sac_backward": "pi pi pi p pi pi iiii s",
     "fcvsr_corr_gather_backward": "piii pi pi iiii s",
+    "fcvsr_psnr_ssim_u8": "pp iiii pp s",
     "fcvsr_charbonnier_loss": "pp li i f pp s",
+    "fcvsr_pixel_loss": "pp l i f d pp s",
+    "fcvsr_pixel_loss_backward": "pp l i f d p pp s",
     "fcvsr_adam_step": "pppp p i dddd d i s",
     "fcvsr_charbonnier_loss_backward": "pp li i f pp pp s",
     "fcvsr_modulated_deform_conv_forward": "ppppp p iiii i ii ii ii ii ii ll i s",

@@ -136,7 +136,8 @@ class _MFFR(_Holder):                 # MultiFreq_Refinment :2183-2199
 
 
 class _FCVSRBase(nn.Module):
-    _SMALL = False
+    _SMALL = False      # 1x1 up-convolutions (GShiftNet_S only)
+    _CH = 1             # image channels: 1 (Y, CVSR_train) or 3 (RGB, the mmedit backbones)
 
     def __init__(self, n_features, wiF, AC_Ks, ACNum, Freq_Inv, SCGroupN):
         super().__init__()
@@ -148,7 +149,8 @@ class _FCVSRBase(nn.Module):
         self.n_feats, self.wiF, self.AC_Ks = n, wiF, AC_Ks
         self.ACNum, self.Freq_Inv, self.SCGroupN = ACNum, Freq_Inv, SCGroupN
         ku = 1 if self._SMALL else 3          # GShiftNet_S uses 1x1 up-convs (:2600-2605)
-        self.feat_extract = nn.Sequential(_conv(7, 7 * n, 3))
+        self.in_ch = self._CH
+        self.feat_extract = nn.Sequential(_conv(7 * self._CH, 7 * n, 3))
         self.lrelu = nn.PReLU()
         self.MGAA = _MGAA(n, ACNum)
         self.rconcat1 = _conv(n, n, 3, stride=2)
@@ -161,7 +163,7 @@ class _FCVSRBase(nn.Module):
         self.upconv1 = _conv(n, 4 * n, ku)
         self.upconv2 = _conv(n, 4 * n, ku)
         self.pixel_shuffle = nn.PixelShuffle(2)
-        self.conv_last0 = _conv(n, 1, 3)
+        self.conv_last0 = _conv(n, self._CH, 3)
         self.MFFRblock = _MFFR(n, Freq_Inv)
         self.upconv_fuse = _conv(n + n // 4 + n // 16, n, 3)
         self._engine = None
@@ -184,8 +186,8 @@ class _FCVSRBase(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("fcvsr_b200 runs only on CUDA (sm_100a); there is no CPU fallback")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            if x.shape[1] != 7 or x.shape[2] != 1 or x.shape[3] % 4 or x.shape[4] % 4:
-                raise ValueError("GShiftNet expects [B, 7, 1, H, W] with H and W multiples of 4")
+            if x.shape[1] != 7 or x.shape[2] != self.in_ch or x.shape[3] % 4 or x.shape[4] % 4:
+                raise ValueError(f"expected [B, 7, {self.in_ch}, H, W] with H and W multiples of 4")
             if x.dtype != torch.float32:
                 raise TypeError("fcvsr_b200 expects float32 input")
             from . import _capi
@@ -211,6 +213,47 @@ class GShiftNet_S(_FCVSRBase):
 
     def __init__(self, n_features=64, wiF=1.5, AC_Ks=3, ACNum=3, Freq_Inv=4, SCGroupN=4):
         super().__init__(n_features, wiF, AC_Ks, ACNum, Freq_Inv, SCGroupN)
+
+
+class FCVSRNet(_FCVSRBase):
+    """mmedit backbone `FCVSRNet` (mmedit_train/mmedit/models/backbones/sr_backbones/fcvsr.py:38-142): GShiftNet with RGB
+    input / output -- feat_extract 21 -> 448, conv_last0 64 -> 3, forward(x[B,7,3,H,W]) -> [B,3,4H,4W].  The mmcv registry
+    decorator of the reference needs mmcv; `register_mmedit_backbones()` below does the registration when mmedit is importable."""
+    _CH = 3
+
+    def __init__(self, n_features=64, wiF=1.5, AC_Ks=3, ACNum=6, Freq_Inv=8, SCGroupN=10):
+        super().__init__(n_features, wiF, AC_Ks, ACNum, Freq_Inv, SCGroupN)
+
+    def init_weights(self, pretrained=None, strict=True):
+        """fcvsr.py:138-153: load a checkpoint when `pretrained` is a path, keep the constructor's init when it is None."""
+        if isinstance(pretrained, str):
+            ckpt = torch.load(pretrained, map_location="cpu", weights_only=True)
+            sd = ckpt.get("state_dict", ckpt)
+            sd = {(k[len("generator."):] if k.startswith("generator.") else k): v for k, v in sd.items()}
+            self.load_state_dict(sd, strict=strict)
+        elif pretrained is not None:
+            raise TypeError(f'"pretrained" must be a str or None. But received {type(pretrained)}.')
+
+
+class FCVSR_SNet(FCVSRNet):
+    """mmedit backbone `FCVSR_SNet` (sr_backbones/fcvsr_s.py:40-): the FCVSR-S hyper-parameters with RGB I/O; unlike GShiftNet_S
+    its up-convolutions are 3x3 (:65-70)."""
+
+    def __init__(self, n_features=64, wiF=1.5, AC_Ks=3, ACNum=3, Freq_Inv=4, SCGroupN=4):
+        super().__init__(n_features, wiF, AC_Ks, ACNum, Freq_Inv, SCGroupN)
+
+
+def register_mmedit_backbones() -> bool:
+    """Register FCVSRNet / FCVSR_SNet in mmedit's BACKBONES registry (what `@BACKBONES.register_module()` does at
+    sr_backbones/fcvsr.py:37) so that `configs/restorers/fcvsr/*.py` build this implementation.  Returns False when mmedit /
+    mmcv are not installed (they are not in the build image)."""
+    try:
+        from mmedit.models.registry import BACKBONES
+    except Exception:
+        return False
+    for cls in (FCVSRNet, FCVSR_SNet):
+        BACKBONES.register_module(module=cls, force=True)
+    return True
 
 
 class GShiftNet_ETC(GShiftNet):
@@ -244,7 +287,7 @@ def seeded_state_dict(variant: str = "S", seed: int = 0, **kw):
     (SURVEY 8d): construct on CPU under torch.manual_seed(seed); every parameter whose init is
     all-zero or all-one (DivEnh.a/.b, biases zeroed by the scaled kaiming init) gets N(0, 0.1^2)
     noise from Generator(seed+1) so that no branch of the forward is dead."""
-    cls = {"S": GShiftNet_S, "full": GShiftNet}[variant]
+    cls = {"S": GShiftNet_S, "full": GShiftNet, "rgb": FCVSRNet, "rgb_S": FCVSR_SNet}[variant]
     rng_state = torch.random.get_rng_state()
     torch.manual_seed(seed)
     m = cls(**kw)

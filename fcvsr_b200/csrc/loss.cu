@@ -125,3 +125,77 @@ extern "C" int fcvsr_charbonnier_loss_backward(const float* x, const float* y, l
                                                                scratch, grad_x, grad_y);
     return fcvsr_launch_status();
 }
+
+// ---- mmedit pixel losses (mmedit_train/mmedit/models/losses/pixelwise_loss.py: l1_loss :13-24, mse_loss :27-38,
+// charbonnier_loss :41-51 with eps = 1e-12; reduction 'mean' | 'sum' and loss_weight folded into `scale`): the REDS
+// configuration of FCVSR trains with MSELoss(mean) (configs/restorers/fcvsr/fcvsr_redsLD_QP22.py:7).
+//   kind 0: sqrt(d^2 + eps)    kind 1: d^2    kind 2: |d|          out = scale * sum
+template <int KIND>
+__device__ __forceinline__ float pl_value(float d, float eps) {
+    return KIND == 0 ? sqrtf(d * d + eps) : (KIND == 1 ? d * d : fabsf(d));
+}
+template <int KIND>
+__device__ __forceinline__ float pl_deriv(float d, float eps) {
+    return KIND == 0 ? d / sqrtf(d * d + eps) : (KIND == 1 ? 2.f * d : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)));
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(CH_THREADS) pixel_loss_partial_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                      size_t n, float eps, double* __restrict__ partial) {
+    __shared__ double red[CH_THREADS / 32];
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * CH_THREADS + threadIdx.x; i < n; i += (size_t)CH_BLOCKS * CH_THREADS)
+        acc += (double)pl_value<KIND>(x[i] - y[i], eps);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < CH_THREADS / 32; ++w) s += red[w];
+        partial[blockIdx.x] = s;
+    }
+}
+__global__ void pixel_loss_final_kernel(const double* __restrict__ partial, double scale, float* __restrict__ out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < CH_BLOCKS; i += 32) s += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = (float)(s * scale);
+}
+template <int KIND>
+__global__ void __launch_bounds__(CH_THREADS) pixel_loss_backward_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                                       size_t n, float eps, float scale,
+                                                                       const float* __restrict__ grad_out, float* __restrict__ gx,
+                                                                       float* __restrict__ gy) {
+    const float g = grad_out[0] * scale;
+    for (size_t i = (size_t)blockIdx.x * CH_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * CH_THREADS) {
+        const float v = g * pl_deriv<KIND>(x[i] - y[i], eps);
+        if (gx) gx[i] = v;
+        if (gy) gy[i] = -v;
+    }
+}
+
+// scratch: CH_BLOCKS (592) doubles; out: one float on the device = scale * sum_i f(x_i - y_i)
+extern "C" int fcvsr_pixel_loss(const float* x, const float* y, long long numel, int kind, float eps, double scale, double* scratch,
+                                float* out, cudaStream_t st) {
+    if (!x || !y || !scratch || !out || numel <= 0 || kind < 0 || kind > 2) return FCVSR_ERR_ARG;
+    if (kind == 0) pixel_loss_partial_kernel<0><<<CH_BLOCKS, CH_THREADS, 0, st>>>(x, y, (size_t)numel, eps, scratch);
+    else if (kind == 1) pixel_loss_partial_kernel<1><<<CH_BLOCKS, CH_THREADS, 0, st>>>(x, y, (size_t)numel, eps, scratch);
+    else pixel_loss_partial_kernel<2><<<CH_BLOCKS, CH_THREADS, 0, st>>>(x, y, (size_t)numel, eps, scratch);
+    pixel_loss_final_kernel<<<1, 32, 0, st>>>(scratch, scale, out);
+    return fcvsr_launch_status();
+}
+
+extern "C" int fcvsr_pixel_loss_backward(const float* x, const float* y, long long numel, int kind, float eps, double scale,
+                                         const float* grad_out, float* grad_x, float* grad_y, cudaStream_t st) {
+    if (!x || !y || !grad_out || numel <= 0 || kind < 0 || kind > 2) return FCVSR_ERR_ARG;
+    if (!grad_x && !grad_y) return FCVSR_OK;
+    const long long want = (numel + CH_THREADS - 1) / CH_THREADS;
+    const int blocks = (int)(want < 8 * CH_BLOCKS ? want : 8 * CH_BLOCKS);
+    const size_t n = (size_t)numel;
+    if (kind == 0) pixel_loss_backward_kernel<0><<<blocks, CH_THREADS, 0, st>>>(x, y, n, eps, (float)scale, grad_out, grad_x, grad_y);
+    else if (kind == 1) pixel_loss_backward_kernel<1><<<blocks, CH_THREADS, 0, st>>>(x, y, n, eps, (float)scale, grad_out, grad_x, grad_y);
+    else pixel_loss_backward_kernel<2><<<blocks, CH_THREADS, 0, st>>>(x, y, n, eps, (float)scale, grad_out, grad_x, grad_y);
+    return fcvsr_launch_status();
+}

@@ -231,3 +231,33 @@ extern "C" int fcvsr_quantize_u8(const float* v, unsigned char* out, int B, int 
     quantize_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v, out, H, W, Ho, Wo, total);
     return fcvsr_launch_status();
 }
+
+// ---- multi-channel output of the mmedit variants (FCVSRNet / FCVSR_SNet, 21 -> 3 channels:
+// mmedit_train/mmedit/models/backbones/sr_backbones/fcvsr.py:133-136) ---------------------------------------------------------
+// out[b,c,y,x] (NCHW, the module's output layout) = t[b,y,x,c] (NHWC conv_last0 result, pixel stride ldt) +
+// bilinear_x4(center[b,c])[y,x] with align_corners=False, center = LR frame [B,C,H,W] with batch stride `bstride`.
+__global__ void rgb_tail_kernel(const float* __restrict__ t, int ldt, const float* __restrict__ center, size_t bstride,
+                                float* __restrict__ out, int C, int H, int W, size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int Wo = 4 * W, Ho = 4 * H;
+    const int x = (int)(idx % Wo), y = (int)((idx / Wo) % Ho);
+    const int c = (int)((idx / ((size_t)Wo * Ho)) % C);
+    const size_t b = idx / ((size_t)Wo * Ho * C);
+    const float sy = fmaxf(0.25f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.25f * (x + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    const float* p = center + b * bstride + (size_t)c * H * W;
+    const float base = (1.f - ly) * ((1.f - lx) * p[(size_t)y0 * W + x0] + lx * p[(size_t)y0 * W + x1]) +
+                       ly * ((1.f - lx) * p[(size_t)y1 * W + x0] + lx * p[(size_t)y1 * W + x1]);
+    out[idx] = t[((b * Ho + y) * Wo + x) * ldt + c] + base;
+}
+
+extern "C" int fcvsr_rgb_tail(const float* t, int ldt, const float* center, long long bstride, float* out, int B, int C, int H,
+                              int W, cudaStream_t st) {
+    if (!t || !center || !out || B <= 0 || C <= 0 || C > ldt || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
+    const size_t total = (size_t)B * C * 16 * H * W;
+    rgb_tail_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(t, ldt, center, (size_t)bstride, out, C, H, W, total);
+    return fcvsr_launch_status();
+}

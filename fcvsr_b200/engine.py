@@ -315,6 +315,8 @@ class Engine:
         buf("up1", B, 4 * P, 64, op=self.use_tc)
         buf("up2", B, 16 * P, 64, op=self.use_tc)
         buf("base", B, 16 * P)
+        if m.in_ch > 1:
+            buf("lastc", B, 16 * P, 4)
         ws["masks"] = bands.symmetric_half_masks(Q, H, W, device)
         ws["tw_w"] = bands.twiddles(W, device)
         ws["tw_h"] = bands.twiddles(H, device)
@@ -417,7 +419,7 @@ class Engine:
             self._ensure_packs(dev)
             ws = self._workspace(B, H, W, dev)
             sx = x.clone()
-            so = torch.empty(B, 1, 4 * H, 4 * W, device=dev, dtype=F32)
+            so = torch.empty(B, Cc, 4 * H, 4 * W, device=dev, dtype=F32)
             self.st = torch.cuda.current_stream().cuda_stream
             self._run(sx, so, ws, B, H, W)
             torch.cuda.synchronize()
@@ -461,8 +463,8 @@ class Engine:
     # -------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, T, Cc, H, W = x.shape
-        if T != 7 or Cc != 1:
-            raise ValueError("GShiftNet expects [B, 7, 1, H, W] (Y-channel clips of 7 frames)")
+        if T != 7 or Cc != self.model.in_ch:
+            raise ValueError(f"expected [B, 7, {self.model.in_ch}, H, W] (clips of 7 frames)")
         if H % 4 or W % 4:
             raise ValueError("H and W must be multiples of 4 (two stride-2 levels, reference :2671-2672)")
         if x.dtype != F32:
@@ -475,7 +477,7 @@ class Engine:
             ws = self._workspace(B, H, W, dev)
             if self.use_graph:
                 return self._forward_graph(x, ws, B, H, W)
-            out = torch.empty(B, 1, 4 * H, 4 * W, device=dev, dtype=F32)
+            out = torch.empty(B, Cc, 4 * H, 4 * W, device=dev, dtype=F32)
             self.st = torch.cuda.current_stream().cuda_stream
             self.launches = 0
             self.tc_launches = 0
@@ -487,7 +489,7 @@ class Engine:
         key = (B, H, W, str(x.device), self._pack_key)
         if key not in self._graphs:
             sx = x.clone()
-            so = torch.empty(B, 1, 4 * H, 4 * W, device=x.device, dtype=F32)
+            so = torch.empty(B, x.shape[2], 4 * H, 4 * W, device=x.device, dtype=F32)
             self.st = torch.cuda.current_stream().cuda_stream
             self.launches = self.tc_launches = 0
             self._run(sx, so, ws, B, H, W)            # eager warm-up: function attributes, error flag, ...
@@ -520,7 +522,7 @@ class Engine:
         f = p["feat"]
         # feat_extract (:2663): NCHW clip -> NHWC 448 channels
         if self.use_tc:
-            self._k("fcvsr_pack_clip", x.data_ptr(), p["clip"], B, 7, H, W, 0)
+            self._k("fcvsr_pack_clip", x.data_ptr(), p["clip"], B, 7 * self.model.in_ch, H, W, 0)
             self._conv(P["feat_tc"], p["clip"], 32, f, 448, B, H, W, op16=0)
         else:
             self._conv(P["feat"], x.data_ptr(), 0, f, 448, B, H, W, nchw=True)
@@ -768,6 +770,13 @@ class Engine:
         self._conv(P["rec0"], p["f1"], 64, p["f2"], 64, B, H, W, rnd=True)
         self._conv(P["up1"], p["f2"], 64, p["up1"], 64, B, H, W, act=PR, slope_ptr=sl, rnd=True)
         self._conv(P["up2"], p["up1"], 64, p["up2"], 64, B, 2 * H, 2 * W, act=PR, slope_ptr=sl, rnd=True)
+        Cc = self.model.in_ch
+        if Cc > 1:
+            # mmedit variants (3-channel output, sr_backbones/fcvsr.py:133-136): conv_last0 into an NHWC scratch (pixel stride 4),
+            # then one pass transposes to the module's NCHW output and adds the bilinear x4 of the centre frame
+            self._conv(P["last"], p["up2"], 64, p["lastc"], 4, B, 4 * H, 4 * W)
+            self._k("fcvsr_rgb_tail", p["lastc"], 4, x.data_ptr() + 3 * Cc * H * W * 4, 7 * Cc * H * W, out.data_ptr(), B, Cc, H, W)
+            return
         # bilinear x4 of the centre LR frame (:2750) rides in conv_last0's epilogue as the residual
         self._k("fcvsr_bilinear_up4", x.data_ptr() + 3 * H * W * 4, 7 * H * W, p["base"], B, H, W)
         if self.op16 and self.use_last_kernel:

@@ -180,6 +180,11 @@ int fcvsr_subsample2(const float* x, int ldx, float* y, int ldy, void* y2, int l
 /* NCHW clip [B,T,H,W] -> NHWC [B,H,W,32] (channels >= T zero, TF32-rounded): tensor-core operand of feat_extract */
 int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int W, int op16, cudaStream_t stream);
 int fcvsr_fill_channels(float* x, int ld, int c0, int nc, float v, long long npix, cudaStream_t stream);
+/* Output stage of the 3-channel mmedit variants (FCVSRNet / FCVSR_SNet, sr_backbones/fcvsr.py:133-136): out [B,C,4H,4W] NCHW =
+ * t [B,4H,4W,ldt] (NHWC conv_last0 result) + bilinear x4 (align_corners=False) of the centre LR frame center [B,C,H,W] with batch
+ * stride bstride (elements). */
+int fcvsr_rgb_tail(const float* t, int ldt, const float* center, long long bstride, float* out, int B, int C, int H, int W,
+                   cudaStream_t stream);
 /* 8-bit output of the evaluation driver (CVSR_train/test_LD_freqCVSR.py:85-93: crop the padded rows, clamp to [0,1], * 255,
  * numpy astype(uint8) = truncation): out [B,Ho,Wo] uint8 = trunc(clamp(v[b, y < Ho, x < Wo], 0, 1) * 255) of v [B,H,W] fp32. */
 int fcvsr_quantize_u8(const float* v, unsigned char* out, int B, int H, int W, int Ho, int Wo, cudaStream_t stream);
@@ -198,6 +203,16 @@ int fcvsr_charbonnier_loss(const float* x, const float* y, long long numel, int 
 int fcvsr_charbonnier_loss_backward(const float* x, const float* y, long long numel, int batch, int mean_res, float eps,
                                     const float* grad_out, const double* scratch, float* grad_x, float* grad_y,
                                     cudaStream_t stream);
+
+/* mmedit pixel losses (mmedit_train/mmedit/models/losses/pixelwise_loss.py:13-51,:54-190; the FCVSR REDS configuration uses
+ * MSELoss(mean), configs/restorers/fcvsr/fcvsr_redsLD_QP22.py:7): out[0] = scale * sum_i f(x_i - y_i) with f = sqrt(d^2 + eps)
+ * (kind 0, CharbonnierLoss, eps 1e-12), d^2 (kind 1, MSELoss) or |d| (kind 2, L1Loss); reduction 'mean' and loss_weight are the
+ * caller's `scale` (loss_weight / numel).  Deterministic; scratch: 592 doubles.  The backward reads the upstream gradient of the
+ * scalar from the device: grad_x = grad_out[0] * scale * f'(d), grad_y = -grad_x (either may be NULL). */
+int fcvsr_pixel_loss(const float* x, const float* y, long long numel, int kind, float eps, double scale, double* scratch, float* out,
+                     cudaStream_t stream);
+int fcvsr_pixel_loss_backward(const float* x, const float* y, long long numel, int kind, float eps, double scale,
+                              const float* grad_out, float* grad_x, float* grad_y, cudaStream_t stream);
 
 /* Adam step of the reference's training loop (train_LD_freqCVSR_22.py:204,251: torch.optim.Adam with L2 weight decay, no
  * amsgrad), multi-tensor: params / grads / exp_avg / exp_avg_sq are HOST arrays of `count` device pointers (fp32), numels
@@ -240,6 +255,13 @@ int fcvsr_sac_backward(const float* wp, int ldw, const float* taps, int ldk, con
 /* adjoint of fcvsr_corr_gather (fp32): dS [B,H*Wf,lddS] is written at the float ranges [a_off, a_off+C2) and [b_off, b_off+C2) */
 int fcvsr_corr_gather_backward(const float* S, int ldS, int a_off, int b_off, const float* dout, int ldo, float* dS, int lddS,
                                int B, int H, int Wf, int C2, cudaStream_t stream);
+
+/* ---- evaluation metrics next to the output (CVSR_train/metric/psnr_ssim.py:278-399, as called at :447-478) ------------------
+ * a, b: [B,H,W] uint8 single-channel frames; out [B][2] floats = (PSNR dB, SSIM) over the frame without its `crop` border
+ * pixels (SSIM: 11 x 11 Gaussian window, sigma 1.5, float64, valid region); scratch: B*ceil((H-2crop)/16)*ceil((W-2crop)/16)*2
+ * doubles.  Deterministic. */
+int fcvsr_psnr_ssim_u8(const unsigned char* a, const unsigned char* b, int B, int H, int W, int crop, double* scratch, float* out,
+                       cudaStream_t stream);
 
 /* ---- deformable convolution operator (CVSR_train/ops/dcn) --------------------------------------- */
 

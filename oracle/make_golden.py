@@ -42,10 +42,32 @@ def make_clip(seed: int, b: int, h: int, w: int) -> torch.Tensor:
     return torch.round(255.0 * x.clamp(0, 1)) / 255.0
 
 
+def make_clip_rgb(seed: int, b: int, h: int, w: int) -> torch.Tensor:
+    """[B,7,3,H,W]: three independently seeded planes of make_clip (the mmedit variants take RGB frames)."""
+    return torch.cat([make_clip(seed + 1000 * k, b, h, w) for k in range(3)], 2)
+
+
+def build_reference(ref, variant: str):
+    """The reference module for a variant.  "rgb" / "rgb_S" are the mmedit backbones FCVSRNet / FCVSR_SNet
+    (mmedit_train/mmedit/models/backbones/sr_backbones/fcvsr.py:38-142, fcvsr_s.py:40-): that file needs mmcv (absent here), and it
+    is GShiftNet's code with feat_extract 21 -> 448 and conv_last0 64 -> 3, so the UNMODIFIED GShiftNet.forward
+    (CVSR_freq.py:2688-2756, channel-count agnostic) is run with those two layers re-shaped."""
+    if variant == "S":
+        return ref.GShiftNet_S()
+    if variant == "full":
+        return ref.GShiftNet()
+    m = ref.GShiftNet() if variant == "rgb" else ref.GShiftNet(ACNum=3, Freq_Inv=4, SCGroupN=4)
+    m.feat_extract = torch.nn.Sequential(torch.nn.Conv2d(21, 7 * 64, 3, 1, 1))
+    m.conv_last0 = torch.nn.Conv2d(64, 3, 3, 1, 1)
+    return m
+
+
 CASES = [
     dict(name="fcvsr_s_64", variant="S", seed=0, clip_seed=1234, b=1, h=64, w=64),
     dict(name="fcvsr_full_64", variant="full", seed=0, clip_seed=1234, b=1, h=64, w=64),
     dict(name="fcvsr_s_36x40", variant="S", seed=3, clip_seed=77, b=2, h=36, w=40),
+    dict(name="fcvsrnet_s_32x40", variant="rgb_S", seed=5, clip_seed=21, b=2, h=32, w=40),
+    dict(name="fcvsrnet_32", variant="rgb", seed=6, clip_seed=22, b=1, h=32, w=32),
 ]
 
 
@@ -59,7 +81,7 @@ def main() -> None:
     shapes = {}
     for case in CASES:
         sd = seeded_state_dict(case["variant"], case["seed"])
-        model = (ref.GShiftNet_S if case["variant"] == "S" else ref.GShiftNet)().eval()
+        model = build_reference(ref, case["variant"]).eval()
         missing = model.load_state_dict(sd, strict=True)
         assert not missing.missing_keys and not missing.unexpected_keys
         shapes[case["variant"]] = [[k, list(v.shape)] for k, v in model.state_dict().items()]
@@ -75,7 +97,8 @@ def main() -> None:
               model.recorb1.register_forward_hook(
                   lambda _m, _i, o: taps.update(sc_l1=sample(o[0]), sc_l3=o[2].clone())),
               model.recorb0.register_forward_hook(lambda _m, _i, o: taps.__setitem__("fuse", sample(o)))]
-        x = make_clip(case["clip_seed"], case["b"], case["h"], case["w"])
+        mk = make_clip_rgb if case["variant"].startswith("rgb") else make_clip
+        x = mk(case["clip_seed"], case["b"], case["h"], case["w"])
         with torch.no_grad():
             y = model(x)
         for hnd in hs:

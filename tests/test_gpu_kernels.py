@@ -268,3 +268,25 @@ def test_quantize_u8_matches_numpy_truncation(dev):
     want = torch.from_numpy((torch.clamp(y[..., :36, :50], 0, 1).numpy() * 255.0).astype("uint8"))
     got = quantize_u8(y.to(dev), 36, 50).cpu()
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("B,H,W,crop", [(2, 60, 70, 4), (1, 144, 160, 4), (3, 19, 23, 4), (1, 32, 40, 0)])
+def test_psnr_ssim_kernel_matches_oracle(dev, B, H, W, crop):
+    """fcvsr_psnr_ssim_u8 (Y-PSNR / SSIM with a cropped border, metric/psnr_ssim.py:278-399) against the numpy restatement that
+    tests/test_oracle.py pins to the live reference; ragged 16-pixel tiles, one identical pair (PSNR = inf, SSIM = 1)."""
+    import numpy as np
+    from fcvsr_b200.metrics import psnr_ssim_u8
+    from oracle import metrics_oracle as M
+    g = torch.Generator().manual_seed(H + W)
+    a = torch.randint(0, 256, (B, 1, H, W), generator=g, dtype=torch.uint8)
+    b = (a.int() + torch.randint(-25, 26, a.shape, generator=g)).clamp(0, 255).to(torch.uint8)
+    b[0] = a[0] if B > 1 else b[0]
+    p, s = psnr_ssim_u8(a.to(dev), b.to(dev), crop)
+    assert p.shape == (B, 1) and s.shape == (B, 1)
+    for i in range(B):
+        af, bf = a[i, 0].numpy().astype(np.float64), b[i, 0].numpy().astype(np.float64)
+        pr, sr = M.calculate_psnr(af, bf, crop), M.calculate_ssim(af, bf, crop)
+        if pr == float("inf"):
+            assert float(p[i, 0]) == float("inf") and abs(float(s[i, 0]) - 1.0) <= 1e-6
+        else:
+            assert abs(float(p[i, 0]) - pr) <= 1e-4 and abs(float(s[i, 0]) - sr) <= 1e-6

@@ -198,6 +198,31 @@ def test_tf32_path_matches_reference_golden(dev, name):
     assert abs(psnr(y, tgt) - psnr(ref, tgt)) <= 0.01
 
 
+@pytest.mark.parametrize("name", ["fcvsrnet_s_32x40", "fcvsrnet_32"])
+def test_mmedit_rgb_variants_match_reference_golden(dev, name):
+    """FCVSRNet / FCVSR_SNet (mmedit backbones, [B,7,3,H,W] -> [B,3,4H,4W]) in the three compute modes against the reference
+    golden, and the differentiable forward in fp32 mode."""
+    from tests.util import make_clip_rgb
+    g = load_golden(name)
+    c = g["case"]
+    sd = arch.seeded_state_dict(c["variant"], c["seed"])
+    x = make_clip_rgb(c["clip_seed"], c["b"], c["h"], c["w"]).to(dev)
+    m = (arch.FCVSRNet if c["variant"] == "rgb" else arch.FCVSR_SNet)().to(dev).eval()
+    m.load_state_dict(sd)
+    for mode, tol in (("fp32", 2e-5), ("tf32", 1e-3), ("bf16", 5e-3)):
+        m.compute_dtype = mode
+        with torch.no_grad():
+            y = m(x).cpu()
+        assert y.shape == g["out"].shape
+        err = float((y - g["out"]).abs().max())
+        assert err <= tol, (mode, err)
+        if mode == "bf16":
+            assert psnr(y, g["out"]) >= 60.0
+    m.compute_dtype = "fp32"
+    yt = m(x)                                             # autograd recording: fcvsr_b200.train_forward
+    assert yt.requires_grad and float((yt.detach().cpu() - g["out"]).abs().max()) <= 2e-5
+
+
 def test_forward_against_oracle_unseen_shape(dev):
     """A shape with no golden file (ragged tiles: 44 x 52, batch 2) against the live oracle."""
     sd = arch.seeded_state_dict("S", 5)

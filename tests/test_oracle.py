@@ -6,10 +6,10 @@ import os
 import pytest
 import torch
 
-from fcvsr_b200.arch import GShiftNet, GShiftNet_S, seeded_state_dict
+from fcvsr_b200.arch import FCVSR_SNet, FCVSRNet, GShiftNet, GShiftNet_S, seeded_state_dict
 from oracle import fcvsr_oracle as O
 from oracle import ref_loader
-from tests.util import GOLD, load_golden, make_clip
+from tests.util import GOLD, load_golden, make_clip, make_clip_rgb
 
 
 @pytest.mark.parametrize("name", ["fcvsr_s_64", "fcvsr_s_36x40"])
@@ -36,12 +36,28 @@ def test_oracle_matches_reference_golden_full():
     assert (y - g["out"]).abs().max().item() <= 2e-5
 
 
+@pytest.mark.parametrize("name", ["fcvsrnet_s_32x40", "fcvsrnet_32"])
+def test_oracle_matches_reference_golden_rgb(name):
+    """The mmedit backbones FCVSRNet / FCVSR_SNet (RGB, 21 -> 3 channels): goldens made by the unmodified GShiftNet.forward with
+    the two re-shaped layers (oracle/make_golden.py:build_reference; the mmedit file itself needs mmcv)."""
+    g = load_golden(name)
+    c = g["case"]
+    sd = seeded_state_dict(c["variant"], c["seed"])
+    x = make_clip_rgb(c["clip_seed"], c["b"], c["h"], c["w"])
+    with torch.no_grad():
+        y, taps = O.forward(sd, x, return_taps=True)
+    assert y.shape == g["out"].shape and y.shape[1] == 3
+    assert (y - g["out"]).abs().max().item() <= 2e-5
+    for k in ("mgaa1", "mgaa2", "mffr", "sc_l1", "fuse"):
+        assert (taps[k][..., ::4, ::4] - g[k]).abs().max().item() <= 5e-5, k
+
+
 def test_state_dict_matches_reference_keys_and_shapes():
     """Drop-in contract: same keys, order and shapes as the reference state_dict, including
     the aliased RCB / body.3 entries."""
     with open(os.path.join(GOLD, "state_dict_shapes.json")) as f:
         ref = json.load(f)
-    for variant, cls in (("S", GShiftNet_S), ("full", GShiftNet)):
+    for variant, cls in (("S", GShiftNet_S), ("full", GShiftNet), ("rgb", FCVSRNet), ("rgb_S", FCVSR_SNet)):
         sd = cls().state_dict()
         mine = [[k, list(v.shape)] for k, v in sd.items()]
         assert mine == ref[variant]
@@ -159,3 +175,27 @@ def test_oracle_autograd_matches_reference_gradients(name):
     a = f1.shape[0] // 384
     dead = torch.cat([f1[i * 384 + 192:(i + 1) * 384] for i in range(a)])
     assert float(dead.abs().max()) == 0.0
+
+
+def test_metrics_oracle_matches_live_reference():
+    """oracle/metrics_oracle.py against the reference's calculate_psnr / calculate_ssim (metric/psnr_ssim.py:278-399) called as
+    the evaluation driver calls them (:470-471).  Needs the reference tree and cv2: skipped on the GPU box."""
+    import importlib.util
+    import numpy as np
+    from oracle import metrics_oracle as M
+    path = "/root/reference/CVSR_train/metric/psnr_ssim.py"
+    if not os.path.isfile(path):
+        pytest.skip("reference tree not present")
+    pytest.importorskip("cv2")
+    spec = importlib.util.spec_from_file_location("ref_psnr_ssim", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(3)
+    for (h, w, noise) in ((60, 70, 20), (48, 33, 3), (40, 40, 0)):
+        a = rng.integers(0, 256, (h, w, 1)).astype(np.uint8)
+        b = np.clip(a.astype(int) + (rng.integers(-noise, noise + 1, a.shape) if noise else 0), 0, 255).astype(np.uint8)
+        af, bf = a.astype(np.float64), b.astype(np.float64)
+        p_ref, s_ref = ref.calculate_psnr(af, bf, 4, test_y_channel=True), ref.calculate_ssim(af, bf, 4, test_y_channel=True)
+        p, s = M.calculate_psnr(af[..., 0], bf[..., 0], 4), M.calculate_ssim(af[..., 0], bf[..., 0], 4)
+        assert (p == p_ref) or abs(p - p_ref) <= 1e-5 * abs(p_ref)
+        assert abs(s - s_ref) <= 1e-12

@@ -3,7 +3,7 @@ import os
 
 import torch
 
-from oracle.make_golden import make_clip  # noqa: F401  (same seeded clips as the golden generator)
+from oracle.make_golden import make_clip, make_clip_rgb  # noqa: F401  (same seeded clips as the golden generator)
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
