@@ -63,7 +63,8 @@ SIGNATURES = {
     "fcvsr_charbonnier_loss_backward": "pp li i f pp pp s",
     "fcvsr_modulated_deform_conv_forward": "ppppp p iiii i ii ii ii ii ii ll i s",
     "fcvsr_modulated_deform_conv_backward": "ppppp ppppp iiii i ii ii ii ii ii p s",
-    "fcvsr_modulated_deform_conv_forward_tc": "ppppp p iiii i ii ii ii ii ii ll i p s",
+    "fcvsr_modulated_deform_conv_forward_tc": "ppppp p iiii i ii ii ii ii ii ll i p i s",
+    "fcvsr_nchw_to_nhwc": "pp iiii i s",
 }
 
 _lib = None

@@ -37,6 +37,8 @@ struct DcnTcArgs {
     const float* xt; const float* w; const float* bias; const float* offset; const float* mask; float* y;
     int B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg, Ho, Wo;
     long long off_bs, mask_bs;
+    int off_cs, off_ps;            // offset / mask addressing: element (channel c, output pixel p) at c * off_cs + p * off_ps
+                                   // (NCHW planes: cs = Ho*Wo, ps = 1; NHWC rows of a conv_offset_mask output: cs = 1, ps = ld)
     int mask_sigmoid;
     int tiles_x, tiles_per_img, tiles, nstage, stage_bytes;
     int* err;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tc_kernel(const DcnTcArgs a
         const int t = threadIdx.x;
         const int gc = t & 7, mrow = t >> 3;
         const int ch_per_dg = a.Cin / a.dg;
-        const int kkP = kk2 * P;
+        const int och = a.off_cs, opx = a.off_ps;
         int wbase[4];                                     // ((n * Cin + j) * kk2) of this thread's first four weight elements
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -111,9 +113,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tc_kernel(const DcnTcArgs a
                 const int g = (gc * 4) / ch_per_dg;
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    oh[r] = __ldg(offb + g * 2 * kkP + pi[r]);
-                    ow[r] = __ldg(offb + g * 2 * kkP + P + pi[r]);
-                    mk[r] = a.mask ? __ldg(mskb + g * kkP + pi[r]) : 1.f;
+                    oh[r] = __ldg(offb + g * 2 * kk2 * och + pi[r] * opx);
+                    ow[r] = __ldg(offb + (g * 2 * kk2 + 1) * och + pi[r] * opx);
+                    mk[r] = a.mask ? __ldg(mskb + g * kk2 * och + pi[r] * opx) : 1.f;
                 }
             }
             int ki = 0, kj = 0;
@@ -161,12 +163,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tc_kernel(const DcnTcArgs a
                         if (ncc == kcc) { ncc = 0; ++ntap; }
                         if (ntap < kk2) {
                             const int g = (ncc * 32 + gc * 4) / ch_per_dg;
-                            const int o = (g * 2 * kk2 + 2 * ntap) * P;
+                            const int o = (g * 2 * kk2 + 2 * ntap) * och;
 #pragma unroll
                             for (int r = 0; r < 2; ++r) {
-                                oh[r] = __ldg(offb + o + pi[r]);
-                                ow[r] = __ldg(offb + o + P + pi[r]);
-                                mk[r] = a.mask ? __ldg(mskb + (g * kk2 + ntap) * P + pi[r]) : 1.f;
+                                oh[r] = __ldg(offb + o + pi[r] * opx);
+                                ow[r] = __ldg(offb + o + och + pi[r] * opx);
+                                mk[r] = a.mask ? __ldg(mskb + (g * kk2 + ntap) * och + pi[r] * opx) : 1.f;
                             }
                         }
                     }
@@ -274,8 +276,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dcn_tc_kernel(const DcnTcArgs a
     }
 }
 
-// NCHW [B][C][P] -> NHWC [B][P][C] through a 32x33 shared tile (coalesced on both sides)
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int P) {
+// NCHW [B][C][P] -> NHWC [B][P][C] through a 32x33 shared tile (coalesced on both sides); rnd: store TF32-rounded values
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int P, int rnd) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const float* xb = x + (size_t)b * C * P;
@@ -287,8 +289,16 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int p = p0 + i, c = c0 + threadIdx.x;
-        if (p < P && c < C) yb[(size_t)p * C + c] = tile[threadIdx.x][i];
+        if (p < P && c < C) yb[(size_t)p * C + c] = rnd ? round_tf32(tile[threadIdx.x][i]) : tile[threadIdx.x][i];
     }
+}
+
+// NCHW fp32 [B,C,H,W] -> NHWC fp32 [B,H,W,C] (optionally TF32-rounded: the operand layout of the tcgen05 kernels).  The DCN
+// modules keep the reference's NCHW tensor contract (ops/dcn/deform_conv.py), the kernels gather from pixel-major copies.
+extern "C" int fcvsr_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, int round_tf32, cudaStream_t st) {
+    if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
+    nchw_to_nhwc_kernel<<<dim3((H * W + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, st>>>(x, y, C, H * W, round_tf32);
+    return fcvsr_launch_status();
 }
 
 // Returns FCVSR_ERR_UNSUPPORTED for shapes outside the tensor-core kernel's class (the caller then uses dcn.cu).
@@ -298,7 +308,7 @@ extern "C" int fcvsr_modulated_deform_conv_forward_tc(const float* input, const 
                                                       int pad_h, int pad_w, int dil_h, int dil_w, int groups,
                                                       int deformable_groups, long long offset_batch_stride,
                                                       long long mask_batch_stride, int mask_sigmoid, float* scratch_nhwc,
-                                                      cudaStream_t st) {
+                                                      int offset_pixel_stride, cudaStream_t st) {
     if (!input || !weight || !offset || !output || !scratch_nhwc) return FCVSR_ERR_ARG;
     if (B <= 0 || groups <= 0 || deformable_groups <= 0 || Cin % groups || Cout % groups || Cin % deformable_groups)
         return FCVSR_ERR_ARG;
@@ -319,6 +329,14 @@ extern "C" int fcvsr_modulated_deform_conv_forward_tc(const float* input, const 
     a.off_bs = offset_batch_stride > 0 ? offset_batch_stride : (long long)deformable_groups * 2 * kh * kw * a.Ho * a.Wo;
     a.mask_bs = mask_batch_stride > 0 ? mask_batch_stride : (long long)deformable_groups * kh * kw * a.Ho * a.Wo;
     a.mask_sigmoid = mask_sigmoid;
+    if (offset_pixel_stride > 0) {          // NHWC offsets / mask: channel c of output pixel p at p * stride + c
+        if ((long long)a.Ho * a.Wo * offset_pixel_stride > 0x7fffffffLL) return FCVSR_ERR_UNSUPPORTED;
+        a.off_cs = 1; a.off_ps = offset_pixel_stride;
+        if (offset_batch_stride <= 0) a.off_bs = (long long)a.Ho * a.Wo * offset_pixel_stride;
+        if (mask_batch_stride <= 0) a.mask_bs = a.off_bs;
+    } else {
+        a.off_cs = a.Ho * a.Wo; a.off_ps = 1;
+    }
     a.tiles_x = (a.Wo + DT_TW - 1) / DT_TW;
     a.tiles_per_img = a.tiles_x * ((a.Ho + DT_TH - 1) / DT_TH);
     a.tiles = a.tiles_per_img * B;
@@ -340,7 +358,10 @@ extern "C" int fcvsr_modulated_deform_conv_forward_tc(const float* input, const 
     a.err = err;
     const size_t smem = 1024 + (size_t)a.nstage * a.stage_bytes + 512;
     const int grid = a.tiles < num_sms ? a.tiles : num_sms;
-    nchw_to_nhwc_kernel<<<dim3((H * W + 31) / 32, Cin / 32, B), dim3(32, 8), 0, st>>>(input, scratch_nhwc, Cin, H * W);
+    // input == scratch_nhwc: the caller already holds the pixel-major copy (ModulatedDeformConvPack shares it with its
+    // conv_offset_mask convolution) and the transposition pre-pass is skipped
+    if (input != scratch_nhwc)
+        nchw_to_nhwc_kernel<<<dim3((H * W + 31) / 32, Cin / 32, B), dim3(32, 8), 0, st>>>(input, scratch_nhwc, Cin, H * W, 0);
     dcn_tc_kernel<<<grid, DT_THREADS, smem, st>>>(a);
     return fcvsr_launch_status();
 }

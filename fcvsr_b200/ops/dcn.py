@@ -75,7 +75,7 @@ def _launch(x, offset, mask, weight, bias, stride, padding, dilation, groups, dg
     with torch.cuda.device(x.device):
         if PRECISION == "tf32" and groups == 1 and cin % 32 == 0 and (cin // dg) % 4 == 0 and cout % 16 == 0 and 16 <= cout <= 256:
             scratch = x.new_empty(x.numel())             # NHWC copy of the input made by the kernel
-            rc = C.try_call("fcvsr_modulated_deform_conv_forward_tc", *args[:-1], scratch.data_ptr(), st)
+            rc = C.try_call("fcvsr_modulated_deform_conv_forward_tc", *args[:-1], scratch.data_ptr(), 0, st)
             if rc == 0:
                 return y
             if rc != C.ERR_UNSUPPORTED:
@@ -319,6 +319,21 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
             o1, o2, mask = torch.chunk(out, 3, dim=1)
             return modulated_deform_conv(x, torch.cat((o1, o2), dim=1), torch.sigmoid(mask), self.weight, self.bias, self.stride,
                                          self.padding, self.dilation, self.groups, self.deformable_groups)
+        kh, kw = self.kernel_size
+        dg = self.deformable_groups
+        stride, padding, dilation = _pair(self.stride), _pair(self.padding), _pair(self.dilation)
+        b, cin, h, w = x.shape
+        c3 = dg * 3 * kh * kw
+        tc = (PRECISION == "tf32" and self.groups == 1 and kh == kw and kh in (1, 3) and stride == (1, 1) and dilation == (1, 1)
+              and padding == (kh // 2, kh // 2) and cin % 32 == 0 and (cin // dg) % 4 == 0 and self.out_channels % 16 == 0
+              and 16 <= self.out_channels <= 256 and c3 % 16 == 0)
+        if tc:
+            # tensor-core path: ONE pixel-major TF32-rounded copy of x feeds both the conv_offset_mask convolution (tcgen05
+            # implicit GEMM, NHWC output) and the fused gather + GEMM DCN kernel, which reads offsets and mask straight from
+            # that NHWC output (sigmoid applied on the fly)
+            y = self._forward_tc(x.contiguous(), b, cin, h, w, c3, kh, dg)
+            if y is not None:
+                return y
         out = _offset_conv(x, self.conv_offset_mask)
         b, c3, ho, wo = out.shape
         kk = self.kernel_size[0] * self.kernel_size[1]
@@ -332,4 +347,34 @@ class ModulatedDeformConvPack(ModulatedDeformConv):
                    self.in_channels, x.shape[2], x.shape[3], self.out_channels, self.kernel_size[0], self.kernel_size[1],
                    stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1], self.groups,
                    self.deformable_groups, c3 * ho * wo, c3 * ho * wo, 1, torch.cuda.current_stream().cuda_stream)
+        return y
+
+    def _forward_tc(self, x, b, cin, h, w, c3, k, dg):
+        st = torch.cuda.current_stream().cuda_stream
+        key = (self.conv_offset_mask.weight.data_ptr(), self.conv_offset_mask.weight._version)
+        if getattr(self, "_tc_pack_key", None) != key:          # [Cout][k*k*Cin] K-major, TF32-rounded (conv_tc.cu layout)
+            wt = self.conv_offset_mask.weight.detach().permute(0, 2, 3, 1).reshape(c3, k * k * cin).contiguous()
+            bits = wt.view(torch.int32)
+            self._tc_pack = ((bits + 0x1000) & -8192).view(torch.float32)
+            self._tc_pack_key = key
+        xt = x.new_empty(b, h, w, cin)
+        off = x.new_empty(b, h, w, c3)
+        y = x.new_empty(b, self.out_channels, h, w)
+        kk = k * k
+        with torch.cuda.device(x.device):
+            C.call("fcvsr_nchw_to_nhwc", x.data_ptr(), xt.data_ptr(), b, cin, h, w, 1, st)
+            rc = C.try_call("fcvsr_conv2d_tc", xt.data_ptr(), cin, self._tc_pack.data_ptr(), self.conv_offset_mask.bias.data_ptr(), 0, 0,
+                            0, 0, off.data_ptr(), c3, b, h, w, cin, c3, k, C.ACT_NONE, 0.0, 0, 0, 0, 0, 0, 0, 0, st)
+            if rc == C.ERR_UNSUPPORTED:
+                return None
+            if rc != 0:
+                raise RuntimeError(f"fcvsr_conv2d_tc failed with status {rc}")
+            rc = C.try_call("fcvsr_modulated_deform_conv_forward_tc", xt.data_ptr(), self.weight.data_ptr(),
+                            self.bias.data_ptr() if self.bias is not None else 0, off.data_ptr(),
+                            off.data_ptr() + dg * 2 * kk * 4, y.data_ptr(), b, cin, h, w, self.out_channels, k, k, 1, 1, k // 2,
+                            k // 2, 1, 1, 1, dg, 0, 0, 1, xt.data_ptr(), c3, st)
+            if rc == C.ERR_UNSUPPORTED:
+                return None
+            if rc != 0:
+                raise RuntimeError(f"fcvsr_modulated_deform_conv_forward_tc failed with status {rc}")
         return y

@@ -284,13 +284,19 @@ int fcvsr_modulated_deform_conv_forward(const float* input, const float* weight,
  * TF32-rounded operands, fp32 accumulate in TMEM, NCHW fp32 in and out.  groups == 1, Cin % 32 == 0, Cout % 16 == 0,
  * (Cin / deformable_groups) % 4 == 0, Cout <= 256; other shapes return FCVSR_ERR_UNSUPPORTED (use the exact-fp32 entry
  * above).  scratch_nhwc: caller-provided B*Cin*H*W floats (the kernel gathers from an NHWC copy of the input it makes
- * there).  Same reference call sites. */
+ * there; input == scratch_nhwc means the caller already made that copy with fcvsr_nchw_to_nhwc).  offset_pixel_stride > 0:
+ * offset and mask are channel slices of an NHWC tensor with that pixel stride (the tcgen05 conv_offset_mask output of
+ * ModulatedDeformConvPack, deform_conv.py:330-337) instead of NCHW planes.  Same reference call sites. */
 int fcvsr_modulated_deform_conv_forward_tc(const float* input, const float* weight, const float* bias,
                                         const float* offset, const float* mask, float* output, int B, int Cin,
                                         int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w,
                                         int pad_h, int pad_w, int dil_h, int dil_w, int groups,
                                         int deformable_groups, long long offset_batch_stride,
-                                        long long mask_batch_stride, int mask_sigmoid, float* scratch_nhwc, cudaStream_t stream);
+                                        long long mask_batch_stride, int mask_sigmoid, float* scratch_nhwc,
+                                        int offset_pixel_stride, cudaStream_t stream);
+/* NCHW fp32 [B,C,H,W] -> NHWC fp32 [B,H,W,C], optionally TF32-rounded (the operand layout of the tcgen05 kernels): the DCN
+ * modules keep the reference's NCHW tensor contract (ops/dcn/deform_conv.py), the kernels gather from pixel-major copies. */
+int fcvsr_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, int round_tf32, cudaStream_t stream);
 
 /* Backward of the operator above (csrc/dcn_bwd.cu), NCHW fp32: replaces modulated_deform_conv_cuda_backward
  * (ops/dcn/src/deform_conv_cuda.cpp:566-700; call site ops/dcn/deform_conv.py:161-166) and, with mask == NULL,

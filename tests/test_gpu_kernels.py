@@ -290,3 +290,33 @@ def test_psnr_ssim_kernel_matches_oracle(dev, B, H, W, crop):
             assert float(p[i, 0]) == float("inf") and abs(float(s[i, 0]) - 1.0) <= 1e-6
         else:
             assert abs(float(p[i, 0]) - pr) <= 1e-4 and abs(float(s[i, 0]) - sr) <= 1e-6
+
+
+@pytest.mark.parametrize("B,cin,cout,H,W,dg", [(1, 64, 64, 20, 24, 16), (2, 64, 48, 13, 17, 16)])
+def test_modulated_dcn_pack_tensor_core_path(dev, B, cin, cout, H, W, dg):
+    """ModulatedDeformConvPack inference on the tensor cores (the reference's canonical use of the operator, SURVEY 8 a10:
+    MVDeformableAlignment(64, 64, 3, padding=1, deformable_groups=16)): one pixel-major TF32 copy of x, conv_offset_mask on
+    tcgen05 with NHWC output, fused gather + GEMM DCN reading offsets / mask from that output (sigmoid on the fly).  Against the
+    oracle (F.conv2d + sigmoid + loop-level DCN) within the TF32 contract; the offsets depend on TF32-rounded convolution
+    outputs, so the bound is 5e-3 of the output scale."""
+    import fcvsr_b200.ops.dcn as dcn_mod
+    torch.manual_seed(B + dg)
+    m = dcn_mod.ModulatedDeformConvPack(cin, cout, 3, stride=1, padding=1, deformable_groups=dg).to(dev)
+    with torch.no_grad():
+        m.conv_offset_mask.weight.normal_(0, 0.02)
+        m.conv_offset_mask.bias.normal_(0, 0.5)
+        m.bias.normal_(0, 0.1)
+        x = torch.randn(B, cin, H, W, device=dev)
+        calls = []
+        orig = dcn_mod.C.try_call
+        dcn_mod.C.try_call = lambda name, *a: (calls.append(name), orig(name, *a))[1]
+        try:
+            y = m(x).cpu()
+        finally:
+            dcn_mod.C.try_call = orig
+        assert calls == ["fcvsr_conv2d_tc", "fcvsr_modulated_deform_conv_forward_tc"], calls
+        o = F.conv2d(x.cpu(), m.conv_offset_mask.weight.cpu(), m.conv_offset_mask.bias.cpu(), padding=1)
+        o1, o2, mk = torch.chunk(o, 3, dim=1)
+        ref = O.modulated_deform_conv(x.cpu(), torch.cat((o1, o2), 1), torch.sigmoid(mk), m.weight.cpu(), m.bias.cpu(), 1, 1, 1, 1, dg)
+    err = float((y - ref).abs().max())
+    assert err <= 5e-3 * max(1.0, float(ref.abs().max())), err
