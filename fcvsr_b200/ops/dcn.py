@@ -6,7 +6,8 @@
                           groups=1, deformable_groups=1)                            (deform_conv.py:117-127,187)
     DeformConv / DeformConvPack / ModulatedDeformConv / ModulatedDeformConvPack     (deform_conv.py:190-337)
 
-Same tensor contract (NCHW contiguous fp32 CUDA tensors; offset [B, dg*2*kh*kw, Ho, Wo] with (dh, dw)
+Same tensor contract (NCHW contiguous CUDA tensors; fp32, and -- as the reference dispatches
+AT_DISPATCH_FLOATING_TYPES_AND_HALF -- fp16 / fp64 tensors, which are computed in fp32 and returned in their own dtype; offset [B, dg*2*kh*kw, Ho, Wo] with (dh, dw)
 interleaved per tap; mask [B, dg*kh*kw, Ho, Wo]; NotImplementedError on CPU, :46-47,:136-137).  The native
 entry it binds is ``fcvsr_modulated_deform_conv_forward`` (include/fcvsr_b200.h), a fused gather + GEMM
 kernel that replaces deform_conv_forward_cuda / modulated_deform_conv_cuda_forward
@@ -38,10 +39,18 @@ def _check(*tensors, allow_grad=False):
             continue
         if not t.is_cuda:
             raise NotImplementedError("deformable convolution is CUDA-only (as the reference, deform_conv.py:46-47)")
-        if t.dtype != torch.float32:
-            raise TypeError("fcvsr_b200 DCN kernels are fp32")
+        if t.dtype not in (torch.float32, torch.float16, torch.float64):
+            raise TypeError("deformable convolution expects floating-point tensors (AT_DISPATCH_FLOATING_TYPES_AND_HALF, "
+                            "deform_conv_cuda_kernel.cu:360)")
         if not allow_grad and torch.is_grad_enabled() and t.requires_grad:
             raise NotImplementedError("fcvsr_b200: this path has no backward kernel; call under torch.no_grad()")
+
+
+def _require_fp32(*tensors):
+    """The *Pack modules own fp32 parameters and hand raw pointers to the kernels: no dtype conversion on that path."""
+    for t in tensors:
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError("the DeformConvPack / ModulatedDeformConvPack modules of fcvsr_b200 are fp32")
 
 
 def _out_hw(h, w, kh, kw, stride, padding, dilation):
@@ -122,10 +131,11 @@ class DeformConvFunction(torch.autograd.Function):
         ho, wo = _out_hw(input.shape[2], input.shape[3], kh, kw, stride, padding, dilation)
         if tuple(offset.shape) != (input.shape[0], deformable_groups * 2 * kh * kw, ho, wo):
             raise ValueError(f"invalid offset shape {tuple(offset.shape)}")
-        input, offset, weight = input.contiguous(), offset.contiguous(), weight.contiguous()
+        ctx.dtypes = (input.dtype, offset.dtype, weight.dtype)
+        input, offset, weight = input.float().contiguous(), offset.float().contiguous(), weight.float().contiguous()
         ctx.cfg = (stride, padding, dilation, groups, deformable_groups)
         ctx.save_for_backward(input, offset, weight)
-        return _launch(input, offset, None, weight, None, stride, padding, dilation, groups, deformable_groups)
+        return _launch(input, offset, None, weight, None, stride, padding, dilation, groups, deformable_groups).to(ctx.dtypes[0])
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -136,9 +146,10 @@ class DeformConvFunction(torch.autograd.Function):
         stride, padding, dilation, groups, dg = ctx.cfg
         n = ctx.needs_input_grad
         need_data = n[0] or n[1]                      # the reference computes both together (:76-82)
-        gx, goff, _, gw, _ = _backward(input, offset, None, weight, grad_output, stride, padding, dilation, groups, dg,
+        gx, goff, _, gw, _ = _backward(input, offset, None, weight, grad_output.float(), stride, padding, dilation, groups, dg,
                                        (need_data, need_data, False, n[2]), False)
-        return gx, goff, gw, None, None, None, None, None, None
+        cast = lambda t, d: t.to(d) if t is not None else None  # noqa: E731
+        return cast(gx, ctx.dtypes[0]), cast(goff, ctx.dtypes[1]), cast(gw, ctx.dtypes[2]), None, None, None, None, None, None
 
 
 class ModulatedDeformConvFunction(torch.autograd.Function):
@@ -155,11 +166,12 @@ class ModulatedDeformConvFunction(torch.autograd.Function):
             raise ValueError(f"invalid offset shape {tuple(offset.shape)}")
         if tuple(mask.shape) != (input.shape[0], deformable_groups * kh * kw, ho, wo):
             raise ValueError(f"invalid mask shape {tuple(mask.shape)}")
-        input, offset, mask, weight = input.contiguous(), offset.contiguous(), mask.contiguous(), weight.contiguous()
-        bias = bias.contiguous() if bias is not None else None
+        ctx.dtypes = (input.dtype, offset.dtype, mask.dtype, weight.dtype, bias.dtype if bias is not None else None)
+        input, offset, mask, weight = (t.float().contiguous() for t in (input, offset, mask, weight))
+        bias = bias.float().contiguous() if bias is not None else None
         ctx.cfg = (stride, padding, dilation, groups, deformable_groups, bias is not None)
         ctx.save_for_backward(input, offset, mask, weight)
-        return _launch(input, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups)
+        return _launch(input, offset, mask, weight, bias, stride, padding, dilation, groups, deformable_groups).to(ctx.dtypes[0])
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -169,9 +181,11 @@ class ModulatedDeformConvFunction(torch.autograd.Function):
         input, offset, mask, weight = ctx.saved_tensors
         stride, padding, dilation, groups, dg, with_bias = ctx.cfg
         n = ctx.needs_input_grad
-        gx, goff, gmask, gw, gb = _backward(input, offset, mask, weight, grad_output, stride, padding, dilation, groups,
+        gx, goff, gmask, gw, gb = _backward(input, offset, mask, weight, grad_output.float(), stride, padding, dilation, groups,
                                             dg, (n[0], n[1], n[2], n[3]), with_bias and n[4])
-        return gx, goff, gmask, gw, gb, None, None, None, None, None
+        cast = lambda t, d: t.to(d) if (t is not None and d is not None) else t  # noqa: E731
+        d = ctx.dtypes
+        return cast(gx, d[0]), cast(goff, d[1]), cast(gmask, d[2]), cast(gw, d[3]), cast(gb, d[4]), None, None, None, None, None
 
 
 def deform_conv(input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64):
@@ -226,6 +240,7 @@ def _offset_conv(x, conv: nn.Conv2d):
     """conv_offset / conv_offset_mask of the *Pack modules (deform_conv.py:243-250,:315-323) on our own
     convolution kernel (NCHW in, NCHW out), autograd-capable."""
     _check(x, conv.weight, conv.bias, allow_grad=True)
+    _require_fp32(x, conv.weight, conv.bias)
     kh, kw = conv.weight.shape[2:]
     if kh != kw or conv.stride[0] != conv.stride[1] or conv.padding[0] != kh // 2 or conv.padding[1] != kw // 2:
         raise NotImplementedError("conv_offset: only square kernels with 'same' padding k//2 are supported")

@@ -320,3 +320,58 @@ def test_modulated_dcn_pack_tensor_core_path(dev, B, cin, cout, H, W, dg):
         ref = O.modulated_deform_conv(x.cpu(), torch.cat((o1, o2), 1), torch.sigmoid(mk), m.weight.cpu(), m.bias.cpu(), 1, 1, 1, 1, dg)
     err = float((y - ref).abs().max())
     assert err <= 5e-3 * max(1.0, float(ref.abs().max())), err
+
+
+def test_deform_conv_cuda_module_mirrors_reference_entry_points(dev):
+    """fcvsr_b200.ops.deform_conv_cuda: the five pybind entry names of the reference extension with its argument order
+    (deform_conv_cuda.cpp:681-695), driven exactly as deform_conv.py:52-57,:76-92,:144-166 drives them, against the oracle's
+    autograd; plus fp16 tensors through the public op (computed in fp32, returned as fp16)."""
+    import fcvsr_b200.ops.dcn as dcn_mod
+    from fcvsr_b200.ops import deform_conv_cuda as ext
+    assert all(hasattr(ext, n) for n in ("deform_conv_forward_cuda", "deform_conv_backward_input_cuda", "deform_conv_backward_parameters_cuda",
+                                          "modulated_deform_conv_cuda_forward", "modulated_deform_conv_cuda_backward"))
+    g = torch.Generator().manual_seed(12)
+    B, ci, co, H, W, dg = 2, 8, 6, 9, 11, 4
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, 3, 3, generator=g) / 6
+    b = torch.randn(co, generator=g)
+    off = 2.0 * torch.randn(B, dg * 18, H, W, generator=g)
+    msk = torch.rand(B, dg * 9, H, W, generator=g)
+    gy = torch.randn(B, co, H, W, generator=g)
+    old = dcn_mod.PRECISION
+    dcn_mod.PRECISION = "fp32"
+    try:
+        # --- modulated (v2), as ModulatedDeformConvFunction.forward / backward call it ---
+        cpu = [t.clone().requires_grad_(True) for t in (x, off, msk, w, b)]
+        ref = O.modulated_deform_conv(cpu[0], cpu[1], cpu[2], cpu[3], cpu[4], 1, 1, 1, 1, dg)
+        (ref * gy).sum().backward()
+        xd, od, md, wd, bd, gyd = (t.to(dev) for t in (x, off, msk, w, b, gy))
+        out = xd.new_empty(B, co, H, W)
+        bufs = [xd.new_empty(0), xd.new_empty(0)]
+        ext.modulated_deform_conv_cuda_forward(xd, wd, bd, bufs[0], od, md, out, bufs[1], 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, True)
+        assert float((out.cpu() - ref.detach()).abs().max()) <= 1e-4
+        gi, go, gm, gw, gb = (torch.zeros_like(t) for t in (xd, od, md, wd, bd))
+        ext.modulated_deform_conv_cuda_backward(xd, wd, bd, bufs[0], od, md, bufs[1], gi, gw, gb, go, gm, gyd, 3, 3, 1, 1, 1, 1, 1, 1, 1,
+                                                dg, True)
+        for name, a, r in zip(("input", "offset", "mask", "weight", "bias"), (gi, go, gm, gw, gb), cpu):
+            assert float((a.cpu() - r.grad).abs().max()) <= 2e-4 * max(1.0, float(r.grad.abs().max())), name
+        # --- v1, as DeformConvFunction calls it (W / H argument order) ---
+        cpu = [t.clone().requires_grad_(True) for t in (x, off, w)]
+        ref = O.modulated_deform_conv(cpu[0], cpu[1], None, cpu[2], None, 1, 1, 1, 1, dg)
+        (ref * gy).sum().backward()
+        out = xd.new_empty(B, co, H, W)
+        assert ext.deform_conv_forward_cuda(xd, wd, od, out, bufs[0], bufs[1], 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, B) == 1
+        assert float((out.cpu() - ref.detach()).abs().max()) <= 1e-4
+        gi, go, gw = torch.zeros_like(xd), torch.zeros_like(od), torch.zeros_like(wd)
+        ext.deform_conv_backward_input_cuda(xd, od, gyd, gi, go, wd, bufs[0], 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, B)
+        ext.deform_conv_backward_parameters_cuda(xd, od, gyd, gw, bufs[0], bufs[1], 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, 1, B)
+        for name, a, r in zip(("input", "offset", "weight"), (gi, go, gw), cpu):
+            assert float((a.cpu() - r.grad).abs().max()) <= 2e-4 * max(1.0, float(r.grad.abs().max())), name
+        # --- fp16 tensors through the public operator ---
+        yh = dcn_mod.modulated_deform_conv(xd.half(), od.half(), md.half(), wd.half(), bd.half(), 1, 1, 1, 1, dg)
+        assert yh.dtype == torch.float16
+        ref16 = O.modulated_deform_conv(x.half().float(), off.half().float(), msk.half().float(), w.half().float(), b.half().float(),
+                                        1, 1, 1, 1, dg)
+        assert float((yh.float().cpu() - ref16).abs().max()) <= 2.0 ** -9 * max(1.0, float(ref16.abs().max()))
+    finally:
+        dcn_mod.PRECISION = old
