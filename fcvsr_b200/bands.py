@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 _MASK1024: Dict[int, torch.Tensor] = {}
-_MASKS: Dict[Tuple[int, int, int, str], torch.Tensor] = {}
+_MASKS: Dict[Tuple[int, int, int, str, str], torch.Tensor] = {}
 _TW: Dict[Tuple[int, str], torch.Tensor] = {}
 
 
@@ -38,12 +38,39 @@ def _gaussian_masks_1024(q: int) -> torch.Tensor:
     return _MASK1024[q]
 
 
-def symmetric_half_masks(q: int, h: int, w: int, device) -> torch.Tensor:
+_IDEAL1024: Dict[int, torch.Tensor] = {}
+
+
+def _ideal_masks_1024(q: int) -> torch.Tensor:
+    """'ideal' mode of the RGB family (CVSR_freq_RGB.py:1493-1506): filled discs drawn with cv2.circle -- the same call is made
+    here on purpose (its rasterisation is part of the reference's result), so this mode needs OpenCV on the host."""
+    if q not in _IDEAL1024:
+        try:
+            import cv2
+        except ImportError as e:           # pragma: no cover
+            raise RuntimeError("the 'ideal' band masks of FCVSR / FCVSR_S are rasterised with cv2.circle as in the reference; "
+                               "OpenCV (cv2) is required for these two classes") from e
+        n = 1024
+        step = math.sqrt(2.0 * (n / 2) ** 2) / q
+        out = []
+        for i in range(q):
+            pf = np.zeros((n, n))
+            cv2.circle(pf, (n // 2, n // 2), math.ceil((i + 1) * step), (1), -1)
+            g = torch.from_numpy(pf).float()
+            for prev in out:
+                g = g - prev
+            out.append(g)
+        _IDEAL1024[q] = torch.stack(out, 0)
+    return _IDEAL1024[q]
+
+
+def symmetric_half_masks(q: int, h: int, w: int, device, mode: str = "gaussian") -> torch.Tensor:
     """[Q, H, W/2+1] float32 on `device`."""
-    key = (q, h, w, str(device))
+    key = (q, h, w, str(device), mode)
     if key not in _MASKS:
         from torchvision.transforms import Resize, functional as TF
-        m = Resize([h, w], interpolation=TF.InterpolationMode.BICUBIC)(_gaussian_masks_1024(q))
+        base = _gaussian_masks_1024(q) if mode == "gaussian" else _ideal_masks_1024(q)
+        m = Resize([h, w], interpolation=TF.InterpolationMode.BICUBIC)(base)
         m = torch.fft.ifftshift(m, dim=(1, 2))
         neg = torch.roll(torch.flip(m, dims=(1, 2)), shifts=(1, 1), dims=(1, 2))   # M(-k)
         msym = 0.5 * (m + neg)

@@ -230,3 +230,29 @@ def test_train_step_on_the_fcvsr_model(dev):
     moved = sum(int(not torch.equal(p.detach(), before[k])) for k, p in m.named_parameters())
     dead = sum(1 for k, _ in m.named_parameters() if ".Conv." in k)
     assert moved == len(before) - dead, (moved, len(before), dead)
+
+
+@pytest.mark.parametrize("name", ["fcvsr_rgb_s_32x40", "fcvsr_rgb_full_32"])
+def test_rgb_family_matches_reference_golden(dev, name):
+    """FCVSR / FCVSR_S of CVSR_freq_RGB.py (arch_rgb + rgb_forward: kernel-library operators + PyTorch glue) against the
+    reference goldens in both compute modes, and one backward pass reaches every live parameter."""
+    pytest.importorskip("cv2")
+    from fcvsr_b200 import arch_rgb
+    from tests.util import make_clip_rgb
+    g = load_golden(name)
+    c = g["case"]
+    m = (arch_rgb.FCVSR_S if c["variant"] == "S" else arch_rgb.FCVSR)().to(dev)
+    m.load_state_dict(arch_rgb.seeded_state_dict_rgb(c["variant"], c["seed"]))
+    x = make_clip_rgb(c["clip_seed"], c["b"], c["h"], c["w"]).to(dev)
+    for mode, tol in (("fp32", 2e-5), ("tf32", 1e-3)):
+        m.compute_dtype = mode
+        with torch.no_grad():
+            y = m(x)
+        err = float((y.cpu() - g["out"]).abs().max())
+        assert y.shape == g["out"].shape and err <= tol, (mode, err)
+    m.compute_dtype = "fp32"
+    hr = torch.rand(g["out"].shape, generator=torch.Generator().manual_seed(1)).to(dev)
+    CharbonnierLoss(m(x), hr).backward()
+    none = [k for k, p in m.named_parameters() if p.grad is None]
+    assert none == [], none
+    assert all(bool(torch.isfinite(p.grad).all()) for p in m.parameters())

@@ -199,3 +199,31 @@ def test_metrics_oracle_matches_live_reference():
         p, s = M.calculate_psnr(af[..., 0], bf[..., 0], 4), M.calculate_ssim(af[..., 0], bf[..., 0], 4)
         assert (p == p_ref) or abs(p - p_ref) <= 1e-5 * abs(p_ref)
         assert abs(s - s_ref) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["fcvsr_rgb_s_32x40", "fcvsr_rgb_full_32"])
+def test_rgb_oracle_matches_reference_golden(name):
+    """oracle/fcvsr_rgb_oracle.py (FCVSR / FCVSR_S of CVSR_freq_RGB.py) against goldens made by the unmodified reference
+    (oracle/make_golden_rgb.py): output and stage taps."""
+    pytest.importorskip("cv2")             # the 'ideal' band masks are rasterised with cv2.circle, as in the reference
+    from fcvsr_b200.arch_rgb import seeded_state_dict_rgb
+    from oracle import fcvsr_rgb_oracle as R
+    g = load_golden(name)
+    c = g["case"]
+    sd = seeded_state_dict_rgb(c["variant"], c["seed"])
+    x = make_clip_rgb(c["clip_seed"], c["b"], c["h"], c["w"])
+    with torch.no_grad():
+        y, taps = R.forward(sd, x, return_taps=True)
+    assert (y - g["out"]).abs().max().item() <= 2e-5
+    for k in ("mgaa1", "mgaa2", "mffr", "sc_l1", "fuse"):
+        assert (taps[k][..., ::4, ::4] - g[k]).abs().max().item() <= 5e-5, k
+
+
+def test_rgb_state_dict_matches_reference_keys_and_shapes():
+    from fcvsr_b200.arch_rgb import FCVSR, FCVSR_S
+    with open(os.path.join(GOLD, "state_dict_shapes_rgb.json")) as f:
+        ref = json.load(f)
+    for variant, cls in (("S", FCVSR_S), ("full", FCVSR)):
+        assert [[k, list(v.shape)] for k, v in cls().state_dict().items()] == ref[variant]
+    assert sum(p.numel() for p in FCVSR().parameters()) == 9042890          # SURVEY 8 f1
+    assert sum(p.numel() for p in FCVSR_S().parameters()) == 4024999
