@@ -14,7 +14,8 @@ channel c (the layout of fcvsr_fft_*).
 
 Compute modes (`mode` arguments): "fp32" runs every convolution on the CUDA-core kernel (exact fp32; used by the golden-
 gradient test), "tf32" runs forward and data-gradient convolutions whose shape fits on the tcgen05 kernel with operands
-rounded to nearest TF32 (the contract's fp32 mode); weight gradients are fp32 FFMA with fp32 atomics in both modes.
+rounded to nearest TF32 (the contract's fp32 mode) and their weight gradients on the tcgen05 wgrad kernel (bf16 copies of
+the activations / upstream gradients, fp32 accumulation; csrc/wgrad_tc.cu); every other weight gradient is fp32 FFMA.
 """
 from __future__ import annotations
 
@@ -26,6 +27,7 @@ from . import _capi as C
 from . import bands
 
 F32 = torch.float32
+WGRAD_TC = True        # "tf32" mode: weight gradients of 64-multiple-channel stride-1 convolutions on tcgen05 (bf16 operands)
 
 
 def _st() -> int:
@@ -114,7 +116,15 @@ class _Conv2d(torch.autograd.Function):
                 gx = _logical(dx)
             if ctx.needs_input_grad[1]:
                 dw = torch.zeros(k * k, ci, co, device=xh.device, dtype=F32)
-                C.call("fcvsr_conv2d_wgrad", xh.data_ptr(), ci, g.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, stride, _st())
+                if mode == "tf32" and WGRAD_TC and stride == 1 and k in (1, 3) and ci % 64 == 0 and co % 64 == 0:
+                    # tensor-core weight gradient: bf16 copies of the activations and of the upstream gradient, fp32 accumulation
+                    xb = torch.empty(B, H, W, ci, device=xh.device, dtype=torch.bfloat16)
+                    gb16 = torch.empty(B, H, W, co, device=xh.device, dtype=torch.bfloat16)
+                    C.call("fcvsr_round_copy", xh.data_ptr(), ci, xb.data_ptr(), ci, ci, ci, B * H * W, 1, _st())
+                    C.call("fcvsr_round_copy", g.data_ptr(), co, gb16.data_ptr(), co, co, co, B * H * W, 1, _st())
+                    C.call("fcvsr_conv2d_wgrad_tc", xb.data_ptr(), ci, gb16.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, _st())
+                else:
+                    C.call("fcvsr_conv2d_wgrad", xh.data_ptr(), ci, g.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, stride, _st())
                 gw = dw.view(k, k, ci, co).permute(3, 2, 0, 1)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 npix = g.shape[0] * g.shape[1] * g.shape[2]

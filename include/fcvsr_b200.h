@@ -235,6 +235,11 @@ int fcvsr_conv2d_dgrad_direct(const float* dy, int lddy, const float* wt, float*
  * fp32 atomics over pixel slices (zero-fill first; run-to-run differences at rounding level, as cuDNN's atomic wgrad). */
 int fcvsr_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
                        int ksize, int stride, cudaStream_t stream);
+/* The same weight gradient on the tcgen05 tensor cores (csrc/wgrad_tc.cu): x and dy are BF16 NHWC tensors (ld in elements,
+ * % 8 == 0, 16-byte aligned), fp32 accumulation in TMEM over a split of the pixel tiles, fp32 vector reductions into dw.
+ * k in {1, 3}, stride 1, Cin % 64 == 0, Cout % 64 == 0; other shapes return FCVSR_ERR_UNSUPPORTED (use fcvsr_conv2d_wgrad). */
+int fcvsr_conv2d_wgrad_tc(const void* x_bf16, int ldx, const void* dy_bf16, int lddy, float* dw, int B, int H, int W, int Cin,
+                          int Cout, int ksize, cudaStream_t stream);
 /* out[c] (+)= sum over npix rows of x[row*ldx + c] (bias gradient), deterministic; scratch: ceil(npix / 256) * C floats. */
 int fcvsr_colsum(const float* x, int ldx, int C, long long npix, float* scratch, float* out, int accumulate, cudaStream_t stream);
 /* flow_warp (CVSR_freq.py:1188-1227) on NHWC maps: y[b,py,px,:] = bilinear(x[b], px + off[b,py,px,0], py + off[b,py,px,1]), zero
