@@ -18,14 +18,14 @@ import torch.nn.functional as F
 
 from . import autograd as A
 from . import bands
-from .train_forward import _ca, _cl, _Ctx
+from .train_forward import _ca, _cl, _Ctx, _index_tensors
 
 
 def _mgaa(cx: _Ctx, x: torch.Tensor) -> torch.Tensor:
     """MGAA.forward :1101-1180 on x [B,192,H,W]."""
     mg, n, acn = cx.m.MGAA, cx.m.n_feats, cx.m.ACNum
     B, _, H, W = x.shape
-    inv = cx.inv.to(x.device)
+    inv, rows = _index_tensors(x.device, n, acn, with_bias_rows=True)
     x1, x2, x3 = x[:, :n], x[:, n:2 * n], x[:, 2 * n:]
     spec = A.rfft2(x)                                              # interleaved, group g at channels [128g, 128g+128)
     s1, s2, s3 = spec[:, :2 * n], spec[:, 2 * n:4 * n], spec[:, 4 * n:]
@@ -48,8 +48,6 @@ def _mgaa(cx: _Ctx, x: torch.Tensor) -> torch.Tensor:
             zs.append(torch.stack([v[:, 0], v[:, 2], v[:, 1], v[:, 3]], 1))      # complex(v[0:2], v[2:4]) interleaved
     offs = A.irfft2(_cl(torch.cat(zs, 1)), W)                      # channel (i*2+dir)*2 + (dx, dy)
     # kernel predictor (:1152-1153): live tap rows i*384 + c*3 + t re-ordered to [i][t][c], bias rows A*384 + i*64 + c
-    ii, tt, cc = torch.meshgrid(torch.arange(acn), torch.arange(3), torch.arange(n), indexing="ij")
-    rows = torch.cat([(ii * 6 * n + cc * 3 + tt).reshape(-1), acn * 6 * n + torch.arange(acn * n)]).to(x.device)
     kp = cx.conv(cx.conv(_cl(x2), mg.conv_KP), mg.F[0])
     pred = cx.conv(kp, mg.F[1].weight[rows], mg.F[1].bias[rows])   # [B, A*192 + A*64, H, W]
     taps, fbs = pred[:, :acn * 3 * n], pred[:, acn * 3 * n:]

@@ -34,6 +34,48 @@ def train_step(model: torch.nn.Module, optimizer: torch.optim.Optimizer, frames:
     return loss.detach()
 
 
+class GraphedTrainStep:
+    """The training step with forward + backward replayed from ONE CUDA graph.
+
+    The eager step is host-bound (about 18 k kernel launches per step for FCVSR at batch 8: 250 ms of Python / launch time for
+    100 ms of device work), so the launch sequence of `loss_fn(model(frames), hr).backward()` is captured once on static
+    input buffers and replayed; the gradient all-reduce (its buckets are issued back to back, NCCL over NVLink) and the
+    optimizer step stay outside the graph -- Adam's bias corrections depend on the step count, which a captured launch would
+    freeze.  Gradients live in the graph's memory pool and are rewritten by every replay (the whole-network capture pattern of
+    the PyTorch CUDA-graphs notes), so `zero_grad` must not be called between steps.
+    """
+
+    def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, loss_fn, frames: torch.Tensor, hr: torch.Tensor,
+                 reducer=None, warmup: int = 3):
+        self.model, self.optimizer, self.reducer = model, optimizer, reducer
+        self.frames, self.hr = frames.clone(), hr.clone()
+        dev = frames.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                   # eager warm-up: lazy initialisation (caches, function attributes), allocator
+            for _ in range(warmup):
+                optimizer.zero_grad(set_to_none=True)
+                loss_fn(model(self.frames), self.hr).backward()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = loss_fn(model(self.frames), self.hr)
+            self.loss.backward()
+
+    def __call__(self, frames: torch.Tensor, hr: torch.Tensor) -> torch.Tensor:
+        self.frames.copy_(frames, non_blocking=True)
+        self.hr.copy_(hr, non_blocking=True)
+        if self.reducer is not None:
+            self.reducer.start_step()
+        self.graph.replay()
+        if self.reducer is not None:
+            self.reducer.finish()            # hooks do not fire on a replay: every bucket goes out here, in order
+        self.optimizer.step()
+        return self.loss.detach()
+
+
 def replicas_in_sync(model: torch.nn.Module, group=None, atol: float = 0.0) -> bool:
     """Debug check: every rank holds the same parameters (max over ranks of |p - p_rank0| <= atol)."""
     import torch.distributed as dist
@@ -48,7 +90,7 @@ def replicas_in_sync(model: torch.nn.Module, group=None, atol: float = 0.0) -> b
 
 
 def bench_train_step(dev, rank: int, world: int, steps: int = 5, warmup: int = 2, variant: str = "full", batch: int = 8,
-                     size: int = 64) -> dict:
+                     size: int = 64, graph: bool = True) -> dict:
     """BASELINE config 4 for bench.py: FCVSR training step (forward + backward + Adam, Charbonnier-sum loss) on a per-GPU batch
     of `batch` synthetic 7 x size x size crops, data parallel with the NCCL gradient all-reduce when world > 1.  Device time
     (CUDA events), max over ranks; the all-reduce is timed separately in a second pass (`time_collectives`: every collective
@@ -63,7 +105,7 @@ def bench_train_step(dev, rank: int, world: int, steps: int = 5, warmup: int = 2
     model.load_state_dict(arch.seeded_state_dict(variant, 0))
     model.compute_dtype = "tf32"
     opt = Adam(model.parameters(), lr=5e-6, weight_decay=1e-5)              # train_LD_freqCVSR_22.py:35,42,204
-    red = GradAllReducer(model.parameters()) if world > 1 else None
+    red = GradAllReducer(model.parameters(), overlap=not graph) if world > 1 else None
     g = torch.Generator().manual_seed(99 + rank)
     frames = (torch.round(255 * torch.rand(batch, 7, 1, size, size, generator=g)) / 255).to(dev)
     hr = torch.rand(batch, 1, 4 * size, 4 * size, generator=g).to(dev)
@@ -73,13 +115,18 @@ def bench_train_step(dev, rank: int, world: int, steps: int = 5, warmup: int = 2
             dist.barrier()
         torch.cuda.synchronize()
 
+    stepper = GraphedTrainStep(model, opt, CharbonnierLoss, frames, hr, red) if graph else None
+
+    def one():
+        return stepper(frames, hr) if graph else train_step(model, opt, frames, hr, CharbonnierLoss, red)
+
     def run(n):
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         loss = None
         for _ in range(n):
-            loss = train_step(model, opt, frames, hr, CharbonnierLoss, red)
+            loss = one()
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -93,7 +140,7 @@ def bench_train_step(dev, rank: int, world: int, steps: int = 5, warmup: int = 2
     ar_ms = None
     if red is not None:
         red.time_collectives = True
-        train_step(model, opt, frames, hr, CharbonnierLoss, red)
+        one()
         t = torch.tensor([red.allreduce_ms()], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ar_ms = float(t)
@@ -102,10 +149,12 @@ def bench_train_step(dev, rank: int, world: int, steps: int = 5, warmup: int = 2
     nparam = sum(p.numel() for p in model.parameters())
     return {"metric": "training steps/sec (fwd + bwd + Adam, per-GPU batch %d of 7x%dx%d crops)" % (batch, size, size),
             "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "clips_per_s": world * batch * 1e3 / ms, "n_gpus": world,
-            "steps": steps, "warmup": warmup, "loss": loss, "dtype": "tf32 (fp32 storage, TF32 tensor-core operands in forward and "
-            "data-gradient convolutions, fp32 weight gradients)", "variant": variant,
+            "steps": steps, "warmup": warmup, "loss": loss, "dtype": "tf32 (fp32 storage; TF32 tensor-core operands in forward and "
+            "data-gradient convolutions; bf16 tcgen05 weight gradients with fp32 accumulation)", "variant": variant,
+            "cuda_graph": "forward + backward replayed from one CUDA graph; all-reduce and Adam outside" if graph else False,
             "allreduce": None if red is None else {"backend": "nccl", "buckets": len(red.buckets), "bytes": 4 * nparam,
                                                    "ms_serialised": ar_ms,
                                                    "note": "sum of the bucket collectives' device time in a pass where each is "
-                                                           "bracketed by events; in the timed steps they overlap the backward"},
+                                                           "bracketed by events; in the timed steps they are issued back to back "
+                                                           "after the backward graph"},
             "optimizer": "fcvsr_adam_step (multi-tensor), lr 5e-6, weight_decay 1e-5", "loss_fn": "Charbonnier sum (fcvsr_charbonnier_loss)"}

@@ -37,13 +37,29 @@ def _ca(mod, x: torch.Tensor) -> torch.Tensor:
     return x * g[:, :, None, None]
 
 
+_IDX = {}
+
+
+def _index_tensors(device, n: int, acn: int, with_bias_rows: bool = False):
+    """Constant index tensors on the device, built once (a host-to-device copy per forward would also be illegal inside a CUDA-graph
+    capture of the training step): `inv` = spectrum-packing permutation, `rows` = live rows of MGAA.F.1 in [iteration][tap][channel]
+    order (plus, for the RGB family, the per-iteration bias rows)."""
+    key = (str(device), n, acn, with_bias_rows)
+    if key not in _IDX:
+        j = torch.arange(2 * n)
+        pi = torch.where(j < n, 2 * j + 1, 2 * (j - n))          # reference xk_f channel j -> interleaved float index
+        inv = torch.argsort(pi)                                    # interleaved index i <- reference channel inv[i]
+        ii, tt, cc = torch.meshgrid(torch.arange(acn), torch.arange(3), torch.arange(n), indexing="ij")
+        rows = (ii * 6 * n + cc * 3 + tt).reshape(-1)
+        if with_bias_rows:
+            rows = torch.cat([rows, acn * 6 * n + torch.arange(acn * n)])
+        _IDX[key] = (inv.to(device), rows.to(device))
+    return _IDX[key]
+
+
 class _Ctx:
     def __init__(self, model, mode: str):
         self.m, self.mode = model, mode
-        n = model.n_feats
-        j = torch.arange(2 * n)
-        pi = torch.where(j < n, 2 * j + 1, 2 * (j - n))          # reference xk_f channel j -> interleaved float index
-        self.inv = torch.argsort(pi)                               # interleaved index i <- reference channel inv[i]
 
     def conv(self, x, mod_or_w, bias=None, stride=1):
         if isinstance(mod_or_w, torch.nn.Conv2d):
@@ -56,7 +72,7 @@ def _mgaa(cx: _Ctx, x: torch.Tensor) -> torch.Tensor:
     """MGAAbk.forward :1442-1547 on x [B,192,H,W] (x1 | x2 | x3)."""
     mg, n, acn = cx.m.MGAA, cx.m.n_feats, cx.m.ACNum
     B, _, H, W = x.shape
-    inv = cx.inv.to(x.device)
+    inv, rows = _index_tensors(x.device, n, acn)
     x1, x2, x3 = x[:, :n], x[:, n:2 * n], x[:, 2 * n:]
     spec = A.rfft2(x)                                              # [B,384,H,Wf]: group g at channels [128g, 128g+128)
     s1, s2, s3 = spec[:, :2 * n], spec[:, 2 * n:4 * n], spec[:, 4 * n:]
@@ -95,8 +111,6 @@ def _mgaa(cx: _Ctx, x: torch.Tensor) -> torch.Tensor:
             zs.append(torch.stack([v[:, 0], v[:, 2], v[:, 1], v[:, 3]], 1))      # complex(v[0:2], v[2:4]) interleaved
     offs = A.irfft2(_cl(torch.cat(zs, 1)), W)                      # [B, 4*ACNum, H, W]: channel (i*2+dir)*2 + (dx, dy)
     # kernel predictor (:1522-1523), live rows of F.1 only, re-ordered to [iteration][tap][channel]
-    ii, tt, cc = torch.meshgrid(torch.arange(acn), torch.arange(3), torch.arange(n), indexing="ij")
-    rows = (ii * 6 * n + cc * 3 + tt).reshape(-1).to(x.device)
     kp = cx.conv(cx.conv(_cl(x2), mg.conv_KP), mg.F[0])
     taps = cx.conv(kp, mg.F[1].weight[rows], mg.F[1].bias[rows])   # [B, ACNum*192, H, W]
     aligned = []

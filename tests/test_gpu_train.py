@@ -278,3 +278,26 @@ def test_rgb_family_matches_reference_golden(dev, name):
     none = [k for k, p in m.named_parameters() if p.grad is None]
     assert none == [], none
     assert all(bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+
+
+def test_graphed_train_step_matches_eager(dev):
+    """GraphedTrainStep (forward + backward replayed from one CUDA graph, Adam outside) follows the eager train_step: same
+    losses and parameters after three steps on changing batches (bit-level differences only from the fp32 atomics of the weight
+    gradients)."""
+    from fcvsr_b200.ops.optim import Adam
+    from fcvsr_b200.train import GraphedTrainStep, train_step
+    sd = arch.seeded_state_dict("S", 0)
+    g = torch.Generator().manual_seed(21)
+    xs = [make_clip(40 + i, 2, 32, 32).to(dev) for i in range(3)]
+    hs = [torch.rand(2, 1, 128, 128, generator=g).to(dev) for _ in range(3)]
+    ma, mb = arch.GShiftNet_S().to(dev).train(), arch.GShiftNet_S().to(dev).train()
+    ma.load_state_dict(sd)
+    mb.load_state_dict(sd)
+    oa, ob = Adam(ma.parameters(), lr=2e-5, weight_decay=1e-5), Adam(mb.parameters(), lr=2e-5, weight_decay=1e-5)
+    stepper = GraphedTrainStep(mb, ob, CharbonnierLoss, xs[0], hs[0])
+    for x, h in zip(xs, hs):
+        la = float(train_step(ma, oa, x, h, CharbonnierLoss))
+        lb = float(stepper(x, h))
+        assert abs(la - lb) <= 1e-4 * abs(la), (la, lb)
+    for (k, p), q in zip(ma.named_parameters(), mb.parameters()):
+        assert float((p.detach() - q.detach()).abs().max()) <= 1e-5 * max(1e-3, float(p.detach().abs().max())), k
