@@ -56,10 +56,15 @@ def _tc_ok(cin: int, cout: int, k: int, stride: int) -> bool:
     return stride == 1 and k in (1, 3) and cin % 32 == 0 and (cout % 16 == 0 or cout < 16) and cout <= 2048
 
 
-def _conv_launch(xh: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride: int, mode: str) -> torch.Tensor:
-    """y = conv(x, w) + bias on an NHWC buffer; w in the reference's [Cout, Cin, k, k] layout."""
+def _conv_launch(xh: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride: int, mode: str,
+                 transposed: bool = False) -> torch.Tensor:
+    """y = conv(x, w) + bias on an NHWC buffer; w in the reference's [Cout, Cin, k, k] layout.  transposed: the data gradient --
+    x is dy and the convolution runs with w's taps flipped and its channel axes swapped (stride 1 only)."""
     B, H, W, ci = xh.shape
-    co, ci_w, k, _ = w.shape
+    if transposed:
+        ci_w, co, k, _ = w.shape
+    else:
+        co, ci_w, k, _ = w.shape
     assert ci_w == ci, (ci_w, ci)
     pad = k // 2
     ho, wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
@@ -68,13 +73,13 @@ def _conv_launch(xh: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     if mode == "tf32" and _tc_ok(ci, co, k, stride):
         xr = torch.empty_like(xh)                            # tcgen05 truncates TF32 operands: round to nearest first
         C.call("fcvsr_round_copy", xh.data_ptr(), ci, xr.data_ptr(), ci, ci, ci, B * H * W, 0, _st())
-        wt = w.permute(0, 2, 3, 1).reshape(co, k * k * ci)
-        if co < 16:
-            wt = torch.cat([wt, wt.new_zeros(16 - co, wt.shape[1])], 0)
-        wt = _round_tf32(wt)
+        wt = torch.empty(max(co, 16), k * k * ci, device=xh.device, dtype=F32)
+        wc = w.contiguous()
+        C.call("fcvsr_pack_conv_weight", wc.data_ptr(), wt.data_ptr(), wc.shape[0], wc.shape[1], k, int(transposed), 16, _st())
         C.call("fcvsr_conv2d_tc", xr.data_ptr(), ci, wt.data_ptr(), bp, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, k,
                C.ACT_NONE, 0.0, 0, 0, 0, 0, 0, 0, 0, _st())
     else:
+        assert not transposed
         wd = w.permute(2, 3, 1, 0).contiguous()              # [k*k][Cin][Cout]
         C.call("fcvsr_conv2d_direct", xh.data_ptr(), ci, 0, wd.data_ptr(), bp, 0, 0, 0, 0, y.data_ptr(), co, B, H, W, ci, co, k,
                stride, C.ACT_NONE, 0.0, 0, 0, 0, 0, 0, 0, 0, _st())
@@ -107,7 +112,7 @@ class _Conv2d(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 if mode == "tf32" and _tc_ok(co, ci, k, stride):
                     # dx = conv(dy, w') with w'[ci][co][ky][kx] = w[co][ci][k-1-ky][k-1-kx]
-                    dx = _conv_launch(g, w.flip(2, 3).transpose(0, 1), None, 1, mode)
+                    dx = _conv_launch(g, w, None, 1, mode, transposed=True)
                 else:
                     dx = torch.empty(B, H, W, ci, device=xh.device, dtype=F32)
                     wt = w.permute(2, 3, 0, 1).contiguous()                      # [k*k][Cout][Cin]

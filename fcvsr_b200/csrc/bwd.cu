@@ -446,3 +446,37 @@ extern "C" int fcvsr_corr_gather_backward(const float* S, int ldS, int a_off, in
                                                                           rsqrtf((float)C2), total);
     return fcvsr_launch_status();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight packing for the tensor-core convolution in ONE launch (the training path re-packs every weight twice per step:
+// forward and data gradient).  w is the reference's [Cout][Cin][k][k]; out is K-major [rows][k*k*C] with TF32 rounding:
+//   transposed = 0:  out[co][tap][ci] = w[co][ci][tap]                      rows = max(Cout, rows_pad), C = Cin   (forward)
+//   transposed = 1:  out[ci][tap][co] = w[co][ci][k*k-1-tap]                rows = max(Cin, rows_pad),  C = Cout  (dgrad: the
+//                    data gradient of a stride-1 'same' convolution is the convolution with flipped, transposed weights)
+// rows beyond the real count are zero (thin heads are padded to 16 GEMM columns).
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kk, int transposed,
+                                        int rows, size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int C = transposed ? Cout : Cin, R = transposed ? Cin : Cout;
+    const int c = (int)(idx % C);
+    const int tap = (int)((idx / C) % kk);
+    const int r = (int)(idx / ((size_t)C * kk));
+    float v = 0.f;
+    if (r < R) {
+        const int co = transposed ? c : r, ci = transposed ? r : c, t = transposed ? kk - 1 - tap : tap;
+        v = round_tf32(w[((size_t)co * Cin + ci) * kk + t]);
+    }
+    out[idx] = v;
+    (void)rows;
+}
+
+extern "C" int fcvsr_pack_conv_weight(const float* w, float* out, int Cout, int Cin, int ksize, int transposed, int rows_pad,
+                                      cudaStream_t st) {
+    if (!w || !out || Cout <= 0 || Cin <= 0 || ksize <= 0) return FCVSR_ERR_ARG;
+    const int R = transposed ? Cin : Cout, C = transposed ? Cout : Cin;
+    const int rows = R > rows_pad ? R : rows_pad;
+    const size_t total = (size_t)rows * ksize * ksize * C;
+    pack_conv_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, out, Cout, Cin, ksize * ksize, transposed, rows, total);
+    return fcvsr_launch_status();
+}

@@ -240,6 +240,12 @@ int fcvsr_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, float
  * k in {1, 3}, stride 1, Cin % 64 == 0, Cout % 64 == 0; other shapes return FCVSR_ERR_UNSUPPORTED (use fcvsr_conv2d_wgrad). */
 int fcvsr_conv2d_wgrad_tc(const void* x_bf16, int ldx, const void* dy_bf16, int lddy, float* dw, int B, int H, int W, int Cin,
                           int Cout, int ksize, cudaStream_t stream);
+/* Weight packing for fcvsr_conv2d_tc in one launch: w [Cout][Cin][k][k] (the reference's nn.Conv2d layout) -> K-major,
+ * TF32-rounded out [rows][k*k*C]: transposed = 0: out[co][tap][ci] (forward, C = Cin); transposed = 1: out[ci][tap][co] with
+ * flipped taps (the data gradient of a stride-1 convolution is the convolution with these weights, C = Cout).  rows =
+ * max(real rows, rows_pad), extra rows zero (thin heads are padded to 16). */
+int fcvsr_pack_conv_weight(const float* w, float* out, int Cout, int Cin, int ksize, int transposed, int rows_pad,
+                           cudaStream_t stream);
 /* out[c] (+)= sum over npix rows of x[row*ldx + c] (bias gradient), deterministic; scratch: ceil(npix / 256) * C floats. */
 int fcvsr_colsum(const float* x, int ldx, int C, long long npix, float* scratch, float* out, int accumulate, cudaStream_t stream);
 /* flow_warp (CVSR_freq.py:1188-1227) on NHWC maps: y[b,py,px,:] = bilinear(x[b], px + off[b,py,px,0], py + off[b,py,px,1]), zero

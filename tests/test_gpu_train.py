@@ -299,7 +299,11 @@ def test_graphed_train_step_matches_eager(dev):
         la = float(train_step(ma, oa, x, h, CharbonnierLoss))
         lb = float(stepper(x, h))
         assert abs(la - lb) <= 1e-4 * abs(la), (la, lb)
-    # Adam normalises every update to about +-lr, so rounding-level gradient noise (fp32 atomics) can move an element by a
-    # fraction of lr per step; the two runs must agree to well below the 3 * lr they have travelled
+    # Adam normalises every update to +-lr, so for an element whose gradient is at rounding level (fp32 atomics) the two runs may
+    # step in opposite directions: the hard bound is 2 * lr per step; on average they must agree far better
+    diffs = []
     for (k, p), q in zip(ma.named_parameters(), mb.parameters()):
-        assert float((p.detach() - q.detach()).abs().max()) <= 0.5 * 2e-5, k
+        d = (p.detach() - q.detach()).abs()
+        assert float(d.max()) <= 3 * 2 * 2e-5 + 1e-9, k
+        diffs.append(d.flatten())
+    assert float(torch.cat(diffs).mean()) <= 0.02 * 2e-5
