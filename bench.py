@@ -272,6 +272,8 @@ def main():
         eng = models[args.dtype]._engine
         how = "event-record nodes around every launch of the graph-replayed step (instrumented capture of the same launch sequence)"
         try:
+            if args.no_graph:
+                raise RuntimeError("--no-graph")
             with torch.no_grad():
                 prof, replay_ms = eng.profile_graph_replay(x_dev, reps=5)
         except Exception as e:                         # external events unavailable: eager per-launch events, said so

@@ -30,8 +30,11 @@ __device__ __forceinline__ float4 load4_any(const void* base, size_t idx, int b1
 struct CtxLevel { const void* x; int P; int nblk; int blk_begin; long long part_off; };    // part_off: floats into `partial`
 struct CtxArgs { CtxLevel lv[SC_MAX_LEV]; int nlev; int ldx; int ppb; int B; const float* wmask; float* partial; };
 
-// One block = ppb pixels (a multiple of 128), 8 warps, 4 pixels in flight per warp (lane owns 2 channels, so a
-// pixel is one coalesced 256-byte load and its logit one 5-step shuffle reduction).
+#define CTX_SEL(field) (l == 0 ? a.lv[0].field : (l == 1 ? a.lv[1].field : a.lv[2].field))
+
+// One block = ppb pixels (a multiple of 128), 8 warps, 8 pixels in flight per warp (lane owns 2 channels, so a
+// pixel is one coalesced 256-byte load and its logit one 5-step shuffle reduction).  The level descriptor is read field by
+// field with compile-time indices: indexing the kernel parameters with a run-time level copies them to local memory.
 template <bool X16>
 __global__ void __launch_bounds__(256) ctx_partial_kernel(const CtxArgs a) {
     __shared__ float sm_m[8], sm_z[8];
@@ -39,22 +42,22 @@ __global__ void __launch_bounds__(256) ctx_partial_kernel(const CtxArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, c = 2 * lane;
     const int bx = blockIdx.x;
     const int l = (a.nlev > 1 && bx >= a.lv[1].blk_begin) ? ((a.nlev > 2 && bx >= a.lv[2].blk_begin) ? 2 : 1) : 0;
-    const CtxLevel& L = a.lv[l];
-    const int P = L.P, ppb = a.ppb, ldx = a.ldx, lbx = bx - L.blk_begin;
-    const float* x = reinterpret_cast<const float*>(L.x);
+    const int P = CTX_SEL(P), ppb = a.ppb, ldx = a.ldx, lbx = bx - CTX_SEL(blk_begin), nblk = CTX_SEL(nblk);
+    const long long part_off = CTX_SEL(part_off);
+    const float* x = reinterpret_cast<const float*>(CTX_SEL(x));
     const float2 w = *reinterpret_cast<const float2*>(a.wmask + c);
     float m = -INFINITY, z = 0.f;
     float2 acc = make_float2(0.f, 0.f);
     const int p0 = lbx * ppb + warp * (ppb >> 3);        // ppb pixels per block (multiple of 128), 1/8 per warp
     const float* xb = x + (size_t)b * P * ldx + c;
     const unsigned short* xb16 = reinterpret_cast<const unsigned short*>(x) + (size_t)b * P * ldx + c;   // x16: bf16 tensor
-    for (int it = 0; it < (ppb >> 5); ++it) {
-        float2 v[4];
-        float lg[4];
+    for (int it = 0; it < (ppb >> 6); ++it) {
+        float2 v[8];
+        float lg[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int p = p0 + it * 4 + u;
-            if (X16) {       // compile-time: the four loads of an iteration stay back to back
+        for (int u = 0; u < 8; ++u) {
+            const int p = p0 + it * 8 + u;
+            if (X16) {       // compile-time: the eight loads of an iteration stay back to back
                 const uint32_t w2 = p < P ? *reinterpret_cast<const uint32_t*>(xb16 + (size_t)p * ldx) : 0u;
                 v[u] = make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u));
             } else {
@@ -65,11 +68,11 @@ __global__ void __launch_bounds__(256) ctx_partial_kernel(const CtxArgs a) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) lg[u] += __shfl_xor_sync(0xffffffffu, lg[u], o);
+            for (int u = 0; u < 8; ++u) lg[u] += __shfl_xor_sync(0xffffffffu, lg[u], o);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (p0 + it * 4 + u >= P) continue;
+        for (int u = 0; u < 8; ++u) {
+            if (p0 + it * 8 + u >= P) continue;
             const float mn = fmaxf(m, lg[u]);
             const float sc = __expf(m - mn), e = __expf(lg[u] - mn);
             z = z * sc + e;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256) ctx_partial_kernel(const CtxArgs a) {
             Z += sm_z[k] * s;
             A += sm_acc[k][threadIdx.x] * s;
         }
-        float* dst = a.partial + L.part_off + ((size_t)b * L.nblk + lbx) * CTX_STRIDE;
+        float* dst = a.partial + part_off + ((size_t)b * nblk + lbx) * CTX_STRIDE;
         if (threadIdx.x == 0) { dst[0] = M; dst[1] = Z; }
         dst[2 + threadIdx.x] = A;
     }
@@ -111,9 +114,9 @@ __global__ void __launch_bounds__(1024) ctx_finalize_kernel(const CtxArgs a, con
     __shared__ float part[16][64];
     __shared__ float ctx[64], hid[64];
     const int l = blockIdx.x / a.B, b = blockIdx.x - l * a.B;
-    const int nblk = a.lv[l].nblk;
+    const int nblk = CTX_SEL(nblk);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const float* pp = a.partial + a.lv[l].part_off + (size_t)b * nblk * CTX_STRIDE;
+    const float* pp = a.partial + CTX_SEL(part_off) + (size_t)b * nblk * CTX_STRIDE;
     float M = -INFINITY;
     for (int k = t; k < nblk; k += 1024) M = fmaxf(M, pp[k * CTX_STRIDE]);
 #pragma unroll
