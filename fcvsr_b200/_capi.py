@@ -26,6 +26,7 @@ SIGNATURES = {
     "fcvsr_fft_c2c_h": "p p p p iiii i f ii p s",
     "fcvsr_fft_c2r_w": "p pi p iiii f s",
     "fcvsr_corr_gather": "piii pi iiii i s",
+    "fcvsr_corr_gather2": "piii ppi iiii i s",
     "fcvsr_offset_blocks": "ppppp pi pppp iiii s",
     "fcvsr_iac_step": "pi pi pi pi pi pi pi ii pi i iii i s",
     "fcvsr_round_copy": "pi pi ii l i s",

@@ -133,7 +133,7 @@ class _Conv2d(torch.autograd.Function):
                 gw = dw.view(k, k, ci, co).permute(3, 2, 0, 1)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 npix = g.shape[0] * g.shape[1] * g.shape[2]
-                scratch = torch.empty(((npix + 255) // 256) * co, device=xh.device, dtype=F32)
+                scratch = torch.empty(((npix + 63) // 64) * co, device=xh.device, dtype=F32)
                 gb = torch.empty(co, device=xh.device, dtype=F32)
                 C.call("fcvsr_colsum", g.data_ptr(), co, co, npix, scratch.data_ptr(), gb.data_ptr(), 0, _st())
         return gx, gw, gb, None, None

@@ -116,7 +116,7 @@ extern "C" int fcvsr_conv2d_wgrad(const float* x, int ldx, const float* dy, int 
 // ------------------------------------------------------------------------------------------------------------------
 // Column sums: out[c] = sum over npix rows of x[row*ldx + c] (bias gradient).  Two deterministic stages: per-block partial
 // sums in `scratch` (nblk x C floats, nblk = fcvsr_colsum_blocks), then one block sums them in fixed order.
-#define CS_ROWS 256
+#define CS_ROWS 64
 // 256 threads = G row groups x Cw channels (Cw = min(C, 256)): group g sums rows r0 + g, r0 + g + G, ... of the block's row
 // range for its channel, the groups are combined through shared memory in fixed order.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ x, int ldx, int C, long long npix,
@@ -140,20 +140,30 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
         __syncthreads();
     }
 }
+// 256 threads = 8 walkers x 32 channels: walker g sums partials g, g + 8, ... of its channel, the walkers are combined in fixed order
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ scratch, int nblk, int C, float* __restrict__ out,
                                                            int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ float red[8][32];
+    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     float s = 0.f;
-    for (int k = 0; k < nblk; ++k) s += scratch[(size_t)k * C + c];
-    out[c] = accumulate ? out[c] + s : s;
+    if (c < C)
+        for (int k = g; k < nblk; k += 8) s += scratch[(size_t)k * C + c];
+    red[g][cl] = s;
+    __syncthreads();
+    if (g == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][cl];
+        out[c] = accumulate ? out[c] + t : t;
+    }
 }
 extern "C" int fcvsr_colsum(const float* x, int ldx, int C, long long npix, float* scratch, float* out, int accumulate,
                             cudaStream_t st) {
     if (!x || !scratch || !out || C <= 0 || npix <= 0) return FCVSR_ERR_ARG;
     const int nblk = (int)((npix + CS_ROWS - 1) / CS_ROWS);
     colsum_partial_kernel<<<nblk, 256, 0, st>>>(x, ldx, C, npix, scratch);
-    colsum_final_kernel<<<(C + 255) / 256, 256, 0, st>>>(scratch, nblk, C, out, accumulate);
+    colsum_final_kernel<<<(C + 31) / 32, 256, 0, st>>>(scratch, nblk, C, out, accumulate);
     return fcvsr_launch_status();
 }
 

@@ -18,39 +18,65 @@
 // CorrBlock gather.  S: [B, P, ldS] floats (P = H*Wf), groups a_off / b_off (float offsets) hold the
 // two spectra.  out: [B, P, ldo], 81 channels.  prod (reference layout [C2][P]) flat index F = p*C2
 // + row*2 + col  ->  ref channel F / P, position F % P.
+// One thread per (position, i) = 9 consecutive output channels j = 0..8 (same column offset, rows y0-4 .. y0+4).  Only positions
+// with x0 <= 5 and y0 <= C2/2 + 3 can hit the 64 x 2 "image" at all: everything else is a plain zero store, without the 64-bit
+// index arithmetic (the first version spent 39 us per launch on it for 9 MB of traffic).  out2 (optional): second copy of
+// the result with the same layout -- the lookup feeds both offset branches (CVSR_freq.py:1487-1488).
 __global__ void corr_gather_kernel(const float* __restrict__ S, int ldS, int a_off, int b_off, void* __restrict__ out,
-                                   int ldo, int H, int Wf, int C2, float inv_sqrt_c, int total, int op_mode) {
+                                   void* __restrict__ out2, int ldo, int H, int Wf, int C2, float inv_sqrt_c, int total,
+                                   int op_mode) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int P = H * Wf;
-    const int o = idx % 81;
-    const int bp = idx / 81;
+    const int i = idx % 9;
+    const int bp = idx / 9;
     const int p = bp % P, b = bp / P;
-    const int i = o / 9, j = o - i * 9;
     const int y0 = p / Wf, x0 = p - y0 * Wf;
-    const int col = x0 + i - 4, row = y0 + j - 4;
-    float v = 0.f;
-    if (col >= 0 && col < 2 && row >= 0 && row < C2 / 2) {
-        const long long F = (long long)p * C2 + row * 2 + col;
-        const int ch = (int)(F / P), p2 = (int)(F - (long long)ch * P);
-        const int half = C2 / 2;
-        const int mi = ch < half ? 2 * ch + 1 : 2 * (ch - half);
-        const float* s = S + ((size_t)b * P + p2) * ldS;
-        v = s[a_off + mi] * s[b_off + mi] * inv_sqrt_c;
+    const int col = x0 + i - 4;
+    const int half = C2 / 2;
+    float v[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) v[j] = 0.f;
+    if (col >= 0 && col < 2 && y0 - 4 < half) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const int row = y0 + j - 4;
+            if (row >= 0 && row < half) {
+                const long long F = (long long)p * C2 + row * 2 + col;
+                const int ch = (int)(F / P), p2 = (int)(F - (long long)ch * P);
+                const int mi = ch < half ? 2 * ch + 1 : 2 * (ch - half);
+                const float* s = S + ((size_t)b * P + p2) * ldS;
+                v[j] = s[a_off + mi] * s[b_off + mi] * inv_sqrt_c;
+            }
+        }
     }
     // op_mode: 0 plain fp32, 1 TF32-rounded fp32, 2 bf16 (the lookup feeds convcorr[0] on the tensor cores)
-    if (op_mode == 0) reinterpret_cast<float*>(out)[((size_t)b * P + p) * ldo + o] = v;
-    else store_operand1(out, ((size_t)b * P + p) * ldo + o, v, op_mode == 2);
+    const size_t o = ((size_t)b * P + p) * ldo + i * 9;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        if (op_mode == 0) {
+            reinterpret_cast<float*>(out)[o + j] = v[j];
+            if (out2) reinterpret_cast<float*>(out2)[o + j] = v[j];
+        } else {
+            store_operand1(out, o + j, v[j], op_mode == 2);
+            if (out2) store_operand1(out2, o + j, v[j], op_mode == 2);
+        }
+    }
+}
+
+extern "C" int fcvsr_corr_gather2(const float* S, int ldS, int a_off, int b_off, void* out, void* out2, int ldo, int B, int H,
+                                  int Wf, int C2, int op_mode, cudaStream_t st) {
+    if (!S || !out || C2 <= 0) return FCVSR_ERR_ARG;
+    const long long total = (long long)B * H * Wf * 9;
+    if (total > 0x7fffffffLL) return FCVSR_ERR_ARG;
+    corr_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, ldS, a_off, b_off, out, out2, ldo, H, Wf, C2,
+                                                                      rsqrtf((float)C2), (int)total, op_mode);
+    return fcvsr_launch_status();
 }
 
 extern "C" int fcvsr_corr_gather(const float* S, int ldS, int a_off, int b_off, void* out, int ldo, int B, int H,
                                  int Wf, int C2, int op_mode, cudaStream_t st) {
-    if (!S || !out || C2 <= 0) return FCVSR_ERR_ARG;
-    const long long total = (long long)B * H * Wf * 81;
-    if (total > 0x7fffffffLL) return FCVSR_ERR_ARG;
-    corr_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, ldS, a_off, b_off, out, ldo, H, Wf, C2,
-                                                                      rsqrtf((float)C2), (int)total, op_mode);
-    return fcvsr_launch_status();
+    return fcvsr_corr_gather2(S, ldS, a_off, b_off, out, nullptr, ldo, B, H, Wf, C2, op_mode, st);
 }
 
 // ------------------------------------------------------------------------------------------------

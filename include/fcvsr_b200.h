@@ -95,6 +95,9 @@ int fcvsr_fft_c2r_w(const float* in_c, float* y, int ldy, const float* tw, int B
  * a_off / b_off (C2 floats each, complex-interleaved); out [B,H*Wf,ldo], 81 channels. */
 int fcvsr_corr_gather(const float* S, int ldS, int a_off, int b_off, void* out, int ldo, int B, int H, int Wf,
                       int C2, int op_mode /* 0 fp32, 1 TF32-rounded, 2 bf16 */, cudaStream_t stream);
+/* same, writing the result to two tensors of the same layout (out2 may be NULL): corr_f feeds both offset branches (:1487-1488) */
+int fcvsr_corr_gather2(const float* S, int ldS, int a_off, int b_off, void* out, void* out2, int ldo, int B, int H, int Wf,
+                       int C2, int op_mode, cudaStream_t stream);
 
 /* ConvBlk(4, index=i) for i < A and both directions (:344-357, :1494-1498):
  * off [2][B][H*Wf][4] (dir-major), w1/w2 packed per iteration [k*k][ci][co] back to back, prelu [A],
@@ -246,7 +249,7 @@ int fcvsr_conv2d_wgrad_tc(const void* x_bf16, int ldx, const void* dy_bf16, int 
  * max(real rows, rows_pad), extra rows zero (thin heads are padded to 16). */
 int fcvsr_pack_conv_weight(const float* w, float* out, int Cout, int Cin, int ksize, int transposed, int rows_pad,
                            cudaStream_t stream);
-/* out[c] (+)= sum over npix rows of x[row*ldx + c] (bias gradient), deterministic; scratch: ceil(npix / 256) * C floats. */
+/* out[c] (+)= sum over npix rows of x[row*ldx + c] (bias gradient), deterministic; scratch: ceil(npix / 64) * C floats. */
 int fcvsr_colsum(const float* x, int ldx, int C, long long npix, float* scratch, float* out, int accumulate, cudaStream_t stream);
 /* flow_warp (CVSR_freq.py:1188-1227) on NHWC maps: y[b,py,px,:] = bilinear(x[b], px + off[b,py,px,0], py + off[b,py,px,1]), zero
  * outside, align_corners=True; C % 4 == 0.  (The inference path fuses this into fcvsr_iac_step.) */
