@@ -29,6 +29,7 @@ SIGNATURES = {
     "fcvsr_corr_gather2": "piii ppi iiii i s",
     "fcvsr_offset_blocks": "ppppp pi pppp iiii s",
     "fcvsr_iac_step": "pi pi pi pi pi pi pi ii pi i iii i s",
+    "fcvsr_iac_step_tc": "pi pi i pi pi pi pi pi ii pi p p iii s",
     "fcvsr_round_copy": "pi pi ii l i s",
     "fcvsr_chansum64": "pi p ii s",
     "fcvsr_reduce_finalize": "p ii f i pp p i s",

@@ -112,6 +112,7 @@ class Engine:
         # that the tools under tools/ can flip them -- nothing in the product path reads the environment
         self.tc_pyramid = True       # rconcat1/2 as stride-1 tcgen05 convs + sampling
         self.iac16 = True            # IAC ping-pong tensors in bf16
+        self.iac_tc = True           # bf16 mode: IAC taps computed on chip (fcvsr_iac_step_tc), no Pred_K tensor
         self.res16 = True            # RCB body output as a bf16 tensor
         self.r016 = True             # RCB input / skip r0 only as a bf16 tensor
         self.rr16 = True             # RCB output rr only as a bf16 tensor
@@ -185,6 +186,12 @@ class Engine:
         ii, tt, cc = torch.meshgrid(torch.arange(A), torch.arange(3), torch.arange(n), indexing="ij")
         rows = (ii * 6 * n + cc * 3 + tt).reshape(-1).to(device)
         P["F1"] = _ConvPack(sd["MGAA.F.1.weight"][rows], sd["MGAA.F.1.bias"][rows], op16=op16)
+        if op16:
+            # the same live rows per iteration as the B operand of fcvsr_iac_step_tc: row c4*12 + t*4 + cc, channel c = 4 c4 + cc
+            ii, gg, tt, cc = torch.meshgrid(torch.arange(A), torch.arange(n // 4), torch.arange(3), torch.arange(4), indexing="ij")
+            rows_tc = (ii * 6 * n + (gg * 4 + cc) * 3 + tt).reshape(-1).to(device)
+            P["F1tc_w"] = sd["MGAA.F.1.weight"][rows_tc].reshape(A, 3 * n, n).to(torch.bfloat16).contiguous()
+            P["F1tc_b"] = sd["MGAA.F.1.bias"][rows_tc].float().reshape(A, 3 * n).contiguous()
         P["conv3"] = cp("MGAA.conv3")
         # --- MFFR (:2104-2133) ---
         for i in range(m.Freq_Inv):
@@ -240,8 +247,12 @@ class Engine:
     # -------------------------------------------------------------------------------------------
     # workspace
     # -------------------------------------------------------------------------------------------
+    def _iac_on_chip(self) -> bool:
+        """bf16 mode with bf16 ping-pong tensors: fcvsr_iac_step_tc computes the taps from kp2 in its own prologue."""
+        return bool(self.op16 and self.iac16 and self.iac_tc and self.model.n_feats == 64)
+
     def _workspace(self, B, H, W, device):
-        key = (B, H, W, str(device))
+        key = (B, H, W, str(device), self._iac_on_chip())
         if key in self._ws:
             return self._ws[key]
         m = self.model
@@ -279,7 +290,8 @@ class Engine:
             buf("kp1" + sfx, B, P, 64, op=True)
             buf("kp2" + sfx, B, P, 64, op=True)
             # per-pixel filter taps (the largest tensor): fp16 in the tensor-core modes (10-bit mantissa = TF32)
-            ws["pk" + sfx] = torch.empty(B, P, A * 192, device=device, dtype=torch.float16 if self.use_tc else F32)
+            if not self._iac_on_chip():
+                ws["pk" + sfx] = torch.empty(B, P, A * 192, device=device, dtype=torch.float16 if self.use_tc else F32)
             buf("ping" + sfx, 2, 2, B, P, 64)
             buf("cat128" + sfx, B, P, 128, op=self.use_tc)
         buf("m2", B, P, 64)
@@ -621,7 +633,9 @@ class Engine:
             x2, ldx2 = p["x2r"], 64
         self._conv(P["kp"], x2, ldx2, p["kp1"], 64, B, H, W, rnd=True)
         self._conv(P["F0"], p["kp1"], 64, p["kp2"], 64, B, H, W, rnd=True)
-        self._conv(P["F1"], p["kp2"], 64, p["pk"], A * 192, B, H, W, rnd=2 if R else False)
+        on_chip = self._iac_on_chip()
+        if not on_chip:
+            self._conv(P["F1"], p["kp2"], 64, p["pk"], A * 192, B, H, W, rnd=2 if R else False)
         TE = 2 if R else 4                                # bytes per tap element
         # IAC (:1526-1527); the last iteration writes the operand-typed conv3 input
         ping = p["ping"]
@@ -634,6 +648,14 @@ class Engine:
             else:
                 nf, nb, ldn = ping + (i % 2) * 2 * sz, ping + ((i % 2) * 2 + 1) * sz, 64
             ro = (2 if O16 else R) if i == A - 1 else (2 if iac16 else 0)     # + 4: prev is a bf16 ping buffer
+            if on_chip:
+                # taps = F.1 slice i of kp2 on tcgen05 inside the IAC kernel (Pred_K never materialised)
+                self.tc_launches += 1
+                self._k("fcvsr_iac_step_tc", prev_f, ldpf, prev_b, ldpb, int(i > 0), src, lds, src + 128 * 4, lds, nf, ldn, nb, ldn,
+                        p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["kp2"], 64, P["F1tc_w"].data_ptr() + i * 192 * 64 * 2,
+                        P["F1tc_b"].data_ptr() + i * 192 * 4, B, H, W)
+                prev_f, ldpf, prev_b, ldpb = nf, ldn, nb, ldn
+                continue
             self._k("fcvsr_iac_step", prev_f, ldpf, prev_b, ldpb, src, lds, src + 128 * 4, lds, nf, ldn, nb, ldn,
                     p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["pk"] + i * 192 * TE, A * 192, R, B, H, W,
                     ro | (4 if (iac16 and i > 0) else 0))

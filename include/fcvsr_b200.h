@@ -117,6 +117,16 @@ int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int l
                    int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const float* taps, int ldtaps,
                    int taps_half, int B, int H, int W, int round_out, cudaStream_t stream);
 
+/* The same IAC iteration with the taps computed on chip (bf16 mode): the iteration's 64 -> 192 slice of the kernel
+ * predictor's last 1x1 convolution (MGAA.F.1, :1522-1523; only rows i*384 + c*3 + t are live, :1231-1235) is one
+ * 128 x 192 x 64 tcgen05 GEMM per 8 x 14 tile, its TMEM accumulator is the tap set, and `Pred_K` never reaches memory.
+ * kp [B,H,W,ldkp] bf16: the F.0 output (64 ch).  w: bf16 [192][64], row c4*12 + t*4 + cc = F.1 row i*384 + (4 c4 + cc)*3 + t;
+ * bias [192] fp32 in the same order.  prev_* fp32 (prev16 = 0) or bf16 (prev16 = 1), ld in elements; next_* bf16. */
+int fcvsr_iac_step_tc(const void* prev_f, int ldprev_f, const void* prev_b, int ldprev_b, int prev16,
+                      const float* xin_f, int ldxin_f, const float* xin_b, int ldxin_b, void* next_f, int ldnext_f,
+                      void* next_b, int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const void* kp,
+                      int ldkp, const void* w, const float* bias, int B, int H, int W, cudaStream_t stream);
+
 /* y[pix,0:Cy] = operand-typed copy (TF32-rounded fp32 or bf16) of x[pix,0:C], channels C..Cy-1 zero: the
  * tensor-core operand copy of a tensor that is also a full-precision residual */
 int fcvsr_round_copy(const float* x, int ldx, void* y, int ldy, int C, int Cy, long long npix, int op16,

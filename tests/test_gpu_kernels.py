@@ -143,6 +143,45 @@ def test_iac_step_kernel(dev, B, H, W, taps_half, prev16, ro):
         assert float((got - want[d]).abs().max()) <= tol, d
 
 
+@pytest.mark.parametrize("B,H,W,prev16", [(1, 19, 37, 0), (2, 8, 14, 1), (1, 25, 18, 1), (2, 33, 45, 0), (1, 7, 13, 1)])
+def test_iac_step_tc_kernel(dev, B, H, W, prev16):
+    """fcvsr_iac_step_tc (taps = MGAA.F.1 slice of kp2 on tcgen05 inside the IAC kernel, CVSR_freq.py:1522-1527) for both
+    directions against oracle.warp_bilinear + oracle.sac with taps from an fp32 matmul of the same bf16 operands: ragged
+    8x14 tiles, images smaller than a tile, offsets leaving the image, fp32 (iteration 0) and bf16 (ping-pong) inputs."""
+    g = torch.Generator().manual_seed(H * W + prev16)
+    prev = [torch.randn(B, 64, H, W, generator=g) for _ in range(2)]
+    xin = [torch.randn(B, 64, H, W, generator=g) for _ in range(2)]
+    off = [3.0 * torch.randn(B, 2, H, W, generator=g) for _ in range(2)]
+    off[1][:, :, H - 1, W - 1] = torch.tensor([70.0, -31.0])
+    kp = _bf16r(torch.randn(B, 64, H, W, generator=g))
+    wt = _bf16r(0.1 * torch.randn(64, 3, 64, generator=g))               # [c][t][k]: reference row c*3 + t
+    bias = 0.2 * torch.randn(64, 3, generator=g)
+    taps = torch.einsum("ctk,bkhw->bcthw", wt, kp) + bias[None, :, :, None, None]        # [B,64,3,H,W]
+    if prev16:
+        prev = [_bf16r(p) for p in prev]
+    want = [F.leaky_relu(O.sac(O.warp_bilinear(prev[d], off[d]), taps.reshape(B, 192, H, W)) + xin[d], 0.1) for d in range(2)]
+    pdt = torch.bfloat16 if prev16 else torch.float32
+    prev_d = [nhwc(p).to(dev).to(pdt) for p in prev]
+    xin_d = [nhwc(t).to(dev) for t in xin]
+    offs_d = torch.zeros(B, H, W, 8, device=dev)
+    offs_d[..., 2:4] = nhwc(off[0]).to(dev)
+    offs_d[..., 6:8] = nhwc(off[1]).to(dev)
+    kp_d = nhwc(kp).to(dev).to(torch.bfloat16)
+    # kernel row order c4*12 + t*4 + cc, channel c = 4 c4 + cc
+    w_d = wt.view(16, 4, 3, 64).permute(0, 2, 1, 3).reshape(192, 64).contiguous().to(dev).to(torch.bfloat16)
+    b_d = bias.view(16, 4, 3).permute(0, 2, 1).reshape(192).contiguous().to(dev)
+    nxt = [torch.empty(B, H, W, 64, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    C.call("fcvsr_iac_step_tc", prev_d[0].data_ptr(), 64, prev_d[1].data_ptr(), 64, prev16, xin_d[0].data_ptr(), 64,
+           xin_d[1].data_ptr(), 64, nxt[0].data_ptr(), 64, nxt[1].data_ptr(), 64, offs_d.data_ptr(), 8, 2, 6, kp_d.data_ptr(), 64,
+           w_d.data_ptr(), b_d.data_ptr(), B, H, W, _st())
+    torch.cuda.synchronize()
+    for d in range(2):
+        got = nchw(nxt[d].float().cpu())
+        scale = max(1.0, float(want[d].abs().max()))
+        # bf16 output rounding; the taps stay fp32 (TMEM accumulator) on the device
+        assert float((got - want[d]).abs().max()) <= (2.0 ** -8 + 2e-4) * scale, d
+
+
 # ------------------------------------------------------------------------------------------------------------------------
 # DivEnh chain + CALayer gates (CVSR_freq.py:2104-2133, :1812-1828, :2201-2254)
 # ------------------------------------------------------------------------------------------------------------------------

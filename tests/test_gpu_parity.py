@@ -152,7 +152,7 @@ def test_conv_tc_reports_unsupported_shapes(dev):
 # model-level parity
 # ------------------------------------------------------------------------------------------------
 def _stage_taps(model, B, H, W, dev):
-    ws = model._engine._ws[(B, H, W, str(dev))]
+    ws = model._engine._workspace(B, H, W, dev)
 
     def tap(t, c0, c1, h, w):
         return nchw(t.view(B, h, w, -1)[..., c0:c1].cpu())

@@ -22,7 +22,7 @@ for (seed, cseed, B, H, W) in ((3, 77, 2, 36, 40), (3, 77, 1, 36, 40), (0, 77, 2
     m.compute_dtype = 'fp32'
     with torch.no_grad():
         y = m(x.to(dev)).cpu()
-    ws = m._engine._ws[(B, H, W, str(dev))]
+    ws = m._engine._workspace(B, H, W, dev)
 
     def tap(t, c0, c1, h, w):
         return t.view(B, h, w, -1)[..., c0:c1].permute(0, 3, 1, 2).cpu()

@@ -26,7 +26,7 @@ def run(seed, cseed, B, H, W):
     m.compute_dtype = 'fp32'
     with torch.no_grad():
         y = m(x.to(dev)).cpu()
-    ws = m._engine._ws[(B, H, W, str(dev))]
+    ws = m._engine._workspace(B, H, W, dev)
     Q = 4
 
     def tap(t, c0, c1, h, w):

@@ -128,7 +128,7 @@ def check_model(variant, H, W, use_tc, B=1, mode=None):
         torch.cuda.synchronize()
     t_gpu = time.time() - t0
     eng = model._engine
-    ws = eng._ws[(B, H, W, str(dev))]
+    ws = eng._workspace(B, H, W, dev)
     P = H * W
 
     def tap(t, c0, c1, h, w):
