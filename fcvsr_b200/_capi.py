@@ -35,8 +35,8 @@ SIGNATURES = {
     "fcvsr_reduce_finalize": "p ii f i pp p i s",
     "fcvsr_divenh_step": "ppppp i ii pppp ppp ii s",
     "fcvsr_mffr_final": "pp pi pi ii s",
-    "fcvsr_context_block": "pi ppp pp ii i s",
-    "fcvsr_context_block_multi": "i pi ppp pp i p i s",
+    "fcvsr_context_block": "pi ppp ppp ii i s",
+    "fcvsr_context_block_multi": "i pi ppp ppp i p i s",
     "fcvsr_rcb_finish_multi": "i ppp ppp pp i iii s",
     "fcvsr_level_mix_multi": "i pi pi p p pp i pp pi iii s",
     "fcvsr_rcb_finish": "ppp p ii p i p ii i i s",

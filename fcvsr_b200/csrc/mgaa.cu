@@ -133,8 +133,9 @@ __global__ void __launch_bounds__(OB_THREADS) offset_blk_conv_kernel(const float
                                                                     int H, int Wf) {
     __shared__ __align__(16) float ws[121 * 16];
     __shared__ float red[OB_THREADS / 32][4];
-    const int it = blockIdx.y, k = 2 * it + 1;
-    const int b = blockIdx.z >> 1, dir = blockIdx.z & 1;
+    // the iteration is the slowest grid dimension, largest kernel first (k = 11 costs 121x k = 1): the light blocks fill the tail
+    const int it = gridDim.z - 1 - blockIdx.z, k = 2 * it + 1;
+    const int bz = blockIdx.y, b = bz >> 1, dir = bz & 1;
     const float* wi = w + ob_woff(it);
     for (int t = threadIdx.x; t < k * k * 16; t += blockDim.x) ws[t] = wi[t];
     __syncthreads();
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(OB_THREADS) offset_blk_conv_kernel(const float
     float sum[4] = {0.f, 0.f, 0.f, 0.f};
     if (q < H * qpr) {
         const int y = q / qpr, x0 = (q - y * qpr) * 4;
-        const int B = gridDim.z >> 1;
+        const int B = gridDim.y >> 1;
         const float* src = in + (SECOND ? (size_t)it * in_iter_stride : 0) + ((size_t)dir * B + b) * P * 4;
         switch (it) {
             case 0: ob_conv_quad<1, SECOND>(src, ws, H, Wf, y, x0, acc); break;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(OB_THREADS) offset_blk_conv_kernel(const float
             float s = 0.f;
             for (int wv = 0; wv < OB_THREADS / 32; ++wv) s += red[wv][threadIdx.x];
             // partial[it][b*2+dir][blk][4]
-            partial[(((size_t)it * gridDim.z + blockIdx.z) * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = s;
+            partial[(((size_t)it * gridDim.y + bz) * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = s;
         }
     }
 }
@@ -246,7 +247,7 @@ extern "C" int fcvsr_offset_blocks(const float* off, const float* w1, const floa
     const int P = H * Wf;
     const int nblk = (P + OB_THREADS - 1) / OB_THREADS;
     const int nqblk = (H * ((Wf + 3) / 4) + OB_THREADS - 1) / OB_THREADS;       // conv blocks: 4 positions per thread (<= nblk)
-    dim3 grid(nblk, A, B * 2), gridq(nqblk, A, B * 2);
+    dim3 grid(nblk, A, B * 2), gridq(nqblk, B * 2, A);
     const size_t iter_stride = (size_t)B * P * 8;
     offset_blk_conv_kernel<false><<<gridq, OB_THREADS, 0, st>>>(off, 0, w1, prelu, t1, iter_stride, nullptr, H, Wf);
     offset_blk_conv_kernel<true><<<gridq, OB_THREADS, 0, st>>>(t1, iter_stride, w2, nullptr, t2, iter_stride, partial, H, Wf);

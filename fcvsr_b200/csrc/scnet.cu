@@ -1,8 +1,9 @@
 // Non-GEMM kernels of the SCNetbk trunk (CVSR_freq.py:657-822).
 //
-//   ctx_partial / ctx_finalize   ContextBlock (:657-701): softmax-over-HW attention pooling done as an
+//   ctx_block                    ContextBlock (:657-701): softmax-over-HW attention pooling done as an
 //                                online-softmax reduction (running max / sum / weighted channel sums
-//                                per block, merged in fixed order) followed by the 64->64->64 MLP.
+//                                per block, merged in fixed order by the last block to finish) followed by
+//                                the 64->64->64 MLP, in one launch.
 //   rcb_finish                   RCB tail (:720-724):  r = lrelu_0.2(res + add_term) + r0
 //   level_mix                    BlockRCB cross-level sum (:766-777):
 //                                x += coef*r + avgpool2(td) + bilinear_x2(tu)
@@ -20,8 +21,10 @@ __device__ __forceinline__ float4 load4_any(const void* base, size_t idx, int b1
     return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
 }
 
-#define CTX_PIX_PER_BLOCK 128
-#define CTX_STRIDE 66          // m, z, acc[64]
+#define CTX_PIX_PER_BLOCK 128   // granularity of the caller's `partial` buffer (upper bound of the block count)
+#define CTX_PPB 256             // pixels per block: 8 warps x 32 pixels per iteration
+#define CTX_STRIDE 66           // m, z, acc[64]
+#define CTX_LOG2E 1.4426950408889634f
 
 #define SC_MAX_LEV 3
 // Every helper below can run the three pyramid levels of a BlockRCB (CVSR_freq.py:766-777) in ONE launch: the levels hold 1, 1/4
@@ -32,162 +35,289 @@ struct CtxArgs { CtxLevel lv[SC_MAX_LEV]; int nlev; int ldx; int ppb; int B; con
 
 #define CTX_SEL(field) (l == 0 ? a.lv[0].field : (l == 1 ? a.lv[1].field : a.lv[2].field))
 
-// One block = ppb pixels (a multiple of 128), 8 warps, 8 pixels in flight per warp (lane owns 2 channels, so a
-// pixel is one coalesced 256-byte load and its logit one 5-step shuffle reduction).  The level descriptor is read field by
-// field with compile-time indices: indexing the kernel parameters with a run-time level copies them to local memory.
+__device__ __forceinline__ float ctx_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <bool X16>
-__global__ void __launch_bounds__(256) ctx_partial_kernel(const CtxArgs a) {
+__device__ __forceinline__ void ctx_unpack(const uint4& r, const float (&v)[8], float (&f)[8]) {
+    if (X16) {
+        f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+        f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+        f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
+        f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = v[j];
+    }
+}
+
+#define CTX_MAX_NBLK 4096
+// ContextBlock in ONE kernel.  A block reduces ppb pixels (a multiple of 256) of one (level, image) to an online-softmax
+// partial (running max m, sum z, weighted channel sums acc[64]); the LAST block of a (level, image) to finish -- found with a
+// counter that it resets, so the launch can be replayed from a CUDA graph -- merges the partials in index order (deterministic)
+// and applies the 64 -> 64 -> 64 MLP.  No second launch: the finalize of one image overlaps the pooling of the others.
+//
+// Pooling pass (the first version of this kernel was issue-bound at 1.7 TB/s: a lane owned 2 channels, so every pixel cost a
+// 5-step shuffle reduction and an online-softmax update with two exponentials): a lane owns 8 channels (one 16-byte load of a
+// bf16 tensor), so 8 lanes cover a pixel, a warp load covers 4 pixels and 8 loads are in flight per lane; the logit needs 3
+// shuffle steps per FOUR pixels; the soft-max state (m, z, acc) is kept per 8-lane group and rescaled once per 8 pixels (the
+// groups are merged once, at the end); logits are pre-scaled by log2(e) so that an exponential is one ex2.approx.
+template <bool X16>
+__global__ void __launch_bounds__(256, X16 ? 3 : 2) ctx_block_kernel(const CtxArgs a, const float* __restrict__ w1, const float* __restrict__ w2,
+                                                           float* __restrict__ add, unsigned* __restrict__ counters) {
     __shared__ float sm_m[8], sm_z[8];
     __shared__ float sm_acc[8][64];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y, c = 2 * lane;
+    __shared__ float esc[CTX_MAX_NBLK];
+    __shared__ float part[8][64];
+    __shared__ float ctx[64], hid[64];
+    __shared__ float red[8];
+    __shared__ int is_last;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, b = blockIdx.y;
+    const int sub = lane >> 3, oct = lane & 7;
     const int bx = blockIdx.x;
     const int l = (a.nlev > 1 && bx >= a.lv[1].blk_begin) ? ((a.nlev > 2 && bx >= a.lv[2].blk_begin) ? 2 : 1) : 0;
     const int P = CTX_SEL(P), ppb = a.ppb, ldx = a.ldx, lbx = bx - CTX_SEL(blk_begin), nblk = CTX_SEL(nblk);
     const long long part_off = CTX_SEL(part_off);
-    const float* x = reinterpret_cast<const float*>(CTX_SEL(x));
-    const float2 w = *reinterpret_cast<const float2*>(a.wmask + c);
+    const void* xv = CTX_SEL(x);
+    // conv_mask weights x log2(e) in shared memory (8 registers that the packed-load variant does not have)
+    __shared__ __align__(16) float wsm[64];
+    if (t < 64) wsm[t] = a.wmask[t] * CTX_LOG2E;
+    __syncthreads();
     float m = -INFINITY, z = 0.f;
-    float2 acc = make_float2(0.f, 0.f);
-    const int p0 = lbx * ppb + warp * (ppb >> 3);        // ppb pixels per block (multiple of 128), 1/8 per warp
-    const float* xb = x + (size_t)b * P * ldx + c;
-    const unsigned short* xb16 = reinterpret_cast<const unsigned short*>(x) + (size_t)b * P * ldx + c;   // x16: bf16 tensor
-    for (int it = 0; it < (ppb >> 6); ++it) {
-        float2 v[8];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int per_warp = ppb >> 3;                          // multiple of 32
+    const int p0 = lbx * ppb + warp * per_warp + sub;
+    const size_t img = (size_t)b * P * ldx + oct * 8;
+    for (int it = 0; it < per_warp; it += 32) {
+        // X16: the eight 16-byte loads stay packed (32 registers) and are unpacked where they are used, once for the logit and once
+        // for the weighted sums -- 16 more ALU instructions per pixel, but three blocks per SM instead of two (the kernel is bound
+        // by bytes in flight, not by issue slots)
+        uint4 raw[X16 ? 8 : 1];
+        float v[X16 ? 1 : 8][8];
         float lg[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int p = p0 + it * 8 + u;
-            if (X16) {       // compile-time: the eight loads of an iteration stay back to back
-                const uint32_t w2 = p < P ? *reinterpret_cast<const uint32_t*>(xb16 + (size_t)p * ldx) : 0u;
-                v[u] = make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u));
+            const int p = p0 + it + 4 * u;
+            if (X16) {
+                raw[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (p < P) raw[u] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(xv) + img + (size_t)p * ldx));
             } else {
-                v[u] = p < P ? *reinterpret_cast<const float2*>(xb + (size_t)p * ldx) : make_float2(0.f, 0.f);
+                float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+                if (p < P) {
+                    const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xv) + img + (size_t)p * ldx);
+                    r0 = __ldg(src); r1 = __ldg(src + 1);
+                }
+                v[u][0] = r0.x; v[u][1] = r0.y; v[u][2] = r0.z; v[u][3] = r0.w;
+                v[u][4] = r1.x; v[u][5] = r1.y; v[u][6] = r1.z; v[u][7] = r1.w;
             }
-            lg[u] = v[u].x * w.x + v[u].y * w.y;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) lg[u] += __shfl_xor_sync(0xffffffffu, lg[u], o);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (p0 + it * 8 + u >= P) continue;
-            const float mn = fmaxf(m, lg[u]);
-            const float sc = __expf(m - mn), e = __expf(lg[u] - mn);
-            z = z * sc + e;
-            acc.x = acc.x * sc + e * v[u].x;
-            acc.y = acc.y * sc + e * v[u].y;
-            m = mn;
+            float f[8];
+            ctx_unpack<X16>(raw[X16 ? u : 0], v[X16 ? 0 : u], f);
+            const float4 wa = *reinterpret_cast<const float4*>(wsm + oct * 8), wb = *reinterpret_cast<const float4*>(wsm + oct * 8 + 4);
+            lg[u] = fmaf(f[7], wb.w, fmaf(f[6], wb.z, fmaf(f[5], wb.y, fmaf(f[4], wb.x,
+                    fmaf(f[3], wa.w, fmaf(f[2], wa.z, fmaf(f[1], wa.y, f[0] * wa.x)))))));
         }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) lg[u] += __shfl_xor_sync(0xffffffffu, lg[u], o);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (p0 + it + 4 * u >= P) lg[u] = -INFINITY;
+            mx = fmaxf(mx, lg[u]);
+        }
+        const float mn = fmaxf(m, mx);
+        const float ms = mn == -INFINITY ? 0.f : mn;        // no valid pixel yet: every exponential below is ex2(-inf) = 0
+        const float sc = ctx_ex2(m - ms);
+        z *= sc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= sc;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float e = ctx_ex2(lg[u] - ms);
+            z += e;
+            float f[8];
+            ctx_unpack<X16>(raw[X16 ? u : 0], v[X16 ? 0 : u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(e, f[j], acc[j]);
+        }
+        m = mn;
+    }
+    // merge the four 8-lane groups of the warp (lanes oct, oct + 8, oct + 16, oct + 24 hold the same channels)
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, o), zo = __shfl_xor_sync(0xffffffffu, z, o);
+        const float mn = fmaxf(m, mo);
+        const float ms = mn == -INFINITY ? 0.f : mn;
+        const float s1 = ctx_ex2(m - ms), s2 = ctx_ex2(mo - ms);
+        z = z * s1 + zo * s2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = acc[j] * s1 + __shfl_xor_sync(0xffffffffu, acc[j], o) * s2;
+        m = mn;
     }
     if (lane == 0) { sm_m[warp] = m; sm_z[warp] = z; }
-    sm_acc[warp][c] = acc.x; sm_acc[warp][c + 1] = acc.y;
+    if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm_acc[warp][oct * 8 + j] = acc[j];
+    }
     __syncthreads();
-    if (threadIdx.x < 64) {
+    if (t < 64) {
         float M = -INFINITY;
 #pragma unroll
         for (int k = 0; k < 8; ++k) M = fmaxf(M, sm_m[k]);
+        const float Ms = M == -INFINITY ? 0.f : M;
         float Z = 0.f, A = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float s = sm_m[k] == -INFINITY ? 0.f : __expf(sm_m[k] - M);
+            const float s = ctx_ex2(sm_m[k] - Ms);
             Z += sm_z[k] * s;
-            A += sm_acc[k][threadIdx.x] * s;
+            A += sm_acc[k][t] * s;
         }
         float* dst = a.partial + part_off + ((size_t)b * nblk + lbx) * CTX_STRIDE;
-        if (threadIdx.x == 0) { dst[0] = M; dst[1] = Z; }
-        dst[2 + threadIdx.x] = A;
+        if (t == 0) { dst[0] = M; dst[1] = Z; }
+        dst[2 + t] = A;
+        __threadfence();
     }
-}
-
-// grid nlev * B, 1024 threads: merge the block partials of one (level, image) in fixed order -> context[64] ->
-// add = W2 lrelu_0.2(W1 ctx).  The kernel is pure latency (a few CTAs on the whole GPU), so every stage is one round of
-// independent loads: warp-shuffle reductions for max / sum, the per-partial scale exp(m_k - M) computed once into shared
-// memory, 16 thread groups x 64 channels walking the partial list with 8 loads in flight, and the two 64x64 mat-vecs done
-// one warp per output row (coalesced 256-byte row reads + shuffle reduction).
-#define CTX_MAX_NBLK 4096
-__global__ void __launch_bounds__(1024) ctx_finalize_kernel(const CtxArgs a, const float* __restrict__ w1,
-                                                            const float* __restrict__ w2, float* __restrict__ add) {
-    __shared__ float red[32];
-    __shared__ float esc[CTX_MAX_NBLK];
-    __shared__ float part[16][64];
-    __shared__ float ctx[64], hid[64];
-    const int l = blockIdx.x / a.B, b = blockIdx.x - l * a.B;
-    const int nblk = CTX_SEL(nblk);
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const float* pp = a.partial + CTX_SEL(part_off) + (size_t)b * nblk * CTX_STRIDE;
-    float M = -INFINITY;
-    for (int k = t; k < nblk; k += 1024) M = fmaxf(M, pp[k * CTX_STRIDE]);
+    __syncthreads();
+    unsigned* cnt = counters + l * a.B + b;
+    if (t == 0) {
+        const unsigned prev = atomicAdd(cnt, 1u);
+        is_last = prev == (unsigned)(nblk - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- finalize (one block per (level, image)): merge the partials in index order -> context[64] -> add = W2 lrelu_0.2(W1 ctx).
+    // A chain of dependent L2 round trips that runs after the last pooling block, so it is kept short: the MLP weights are
+    // requested first (thread = (row t >> 2, 16 columns)), (m, z) of a partial come with one 8-byte load and stay in registers
+    // when there are at most 256 partials, and the channel sums are walked by 8 thread groups with 8 loads in flight.
+    float4 wr1[4], wr2[4];
+    {
+        const float4* a1 = reinterpret_cast<const float4*>(w1 + (t >> 2) * 64 + (t & 3) * 16);
+        const float4* a2 = reinterpret_cast<const float4*>(w2 + (t >> 2) * 64 + (t & 3) * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { wr1[j] = __ldg(a1 + j); wr2[j] = __ldg(a2 + j); }
+    }
+    const float* pp = a.partial + part_off + (size_t)b * nblk * CTX_STRIDE;
+    float2 mz0 = make_float2(-INFINITY, 0.f);
+    if (t < nblk) mz0 = __ldcg(reinterpret_cast<const float2*>(pp + t * CTX_STRIDE));
+    float M = mz0.x;
+    for (int k = t + 256; k < nblk; k += 256) M = fmaxf(M, __ldcg(pp + k * CTX_STRIDE));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
     if (lane == 0) red[warp] = M;
     __syncthreads();
-    M = red[lane];
+    M = red[lane & 7];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    for (int o = 4; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
     __syncthreads();
     float Z = 0.f;
-    for (int k = t; k < nblk; k += 1024) {
-        const float e = __expf(pp[k * CTX_STRIDE] - M);
+    if (t < nblk) {
+        const float e = ctx_ex2(mz0.x - M);
+        esc[t] = e;
+        Z = mz0.y * e;
+    }
+    for (int k = t + 256; k < nblk; k += 256) {
+        const float2 mz = __ldcg(reinterpret_cast<const float2*>(pp + k * CTX_STRIDE));
+        const float e = ctx_ex2(mz.x - M);
         esc[k] = e;
-        Z += pp[k * CTX_STRIDE + 1] * e;
+        Z += mz.y * e;
     }
     // fixed-order (deterministic) tree: lanes, then warps
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
     if (lane == 0) red[warp] = Z;
     __syncthreads();
-    Z = red[lane];
+    Z = red[lane & 7];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
-    const int c = t & 63, q = t >> 6;
-    float A = 0.f;
-    int k = q;
-    for (; k + 112 < nblk; k += 128) {
-        float av[8];
+    for (int o = 4; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
+    {
+        const int c2 = (t & 31) * 2, q = t >> 5;          // 8 groups (warps), a lane owns 2 channels
+        float2 A = make_float2(0.f, 0.f);
+        int k = q;
+        for (; k + 56 < nblk; k += 64) {
+            float2 av[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) av[u] = pp[(k + 16 * u) * CTX_STRIDE + 2 + c];
+            for (int u = 0; u < 8; ++u) av[u] = __ldcg(reinterpret_cast<const float2*>(pp + (k + 8 * u) * CTX_STRIDE + 2 + c2));
 #pragma unroll
-        for (int u = 0; u < 8; ++u) A += av[u] * esc[k + 16 * u];
+            for (int u = 0; u < 8; ++u) { const float e = esc[k + 8 * u]; A.x = fmaf(av[u].x, e, A.x); A.y = fmaf(av[u].y, e, A.y); }
+        }
+        for (; k < nblk; k += 8) {
+            const float2 av = __ldcg(reinterpret_cast<const float2*>(pp + k * CTX_STRIDE + 2 + c2));
+            const float e = esc[k];
+            A.x = fmaf(av.x, e, A.x); A.y = fmaf(av.y, e, A.y);
+        }
+        part[q][c2] = A.x; part[q][c2 + 1] = A.y;
     }
-    for (; k < nblk; k += 16) A += pp[k * CTX_STRIDE + 2 + c] * esc[k];
-    part[q][c] = A;
     __syncthreads();
     if (t < 64) {
-        float s = 0.f;
+        float sacc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) s += part[j][t];
-        ctx[t] = s / Z;
+        for (int j = 0; j < 8; ++j) sacc += part[j][t];
+        ctx[t] = sacc / Z;
     }
     __syncthreads();
-    for (int r = warp; r < 64; r += 32) {            // hid[r] = lrelu_0.2(W1[r,:] . ctx)
-        float h = w1[r * 64 + lane] * ctx[lane] + w1[r * 64 + 32 + lane] * ctx[32 + lane];
+    {   // hid[r] = lrelu_0.2(W1[r,:] . ctx): thread = (row t >> 2, columns (t & 3) * 16 ..), two shuffle steps
+        const float* cv = ctx + (t & 3) * 16;
+        float h = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-        if (lane == 0) hid[r] = h >= 0.f ? h : 0.2f * h;
+        for (int j = 0; j < 4; ++j)
+            h += wr1[j].x * cv[4 * j] + wr1[j].y * cv[4 * j + 1] + wr1[j].z * cv[4 * j + 2] + wr1[j].w * cv[4 * j + 3];
+        h += __shfl_xor_sync(0xffffffffu, h, 1);
+        h += __shfl_xor_sync(0xffffffffu, h, 2);
+        if ((t & 3) == 0) hid[t >> 2] = h >= 0.f ? h : 0.2f * h;
     }
     __syncthreads();
-    for (int r = warp; r < 64; r += 32) {            // add[r] = W2[r,:] . hid
-        float o2 = w2[r * 64 + lane] * hid[lane] + w2[r * 64 + 32 + lane] * hid[32 + lane];
+    {   // add[r] = W2[r,:] . hid
+        const float* hv = hid + (t & 3) * 16;
+        float o2 = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) o2 += __shfl_xor_sync(0xffffffffu, o2, o);
-        if (lane == 0) add[(size_t)blockIdx.x * 64 + r] = o2;
+        for (int j = 0; j < 4; ++j)
+            o2 += wr2[j].x * hv[4 * j] + wr2[j].y * hv[4 * j + 1] + wr2[j].z * hv[4 * j + 2] + wr2[j].w * hv[4 * j + 3];
+        o2 += __shfl_xor_sync(0xffffffffu, o2, 1);
+        o2 += __shfl_xor_sync(0xffffffffu, o2, 2);
+        if ((t & 3) == 0) add[((size_t)l * a.B + b) * 64 + (t >> 2)] = o2;
     }
+    if (t == 0) *cnt = 0u;                           // ready for the next launch / graph replay
 }
 
 // x: HOST array of nlev device pointers ([B,P_l,ldx] tensors), P: HOST array; partial: sum_l B*ceil(P_l/128)*66 floats;
-// add: [nlev][B][64].
+// add: [nlev][B][64]; counters: nlev*B unsigned ints, zero before the first call (the kernel leaves them zero).
 extern "C" int fcvsr_context_block_multi(int nlev, const void* const* x, int ldx, const float* wmask, const float* w1,
-                                         const float* w2, float* partial, float* add, int B, const int* P, int x_bf16,
+                                         const float* w2, float* partial, float* add, int* counters, int B, const int* P, int x_bf16,
                                          cudaStream_t st) {
-    if (nlev < 1 || nlev > SC_MAX_LEV || !x || !P || !wmask || !w1 || !w2 || !partial || !add || (ldx & 1) || B <= 0) return FCVSR_ERR_ARG;
+    if (nlev < 1 || nlev > SC_MAX_LEV || !x || !P || !wmask || !w1 || !w2 || !partial || !add || !counters || (ldx & 7) || B <= 0)
+        return FCVSR_ERR_ARG;
     CtxArgs a;
     a.nlev = nlev; a.ldx = ldx; a.B = B; a.wmask = wmask; a.partial = partial;
-    // 128 pixels per block (as sized by the caller's `partial` buffer) unless that needs more than CTX_MAX_NBLK blocks
-    int ppb = CTX_PIX_PER_BLOCK, pmax = 0;
-    for (int l = 0; l < nlev; ++l) { if (!x[l] || P[l] <= 0) return FCVSR_ERR_ARG; pmax = P[l] > pmax ? P[l] : pmax; }
-    while ((pmax + ppb - 1) / ppb > CTX_MAX_NBLK) ppb += CTX_PIX_PER_BLOCK;
+    // Pixels per block: a multiple of 256, sized so that the launch is about one wave of three blocks per SM -- a block's fixed
+    // costs (launch, fence + counter round trip) are ~3 us, as long as the pooling of 256 pixels -- and so that no level needs
+    // more than CTX_MAX_NBLK blocks (the caller's `partial` buffer is sized for 128 pixels per block, an upper bound)
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    int pmax = 0;
+    long long ptot = 0;
+    for (int l = 0; l < nlev; ++l) {
+        if (!x[l] || P[l] <= 0 || ((uintptr_t)x[l] & 15)) return FCVSR_ERR_ARG;
+        pmax = P[l] > pmax ? P[l] : pmax;
+        ptot += (long long)B * P[l];
+    }
+    int ppb = CTX_PPB * (int)((ptot + 3LL * num_sms * CTX_PPB - 1) / (3LL * num_sms * CTX_PPB));
+    if (ppb > 16 * CTX_PPB) ppb = 16 * CTX_PPB;
+    while ((pmax + ppb - 1) / ppb > CTX_MAX_NBLK) ppb += CTX_PPB;
     a.ppb = ppb;
     int blk = 0;
     long long off = 0;
@@ -197,17 +327,16 @@ extern "C" int fcvsr_context_block_multi(int nlev, const void* const* x, int ldx
         a.lv[l].blk_begin = blk; a.lv[l].part_off = off;
         if (l < nlev) { blk += a.lv[l].nblk; off += (long long)B * ((P[j] + CTX_PIX_PER_BLOCK - 1) / CTX_PIX_PER_BLOCK) * CTX_STRIDE; }
     }
-    if (x_bf16) ctx_partial_kernel<true><<<dim3(blk, B), 256, 0, st>>>(a);
-    else ctx_partial_kernel<false><<<dim3(blk, B), 256, 0, st>>>(a);
-    ctx_finalize_kernel<<<nlev * B, 1024, 0, st>>>(a, w1, w2, add);
+    if (x_bf16) ctx_block_kernel<true><<<dim3(blk, B), 256, 0, st>>>(a, w1, w2, add, reinterpret_cast<unsigned*>(counters));
+    else ctx_block_kernel<false><<<dim3(blk, B), 256, 0, st>>>(a, w1, w2, add, reinterpret_cast<unsigned*>(counters));
     return fcvsr_launch_status();
 }
 
 extern "C" int fcvsr_context_block(const void* x, int ldx, const float* wmask, const float* w1, const float* w2,
-                                   float* partial, float* add, int B, int P, int x_bf16, cudaStream_t st) {
+                                   float* partial, float* add, int* counters, int B, int P, int x_bf16, cudaStream_t st) {
     if (!x) return FCVSR_ERR_ARG;
     const void* xs[1] = {x};
-    return fcvsr_context_block_multi(1, xs, ldx, wmask, w1, w2, partial, add, B, &P, x_bf16, st);
+    return fcvsr_context_block_multi(1, xs, ldx, wmask, w1, w2, partial, add, counters, B, &P, x_bf16, st);
 }
 
 // ---- RCB tail (:720-724): r = lrelu_0.2(res + add[b]) + r0, all 64 channels, float4 per thread ----------------------------

@@ -316,6 +316,7 @@ class Engine:
             buf(f"tu{l}", B, p, 64)
         buf("ctxall", sum(B * ((h * w + 127) // 128) * 66 for h, w in dims))       # ContextBlock partials of the three levels
         buf("addall", 3, B, 64)
+        ws["ctxcnt"] = torch.zeros(3 * B, device=device, dtype=torch.int32)      # per (level, image) block counters, self-resetting
         p2, p3 = dims[1][0] * dims[1][1], dims[2][0] * dims[2][1]
         buf("o2", B, p2, 64, op=self.use_tc)
         buf("o3", B, p3, 64, op=self.use_tc)
@@ -740,9 +741,8 @@ class Engine:
                 # res (RCB body output, consumed by the ContextBlock and the RCB tail only) is a bf16 tensor in bf16 mode
                 res = [p[f"res{l}"] for l in L3]
                 self._conv_multi(P[q + "r2"], [p[f"c1{l}"] for l in L3], 64, res, 64, B, dims, rnd=bool(res16))
-                self.launches += 1
                 self._k("fcvsr_context_block_multi", 3, vp(*res), 64, P[q + "mask"].data_ptr(), P[q + "a0"].data_ptr(),
-                        P[q + "a2"].data_ptr(), p["ctxall"], p["addall"], B, P3, res16)
+                        P[q + "a2"].data_ptr(), p["ctxall"], p["addall"], p["ctxcnt"], B, P3, res16)
                 self._k("fcvsr_rcb_finish_multi", 3, vp(*res), vp(*adds), vp(*[p[f"r0h{l}"] if r016 else p[f"r0{l}"] for l in L3]),
                         vp(*[0 if rr16 else p[f"rr{l}"] for l in L3]),
                         vp(*[p[f"rrh{l}"] if (R and (l > 0 or rr16)) else 0 for l in L3]),

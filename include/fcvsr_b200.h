@@ -148,10 +148,13 @@ int fcvsr_mffr_final(const float* so, const float* gate, const float* x, int ldx
 
 /* ---- SCNetbk helpers (CVSR_freq.py:657-777) ----------------------------------------------------- */
 
-/* ContextBlock (:657-701): add[b][64] = W2 lrelu_0.2(W1 softmax-pool(x)); partial [B][ceil(P/128)][66].
- * x_bf16 = 1: x is a bf16 tensor (ld in elements) -- the bf16 mode stores the RCB's second conv output that way. */
+/* ContextBlock (:657-701): add[b][64] = W2 lrelu_0.2(W1 softmax-pool(x)); partial [B][ceil(P/128)][66] (scratch).
+ * x_bf16 = 1: x is a bf16 tensor (ld in elements, a multiple of 8; x 16-byte aligned) -- the bf16 mode stores the RCB's second
+ * conv output that way.  counters: B ints of scratch that must be ZERO before the first call; the kernel leaves them zero
+ * (the last block of an image to finish merges the partials and resets its counter, so the launch replays from a CUDA graph).
+ * Two launches that share `counters` / `partial` must not run concurrently. */
 int fcvsr_context_block(const void* x, int ldx, const float* wmask, const float* w1, const float* w2,
-                        float* partial, float* add, int B, int P, int x_bf16, cudaStream_t stream);
+                        float* partial, float* add, int* counters, int B, int P, int x_bf16, cudaStream_t stream);
 /* RCB tail (:720-724): r = lrelu_0.2(res + add[b]) + r0 (64 ch, ld 64).  r_pool (optional, needs even H, W with
  * H*W == P): 2x2 mean of r, [B,H/2,W/2,64], operand-typed or plain fp32 (pool_plain) -- the input of the 1x1 `down`
  * convolution, which commutes with the reference's Interpolate(0.5) (:753-757).  res_bf16: bit 0 = res is a bf16 tensor, bit 1 = r0 is. */
@@ -167,9 +170,10 @@ int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const void*
 
 /* The three SCNet helpers over up to three pyramid levels in one launch (same weights / flags for every level; pointer
  * arguments are HOST arrays of nlev device pointers, H / W / P / coef HOST arrays).  partial: sum over levels of
- * B*ceil(P_l/128)*66 floats; add: [nlev][B][64].  NULL entries in r / r_op / r_pool / td / tu / xout_r skip that output or term. */
+ * B*ceil(P_l/128)*66 floats; add: [nlev][B][64]; counters: nlev*B zeroed ints (see fcvsr_context_block).  NULL entries in
+ * r / r_op / r_pool / td / tu / xout_r skip that output or term. */
 int fcvsr_context_block_multi(int nlev, const void* const* x, int ldx, const float* wmask, const float* w1, const float* w2,
-                              float* partial, float* add, int B, const int* P, int x_bf16, cudaStream_t stream);
+                              float* partial, float* add, int* counters, int B, const int* P, int x_bf16, cudaStream_t stream);
 int fcvsr_rcb_finish_multi(int nlev, const void* const* res, const float* const* add, const void* const* r0, float* const* r,
                            void* const* r_op, void* const* r_pool, const int* H, const int* W, int B, int op16, int pool_plain,
                            int res_bf16, cudaStream_t stream);

@@ -688,8 +688,11 @@ def test_scnet_helpers_bf16_inputs(dev, b16):
     part = torch.zeros(B * nblk * 66, device=dev)
     add = torch.zeros(B, 64, device=dev)
     wm_d, w1_d, w2_d = wm.to(dev), w1.to(dev), w2.to(dev)
-    C.call("fcvsr_context_block", res_d.data_ptr(), 64, wm_d.data_ptr(), w1_d.data_ptr(), w2_d.data_ptr(),
-           part.data_ptr(), add.data_ptr(), B, P, b16, _st())
+    cnt = torch.zeros(B, device=dev, dtype=torch.int32)
+    for _ in range(2):          # twice: the block counters reset themselves
+        C.call("fcvsr_context_block", res_d.data_ptr(), 64, wm_d.data_ptr(), w1_d.data_ptr(), w2_d.data_ptr(),
+               part.data_ptr(), add.data_ptr(), cnt.data_ptr(), B, P, b16, _st())
+    assert int(cnt.abs().sum()) == 0
     att = torch.softmax(res @ wm, dim=1)                                   # [B,P]
     ctx = torch.einsum("bp,bpc->bc", att, res)
     add_ref = F.leaky_relu(ctx @ w1.t(), 0.2) @ w2.t()

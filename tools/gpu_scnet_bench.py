@@ -35,8 +35,9 @@ for (H, W) in ((180, 320), (90, 160), (46, 80)):
     add = f(B, 64)
     wm, w1, w2 = f(64), f(64, 64), f(64, 64)
     part = torch.empty(B * ((P + 127) // 128) * 66, device=dev)
+    cnt = torch.zeros(B, device=dev, dtype=torch.int32)
     MB = B * P * 64 * 4 / 1e6
-    t = timeit(lambda: C.call("fcvsr_context_block", res.data_ptr(), 64, wm.data_ptr(), w1.data_ptr(), w2.data_ptr(), part.data_ptr(), add.data_ptr(), B, P, 0, st))
+    t = timeit(lambda: C.call("fcvsr_context_block", res.data_ptr(), 64, wm.data_ptr(), w1.data_ptr(), w2.data_ptr(), part.data_ptr(), add.data_ptr(), cnt.data_ptr(), B, P, 0, st))
     line = f"B{B} {H}x{W}: context {t:6.1f} us {MB / t * 1e3:6.0f} GB/s"
     t = timeit(lambda: C.call("fcvsr_rcb_finish", res.data_ptr(), add.data_ptr(), r0.data_ptr(), rr.data_ptr(), B, P, rrh.data_ptr(), 1, 0, 0, 0, 0, 0, st))
     line += f" | rcb_finish {t:6.1f} us {3.5 * MB / t * 1e3:6.0f} GB/s"
