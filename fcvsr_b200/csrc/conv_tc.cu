@@ -41,6 +41,8 @@
 #define TC_ROW_BYTES 128
 #define TC_A_COPY_BYTES ((TC_TH + 2) * TC_TW * TC_ROW_BYTES)      // 20480
 #define TC_A_STAGE_BYTES (3 * TC_A_COPY_BYTES)                    // 61440
+#define TC_STG_BYTES (TC_TH * TC_TW * TC_ROW_BYTES)               // 16384: one staged output tile
+#define TC_SMEM_LIMIT 232448                                      // 227 KB of dynamic shared memory per CTA
 
 #define TC_EPI_WARPS 16                 // epilogue warps: TC_EPI_WARPS / 4 per TMEM lane quarter, each a share of the columns
 #define TC_THREADS (32 * (3 + TC_EPI_WARPS))
@@ -80,6 +82,8 @@ struct ConvTcParams {
     int act; float slope; const float* slope_ptr; int ps;
     int wide;                            // 32-byte aligned tensors: use 256-bit loads / stores in the epilogue
     int epi_sets;                        // 1, 2 or 4 epilogue warp sets (see the epilogue)
+    int b_ring_bytes;                    // weight ring size (TC_B_RING_BYTES, or less when the output staging tiles take the space)
+    int stage_out;                       // output tile staged in shared memory and written with one TMA store per tile
     int* err;
     int dbg;                             // bring-up only (FCVSR_TC_DBG): 1 no MMA, 2 no A loads, 4 no B loads, 8 no stores
 };
@@ -99,7 +103,9 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const ConvTcParams& p) {
 template <int KS, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x1,
-               const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_w, const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y1,
+               const __grid_constant__ CUtensorMap map_y2, const ConvTcParams p) {
     // Programmatic dependent launch: let the next convolution's CTAs take each SM as soon as this grid's CTA leaves it
     // and run their prologue (barriers, TMEM, bias, first weight stages) while the rest of this grid drains; everything
     // that touches activations sits behind griddepcontrol.wait (a no-op for a normally serialized launch).
@@ -108,7 +114,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* a_buf = smem;                                        // TC_NA x 61440
     uint8_t* b_buf = smem + TC_NA * TC_A_STAGE_BYTES;             // weight ring, TC_B_RING_BYTES
-    uint64_t* bars = (uint64_t*)(b_buf + TC_B_RING_BYTES);
+    // output staging: one [128 pixels][128 B] SWIZZLE_128B tile per epilogue set (bf16 outputs with 64 channels)
+    uint8_t* stg_buf = b_buf + p.b_ring_bytes;
+    uint64_t* bars = (uint64_t*)(stg_buf + (p.stage_out ? p.epi_sets * TC_STG_BYTES : 0));
     uint64_t* full_a = bars;                // [TC_NA_MAX]
     uint64_t* empty_a = bars + TC_NA_MAX;   // [TC_NA_MAX]
     uint64_t* full_b = bars + 2 * TC_NA_MAX;            // [TC_NB_MAX]
@@ -133,7 +141,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t a_copy_bytes = (uint32_t)nrows * TC_TW * TC_ROW_BYTES;
     const uint32_t b_bytes = (uint32_t)p.n_tile * TC_ROW_BYTES;      // multiple of 2048 (n_tile % 16 == 0): stays 1024-aligned
     const uint32_t b_stage_bytes = b_bytes * KS;                    // one filter row of taps per stage
-    const int nb_stages = min(TC_NB_MAX, (int)(TC_B_RING_BYTES / b_stage_bytes));
+    const int nb_stages = min(TC_NB_MAX, (int)((uint32_t)p.b_ring_bytes / b_stage_bytes));
     // Weights resident: with a single N pass and every (K chunk, filter row) stage fitting in the ring at once, the
     // stages are loaded once per CTA and never released (bf16 64->64 3x3: 72 KB).  ncu showed the L2->SM read path
     // at 97 % of peak with the weights re-streamed per tile; this halves that traffic for the most common shape.
@@ -291,6 +299,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const float slope = p.act == FCVSR_ACT_PRELU ? p.slope_ptr[0] : p.slope;
         const int c4 = p.Cout >> 2;
         int acc = 0; uint32_t pacc = 0;
+        // Staged output (p.stage_out): a lane's direct stores touch 32 different lines per instruction, and the LSU retires them
+        // at about one line per 3 clk while the tensor core's operand fetches own the shared-memory pipe -- as long as the
+        // tile's MMAs.  Instead the set writes the tile into a [128 pixels][128 B] SWIZZLE_128B buffer (conflict-free 16-byte
+        // shared stores) and one elected thread hands it to the TMA unit, which writes whole lines and clips at the image border.
+        const bool stg = p.stage_out != 0;
+        const uint32_t srow = smem_u32(stg_buf + eset * TC_STG_BYTES) + (uint32_t)m * TC_ROW_BYTES;
+        const uint32_t sxor = (uint32_t)(m & 7);
+        const bool stager = eh == 0 && q == 0 && lane == 0;
+        const int set_threads = 32 * TC_EPI_WARPS / S;
         asm volatile("griddepcontrol.wait;" ::: "memory");          // res may be, and y may still be read by, earlier kernels
         int tn = eset;
         for (int t = blockIdx.x + tn * gridDim.x; t < p.total_tiles; t += S * gridDim.x, tn += S) {
@@ -305,6 +322,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             mbar_wait_warp(&tm_full[acc], pacc, p.err, 6);
             tc_fence_after();
             if (warp == 3 && lane == 0) TC_STAMP(tn, 8);
+            if (stg) {          // the set's previous tile must have left the staging buffer
+                if (stager) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + eset), "r"(set_threads) : "memory");
+            }
+            if (warp == 3 && lane == 0) TC_STAMP(tn, 10);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile);
             // Software-pipelined TMEM reads: the tcgen05.ld of chunk c+1 is in flight while chunk c is
             // post-processed and stored (tcgen05.wait::ld sits right before the data is needed).
@@ -324,13 +346,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             pq.y[pix * p.ldy + n] = f;
                         }
                     }
-                } else if (valid) {
+                } else if (valid || stg) {
                     const int n0 = tc.nt * p.n_tile + cb;
                     float v[16];
                     lds_bias16(bias_sa + n0 * 4, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fcvsr_act(__uint_as_float(r[j]) + v[j], p.act, slope);
-                    if (pq.res) {
+                    if (pq.res && valid) {
                         float rv[16];
                         if (p.wide) {
                             ld_global_v8(pq.res + pix * p.ldres + n0, rv);
@@ -343,13 +365,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] += rv[j];
                     }
-                    if (pq.res2) {
+                    if (pq.res2 && valid) {
                         const float4* rp = reinterpret_cast<const float4*>(pq.res2 + pix * p.ldres2 + n0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 rv = rp[j];
                             v[4 * j] -= rv.x; v[4 * j + 1] -= rv.y; v[4 * j + 2] -= rv.z; v[4 * j + 3] -= rv.w;
                         }
+                    }
+                    if (stg) {          // bf16 tile row of this pixel, 16-byte chunks XOR-swizzled by the row (SWIZZLE_128B)
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+                        const uint32_t ch = (uint32_t)cb >> 3;
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((ch ^ sxor) << 4)), "r"(w[0]), "r"(w[1]),
+                                     "r"(w[2]), "r"(w[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + (((ch + 1) ^ sxor) << 4)), "r"(w[4]), "r"(w[5]),
+                                     "r"(w[6]), "r"(w[7]) : "memory");
+                        return;
                     }
                     // operand-typed outputs: TF32-rounded fp32, or bf16 in bf16 mode
                     if (pq.y2) {
@@ -404,6 +437,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (c_begin < c_end) tmem_ld16(taddr + c_begin * 16, ra);
                 for (int c = c_begin; c < c_end; c += 2) {
                     tmem_ld_wait();
+                    if (warp == 3 && lane == 0 && c == c_begin) TC_STAMP(tn, 11);
                     const bool has_b = c + 1 < c_end;
                     if (has_b) tmem_ld16(taddr + (c + 1) * 16, rb);
                     process(ra, c * 16);
@@ -414,12 +448,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     }
                 }
             }
+            if (warp == 3 && lane == 0) TC_STAMP(tn, 12);
+            if (stg) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic writes -> TMA (async proxy) reads
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tm_empty[acc]);
+            if (stg) {
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + eset), "r"(set_threads) : "memory");
+                if (stager) {
+                    const CUtensorMap* my = tc.pr == 0 ? &map_y : (tc.pr == 1 ? &map_y1 : &map_y2);
+                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                 ::"l"(my), "r"(srow), "r"(0), "r"(tc.tx * TC_TW), "r"(tc.ty * TC_TH), "r"(tc.b) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
             if (warp == 3 && lane == 0) TC_STAMP(tn, 9);
 
         }
+        if (stg && stager) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all tiles written before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -552,6 +598,31 @@ static int conv_tc_launch(int np, const void* const* xs, const float* const* res
     }
     p.act = act; p.slope = slope; p.slope_ptr = slope_ptr; p.ps = pixel_shuffle;
     p.err = tc_err_flag();
+    // bf16 outputs with 64 channels: the epilogue stages the tile in shared memory and stores it with TMA.  The staging tiles
+    // (one per epilogue set) come out of the weight ring, which keeps at least the 72 KB that hold a 64 -> 64 3x3 filter resident.
+    const int smem_fixed = 1024 + TC_NA * TC_A_STAGE_BYTES + 512 + 4 * Cout;
+    p.stage_out = op16 && round_out == 1 && n_tile == 64 && n_tiles == 1 && !pixel_shuffle && !any_y2 && !thin && !(ldy & 7);
+    p.b_ring_bytes = TC_B_RING_BYTES;
+    if (p.stage_out) {
+        p.b_ring_bytes = ((TC_SMEM_LIMIT - smem_fixed) & ~1023) - p.epi_sets * TC_STG_BYTES;
+        if (p.b_ring_bytes > TC_B_RING_BYTES) p.b_ring_bytes = TC_B_RING_BYTES;
+        // only where the smaller ring still holds every weight stage at once (64 -> 64 3x3, the 1x1 convolutions): a streamed
+        // filter (128 -> 64 3x3) measured slower with three ring stages than with four (40.0 vs 38.6 us at 4 x 180 x 320)
+        if (p.b_ring_bytes < (Cin / kch) * ksize * ksize * n_tile * TC_ROW_BYTES) { p.stage_out = 0; p.b_ring_bytes = TC_B_RING_BYTES; }
+    }
+    CUtensorMap map_y[TC_MAX_PROB];
+    for (int i = 0; i < TC_MAX_PROB; ++i) {
+        if (!p.stage_out) { map_y[i] = map_x[0]; continue; }      // never read
+        const int j = i < np ? i : 0;
+        if (i >= np) { map_y[i] = map_y[0]; continue; }
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Ws[j], (cuuint64_t)Hs[j], (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)ldy * 2, (cuuint64_t)Ws[j] * ldy * 2, (cuuint64_t)Hs[j] * Ws[j] * ldy * 2};
+        cuuint32_t box[4] = {64, TC_TW, TC_TH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&map_y[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ys[j], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FCVSR_ERR_CUDA;
+    }
     {   // 256-bit epilogue accesses need 32-byte aligned rows for every tensor the epilogue touches
         const int esz_y = ((op16 && round_out) || round_out == 2) ? 2 : 4, esz_y2 = op16 ? 2 : 4;
         p.wide = !thin && !(align_or & 31) && !((ldy * esz_y) & 31) && (!any_res || !((ldres * 4) & 31)) &&
@@ -565,8 +636,9 @@ static int conv_tc_launch(int np, const void* const* xs, const float* const* res
 
     static int num_sms = 0;
     static bool attr_set = false;
-    const size_t smem_max = 1024 + TC_NA * TC_A_STAGE_BYTES + TC_B_RING_BYTES + 512 + 4 * TC_MAX_COUT;
-    const size_t smem = smem_max - 4 * TC_MAX_COUT + 4 * (size_t)p.Cout;
+    const size_t smem_max = TC_SMEM_LIMIT;
+    const size_t smem = (size_t)smem_fixed + p.b_ring_bytes + (p.stage_out ? p.epi_sets * TC_STG_BYTES : 0);
+    if (smem > smem_max) return FCVSR_ERR_UNSUPPORTED;
     if (!attr_set) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -592,11 +664,11 @@ static int conv_tc_launch(int np, const void* const* xs, const float* const* res
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t le;
     if (op16) {
-        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, true>, map_x[0], map_x[1], map_x[2], map_w, p);
-        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, map_x[0], map_x[1], map_x[2], map_w, p);
+        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, true>, map_x[0], map_x[1], map_x[2], map_w, map_y[0], map_y[1], map_y[2], p);
+        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, map_x[0], map_x[1], map_x[2], map_w, map_y[0], map_y[1], map_y[2], p);
     } else {
-        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, false>, map_x[0], map_x[1], map_x[2], map_w, p);
-        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, map_x[0], map_x[1], map_x[2], map_w, p);
+        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, false>, map_x[0], map_x[1], map_x[2], map_w, map_y[0], map_y[1], map_y[2], p);
+        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, map_x[0], map_x[1], map_x[2], map_w, map_y[0], map_y[1], map_y[2], p);
     }
     if (le != cudaSuccess) return FCVSR_ERR_CUDA;
     return fcvsr_launch_status();

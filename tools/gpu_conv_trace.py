@@ -73,10 +73,10 @@ for t_ in (62, 63):
     for s_ in range(16):
         v[t_ * 16 + s_] = 0
 t0 = min(t for t in v if t > 0)
-names = {0: "pr_aE", 1: "pr_iss", 4: "mma_tmE", 5: "aF_first", 6: "aF_last", 7: "mma_iss", 8: "epi_tmF", 9: "epi_done"}
-print("clk since first stamp, CTA 0, per tile: ", " ".join(f"{names[k]:>9s}" for k in sorted(names)))
+names = {0: "pr_aE", 1: "pr_iss", 4: "mma_tmE", 5: "aF_first", 6: "aF_last", 7: "mma_iss", 8: "epi_tmF", 10: "epi_bar", 11: "epi_ld", 12: "epi_math", 9: "epi_done"}
+print("clk since first stamp, CTA 0, per tile: ", " ".join(f"{names[k]:>9s}" for k in names))
 for t in range(16):
-    row = [v[t * 16 + k] for k in sorted(names)]
+    row = [v[t * 16 + k] for k in names]
     if not any(row):
         break
     print(f"tile {t:2d}:                                ", " ".join(f"{(r - t0) if r else 0:9d}" for r in row))
