@@ -3,6 +3,7 @@
 //   bilinear_up4         F.interpolate(center LR frame, x4, 'bilinear', align_corners=False) (:2750)
 // (The pixel shuffles that follow a convolution are fused into that convolution's epilogue.)
 #include "common.cuh"
+#include <string.h>
 
 // in [B,H,W,ldi] with 4*Co channels (channel co*4 + i*2 + j) -> out [B,2H,2W,ldo] with Co channels
 __global__ void pixel_shuffle_kernel(const void* __restrict__ in, int ldi, void* __restrict__ out, int ldo, int H, int W,
@@ -85,91 +86,142 @@ extern "C" int fcvsr_pack_clip(const float* x, void* y, int B, int T, int H, int
 }
 
 // ---- conv_last0: 3x3, 64 -> 1 channel, bf16 NHWC input, + bias + residual plane (CVSR_freq.py:2749-2751) -------------
-// On the tensor cores this is an N = 16 MMA with one useful column: A-operand bound (369 us at 720x1280, batch 4, for 73 us
-// of HBM time).  Here a thread computes 4 horizontally adjacent outputs: per filter row it reads the 6 input pixels of its
-// window once (8 x 16-byte ld.shared per pixel) and feeds all taps that use them; the 576 weights ride in the kernel
-// parameter space, so every FFMA takes its weight from the constant bank.  Tile = 8 x 64 outputs, haloed input tile
-// (10 x 66 pixels x 128 B) loaded with zero-filling cp.async, 16-byte chunks XOR-swizzled with (pixel >> 2) so that the
-// 64-byte thread stride is conflict-free.
-#define L1_TH 8
-#define L1_TW 64
-#define L1_THREADS 128
+// On tcgen05 this is an N = 16 MMA with one useful column and a nine-fold re-read of the input: A-operand bound (369 us at
+// 720x1280, batch 4, for 73 us of HBM time).  The first CUDA-core version (a thread = 4 outputs, weights in the constant bank)
+// needed ~875 instructions per output pixel (bf16 unpacking + 576 FFMA) and ran at 254 us, issue bound.  The convolution is
+// linear in the filter taps, so it splits into
+//     d[p][k] = sum_c x[p][c] * w[k][c]          a [pixels x 64] x [64 x 9] GEMM: every input pixel is read ONCE
+//     y[p]    = bias + res[p] + sum_k d[p + tap_k][k]      nine shifted adds of single values
+// The GEMM runs on the tensor cores through warp-level mma.sync (m16n8k16, bf16, fp32 accumulate; N = 9 padded to 16 is far too
+// thin for a tcgen05 tile and the kernel is bound by the one read of the input anyway): a block stages a haloed 18 x 34 pixel
+// tile (128 B per pixel, 16-byte chunks XOR-swizzled by the pixel so that ldmatrix is conflict-free) with zero-filling cp.async,
+// its 8 warps walk the 16-pixel row groups (A by ldmatrix.x4, the 9 x 64 weights as B fragments in 16 registers), d goes to
+// shared memory as nine planes, and every thread sums the nine shifted taps of two outputs.  Weights are rounded to bf16 like
+// every other convolution weight of the bf16 mode.
+#define L1_TH 16
+#define L1_TW 32
+#define L1_THREADS 256
+#define L1_HW (L1_TW + 2)
+#define L1_NPX ((L1_TH + 2) * L1_HW)               // 612 haloed pixels
+#define L1_MT ((L1_NPX + 15) / 16)                 // 39 row groups of 16 pixels
+#define L1_DPITCH 644                              // floats per d plane: >= 16 * L1_MT and == 4 (mod 32): conflict-free fragment stores
 struct ToOneParams {
     const unsigned short* x; int ldx;
     const float* res; float* y;
     int B, H, W;
     float bias;
-    float w[9 * 64];           // [ky][kx][c]
+    unsigned w16[16 * 32];     // bf16 pairs: w16[n * 32 + k / 2] = (w[n][k], w[n][k + 1]), n = tap (9..15 zero), k = channel
 };
 
-__global__ void __launch_bounds__(L1_THREADS) conv3x3_c64_to1_kernel(const __grid_constant__ ToOneParams p) {
+__global__ void __launch_bounds__(L1_THREADS, 2) conv3x3_c64_to1_kernel(const __grid_constant__ ToOneParams p) {
     extern __shared__ __align__(16) unsigned char l1_smem[];
+    float* dsm = reinterpret_cast<float*>(l1_smem + L1_MT * 16 * 128);       // [9][L1_DPITCH]
     const int tx0 = blockIdx.x * L1_TW, ty0 = blockIdx.y * L1_TH, b = blockIdx.z;
     const unsigned short* xb = p.x + (size_t)b * p.H * p.W * p.ldx;
-    constexpr int TWP = L1_TW + 2, NPX = (L1_TH + 2) * TWP;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(l1_smem);
-    for (int e = threadIdx.x; e < NPX * 8; e += L1_THREADS) {
+    for (int e = threadIdx.x; e < L1_MT * 16 * 8; e += L1_THREADS) {
         const int px = e >> 3, c8 = e & 7;
-        const int r = px / TWP, c = px - r * TWP;
+        const int r = px / L1_HW, c = px - r * L1_HW;
         const int yy = ty0 - 1 + r, xx = tx0 - 1 + c;
-        const bool ok = yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+        const bool ok = px < L1_NPX && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
         const void* src = ok ? (const void*)(xb + ((size_t)yy * p.W + xx) * p.ldx + c8 * 8) : (const void*)p.x;
-        const unsigned dst = sbase + px * 128 + ((c8 ^ ((px >> 2) & 7)) << 4);
+        const unsigned dst = sbase + px * 128 + ((c8 ^ (px & 7)) << 4);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    // the weights go through shared memory (row pitch 36 words: conflict-free fragment reads): a per-lane index into the kernel
+    // parameters is a constant-bank load that is replayed once per distinct address (measured: half of the kernel's stalls)
+    unsigned* wsm = reinterpret_cast<unsigned*>(dsm + 9 * L1_DPITCH);         // [16][36]
+    for (int i = threadIdx.x; i < 16 * 32; i += L1_THREADS) wsm[(i >> 5) * 36 + (i & 31)] = p.w16[i];
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    const int ty = threadIdx.x >> 4, x0 = (threadIdx.x & 15) * 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // B fragments (col-major K x N == w[n][k]): b0 = k pair tig * 2, b1 = k pair tig * 2 + 8 of column n = gid (+ 8 for the second n tile)
+    unsigned bf[4][2][2];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
+    for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int px = (ty + ky) * TWP + x0 + i;
-            const unsigned char* pp = l1_smem + px * 128;
-            const int sw = (px >> 2) & 7;
+        for (int nt = 0; nt < 2; ++nt) {
+            bf[ks][nt][0] = wsm[(nt * 8 + gid) * 36 + ks * 8 + tig];
+            bf[ks][nt][1] = wsm[(nt * 8 + gid) * 36 + ks * 8 + tig + 4];
+        }
+    for (int mt = warp; mt < L1_MT; mt += L1_THREADS / 32) {
+        float acc[2][4];
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                const uint4 u = *reinterpret_cast<const uint4*>(pp + ((c8 ^ sw) << 4));
-                float f[8];
-                f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
-                f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
-                f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
-                f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int kx = i - j;
-                    if (kx >= 0 && kx < 3) {
+            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+        // ldmatrix.x4: lanes 0-15 address rows 0-15 of the low 8 k (16-byte chunk 2 ks), lanes 16-31 the same rows of the high 8 k
+        const int row = mt * 16 + (lane & 15);
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[j] = fmaf(f[c], p.w[(ky * 3 + kx) * 64 + c8 * 8 + c], acc[j]);
-                    }
-                }
-            }
+        for (int ks = 0; ks < 4; ++ks) {
+            const int chunk = 2 * ks + (lane >> 4);
+            const unsigned addr = sbase + row * 128 + ((chunk ^ (row & 7)) << 4);
+            unsigned a0, a1, a2, a3;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[ks][nt][0]), "r"(bf[ks][nt][1]));
+        }
+        // accumulator fragment: c0, c1 = row gid, columns 2 tig, 2 tig + 1; c2, c3 = row gid + 8.  Columns 0..8 are taps.
+        const int r0 = mt * 16 + gid;
+        dsm[(2 * tig) * L1_DPITCH + r0] = acc[0][0];
+        dsm[(2 * tig + 1) * L1_DPITCH + r0] = acc[0][1];
+        dsm[(2 * tig) * L1_DPITCH + r0 + 8] = acc[0][2];
+        dsm[(2 * tig + 1) * L1_DPITCH + r0 + 8] = acc[0][3];
+        if (tig == 0) {                                     // column 8 lives in the second n tile
+            dsm[8 * L1_DPITCH + r0] = acc[1][0];
+            dsm[8 * L1_DPITCH + r0 + 8] = acc[1][2];
         }
     }
+    __syncthreads();
+    // out(y, x) = sum_{ky, kx} d[(y + ky) * L1_HW + x + kx][ky * 3 + kx]: two horizontally adjacent outputs per thread
+    const int ty = threadIdx.x >> 4, x0 = (threadIdx.x & 15) * 2;
+    float o0 = p.bias, o1 = p.bias;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float* d = dsm + (ky * 3 + kx) * L1_DPITCH + (ty + ky) * L1_HW + x0 + kx;
+            o0 += d[0];
+            o1 += d[1];
+        }
     const int y = ty0 + ty, x = tx0 + x0;
     if (y < p.H && x < p.W) {
         const size_t o = ((size_t)b * p.H + y) * p.W + x;
-        if (x + 3 < p.W && !(o & 3)) {
-            float4 r = p.res ? *reinterpret_cast<const float4*>(p.res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(p.y + o) =
-                make_float4(acc[0] + p.bias + r.x, acc[1] + p.bias + r.y, acc[2] + p.bias + r.z, acc[3] + p.bias + r.w);
+        if (x + 1 < p.W && !(o & 1)) {
+            const float2 r = p.res ? *reinterpret_cast<const float2*>(p.res + o) : make_float2(0.f, 0.f);
+            *reinterpret_cast<float2*>(p.y + o) = make_float2(o0 + r.x, o1 + r.y);
         } else {
-            for (int j = 0; j < 4 && x + j < p.W; ++j) p.y[o + j] = acc[j] + p.bias + (p.res ? p.res[o + j] : 0.f);
+            p.y[o] = o0 + (p.res ? p.res[o] : 0.f);
+            if (x + 1 < p.W) p.y[o + 1] = o1 + (p.res ? p.res[o + 1] : 0.f);
         }
     }
 }
 
-// x: bf16 NHWC [B,H,W,ldx] (64 channels used); w_host: HOST pointer to 9*64 floats [ky][kx][c] (they travel as kernel
-// parameters); res / y: fp32 planes [B,H,W].  Replaces conv_last0 + the bilinear-skip add (CVSR_freq.py:2749-2751).
+static unsigned short l1_bf16_rn(float f) {
+    unsigned u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (unsigned short)(u >> 16);     // inf / nan
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (unsigned short)(u >> 16);
+}
+
+// x: bf16 NHWC [B,H,W,ldx] (64 channels used); w_host: HOST pointer to 9*64 floats [ky][kx][c] (rounded to bf16 here; they
+// travel as kernel parameters); res / y: fp32 planes [B,H,W].  Replaces conv_last0 + the bilinear-skip add (CVSR_freq.py:2749-2751).
 extern "C" int fcvsr_conv3x3_c64_to1(const void* x, int ldx, const float* w_host, float bias, const float* res, float* y, int B,
                                      int H, int W, cudaStream_t st) {
     if (!x || !w_host || !y || B <= 0 || H <= 0 || W <= 0 || (ldx & 7) || ((uintptr_t)x & 15)) return FCVSR_ERR_ARG;
     ToOneParams p;
     p.x = (const unsigned short*)x; p.ldx = ldx; p.res = res; p.y = y; p.B = B; p.H = H; p.W = W; p.bias = bias;
-    for (int i = 0; i < 9 * 64; ++i) p.w[i] = w_host[i];
-    const size_t smem = (size_t)(L1_TH + 2) * (L1_TW + 2) * 128;
+    for (int n = 0; n < 16; ++n)
+        for (int k2 = 0; k2 < 32; ++k2) {
+            const unsigned lo = n < 9 ? l1_bf16_rn(w_host[n * 64 + 2 * k2]) : 0u, hi = n < 9 ? l1_bf16_rn(w_host[n * 64 + 2 * k2 + 1]) : 0u;
+            p.w16[n * 32 + k2] = lo | (hi << 16);
+        }
+    const size_t smem = (size_t)L1_MT * 16 * 128 + (size_t)9 * L1_DPITCH * 4 + 16 * 36 * 4;
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(conv3x3_c64_to1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

@@ -518,7 +518,7 @@ def test_baseline_size_parity_against_oracle(dev, variant, b, h, w):
 
 @pytest.mark.parametrize("B,H,W", [(1, 8, 64), (2, 19, 70), (1, 40, 200)])
 def test_conv_last_to1_kernel(dev, B, H, W):
-    """fcvsr_conv3x3_c64_to1 (conv_last0 + skip, bf16 input): exact on the bf16-rounded input up to fp32 summation order."""
+    """fcvsr_conv3x3_c64_to1 (conv_last0 + skip, bf16 input): exact on the bf16-rounded input and weights up to fp32 summation order."""
     import ctypes
     g = torch.Generator().manual_seed(H * W)
     x = torch.randn(B, 64, H, W, generator=g)
@@ -530,7 +530,8 @@ def test_conv_last_to1_kernel(dev, B, H, W):
     wh = (ctypes.c_float * 576)(*w[0].permute(1, 2, 0).reshape(-1).tolist())
     C.call("fcvsr_conv3x3_c64_to1", xd.data_ptr(), 64, ctypes.addressof(wh), 0.25, rd.data_ptr(), y.data_ptr(), B, H, W, _st())
     torch.cuda.synchronize()
-    ref = F.conv2d(x.to(torch.bfloat16).float(), w, torch.tensor([0.25]), padding=1) + res
+    # the kernel rounds the weights to bf16 (mma.sync operands, like every other convolution weight of the bf16 mode)
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), torch.tensor([0.25]), padding=1) + res
     assert float((y.cpu() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
 
 
