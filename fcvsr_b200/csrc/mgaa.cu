@@ -88,25 +88,29 @@ __device__ __forceinline__ int ob_woff(int i) {   // 16 * sum_{t<i} (2t+1)^2 = 1
     return 16 * (i * (2 * i - 1) * (2 * i + 1) / 3);
 }
 
-// A thread computes 4 consecutive x positions of one row for all 4 output channels.  Per filter row it holds the
-// K + 3 input float4 of its window in registers and walks the K taps with the tap's 16 weights loaded once
-// (4 broadcast ld.shared.v4 per 64 FMAs; the one-position-per-thread version issued one per 4 FMAs and ran at
-// 13 TFLOP/s).
+// Tile = 8 rows x 64 columns of one (iteration, direction, image); thread = (row, quad of 4 consecutive columns), all 4 output
+// channels.  The haloed input tile ((8 + K - 1) x (64 + K - 1) float4 pixels) is staged in shared memory: gathering the windows
+// straight from global memory had neighbouring lanes 64 bytes apart, so every warp load touched 16 lines at 25 % sector use and
+// the kernel was L1-bound (ncu: l1tex 82 %, FMA pipe 43 %, 33.9 M sectors for a 5.6 MB input).  In shared memory the pixels of
+// a row are de-interleaved by (x mod 4): window element d of quad c lives in array d % 4, slot c + d / 4, so the 16 quads of a
+// half-warp read 16 consecutive 16-byte slots -- conflict-free.  Per filter row a thread holds its K + 3 window pixels in
+// registers and walks the K taps with the tap's 16 weights loaded once (4 broadcast ld.shared.v4 per 64 FMAs).
+#define OB_TH 8
+#define OB_TQ 16                                   // quads per tile row
+#define OB_TW (4 * OB_TQ)
+#define OB_KMAX 11
+#define OB_SLOTS (OB_TQ + (OB_KMAX + 2) / 4 + 1)   // 16-byte slots per (row, x mod 4) array
+#define OB_ROWF4 (4 * OB_SLOTS)                    // float4 per staged row
+
 template <int K, bool SECOND>
-__device__ __forceinline__ void ob_conv_quad(const float* __restrict__ src, const float* __restrict__ ws, int H, int Wf, int y,
-                                             int x0, float (&acc)[4][4]) {
-    constexpr int PAD = K / 2;
+__device__ __forceinline__ void ob_conv_quad(const float4* __restrict__ tile, const float* __restrict__ ws, int r, int c,
+                                             float (&acc)[4][4]) {
 #pragma unroll 1
     for (int ky = 0; ky < K; ++ky) {
-        const int yy = y + ky - PAD;
-        if (yy < 0 || yy >= H) continue;
+        const float4* rowp = tile + (r + ky) * OB_ROWF4 + c;
         float4 row[K + 3];
 #pragma unroll
-        for (int j = 0; j < K + 3; ++j) {
-            const int xx = x0 - PAD + j;
-            row[j] = (xx >= 0 && xx < Wf) ? __ldg(reinterpret_cast<const float4*>(src + ((size_t)yy * Wf + xx) * 4))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int j = 0; j < K + 3; ++j) row[j] = rowp[(j & 3) * OB_SLOTS + (j >> 2)];
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
             const float4* wt = reinterpret_cast<const float4*>(ws + (ky * K + kx) * 16);
@@ -130,35 +134,46 @@ __global__ void __launch_bounds__(OB_THREADS) offset_blk_conv_kernel(const float
                                                                     const float* __restrict__ prelu,   // [A] (stage 1)
                                                                     float* __restrict__ out, size_t out_iter_stride,
                                                                     float* __restrict__ partial,       // stage 2
-                                                                    int H, int Wf) {
+                                                                    int H, int Wf, int tiles_x) {
     __shared__ __align__(16) float ws[121 * 16];
+    __shared__ __align__(16) float4 tile[(OB_TH + OB_KMAX - 1) * OB_ROWF4];
     __shared__ float red[OB_THREADS / 32][4];
     // the iteration is the slowest grid dimension, largest kernel first (k = 11 costs 121x k = 1): the light blocks fill the tail
-    const int it = gridDim.z - 1 - blockIdx.z, k = 2 * it + 1;
+    const int it = gridDim.z - 1 - blockIdx.z, k = 2 * it + 1, pad = it;
     const int bz = blockIdx.y, b = bz >> 1, dir = bz & 1;
+    const int B = gridDim.y >> 1;
+    const int ty0 = (blockIdx.x / tiles_x) * OB_TH, tx0 = (blockIdx.x % tiles_x) * OB_TW;
+    const int P = H * Wf;
     const float* wi = w + ob_woff(it);
     for (int t = threadIdx.x; t < k * k * 16; t += blockDim.x) ws[t] = wi[t];
+    {   // haloed input tile, zero outside the image (the convolution's zero padding), rows de-interleaved by (x mod 4)
+        const float* src = in + (SECOND ? (size_t)it * in_iter_stride : 0) + ((size_t)dir * B + b) * P * 4;
+        const int tw = OB_TW + k - 1, th = OB_TH + k - 1;
+        for (int e = threadIdx.x; e < th * tw; e += blockDim.x) {
+            const int rr = e / tw, pp = e - rr * tw;
+            const int yy = ty0 - pad + rr, xx = tx0 - pad + pp;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < Wf) v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)yy * Wf + xx) * 4));
+            tile[rr * OB_ROWF4 + (pp & 3) * OB_SLOTS + (pp >> 2)] = v;
+        }
+    }
     __syncthreads();
-    const int P = H * Wf;
-    const int qpr = (Wf + 3) >> 2;                         // quads per row
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+    const int y = ty0 + r, x0 = tx0 + 4 * c;
     float acc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int co = 0; co < 4; ++co) acc[j][co] = 0.f;
     float sum[4] = {0.f, 0.f, 0.f, 0.f};
-    if (q < H * qpr) {
-        const int y = q / qpr, x0 = (q - y * qpr) * 4;
-        const int B = gridDim.y >> 1;
-        const float* src = in + (SECOND ? (size_t)it * in_iter_stride : 0) + ((size_t)dir * B + b) * P * 4;
+    if (y < H && x0 < Wf) {
         switch (it) {
-            case 0: ob_conv_quad<1, SECOND>(src, ws, H, Wf, y, x0, acc); break;
-            case 1: ob_conv_quad<3, SECOND>(src, ws, H, Wf, y, x0, acc); break;
-            case 2: ob_conv_quad<5, SECOND>(src, ws, H, Wf, y, x0, acc); break;
-            case 3: ob_conv_quad<7, SECOND>(src, ws, H, Wf, y, x0, acc); break;
-            case 4: ob_conv_quad<9, SECOND>(src, ws, H, Wf, y, x0, acc); break;
-            default: ob_conv_quad<11, SECOND>(src, ws, H, Wf, y, x0, acc); break;
+            case 0: ob_conv_quad<1, SECOND>(tile, ws, r, c, acc); break;
+            case 1: ob_conv_quad<3, SECOND>(tile, ws, r, c, acc); break;
+            case 2: ob_conv_quad<5, SECOND>(tile, ws, r, c, acc); break;
+            case 3: ob_conv_quad<7, SECOND>(tile, ws, r, c, acc); break;
+            case 4: ob_conv_quad<9, SECOND>(tile, ws, r, c, acc); break;
+            default: ob_conv_quad<11, SECOND>(tile, ws, r, c, acc); break;
         }
         const float sl = SECOND ? 0.f : prelu[it];
         float* dst = out + (size_t)it * out_iter_stride + (((size_t)dir * B + b) * P + (size_t)y * Wf + x0) * 4;
@@ -246,11 +261,12 @@ extern "C" int fcvsr_offset_blocks(const float* off, const float* w1, const floa
         return FCVSR_ERR_ARG;
     const int P = H * Wf;
     const int nblk = (P + OB_THREADS - 1) / OB_THREADS;
-    const int nqblk = (H * ((Wf + 3) / 4) + OB_THREADS - 1) / OB_THREADS;       // conv blocks: 4 positions per thread (<= nblk)
+    // conv blocks: 8 x 64 tiles, one CALayer partial sum each (`partial` holds max(nblk, nqblk) entries per iteration and image)
+    const int tiles_x = (Wf + OB_TW - 1) / OB_TW, nqblk = tiles_x * ((H + OB_TH - 1) / OB_TH);
     dim3 grid(nblk, A, B * 2), gridq(nqblk, B * 2, A);
     const size_t iter_stride = (size_t)B * P * 8;
-    offset_blk_conv_kernel<false><<<gridq, OB_THREADS, 0, st>>>(off, 0, w1, prelu, t1, iter_stride, nullptr, H, Wf);
-    offset_blk_conv_kernel<true><<<gridq, OB_THREADS, 0, st>>>(t1, iter_stride, w2, nullptr, t2, iter_stride, partial, H, Wf);
+    offset_blk_conv_kernel<false><<<gridq, OB_THREADS, 0, st>>>(off, 0, w1, prelu, t1, iter_stride, nullptr, H, Wf, tiles_x);
+    offset_blk_conv_kernel<true><<<gridq, OB_THREADS, 0, st>>>(t1, iter_stride, w2, nullptr, t2, iter_stride, partial, H, Wf, tiles_x);
     offset_blk_finish_kernel<<<grid, OB_THREADS, 0, st>>>(t2, iter_stride, partial, nqblk, ca_w, sim, ldsim, z, A, H, Wf);
     return fcvsr_launch_status();
 }

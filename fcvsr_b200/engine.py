@@ -283,7 +283,7 @@ class Engine:
             buf("sim" + sfx, B, Pf, 4)
             buf("ob_t1" + sfx, A, 2 * B, Pf, 4)
             buf("ob_t2" + sfx, A, 2 * B, Pf, 4)
-            buf("ob_partial" + sfx, A * 2 * B * ((Pf + 127) // 128) * 4)
+            buf("ob_partial" + sfx, A * 2 * B * max((Pf + 127) // 128, ((Wf + 63) // 64) * ((H + 7) // 8)) * 4)
             buf("z" + sfx, B, Pf, 8 * A)
             buf("offs" + sfx, B, P, 4 * A)
             buf("x2r" + sfx, B, P, 64, op=True)

@@ -102,7 +102,7 @@ int fcvsr_corr_gather2(const float* S, int ldS, int a_off, int b_off, void* out,
 /* ConvBlk(4, index=i) for i < A and both directions (:344-357, :1494-1498):
  * off [2][B][H*Wf][4] (dir-major), w1/w2 packed per iteration [k*k][ci][co] back to back, prelu [A],
  * ca_w [A][2][4][4], sim [B,H*Wf,ldsim] (4 ch).  Scratch t1,t2 [A][2][B][H*Wf][4], partial
- * [A][2B][ceil(H*Wf/128)][4].  z: complex [B,H*Wf,4A], channel (i*2+dir)*2+m = (v[m], v[2+m]). */
+ * [A][2B][max(ceil(H*Wf/128), ceil(Wf/64)*ceil(H/8))][4].  z: complex [B,H*Wf,4A], channel (i*2+dir)*2+m = (v[m], v[2+m]). */
 int fcvsr_offset_blocks(const float* off, const float* w1, const float* w2, const float* prelu,
                         const float* ca_w, const float* sim, int ldsim, float* t1, float* t2, float* partial,
                         float* z, int B, int H, int Wf, int A, cudaStream_t stream);

@@ -86,7 +86,7 @@ def test_offset_blocks_kernel(dev, variant, B, H, W):
     simd = nhwc(sim).to(dev)
     t1 = torch.empty(A, 2 * B, P, 4, device=dev)
     t2 = torch.empty_like(t1)
-    part = torch.empty(A * 2 * B * ((P + 127) // 128) * 4, device=dev)
+    part = torch.empty(A * 2 * B * max((P + 127) // 128, ((Wf + 63) // 64) * ((H + 7) // 8)) * 4, device=dev)
     z = torch.empty(B, P, 8 * A, device=dev)
     C.call("fcvsr_offset_blocks", offd.data_ptr(), Pk["ob_w1"].data_ptr(), Pk["ob_w2"].data_ptr(), Pk["ob_prelu"].data_ptr(),
            Pk["ob_ca"].data_ptr(), simd.data_ptr(), 4, t1.data_ptr(), t2.data_ptr(), part.data_ptr(), z.data_ptr(), B, H, Wf, A,
