@@ -240,12 +240,15 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
 
     // output stage ownership: a half-warp per output pixel (128 contiguous bytes of bf16), a lane 4 channels
     const int oslot = tid >> 4, oc0 = (tid & 15) * 4;
+    // Both directions use the same two tile buffers: buf1 = warped samples (phase 1 -> 2), buf0 = pass results (phase 2 -> 3;
+    // it starts life as the MMA's operand tiles, which are dead once the accumulator barrier has been waited for).  Two
+    // barriers per direction: the next direction's gathers overwrite the samples only after every thread has passed the
+    // barrier behind phase 2, and its phase 2 overwrites the results only after the barrier behind its own gathers, which
+    // every thread reaches after its phase 3 reads.
+    float* bufS = buf1;
+    float* bufO = buf0;
 #pragma unroll 1
     for (int dir = 0; dir < 2; ++dir) {
-        // the two tile buffers swap roles between the directions, so three barriers per direction are enough:
-        // bufA: samples (phase 1 -> 2), then the horizontal-pass result (phase 3 -> 4);  bufB: vertical-pass result (phase 2 -> 3)
-        float* bufA = dir ? buf0 : buf1;
-        float* bufB = dir ? buf1 : buf0;
         // phase 1: warped samples; a half-warp owns five halo pixels, a lane 4 channels
         {
             const int ldp = (dir ? a.ldprev[1] : a.ldprev[0]);
@@ -254,16 +257,16 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
             const int4* gi = geo_i + dir * IT_HALO;
             const float4* gw = geo_w + dir * IT_HALO;
             if (P16) {          // 12 + 8 eight-byte gathers in flight
-                it_gather<P16, 3>(pbase, ldp, gi, gw, bufA + oc0, oslot);
-                it_gather<P16, 2>(pbase, ldp, gi, gw, bufA + oc0, oslot + 3 * (IT_THREADS / 16));
+                it_gather<P16, 3>(pbase, ldp, gi, gw, bufS + oc0, oslot);
+                it_gather<P16, 2>(pbase, ldp, gi, gw, bufS + oc0, oslot + 3 * (IT_THREADS / 16));
             } else {            // 8 + 8 + 4 sixteen-byte gathers
-                it_gather<P16, 2>(pbase, ldp, gi, gw, bufA + oc0, oslot);
-                it_gather<P16, 2>(pbase, ldp, gi, gw, bufA + oc0, oslot + 2 * (IT_THREADS / 16));
-                it_gather<P16, 1>(pbase, ldp, gi, gw, bufA + oc0, oslot + 4 * (IT_THREADS / 16));
+                it_gather<P16, 2>(pbase, ldp, gi, gw, bufS + oc0, oslot);
+                it_gather<P16, 2>(pbase, ldp, gi, gw, bufS + oc0, oslot + 2 * (IT_THREADS / 16));
+                it_gather<P16, 1>(pbase, ldp, gi, gw, bufS + oc0, oslot + 4 * (IT_THREADS / 16));
             }
         }
         __syncthreads();
-        // residual input of this thread's output-stage pixels (coalesced: 256 contiguous bytes per half-warp), used in phase 4
+        // residual input of this thread's output-stage pixels (coalesced: 256 contiguous bytes per half-warp), used in phase 3
         float4 xi[4];
         {
             const float* xin = (dir ? a.xin[1] : a.xin[0]) + oc0;
@@ -275,54 +278,47 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
                 if (o < IT_TH * IT_TW && yy < H && xx < W) xi[i] = __ldg(reinterpret_cast<const float4*>(xin + (img + (size_t)yy * W + xx) * ldx));
             }
         }
-        // the taps are read from TMEM where they are used (twice per direction: 12 values per 4 channels), never held
         if (dir == 0) mbar_wait(bar, 0, nullptr, 0);
         tc_fence_after();
-        // phase 2: vertical pass (halo row hy = row + t <-> image row y + t - 1)
+        // phase 2: both SAC passes with the taps read from TMEM once (fp32, never rounded).  Vertical pass: halo rows row,
+        // row + 1, row + 2 of the thread's column from the sample tile (halo row hy = row + t <-> image row y + t - 1).
+        // Horizontal pass: the vertical-pass values of the two neighbouring columns are in the neighbouring lanes (a warp holds
+        // two tile rows of 16 columns, lane & 15 = column), so they come by shuffle -- no second tile buffer, no barrier between
+        // the passes, half the shared-memory traffic of the passes.  tcgen05.ld and the shuffles are warp-collective: every lane
+        // runs them, only the owners of an output pixel store.
         {
-            const float* s = bufA + (row * IT_HX + hx) * IT_P + g * 16;
-            float* v = bufB + px * IT_P + g * 16;
+            const float* sp = bufS + (row * IT_HX + hx) * IT_P + g * 16;
+            float* ob = bufO + px * IT_P + g * 16;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float k[12];
                 it_tmem_ld12(taddr + j * 12, k);
-                const float4 s0 = *reinterpret_cast<const float4*>(s + 4 * j);
-                const float4 s1 = *reinterpret_cast<const float4*>(s + IT_HX * IT_P + 4 * j);
-                const float4 s2 = *reinterpret_cast<const float4*>(s + 2 * IT_HX * IT_P + 4 * j);
-                float4 o;
-                o.x = fmaf(k[8], s2.x, fmaf(k[4], s1.x, k[0] * s0.x));
-                o.y = fmaf(k[9], s2.y, fmaf(k[5], s1.y, k[1] * s0.y));
-                o.z = fmaf(k[10], s2.z, fmaf(k[6], s1.z, k[2] * s0.z));
-                o.w = fmaf(k[11], s2.w, fmaf(k[7], s1.w, k[3] * s0.w));
-                *reinterpret_cast<float4*>(v + 4 * j) = o;
-            }
-        }
-        __syncthreads();
-        // phase 3: horizontal pass for the 14 inner columns, result back into bufA (the samples are dead).  tcgen05.ld is
-        // warp-collective (.sync.aligned): every lane reads its taps, only the owners of an output pixel go on
-        {
-            const float* v = bufB + (px - 1) * IT_P + g * 16;
-            float* ob = bufA + px * IT_P + g * 16;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float k[12];
-                it_tmem_ld12(taddr + j * 12, k);
+                const float4 s0 = *reinterpret_cast<const float4*>(sp + 4 * j);
+                const float4 s1 = *reinterpret_cast<const float4*>(sp + IT_HX * IT_P + 4 * j);
+                const float4 s2 = *reinterpret_cast<const float4*>(sp + 2 * IT_HX * IT_P + 4 * j);
+                float4 v;
+                v.x = fmaf(k[8], s2.x, fmaf(k[4], s1.x, k[0] * s0.x));
+                v.y = fmaf(k[9], s2.y, fmaf(k[5], s1.y, k[1] * s0.y));
+                v.z = fmaf(k[10], s2.z, fmaf(k[6], s1.z, k[2] * s0.z));
+                v.w = fmaf(k[11], s2.w, fmaf(k[7], s1.w, k[3] * s0.w));
+                float4 vl, vr;
+                vl.x = __shfl_up_sync(0xffffffffu, v.x, 1, 16); vr.x = __shfl_down_sync(0xffffffffu, v.x, 1, 16);
+                vl.y = __shfl_up_sync(0xffffffffu, v.y, 1, 16); vr.y = __shfl_down_sync(0xffffffffu, v.y, 1, 16);
+                vl.z = __shfl_up_sync(0xffffffffu, v.z, 1, 16); vr.z = __shfl_down_sync(0xffffffffu, v.z, 1, 16);
+                vl.w = __shfl_up_sync(0xffffffffu, v.w, 1, 16); vr.w = __shfl_down_sync(0xffffffffu, v.w, 1, 16);
                 if (owns_out) {
-                    const float4 v0 = *reinterpret_cast<const float4*>(v + 4 * j);
-                    const float4 v1 = *reinterpret_cast<const float4*>(v + IT_P + 4 * j);
-                    const float4 v2 = *reinterpret_cast<const float4*>(v + 2 * IT_P + 4 * j);
                     float4 o;
-                    o.x = fmaf(k[8], v2.x, fmaf(k[4], v1.x, k[0] * v0.x));
-                    o.y = fmaf(k[9], v2.y, fmaf(k[5], v1.y, k[1] * v0.y));
-                    o.z = fmaf(k[10], v2.z, fmaf(k[6], v1.z, k[2] * v0.z));
-                    o.w = fmaf(k[11], v2.w, fmaf(k[7], v1.w, k[3] * v0.w));
+                    o.x = fmaf(k[8], vr.x, fmaf(k[4], v.x, k[0] * vl.x));
+                    o.y = fmaf(k[9], vr.y, fmaf(k[5], v.y, k[1] * vl.y));
+                    o.z = fmaf(k[10], vr.z, fmaf(k[6], v.z, k[2] * vl.z));
+                    o.w = fmaf(k[11], vr.w, fmaf(k[7], v.w, k[3] * vl.w));
                     *reinterpret_cast<float4*>(ob + 4 * j) = o;
                 }
             }
         }
         tc_fence_before();
         __syncthreads();
-        // phase 4: + residual, LeakyReLU(0.1), bf16, coalesced stores (the thread-per-pixel layout of the passes would touch 32
+        // phase 3: + residual, LeakyReLU(0.1), bf16, coalesced stores (the thread-per-pixel layout of the passes would touch 32
         // different lines per load / store instruction)
         {
             unsigned short* next = reinterpret_cast<unsigned short*>(dir ? a.next[1] : a.next[0]) + oc0;
@@ -332,7 +328,7 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
                 const int o = oslot + 32 * i, orow = o / IT_TW, ocol = o - orow * IT_TW;
                 const int yy = ty0 + orow, xx = tx0 + ocol;
                 if (o < IT_TH * IT_TW && yy < H && xx < W) {
-                    const float4 r = *reinterpret_cast<const float4*>(bufA + (orow * IT_HX + ocol + 1) * IT_P + oc0);
+                    const float4 r = *reinterpret_cast<const float4*>(bufO + (orow * IT_HX + ocol + 1) * IT_P + oc0);
                     const float p0 = r.x + xi[i].x, p1 = r.y + xi[i].y, p2 = r.z + xi[i].z, p3 = r.w + xi[i].w;
                     uint32_t lo, hi;
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(p1 >= 0.f ? p1 : 0.1f * p1), "f"(p0 >= 0.f ? p0 : 0.1f * p0));
@@ -341,7 +337,7 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
                 }
             }
         }
-        // no barrier here: the next direction's gathers write the other buffer (last read in this direction's phase 3)
+        // no barrier here: the next direction's gathers write the sample buffer, last read before the barrier above
     }
     __syncthreads();
     if (warp == 1) {
