@@ -22,6 +22,7 @@ SIGNATURES = {
     "fcvsr_conv2d_direct": "pii pp pi pi pi iiiiiii if p ii pii i s",
     "fcvsr_conv2d_tc": "pi pp pi pi pi iiiiii if p i pii i i s",
     "fcvsr_conv2d_tc_multi": "i pi pp pi pi pp iiii i f p pi i i s",
+    "fcvsr_conv2d_tc_multi_w": "i pi pp pi pi pp iiii i f i i s",
     "fcvsr_fft_r2c_w": "pi p p iiii s",
     "fcvsr_fft_c2c_h": "p p p p iiii i f ii p s",
     "fcvsr_fft_c2r_w": "p pi p iiii f s",

@@ -61,7 +61,7 @@ extern "C" int fcvsr_debug_conv_trace(long long* host, int n) {
 #define TC_STAMP_NS(n) do {} while (0)
 #endif
 
-#define TC_MAX_PROB 3
+#define TC_MAX_PROB 4
 // One launch can run the same convolution (same weights, bias, activation, strides) on up to three tensors of different
 // spatial size: the three pyramid levels of SCNetbk (BlockRCB applies one body to every level, CVSR_freq.py:766-770).  The
 // persistent CTAs walk ONE tile list that spans the levels, so the small levels (1/4 and 1/16 of the pixels) fill the SMs
@@ -69,6 +69,7 @@ extern "C" int fcvsr_debug_conv_trace(long long* host, int n) {
 struct ConvTcProblem {
     const float* res; const float* res2; float* y; float* y2;
     int H, W, tiles_x, tiles_y, tile_begin;    // tile_begin: index of the problem's first tile in the launch's tile list
+    int wrow;                                  // first row of the problem's filter in the (stacked) weight matrix / bias vector
 };
 struct ConvTcParams {
     const float* bias; int ldres; int ldres2;
@@ -78,6 +79,7 @@ struct ConvTcParams {
     int cout_valid;                      // channels actually stored (== Cout, or < 16 for thin heads)
     int n_tile, n_tiles;               // N per pass, number of passes
     int nprob, total_tiles;
+    int w_rows, multi_w;                 // rows of the weight matrix (>= Cout: several filters stacked); problems use different filters
     ConvTcProblem prob[TC_MAX_PROB];
     int act; float slope; const float* slope_ptr; int ps;
     int wide;                            // 32-byte aligned tensors: use 256-bit loads / stores in the epilogue
@@ -91,7 +93,8 @@ struct ConvTcParams {
 struct TileCoord { int nt, tx, ty, b, pr; };
 __device__ __forceinline__ TileCoord decode_tile(int t, const ConvTcParams& p) {
     TileCoord c;
-    c.pr = (p.nprob > 1 && t >= p.prob[1].tile_begin) ? ((p.nprob > 2 && t >= p.prob[2].tile_begin) ? 2 : 1) : 0;
+    c.pr = (p.nprob > 1 && t >= p.prob[1].tile_begin)
+               ? ((p.nprob > 2 && t >= p.prob[2].tile_begin) ? ((p.nprob > 3 && t >= p.prob[3].tile_begin) ? 3 : 2) : 1) : 0;
     const ConvTcProblem& q = p.prob[c.pr];
     t -= q.tile_begin;
     c.nt = t % p.n_tiles; t /= p.n_tiles;
@@ -103,9 +106,10 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const ConvTcParams& p) {
 template <int KS, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x1,
-               const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_y1,
-               const __grid_constant__ CUtensorMap map_y2, const ConvTcParams p) {
+               const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_x3,
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_y,
+               const __grid_constant__ CUtensorMap map_y1, const __grid_constant__ CUtensorMap map_y2,
+               const __grid_constant__ CUtensorMap map_y3, const ConvTcParams p) {
     // Programmatic dependent launch: let the next convolution's CTAs take each SM as soon as this grid's CTA leaves it
     // and run their prologue (barriers, TMEM, bias, first weight stages) while the rest of this grid drains; everything
     // that touches activations sits behind griddepcontrol.wait (a no-op for a normally serialized launch).
@@ -130,7 +134,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // global loads here cost more than the tile's MMAs: the tensor core's operand fetches saturate the L1/shared pipe
     // and every LDG queues behind them (measured: 64->128 bf16 conv 60 us without bias, 147 us with __ldg bias).
     float* bias_s = (float*)((uint8_t*)bars + 512);
-    for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) bias_s[i] = (p.bias && i < p.cout_valid) ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < p.w_rows; i += TC_THREADS)
+        bias_s[i] = (p.bias && (p.multi_w || i < p.cout_valid)) ? p.bias[i] : 0.f;
     const uint32_t bias_sa = smem_u32(bias_s);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,7 +150,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // Weights resident: with a single N pass and every (K chunk, filter row) stage fitting in the ring at once, the
     // stages are loaded once per CTA and never released (bf16 64->64 3x3: 72 KB).  ncu showed the L2->SM read path
     // at 97 % of peak with the weights re-streamed per tile; this halves that traffic for the most common shape.
-    const bool b_resident = p.n_tiles == 1 && kchunks * KS <= nb_stages;
+    const bool b_resident = p.n_tiles == 1 && kchunks * KS <= nb_stages && !p.multi_w;
     // TC_NACC accumulator tiles in TMEM (all 512 columns at n_tile = 128): with two, the MMAs of tile t wait for the
     // epilogue of tile t-2, a chain of MMA drain + barrier wake-ups + store latency that idled the tensor pipe ~30 %
     const int nacc = TC_NACC;
@@ -184,7 +189,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     if (p.dbg & 2) { mbar_arrive(&full_a[stage]); if (++stage == NA) { stage = 0; phase ^= 1; } continue; }
                     mbar_expect_tx(&full_a[stage], a_copy_bytes * ncopies);
                     uint8_t* dst = a_buf + stage * A_STAGE;
-                    const CUtensorMap* mx = tc.pr == 0 ? &map_x : (tc.pr == 1 ? &map_x1 : &map_x2);
+                    const CUtensorMap* mx = tc.pr == 0 ? &map_x : (tc.pr == 1 ? &map_x1 : (tc.pr == 2 ? &map_x2 : &map_x3));
                     for (int cpy = 0; cpy < ncopies; ++cpy)
                         tma_load_4d(dst + cpy * TC_A_COPY_BYTES, mx, &full_a[stage], kc * KCH, x0 + cpy, y0, tc.b);
                     if (kc == kchunks - 1) TC_STAMP(tn, 1);
@@ -207,7 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                         for (int kx = 0; kx < KS; ++kx)
                             tma_load_2d(b_buf + stage * b_stage_bytes + kx * b_bytes, &map_w, &full_b[stage],
-                                        (ky * KS + kx) * p.Cin + kc * KCH, tc.nt * p.n_tile);
+                                        (ky * KS + kx) * p.Cin + kc * KCH, tc.nt * p.n_tile + p.prob[tc.pr].wrow);
                         if (++stage == nb_stages) { stage = 0; phase ^= 1; }
                     }
             }
@@ -349,7 +354,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 } else if (valid || stg) {
                     const int n0 = tc.nt * p.n_tile + cb;
                     float v[16];
-                    lds_bias16(bias_sa + n0 * 4, v);
+                    lds_bias16(bias_sa + (pq.wrow + n0) * 4, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fcvsr_act(__uint_as_float(r[j]) + v[j], p.act, slope);
                     if (pq.res && valid) {
@@ -456,7 +461,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             if (stg) {
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + eset), "r"(set_threads) : "memory");
                 if (stager) {
-                    const CUtensorMap* my = tc.pr == 0 ? &map_y : (tc.pr == 1 ? &map_y1 : &map_y2);
+                    const CUtensorMap* my = tc.pr == 0 ? &map_y : (tc.pr == 1 ? &map_y1 : (tc.pr == 2 ? &map_y2 : &map_y3));
                     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                  ::"l"(my), "r"(srow), "r"(0), "r"(tc.tx * TC_TW), "r"(tc.ty * TC_TH), "r"(tc.b) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -506,7 +511,8 @@ static int* tc_err_flag() {
 static int conv_tc_launch(int np, const void* const* xs, const float* const* ress, const float* const* res2s, float* const* ys,
                           float* const* y2s, const int* Hs, const int* Ws, int ldx, const float* w, const float* bias, int ldres,
                           int ldres2, int ldy, int B, int Cin, int Cout, int ksize, int act, float slope, const float* slope_ptr,
-                          int pixel_shuffle, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t st) {
+                          int pixel_shuffle, int ldy2, int round_out, int max_ctas, int op16, cudaStream_t st,
+                          const int* wrows = nullptr, int w_rows = 0) {
     if (np < 1 || np > TC_MAX_PROB || !w || B <= 0) return FCVSR_ERR_ARG;
     const int kch = op16 ? 64 : 32, esz = op16 ? 2 : 4;
     if ((ksize != 1 && ksize != 3) || Cin % kch || Cin <= 0 || Cout <= 0) return FCVSR_ERR_UNSUPPORTED;
@@ -564,7 +570,7 @@ static int conv_tc_launch(int np, const void* const* xs, const float* const* res
     }
     {
         const int ktot = ksize * ksize * Cin;
-        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)Cout};
+        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)(wrows ? w_rows : Cout)};
         cuuint64_t strides[1] = {(cuuint64_t)ktot * esz};
         cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)n_tile};
         cuuint32_t estr[2] = {1, 1};
@@ -577,12 +583,19 @@ static int conv_tc_launch(int np, const void* const* xs, const float* const* res
     p.B = B; p.Cin = Cin; p.Cout = Cout; p.ks = ksize; p.cout_valid = cout_valid;
     p.n_tile = n_tile; p.n_tiles = n_tiles;
     p.nprob = np;
+    p.w_rows = wrows ? w_rows : Cout; p.multi_w = wrows != nullptr;
+    if (wrows) {        // stacked filters: whole 64-channel 16-column-aligned filters, single N pass
+        if (thin || n_tiles != 1 || pixel_shuffle || w_rows < Cout || w_rows > TC_MAX_COUT) return FCVSR_ERR_UNSUPPORTED;
+        for (int i = 0; i < np; ++i)
+            if (wrows[i] < 0 || (wrows[i] & 15) || wrows[i] + Cout > w_rows) return FCVSR_ERR_ARG;
+    }
     int tiles = 0;
     for (int i = 0; i < TC_MAX_PROB; ++i) {
         ConvTcProblem& q = p.prob[i];
         const int j = i < np ? i : 0;
         q.res = ress ? ress[j] : nullptr; q.res2 = res2s ? res2s[j] : nullptr; q.y = ys[j]; q.y2 = y2s ? y2s[j] : nullptr;
         q.H = Hs[j]; q.W = Ws[j];
+        q.wrow = wrows ? wrows[j] : 0;
         q.tiles_x = (q.W + TC_TW - 1) / TC_TW; q.tiles_y = (q.H + TC_TH - 1) / TC_TH;
         q.tile_begin = tiles;
         if (i < np) tiles += q.tiles_x * q.tiles_y * B * n_tiles;
@@ -600,7 +613,7 @@ static int conv_tc_launch(int np, const void* const* xs, const float* const* res
     p.err = tc_err_flag();
     // bf16 outputs with 64 channels: the epilogue stages the tile in shared memory and stores it with TMA.  The staging tiles
     // (one per epilogue set) come out of the weight ring, which keeps at least the 72 KB that hold a 64 -> 64 3x3 filter resident.
-    const int smem_fixed = 1024 + TC_NA * TC_A_STAGE_BYTES + 512 + 4 * Cout;
+    const int smem_fixed = 1024 + TC_NA * TC_A_STAGE_BYTES + 512 + 4 * p.w_rows;
     p.stage_out = op16 && round_out == 1 && n_tile == 64 && n_tiles == 1 && !pixel_shuffle && !any_y2 && !thin && !(ldy & 7);
     p.b_ring_bytes = TC_B_RING_BYTES;
     if (p.stage_out) {
@@ -664,11 +677,11 @@ static int conv_tc_launch(int np, const void* const* xs, const float* const* res
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t le;
     if (op16) {
-        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, true>, map_x[0], map_x[1], map_x[2], map_w, map_y[0], map_y[1], map_y[2], p);
-        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, map_x[0], map_x[1], map_x[2], map_w, map_y[0], map_y[1], map_y[2], p);
+        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, true>, map_x[0], map_x[1], map_x[2], map_x[3], map_w, map_y[0], map_y[1], map_y[2], map_y[3], p);
+        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, true>, map_x[0], map_x[1], map_x[2], map_x[3], map_w, map_y[0], map_y[1], map_y[2], map_y[3], p);
     } else {
-        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, false>, map_x[0], map_x[1], map_x[2], map_w, map_y[0], map_y[1], map_y[2], p);
-        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, map_x[0], map_x[1], map_x[2], map_w, map_y[0], map_y[1], map_y[2], p);
+        if (ksize == 3) le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, false>, map_x[0], map_x[1], map_x[2], map_x[3], map_w, map_y[0], map_y[1], map_y[2], map_y[3], p);
+        else le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false>, map_x[0], map_x[1], map_x[2], map_x[3], map_w, map_y[0], map_y[1], map_y[2], map_y[3], p);
     }
     if (le != cudaSuccess) return FCVSR_ERR_CUDA;
     return fcvsr_launch_status();
@@ -698,4 +711,15 @@ extern "C" int fcvsr_conv2d_tc_multi(int nprob, const void* const* x, int ldx, c
     if (!x || !y || !H || !W) return FCVSR_ERR_ARG;
     return conv_tc_launch(nprob, x, res, nullptr, y, y2, H, W, ldx, w, bias, ldres, 0, ldy, B, Cin, Cout, ksize, act, slope,
                           slope_ptr, 0, ldy2, round_out, 0, op16, st);
+}
+
+// As fcvsr_conv2d_tc_multi with a different filter per problem: `w` / `bias` hold w_rows >= Cout rows (several [Cout][k*k*Cin]
+// filters stacked) and problem i uses rows wrow[i] .. wrow[i] + Cout (multiples of 16; HOST array).  Up to four problems: the
+// 1x1 `down` and `up` convolutions of a BlockRCB (CVSR_freq.py:753-763) -- two filters on two pyramid levels each -- are one launch.
+extern "C" int fcvsr_conv2d_tc_multi_w(int nprob, const void* const* x, int ldx, const float* w, const float* bias, const int* wrow,
+                                       int w_rows, float* const* y, int ldy, const int* H, const int* W, int B, int Cin, int Cout,
+                                       int ksize, int act, float slope, int round_out, int op16, cudaStream_t st) {
+    if (!x || !y || !H || !W || !wrow) return FCVSR_ERR_ARG;
+    return conv_tc_launch(nprob, x, nullptr, nullptr, y, nullptr, H, W, ldx, w, bias, 0, 0, ldy, B, Cin, Cout, ksize, act, slope,
+                          nullptr, 0, 0, round_out, 0, op16, st, wrow, w_rows);
 }

@@ -118,6 +118,7 @@ class Engine:
         self.rr16 = True             # RCB output rr only as a bf16 tensor
         self.t16 = True              # cross-level terms td / tu as bf16 tensors
         self.use_last_kernel = True  # dedicated Cout = 1 kernel
+        self.merge_down_up = True    # the 1x1 down / up convolutions of a BlockRCB as one launch (stacked filters)
         self.mgaa_ctas = 74          # SM cap of each of the two concurrently running MGAA calls
         self.stop_after = None       # tools/gpu_phase_times.py: return after "mgaa_pair" | "mgaa" | "mffr" | "scnet"
         self.profile_flavor = False  # tools: per-launch profile entries also name the output flavour
@@ -221,6 +222,11 @@ class Engine:
                 P[q + "a2"] = sd[pre + ".RCB.gcnet.channel_add_conv.2.weight"].reshape(n, n).contiguous()
                 P[q + "down"] = cp(pre + ".down.0")
                 P[q + "up"] = cp(pre + ".up.0")
+                if self.use_tc:       # both 1x1 filters stacked: one launch runs `down` on two levels and `up` on two levels
+                    dn, up = P[q + "down"], P[q + "up"]
+                    zb = torch.zeros(n, device=device, dtype=F32)
+                    P[q + "du_w"] = torch.cat([dn.w_tc, up.w_tc], 0).contiguous()
+                    P[q + "du_b"] = torch.cat([dn.bias if dn.bias is not None else zb, up.bias if up.bias is not None else zb]).contiguous()
         # --- tail (:2739-2749) ---
         c4 = n // 4
         ps_pos = torch.empty(n, dtype=torch.long, device=device)   # position of reference channel c*4+ij
@@ -412,6 +418,26 @@ class Engine:
                          4.0 * B * npix * (pk.cin_logical + pk.cout), e0, e1))
             return
         C.call("fcvsr_conv2d_tc_multi", *args)
+
+    def _conv_down_up(self, w, b, xs, ys, B, dims, rnd):
+        """The 1x1 `down` (filter rows 0..63) and `up` (rows 64..127) convolutions of a BlockRCB on two pyramid levels each, one launch."""
+        n = len(xs)
+        self.launches += 1
+        self.tc_launches += 1
+        vp = lambda ptrs: (ctypes.c_void_p * n)(*ptrs)  # noqa: E731
+        args = (n, vp(xs), 64, w.data_ptr(), b.data_ptr(), (ctypes.c_int * n)(0, 0, 64, 64), 128, vp(ys), 64,
+                (ctypes.c_int * n)(*[d[0] for d in dims]), (ctypes.c_int * n)(*[d[1] for d in dims]), B, 64, 64, 1, C.ACT_NONE, 0.0,
+                int(rnd), int(self.op16), self.st)
+        prof = self.profile
+        if prof is not None:
+            e0, e1 = self._event_pair()
+            e0.record()
+            C.call("fcvsr_conv2d_tc_multi_w", *args)
+            e1.record()
+            npix = sum(h * w_ for h, w_ in dims)
+            prof.append(("tc 64->64 k1 down+up x4", 2.0 * B * npix * 64 * 64, 4.0 * B * npix * 128, e0, e1))
+            return
+        C.call("fcvsr_conv2d_tc_multi_w", *args)
 
     def _event_pair(self):
         # inside a graph capture only "external" events become event-record nodes whose times can be read after a replay
@@ -748,8 +774,12 @@ class Engine:
                         vp(*[p[f"rrh{l}"] if (R and (l > 0 or rr16)) else 0 for l in L3]),
                         vp(p["rrp0"], p["rrp1"], 0), H3, W3, B, O16, int(not R), res16 | (2 if r016 else 0))
                 # down: 1x1 conv on the 2x2 mean == mean of the conv (:753-757); up: 1x1 conv, interpolated in level_mix (:759-763)
-                self._conv_multi(P[q + "down"], [p["rrp0"], p["rrp1"]], 64, [p["td0"], p["td1"]], 64, B, dims[1:], rnd=bool(t16))
-                self._conv_multi(P[q + "up"], rr_op[1:], 64, [p["tu1"], p["tu2"]], 64, B, dims[1:], rnd=bool(t16))
+                if R and self.merge_down_up:
+                    self._conv_down_up(P[q + "du_w"], P[q + "du_b"], [p["rrp0"], p["rrp1"], rr_op[1], rr_op[2]],
+                                       [p["td0"], p["td1"], p["tu1"], p["tu2"]], B, [dims[1], dims[2], dims[1], dims[2]], bool(t16))
+                else:
+                    self._conv_multi(P[q + "down"], [p["rrp0"], p["rrp1"]], 64, [p["td0"], p["td1"]], 64, B, dims[1:], rnd=bool(t16))
+                    self._conv_multi(P[q + "up"], rr_op[1:], 64, [p["tu1"], p["tu2"]], 64, B, dims[1:], rnd=bool(t16))
                 # x + r + d + u (:771-776)
                 self._k("fcvsr_level_mix_multi", 3, vp(*src), 64, vp(*[p[f"t{l}"] for l in L3]), 64,
                         vp(*[p[f"rrh{l}" if rr16 else f"rr{l}"] for l in L3]), coef3, vp(0, p["td0"], p["td1"]),

@@ -146,6 +146,13 @@ int fcvsr_divenh_step(const float* x_prev, const float* a_prev, const float* b_p
 int fcvsr_mffr_final(const float* so, const float* gate, const float* x, int ldx, float* y, int ldy, int B, int P,
                      cudaStream_t stream);
 
+/* fcvsr_conv2d_tc_multi with a different filter per problem (csrc/conv_tc.cu): w / bias hold w_rows >= Cout rows (several
+ * [Cout][k*k*Cin] filters stacked), problem i uses rows wrow[i] .. wrow[i] + Cout (HOST array, multiples of 16); up to four
+ * problems.  The 1x1 `down` and `up` convolutions of a BlockRCB (CVSR_freq.py:753-763) run as one launch this way. */
+int fcvsr_conv2d_tc_multi_w(int nprob, const void* const* x, int ldx, const float* w, const float* bias, const int* wrow,
+                            int w_rows, float* const* y, int ldy, const int* H, const int* W, int B, int Cin, int Cout,
+                            int ksize, int act, float slope, int round_out, int op16, cudaStream_t stream);
+
 /* ---- SCNetbk helpers (CVSR_freq.py:657-777) ----------------------------------------------------- */
 
 /* ContextBlock (:657-701): add[b][64] = W2 lrelu_0.2(W1 softmax-pool(x)); partial [B][ceil(P/128)][66] (scratch).

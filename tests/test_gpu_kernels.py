@@ -414,3 +414,41 @@ def test_deform_conv_cuda_module_mirrors_reference_entry_points(dev):
         assert float((yh.float().cpu() - ref16).abs().max()) <= 2.0 ** -9 * max(1.0, float(ref16.abs().max()))
     finally:
         dcn_mod.PRECISION = old
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# fcvsr_conv2d_tc_multi_w: the 1x1 `down` and `up` convolutions of a BlockRCB (CVSR_freq.py:753-763) as one launch
+# ------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("op16", [0, 1])
+def test_conv_multi_stacked_filters(dev, op16):
+    """Four problems (two pyramid levels x two stacked 64 -> 64 1x1 filters with bias) in one launch against F.conv2d on the
+    operand-rounded inputs / weights; ragged tiles (sizes that are not multiples of the 8 x 16 tile)."""
+    import ctypes
+    g = torch.Generator().manual_seed(3 + op16)
+    B = 2
+    dims = [(18, 20), (9, 10), (18, 20), (9, 10)]
+    wrow = [0, 0, 64, 64]
+    w = torch.randn(128, 64, generator=g) / 8
+    b = torch.randn(128, generator=g)
+    xs = [torch.randn(B, 64, h, ww, generator=g) for h, ww in dims]
+    if op16:
+        rnd = lambda t: t.to(torch.bfloat16).float()  # noqa: E731
+    else:
+        rnd = lambda t: ((t.contiguous().view(torch.int32) + 0x1000) & -8192).view(torch.float32)  # noqa: E731
+    wr = rnd(w)
+    dt = torch.bfloat16 if op16 else torch.float32
+    xd = [nhwc(rnd(x)).to(dev).to(dt).contiguous() for x in xs]
+    wd = wr.to(dev).to(dt).contiguous()
+    bd = b.to(dev)
+    yd = [torch.zeros(B, h, ww, 64, device=dev, dtype=dt) for h, ww in dims]
+    n = 4
+    vp = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
+    ia = lambda v: (ctypes.c_int * n)(*v)  # noqa: E731
+    C.call("fcvsr_conv2d_tc_multi_w", n, vp(xd), 64, wd.data_ptr(), bd.data_ptr(), ia(wrow), 128, vp(yd), 64, ia([d[0] for d in dims]),
+           ia([d[1] for d in dims]), B, 64, 64, 1, C.ACT_NONE, 0.0, op16, op16, _st())
+    torch.cuda.synchronize()
+    for i in range(n):
+        ref = F.conv2d(rnd(xs[i]), wr[wrow[i]:wrow[i] + 64].view(64, 64, 1, 1), b[wrow[i]:wrow[i] + 64])
+        got = nchw(yd[i].float().cpu())
+        tol = (2 ** -8 if op16 else 2e-5) * max(1.0, float(ref.abs().max()))
+        assert float((got - ref).abs().max()) <= tol, (i, float((got - ref).abs().max()))
