@@ -10,12 +10,13 @@
 //
 // Tile = 8 rows x 14 output columns; with the one-column halo of the horizontal pass that is 8 x 16 = 128 pixels = the M of one
 // MMA, so TMEM lane == haloed pixel.  A thread owns one haloed pixel and 16 channels (warp w: lane quarter w & 3 of TMEM, channel
-// group w >> 2) and reads the taps from TMEM where each pass uses them (fp32, never rounded); the sample and vertical-pass
-// tiles live in shared memory pixel-major with a 68-float pitch, so that the 16-byte accesses of 8 consecutive pixels (one
-// wavefront) fall into 8 different 4-bank groups.
+// group w >> 2) and reads the taps from TMEM once per four channels (fp32, never rounded); the sample tile and the result tile
+// live in shared memory pixel-major with a 68-float pitch, so that the 16-byte accesses of 8 consecutive pixels (one wavefront)
+// fall into 8 different 4-bank groups.
 // Order inside a CTA: operand tiles by cp.async -> sample geometry of both directions -> MMA issued -> per direction: bilinear
-// gathers (the MMA runs under the first ones) -> taps from TMEM -> vertical pass -> horizontal pass.  Both directions share
-// the taps (:1526-1527 call IAC with the same Pred_K), so one CTA serves both and kp2 is read once.
+// gathers (the MMA runs under the first ones) -> both filter passes in one phase (vertical pass from the sample tile, the
+// neighbouring columns of the horizontal pass by warp shuffle: a warp holds two tile rows of 16 columns) -> coalesced output
+// stage.  Both directions share the taps (:1526-1527 call IAC with the same Pred_K), so one CTA serves both and kp2 is read once.
 #include "tc_common.cuh"
 
 #define IT_TH 8
