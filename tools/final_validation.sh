@@ -6,7 +6,7 @@ python bench.py --dtype tf32 --no-cpu-baseline > gpurun_out/final_tf32.json 2> g
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final_ref.json 2>/dev/null; head -c 250 gpurun_out/final_ref.json
 L=$(python -c "import json;d=json.load(open('gpurun_out/final_bf16.json'));print(d['gpu_launches']//d['steps'])")
 echo launches per step $L
-ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip $((3*L)) --launch-count $L --csv --log-file gpurun_out/r1_launches_step_b4.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/final_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip $((3*L)) --launch-count $L --csv --log-file gpurun_out/final_launches_step.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/final_ncu.log 2>&1
 tail -c 300 gpurun_out/final_ncu.log
 if [ -n "$FULL" ]; then
 python bench.py --variant S --height 272 --width 480 --batch 2 --no-cpu-baseline > gpurun_out/final_S_272x480.json 2>/dev/null; head -c 160 gpurun_out/final_S_272x480.json; echo
