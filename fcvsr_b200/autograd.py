@@ -56,6 +56,12 @@ def _tc_ok(cin: int, cout: int, k: int, stride: int) -> bool:
     return stride == 1 and k in (1, 3) and cin % 32 == 0 and (cout % 16 == 0 or cout < 16) and cout <= 2048
 
 
+def _is_conv4(ci: int, co: int, k: int, stride: int, bias) -> bool:
+    """The 4 -> 4 channel ConvBlk convolutions (CVSR_freq.py:344-357: k = 1 .. 11, no bias): dedicated kernels in both modes (exact
+    fp32 FFMA) -- the generic kernels tile 64 pixels x 64 channels and spend 1/16 .. 1/256 of their work on this shape."""
+    return ci == 4 and co == 4 and stride == 1 and (k & 1) and k <= 11 and bias is None
+
+
 def _conv_launch(xh: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride: int, mode: str,
                  transposed: bool = False) -> torch.Tensor:
     """y = conv(x, w) + bias on an NHWC buffer; w in the reference's [Cout, Cin, k, k] layout.  transposed: the data gradient --
@@ -70,6 +76,11 @@ def _conv_launch(xh: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     ho, wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     y = torch.empty(B, ho, wo, co, device=xh.device, dtype=F32)
     bp = bias.contiguous().data_ptr() if bias is not None else 0
+    if _is_conv4(ci, co, k, stride, bias):
+        # transposed (data gradient): w'[tap][co][ci] = w[k*k - 1 - tap][ci][co]
+        wd = (w.flip(2, 3).permute(2, 3, 0, 1) if transposed else w.permute(2, 3, 1, 0)).contiguous()
+        C.call("fcvsr_conv4x4", xh.data_ptr(), wd.data_ptr(), y.data_ptr(), B, H, W, k, _st())
+        return y
     if mode == "tf32" and _tc_ok(ci, co, k, stride):
         xr = torch.empty_like(xh)                            # tcgen05 truncates TF32 operands: round to nearest first
         C.call("fcvsr_round_copy", xh.data_ptr(), ci, xr.data_ptr(), ci, ci, ci, B * H * W, 0, _st())
@@ -110,7 +121,7 @@ class _Conv2d(torch.autograd.Function):
         gx = gw = gb = None
         with torch.cuda.device(xh.device):
             if ctx.needs_input_grad[0]:
-                if mode == "tf32" and _tc_ok(co, ci, k, stride):
+                if _is_conv4(ci, co, k, stride, None if not ctx.has_bias else 1) or (mode == "tf32" and _tc_ok(co, ci, k, stride)):
                     # dx = conv(dy, w') with w'[ci][co][ky][kx] = w[co][ci][k-1-ky][k-1-kx]
                     dx = _conv_launch(g, w, None, 1, mode, transposed=True)
                 else:
@@ -121,7 +132,9 @@ class _Conv2d(torch.autograd.Function):
                 gx = _logical(dx)
             if ctx.needs_input_grad[1]:
                 dw = torch.zeros(k * k, ci, co, device=xh.device, dtype=F32)
-                if mode == "tf32" and WGRAD_TC and stride == 1 and k in (1, 3) and ci % 64 == 0 and co % 64 == 0:
+                if _is_conv4(ci, co, k, stride, None if not ctx.has_bias else 1):
+                    C.call("fcvsr_conv4x4_wgrad", xh.data_ptr(), g.data_ptr(), dw.data_ptr(), B, H, W, k, _st())
+                elif mode == "tf32" and WGRAD_TC and stride == 1 and k in (1, 3) and ci % 64 == 0 and co % 64 == 0:
                     # tensor-core weight gradient: bf16 copies of the activations and of the upstream gradient, fp32 accumulation
                     xb = torch.empty(B, H, W, ci, device=xh.device, dtype=torch.bfloat16)
                     gb16 = torch.empty(B, H, W, co, device=xh.device, dtype=torch.bfloat16)

@@ -272,6 +272,130 @@ extern "C" int fcvsr_offset_blocks(const float* off, const float* w1, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same 4 -> 4 channel convolution as a stand-alone operator for the training step (the ConvBlk convolutions of
+// CVSR_freq.py:344-357 under autograd): forward, data gradient (the forward kernel on flipped / transposed weights) and weight
+// gradient.  The generic CUDA-core kernels tile 64 pixels x 64 channels, so a 4 x 4 filter used 1/16 .. 1/256 of their work
+// (11 x 11: 387 us forward, 1.5 ms backward at 16 x 64 x 33; 36 such convolutions per training step).
+template <int DUMMY>
+__global__ void __launch_bounds__(OB_THREADS) conv4_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                                                           int H, int Wd, int tiles_x, int k) {
+    __shared__ __align__(16) float ws[121 * 16];
+    __shared__ __align__(16) float4 tile[(OB_TH + OB_KMAX - 1) * OB_ROWF4];
+    const int pad = k >> 1, b = blockIdx.y;
+    const int ty0 = (blockIdx.x / tiles_x) * OB_TH, tx0 = (blockIdx.x % tiles_x) * OB_TW;
+    const size_t P = (size_t)H * Wd;
+    for (int t = threadIdx.x; t < k * k * 16; t += blockDim.x) ws[t] = w[t];
+    {
+        const float* src = x + (size_t)b * P * 4;
+        const int tw = OB_TW + k - 1, th = OB_TH + k - 1;
+        for (int e = threadIdx.x; e < th * tw; e += blockDim.x) {
+            const int rr = e / tw, pp = e - rr * tw;
+            const int yy = ty0 - pad + rr, xx = tx0 - pad + pp;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < Wd) v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)yy * Wd + xx) * 4));
+            tile[rr * OB_ROWF4 + (pp & 3) * OB_SLOTS + (pp >> 2)] = v;
+        }
+    }
+    __syncthreads();
+    const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+    const int yo = ty0 + r, x0 = tx0 + 4 * c;
+    if (yo >= H || x0 >= Wd) return;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int co = 0; co < 4; ++co) acc[j][co] = 0.f;
+    switch (k) {
+        case 1: ob_conv_quad<1, false>(tile, ws, r, c, acc); break;
+        case 3: ob_conv_quad<3, false>(tile, ws, r, c, acc); break;
+        case 5: ob_conv_quad<5, false>(tile, ws, r, c, acc); break;
+        case 7: ob_conv_quad<7, false>(tile, ws, r, c, acc); break;
+        case 9: ob_conv_quad<9, false>(tile, ws, r, c, acc); break;
+        default: ob_conv_quad<11, false>(tile, ws, r, c, acc); break;
+    }
+    float* dst = y + ((size_t)b * P + (size_t)yo * Wd + x0) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (x0 + j < Wd) *reinterpret_cast<float4*>(dst + j * 4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+}
+
+// x, y: [B,H,W,4] fp32; w: [k*k][ci][co] (the layout of fcvsr_conv2d_direct); k odd, <= 11, zero padding k / 2, stride 1.
+// The data gradient is the same call with dy as x and w'[tap'][co][ci] = w[k*k - 1 - tap'][ci][co].
+extern "C" int fcvsr_conv4x4(const float* x, const float* w, float* y, int B, int H, int W, int ksize, cudaStream_t st) {
+    if (!x || !w || !y || B <= 0 || H <= 0 || W <= 0 || !(ksize & 1) || ksize < 1 || ksize > OB_KMAX) return FCVSR_ERR_ARG;
+    if (((uintptr_t)x | (uintptr_t)y) & 15) return FCVSR_ERR_ARG;
+    const int tiles_x = (W + OB_TW - 1) / OB_TW, tiles = tiles_x * ((H + OB_TH - 1) / OB_TH);
+    if (B > 65535) return FCVSR_ERR_UNSUPPORTED;
+    conv4_kernel<0><<<dim3(tiles, B), OB_THREADS, 0, st>>>(x, w, y, H, W, tiles_x, ksize);
+    return fcvsr_launch_status();
+}
+
+// Weight gradient dw[tap][ci][co] += sum_p x[p + tap - pad][ci] * dy[p][co] of the same convolution.  A thread owns ONE filter
+// tap (and, when there are fewer than 64 taps, one slice of the tile's rows) and walks the tile's pixels: x comes from the
+// haloed tile in shared memory (neighbouring taps = neighbouring pixels), dy is a broadcast read, 16 FMAs per pixel, no
+// reduction across threads; one vector of 16 atomics per thread and tile at the end.
+__global__ void __launch_bounds__(OB_THREADS) conv4_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 float* __restrict__ dw, int H, int Wd, int tiles_x, int k) {
+    constexpr int XP = OB_TW + OB_KMAX - 1;                       // x tile pitch in float4
+    __shared__ __align__(16) float4 xt[(OB_TH + OB_KMAX - 1) * XP];
+    __shared__ __align__(16) float4 gt[OB_TH * OB_TW];
+    const int pad = k >> 1, b = blockIdx.y;
+    const int ty0 = (blockIdx.x / tiles_x) * OB_TH, tx0 = (blockIdx.x % tiles_x) * OB_TW;
+    const size_t P = (size_t)H * Wd;
+    const float* xs = x + (size_t)b * P * 4;
+    const float* gs = dy + (size_t)b * P * 4;
+    const int tw = OB_TW + k - 1, th = OB_TH + k - 1;
+    for (int e = threadIdx.x; e < th * tw; e += blockDim.x) {
+        const int rr = e / tw, pp = e - rr * tw;
+        const int yy = ty0 - pad + rr, xx = tx0 - pad + pp;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < Wd) v = __ldg(reinterpret_cast<const float4*>(xs + ((size_t)yy * Wd + xx) * 4));
+        xt[rr * XP + pp] = v;
+    }
+    for (int e = threadIdx.x; e < OB_TH * OB_TW; e += blockDim.x) {
+        const int rr = e / OB_TW, pp = e - rr * OB_TW;
+        const int yy = ty0 + rr, xx = tx0 + pp;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy < H && xx < Wd) v = __ldg(reinterpret_cast<const float4*>(gs + ((size_t)yy * Wd + xx) * 4));
+        gt[e] = v;
+    }
+    __syncthreads();
+    const int nt = k * k;
+    const int groups = OB_THREADS / nt > OB_TH ? OB_TH : (OB_THREADS / nt < 1 ? 1 : OB_THREADS / nt);   // row slices
+    const int tap = threadIdx.x % nt, slice = threadIdx.x / nt;
+    if (slice >= groups) return;
+    const int ky = tap / k, kx = tap - ky * k;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int r = slice; r < OB_TH; r += groups) {
+        const float4* xr = xt + (r + ky) * XP + kx;
+        const float4* gr = gt + r * OB_TW;
+#pragma unroll 4
+        for (int c = 0; c < OB_TW; ++c) {
+            const float4 xv = xr[c], gv = gr[c];
+            acc[0] = fmaf(xv.x, gv.x, acc[0]); acc[1] = fmaf(xv.x, gv.y, acc[1]); acc[2] = fmaf(xv.x, gv.z, acc[2]); acc[3] = fmaf(xv.x, gv.w, acc[3]);
+            acc[4] = fmaf(xv.y, gv.x, acc[4]); acc[5] = fmaf(xv.y, gv.y, acc[5]); acc[6] = fmaf(xv.y, gv.z, acc[6]); acc[7] = fmaf(xv.y, gv.w, acc[7]);
+            acc[8] = fmaf(xv.z, gv.x, acc[8]); acc[9] = fmaf(xv.z, gv.y, acc[9]); acc[10] = fmaf(xv.z, gv.z, acc[10]); acc[11] = fmaf(xv.z, gv.w, acc[11]);
+            acc[12] = fmaf(xv.w, gv.x, acc[12]); acc[13] = fmaf(xv.w, gv.y, acc[13]); acc[14] = fmaf(xv.w, gv.z, acc[14]); acc[15] = fmaf(xv.w, gv.w, acc[15]);
+        }
+    }
+    float* d = dw + (size_t)tap * 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) atomicAdd(d + i, acc[i]);
+}
+
+// dw: [k*k][4][4] fp32, ACCUMULATED with atomics (zero it first), as fcvsr_conv2d_wgrad.
+extern "C" int fcvsr_conv4x4_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int ksize, cudaStream_t st) {
+    if (!x || !dy || !dw || B <= 0 || H <= 0 || W <= 0 || !(ksize & 1) || ksize < 1 || ksize > OB_KMAX) return FCVSR_ERR_ARG;
+    if (((uintptr_t)x | (uintptr_t)dy) & 15) return FCVSR_ERR_ARG;
+    const int tiles_x = (W + OB_TW - 1) / OB_TW, tiles = tiles_x * ((H + OB_TH - 1) / OB_TH);
+    if (B > 65535) return FCVSR_ERR_UNSUPPORTED;
+    conv4_wgrad_kernel<<<dim3(tiles, B), OB_THREADS, 0, st>>>(x, dy, dw, H, W, tiles_x, ksize);
+    return fcvsr_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
 // One IAC iteration for both directions.  Tile = 8 x 16 output pixels x 64 channels; a half-warp owns a
 // pixel at a time and a lane owns 4 consecutive channels (16-byte accesses, two pixels per warp instruction).
 //   samp(y',x')  = bilinear(prev, x'+dx(y',x'), y'+dy(y',x'))        zeros outside, align_corners

@@ -259,6 +259,12 @@ int fcvsr_conv2d_dgrad_direct(const float* dy, int lddy, const float* wt, float*
  * fp32 atomics over pixel slices (zero-fill first; run-to-run differences at rounding level, as cuDNN's atomic wgrad). */
 int fcvsr_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
                        int ksize, int stride, cudaStream_t stream);
+/* 4 -> 4 channel convolutions (the ConvBlk convolutions of CVSR_freq.py:344-357 under autograd; csrc/mgaa.cu): x, y, dy
+ * [B,H,W,4] fp32 (16-byte aligned), w [k*k][ci][co], k odd <= 11, stride 1, zero padding k / 2, no bias.  The data gradient is
+ * fcvsr_conv4x4 on dy with w'[tap][co][ci] = w[k*k - 1 - tap][ci][co]; fcvsr_conv4x4_wgrad ACCUMULATES dw [k*k][4][4] with
+ * fp32 atomics (zero it first).  They replace the generic 64 x 64-tiled kernels above for this shape (1/16 .. 1/256 useful work). */
+int fcvsr_conv4x4(const float* x, const float* w, float* y, int B, int H, int W, int ksize, cudaStream_t stream);
+int fcvsr_conv4x4_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int ksize, cudaStream_t stream);
 /* The same weight gradient on the tcgen05 tensor cores (csrc/wgrad_tc.cu): x and dy are BF16 NHWC tensors (ld in elements,
  * % 8 == 0, 16-byte aligned), fp32 accumulation in TMEM over a split of the pixel tiles, fp32 vector reductions into dw.
  * k in {1, 3}, stride 1, Cin % 64 == 0, Cout % 64 == 0; other shapes return FCVSR_ERR_UNSUPPORTED (use fcvsr_conv2d_wgrad). */

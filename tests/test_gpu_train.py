@@ -70,6 +70,29 @@ def test_conv2d_function_forward_and_gradients(dev, ci, co, k, stride, H, W, mod
         assert _rel(a.grad.cpu(), r.grad) <= t, (name, _rel(a.grad.cpu(), r.grad))
 
 
+@pytest.mark.parametrize("k,H,W", [(1, 10, 9), (3, 7, 70), (5, 20, 33), (9, 64, 33), (11, 9, 6), (11, 70, 130)])
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_conv4x4_function_forward_and_gradients(dev, k, H, W, mode):
+    """The bias-free 4 -> 4 ConvBlk convolutions (CVSR_freq.py:344-357) on their dedicated kernels (fcvsr_conv4x4 forward and --
+    on flipped / transposed weights -- data gradient, fcvsr_conv4x4_wgrad): exact fp32 in both modes, against F.conv2d +
+    autograd on the CPU; maps smaller than the filter, ragged and multiple 8 x 64 tiles."""
+    g = torch.Generator().manual_seed(k * 100 + H)
+    x = torch.randn(3, 4, H, W, generator=g)
+    w = torch.randn(4, 4, k, k, generator=g) / math.sqrt(4 * k * k)
+    gy = torch.randn(3, 4, H, W, generator=g)
+    ref_in = [t.clone().requires_grad_(True) for t in (x, w)]
+    yr = F.conv2d(ref_in[0], ref_in[1], None, padding=k // 2)
+    (yr * gy).sum().backward()
+    ins = [t.to(dev).requires_grad_(True) for t in (x, w)]
+    assert A._is_conv4(4, 4, k, 1, None)
+    y = A.conv2d(_cl(ins[0]), ins[1], None, 1, mode)
+    (y * gy.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert _rel(y.detach().cpu(), yr.detach()) <= 2e-5
+    for name, a, r in zip(("x", "w"), ins, ref_in):
+        assert _rel(a.grad.cpu(), r.grad) <= 2e-5, (name, _rel(a.grad.cpu(), r.grad))
+
+
 @pytest.mark.parametrize("B,ci,co,k,H,W", [(2, 64, 64, 3, 16, 32), (1, 64, 128, 3, 19, 37), (3, 128, 64, 3, 8, 16), (1, 64, 256, 1, 24, 20),
                                           (2, 256, 64, 3, 12, 18), (8, 64, 64, 3, 64, 64)])
 def test_wgrad_tcgen05_kernel(dev, B, ci, co, k, H, W):
