@@ -53,6 +53,7 @@ SIGNATURES = {
     "fcvsr_conv2d_dgrad_direct": "pi p pi iiiiiii s",
     "fcvsr_conv2d_wgrad": "pi pi p iiiiiii s",
     "fcvsr_conv2d_wgrad_tc": "pi pi p iiiiii s",
+    "fcvsr_round_copy_dual": "ppp l s",
     "fcvsr_conv4x4": "ppp iiii s",
     "fcvsr_conv4x4_wgrad": "ppp iiii s",
     "fcvsr_pack_conv_weight": "pp iiiii s",

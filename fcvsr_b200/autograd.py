@@ -63,9 +63,11 @@ def _is_conv4(ci: int, co: int, k: int, stride: int, bias) -> bool:
 
 
 def _conv_launch(xh: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride: int, mode: str,
-                 transposed: bool = False) -> torch.Tensor:
+                 transposed: bool = False, x16: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = conv(x, w) + bias on an NHWC buffer; w in the reference's [Cout, Cin, k, k] layout.  transposed: the data gradient --
-    x is dy and the convolution runs with w's taps flipped and its channel axes swapped (stride 1 only)."""
+    x is dy and the convolution runs with w's taps flipped and its channel axes swapped (stride 1 only).  x16: optional bf16
+    buffer of x's shape that receives the bf16 copy of x in the same pass as the TF32-rounded one (tensor-core path only: the
+    operand of the tcgen05 weight gradient)."""
     B, H, W, ci = xh.shape
     if transposed:
         ci_w, co, k, _ = w.shape
@@ -83,7 +85,7 @@ def _conv_launch(xh: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
         return y
     if mode == "tf32" and _tc_ok(ci, co, k, stride):
         xr = torch.empty_like(xh)                            # tcgen05 truncates TF32 operands: round to nearest first
-        C.call("fcvsr_round_copy", xh.data_ptr(), ci, xr.data_ptr(), ci, ci, ci, B * H * W, 0, _st())
+        C.call("fcvsr_round_copy_dual", xh.data_ptr(), xr.data_ptr(), x16.data_ptr() if x16 is not None else 0, xh.numel(), _st())
         wt = torch.empty(max(co, 16), k * k * ci, device=xh.device, dtype=F32)
         wc = w.contiguous()
         C.call("fcvsr_pack_conv_weight", wc.data_ptr(), wt.data_ptr(), wc.shape[0], wc.shape[1], k, int(transposed), 16, _st())
@@ -103,10 +105,16 @@ class _Conv2d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, stride, mode):
         xh = _nhwc(x)
+        co, ci, k, _ = w.shape
+        # tcgen05 weight gradient ahead: its bf16 copy of the activation is made in the same pass as the forward's TF32-rounded
+        # copy and is what backward keeps (half the bytes of the fp32 activation, one launch less per convolution)
+        wg_tc = (mode == "tf32" and WGRAD_TC and stride == 1 and k in (1, 3) and ci % 64 == 0 and co % 64 == 0
+                 and ctx.needs_input_grad[1] and _tc_ok(ci, co, k, stride))
+        xb = torch.empty(xh.shape, device=xh.device, dtype=torch.bfloat16) if wg_tc else None
         with torch.cuda.device(x.device):
-            y = _conv_launch(xh, w.detach(), None if bias is None else bias.detach(), stride, mode)
-        ctx.save_for_backward(xh, w)
-        ctx.stride, ctx.mode, ctx.has_bias = stride, mode, bias is not None
+            y = _conv_launch(xh, w.detach(), None if bias is None else bias.detach(), stride, mode, x16=xb)
+        ctx.save_for_backward(xb if wg_tc else xh, w)
+        ctx.stride, ctx.mode, ctx.has_bias, ctx.wg_tc = stride, mode, bias is not None, wg_tc
         return _logical(y)
 
     @staticmethod
@@ -119,11 +127,16 @@ class _Conv2d(torch.autograd.Function):
         B, H, W, ci = xh.shape
         co, _, k, _ = w.shape
         gx = gw = gb = None
+        wg_tc = ctx.wg_tc and ctx.needs_input_grad[1]
+        gb16 = torch.empty(g.shape, device=g.device, dtype=torch.bfloat16) if wg_tc else None
+        g16_done = False
         with torch.cuda.device(xh.device):
             if ctx.needs_input_grad[0]:
                 if _is_conv4(ci, co, k, stride, None if not ctx.has_bias else 1) or (mode == "tf32" and _tc_ok(co, ci, k, stride)):
                     # dx = conv(dy, w') with w'[ci][co][ky][kx] = w[co][ci][k-1-ky][k-1-kx]
-                    dx = _conv_launch(g, w, None, 1, mode, transposed=True)
+                    tc_dgrad = not _is_conv4(ci, co, k, stride, None if not ctx.has_bias else 1)
+                    dx = _conv_launch(g, w, None, 1, mode, transposed=True, x16=gb16 if tc_dgrad else None)
+                    g16_done = tc_dgrad and gb16 is not None
                 else:
                     dx = torch.empty(B, H, W, ci, device=xh.device, dtype=F32)
                     wt = w.permute(2, 3, 0, 1).contiguous()                      # [k*k][Cout][Cin]
@@ -134,13 +147,12 @@ class _Conv2d(torch.autograd.Function):
                 dw = torch.zeros(k * k, ci, co, device=xh.device, dtype=F32)
                 if _is_conv4(ci, co, k, stride, None if not ctx.has_bias else 1):
                     C.call("fcvsr_conv4x4_wgrad", xh.data_ptr(), g.data_ptr(), dw.data_ptr(), B, H, W, k, _st())
-                elif mode == "tf32" and WGRAD_TC and stride == 1 and k in (1, 3) and ci % 64 == 0 and co % 64 == 0:
-                    # tensor-core weight gradient: bf16 copies of the activations and of the upstream gradient, fp32 accumulation
-                    xb = torch.empty(B, H, W, ci, device=xh.device, dtype=torch.bfloat16)
-                    gb16 = torch.empty(B, H, W, co, device=xh.device, dtype=torch.bfloat16)
-                    C.call("fcvsr_round_copy", xh.data_ptr(), ci, xb.data_ptr(), ci, ci, ci, B * H * W, 1, _st())
-                    C.call("fcvsr_round_copy", g.data_ptr(), co, gb16.data_ptr(), co, co, co, B * H * W, 1, _st())
-                    C.call("fcvsr_conv2d_wgrad_tc", xb.data_ptr(), ci, gb16.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, _st())
+                elif wg_tc:
+                    # tensor-core weight gradient: bf16 copies of the activation (made by the forward pass) and of the upstream
+                    # gradient (made together with the data gradient's TF32 copy when there is one), fp32 accumulation
+                    if not g16_done:
+                        C.call("fcvsr_round_copy_dual", g.data_ptr(), 0, gb16.data_ptr(), g.numel(), _st())
+                    C.call("fcvsr_conv2d_wgrad_tc", xh.data_ptr(), ci, gb16.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, _st())
                 else:
                     C.call("fcvsr_conv2d_wgrad", xh.data_ptr(), ci, g.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, stride, _st())
                 gw = dw.view(k, k, ci, co).permute(3, 2, 0, 1)

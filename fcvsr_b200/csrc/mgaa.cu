@@ -649,6 +649,25 @@ __global__ void round_copy_kernel(const float* __restrict__ x, int ldx, void* __
     store_operand4(y, pix * ldy + c, v, op16);
 }
 
+// Both operand-typed copies of a dense [npix, C] tensor in one pass: y32 = TF32-rounded fp32, y16 = bf16 (either may be NULL).
+// The training step needs both of an activation (forward convolution / tcgen05 weight gradient) and of an upstream gradient
+// (data-gradient convolution / weight gradient); as separate launches these copies were 2239 launches of ~3 us per step.
+__global__ void round_copy_dual_kernel(const float* __restrict__ x, float* __restrict__ y32, void* __restrict__ y16, size_t total4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    if (y32) store_operand4(y32, i * 4, v, 0);
+    if (y16) store_operand4(y16, i * 4, v, 1);
+}
+
+extern "C" int fcvsr_round_copy_dual(const float* x, float* y_tf32, void* y_bf16, long long numel, cudaStream_t st) {
+    if (!x || (!y_tf32 && !y_bf16) || numel <= 0 || (numel & 3) || ((uintptr_t)x & 15) || ((uintptr_t)y_tf32 & 15) || ((uintptr_t)y_bf16 & 7))
+        return FCVSR_ERR_ARG;
+    const size_t total4 = (size_t)numel / 4;
+    round_copy_dual_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x, y_tf32, y_bf16, total4);
+    return fcvsr_launch_status();
+}
+
 extern "C" int fcvsr_round_copy(const float* x, int ldx, void* y, int ldy, int C, int Cy, long long npix, int op16,
                                 cudaStream_t st) {
     if (!x || !y || (C & 3) || (Cy & 3) || Cy < C || (ldx & 3) || (ldy & 3)) return FCVSR_ERR_ARG;

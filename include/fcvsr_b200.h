@@ -259,6 +259,9 @@ int fcvsr_conv2d_dgrad_direct(const float* dy, int lddy, const float* wt, float*
  * fp32 atomics over pixel slices (zero-fill first; run-to-run differences at rounding level, as cuDNN's atomic wgrad). */
 int fcvsr_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int H, int W, int Cin, int Cout,
                        int ksize, int stride, cudaStream_t stream);
+/* Both operand-typed copies of a dense fp32 tensor in one pass: y_tf32 = values rounded to nearest TF32 (fp32 storage), y_bf16 =
+ * bf16; either may be NULL; numel % 4 == 0.  (Forward / data-gradient operands and the tcgen05 weight gradient's operands.) */
+int fcvsr_round_copy_dual(const float* x, float* y_tf32, void* y_bf16, long long numel, cudaStream_t stream);
 /* 4 -> 4 channel convolutions (the ConvBlk convolutions of CVSR_freq.py:344-357 under autograd; csrc/mgaa.cu): x, y, dy
  * [B,H,W,4] fp32 (16-byte aligned), w [k*k][ci][co], k odd <= 11, stride 1, zero padding k / 2, no bias.  The data gradient is
  * fcvsr_conv4x4 on dy with w'[tap][co][ci] = w[k*k - 1 - tap][ci][co]; fcvsr_conv4x4_wgrad ACCUMULATES dw [k*k][4][4] with
