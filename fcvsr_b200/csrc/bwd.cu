@@ -88,9 +88,70 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(WgradArgs a) {
     }
 }
 
+// Thin heads (Cout <= 4: conv_last0 64 -> 1, the 64 -> 4 offset / similarity heads): the 64 x 64 slab of the kernel above is
+// 1/16 .. 1/64 full.  Here a block owns WT_ROWS image rows and ONE filter tap; thread = (4 input channels, pixel slot): it
+// walks its pixels (the 4-channel groups of a pixel are one coalesced line), 4 x Cout FMAs each, the slots are summed through
+// shared memory and the block adds its 4 x Cin x Cout partial sums with atomics.
+#define WT_ROWS 16
+__global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(WgradArgs a) {
+    __shared__ float red[256 * 16];
+    const int ncg = a.Cin >> 2, nslot = 256 / ncg;              // Cin % 4 == 0, Cin <= 256 (host)
+    const int cg = threadIdx.x % ncg, slot = threadIdx.x / ncg;
+    const int tap = blockIdx.y, ky = tap / a.ks, kx = tap - ky * a.ks, pad = a.ks >> 1;
+    const int rows_total = a.B * a.H;
+    const int r0 = blockIdx.x * WT_ROWS, r1 = min(r0 + WT_ROWS, rows_total);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[i][o] = 0.f;
+    if (slot < nslot) {
+        for (int r = r0; r < r1; ++r) {
+            const int b = r / a.H, y = r - b * a.H, yy = y + ky - pad;
+            if (yy < 0 || yy >= a.H) continue;
+            const float* xrow = a.x + ((size_t)(b * a.H + yy) * a.W) * a.ldx + cg * 4;
+            const float* grow = a.dy + ((size_t)r * a.W) * a.lddy;
+            for (int xo = slot; xo < a.W; xo += nslot) {
+                const int xx = xo + kx - pad;
+                if (xx < 0 || xx >= a.W) continue;
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(xrow + (size_t)xx * a.ldx));
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int o = 0; o < a.Cout; ++o) g[o] = __ldg(grow + (size_t)xo * a.lddy + o);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    acc[0][o] = fmaf(xv.x, g[o], acc[0][o]); acc[1][o] = fmaf(xv.y, g[o], acc[1][o]);
+                    acc[2][o] = fmaf(xv.z, g[o], acc[2][o]); acc[3][o] = fmaf(xv.w, g[o], acc[3][o]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) red[(i * 4 + o) * 256 + threadIdx.x] = acc[i][o];
+    __syncthreads();
+    // fixed-order sum over the slots, then one atomic per (ci, co) of the block
+    for (int e = threadIdx.x; e < ncg * 16; e += 256) {
+        const int c = e % ncg, io = e / ncg, i = io >> 2, o = io & 3;
+        if (o >= a.Cout) continue;
+        float sum = 0.f;
+        for (int sl = 0; sl < nslot; ++sl) sum += red[io * 256 + sl * ncg + c];
+        atomicAdd(a.dw + ((size_t)tap * a.Cin + c * 4 + i) * a.Cout + o, sum);
+    }
+}
+
 extern "C" int fcvsr_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, float* dw, int B, int H, int W,
                                   int Cin, int Cout, int ksize, int stride, cudaStream_t st) {
     if (!x || !dy || !dw || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || !(ksize & 1) || stride < 1) return FCVSR_ERR_ARG;
+    if (Cout <= 4 && stride == 1 && !(Cin & 3) && Cin <= 256 && !(ldx & 3) && !((uintptr_t)x & 15) && (long long)B * H <= 0x7fffffffLL) {
+        WgradArgs t;
+        t.x = x; t.ldx = ldx; t.dy = dy; t.lddy = lddy; t.dw = dw;
+        t.B = B; t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.ks = ksize; t.stride = 1;
+        t.Ho = H; t.Wo = W; t.npix = (long long)B * H * W; t.pix_per_slice = 0;
+        dim3 grid((unsigned)((B * H + WT_ROWS - 1) / WT_ROWS), ksize * ksize);
+        conv_wgrad_thin_kernel<<<grid, 256, 0, st>>>(t);
+        return fcvsr_launch_status();
+    }
     WgradArgs a;
     a.x = x; a.ldx = ldx; a.dy = dy; a.lddy = lddy; a.dw = dw;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ksize; a.stride = stride;

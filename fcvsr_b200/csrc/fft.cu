@@ -39,6 +39,16 @@ static bool make_plan(int n, FftPlan* p) {
             rem /= r;
         }
     }
+    // any other prime factor (19, 23, ...): a generic radix pass, O(R) per output element -- torch.fft accepts every length and
+    // so does this operator; such lengths are rare (H, W are multiples of 4) and short of the tuned radices only in speed
+    for (int r = 19; rem > 1; r += 2) {
+        if (r * r > rem) r = rem;
+        while (rem % r == 0) {
+            if (p->npass >= FFT_MAX_PASSES) return false;
+            p->radix[p->npass++] = r;
+            rem /= r;
+        }
+    }
     return rem == 1 && n >= 2;
 }
 
@@ -102,6 +112,26 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ in, float2* 
     }
 }
 
+// The same pass for a run-time radix R (prime factors above 17): one output element per thread, the R inputs read from shared memory.
+__device__ __forceinline__ void fft_pass_generic(const float2* __restrict__ in, float2* __restrict__ out, int n, int cb_log2, int s,
+                                                 const float2* __restrict__ tw, int R) {
+    const int nb = n / R, m = nb / s;
+    const int cb = 1 << cb_log2;
+    for (int idx = threadIdx.x; idx < (n << cb_log2); idx += blockDim.x) {
+        const int e = idx >> cb_log2, ch = idx & (cb - 1);
+        const int bf = e / R, j = e - bf * R;
+        const int p = bf / s, q = bf - p * s;
+        float2 acc = in[((q + s * p) << cb_log2) + ch];
+        int jk = 0;
+        for (int k = 1; k < R; ++k) {
+            jk += j;
+            if (jk >= R) jk -= R;
+            acc = cadd(acc, cmul(in[((q + s * (p + m * k)) << cb_log2) + ch], tw[jk * nb]));
+        }
+        out[((q + s * R * p + s * j) << cb_log2) + ch] = j ? cmul(acc, tw[p * j * s]) : acc;
+    }
+}
+
 // Runs all passes; returns the buffer that holds the result.
 __device__ float2* fft_line(float2* a, float2* b, const FftPlan& plan, int cb_log2, const float2* tw, bool inverse) {
     int s = 1;
@@ -115,7 +145,8 @@ __device__ float2* fft_line(float2* a, float2* b, const FftPlan& plan, int cb_lo
             case 7: fft_pass<7>(a, b, plan.n, cb_log2, s, tw, inverse); break;
             case 11: fft_pass<11>(a, b, plan.n, cb_log2, s, tw, inverse); break;
             case 13: fft_pass<13>(a, b, plan.n, cb_log2, s, tw, inverse); break;
-            default: fft_pass<17>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+            case 17: fft_pass<17>(a, b, plan.n, cb_log2, s, tw, inverse); break;
+            default: fft_pass_generic(a, b, plan.n, cb_log2, s, tw, r); break;
         }
         __syncthreads();
         float2* t = a;

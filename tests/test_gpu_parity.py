@@ -43,7 +43,7 @@ def _model(variant, sd, dev, use_tc=True):
 # ------------------------------------------------------------------------------------------------
 # kernels
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("H,W,Cc", [(64, 64, 64), (36, 40, 24), (180, 320, 16), (272, 480, 12), (4, 4, 2)])
+@pytest.mark.parametrize("H,W,Cc", [(64, 64, 64), (36, 40, 24), (180, 320, 16), (272, 480, 12), (4, 4, 2), (38, 76, 8), (46, 124, 4)])
 def test_fft_kernels_match_torch_fft(dev, H, W, Cc):
     g = torch.Generator().manual_seed(H * W)
     x = torch.randn(2, Cc, H, W, generator=g)
@@ -66,11 +66,19 @@ def test_fft_kernels_match_torch_fft(dev, H, W, Cc):
     assert float((nchw(y.cpu()) - ref2).abs().max()) <= 2e-6 * float(ref2.abs().max())
 
 
-def test_fft_rejects_unsupported_length(dev):
-    x = torch.zeros(1, 4, 38, 2, device=dev)          # 38 = 2 * 19: radix 19 is not built
+def test_fft_accepts_any_even_length_and_rejects_odd_width(dev):
+    """torch.fft takes every length: prime factors above 17 run on the generic radix pass (38 = 2 * 19); a real transform of odd
+    width (no packed two-channel form) is the one shape the operator refuses."""
+    x = torch.randn(1, 4, 38, 2, device=dev)
     out = torch.zeros(1, 4, 20, 2, 2, device=dev)
     tw = bands.twiddles(38, dev)
     rc = C.try_call("fcvsr_fft_r2c_w", x.data_ptr(), 2, out.data_ptr(), tw.data_ptr(), 1, 4, 38, 2, _st())
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = torch.fft.rfft(x.cpu(), dim=2)                      # [1, 4, 20, 2] complex (channels last)
+    got = torch.view_as_complex(out.cpu().contiguous())
+    assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+    rc = C.try_call("fcvsr_fft_r2c_w", x.data_ptr(), 2, out.data_ptr(), tw.data_ptr(), 1, 4, 37, 2, _st())
     assert rc == C.ERR_ARG
 
 

@@ -13,7 +13,8 @@ from oracle.make_golden import make_clip  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.set_num_threads(os.cpu_count() or 1)
-cases = [("S", 1, 64, 96), ("S", 2, 96, 128), ("S", 1, 120, 160), ("S", 1, 180, 320), ("full", 1, 180, 320), ("S", 1, 272, 480)]
+cases = [("S", 1, 64, 96), ("S", 2, 96, 128), ("S", 1, 120, 160), ("S", 1, 180, 320), ("full", 1, 180, 320), ("S", 1, 272, 480),
+         ("full", 2, 68, 100), ("S", 3, 52, 76), ("full", 1, 100, 132)]      # ragged conv / IAC / ConvBlk tiles, odd FFT radix pairs
 if len(sys.argv) > 1:
     cases = cases[: int(sys.argv[1])]
 worst = {"fp32": 0.0, "tf32": 0.0, "bf16": 0.0}
