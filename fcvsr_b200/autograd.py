@@ -168,6 +168,100 @@ def conv2d(x, w, bias=None, stride: int = 1, mode: str = "tf32"):
     return _Conv2d.apply(x, w, bias, stride, mode)
 
 
+def _conv_multi_launch(xs, wt: torch.Tensor, bias: Optional[torch.Tensor], co: int, k: int):
+    """fcvsr_conv2d_tc_multi on NHWC fp32 buffers of different spatial size (same batch, same channels): TF32 operands, fp32 out."""
+    import ctypes
+    n = len(xs)
+    B, ci = xs[0].shape[0], xs[0].shape[3]
+    ys = [torch.empty(x.shape[0], x.shape[1], x.shape[2], co, device=x.device, dtype=F32) for x in xs]
+    vp = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
+    ia = lambda v: (ctypes.c_int * n)(*v)  # noqa: E731
+    C.call("fcvsr_conv2d_tc_multi", n, vp(xs), ci, wt.data_ptr(), bias.contiguous().data_ptr() if bias is not None else 0, None, 0,
+           vp(ys), co, ia([x.shape[1] for x in xs]), ia([x.shape[2] for x in xs]), B, ci, co, k, C.ACT_NONE, 0.0, 0, None, 0, 0, 0, _st())
+    return ys
+
+
+class _Conv2dLevels(torch.autograd.Function):
+    """The same stride-1 convolution (one weight, one bias) on several tensors of different spatial size -- the pyramid levels
+    of a BlockRCB / SCGroup convolution (CVSR_freq.py:766-770, :797-803) -- in ONE tcgen05 launch for the forward and one for
+    the data gradients (fcvsr_conv2d_tc_multi); the weight gradients of the levels accumulate into one buffer.  At the training
+    crop (64 x 64 and below) a convolution launch is latency, not work, so three levels per launch is three times fewer of them."""
+
+    @staticmethod
+    def forward(ctx, w, bias, *xs):
+        co, ci, k, _ = w.shape
+        xh = [_nhwc(x) for x in xs]
+        wg_tc = WGRAD_TC and ci % 64 == 0 and co % 64 == 0 and ctx.needs_input_grad[0]
+        with torch.cuda.device(w.device):
+            wt = torch.empty(max(co, 16), k * k * ci, device=w.device, dtype=F32)
+            wc = w.detach().contiguous()
+            C.call("fcvsr_pack_conv_weight", wc.data_ptr(), wt.data_ptr(), co, ci, k, 0, 16, _st())
+            xr, xb = [], []
+            for x in xh:
+                r = torch.empty_like(x)
+                b16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if wg_tc else None
+                C.call("fcvsr_round_copy_dual", x.data_ptr(), r.data_ptr(), b16.data_ptr() if wg_tc else 0, x.numel(), _st())
+                xr.append(r)
+                xb.append(b16)
+            ys = _conv_multi_launch(xr, wt, None if bias is None else bias.detach(), co, k)
+        ctx.save_for_backward(w, *(xb if wg_tc else xh))
+        ctx.wg_tc, ctx.has_bias, ctx.n = wg_tc, bias is not None, len(xs)
+        return tuple(_logical(y) for y in ys)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gys):
+        w, *xsaved = ctx.saved_tensors
+        w = w.detach()
+        co, ci, k, _ = w.shape
+        g = [_nhwc(t) for t in gys]
+        need_x = any(ctx.needs_input_grad[2:])
+        gw = gb = None
+        gxs = [None] * ctx.n
+        with torch.cuda.device(w.device):
+            gr, g16 = [], []
+            for t in g:
+                r = torch.empty_like(t) if need_x else None
+                b16 = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16) if (ctx.wg_tc and ctx.needs_input_grad[0]) else None
+                if r is not None or b16 is not None:
+                    C.call("fcvsr_round_copy_dual", t.data_ptr(), r.data_ptr() if r is not None else 0,
+                           b16.data_ptr() if b16 is not None else 0, t.numel(), _st())
+                gr.append(r)
+                g16.append(b16)
+            if need_x:
+                wt = torch.empty(max(ci, 16), k * k * co, device=w.device, dtype=F32)
+                wc = w.contiguous()
+                C.call("fcvsr_pack_conv_weight", wc.data_ptr(), wt.data_ptr(), co, ci, k, 1, 16, _st())
+                dxs = _conv_multi_launch(gr, wt, None, ci, k)
+                gxs = [_logical(d) for d in dxs]
+            if ctx.needs_input_grad[0]:
+                dw = torch.zeros(k * k, ci, co, device=w.device, dtype=F32)
+                for xs_l, g_l, g16_l in zip(xsaved, g, g16):
+                    B, H, W, _ = xs_l.shape
+                    if ctx.wg_tc:
+                        C.call("fcvsr_conv2d_wgrad_tc", xs_l.data_ptr(), ci, g16_l.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, _st())
+                    else:
+                        C.call("fcvsr_conv2d_wgrad", xs_l.data_ptr(), ci, g_l.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, 1, _st())
+                gw = dw.view(k, k, ci, co).permute(3, 2, 0, 1)
+            if ctx.has_bias and ctx.needs_input_grad[1]:
+                gb = torch.zeros(co, device=w.device, dtype=F32)
+                for g_l in g:
+                    npix = g_l.shape[0] * g_l.shape[1] * g_l.shape[2]
+                    scratch = torch.empty(((npix + 63) // 64) * co, device=w.device, dtype=F32)
+                    part = torch.empty(co, device=w.device, dtype=F32)
+                    C.call("fcvsr_colsum", g_l.data_ptr(), co, co, npix, scratch.data_ptr(), part.data_ptr(), 0, _st())
+                    gb += part
+        return (gw, gb) + tuple(gxs)
+
+
+def conv2d_levels(xs, w, bias=None, mode: str = "tf32"):
+    """[conv2d(x, w, bias) for x in xs] for stride-1 convolutions; one launch per pass in "tf32" mode when the shape fits tcgen05."""
+    co, ci, k, _ = w.shape
+    if mode == "tf32" and len(xs) > 1 and len(xs) <= 4 and _tc_ok(ci, co, k, 1) and _tc_ok(co, ci, k, 1) and co >= 16:
+        return list(_Conv2dLevels.apply(w, bias, *xs))
+    return [conv2d(x, w, bias, 1, mode) for x in xs]
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # 2-D real FFTs (torch.fft.rfft2 / irfft2 with norm="backward", CVSR_freq.py:1452-1454, :1499-1504, :2082-2088)
 # ----------------------------------------------------------------------------------------------------------------------

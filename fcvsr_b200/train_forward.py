@@ -66,6 +66,10 @@ class _Ctx:
             return A.conv2d(x, mod_or_w.weight, mod_or_w.bias, mod_or_w.stride[0], self.mode)
         return A.conv2d(x, mod_or_w, bias, stride, self.mode)
 
+    def conv_levels(self, xs, mod):
+        """One convolution module applied to every pyramid level (BlockRCB / SCGroup): a single launch per pass in tf32 mode."""
+        return A.conv2d_levels(xs, mod.weight, mod.bias, self.mode)
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 def _mgaa(cx: _Ctx, x: torch.Tensor) -> torch.Tensor:
@@ -162,11 +166,11 @@ def _context(gc, x: torch.Tensor) -> torch.Tensor:
 
 def _block_rcb(cx: _Ctx, blk, xs: List[torch.Tensor]) -> List[torch.Tensor]:
     """BlockRCB.forward :766-777 with RCB :705-725."""
-    res = []
-    for x in xs:
-        r0 = cx.conv(F.leaky_relu(cx.conv(x, blk.body[0]), 0.1), blk.body[2])
-        r = cx.conv(F.leaky_relu(cx.conv(r0, blk.RCB.body[0]), 0.2), blk.RCB.body[2])
-        res.append(F.leaky_relu(_context(blk.RCB.gcnet, r), 0.2) + r0)
+    a = [F.leaky_relu(t, 0.1) for t in cx.conv_levels(xs, blk.body[0])]
+    r0s = cx.conv_levels(a, blk.body[2])
+    c1 = [F.leaky_relu(t, 0.2) for t in cx.conv_levels(r0s, blk.RCB.body[0])]
+    rs = cx.conv_levels(c1, blk.RCB.body[2])
+    res = [F.leaky_relu(_context(blk.RCB.gcnet, r), 0.2) + r0 for r, r0 in zip(rs, r0s)]
     # Interpolate(0.5) of an even-sized map is the 2x2 mean, which commutes with the 1x1 `down` convolution (:753-757)
     down = [res[0]] + [cx.conv(_cl(F.avg_pool2d(r, 2)), blk.down[0]) for r in res[:-1]]
     up = [F.interpolate(cx.conv(r, blk.up[0]), scale_factor=2.0, mode="bilinear", align_corners=False) for r in res[1:]] + [res[-1]]
@@ -180,7 +184,7 @@ def _scnet(cx: _Ctx, xs: List[torch.Tensor]) -> List[torch.Tensor]:
         t = cur
         for blk in grp.body:
             t = _block_rcb(cx, blk, t)
-        cur = [x + cx.conv(r, grp.conv) for x, r in zip(cur, t)]
+        cur = [x + c for x, c in zip(cur, cx.conv_levels(t, grp.conv))]
     return [x + r for x, r in zip(xs, cur)]
 
 

@@ -70,6 +70,29 @@ def test_conv2d_function_forward_and_gradients(dev, ci, co, k, stride, H, W, mod
         assert _rel(a.grad.cpu(), r.grad) <= t, (name, _rel(a.grad.cpu(), r.grad))
 
 
+@pytest.mark.parametrize("ci,co,k", [(64, 64, 3), (64, 128, 3), (128, 64, 3), (64, 64, 1)])
+def test_conv2d_levels_matches_per_level_convolutions(dev, ci, co, k):
+    """conv2d_levels (one tcgen05 launch for the pyramid levels in forward and in the data gradient, weight gradients of the
+    levels accumulated) against F.conv2d + autograd on the CPU with the tf32-mode tolerances of the single-tensor Function."""
+    g = torch.Generator().manual_seed(ci + co + k)
+    sizes = [(20, 24), (10, 12), (5, 6)]
+    xs = [torch.randn(2, ci, h, w, generator=g) for h, w in sizes]
+    w = torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)
+    b = torch.randn(co, generator=g)
+    gys = [torch.randn(2, co, h, ww, generator=g) for h, ww in sizes]
+    ref_in = [t.clone().requires_grad_(True) for t in xs + [w, b]]
+    sum((F.conv2d(x, ref_in[3], ref_in[4], padding=k // 2) * gy).sum() for x, gy in zip(ref_in[:3], gys)).backward()
+    ins = [t.to(dev).requires_grad_(True) for t in xs + [w, b]]
+    ys = A.conv2d_levels([_cl(t) for t in ins[:3]], ins[3], ins[4], "tf32")
+    sum((y * gy.to(dev)).sum() for y, gy in zip(ys, gys)).backward()
+    torch.cuda.synchronize()
+    for y, x in zip(ys, ref_in[:3]):
+        assert _rel(y.detach().cpu(), F.conv2d(x.detach(), w, b, padding=k // 2)) <= 2e-3
+    for i, name in enumerate(("x0", "x1", "x2", "w", "b")):
+        t = 2e-5 if name == "b" else (4e-3 if name == "w" else 2e-3)
+        assert _rel(ins[i].grad.cpu(), ref_in[i].grad) <= t, (name, _rel(ins[i].grad.cpu(), ref_in[i].grad))
+
+
 @pytest.mark.parametrize("k,H,W", [(1, 10, 9), (3, 7, 70), (5, 20, 33), (9, 64, 33), (11, 9, 6), (11, 70, 130)])
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
 def test_conv4x4_function_forward_and_gradients(dev, k, H, W, mode):
