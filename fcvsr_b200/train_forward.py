@@ -86,33 +86,33 @@ def _mgaa(cx: _Ctx, x: torch.Tensor) -> torch.Tensor:
     w0 = torch.cat([w0[:, :2 * n][:, inv], w0[:, 2 * n:][:, inv]], 1)
     w4 = mg.convfuse[4].weight[inv]
 
-    def fuse(sa):
-        h = F.relu(cx.conv(_cl(torch.cat([sa, s2], 1)), w0))
-        h = F.relu(cx.conv(h, mg.convfuse[2].weight))
-        return cx.conv(h, w4) + (sa - s2)              # :1472-1473
-
-    of, ob = fuse(s1), fuse(s3)
+    # the forward (x1) and backward (x3) branches share every weight: both run as ONE batch of 2B (at the training crop a
+    # convolution launch is latency, not work)
+    s22 = torch.cat([s2, s2], 0)
+    sa = torch.cat([s1, s3], 0)
+    h = F.relu(cx.conv(_cl(torch.cat([sa, s22], 1)), w0))
+    h = F.relu(cx.conv(h, mg.convfuse[2].weight))
+    ofb = cx.conv(h, w4) + (sa - s22)                              # :1472-1473, [of; ob]
     sim = cx.conv(F.relu(cx.conv(_cl(s2), mg.convcrt[0].weight[:, inv])), mg.convcrt[2].weight)   # :1474
     corr = A.corr_lookup(spec, 0, 2 * n)                           # corr_f feeds both branches (:1488)
     wc = mg.convcorr[0].weight[:, :2 * n + 81]                     # the two flow channels are zeros (:1484-1485)
     wc = torch.cat([wc[:, :2 * n][:, inv], wc[:, 2 * n:], wc.new_zeros(wc.shape[0], 15, 1, 1)], 1)   # K padded to 224
     zpad = spec.new_zeros(B, 15, H, spec.shape[3])
 
-    def corr_mlp(o):
-        h = F.relu(cx.conv(_cl(torch.cat([o, corr, zpad], 1)), wc))
-        h = F.relu(cx.conv(h, mg.convcorr[2].weight))
-        return cx.conv(h, mg.convcorr[4].weight)       # [B,4,H,Wf]
-
-    off_f, off_b = corr_mlp(of), corr_mlp(ob)
+    h = F.relu(cx.conv(_cl(torch.cat([ofb, torch.cat([corr, corr], 0), torch.cat([zpad, zpad], 0)], 1)), wc))
+    h = F.relu(cx.conv(h, mg.convcorr[2].weight))
+    off_fb = cx.conv(h, mg.convcorr[4].weight)                     # [2B,4,H,Wf]: [off_f; off_b]
+    sim2 = torch.cat([sim, sim], 0)
     zs = []
-    for i in range(acn):                                           # ConvBlk_i * x2_f_sim (:1494-1498)
+    for i in range(acn):                                           # ConvBlk_i * x2_f_sim (:1494-1498), both directions per call
         blk = mg.MConvB[i]
-        for o in (off_f, off_b):
-            t = cx.conv(o, blk.conv1.weight)
-            t = F.prelu(t, blk.relu.weight)
-            t = cx.conv(t, blk.conv2.weight)
-            v = (_ca(blk.CA, t) + t) * sim
-            zs.append(torch.stack([v[:, 0], v[:, 2], v[:, 1], v[:, 3]], 1))      # complex(v[0:2], v[2:4]) interleaved
+        t = cx.conv(off_fb, blk.conv1.weight)
+        t = F.prelu(t, blk.relu.weight)
+        t = cx.conv(t, blk.conv2.weight)
+        v = (_ca(blk.CA, t) + t) * sim2
+        z = torch.stack([v[:, 0], v[:, 2], v[:, 1], v[:, 3]], 1)   # complex(v[0:2], v[2:4]) interleaved
+        zs.append(z[:B])
+        zs.append(z[B:])
     offs = A.irfft2(_cl(torch.cat(zs, 1)), W)                      # [B, 4*ACNum, H, W]: channel (i*2+dir)*2 + (dx, dy)
     # kernel predictor (:1522-1523), live rows of F.1 only, re-ordered to [iteration][tap][channel]
     kp = cx.conv(cx.conv(_cl(x2), mg.conv_KP), mg.F[0])
@@ -172,8 +172,8 @@ def _block_rcb(cx: _Ctx, blk, xs: List[torch.Tensor]) -> List[torch.Tensor]:
     rs = cx.conv_levels(c1, blk.RCB.body[2])
     res = [F.leaky_relu(_context(blk.RCB.gcnet, r), 0.2) + r0 for r, r0 in zip(rs, r0s)]
     # Interpolate(0.5) of an even-sized map is the 2x2 mean, which commutes with the 1x1 `down` convolution (:753-757)
-    down = [res[0]] + [cx.conv(_cl(F.avg_pool2d(r, 2)), blk.down[0]) for r in res[:-1]]
-    up = [F.interpolate(cx.conv(r, blk.up[0]), scale_factor=2.0, mode="bilinear", align_corners=False) for r in res[1:]] + [res[-1]]
+    down = [res[0]] + cx.conv_levels([_cl(F.avg_pool2d(r, 2)) for r in res[:-1]], blk.down[0])
+    up = [F.interpolate(u, scale_factor=2.0, mode="bilinear", align_corners=False) for u in cx.conv_levels(res[1:], blk.up[0])] + [res[-1]]
     return [x + r + d + u for x, r, d, u in zip(xs, res, down, up)]
 
 
