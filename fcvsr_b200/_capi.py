@@ -38,6 +38,9 @@ SIGNATURES = {
     "fcvsr_mffr_final": "pp pi pi ii s",
     "fcvsr_context_block": "pi ppp ppp ii i s",
     "fcvsr_context_block_multi": "i pi ppp ppp i p i s",
+    "fcvsr_context_pool_multi": "i pi p pp p i p i s",
+    "fcvsr_context_pool_backward_multi": "i pi p pp pp i p s",
+    "fcvsr_context_pool_backward_blocks": "i p",          # returns a block count, not a status
     "fcvsr_rcb_finish_multi": "i ppp ppp pp i iii s",
     "fcvsr_level_mix_multi": "i pi pi p p pp i pp pi iii s",
     "fcvsr_rcb_finish": "ppp p ii p i p ii i i s",

@@ -254,6 +254,60 @@ class _Conv2dLevels(torch.autograd.Function):
         return (gw, gb) + tuple(gxs)
 
 
+class _ContextPool(torch.autograd.Function):
+    """Soft-max attention pooling of the ContextBlock (CVSR_freq.py:657-690) for the pyramid levels of a BlockRCB in one launch:
+    ctx[l, b, :] = sum_p softmax_p(w . x_l[b, p, :]) x_l[b, p, :].  Forward = the inference path's online-softmax kernel without
+    its MLP (fcvsr_context_pool_multi), backward = one pass over x (fcvsr_context_pool_backward_multi).  As PyTorch glue this
+    was ~10 forward and ~20 backward launches per level."""
+
+    @staticmethod
+    def forward(ctx, wmask, *xs):
+        import ctypes
+        n = len(xs)
+        xh = [_nhwc(x) for x in xs]
+        B, c = xh[0].shape[0], xh[0].shape[3]
+        P = [x.shape[1] * x.shape[2] for x in xh]
+        dev = xh[0].device
+        wm = wmask.detach().reshape(-1).contiguous()
+        pool = torch.empty(n, B, 66, device=dev, dtype=F32)
+        partial = torch.empty(sum(B * ((p + 127) // 128) * 66 for p in P), device=dev, dtype=F32)
+        counters = torch.zeros(n * B, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            C.call("fcvsr_context_pool_multi", n, (ctypes.c_void_p * n)(*[x.data_ptr() for x in xh]), c, wm.data_ptr(),
+                   partial.data_ptr(), pool.data_ptr(), counters.data_ptr(), B, (ctypes.c_int * n)(*P), 0, _st())
+        ctx.save_for_backward(wm, pool, *xh)
+        ctx.wshape = wmask.shape
+        return pool[:, :, :64].contiguous()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        import ctypes
+        wm, pool, *xh = ctx.saved_tensors
+        n = len(xh)
+        B, c = xh[0].shape[0], xh[0].shape[3]
+        P = [x.shape[1] * x.shape[2] for x in xh]
+        dev = xh[0].device
+        g = g.contiguous()
+        dxs = [torch.empty_like(x) for x in xh]
+        Parr = (ctypes.c_int * n)(*P)
+        nblk = C.lib().fcvsr_context_pool_backward_blocks(n, Parr)
+        dwpart = torch.empty(B * nblk, 64, device=dev, dtype=F32)
+        with torch.cuda.device(dev):
+            C.call("fcvsr_context_pool_backward_multi", n, (ctypes.c_void_p * n)(*[x.data_ptr() for x in xh]), c, wm.data_ptr(),
+                   pool.data_ptr(), g.data_ptr(), (ctypes.c_void_p * n)(*[d.data_ptr() for d in dxs]), dwpart.data_ptr(), B, Parr,
+                   _st())
+        gw = dwpart.sum(0).view(ctx.wshape) if ctx.needs_input_grad[0] else None
+        return (gw,) + tuple(_logical(d) for d in dxs)
+
+
+def context_pool(xs, wmask):
+    """xs: up to three [B,64,H_l,W_l] tensors, wmask: the ContextBlock's conv_mask weight [1,64,1,1] -> pooled context [len(xs), B, 64]."""
+    if xs[0].shape[1] != 64 or len(xs) > 3:
+        raise ValueError("context_pool handles up to three 64-channel tensors")
+    return _ContextPool.apply(wmask, *xs)
+
+
 def conv2d_levels(xs, w, bias=None, mode: str = "tf32"):
     """[conv2d(x, w, bias) for x in xs] for stride-1 convolutions; one launch per pass in "tf32" mode when the shape fits tcgen05."""
     co, ci, k, _ = w.shape

@@ -67,7 +67,8 @@ __device__ __forceinline__ void ctx_unpack(const uint4& r, const float (&v)[8], 
 // groups are merged once, at the end); logits are pre-scaled by log2(e) so that an exponential is one ex2.approx.
 template <bool X16>
 __global__ void __launch_bounds__(256, X16 ? 3 : 2) ctx_block_kernel(const CtxArgs a, const float* __restrict__ w1, const float* __restrict__ w2,
-                                                           float* __restrict__ add, unsigned* __restrict__ counters) {
+                                                           float* __restrict__ add, unsigned* __restrict__ counters,
+                                                           float* __restrict__ pool_out) {
     __shared__ float sm_m[8], sm_z[8];
     __shared__ float sm_acc[8][64];
     __shared__ float esc[CTX_MAX_NBLK];
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(256, X16 ? 3 : 2) ctx_block_kernel(const CtxAr
     // requested first (thread = (row t >> 2, 16 columns)), (m, z) of a partial come with one 8-byte load and stay in registers
     // when there are at most 256 partials, and the channel sums are walked by 8 thread groups with 8 loads in flight.
     float4 wr1[4], wr2[4];
-    {
+    if (w1) {
         const float4* a1 = reinterpret_cast<const float4*>(w1 + (t >> 2) * 64 + (t & 3) * 16);
         const float4* a2 = reinterpret_cast<const float4*>(w2 + (t >> 2) * 64 + (t & 3) * 16);
 #pragma unroll
@@ -264,6 +265,15 @@ __global__ void __launch_bounds__(256, X16 ? 3 : 2) ctx_block_kernel(const CtxAr
 #pragma unroll
         for (int j = 0; j < 8; ++j) sacc += part[j][t];
         ctx[t] = sacc / Z;
+        if (pool_out) {          // training: the pooled context and the soft-max statistics (log2 domain) for the backward pass
+            float* po = pool_out + ((size_t)l * a.B + b) * CTX_STRIDE;
+            po[t] = sacc / Z;
+            if (t == 0) { po[64] = M; po[65] = Z; }
+        }
+    }
+    if (!w1) {                   // pooling only (the MLP stays with autograd)
+        if (t == 0) *cnt = 0u;
+        return;
     }
     __syncthreads();
     {   // hid[r] = lrelu_0.2(W1[r,:] . ctx): thread = (row t >> 2, columns (t & 3) * 16 ..), two shuffle steps
@@ -292,10 +302,9 @@ __global__ void __launch_bounds__(256, X16 ? 3 : 2) ctx_block_kernel(const CtxAr
 
 // x: HOST array of nlev device pointers ([B,P_l,ldx] tensors), P: HOST array; partial: sum_l B*ceil(P_l/128)*66 floats;
 // add: [nlev][B][64]; counters: nlev*B unsigned ints, zero before the first call (the kernel leaves them zero).
-extern "C" int fcvsr_context_block_multi(int nlev, const void* const* x, int ldx, const float* wmask, const float* w1,
-                                         const float* w2, float* partial, float* add, int* counters, int B, const int* P, int x_bf16,
-                                         cudaStream_t st) {
-    if (nlev < 1 || nlev > SC_MAX_LEV || !x || !P || !wmask || !w1 || !w2 || !partial || !add || !counters || (ldx & 7) || B <= 0)
+static int ctx_launch(int nlev, const void* const* x, int ldx, const float* wmask, const float* w1, const float* w2, float* partial,
+                      float* add, float* pool_out, int* counters, int B, const int* P, int x_bf16, cudaStream_t st) {
+    if (nlev < 1 || nlev > SC_MAX_LEV || !x || !P || !wmask || !partial || !counters || (ldx & 7) || B <= 0)
         return FCVSR_ERR_ARG;
     CtxArgs a;
     a.nlev = nlev; a.ldx = ldx; a.B = B; a.wmask = wmask; a.partial = partial;
@@ -327,9 +336,24 @@ extern "C" int fcvsr_context_block_multi(int nlev, const void* const* x, int ldx
         a.lv[l].blk_begin = blk; a.lv[l].part_off = off;
         if (l < nlev) { blk += a.lv[l].nblk; off += (long long)B * ((P[j] + CTX_PIX_PER_BLOCK - 1) / CTX_PIX_PER_BLOCK) * CTX_STRIDE; }
     }
-    if (x_bf16) ctx_block_kernel<true><<<dim3(blk, B), 256, 0, st>>>(a, w1, w2, add, reinterpret_cast<unsigned*>(counters));
-    else ctx_block_kernel<false><<<dim3(blk, B), 256, 0, st>>>(a, w1, w2, add, reinterpret_cast<unsigned*>(counters));
+    if (x_bf16) ctx_block_kernel<true><<<dim3(blk, B), 256, 0, st>>>(a, w1, w2, add, reinterpret_cast<unsigned*>(counters), pool_out);
+    else ctx_block_kernel<false><<<dim3(blk, B), 256, 0, st>>>(a, w1, w2, add, reinterpret_cast<unsigned*>(counters), pool_out);
     return fcvsr_launch_status();
+}
+
+extern "C" int fcvsr_context_block_multi(int nlev, const void* const* x, int ldx, const float* wmask, const float* w1,
+                                         const float* w2, float* partial, float* add, int* counters, int B, const int* P, int x_bf16,
+                                         cudaStream_t st) {
+    if (!w1 || !w2 || !add) return FCVSR_ERR_ARG;
+    return ctx_launch(nlev, x, ldx, wmask, w1, w2, partial, add, nullptr, counters, B, P, x_bf16, st);
+}
+
+// Training: the soft-max pooling alone.  pool: [nlev][B][66] = context[64], running max (log2 domain), sum -- what
+// fcvsr_context_pool_backward_multi needs; the 64 -> 64 -> 64 MLP of the ContextBlock stays with autograd.
+extern "C" int fcvsr_context_pool_multi(int nlev, const void* const* x, int ldx, const float* wmask, float* partial, float* pool,
+                                        int* counters, int B, const int* P, int x_bf16, cudaStream_t st) {
+    if (!pool) return FCVSR_ERR_ARG;
+    return ctx_launch(nlev, x, ldx, wmask, nullptr, nullptr, partial, nullptr, pool, counters, B, P, x_bf16, st);
 }
 
 extern "C" int fcvsr_context_block(const void* x, int ldx, const float* wmask, const float* w1, const float* w2,
@@ -337,6 +361,141 @@ extern "C" int fcvsr_context_block(const void* x, int ldx, const float* wmask, c
     if (!x) return FCVSR_ERR_ARG;
     const void* xs[1] = {x};
     return fcvsr_context_block_multi(1, xs, ldx, wmask, w1, w2, partial, add, counters, B, &P, x_bf16, st);
+}
+
+// Backward of the soft-max pooling ctx[c] = sum_p prob_p x[p][c], prob = softmax_p(w . x[p]) (training step; the inference
+// path never needs it).  With g = d loss / d ctx and cg = ctx . g:
+//     d loss / d x[p][c] = prob_p * (g[c] + w[c] * (x[p] . g - cg)),      d loss / d w[c] = sum_p prob_p * (x[p] . g - cg) * x[p][c]
+// One pass over x: a lane owns 8 channels (as in the forward pass), the two dot products of a pixel need 3 shuffle steps per
+// four pixels; the weight gradient is accumulated per lane and reduced per block into dwpart[block][64] (summed by the caller).
+struct CtxBwdArgs {
+    CtxLevel lv[SC_MAX_LEV]; int nlev; int ldx; int ppb; int B;
+    const float* wmask; const float* pool; const float* gctx; float* dwpart;
+    float* dx[SC_MAX_LEV];
+};
+
+__global__ void __launch_bounds__(256) ctx_pool_bwd_kernel(const CtxBwdArgs a) {
+    __shared__ __align__(16) float gs[64], wsm[64], cs[64];
+    __shared__ float red[8][64];
+    __shared__ float cg_s;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, b = blockIdx.y;
+    const int sub = lane >> 3, oct = lane & 7;
+    const int bx = blockIdx.x;
+    const int l = (a.nlev > 1 && bx >= a.lv[1].blk_begin) ? ((a.nlev > 2 && bx >= a.lv[2].blk_begin) ? 2 : 1) : 0;
+    const int P = CTX_SEL(P), ppb = a.ppb, ldx = a.ldx, lbx = bx - CTX_SEL(blk_begin);
+    const float* x = reinterpret_cast<const float*>(CTX_SEL(x));
+    float* dx = l == 0 ? a.dx[0] : (l == 1 ? a.dx[1] : a.dx[2]);
+    const float* po = a.pool + ((size_t)l * a.B + b) * CTX_STRIDE;
+    if (t < 64) {
+        gs[t] = a.gctx[((size_t)l * a.B + b) * 64 + t];
+        wsm[t] = a.wmask[t];
+        cs[t] = po[t];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float v = gs[lane] * cs[lane] + gs[lane + 32] * cs[lane + 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) cg_s = v;
+    }
+    __syncthreads();
+    const float M = po[64], rZ = 1.f / po[65], cg = cg_s;
+    float g[8], w[8], dw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { g[j] = gs[oct * 8 + j]; w[j] = wsm[oct * 8 + j]; dw[j] = 0.f; }
+    const int per_warp = ppb >> 3;
+    const int p0 = lbx * ppb + warp * per_warp + sub;
+    const size_t img = (size_t)b * P * ldx + oct * 8;
+    for (int it = 0; it < per_warp; it += 16) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + it + 4 * u;
+            float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+            if (p < P) {
+                const float4* src = reinterpret_cast<const float4*>(x + img + (size_t)p * ldx);
+                r0 = __ldg(src); r1 = __ldg(src + 1);
+            }
+            v[u][0] = r0.x; v[u][1] = r0.y; v[u][2] = r0.z; v[u][3] = r0.w;
+            v[u][4] = r1.x; v[u][5] = r1.y; v[u][6] = r1.z; v[u][7] = r1.w;
+        }
+        float lg[4], sg[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a0 = fmaf(v[u][j], w[j], a0); a1 = fmaf(v[u][j], g[j], a1); }
+            lg[u] = a0; sg[u] = a1;
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                lg[u] += __shfl_xor_sync(0xffffffffu, lg[u], o);
+                sg[u] += __shfl_xor_sync(0xffffffffu, sg[u], o);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + it + 4 * u;
+            if (p >= P) continue;
+            const float prob = ctx_ex2(lg[u] * CTX_LOG2E - M) * rZ;
+            const float tt = prob * (sg[u] - cg);
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o[j] = fmaf(tt, w[j], prob * g[j]);
+                dw[j] = fmaf(tt, v[u][j], dw[j]);
+            }
+            float4* dst = reinterpret_cast<float4*>(dx + img + (size_t)p * ldx);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dw[j] += __shfl_xor_sync(0xffffffffu, dw[j], o);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][oct * 8 + j] = dw[j];
+    }
+    __syncthreads();
+    if (t < 64) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += red[k][t];
+        a.dwpart[((size_t)b * gridDim.x + bx) * 64 + t] = sum;
+    }
+}
+
+// x / dx: HOST arrays of nlev device pointers ([B,P_l,ldx] fp32; dx is WRITTEN); pool: the output of fcvsr_context_pool_multi;
+// gctx: d loss / d context [nlev][B][64]; dwpart: B * nblocks * 64 floats, nblocks = fcvsr_context_pool_backward_blocks(...)
+// (the caller sums them: d loss / d wmask).
+extern "C" int fcvsr_context_pool_backward_blocks(int nlev, const int* P) {
+    int blk = 0;
+    for (int l = 0; l < nlev && l < SC_MAX_LEV; ++l) blk += (P[l] + CTX_PPB - 1) / CTX_PPB;
+    return blk;
+}
+extern "C" int fcvsr_context_pool_backward_multi(int nlev, const void* const* x, int ldx, const float* wmask, const float* pool,
+                                                 const float* gctx, float* const* dx, float* dwpart, int B, const int* P,
+                                                 cudaStream_t st) {
+    if (nlev < 1 || nlev > SC_MAX_LEV || !x || !P || !wmask || !pool || !gctx || !dx || !dwpart || (ldx & 7) || B <= 0 || B > 65535)
+        return FCVSR_ERR_ARG;
+    CtxBwdArgs a;
+    a.nlev = nlev; a.ldx = ldx; a.B = B; a.ppb = CTX_PPB; a.wmask = wmask; a.pool = pool; a.gctx = gctx; a.dwpart = dwpart;
+    int blk = 0;
+    for (int l = 0; l < SC_MAX_LEV; ++l) {
+        const int j = l < nlev ? l : 0;
+        if (!x[j] || !dx[j] || P[j] <= 0 || (((uintptr_t)x[j] | (uintptr_t)dx[j]) & 15)) return FCVSR_ERR_ARG;
+        a.lv[l].x = x[j]; a.lv[l].P = P[j]; a.lv[l].nblk = (P[j] + CTX_PPB - 1) / CTX_PPB;
+        a.lv[l].blk_begin = blk; a.lv[l].part_off = 0;
+        a.dx[l] = dx[j];
+        if (l < nlev) blk += a.lv[l].nblk;
+    }
+    ctx_pool_bwd_kernel<<<dim3(blk, B), 256, 0, st>>>(a);
+    return fcvsr_launch_status();
 }
 
 // ---- RCB tail (:720-724): r = lrelu_0.2(res + add[b]) + r0, all 64 channels, float4 per thread ----------------------------

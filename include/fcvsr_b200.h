@@ -181,6 +181,15 @@ int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const void*
  * r / r_op / r_pool / td / tu / xout_r skip that output or term. */
 int fcvsr_context_block_multi(int nlev, const void* const* x, int ldx, const float* wmask, const float* w1, const float* w2,
                               float* partial, float* add, int* counters, int B, const int* P, int x_bf16, cudaStream_t stream);
+/* Training step: the ContextBlock's soft-max pooling alone and its backward (csrc/scnet.cu); the 64 -> 64 -> 64 MLP stays with
+ * autograd.  pool: [nlev][B][66] = context[64], soft-max running max (log2 domain) and sum; partial / counters as above.
+ * Backward: gctx = d loss / d context [nlev][B][64]; dx[l] ([B,P_l,ldx] fp32) is WRITTEN with d loss / d x; dwpart receives
+ * B * fcvsr_context_pool_backward_blocks(nlev, P) rows of 64 partial sums of d loss / d wmask (the caller adds them up). */
+int fcvsr_context_pool_multi(int nlev, const void* const* x, int ldx, const float* wmask, float* partial, float* pool,
+                             int* counters, int B, const int* P, int x_bf16, cudaStream_t stream);
+int fcvsr_context_pool_backward_blocks(int nlev, const int* P);
+int fcvsr_context_pool_backward_multi(int nlev, const void* const* x, int ldx, const float* wmask, const float* pool,
+                                      const float* gctx, float* const* dx, float* dwpart, int B, const int* P, cudaStream_t stream);
 int fcvsr_rcb_finish_multi(int nlev, const void* const* res, const float* const* add, const void* const* r0, float* const* r,
                            void* const* r_op, void* const* r_pool, const int* H, const int* W, int B, int op16, int pool_plain,
                            int res_bf16, cudaStream_t stream);
