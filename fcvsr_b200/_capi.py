@@ -42,6 +42,7 @@ SIGNATURES = {
     "fcvsr_context_pool_backward_multi": "i pi p pp pp i p s",
     "fcvsr_context_pool_backward_blocks": "i p",          # returns a block count, not a status
     "fcvsr_rcb_finish_multi": "i ppp ppp pp i iii s",
+    "fcvsr_rcb_finish_backward_multi": "i ppp pp p i s",
     "fcvsr_level_mix_multi": "i pi pi p p pp i pp pi iii s",
     "fcvsr_rcb_finish": "ppp p ii p i p ii i i s",
     "fcvsr_level_mix": "pi pi p f pp iii pi i i i s",

@@ -301,6 +301,55 @@ class _ContextPool(torch.autograd.Function):
         return (gw,) + tuple(_logical(d) for d in dxs)
 
 
+class _RcbTail(torch.autograd.Function):
+    """RCB tail r_l = lrelu_0.2(res_l + add[l, b]) + r0_l (CVSR_freq.py:720-724) for the pyramid levels of a BlockRCB: forward =
+    the inference kernel (fcvsr_rcb_finish_multi, plain fp32 output), backward = one kernel for the three levels (the gradient of
+    r0 is the incoming gradient itself).  As PyTorch glue: a broadcast add, an activation and an add per level, and their adjoints."""
+
+    @staticmethod
+    def forward(ctx, add, *ts):
+        import ctypes
+        n = len(ts) // 2
+        res = [_nhwc(t) for t in ts[:n]]
+        r0 = [_nhwc(t) for t in ts[n:]]
+        addc = add.detach().contiguous()                                  # [n, B, 64]
+        B = res[0].shape[0]
+        outs = [torch.empty_like(t) for t in res]
+        vp = lambda ptrs: (ctypes.c_void_p * n)(*ptrs)  # noqa: E731
+        ia = lambda v: (ctypes.c_int * n)(*v)  # noqa: E731
+        with torch.cuda.device(res[0].device):
+            C.call("fcvsr_rcb_finish_multi", n, vp([t.data_ptr() for t in res]), vp([addc[i].data_ptr() for i in range(n)]),
+                   vp([t.data_ptr() for t in r0]), vp([t.data_ptr() for t in outs]), None, None, ia([t.shape[1] for t in res]),
+                   ia([t.shape[2] for t in res]), B, 0, 1, 0, _st())
+        ctx.save_for_backward(addc, *res)
+        ctx.n = n
+        return tuple(_logical(t) for t in outs)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *gs):
+        import ctypes
+        addc, *res = ctx.saved_tensors
+        n = ctx.n
+        g = [_nhwc(t) for t in gs]
+        B = res[0].shape[0]
+        gres = [torch.empty_like(t) for t in res]
+        gadd = torch.zeros_like(addc)
+        vp = lambda ptrs: (ctypes.c_void_p * n)(*ptrs)  # noqa: E731
+        with torch.cuda.device(res[0].device):
+            C.call("fcvsr_rcb_finish_backward_multi", n, vp([t.data_ptr() for t in res]), vp([addc[i].data_ptr() for i in range(n)]),
+                   vp([t.data_ptr() for t in g]), vp([t.data_ptr() for t in gres]), vp([gadd[i].data_ptr() for i in range(n)]),
+                   (ctypes.c_int * n)(*[t.shape[1] * t.shape[2] for t in res]), B, _st())
+        return (gadd,) + tuple(_logical(t) for t in gres) + tuple(gs)
+
+
+def rcb_tail(res, add, r0):
+    """[lrelu_0.2(res_l + add[l][:, :, None, None]) + r0_l for l] -- res, r0: lists of up to three [B,64,H_l,W_l] tensors, add [len, B, 64]."""
+    if len(res) > 3 or res[0].shape[1] != 64:
+        raise ValueError("rcb_tail handles up to three 64-channel tensors")
+    return list(_RcbTail.apply(add, *res, *r0))
+
+
 def context_pool(xs, wmask):
     """xs: up to three [B,64,H_l,W_l] tensors, wmask: the ContextBlock's conv_mask weight [1,64,1,1] -> pooled context [len(xs), B, 64]."""
     if xs[0].shape[1] != 64 or len(xs) > 3:

@@ -612,6 +612,69 @@ extern "C" int fcvsr_rcb_finish(const void* res, const float* add, const void* r
     return fcvsr_rcb_finish_multi(1, ress, adds, r0s, rs, rops, rpools, &H, &W, B, op16, pool_plain, res_bf16, st);
 }
 
+// Backward of the RCB tail r = lrelu_0.2(res + add[b]) + r0 (training step): gres = g * (res + add >= 0 ? 1 : 0.2), the gradient
+// of r0 is g itself, and gadd[level][b][c] += sum over pixels of gres (fp32 atomics of per-block sums; zero it first).  Same
+// row-based mapping as the forward kernel: a block is a run of 16 pixels of one image, a thread 4 channels.
+struct RcbBwdLevel { const float* res; const float* add; const float* g; float* gres; float* gadd; int P; int blk_begin, bpr; };
+struct RcbBwdArgs { RcbBwdLevel lv[SC_MAX_LEV]; int nlev; };
+
+__global__ void __launch_bounds__(256) rcb_finish_bwd_kernel(const RcbBwdArgs a) {
+    __shared__ float4 red[256];
+    const int bx = blockIdx.x;
+    const int l = (a.nlev > 1 && bx >= a.lv[1].blk_begin) ? ((a.nlev > 2 && bx >= a.lv[2].blk_begin) ? 2 : 1) : 0;
+    const RcbBwdLevel& L = a.lv[l];
+    const int lb = bx - L.blk_begin;
+    const int b = lb / L.bpr, xq = (lb - b * L.bpr) * 16 + (threadIdx.x >> 4);
+    const int c = (threadIdx.x & 15) * 4;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xq < L.P) {
+        const size_t i = ((size_t)b * L.P + xq) * 64 + c;
+        const float4 r = *reinterpret_cast<const float4*>(L.res + i);
+        const float4 ad = *reinterpret_cast<const float4*>(L.add + (size_t)b * 64 + c);
+        const float4 g = *reinterpret_cast<const float4*>(L.g + i);
+        o.x = g.x * (r.x + ad.x >= 0.f ? 1.f : 0.2f);
+        o.y = g.y * (r.y + ad.y >= 0.f ? 1.f : 0.2f);
+        o.z = g.z * (r.z + ad.z >= 0.f ? 1.f : 0.2f);
+        o.w = g.w * (r.w + ad.w >= 0.f ? 1.f : 0.2f);
+        *reinterpret_cast<float4*>(L.gres + i) = o;
+    }
+    red[threadIdx.x] = o;
+    __syncthreads();
+    if (threadIdx.x < 16) {            // sum of the block's 16 pixels for this thread's 4 channels
+        float4 sum = red[threadIdx.x];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) {
+            const float4 v = red[threadIdx.x + 16 * k];
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        float* d = L.gadd + (size_t)b * 64 + threadIdx.x * 4;
+        atomicAdd(d, sum.x); atomicAdd(d + 1, sum.y); atomicAdd(d + 2, sum.z); atomicAdd(d + 3, sum.w);
+    }
+}
+
+// res / add / g / gres / gadd: HOST arrays of nlev device pointers (64-channel fp32 tensors [B,P_l,64]; add, gadd: [B,64]);
+// gres is WRITTEN, gadd ACCUMULATED (zero it first).
+extern "C" int fcvsr_rcb_finish_backward_multi(int nlev, const float* const* res, const float* const* add, const float* const* g,
+                                               float* const* gres, float* const* gadd, const int* P, int B, cudaStream_t st) {
+    if (nlev < 1 || nlev > SC_MAX_LEV || !res || !add || !g || !gres || !gadd || !P || B <= 0) return FCVSR_ERR_ARG;
+    RcbBwdArgs a;
+    a.nlev = nlev;
+    long long t = 0;
+    for (int l = 0; l < SC_MAX_LEV; ++l) {
+        const int j = l < nlev ? l : 0;
+        RcbBwdLevel& L = a.lv[l];
+        L.res = res[j]; L.add = add[j]; L.g = g[j]; L.gres = gres[j]; L.gadd = gadd[j]; L.P = P[j];
+        L.blk_begin = (int)t; L.bpr = (P[j] + 15) / 16;
+        if (l >= nlev) continue;
+        if (!L.res || !L.add || !L.g || !L.gres || !L.gadd || L.P <= 0) return FCVSR_ERR_ARG;
+        if (((uintptr_t)L.res | (uintptr_t)L.add | (uintptr_t)L.g | (uintptr_t)L.gres) & 15) return FCVSR_ERR_ARG;
+        t += (long long)B * L.bpr;
+        if (t > 0x7fffffffLL) return FCVSR_ERR_UNSUPPORTED;
+    }
+    rcb_finish_bwd_kernel<<<(unsigned)t, 256, 0, st>>>(a);
+    return fcvsr_launch_status();
+}
+
 // ---- BlockRCB cross-level sum (:766-777): x[b,y,x,:] += coef * r + mean2x2(td) + bilinear_x2(tu) (64 channels) -------------
 struct MixLevel {
     const float* xin; float* xout; const void* r; const void* td; const void* tu; void* xout_r;

@@ -175,7 +175,7 @@ def _block_rcb(cx: _Ctx, blk, xs: List[torch.Tensor]) -> List[torch.Tensor]:
     pooled = A.context_pool(rs, gc.conv_mask.weight)                               # [levels, B, 64]
     tadd = _mlp_vec(pooled.reshape(-1, pooled.shape[-1]), gc.channel_add_conv[0].weight, gc.channel_add_conv[2].weight,
                     lambda v: F.leaky_relu(v, 0.2)).view_as(pooled)
-    res = [F.leaky_relu(r + tadd[i][:, :, None, None], 0.2) + r0 for i, (r, r0) in enumerate(zip(rs, r0s))]
+    res = A.rcb_tail(rs, tadd, r0s)                                                # lrelu_0.2(r + t) + r0 (:720-724)
     # Interpolate(0.5) of an even-sized map is the 2x2 mean, which commutes with the 1x1 `down` convolution (:753-757)
     down = [res[0]] + cx.conv_levels([_cl(F.avg_pool2d(r, 2)) for r in res[:-1]], blk.down[0])
     up = [F.interpolate(u, scale_factor=2.0, mode="bilinear", align_corners=False) for u in cx.conv_levels(res[1:], blk.up[0])] + [res[-1]]

@@ -190,6 +190,11 @@ int fcvsr_context_pool_multi(int nlev, const void* const* x, int ldx, const floa
 int fcvsr_context_pool_backward_blocks(int nlev, const int* P);
 int fcvsr_context_pool_backward_multi(int nlev, const void* const* x, int ldx, const float* wmask, const float* pool,
                                       const float* gctx, float* const* dx, float* dwpart, int B, const int* P, cudaStream_t stream);
+/* Backward of the RCB tail r = lrelu_0.2(res + add[b]) + r0 (training step): gres[l] = g[l] * (res + add >= 0 ? 1 : 0.2) is WRITTEN,
+ * gadd[l] ([B,64]) ACCUMULATES the sum of gres over the pixels (zero it first); the gradient of r0 is g itself.  HOST arrays of
+ * nlev device pointers, 64-channel fp32 tensors [B,P_l,64]. */
+int fcvsr_rcb_finish_backward_multi(int nlev, const float* const* res, const float* const* add, const float* const* g,
+                                    float* const* gres, float* const* gadd, const int* P, int B, cudaStream_t stream);
 int fcvsr_rcb_finish_multi(int nlev, const void* const* res, const float* const* add, const void* const* r0, float* const* r,
                            void* const* r_op, void* const* r_pool, const int* H, const int* W, int B, int op16, int pool_plain,
                            int res_bf16, cudaStream_t stream);

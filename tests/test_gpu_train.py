@@ -70,6 +70,29 @@ def test_conv2d_function_forward_and_gradients(dev, ci, co, k, stride, H, W, mod
         assert _rel(a.grad.cpu(), r.grad) <= t, (name, _rel(a.grad.cpu(), r.grad))
 
 
+@pytest.mark.parametrize("sizes", [[(20, 24), (10, 12), (5, 6)], [(7, 9)]])
+def test_rcb_tail_function_forward_and_gradients(dev, sizes):
+    """_RcbTail: lrelu_0.2(res + add[b]) + r0 for the pyramid levels in one launch, and its backward kernel (gradient of the
+    per-image vector = pixel sums accumulated with atomics), against the PyTorch expression on the CPU."""
+    g = torch.Generator().manual_seed(11 + len(sizes))
+    B, n = 3, len(sizes)
+    res = [torch.randn(B, 64, h, w, generator=g) for h, w in sizes]
+    r0 = [torch.randn(B, 64, h, w, generator=g) for h, w in sizes]
+    add = torch.randn(n, B, 64, generator=g)
+    gys = [torch.randn(B, 64, h, w, generator=g) for h, w in sizes]
+    ref_in = [t.clone().requires_grad_(True) for t in res + r0 + [add]]
+    ref = [F.leaky_relu(ref_in[i] + ref_in[-1][i][:, :, None, None], 0.2) + ref_in[n + i] for i in range(n)]
+    sum((y * gy).sum() for y, gy in zip(ref, gys)).backward()
+    ins = [t.to(dev).requires_grad_(True) for t in res + r0 + [add]]
+    out = A.rcb_tail([_cl(t) for t in ins[:n]], ins[-1], [_cl(t) for t in ins[n:2 * n]])
+    sum((y * gy.to(dev)).sum() for y, gy in zip(out, gys)).backward()
+    torch.cuda.synchronize()
+    for y, r in zip(out, ref):
+        assert _rel(y.detach().cpu(), r.detach()) <= 1e-6
+    for i in range(2 * n + 1):
+        assert _rel(ins[i].grad.cpu(), ref_in[i].grad) <= 2e-5, (i, _rel(ins[i].grad.cpu(), ref_in[i].grad))
+
+
 @pytest.mark.parametrize("sizes", [[(20, 24), (10, 12), (5, 6)], [(64, 64), (32, 32), (16, 16)], [(7, 9)]])
 def test_context_pool_function_forward_and_gradients(dev, sizes):
     """_ContextPool (soft-max attention pooling of the ContextBlock, CVSR_freq.py:657-690, all levels in one launch; backward in
