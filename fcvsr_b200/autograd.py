@@ -343,6 +343,47 @@ class _RcbTail(torch.autograd.Function):
         return (gadd,) + tuple(_logical(t) for t in gres) + tuple(gs)
 
 
+class _LevelMix(torch.autograd.Function):
+    """BlockRCB cross-level sum (CVSR_freq.py:766-777) of a three-level pyramid in one launch (fcvsr_level_mix_multi):
+        out_0 = x_0 + 2 r_0 + up2(tu_0),   out_1 = x_1 + r_1 + td_1 + up2(tu_1),   out_2 = x_2 + 2 r_2 + td_2
+    (td_l: the `down` convolution of the pooled finer level, already at level l's size; tu_l: the `up` convolution of the coarser
+    level, bilinearly up-sampled in the kernel; level 0 has d = r, level 2 has u = r).  Backward: identities, two scalings and
+    ATen's adjoint of the bilinear up-sampling."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, x2, r0, r1, r2, td1, td2, tu0, tu1):
+        import ctypes
+        xs = [_nhwc(t) for t in (x0, x1, x2)]
+        rs = [_nhwc(t) for t in (r0, r1, r2)]
+        tds = [None, _nhwc(td1), _nhwc(td2)]
+        tus = [_nhwc(tu0), _nhwc(tu1), None]
+        outs = [torch.empty_like(t) for t in xs]
+        B = xs[0].shape[0]
+        ptr = lambda t: t.data_ptr() if t is not None else 0  # noqa: E731
+        vp = lambda ts: (ctypes.c_void_p * 3)(*[ptr(t) for t in ts])  # noqa: E731
+        with torch.cuda.device(xs[0].device):
+            C.call("fcvsr_level_mix_multi", 3, vp(xs), 64, vp(outs), 64, vp(rs), (ctypes.c_float * 3)(2.0, 1.0, 2.0), vp(tds), vp(tus), B,
+                   (ctypes.c_int * 3)(*[t.shape[1] for t in xs]), (ctypes.c_int * 3)(*[t.shape[2] for t in xs]), None, 0, 0, 0, 1, _st())
+        ctx.shapes = [tuple(t.shape) for t in (tu0, tu1)]
+        return tuple(_logical(t) for t in outs)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g0, g1, g2):
+        up = torch.ops.aten.upsample_bilinear2d_backward
+        gtu0 = up(g0, [g0.shape[2], g0.shape[3]], list(ctx.shapes[0]), False, 2.0, 2.0)
+        gtu1 = up(g1, [g1.shape[2], g1.shape[3]], list(ctx.shapes[1]), False, 2.0, 2.0)
+        return g0, g1, g2, g0 * 2.0, g1, g2 * 2.0, g1, g2, gtu0, gtu1
+
+
+def level_mix(xs, rs, tds, tus):
+    """xs, rs: three-level lists [B,64,H_l,W_l]; tds = [td_1, td_2] (at the sizes of levels 1, 2); tus = [tu_0, tu_1] (at the sizes
+    of levels 1, 2, i.e. half of the level they are added to)."""
+    if len(xs) != 3 or xs[0].shape[1] != 64:
+        raise ValueError("level_mix handles a three-level 64-channel pyramid")
+    return list(_LevelMix.apply(*xs, *rs, *tds, *tus))
+
+
 def rcb_tail(res, add, r0):
     """[lrelu_0.2(res_l + add[l][:, :, None, None]) + r0_l for l] -- res, r0: lists of up to three [B,64,H_l,W_l] tensors, add [len, B, 64]."""
     if len(res) > 3 or res[0].shape[1] != 64:

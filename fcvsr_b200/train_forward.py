@@ -177,8 +177,12 @@ def _block_rcb(cx: _Ctx, blk, xs: List[torch.Tensor]) -> List[torch.Tensor]:
                     lambda v: F.leaky_relu(v, 0.2)).view_as(pooled)
     res = A.rcb_tail(rs, tadd, r0s)                                                # lrelu_0.2(r + t) + r0 (:720-724)
     # Interpolate(0.5) of an even-sized map is the 2x2 mean, which commutes with the 1x1 `down` convolution (:753-757)
-    down = [res[0]] + cx.conv_levels([_cl(F.avg_pool2d(r, 2)) for r in res[:-1]], blk.down[0])
-    up = [F.interpolate(u, scale_factor=2.0, mode="bilinear", align_corners=False) for u in cx.conv_levels(res[1:], blk.up[0])] + [res[-1]]
+    tds = cx.conv_levels([_cl(F.avg_pool2d(r, 2)) for r in res[:-1]], blk.down[0])
+    tus = cx.conv_levels(res[1:], blk.up[0])
+    if len(xs) == 3 and xs[0].shape[1] == 64 and all(x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 for x in xs[:2]):
+        return A.level_mix(xs, res, tds, tus)                                       # x + r + d + u (:771-776), one launch
+    down = [res[0]] + tds
+    up = [F.interpolate(u, scale_factor=2.0, mode="bilinear", align_corners=False) for u in tus] + [res[-1]]
     return [x + r + d + u for x, r, d, u in zip(xs, res, down, up)]
 
 

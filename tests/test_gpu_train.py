@@ -70,6 +70,31 @@ def test_conv2d_function_forward_and_gradients(dev, ci, co, k, stride, H, W, mod
         assert _rel(a.grad.cpu(), r.grad) <= t, (name, _rel(a.grad.cpu(), r.grad))
 
 
+def test_level_mix_function_forward_and_gradients(dev):
+    """_LevelMix (BlockRCB cross-level sum, CVSR_freq.py:766-777, three levels in one launch; bilinear x2 inside the kernel)
+    against x + r + d + u with F.interpolate on the CPU, all ten gradients."""
+    g = torch.Generator().manual_seed(23)
+    B, sizes = 2, [(20, 24), (10, 12), (5, 6)]
+    mk = lambda h, w: torch.randn(B, 64, h, w, generator=g)  # noqa: E731
+    xs, rs = [mk(*s) for s in sizes], [mk(*s) for s in sizes]
+    tds, tus = [mk(*sizes[1]), mk(*sizes[2])], [mk(*sizes[1]), mk(*sizes[2])]
+    gys = [mk(*s) for s in sizes]
+    ref_in = [t.clone().requires_grad_(True) for t in xs + rs + tds + tus]
+    rx, rr, rtd, rtu = ref_in[:3], ref_in[3:6], ref_in[6:8], ref_in[8:]
+    up = lambda t: F.interpolate(t, scale_factor=2.0, mode="bilinear", align_corners=False)  # noqa: E731
+    ref = [rx[0] + rr[0] + rr[0] + up(rtu[0]), rx[1] + rr[1] + rtd[0] + up(rtu[1]), rx[2] + rr[2] + rtd[1] + rr[2]]
+    sum((y * gy).sum() for y, gy in zip(ref, gys)).backward()
+    ins = [t.to(dev).requires_grad_(True) for t in xs + rs + tds + tus]
+    cl = [_cl(t) for t in ins]
+    out = A.level_mix(cl[:3], cl[3:6], cl[6:8], cl[8:])
+    sum((y * gy.to(dev)).sum() for y, gy in zip(out, gys)).backward()
+    torch.cuda.synchronize()
+    for y, r in zip(out, ref):
+        assert _rel(y.detach().cpu(), r.detach()) <= 2e-6
+    for i in range(10):
+        assert _rel(ins[i].grad.cpu(), ref_in[i].grad) <= 2e-6, i
+
+
 @pytest.mark.parametrize("sizes", [[(20, 24), (10, 12), (5, 6)], [(7, 9)]])
 def test_rcb_tail_function_forward_and_gradients(dev, sizes):
     """_RcbTail: lrelu_0.2(res + add[b]) + r0 for the pyramid levels in one launch, and its backward kernel (gradient of the
