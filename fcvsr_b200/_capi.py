@@ -57,6 +57,7 @@ SIGNATURES = {
     "fcvsr_conv2d_dgrad_direct": "pi p pi iiiiiii s",
     "fcvsr_conv2d_wgrad": "pi pi p iiiiiii s",
     "fcvsr_conv2d_wgrad_tc": "pi pi p iiiiii s",
+    "fcvsr_conv2d_wgrad_tc_multi": "i pi pi p i pp iii s",
     "fcvsr_round_copy_dual": "ppp l s",
     "fcvsr_conv4x4": "ppp iiii s",
     "fcvsr_conv4x4_wgrad": "ppp iiii s",

@@ -236,11 +236,15 @@ class _Conv2dLevels(torch.autograd.Function):
                 gxs = [_logical(d) for d in dxs]
             if ctx.needs_input_grad[0]:
                 dw = torch.zeros(k * k, ci, co, device=w.device, dtype=F32)
-                for xs_l, g_l, g16_l in zip(xsaved, g, g16):
-                    B, H, W, _ = xs_l.shape
-                    if ctx.wg_tc:
-                        C.call("fcvsr_conv2d_wgrad_tc", xs_l.data_ptr(), ci, g16_l.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, _st())
-                    else:
+                if ctx.wg_tc:            # the levels' weight gradients add up: one launch walks the tiles of all of them
+                    import ctypes
+                    n = len(xsaved)
+                    C.call("fcvsr_conv2d_wgrad_tc_multi", n, (ctypes.c_void_p * n)(*[t.data_ptr() for t in xsaved]), ci,
+                           (ctypes.c_void_p * n)(*[t.data_ptr() for t in g16]), co, dw.data_ptr(), xsaved[0].shape[0],
+                           (ctypes.c_int * n)(*[t.shape[1] for t in xsaved]), (ctypes.c_int * n)(*[t.shape[2] for t in xsaved]), ci, co, k, _st())
+                else:
+                    for xs_l, g_l in zip(xsaved, g):
+                        B, H, W, _ = xs_l.shape
                         C.call("fcvsr_conv2d_wgrad", xs_l.data_ptr(), ci, g_l.data_ptr(), co, dw.data_ptr(), B, H, W, ci, co, k, 1, _st())
                 gw = dw.view(k, k, ci, co).permute(3, 2, 0, 1)
             if ctx.has_bias and ctx.needs_input_grad[1]:
@@ -401,7 +405,7 @@ def context_pool(xs, wmask):
 def conv2d_levels(xs, w, bias=None, mode: str = "tf32"):
     """[conv2d(x, w, bias) for x in xs] for stride-1 convolutions; one launch per pass in "tf32" mode when the shape fits tcgen05."""
     co, ci, k, _ = w.shape
-    if mode == "tf32" and len(xs) > 1 and len(xs) <= 4 and _tc_ok(ci, co, k, 1) and _tc_ok(co, ci, k, 1) and co >= 16:
+    if mode == "tf32" and 1 < len(xs) <= 3 and _tc_ok(ci, co, k, 1) and _tc_ok(co, ci, k, 1) and co >= 16:
         return list(_Conv2dLevels.apply(w, bias, *xs))
     return [conv2d(x, w, bias, 1, mode) for x in xs]
 

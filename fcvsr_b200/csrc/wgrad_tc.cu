@@ -32,10 +32,14 @@
 #define WG_THREADS (32 * 6)                               // TMA producer, MMA issuer, 4 epilogue warps
 #define WG_MAXG 5
 
+#define WG_MAX_PROB 3
+// Up to three problems (tensor pairs of different spatial size, same channels and batch: the pyramid levels of a BlockRCB
+// convolution, whose weight gradients add up) share one launch: the CTAs walk ONE tile list and accumulate into the same dW.
 struct WgradTcParams {
     float* dw;                   // [k*k][Cin][Cout] fp32, accumulated
-    int B, H, W, Cin, Cout, ks;
-    int tiles_x, tiles_y, total_tiles;
+    int B, Cin, Cout, ks;
+    int nprob, total_tiles;
+    int tiles_x[WG_MAX_PROB], tiles_y[WG_MAX_PROB], tile_begin[WG_MAX_PROB];
     int* err;
 };
 
@@ -46,7 +50,9 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_by
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, const WgradTcParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_dy1,
+                const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_dy2, const WgradTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + WG_NSTAGE * WG_STAGE);
@@ -77,19 +83,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int tx = t % p.tiles_x, r = t / p.tiles_x;
-                const int ty = r % p.tiles_y, b = r / p.tiles_y;
+                const int pr = (p.nprob > 1 && t >= p.tile_begin[1]) ? ((p.nprob > 2 && t >= p.tile_begin[2]) ? 2 : 1) : 0;
+                const int txs = pr == 0 ? p.tiles_x[0] : (pr == 1 ? p.tiles_x[1] : p.tiles_x[2]);
+                const int tys = pr == 0 ? p.tiles_y[0] : (pr == 1 ? p.tiles_y[1] : p.tiles_y[2]);
+                const int tl = t - (pr == 0 ? 0 : (pr == 1 ? p.tile_begin[1] : p.tile_begin[2]));
+                const CUtensorMap* mx = pr == 0 ? &map_x : (pr == 1 ? &map_x1 : &map_x2);
+                const CUtensorMap* mdy = pr == 0 ? &map_dy : (pr == 1 ? &map_dy1 : &map_dy2);
+                const int tx = tl % txs, r = tl / txs;
+                const int ty = r % tys, b = r / tys;
                 const int y0 = ty * WG_TH, x0 = tx * WG_TW;
                 mbar_wait(&empty[stage], phase ^ 1, p.err, 31);
                 uint8_t* sa = smem + stage * WG_STAGE;
                 if (KS == 3) {
                     mbar_expect_tx(&full[stage], WG_STAGE);
-                    for (int c = 0; c < 3; ++c) tma_load_4d(sa + c * WG_A_COPY, &map_x, &full[stage], ci0, x0 - 1 + c, y0 - 1, b);
+                    for (int c = 0; c < 3; ++c) tma_load_4d(sa + c * WG_A_COPY, mx, &full[stage], ci0, x0 - 1 + c, y0 - 1, b);
                 } else {
                     mbar_expect_tx(&full[stage], 2 * WG_B_STAGE);
-                    tma_load_4d(sa, &map_x, &full[stage], ci0, x0, y0, b);
+                    tma_load_4d(sa, mx, &full[stage], ci0, x0, y0, b);
                 }
-                tma_load_4d(sa + WG_A_STAGE, &map_dy, &full[stage], co0, x0, y0, b);
+                tma_load_4d(sa + WG_A_STAGE, mdy, &full[stage], co0, x0, y0, b);
                 if (++stage == WG_NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
@@ -168,14 +180,15 @@ typedef CUresult (*WgEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// x: bf16 NHWC [B,H,W,ldx] (Cin channels), dy: bf16 NHWC [B,H,W,lddy] (Cout channels), both 16-byte aligned with ld % 8 == 0;
-// dw: fp32 [k*k][Cin][Cout], ACCUMULATED (zero-fill first; Cout % 4 == 0 and 16-byte aligned for the vector reductions).
+// x[i]: bf16 NHWC [B,H_i,W_i,ldx] (Cin channels), dy[i]: bf16 NHWC [B,H_i,W_i,lddy] (Cout channels), 16-byte aligned, ld % 8 == 0
+// (HOST arrays of nprob <= 3 device pointers; H, W HOST arrays); dw: fp32 [k*k][Cin][Cout], ACCUMULATED over every problem
+// (zero-fill first; Cout % 4 == 0 and 16-byte aligned for the vector reductions).
 // k in {1, 3}, stride 1, padding k/2, Cin % 64 == 0, Cout % 64 == 0; other shapes return FCVSR_ERR_UNSUPPORTED.
-extern "C" int fcvsr_conv2d_wgrad_tc(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin,
-                                     int Cout, int ksize, cudaStream_t st) {
-    if (!x || !dy || !dw || B <= 0 || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
+extern "C" int fcvsr_conv2d_wgrad_tc_multi(int nprob, const void* const* x, int ldx, const void* const* dy, int lddy, float* dw, int B,
+                                           const int* H, const int* W, int Cin, int Cout, int ksize, cudaStream_t st) {
+    if (nprob < 1 || nprob > WG_MAX_PROB || !x || !dy || !dw || !H || !W || B <= 0) return FCVSR_ERR_ARG;
     if ((ksize != 1 && ksize != 3) || Cin <= 0 || Cout <= 0 || (Cin & 63) || (Cout & 63)) return FCVSR_ERR_UNSUPPORTED;
-    if ((ldx & 7) || (lddy & 7) || (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15)) return FCVSR_ERR_UNSUPPORTED;
+    if ((ldx & 7) || (lddy & 7) || ((uintptr_t)dw & 15)) return FCVSR_ERR_UNSUPPORTED;
     static WgEncodeFn enc = nullptr;
     if (!enc) {
         void* ptr = nullptr;
@@ -185,29 +198,38 @@ extern "C" int fcvsr_conv2d_wgrad_tc(const void* x, int ldx, const void* dy, int
             return FCVSR_ERR_CUDA;
         enc = (WgEncodeFn)ptr;
     }
-    CUtensorMap map_x, map_dy;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W * ldx * 2, (cuuint64_t)H * W * ldx * 2};
-        cuuint32_t box[4] = {64, WG_TW, (cuuint32_t)(ksize == 3 ? WG_TH + 2 : WG_TH), 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return FCVSR_ERR_CUDA;
-    }
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)lddy * 2, (cuuint64_t)W * lddy * 2, (cuuint64_t)H * W * lddy * 2};
-        cuuint32_t box[4] = {64, WG_TW, WG_TH, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (enc(&map_dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)dy, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return FCVSR_ERR_CUDA;
-    }
+    CUtensorMap map_x[WG_MAX_PROB], map_dy[WG_MAX_PROB];
     WgradTcParams p;
-    p.dw = dw; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.ks = ksize;
-    p.tiles_x = (W + WG_TW - 1) / WG_TW; p.tiles_y = (H + WG_TH - 1) / WG_TH;
-    p.total_tiles = p.tiles_x * p.tiles_y * B;
+    p.dw = dw; p.B = B; p.Cin = Cin; p.Cout = Cout; p.ks = ksize; p.nprob = nprob;
+    int tiles = 0;
+    for (int i = 0; i < WG_MAX_PROB; ++i) {
+        const int j = i < nprob ? i : 0;
+        if (i >= nprob) { map_x[i] = map_x[0]; map_dy[i] = map_dy[0]; p.tiles_x[i] = p.tiles_x[0]; p.tiles_y[i] = p.tiles_y[0]; p.tile_begin[i] = tiles; continue; }
+        if (!x[j] || !dy[j] || H[j] <= 0 || W[j] <= 0) return FCVSR_ERR_ARG;
+        if (((uintptr_t)x[j] | (uintptr_t)dy[j]) & 15) return FCVSR_ERR_UNSUPPORTED;
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W[j], (cuuint64_t)H[j], (cuuint64_t)B};
+            cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)W[j] * ldx * 2, (cuuint64_t)H[j] * W[j] * ldx * 2};
+            cuuint32_t box[4] = {64, WG_TW, (cuuint32_t)(ksize == 3 ? WG_TH + 2 : WG_TH), 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            if (enc(&map_x[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x[j], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return FCVSR_ERR_CUDA;
+        }
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W[j], (cuuint64_t)H[j], (cuuint64_t)B};
+            cuuint64_t strides[3] = {(cuuint64_t)lddy * 2, (cuuint64_t)W[j] * lddy * 2, (cuuint64_t)H[j] * W[j] * lddy * 2};
+            cuuint32_t box[4] = {64, WG_TW, WG_TH, 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            if (enc(&map_dy[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)dy[j], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return FCVSR_ERR_CUDA;
+        }
+        p.tiles_x[i] = (W[j] + WG_TW - 1) / WG_TW; p.tiles_y[i] = (H[j] + WG_TH - 1) / WG_TH;
+        p.tile_begin[i] = tiles;
+        tiles += p.tiles_x[i] * p.tiles_y[i] * B;
+    }
+    p.total_tiles = tiles;
     static int* err = nullptr;
     static int num_sms = 0;
     const size_t smem = 1024 + (size_t)WG_NSTAGE * WG_STAGE + 256;
@@ -225,6 +247,14 @@ extern "C" int fcvsr_conv2d_wgrad_tc(const void* x, int ldx, const void* dy, int
     if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
     dim3 grid(gx, Cout / 64, Cin / 64);
-    wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(map_x, map_dy, p);
+    wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(map_x[0], map_dy[0], map_x[1], map_dy[1], map_x[2], map_dy[2], p);
     return fcvsr_launch_status();
+}
+
+extern "C" int fcvsr_conv2d_wgrad_tc(const void* x, int ldx, const void* dy, int lddy, float* dw, int B, int H, int W, int Cin,
+                                     int Cout, int ksize, cudaStream_t st) {
+    if (!x || !dy) return FCVSR_ERR_ARG;
+    const void* xs[1] = {x};
+    const void* dys[1] = {dy};
+    return fcvsr_conv2d_wgrad_tc_multi(1, xs, ldx, dys, lddy, dw, B, &H, &W, Cin, Cout, ksize, st);
 }

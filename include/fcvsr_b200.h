@@ -276,6 +276,10 @@ int fcvsr_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, float
 /* Both operand-typed copies of a dense fp32 tensor in one pass: y_tf32 = values rounded to nearest TF32 (fp32 storage), y_bf16 =
  * bf16; either may be NULL; numel % 4 == 0.  (Forward / data-gradient operands and the tcgen05 weight gradient's operands.) */
 int fcvsr_round_copy_dual(const float* x, float* y_tf32, void* y_bf16, long long numel, cudaStream_t stream);
+/* fcvsr_conv2d_wgrad_tc over up to three tensor pairs of different spatial size (same batch and channels: the pyramid levels of a
+ * BlockRCB convolution) in one launch; dw accumulates over all of them.  x, dy, H, W: HOST arrays. */
+int fcvsr_conv2d_wgrad_tc_multi(int nprob, const void* const* x, int ldx, const void* const* dy, int lddy, float* dw, int B,
+                                const int* H, const int* W, int Cin, int Cout, int ksize, cudaStream_t stream);
 /* 4 -> 4 channel convolutions (the ConvBlk convolutions of CVSR_freq.py:344-357 under autograd; csrc/mgaa.cu): x, y, dy
  * [B,H,W,4] fp32 (16-byte aligned), w [k*k][ci][co], k odd <= 11, stride 1, zero padding k / 2, no bias.  The data gradient is
  * fcvsr_conv4x4 on dy with w'[tap][co][ci] = w[k*k - 1 - tap][ci][co]; fcvsr_conv4x4_wgrad ACCUMULATES dw [k*k][4][4] with
