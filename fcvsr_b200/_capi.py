@@ -59,6 +59,7 @@ SIGNATURES = {
     "fcvsr_conv2d_wgrad_tc": "pi pi p iiiiii s",
     "fcvsr_conv2d_wgrad_tc_multi": "i pi pi p i pp iii s",
     "fcvsr_round_copy_dual": "ppp l s",
+    "fcvsr_round_copy_dual_multi": "i ppp p s",
     "fcvsr_conv4x4": "ppp iiii s",
     "fcvsr_conv4x4_wgrad": "ppp iiii s",
     "fcvsr_pack_conv_weight": "pp iiiii s",

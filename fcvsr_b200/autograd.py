@@ -181,6 +181,14 @@ def _conv_multi_launch(xs, wt: torch.Tensor, bias: Optional[torch.Tensor], co: i
     return ys
 
 
+def _round_dual_multi(xs, y32, y16):
+    """TF32-rounded and / or bf16 copies of up to three dense fp32 tensors in one launch."""
+    import ctypes
+    n = len(xs)
+    vp = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts]) if ts is not None else None  # noqa: E731
+    C.call("fcvsr_round_copy_dual_multi", n, vp(xs), vp(y32), vp(y16), (ctypes.c_longlong * n)(*[t.numel() for t in xs]), _st())
+
+
 class _Conv2dLevels(torch.autograd.Function):
     """The same stride-1 convolution (one weight, one bias) on several tensors of different spatial size -- the pyramid levels
     of a BlockRCB / SCGroup convolution (CVSR_freq.py:766-770, :797-803) -- in ONE tcgen05 launch for the forward and one for
@@ -196,13 +204,9 @@ class _Conv2dLevels(torch.autograd.Function):
             wt = torch.empty(max(co, 16), k * k * ci, device=w.device, dtype=F32)
             wc = w.detach().contiguous()
             C.call("fcvsr_pack_conv_weight", wc.data_ptr(), wt.data_ptr(), co, ci, k, 0, 16, _st())
-            xr, xb = [], []
-            for x in xh:
-                r = torch.empty_like(x)
-                b16 = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if wg_tc else None
-                C.call("fcvsr_round_copy_dual", x.data_ptr(), r.data_ptr(), b16.data_ptr() if wg_tc else 0, x.numel(), _st())
-                xr.append(r)
-                xb.append(b16)
+            xr = [torch.empty_like(x) for x in xh]
+            xb = [torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if wg_tc else None for x in xh]
+            _round_dual_multi(xh, xr, xb if wg_tc else None)
             ys = _conv_multi_launch(xr, wt, None if bias is None else bias.detach(), co, k)
         ctx.save_for_backward(w, *(xb if wg_tc else xh))
         ctx.wg_tc, ctx.has_bias, ctx.n = wg_tc, bias is not None, len(xs)
@@ -219,15 +223,11 @@ class _Conv2dLevels(torch.autograd.Function):
         gw = gb = None
         gxs = [None] * ctx.n
         with torch.cuda.device(w.device):
-            gr, g16 = [], []
-            for t in g:
-                r = torch.empty_like(t) if need_x else None
-                b16 = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16) if (ctx.wg_tc and ctx.needs_input_grad[0]) else None
-                if r is not None or b16 is not None:
-                    C.call("fcvsr_round_copy_dual", t.data_ptr(), r.data_ptr() if r is not None else 0,
-                           b16.data_ptr() if b16 is not None else 0, t.numel(), _st())
-                gr.append(r)
-                g16.append(b16)
+            want16 = ctx.wg_tc and ctx.needs_input_grad[0]
+            gr = [torch.empty_like(t) if need_x else None for t in g]
+            g16 = [torch.empty(t.shape, device=t.device, dtype=torch.bfloat16) if want16 else None for t in g]
+            if need_x or want16:
+                _round_dual_multi(g, gr if need_x else None, g16 if want16 else None)
             if need_x:
                 wt = torch.empty(max(ci, 16), k * k * co, device=w.device, dtype=F32)
                 wc = w.contiguous()

@@ -660,6 +660,44 @@ __global__ void round_copy_dual_kernel(const float* __restrict__ x, float* __res
     if (y16) store_operand4(y16, i * 4, v, 1);
 }
 
+// The same for up to three tensors in one launch (the pyramid levels of a convolution's input or upstream gradient).
+struct RoundDualSeg { const float* x; float* y32; void* y16; unsigned long long begin4; };
+struct RoundDualArgs { RoundDualSeg seg[3]; int n; unsigned long long total4; };
+__global__ void round_copy_dual_multi_kernel(const RoundDualArgs a) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.total4) return;
+    const int s = (a.n > 1 && i >= a.seg[1].begin4) ? ((a.n > 2 && i >= a.seg[2].begin4) ? 2 : 1) : 0;
+    const float* x = s == 0 ? a.seg[0].x : (s == 1 ? a.seg[1].x : a.seg[2].x);
+    float* y32 = s == 0 ? a.seg[0].y32 : (s == 1 ? a.seg[1].y32 : a.seg[2].y32);
+    void* y16 = s == 0 ? a.seg[0].y16 : (s == 1 ? a.seg[1].y16 : a.seg[2].y16);
+    const size_t j = (size_t)(i - (s == 0 ? 0ull : (s == 1 ? a.seg[1].begin4 : a.seg[2].begin4)));
+    const float4 v = reinterpret_cast<const float4*>(x)[j];
+    if (y32) store_operand4(y32, j * 4, v, 0);
+    if (y16) store_operand4(y16, j * 4, v, 1);
+}
+
+// x / y_tf32 / y_bf16: HOST arrays of n <= 3 device pointers (entries of y_tf32 / y_bf16, or the arrays themselves, may be NULL);
+// numel: HOST array, each % 4 == 0.
+extern "C" int fcvsr_round_copy_dual_multi(int n, const float* const* x, float* const* y_tf32, void* const* y_bf16,
+                                           const long long* numel, cudaStream_t st) {
+    if (n < 1 || n > 3 || !x || !numel || (!y_tf32 && !y_bf16)) return FCVSR_ERR_ARG;
+    RoundDualArgs a;
+    a.n = n;
+    unsigned long long t = 0;
+    for (int i = 0; i < 3; ++i) {
+        const int j = i < n ? i : 0;
+        a.seg[i].x = x[j]; a.seg[i].y32 = y_tf32 ? y_tf32[j] : nullptr; a.seg[i].y16 = y_bf16 ? y_bf16[j] : nullptr;
+        a.seg[i].begin4 = t;
+        if (i >= n) continue;
+        if (!x[j] || numel[j] <= 0 || (numel[j] & 3) || (!a.seg[i].y32 && !a.seg[i].y16)) return FCVSR_ERR_ARG;
+        if (((uintptr_t)x[j] | (uintptr_t)a.seg[i].y32) & 15 || ((uintptr_t)a.seg[i].y16 & 7)) return FCVSR_ERR_ARG;
+        t += (unsigned long long)numel[j] / 4;
+    }
+    a.total4 = t;
+    round_copy_dual_multi_kernel<<<(unsigned)((t + 255) / 256), 256, 0, st>>>(a);
+    return fcvsr_launch_status();
+}
+
 extern "C" int fcvsr_round_copy_dual(const float* x, float* y_tf32, void* y_bf16, long long numel, cudaStream_t st) {
     if (!x || (!y_tf32 && !y_bf16) || numel <= 0 || (numel & 3) || ((uintptr_t)x & 15) || ((uintptr_t)y_tf32 & 15) || ((uintptr_t)y_bf16 & 7))
         return FCVSR_ERR_ARG;

@@ -276,6 +276,10 @@ int fcvsr_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, float
 /* Both operand-typed copies of a dense fp32 tensor in one pass: y_tf32 = values rounded to nearest TF32 (fp32 storage), y_bf16 =
  * bf16; either may be NULL; numel % 4 == 0.  (Forward / data-gradient operands and the tcgen05 weight gradient's operands.) */
 int fcvsr_round_copy_dual(const float* x, float* y_tf32, void* y_bf16, long long numel, cudaStream_t stream);
+/* fcvsr_round_copy_dual for up to three tensors in one launch (HOST arrays of n device pointers / element counts; entries of
+ * y_tf32 / y_bf16, or the arrays themselves, may be NULL). */
+int fcvsr_round_copy_dual_multi(int n, const float* const* x, float* const* y_tf32, void* const* y_bf16, const long long* numel,
+                                cudaStream_t stream);
 /* fcvsr_conv2d_wgrad_tc over up to three tensor pairs of different spatial size (same batch and channels: the pyramid levels of a
  * BlockRCB convolution) in one launch; dw accumulates over all of them.  x, dy, H, W: HOST arrays. */
 int fcvsr_conv2d_wgrad_tc_multi(int nprob, const void* const* x, int ldx, const void* const* dy, int lddy, float* dw, int B,
