@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the config-4 training-step pass")
     ap.add_argument("--single-mode", action="store_true", help="measure only --dtype (profiling runs)")
     ap.add_argument("--seq-frames", type=int, default=100)
-    ap.add_argument("--train-steps", type=int, default=5)
+    ap.add_argument("--train-steps", type=int, default=10)
     return ap.parse_args()
 
 
