@@ -1,30 +1,31 @@
 // tcgen05 / TMEM implicit-GEMM convolution fed by TMA  (sm_100a only).
 //
-// Computes, for NHWC fp32 tensors, y = act(conv_kxk(x, w) + bias) + res - res2 (k in {1,3}, stride 1,
-// zero padding k/2) as a GEMM  D[pixels, Cout] = sum_{tap, cin} A_tap[pixels, cin] * W[Cout, tap, cin]
-// on the 5th-generation tensor cores with TF32 operands and fp32 accumulation in tensor memory.
-// It replaces every 3x3 / 1x1 nn.Conv2d of the reference hot path whose shape fits
-// (CVSR_freq.py:1371-1430 MGAAbk, :705-822 SCNetbk, :2739-2749 tail); the library-call equivalent in
-// the reference is cuDNN (conv2d) -- there is no such kernel in the reference to port.
+// Computes, for NHWC tensors, y = act(conv_kxk(x, w) + bias) + res - res2 (k in {1,3}, stride 1, zero padding k/2) as a GEMM
+// D[pixels, Cout] = sum_{tap, cin} A_tap[pixels, cin] * W[Cout, tap, cin] on the 5th-generation tensor cores: bf16 operand tensors
+// (kind::f16) or TF32-rounded fp32 tensors (kind::tf32), fp32 accumulation in tensor memory.  It replaces every 3x3 / 1x1 nn.Conv2d
+// of the reference hot path whose shape fits (CVSR_freq.py:1371-1430 MGAAbk, :705-822 SCNetbk, :2739-2749 tail); the library-call
+// equivalent in the reference is cuDNN (conv2d) -- there is no such kernel in the reference to port.
 //
-// Design (one persistent CTA per SM, 7 warps, warp-specialised):
-//   * M tile = 8 x 16 output pixels (128 = UMMA M), N tile = Cout (<= 128 per pass), K walked as
-//     (32-channel chunk) x (filter tap); one tcgen05.mma covers K = 8 (32 bytes of TF32).
-//   * A operand, halo re-use: for each 32-channel chunk the producer warp TMA-loads THREE copies of the
-//     (8+2) x 16-pixel input window, shifted by -1/0/+1 pixel in x (TMA zero-fills out-of-image
-//     pixels = the conv padding).  Each copy is a [160 rows][128 B] SWIZZLE_128B K-major tile, so the
-//     operand of filter tap (ky,kx) is simply copy[kx] viewed from row ky*16 on: a 2048-byte (1024-
-//     aligned) shift of the matrix descriptor.  Nine taps read 3 loads instead of 9: L2->SMEM traffic
-//     per pixel drops from 9x to 3.75x the input bytes, which is what lets a Cout=64 conv stay
-//     tensor-bound instead of L2-bound.
-//   * B operand (weights, [Cout][tap*Cin] K-major in HBM/L2) streams through its own 4-stage ring,
-//     one (tap, chunk) slice of [Cout][32] per stage.
-//   * Accumulators: 2 x N columns of TMEM, double-buffered so the epilogue of tile t overlaps the MMAs
-//     of tile t+1.  Epilogue warps read TMEM with tcgen05.ld (lane == pixel), apply bias / activation /
-//     residuals in registers and store 64-byte runs per thread (optionally through pixel_shuffle(2)).
+// Design (one persistent CTA per SM, 19 warps, warp-specialised: A producer, B producer, MMA issuer, 16 epilogue warps):
+//   * M tile = 8 x 16 output pixels (128 = UMMA M), N tile = Cout (<= 128 per pass), K walked as (128-byte channel chunk: 64 bf16
+//     or 32 TF32 channels) x (filter tap); one tcgen05.mma covers 32 bytes of K.
+//   * A operand, halo re-use: for each channel chunk the producer TMA-loads THREE copies of the (8+2) x 16-pixel input window,
+//     shifted by -1/0/+1 pixel in x (TMA zero-fills out-of-image pixels = the conv padding).  Each copy is a [160 rows][128 B]
+//     SWIZZLE_128B K-major tile, so the operand of filter tap (ky,kx) is copy[kx] viewed from row ky*16 on: a 2048-byte
+//     (1024-aligned) shift of the matrix descriptor.  Nine taps read 3 loads instead of 9.
+//   * B operand (weights, [Cout][tap*Cin] K-major): one filter row of taps per ring stage; when every stage of the filter fits
+//     the ring (bf16 64 -> 64 3x3: 72 KB) the weights are loaded once per CTA and stay resident.  Several filters can be stacked
+//     in one weight matrix with a row offset per problem (fcvsr_conv2d_tc_multi_w).
+//   * Accumulators: FOUR N-column tiles in TMEM; the epilogue warps form 1, 2 or 4 sets that drain different accumulator tiles
+//     concurrently (tcgen05.ld, lane == pixel), apply bias (staged in shared memory) / activation / residuals in registers and
+//     store 256-bit runs per thread (optionally through pixel_shuffle(2), optionally a second operand-typed output); bf16
+//     64-channel outputs are staged in a SWIZZLE_128B shared tile per set and leave with ONE TMA store per tile.
+//   * Up to four problems (tensors of different spatial size: the pyramid levels of SCNetbk) share one persistent tile list;
+//     programmatic dependent launch overlaps the prologue with the previous convolution's drain.
 //
-// Roofline: tensor (TF32: K=8 per instruction, half the bf16 rate).  Algorithmic FLOPs per output pixel
-// = 2 * Cin * Cout * k * k; algorithmic HBM bytes per pixel = 4 * (Cin + Cout) (+4*Cout per residual).
+// Roofline: tensor for N >= 128; the N = 64 shapes are bound by shared-memory bandwidth (an MMA reads 6 KB of operands for 32 clk of
+// tensor time; 312 KB per tile = the measured 2440 clk tile period, profiles/r2_notes.md 5).  Algorithmic FLOPs per output pixel
+// = 2 * Cin * Cout * k * k; algorithmic HBM bytes per pixel = esz * (Cin + Cout) (+4*Cout per residual).
 #include "tc_common.cuh"
 #include <cuda_bf16.h>
 #include <stdlib.h>

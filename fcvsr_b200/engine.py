@@ -6,7 +6,7 @@ packing of the reference disappear), (2) a per-shape workspace of NHWC device bu
 launch sequence that restates ``GShiftNet.forward`` (CVSR_train/arch/CVSR_freq.py:2688-2756) kernel
 by kernel.  Every arithmetic step is a call into ``libfcvsr_b200.so`` through the C ABI
 (include/fcvsr_b200.h); no ATen op touches the data path.  The whole launch sequence can be captured
-into a CUDA graph (``use_graph``), which removes the Python launch overhead of the ~10^3 launches.
+into a CUDA graph (``use_graph``), which removes the Python launch overhead of the 378 launches (FCVSR).
 
 Line numbers in comments refer to CVSR_train/arch/CVSR_freq.py.
 """
