@@ -93,9 +93,12 @@ def quantize_u8(y: torch.Tensor, h: int, w: int) -> torch.Tensor:
 def _run_range(model, local, h_lo, lo, hi, n, mode, batch, scale, h, w, to_uint8):
     dev = local.device
     outs = []
+    # the window indices of the whole range travel to the device ONCE: a per-launch torch.tensor(..., device=...) is a blocking
+    # pageable copy that makes the host wait for the previous forward before it can queue the next one
+    idx_all = torch.tensor([[j - h_lo for j in window_indices(t, n, mode)] for t in range(lo, hi)], dtype=torch.long).to(dev)
     for t0 in range(lo, hi, batch):
         ts = range(t0, min(t0 + batch, hi))
-        idx = torch.tensor([[j - h_lo for j in window_indices(t, n, mode)] for t in ts], device=dev)
+        idx = idx_all[t0 - lo:t0 - lo + len(ts)]
         clips = local[idx.reshape(-1)].view(len(ts), 2 * RADIUS + 1, *local.shape[1:])
         y = model(clips)
         outs.append(quantize_u8(y, scale * h, scale * w) if to_uint8 else y[..., : scale * h, : scale * w])
