@@ -641,7 +641,7 @@ class Engine:
         self._conv(P["crt2"], p["simh"], 64, p["sim"], 4, B, H, Wf)
         # CorrBlock lookup (:1475-1483); corr_f feeds both branches (:1487-1488)
         om = 2 if O16 else R
-        self._k("fcvsr_corr_gather2", spec, 384, 0, 128, cc + 128 * E, cc + (half * CC + 128) * E, CC, B, H, Wf, 128, om)
+        self._k("fcvsr_corr_gather2", spec, 384, 0, 128, cc + 128 * E, cc + (half * CC + 128) * E, CC, B, H, Wf, 128, om | 4)
         # convcorr (:1487-1488), both branches as a batch of 2B
         self._conv(P["corr0"], cc, CC, p["c1"], 64, 2 * B, H, Wf, act=RELU, rnd=True)
         self._conv(P["corr2"], p["c1"], 64, p["c2"], 64, 2 * B, H, Wf, act=RELU, rnd=True)

@@ -94,7 +94,8 @@ int fcvsr_fft_c2r_w(const float* in_c, float* y, int ldy, const float* tw, int B
 /* CorrBlock lookup (:1279-1337): S [B,H*Wf,ldS] floats with the two packed spectra at float offsets
  * a_off / b_off (C2 floats each, complex-interleaved); out [B,H*Wf,ldo], 81 channels. */
 int fcvsr_corr_gather(const float* S, int ldS, int a_off, int b_off, void* out, int ldo, int B, int H, int Wf,
-                      int C2, int op_mode /* 0 fp32, 1 TF32-rounded, 2 bf16 */, cudaStream_t stream);
+                      int C2, int op_mode /* 0 fp32, 1 TF32-rounded, 2 bf16; + 4: 16-byte aligned rows whose channels 81 .. 83 (fp32) /
+                      81 .. 87 (bf16) may be zero-filled: vector stores */, cudaStream_t stream);
 /* same, writing the result to two tensors of the same layout (out2 may be NULL): corr_f feeds both offset branches (:1487-1488) */
 int fcvsr_corr_gather2(const float* S, int ldS, int a_off, int b_off, void* out, void* out2, int ldo, int B, int H, int Wf,
                        int C2, int op_mode, cudaStream_t stream);

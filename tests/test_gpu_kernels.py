@@ -38,7 +38,8 @@ def _bf16r(t):
 # ------------------------------------------------------------------------------------------------------------------------
 # CorrBlock lookup (CVSR_freq.py:1279-1337)
 # ------------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,H,W,mode", [(1, 12, 20, 0), (2, 70, 18, 0), (2, 9, 14, 1), (1, 70, 12, 2)])
+@pytest.mark.parametrize("B,H,W,mode", [(1, 12, 20, 0), (2, 70, 18, 0), (2, 9, 14, 1), (1, 70, 12, 2), (2, 70, 18, 4), (2, 9, 14, 5),
+                                        (1, 70, 12, 6), (2, 24, 36, 6)])
 def test_corr_gather_kernel(dev, B, H, W, mode):
     """fcvsr_corr_gather on an interleaved spectrum against oracle.corr_lookup on the reference's cat([imag, real]) packing;
     H = 70 > 68 exercises the rows where the 64x2 'image' reinterpretation runs out; op_mode 1 / 2 store
@@ -55,12 +56,13 @@ def test_corr_gather_kernel(dev, B, H, W, mode):
         S[:, :, 128 * k + 1:128 * k + 128:2] = zz.imag
     Sd = S.to(dev)
     ldo = 96
-    out = torch.zeros(B, H * Wf, ldo, device=dev, dtype=torch.bfloat16 if mode == 2 else torch.float32)
+    out = torch.zeros(B, H * Wf, ldo, device=dev, dtype=torch.bfloat16 if (mode & 3) == 2 else torch.float32)
     C.call("fcvsr_corr_gather", Sd.data_ptr(), 384, 0, 128, out.data_ptr() + 8 * out.element_size(), ldo, B, H, Wf, 128, mode, _st())
     torch.cuda.synchronize()
     got = out.float().cpu()[:, :, 8:89].reshape(B, H, Wf, 81).permute(0, 3, 1, 2)
-    tol = {0: 1e-6, 1: 2.0 ** -11, 2: 2.0 ** -8}[mode] * max(1.0, float(ref.abs().max()))
+    tol = {0: 1e-6, 1: 2.0 ** -11, 2: 2.0 ** -8}[mode & 3] * max(1.0, float(ref.abs().max()))
     assert float((got - ref).abs().max()) <= tol
+    # mode + 4 (vector stores) zero-fills the padding channels behind the 81 real ones; nothing else is touched
     assert float(out.float().cpu()[:, :, :8].abs().max()) == 0.0 and float(out.float().cpu()[:, :, 89:].abs().max()) == 0.0
 
 
