@@ -682,7 +682,7 @@ struct MixLevel {
 };
 struct MixArgs { MixLevel lv[SC_MAX_LEV]; int nlev; int ldx, ldo, ldr; int round_main, op16, td_pooled; };
 
-template <int R16, int T16>
+template <int R16, int T16, int X16>
 __global__ void level_mix_kernel(const MixArgs a) {
     // a block is a run of 16 pixels of ONE image row: level, row and column come from block-uniform divisions (three 64-bit
     // div / mod per thread were a third of the kernel's instructions; ncu: SM throughput 74 % at 61 % of the copy bandwidth)
@@ -700,7 +700,7 @@ __global__ void level_mix_kernel(const MixArgs a) {
     const void* td = L.td;
     const void* tu = L.tu;
     const float coef = L.coef;
-    float4 o = *reinterpret_cast<const float4*>(L.xin + pix * a.ldx + c);
+    float4 o = load4_any(L.xin, pix * a.ldx + c, X16);      // X16: the carried x is the previous block's bf16 operand copy
     constexpr int t16 = T16;            // compile-time: the loads below stay straight-line (a run-time flag put every load
     const float4 rv = load4_any(L.r, pix * 64 + c, R16);    // behind its own branch: 18.7 -> 23.7 us per launch)
     o.x = fmaf(coef, rv.x, o.x); o.y = fmaf(coef, rv.y, o.y); o.z = fmaf(coef, rv.z, o.z); o.w = fmaf(coef, rv.w, o.w);
@@ -736,8 +736,89 @@ __global__ void level_mix_kernel(const MixArgs a) {
         o.w += w00 * a00.w + w01 * a01.w + w10 * a10.w + w11 * a11.w;
     }
     if (L.xout_r) store_operand4(L.xout_r, pix * a.ldr + c, o, a.op16);
+    if (!L.xout) return;                                                        // only the operand copy is kept (bf16 mode)
     if (a.round_main) store_operand4(L.xout, pix * a.ldo + c, o, a.op16);      // xout itself is an operand-typed tensor
     else *reinterpret_cast<float4*>(L.xout + pix * a.ldo + c) = o;
+}
+
+// The bf16 mode's BlockRCB launch (r, td, tu bf16, td already pooled, only the bf16 operand copy written): eight channels per
+// thread, 16-byte accesses on every bf16 tensor, a block = 32 pixels of one image row.  With four channels per thread the
+// kernel is bound by its instruction count (ncu: SM throughput 74 % at 4.6 TB/s; halving its DRAM bytes moved it by 3 %), and
+// the per-pixel index / weight arithmetic is what eight threads per pixel instead of sixteen halve.  Same expressions per
+// channel as level_mix_kernel: the results are bit-identical.
+__device__ __forceinline__ void lm8_unpack(const uint4 u, float* f) {
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+template <int X16>
+__global__ void __launch_bounds__(256, 4) level_mix8_kernel(const MixArgs a) {
+    const int bx = blockIdx.x;
+    const int l = (a.nlev > 1 && bx >= a.lv[1].blk_begin) ? ((a.nlev > 2 && bx >= a.lv[2].blk_begin) ? 2 : 1) : 0;
+    const MixLevel& L = a.lv[l];
+    const int H = L.H, W = L.W;
+    const int lb = bx - L.blk_begin;
+    const int rowid = lb / L.bpr, chunk = lb - rowid * L.bpr;      // rowid = b * H + y
+    const int x = chunk * 32 + (threadIdx.x >> 3);
+    if (x >= W) return;
+    const int b = rowid / H, y = rowid - b * H;
+    const int c = (threadIdx.x & 7) * 8;
+    const size_t pix = (size_t)rowid * W + x;
+    const unsigned short* td = reinterpret_cast<const unsigned short*>(L.td);
+    const unsigned short* tu = reinterpret_cast<const unsigned short*>(L.tu);
+    const float coef = L.coef;
+    // every load is issued before the first use
+    uint4 xr = make_uint4(0u, 0u, 0u, 0u), dv = xr, u00 = xr, u01 = xr, u10 = xr, u11 = xr;
+    float4 xf0 = make_float4(0.f, 0.f, 0.f, 0.f), xf1 = xf0;
+    if (X16) {
+        xr = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(L.xin) + pix * a.ldx + c);
+    } else {
+        xf0 = *reinterpret_cast<const float4*>(L.xin + pix * a.ldx + c);
+        xf1 = *reinterpret_cast<const float4*>(L.xin + pix * a.ldx + c + 4);
+    }
+    const uint4 rv = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(L.r) + pix * 64 + c);
+    if (td) dv = *reinterpret_cast<const uint4*>(td + pix * 64 + c);
+    float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;
+    if (tu) {
+        const int hs = H >> 1, ws = W >> 1;
+        const float sy = fmaxf(0.5f * (y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * (x + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
+        const float ly = sy - y0, lx = sx - x0;
+        const unsigned short* tb = tu + (size_t)b * hs * ws * 64 + c;
+        u00 = *reinterpret_cast<const uint4*>(tb + ((size_t)y0 * ws + x0) * 64);
+        u01 = *reinterpret_cast<const uint4*>(tb + ((size_t)y0 * ws + x1) * 64);
+        u10 = *reinterpret_cast<const uint4*>(tb + ((size_t)y1 * ws + x0) * 64);
+        u11 = *reinterpret_cast<const uint4*>(tb + ((size_t)y1 * ws + x1) * 64);
+        w00 = (1.f - ly) * (1.f - lx); w01 = (1.f - ly) * lx; w10 = ly * (1.f - lx); w11 = ly * lx;
+    }
+    float o[8], t[8];
+    if (X16) {
+        lm8_unpack(xr, o);
+    } else {
+        o[0] = xf0.x; o[1] = xf0.y; o[2] = xf0.z; o[3] = xf0.w; o[4] = xf1.x; o[5] = xf1.y; o[6] = xf1.z; o[7] = xf1.w;
+    }
+    lm8_unpack(rv, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(coef, t[i], o[i]);
+    if (td) {
+        lm8_unpack(dv, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += t[i];
+    }
+    if (tu) {
+        float t1[8], t2[8], t3[8];
+        lm8_unpack(u00, t); lm8_unpack(u01, t1); lm8_unpack(u10, t2); lm8_unpack(u11, t3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += w00 * t[i] + w01 * t1[i] + w10 * t2[i] + w11 * t3[i];
+    }
+    uint4 pk;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[1]), "f"(o[0]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[3]), "f"(o[2]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.z) : "f"(o[5]), "f"(o[4]));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk.w) : "f"(o[7]), "f"(o[6]));
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(L.xout_r) + pix * a.ldr + c) = pk;
 }
 
 // xin / xout / r / td / tu / xout_r: HOST arrays of nlev device pointers (td, tu, xout_r entries may be NULL); coef, H, W: HOST
@@ -747,6 +828,7 @@ extern "C" int fcvsr_level_mix_multi(int nlev, const float* const* xin, int ldx,
                                      const int* W, void* const* xout_r, int ldr, int round_main, int op16, int td_pooled,
                                      cudaStream_t st) {
     if (nlev < 1 || nlev > SC_MAX_LEV || !xin || !xout || !r || !coef || !H || !W || (ldx & 3) || (ldo & 3) || B <= 0) return FCVSR_ERR_ARG;
+    if ((td_pooled & 8) && !xout_r) return FCVSR_ERR_ARG;
     MixArgs a;
     a.nlev = nlev; a.ldx = ldx; a.ldo = ldo; a.ldr = ldr; a.round_main = round_main; a.op16 = op16; a.td_pooled = td_pooled;
     long long t = 0;
@@ -757,17 +839,34 @@ extern "C" int fcvsr_level_mix_multi(int nlev, const float* const* xin, int ldx,
         L.xout_r = xout_r ? xout_r[j] : nullptr; L.coef = coef[j]; L.H = H[j]; L.W = W[j];
         L.blk_begin = (int)t; L.bpr = (W[j] + 15) / 16;
         if (l >= nlev) continue;
-        if (!L.xin || !L.xout || !L.r || L.H <= 0 || L.W <= 0 || (L.tu && ((L.H | L.W) & 1)) || (L.xout_r && (ldr & 3))) return FCVSR_ERR_ARG;
+        if (!L.xin || (!L.xout && !L.xout_r) || !L.r || L.H <= 0 || L.W <= 0 || (L.tu && ((L.H | L.W) & 1)) || (L.xout_r && (ldr & 3))) return FCVSR_ERR_ARG;
         t += (long long)B * L.H * L.bpr;
         if (t > 0x7fffffffLL) return FCVSR_ERR_UNSUPPORTED;
     }
+    // bf16 mode's BlockRCB launch: only the operand copy is written, every side tensor is bf16, td is pooled
+    bool all8 = op16 && (td_pooled & 7) == 7 && xout_r && !(ldx & 7) && !(ldr & 7);
+    for (int l = 0; l < nlev && all8; ++l)
+        all8 = !xout[l] && xout_r[l] && !(((uintptr_t)xin[l] | (uintptr_t)r[l] | (uintptr_t)xout_r[l] | (uintptr_t)(td ? td[l] : nullptr) |
+                                           (uintptr_t)(tu ? tu[l] : nullptr)) & 15);
+    if (all8) {
+        long long t8 = 0;
+        for (int l = 0; l < SC_MAX_LEV; ++l) {
+            a.lv[l].blk_begin = (int)t8; a.lv[l].bpr = (a.lv[l].W + 31) / 32;
+            if (l < nlev) t8 += (long long)B * a.lv[l].H * a.lv[l].bpr;
+        }
+        if (td_pooled & 8) level_mix8_kernel<1><<<(unsigned)t8, 256, 0, st>>>(a);
+        else level_mix8_kernel<0><<<(unsigned)t8, 256, 0, st>>>(a);
+        return fcvsr_launch_status();
+    }
     const unsigned grid = (unsigned)t;
-#define LM_LAUNCH(R, T) level_mix_kernel<R, T><<<grid, 256, 0, st>>>(a)
-    switch ((td_pooled >> 1) & 3) {
-        case 0: LM_LAUNCH(0, 0); break;
-        case 1: LM_LAUNCH(1, 0); break;
-        case 2: LM_LAUNCH(0, 1); break;
-        default: LM_LAUNCH(1, 1); break;
+#define LM_LAUNCH(R, T, X) level_mix_kernel<R, T, X><<<grid, 256, 0, st>>>(a)
+    switch ((td_pooled >> 1) & 7) {
+        case 0: LM_LAUNCH(0, 0, 0); break;
+        case 1: LM_LAUNCH(1, 0, 0); break;
+        case 2: LM_LAUNCH(0, 1, 0); break;
+        case 3: LM_LAUNCH(1, 1, 0); break;
+        case 7: LM_LAUNCH(1, 1, 1); break;          // bf16 mode, blocks 2 and 3 of a group: x carried as the bf16 operand copy
+        default: return FCVSR_ERR_UNSUPPORTED;      // a bf16 xin only together with bf16 r / td / tu
     }
 #undef LM_LAUNCH
     return fcvsr_launch_status();

@@ -117,6 +117,7 @@ class Engine:
         self.r016 = True             # RCB input / skip r0 only as a bf16 tensor
         self.rr16 = True             # RCB output rr only as a bf16 tensor
         self.t16 = True              # cross-level terms td / tu as bf16 tensors
+        self.x16 = True              # x carried through a group's three BlockRCBs only as the bf16 operand copy
         self.use_last_kernel = True  # dedicated Cout = 1 kernel
         self.merge_down_up = True    # the 1x1 down / up convolutions of a BlockRCB as one launch (stacked filters)
         self.mgaa_ctas = 74          # SM cap of each of the two concurrently running MGAA calls
@@ -739,6 +740,7 @@ class Engine:
         r016 = bool(O16) and self.r016
         rr16 = int(bool(O16) and self.rr16)
         t16 = 4 if (O16 and self.t16) else 0      # down / up conv outputs td, tu as bf16 tensors (flag bit of level_mix)
+        x16 = bool(O16 and R and rr16 and t16 and self.x16)
         L3 = (0, 1, 2)
         vp = lambda *ptrs: (ctypes.c_void_p * len(ptrs))(*ptrs)  # noqa: E731
         ia = lambda *v: (ctypes.c_int * len(v))(*v)  # noqa: E731
@@ -781,10 +783,13 @@ class Engine:
                     self._conv_multi(P[q + "down"], [p["rrp0"], p["rrp1"]], 64, [p["td0"], p["td1"]], 64, B, dims[1:], rnd=bool(t16))
                     self._conv_multi(P[q + "up"], rr_op[1:], 64, [p["tu1"], p["tu2"]], 64, B, dims[1:], rnd=bool(t16))
                 # x + r + d + u (:771-776)
-                self._k("fcvsr_level_mix_multi", 3, vp(*src), 64, vp(*[p[f"t{l}"] for l in L3]), 64,
+                # bf16 mode: the x carried through the group's three blocks lives only as the bf16 operand copy (what the block's
+                # first convolution read); the fp32 copy of every block (116 MB read + 116 MB written at 6 windows) is gone
+                xin = [p[f"tr{l}"] for l in L3] if (x16 and k > 0) else src
+                self._k("fcvsr_level_mix_multi", 3, vp(*xin), 64, vp(*[0 if x16 else p[f"t{l}"] for l in L3]), 64,
                         vp(*[p[f"rrh{l}" if rr16 else f"rr{l}"] for l in L3]), coef3, vp(0, p["td0"], p["td1"]),
                         vp(p["tu1"], p["tu2"], 0), B, H3, W3, vp(*[p[f"tr{l}"] if R else 0 for l in L3]), 64, 0, O16,
-                        1 + 2 * rr16 + t16)
+                        1 + 2 * rr16 + t16 + (8 if (x16 and k > 0) else 0))
             # SCGroupbk tail: x + conv(res) (:797-803)
             self._conv_multi(P[f"g{g}.conv"], [p[f"tr{l}"] if R else p[f"t{l}"] for l in L3], 64, [p[f"cur{l}"] for l in L3], 64,
                              B, dims, res=inp, ldres=64, y2=[p[f"curr{l}"] for l in L3], ldy2=64)

@@ -171,7 +171,10 @@ int fcvsr_rcb_finish(const void* res, const float* add, const void* r0, float* r
                      cudaStream_t stream);
 /* BlockRCB cross-level sum (:766-777): xout = xin + coef*r + d + bilinear_x2(tu[B,H/2,W/2,64]) with
  * d = mean2x2(td[B,2H,2W,64]), or d = td[B,H,W,64] when td_pooled & 1 (down conv applied to the pooled tensor);
- * td_pooled & 2: r is a bf16 tensor; td_pooled & 4: td and tu are.  fcvsr_rcb_finish: r may be NULL when r_operand_copy is given. */
+ * td_pooled & 2: r is a bf16 tensor; td_pooled & 4: td and tu are; td_pooled & 8 (only with 2 and 4): xin is a bf16 tensor too
+ * (pass its address through the float pointer; ldx in elements).  xout may be NULL when xout_r is given: only the operand copy
+ * is written (xin == xout_r in place is fine, a thread reads and writes its own four channels).
+ * fcvsr_rcb_finish: r may be NULL when r_operand_copy is given. */
 int fcvsr_level_mix(const float* xin, int ldx, float* xout, int ldo, const void* r, float coef, const void* td,
                     const void* tu, int B, int H, int W, void* xout_r, int ldr, int round_main, int op16,
                     int td_pooled, cudaStream_t stream);

@@ -736,6 +736,25 @@ def test_scnet_helpers_bf16_inputs(dev, b16):
     torch.cuda.synchronize()
     assert float((out.cpu() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
     assert float((out_r.float().cpu() - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max())
+    if b16:     # x carried as the bf16 operand copy, in place, no fp32 output (td_pooled & 8; blocks 2 and 3 of a group)
+        xr = rnd(xin)
+        x16 = xr.to(dev).to(dt)
+        C.call("fcvsr_level_mix", x16.data_ptr(), 64, 0, 64, rr_d.data_ptr(), 1.0, td_d.data_ptr(), tu_d.data_ptr(),
+               B, H, W, x16.data_ptr(), 64, 0, 1, 15, _st())
+        ref16 = xr + rrv + td + up.permute(0, 2, 3, 1).reshape(B, P, 64)
+        torch.cuda.synchronize()
+        assert float((x16.float().cpu() - ref16).abs().max()) <= 2 ** -8 * float(ref16.abs().max())
+        # fp32 xin, only the operand copy written: the eight-channel kernel, bit-identical to the four-channel one above
+        out_r8 = torch.zeros_like(out_r)
+        C.call("fcvsr_level_mix", xin_d.data_ptr(), 64, 0, 64, rr_d.data_ptr(), 1.0, td_d.data_ptr(), tu_d.data_ptr(),
+               B, H, W, out_r8.data_ptr(), 64, 0, 1, 7, _st())
+        torch.cuda.synchronize()
+        assert torch.equal(out_r8, out_r)
+        # a bf16 xin without bf16 r / td / tu is refused, and so is a call without any output
+        assert C.try_call("fcvsr_level_mix", x16.data_ptr(), 64, 0, 64, rr_d.data_ptr(), 1.0, td_d.data_ptr(), tu_d.data_ptr(),
+                          B, H, W, x16.data_ptr(), 64, 0, 1, 9, _st()) == C.ERR_UNSUPPORTED
+        assert C.try_call("fcvsr_level_mix", x16.data_ptr(), 64, 0, 64, rr_d.data_ptr(), 1.0, td_d.data_ptr(), tu_d.data_ptr(),
+                          B, H, W, 0, 64, 0, 1, 15, _st()) == C.ERR_ARG
 
 
 @pytest.mark.parametrize("kind,cin,cout,stride", [("v2", 6, 4, 1), ("v2", 8, 8, 1), ("v1", 8, 6, 2)])
