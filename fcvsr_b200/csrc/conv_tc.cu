@@ -121,7 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint8_t* b_buf = smem + TC_NA * TC_A_STAGE_BYTES;             // weight ring, TC_B_RING_BYTES
     // output staging: one [128 pixels][128 B] SWIZZLE_128B tile per epilogue set (bf16 outputs with 64 channels)
     uint8_t* stg_buf = b_buf + p.b_ring_bytes;
-    uint64_t* bars = (uint64_t*)(stg_buf + (p.stage_out ? p.epi_sets * TC_STG_BYTES : 0));
+    uint64_t* bars = (uint64_t*)(stg_buf + (p.stage_out ? p.epi_sets * (p.n_tile >> 6) * TC_STG_BYTES : 0));
     uint64_t* full_a = bars;                // [TC_NA_MAX]
     uint64_t* empty_a = bars + TC_NA_MAX;   // [TC_NA_MAX]
     uint64_t* full_b = bars + 2 * TC_NA_MAX;            // [TC_NB_MAX]
@@ -310,7 +310,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // tile's MMAs.  Instead the set writes the tile into a [128 pixels][128 B] SWIZZLE_128B buffer (conflict-free 16-byte
         // shared stores) and one elected thread hands it to the TMA unit, which writes whole lines and clips at the image border.
         const bool stg = p.stage_out != 0;
-        const uint32_t srow = smem_u32(stg_buf + eset * TC_STG_BYTES) + (uint32_t)m * TC_ROW_BYTES;
+        const uint32_t stg_halves = (uint32_t)p.n_tile >> 6;      // 64-channel halves of a staged tile (1 or 2), 16 KB each
+        const uint32_t srow = smem_u32(stg_buf + eset * (TC_STG_BYTES * stg_halves)) + (uint32_t)m * TC_ROW_BYTES;
         const uint32_t sxor = (uint32_t)(m & 7);
         const bool stager = eh == 0 && q == 0 && lane == 0;
         const int set_threads = 32 * TC_EPI_WARPS / S;
@@ -357,7 +358,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     float v[16];
                     lds_bias16(bias_sa + (pq.wrow + n0) * 4, v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fcvsr_act(__uint_as_float(r[j]) + v[j], p.act, slope);
+                    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
+                    // one uniform switch per chunk (per element it was 7 of the chunk's ~11 instructions per value)
+                    if (p.act == FCVSR_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (p.act != FCVSR_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
+                    }
                     if (pq.res && valid) {
                         float rv[16];
                         if (p.wide) {
@@ -383,10 +392,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         uint32_t w[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
-                        const uint32_t ch = (uint32_t)cb >> 3;
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + ((ch ^ sxor) << 4)), "r"(w[0]), "r"(w[1]),
+                        const uint32_t ch = ((uint32_t)cb & 63u) >> 3;
+                        const uint32_t hrow = srow + ((uint32_t)cb >> 6) * TC_STG_BYTES;
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hrow + ((ch ^ sxor) << 4)), "r"(w[0]), "r"(w[1]),
                                      "r"(w[2]), "r"(w[3]) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + (((ch + 1) ^ sxor) << 4)), "r"(w[4]), "r"(w[5]),
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(hrow + (((ch + 1) ^ sxor) << 4)), "r"(w[4]), "r"(w[5]),
                                      "r"(w[6]), "r"(w[7]) : "memory");
                         return;
                     }
@@ -463,8 +473,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + eset), "r"(set_threads) : "memory");
                 if (stager) {
                     const CUtensorMap* my = tc.pr == 0 ? &map_y : (tc.pr == 1 ? &map_y1 : (tc.pr == 2 ? &map_y2 : &map_y3));
-                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                 ::"l"(my), "r"(srow), "r"(0), "r"(tc.tx * TC_TW), "r"(tc.ty * TC_TH), "r"(tc.b) : "memory");
+                    for (uint32_t h = 0; h < stg_halves; ++h)
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"(my), "r"(srow + h * TC_STG_BYTES), "r"(64 * h), "r"(tc.tx * TC_TW), "r"(tc.ty * TC_TH), "r"(tc.b)
+                                     : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -615,14 +627,21 @@ static int conv_tc_launch(int np, const void* const* xs, const float* const* res
     // bf16 outputs with 64 channels: the epilogue stages the tile in shared memory and stores it with TMA.  The staging tiles
     // (one per epilogue set) come out of the weight ring, which keeps at least the 72 KB that hold a 64 -> 64 3x3 filter resident.
     const int smem_fixed = 1024 + TC_NA * TC_A_STAGE_BYTES + 512 + 4 * p.w_rows;
-    p.stage_out = op16 && round_out == 1 && n_tile == 64 && n_tiles == 1 && !pixel_shuffle && !any_y2 && !thin && !(ldy & 7);
+    p.stage_out = op16 && round_out == 1 && (n_tile == 64 || n_tile == 128) && n_tiles == 1 && !pixel_shuffle && !any_y2 && !thin &&
+                  !(ldy & 7);
+    // a 128-channel tile is staged as two 64-channel halves (32 KB per set): two sets of eight warps, each warp one half
+    if (p.stage_out && n_tile == 128 && p.epi_sets == 4) p.epi_sets = 2;
+    const int stg_total = p.epi_sets * (n_tile >> 6) * TC_STG_BYTES;
     p.b_ring_bytes = TC_B_RING_BYTES;
     if (p.stage_out) {
-        p.b_ring_bytes = ((TC_SMEM_LIMIT - smem_fixed) & ~1023) - p.epi_sets * TC_STG_BYTES;
+        p.b_ring_bytes = ((TC_SMEM_LIMIT - smem_fixed) & ~1023) - stg_total;
         if (p.b_ring_bytes > TC_B_RING_BYTES) p.b_ring_bytes = TC_B_RING_BYTES;
         // only where the smaller ring still holds every weight stage at once (64 -> 64 3x3, the 1x1 convolutions): a streamed
         // filter (128 -> 64 3x3) measured slower with three ring stages than with four (40.0 vs 38.6 us at 4 x 180 x 320)
-        if (p.b_ring_bytes < (Cin / kch) * ksize * ksize * n_tile * TC_ROW_BYTES) { p.stage_out = 0; p.b_ring_bytes = TC_B_RING_BYTES; }
+        if (p.b_ring_bytes < (Cin / kch) * ksize * ksize * n_tile * TC_ROW_BYTES) {
+            p.stage_out = 0; p.b_ring_bytes = TC_B_RING_BYTES;
+            if (ksize == 1 && p.epi_sets == 2 && n_tile == 128) p.epi_sets = 4;
+        }
     }
     CUtensorMap map_y[TC_MAX_PROB];
     for (int i = 0; i < TC_MAX_PROB; ++i) {
@@ -651,7 +670,7 @@ static int conv_tc_launch(int np, const void* const* xs, const float* const* res
     static int num_sms = 0;
     static bool attr_set = false;
     const size_t smem_max = TC_SMEM_LIMIT;
-    const size_t smem = (size_t)smem_fixed + p.b_ring_bytes + (p.stage_out ? p.epi_sets * TC_STG_BYTES : 0);
+    const size_t smem = (size_t)smem_fixed + p.b_ring_bytes + (p.stage_out ? stg_total : 0);
     if (smem > smem_max) return FCVSR_ERR_UNSUPPORTED;
     if (!attr_set) {
         int dev = 0;

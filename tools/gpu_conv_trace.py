@@ -1,5 +1,5 @@
 """Bring-up helper: per-tile pipeline timeline of CTA 0 of conv_tc (v1) or conv_tc2 (v2), built separately with
--DTC_TRACE / -DT2_TRACE.   usage: python tools/gpu_conv_trace.py [v1|v2] [bf16|tf32] [Cin] [Cout] [B]"""
+-DTC_TRACE / -DT2_TRACE.   usage: [KS=1|3] [HW=180x320] python tools/gpu_conv_trace.py [v1|v2] [bf16|tf32] [Cin] [Cout] [B]"""
 import ctypes
 import os
 import subprocess
@@ -31,7 +31,8 @@ dev = torch.device("cuda:0")
 st = torch.cuda.current_stream().cuda_stream
 H, W = [int(v) for v in os.environ.get("HW", "180x320").split("x")]
 x = torch.randn(B, H, W, ci, device=dev)
-w = torch.randn(co, ci, 3, 3, device=dev) / (9 * ci) ** 0.5
+KS = int(os.environ.get("KS", "3"))
+w = torch.randn(co, ci, KS, KS, device=dev) / (KS * KS * ci) ** 0.5
 bias = torch.randn(co, device=dev)
 pk = _ConvPack(w, None, op16=op16)
 if op16:
@@ -43,7 +44,7 @@ V, I, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 if ver == "v1":
     fn = lib.fcvsr_conv2d_tc
     fn.argtypes = [V, I, V, V, V, I, V, I, V, I, I, I, I, I, I, I, I, F, V, I, V, I, I, I, I, V]
-    args = (x.data_ptr(), ci, pk.w_tc.data_ptr(), bias.data_ptr(), None, 0, None, 0, y.data_ptr(), co, B, H, W, ci, co, 3, 2, 0.1,
+    args = (x.data_ptr(), ci, pk.w_tc.data_ptr(), bias.data_ptr(), None, 0, None, 0, y.data_ptr(), co, B, H, W, ci, co, KS, 2, 0.1,
             None, 0, y2.data_ptr() if f32out else None, co if f32out else 0, 0 if f32out else (1 if op16 else 0), 0, int(op16), st)
 else:
     fn = lib.fcvsr_conv3x3_tc_resident
