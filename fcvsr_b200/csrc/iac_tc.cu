@@ -44,6 +44,7 @@ struct IacTcArgs {
     const unsigned short* w;               // this iteration's F1 slice: bf16 [192][64], row n = c4*12 + t*4 + cc  (c = 4 c4 + cc)
     const float* bias;                     // [192], same order
     int B, H, W, prev16;
+    int round_tf32;                        // TF variant: outputs are TF32-rounded fp32 (the conv3 operand of the last iteration)
 };
 
 __device__ __forceinline__ float4 it_bf16x4(uint2 u) {
@@ -117,7 +118,10 @@ __device__ __forceinline__ void it_gather(const void* pbase, int ldp, const int4
     }
 }
 
-template <bool P16>
+// TF: the fp32-contract mode -- kp2 and the F1 slice are TF32-rounded fp32 tensors (two 32-channel SWIZZLE_128B chunks each, eight
+// kind::tf32 MMAs), prev / next are fp32.  The 80 KB of operand tiles then cover both tile buffers, so the first gathers wait for
+// the accumulator instead of running under the MMAs.
+template <bool P16, bool TF>
 __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a) {
     extern __shared__ uint8_t it_smem_raw[];
     // (pointer + offset, not an integer round trip: the compiler must keep seeing the shared address space)
@@ -151,7 +155,23 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
     }
     // operand tiles, 16-byte chunks XOR-swizzled inside their 128-byte row (SWIZZLE_128B, K-major): the kp2 rows of the 128
     // haloed pixels (clamped == replicate padding of both passes) and the 192 weight rows of this iteration
-    {
+    if (TF) {
+        const uint32_t sA = smem_u32(sm), sW = smem_u32(sm + 2 * IT_OFF_W);
+        const float* kpf = reinterpret_cast<const float*>(a.kp);
+        const float* wf = reinterpret_cast<const float*>(a.w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {       // 128 pixels x 16 chunks of 4 floats; K chunk kc = channels [32 kc, 32 kc + 32)
+            const int q = tid + j * IT_THREADS, ppx = q >> 4, ch = q & 15, kc = ch >> 3, c8 = ch & 7;
+            const int yy = min(ty0 + (ppx >> 4), H - 1), xx = min(max(tx0 - 1 + (ppx & 15), 0), W - 1);
+            it_cp16(sA + kc * IT_OFF_W + ppx * 128 + ((c8 ^ (ppx & 7)) << 4), kpf + (img + (size_t)yy * W + xx) * a.ldkp + ch * 4);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {       // 192 rows x 16 chunks
+            const int q = tid + j * IT_THREADS, n = q >> 4, ch = q & 15, kc = ch >> 3, c8 = ch & 7;
+            it_cp16(sW + kc * (IT_N * 128) + n * 128 + ((c8 ^ (n & 7)) << 4), wf + n * 64 + ch * 4);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
         const uint32_t sA = smem_u32(sm), sW = smem_u32(sm + IT_OFF_W);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -231,10 +251,21 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
     __syncthreads();
     tc_fence_after();
     if (warp == 0 && elect_one()) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(IT_N >> 3) << 17) | ((128u >> 4) << 24);
-        const uint64_t a_d = make_desc(smem_u32(sm)), b_d = make_desc(smem_u32(sm + IT_OFF_W));
+        if (TF) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(IT_N >> 3) << 17) | ((128u >> 4) << 24);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_d + 2 * k, b_d + 2 * k, idesc, 1u);
+            for (int kc = 0; kc < 2; ++kc) {
+                const uint64_t a_d = make_desc(smem_u32(sm + kc * IT_OFF_W));
+                const uint64_t b_d = make_desc(smem_u32(sm + 2 * IT_OFF_W + kc * (IT_N * 128)));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, a_d + 2 * k, b_d + 2 * k, idesc, 1u);
+            }
+        } else {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(IT_N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t a_d = make_desc(smem_u32(sm)), b_d = make_desc(smem_u32(sm + IT_OFF_W));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_d + 2 * k, b_d + 2 * k, idesc, 1u);
+        }
         umma_commit(bar);
     }
     __syncwarp();
@@ -248,6 +279,10 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
     // every thread reaches after its phase 3 reads.
     float* bufS = buf1;
     float* bufO = buf0;
+    if (TF) {       // the operand tiles reach into the sample buffer: nothing may be gathered before the MMAs have read them
+        mbar_wait(bar, 0, nullptr, 0);
+        tc_fence_after();
+    }
 #pragma unroll 1
     for (int dir = 0; dir < 2; ++dir) {
         // phase 1: warped samples; a half-warp owns five halo pixels, a lane 4 channels
@@ -279,7 +314,7 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
                 if (o < IT_TH * IT_TW && yy < H && xx < W) xi[i] = __ldg(reinterpret_cast<const float4*>(xin + (img + (size_t)yy * W + xx) * ldx));
             }
         }
-        if (dir == 0) mbar_wait(bar, 0, nullptr, 0);
+        if (!TF && dir == 0) mbar_wait(bar, 0, nullptr, 0);
         tc_fence_after();
         // phase 2: both SAC passes with the taps read from TMEM once (fp32, never rounded).  Vertical pass: halo rows row,
         // row + 1, row + 2 of the thread's column from the sample tile (halo row hy = row + t <-> image row y + t - 1).
@@ -331,6 +366,14 @@ __global__ void __launch_bounds__(IT_THREADS, 2) iac_step_tc_kernel(IacTcArgs a)
                 if (o < IT_TH * IT_TW && yy < H && xx < W) {
                     const float4 r = *reinterpret_cast<const float4*>(bufO + (orow * IT_HX + ocol + 1) * IT_P + oc0);
                     const float p0 = r.x + xi[i].x, p1 = r.y + xi[i].y, p2 = r.z + xi[i].z, p3 = r.w + xi[i].w;
+                    if (TF) {
+                        float4 v = make_float4(p0 >= 0.f ? p0 : 0.1f * p0, p1 >= 0.f ? p1 : 0.1f * p1, p2 >= 0.f ? p2 : 0.1f * p2,
+                                               p3 >= 0.f ? p3 : 0.1f * p3);
+                        if (a.round_tf32) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+                        float* nf = reinterpret_cast<float*>(dir ? a.next[1] : a.next[0]) + oc0;
+                        *reinterpret_cast<float4*>(nf + (img + (size_t)yy * W + xx) * ldn) = v;
+                        continue;
+                    }
                     uint32_t lo, hi;
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(p1 >= 0.f ? p1 : 0.1f * p1), "f"(p0 >= 0.f ? p0 : 0.1f * p0));
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(p3 >= 0.f ? p3 : 0.1f * p3), "f"(p2 >= 0.f ? p2 : 0.1f * p2));
@@ -353,11 +396,13 @@ extern "C" int fcvsr_iac_step_tc(const void* prev_f, int ldprev_f, const void* p
                                  int ldkp, const void* w, const float* bias, int B, int H, int W, cudaStream_t st) {
     if (!prev_f || !prev_b || !xin_f || !xin_b || !next_f || !next_b || !offs || !kp || !w || !bias) return FCVSR_ERR_ARG;
     if (B <= 0 || H <= 0 || W <= 0) return FCVSR_ERR_ARG;
-    if (((ldprev_f | ldprev_b | ldxin_f | ldxin_b) & 3) || ((ldnext_f | ldnext_b | ldkp) & 7) || ((ldoffs | ch_f | ch_b) & 1))
+    const bool tf = (prev16 & 2) != 0;                 // fp32-contract mode: fp32 (TF32-rounded) kp / w, fp32 prev / next
+    if (tf && (prev16 & 1)) return FCVSR_ERR_ARG;
+    if (((ldprev_f | ldprev_b | ldxin_f | ldxin_b) & 3) || ((ldnext_f | ldnext_b | ldkp) & (tf ? 3 : 7)) || ((ldoffs | ch_f | ch_b) & 1))
         return FCVSR_ERR_ARG;
     if (((uintptr_t)xin_f | (uintptr_t)xin_b | (uintptr_t)next_f | (uintptr_t)next_b | (uintptr_t)kp | (uintptr_t)w) & 15)
         return FCVSR_ERR_ARG;
-    if (((uintptr_t)prev_f | (uintptr_t)prev_b) & (prev16 ? 7 : 15)) return FCVSR_ERR_ARG;
+    if (((uintptr_t)prev_f | (uintptr_t)prev_b) & ((prev16 & 1) ? 7 : 15)) return FCVSR_ERR_ARG;
     if (((uintptr_t)offs & 7) || ((uintptr_t)bias & 3)) return FCVSR_ERR_ARG;
     IacTcArgs a;
     a.prev[0] = prev_f; a.prev[1] = prev_b; a.ldprev[0] = ldprev_f; a.ldprev[1] = ldprev_b;
@@ -366,16 +411,18 @@ extern "C" int fcvsr_iac_step_tc(const void* prev_f, int ldprev_f, const void* p
     a.offs = offs; a.ldoffs = ldoffs; a.offs_ch[0] = ch_f; a.offs_ch[1] = ch_b;
     a.kp = reinterpret_cast<const unsigned short*>(kp); a.ldkp = ldkp;
     a.w = reinterpret_cast<const unsigned short*>(w); a.bias = bias;
-    a.B = B; a.H = H; a.W = W; a.prev16 = prev16 ? 1 : 0;
+    a.B = B; a.H = H; a.W = W; a.prev16 = prev16 & 1; a.round_tf32 = (prev16 & 4) ? 1 : 0;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(iac_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IT_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(iac_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IT_SMEM) != cudaSuccess)
+        if (cudaFuncSetAttribute(iac_step_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IT_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(iac_step_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IT_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(iac_step_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IT_SMEM) != cudaSuccess)
             return FCVSR_ERR_CUDA;
         attr_set = true;
     }
     dim3 grid(((H + IT_TH - 1) / IT_TH) * ((W + IT_TW - 1) / IT_TW), B, 1);
-    if (prev16) iac_step_tc_kernel<true><<<grid, IT_THREADS, IT_SMEM, st>>>(a);
-    else iac_step_tc_kernel<false><<<grid, IT_THREADS, IT_SMEM, st>>>(a);
+    if (tf) iac_step_tc_kernel<false, true><<<grid, IT_THREADS, IT_SMEM, st>>>(a);
+    else if (prev16 & 1) iac_step_tc_kernel<true, false><<<grid, IT_THREADS, IT_SMEM, st>>>(a);
+    else iac_step_tc_kernel<false, false><<<grid, IT_THREADS, IT_SMEM, st>>>(a);
     return fcvsr_launch_status();
 }

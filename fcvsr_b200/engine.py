@@ -112,7 +112,8 @@ class Engine:
         # that the tools under tools/ can flip them -- nothing in the product path reads the environment
         self.tc_pyramid = True       # rconcat1/2 as stride-1 tcgen05 convs + sampling
         self.iac16 = True            # IAC ping-pong tensors in bf16
-        self.iac_tc = True           # bf16 mode: IAC taps computed on chip (fcvsr_iac_step_tc), no Pred_K tensor
+        self.iac_tc = True           # IAC taps computed on chip (fcvsr_iac_step_tc), no Pred_K tensor
+        self.iac_tc_tf32 = True      # ... also in the fp32-contract mode (TF32 operands, fp32 ping-pong)
         self.res16 = True            # RCB body output as a bf16 tensor
         self.r016 = True             # RCB input / skip r0 only as a bf16 tensor
         self.rr16 = True             # RCB output rr only as a bf16 tensor
@@ -188,11 +189,13 @@ class Engine:
         ii, tt, cc = torch.meshgrid(torch.arange(A), torch.arange(3), torch.arange(n), indexing="ij")
         rows = (ii * 6 * n + cc * 3 + tt).reshape(-1).to(device)
         P["F1"] = _ConvPack(sd["MGAA.F.1.weight"][rows], sd["MGAA.F.1.bias"][rows], op16=op16)
-        if op16:
+        if self.use_tc:
             # the same live rows per iteration as the B operand of fcvsr_iac_step_tc: row c4*12 + t*4 + cc, channel c = 4 c4 + cc
+            # (bf16, or TF32-rounded fp32 in the fp32-contract mode)
             ii, gg, tt, cc = torch.meshgrid(torch.arange(A), torch.arange(n // 4), torch.arange(3), torch.arange(4), indexing="ij")
             rows_tc = (ii * 6 * n + (gg * 4 + cc) * 3 + tt).reshape(-1).to(device)
-            P["F1tc_w"] = sd["MGAA.F.1.weight"][rows_tc].reshape(A, 3 * n, n).to(torch.bfloat16).contiguous()
+            w_tc = sd["MGAA.F.1.weight"][rows_tc].reshape(A, 3 * n, n).float().contiguous()
+            P["F1tc_w"] = w_tc.to(torch.bfloat16).contiguous() if op16 else _round_tf32(w_tc)
             P["F1tc_b"] = sd["MGAA.F.1.bias"][rows_tc].float().reshape(A, 3 * n).contiguous()
         P["conv3"] = cp("MGAA.conv3")
         # --- MFFR (:2104-2133) ---
@@ -255,8 +258,11 @@ class Engine:
     # workspace
     # -------------------------------------------------------------------------------------------
     def _iac_on_chip(self) -> bool:
-        """bf16 mode with bf16 ping-pong tensors: fcvsr_iac_step_tc computes the taps from kp2 in its own prologue."""
-        return bool(self.op16 and self.iac16 and self.iac_tc and self.model.n_feats == 64)
+        """fcvsr_iac_step_tc computes the taps from kp2 in its own prologue: bf16 mode with bf16 ping-pong tensors, or the
+        fp32-contract mode with TF32 operands and fp32 ping-pong tensors."""
+        if not (self.use_tc and self.iac_tc and self.model.n_feats == 64):
+            return False
+        return bool(self.iac16) if self.op16 else bool(self.iac_tc_tf32)
 
     def _workspace(self, B, H, W, device):
         key = (B, H, W, str(device), self._iac_on_chip())
@@ -679,8 +685,9 @@ class Engine:
             if on_chip:
                 # taps = F.1 slice i of kp2 on tcgen05 inside the IAC kernel (Pred_K never materialised)
                 self.tc_launches += 1
-                self._k("fcvsr_iac_step_tc", prev_f, ldpf, prev_b, ldpb, int(i > 0), src, lds, src + 128 * 4, lds, nf, ldn, nb, ldn,
-                        p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["kp2"], 64, P["F1tc_w"].data_ptr() + i * 192 * 64 * 2,
+                pm = int(i > 0) if O16 else (2 + (4 if i == A - 1 else 0))      # TF32 operands; the last iteration is conv3's operand
+                self._k("fcvsr_iac_step_tc", prev_f, ldpf, prev_b, ldpb, pm, src, lds, src + 128 * 4, lds, nf, ldn, nb, ldn,
+                        p["offs"], 4 * A, (i * 2) * 2, (i * 2 + 1) * 2, p["kp2"], 64, P["F1tc_w"].data_ptr() + i * 192 * 64 * E,
                         P["F1tc_b"].data_ptr() + i * 192 * 4, B, H, W)
                 prev_f, ldpf, prev_b, ldpb = nf, ldn, nb, ldn
                 continue

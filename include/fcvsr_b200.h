@@ -122,7 +122,9 @@ int fcvsr_iac_step(const float* prev_f, int ldprev_f, const float* prev_b, int l
  * predictor's last 1x1 convolution (MGAA.F.1, :1522-1523; only rows i*384 + c*3 + t are live, :1231-1235) is one
  * 128 x 192 x 64 tcgen05 GEMM per 8 x 14 tile, its TMEM accumulator is the tap set, and `Pred_K` never reaches memory.
  * kp [B,H,W,ldkp] bf16: the F.0 output (64 ch).  w: bf16 [192][64], row c4*12 + t*4 + cc = F.1 row i*384 + (4 c4 + cc)*3 + t;
- * bias [192] fp32 in the same order.  prev_* fp32 (prev16 = 0) or bf16 (prev16 = 1), ld in elements; next_* bf16. */
+ * bias [192] fp32 in the same order.  prev_* fp32 (prev16 = 0) or bf16 (prev16 = 1), ld in elements; next_* bf16.
+ * prev16 = 2 (+ 4): the fp32-contract mode -- kp and w are TF32-rounded fp32 tensors (kind::tf32 MMAs), prev_* and next_* fp32;
+ * with + 4 the outputs are TF32-rounded (the last iteration feeds conv3). */
 int fcvsr_iac_step_tc(const void* prev_f, int ldprev_f, const void* prev_b, int ldprev_b, int prev16,
                       const float* xin_f, int ldxin_f, const float* xin_b, int ldxin_b, void* next_f, int ldnext_f,
                       void* next_b, int ldnext_b, const float* offs, int ldoffs, int ch_f, int ch_b, const void* kp,

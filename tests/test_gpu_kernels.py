@@ -14,7 +14,7 @@ import torch
 import torch.nn.functional as F
 
 from fcvsr_b200 import _capi as C, arch
-from fcvsr_b200.engine import Engine
+from fcvsr_b200.engine import Engine, _round_tf32 as _tf32r
 from oracle import fcvsr_oracle as O
 from tests.util import make_clip, nchw, nhwc, psnr
 
@@ -182,6 +182,43 @@ def test_iac_step_tc_kernel(dev, B, H, W, prev16):
         scale = max(1.0, float(want[d].abs().max()))
         # bf16 output rounding; the taps stay fp32 (TMEM accumulator) on the device
         assert float((got - want[d]).abs().max()) <= (2.0 ** -8 + 2e-4) * scale, d
+
+
+@pytest.mark.parametrize("B,H,W,rnd", [(1, 19, 37, 0), (2, 8, 14, 4), (2, 33, 45, 0), (1, 7, 13, 4)])
+def test_iac_step_tc_kernel_tf32(dev, B, H, W, rnd):
+    """fcvsr_iac_step_tc in the fp32-contract mode (prev16 = 2 [+ 4]): TF32-rounded fp32 kp2 / F.1 slice on kind::tf32 MMAs, fp32
+    prev / next, against the oracle with taps from an fp32 matmul of the same rounded operands."""
+    g = torch.Generator().manual_seed(H * W + 5)
+    prev = [torch.randn(B, 64, H, W, generator=g) for _ in range(2)]
+    xin = [torch.randn(B, 64, H, W, generator=g) for _ in range(2)]
+    off = [3.0 * torch.randn(B, 2, H, W, generator=g) for _ in range(2)]
+    off[0][:, :, 0, 0] = torch.tensor([-55.0, 12.0])
+    kp = _tf32r(torch.randn(B, 64, H, W, generator=g))
+    wt = _tf32r(0.1 * torch.randn(64, 3, 64, generator=g))               # [c][t][k]: reference row c*3 + t
+    bias = 0.2 * torch.randn(64, 3, generator=g)
+    taps = torch.einsum("ctk,bkhw->bcthw", wt, kp) + bias[None, :, :, None, None]
+    want = [F.leaky_relu(O.sac(O.warp_bilinear(prev[d], off[d]), taps.reshape(B, 192, H, W)) + xin[d], 0.1) for d in range(2)]
+    prev_d = [nhwc(p).to(dev) for p in prev]
+    xin_d = [nhwc(t).to(dev) for t in xin]
+    offs_d = torch.zeros(B, H, W, 8, device=dev)
+    offs_d[..., 2:4] = nhwc(off[0]).to(dev)
+    offs_d[..., 6:8] = nhwc(off[1]).to(dev)
+    kp_d = nhwc(kp).to(dev)
+    w_d = wt.view(16, 4, 3, 64).permute(0, 2, 1, 3).reshape(192, 64).contiguous().to(dev)
+    b_d = bias.view(16, 4, 3).permute(0, 2, 1).reshape(192).contiguous().to(dev)
+    nxt = torch.zeros(B, H, W, 128, device=dev)                         # both directions side by side (ld 128), as cat128
+    C.call("fcvsr_iac_step_tc", prev_d[0].data_ptr(), 64, prev_d[1].data_ptr(), 64, 2 + rnd, xin_d[0].data_ptr(), 64,
+           xin_d[1].data_ptr(), 64, nxt.data_ptr(), 128, nxt.data_ptr() + 64 * 4, 128, offs_d.data_ptr(), 8, 2, 6, kp_d.data_ptr(), 64,
+           w_d.data_ptr(), b_d.data_ptr(), B, H, W, _st())
+    torch.cuda.synchronize()
+    for d in range(2):
+        got = nchw(nxt[..., 64 * d:64 * d + 64].cpu())
+        scale = max(1.0, float(want[d].abs().max()))
+        assert float((got - want[d]).abs().max()) <= ((2.0 ** -11 if rnd else 0.0) + 1e-4) * scale, d
+    # a bf16 prev together with TF32 operands is refused
+    assert C.try_call("fcvsr_iac_step_tc", prev_d[0].data_ptr(), 64, prev_d[1].data_ptr(), 64, 3, xin_d[0].data_ptr(), 64,
+                      xin_d[1].data_ptr(), 64, nxt.data_ptr(), 128, nxt.data_ptr() + 256, 128, offs_d.data_ptr(), 8, 2, 6,
+                      kp_d.data_ptr(), 64, w_d.data_ptr(), b_d.data_ptr(), B, H, W, _st()) == C.ERR_ARG
 
 
 # ------------------------------------------------------------------------------------------------------------------------
