@@ -12,8 +12,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip $((3*L))
 python tools/summarize_launches.py gpurun_out/r2f_launches_step_b6.csv > gpurun_out/r2f_launches_summary_b6.txt 2>&1
 head -34 gpurun_out/r2f_launches_summary_b6.txt
 # SCNet phase: level-batched convolutions (TMA-store epilogue), one-launch ContextBlock, RCB tail, merged down/up, cross-level mix
-ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel|level_mix_kernel|rcb_finish_kernel|ctx_block_kernel" --launch-skip 1000 --launch-count 12 -o gpurun_out/r2f_scnet_full -f $BENCH > gpurun_out/r2f_ncu_scnet.log 2>&1
-python tools/ncu_summary.py gpurun_out/r2f_scnet_full.ncu-rep "ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel|level_mix_kernel|rcb_finish_kernel|ctx_block_kernel --launch-count 12, of: $BENCH (bf16, FCVSR 180x320, 6 windows; SCNetbk phase)" > gpurun_out/r2f_conv_tc_full_summary.txt 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel|level_mix|rcb_finish_kernel|ctx_block_kernel" --launch-skip 1000 --launch-count 12 -o gpurun_out/r2f_scnet_full -f $BENCH > gpurun_out/r2f_ncu_scnet.log 2>&1
+python tools/ncu_summary.py gpurun_out/r2f_scnet_full.ncu-rep "ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel|level_mix|rcb_finish_kernel|ctx_block_kernel --launch-count 12, of: $BENCH (bf16, FCVSR 180x320, 6 windows; SCNetbk phase)" > gpurun_out/r2f_conv_tc_full_summary.txt 2>&1
 # MGAA: IAC step with on-chip taps, FFT passes, offset blocks, CorrBlock lookup; tail: conv_last0
 ncu --set full --clock-control none --import-source on -k regex:"iac_step_tc_kernel|fft2_|offset_blk|corr_gather|conv3x3_c64_to1" --launch-skip 140 --launch-count 16 -o gpurun_out/r2f_mgaa_full -f $BENCH > gpurun_out/r2f_ncu_mgaa.log 2>&1
 python tools/ncu_summary.py gpurun_out/r2f_mgaa_full.ncu-rep "ncu --set full: MGAA kernels (IAC step with on-chip taps, FFT passes, offset blocks, CorrBlock lookup), same command" > gpurun_out/r2f_mgaa_full_summary.txt 2>&1
