@@ -637,6 +637,34 @@ def test_conv_tcgen05_bf16_operands(dev, case):
         assert float((nchw(y2.float().cpu()) - ref2).abs().max()) <= 1e-2 * max(1.0, float(ref2.abs().max()))
 
 
+@pytest.mark.parametrize("case", [(2, 128, 128, 13, 33, 1, 216, 1), (1, 128, 128, 20, 16, 1, 128, 2), (2, 64, 64, 11, 21, 1, 64, 0),
+                                  (1, 64, 64, 17, 35, 3, 96, 2), (1, 256, 128, 9, 18, 1, 128, 1), (1, 64, 128, 12, 20, 3, 128, 2)])
+def test_conv_tcgen05_bf16_output_tensor(dev, case):
+    """bf16 operands AND a bf16 output tensor (round_out = 1): 64- and 128-channel outputs of resident-weight convolutions leave
+    through the staged epilogue (SWIZZLE_128B tile in shared memory, one or two TMA stores per tile, clipped at the image border);
+    the 64 -> 128 3x3 case streams its filter and keeps the direct stores.  Output rows wider than Cout (ldy), every activation,
+    the res - res2 skip of MGAA.convfuse (CVSR_freq.py:1472-1473)."""
+    B, ci, co, H, W, k, ldy, act = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+    b = torch.randn(co, generator=g)
+    res, res2 = torch.randn(B, co, H, W, generator=g), torch.randn(B, co, H, W, generator=g)
+    pk = _ConvPack(w.to(dev), b.to(dev), op16=True)
+    xd = nhwc(x).to(dev).to(torch.bfloat16)
+    rd, r2d = nhwc(res).to(dev), nhwc(res2).to(dev)
+    y = torch.full((B, H, W, ldy), 7.0, device=dev, dtype=torch.bfloat16)
+    C.call("fcvsr_conv2d_tc", xd.data_ptr(), ci, pk.w_tc.data_ptr(), pk.bias.data_ptr(), rd.data_ptr(), co, r2d.data_ptr(), co,
+           y.data_ptr(), ldy, B, H, W, ci, co, k, act, 0.2, 0, 0, 0, 0, 1, 0, 1, _st())
+    torch.cuda.synchronize()
+    xr, wr = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
+    pre = F.conv2d(xr, wr, b, padding=k // 2)
+    ref = {0: pre, 1: F.relu(pre), 2: F.leaky_relu(pre, 0.2)}[act] + res - res2
+    got = y.float().cpu()
+    assert float((nchw(got[..., :co]) - ref).abs().max()) <= (2.0 ** -8 + 2e-4) * max(1.0, float(ref.abs().max()))
+    assert bool((got[..., co:] == 7.0).all())            # channels beyond Cout of a wider row are not touched
+
+
 @pytest.mark.parametrize("name", ["fcvsr_s_64", "fcvsr_s_36x40", "fcvsr_full_64"])
 def test_bf16_path_matches_reference_golden(dev, name):
     g = load_golden(name)
