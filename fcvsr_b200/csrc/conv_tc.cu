@@ -19,7 +19,10 @@
 //   * Accumulators: FOUR N-column tiles in TMEM; the epilogue warps form 1, 2 or 4 sets that drain different accumulator tiles
 //     concurrently (tcgen05.ld, lane == pixel), apply bias (staged in shared memory) / activation / residuals in registers and
 //     store 256-bit runs per thread (optionally through pixel_shuffle(2), optionally a second operand-typed output); bf16
-//     64-channel outputs are staged in a SWIZZLE_128B shared tile per set and leave with ONE TMA store per tile.
+//     64- and 128-channel outputs of resident-filter convolutions are staged in SWIZZLE_128B shared tiles per set (one per 64
+//     channels) and leave with one TMA store per 64 channels and tile.  The activation is one uniform switch per 16-column
+//     chunk: the epilogue warps share issue slots and the shared-memory pipe with the TMA / MMA path, so its instruction count
+//     shows in the tile period.
 //   * Up to four problems (tensors of different spatial size: the pyramid levels of SCNetbk) share one persistent tile list;
 //     programmatic dependent launch overlaps the prologue with the previous convolution's drain.
 //

@@ -17,6 +17,8 @@
 // gathers (the MMA runs under the first ones) -> both filter passes in one phase (vertical pass from the sample tile, the
 // neighbouring columns of the horizontal pass by warp shuffle: a warp holds two tile rows of 16 columns) -> coalesced output
 // stage.  Both directions share the taps (:1526-1527 call IAC with the same Pred_K), so one CTA serves both and kp2 is read once.
+// The fp32-contract mode runs the same kernel with TF32 operands (template parameter TF: fp32 kp2 / F1 tiles, kind::tf32 MMAs,
+// fp32 prev / next tensors).
 #include "tc_common.cuh"
 
 #define IT_TH 8

@@ -9,6 +9,8 @@
 //                                x += coef*r + avgpool2(td) + bilinear_x2(tu)
 //                                (Interpolate(0.5) of an even-sized map == 2x2 mean; Interpolate(2.0) is
 //                                bilinear, align_corners=False; td/tu are the 1x1 down/up conv outputs)
+//   level_mix8                   the same sum for the bf16 mode's BlockRCB launch (every side tensor bf16, x carried as the
+//                                bf16 operand copy, eight channels per thread)
 #include "common.cuh"
 
 // 4 consecutive channels at element index idx of an fp32 tensor, or of a bf16 tensor (b16) with the same element indexing
