@@ -328,6 +328,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const int y = tc.ty * TC_TH + ly, x = tc.tx * TC_TW + lx;
             const bool valid = y < pq.H && x < pq.W;
             const size_t pix = ((size_t)tc.b * pq.H + y) * pq.W + x;
+            // per-tile copies of the problem's fields: p.prob[tc.pr] is an indexed constant-bank access (LDC with a register
+            // index), which the chunk loop below would otherwise repeat four times per 16 columns
+            const float* const res_p = valid ? pq.res : nullptr;
+            const float* const res2_p = valid ? pq.res2 : nullptr;
+            const int wrow = pq.wrow;
 
             mbar_wait_warp(&tm_full[acc], pacc, p.err, 6);
             tc_fence_after();
@@ -341,7 +346,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             // Software-pipelined TMEM reads: the tcgen05.ld of chunk c+1 is in flight while chunk c is
             // post-processed and stored (tcgen05.wait::ld sits right before the data is needed).
             auto process = [&](const uint32_t* r, const int cb) {
+#ifdef FCVSR_BRINGUP
                 if (p.dbg & 8) return;
+#endif
                 if (valid && p.cout_valid < p.Cout) {
                     // thin head (Cout in {1,4}): scalar stores of the first cout_valid columns
                     const int n0 = tc.nt * p.n_tile + cb;
@@ -359,7 +366,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 } else if (valid || stg) {
                     const int n0 = tc.nt * p.n_tile + cb;
                     float v[16];
-                    lds_bias16(bias_sa + (pq.wrow + n0) * 4, v);
+                    lds_bias16(bias_sa + (wrow + n0) * 4, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r[j]);
                     // one uniform switch per chunk (per element it was 7 of the chunk's ~11 instructions per value)
@@ -370,21 +377,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
                     }
-                    if (pq.res && valid) {
+                    if (res_p) {
                         float rv[16];
                         if (p.wide) {
-                            ld_global_v8(pq.res + pix * p.ldres + n0, rv);
-                            ld_global_v8(pq.res + pix * p.ldres + n0 + 8, rv + 8);
+                            ld_global_v8(res_p + pix * p.ldres + n0, rv);
+                            ld_global_v8(res_p + pix * p.ldres + n0 + 8, rv + 8);
                         } else {
-                            const float4* rp = reinterpret_cast<const float4*>(pq.res + pix * p.ldres + n0);
+                            const float4* rp = reinterpret_cast<const float4*>(res_p + pix * p.ldres + n0);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) { const float4 t4 = rp[j]; rv[4 * j] = t4.x; rv[4 * j + 1] = t4.y; rv[4 * j + 2] = t4.z; rv[4 * j + 3] = t4.w; }
                         }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] += rv[j];
                     }
-                    if (pq.res2 && valid) {
-                        const float4* rp = reinterpret_cast<const float4*>(pq.res2 + pix * p.ldres2 + n0);
+                    if (res2_p) {
+                        const float4* rp = reinterpret_cast<const float4*>(res2_p + pix * p.ldres2 + n0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 rv = rp[j];
